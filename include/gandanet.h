@@ -1,0 +1,209 @@
+/*
+ * gandanet.h -- C ABI of libgandanet_sm100.so
+ *
+ * B200 (sm_100a) kernels for the GAN-DANet generator/discriminator training
+ * step.  The reference (/root/reference, Aster32/GAN-DANet) has no FFI: its hot
+ * path is PyTorch ATen calls made from models/generator.py, models/discriminator.py,
+ * models/losses.py and the step glue in GAN_DANet_train.ipynb.  Every entry point
+ * below names the reference call site it replaces (file:line into /root/reference).
+ *
+ * Conventions
+ *   - plain C: raw device pointers, ints, floats.  No C++/torch types.
+ *   - activations are float32 NHWC; a tensor argument is (ptr, pitch, c0): the
+ *     channel slice [c0, c0+C) of a buffer whose innermost dimension is `pitch`.
+ *   - the caller owns every buffer including workspaces; the library never
+ *     allocates device memory.
+ *   - every call enqueues on the given stream and returns without synchronising.
+ *   - return value: GDN_OK (0) or a negative gdn_status; gdn_last_error() gives
+ *     a thread-local message.  Never throws, never exits.
+ */
+#ifndef GANDANET_H_
+#define GANDANET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gdn_stream_t; /* cudaStream_t */
+
+typedef enum {
+  GDN_OK = 0,
+  GDN_EINVAL = -1, /* bad shape / alignment / null pointer           */
+  GDN_EARCH = -2,  /* device is not sm_100                            */
+  GDN_ECUDA = -3,  /* CUDA runtime error, see gdn_last_error()        */
+  GDN_EWORKSPACE = -4 /* workspace too small                          */
+} gdn_status;
+
+enum { GDN_ACT_NONE = 0, GDN_ACT_RELU = 1, GDN_ACT_LRELU = 2 };
+enum { GDN_PREC_FP32 = 0, GDN_PREC_BF16 = 1, GDN_PREC_FP16 = 2 };
+
+int gdn_version(void);
+const char* gdn_last_error(void);
+/* Checks the device is sm_100 and opts kernels into large dynamic shared memory. */
+int gdn_init(int device);
+
+/* ------------------------------------------------------------------ layout */
+/* NCHW <-> NHWC slice (module boundary; replaces nothing in the reference, which is NCHW throughout). */
+int gdn_nchw_to_nhwc(const float* src, float* dst, int dst_pitch, int dst_c0, int B, int C, int H, int W, gdn_stream_t s);
+int gdn_nhwc_to_nchw(const float* src, int src_pitch, int src_c0, float* dst, int B, int C, int H, int W, gdn_stream_t s);
+/* Conv weight OIHW -> [O][kh][kw][I] (forward operand) and -> [I][kh][kw][O] (dgrad operand). */
+int gdn_weight_oihw_to_ohwi(const float* w, float* out, int O, int I, int kh, int kw, gdn_stream_t s);
+int gdn_weight_oihw_to_ihwo(const float* w, float* out, int O, int I, int kh, int kw, gdn_stream_t s);
+
+/* ------------------------------------------------------------- convolution */
+/*
+ * Implicit-GEMM convolution / linear layer, fp32 CUDA-core ("parity") engine.
+ * Replaces nn.Conv2d at generator.py:20,34,63,108-110,148,188,214,218,222,228,
+ * discriminator.py:62-67, the VGG19 convs of losses.py:58, and torch.bmm in CAM
+ * (generator.py:138) via per-group weights.
+ *
+ *   y[b,ho,wo,n] = act(alpha * sum_{kh,kw,c} xin(b,ho,wo,kh,kw,c) * w[g][n][kh][kw][w_c0+c] + bias[n]) + res[b,ho,wo,n]
+ *
+ * transposed == 0: xin = x[b, ho*stride-pad+kh, wo*stride-pad+kw, c]            (forward)
+ * transposed == 1: xin = x[b, (ho+pad-kh)/stride, (wo+pad-kw)/stride, c] when divisible (data gradient;
+ *                  then (Hi,Wi) is the conv-output grid and (Ho,Wo) the conv-input grid)
+ * groups > 1: weights differ per group of B/groups consecutive samples (w_group_stride floats apart).
+ * alpha_ptr (device scalar, may be NULL => 1.0f).  res may alias y.
+ * splits > 1: split-K through `ws` (splits*M*Cout floats).
+ */
+typedef struct {
+  const float* x; int x_pitch, x_c0;
+  const float* w; int w_k_pitch, w_c0; long long w_group_stride; int groups;
+  float* y; int y_pitch, y_c0;
+  const float* bias;
+  const float* alpha_ptr;
+  const float* res; int res_pitch, res_c0;
+  int B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad, transposed;
+  int act; float slope;
+  int splits; float* ws; size_t ws_bytes;
+} gdn_conv_args;
+int gdn_conv2d(const gdn_conv_args* a, gdn_stream_t s);
+
+/*
+ * Reduction-over-pixels GEMM: weight gradient of the convolution above and the CAM Gram matrix
+ * (generator.py:132).
+ *   out[g][i][j] = scale * sum_{pixels m of group g} dy[m, dy_c0+i] * xin(m, j)      j = (kh,kw,c)
+ * layout == 0: out is [groups][Cout][kh*kw*Cin] row-major (Gram / generic)
+ * layout == 1: out is an OIHW weight gradient [Cout][out_cin_total][kh][kw], channels [out_c0, out_c0+Cin)
+ * accumulate != 0 adds into out.  ws: splits*groups*Cout*K floats.
+ */
+typedef struct {
+  const float* dy; int dy_pitch, dy_c0;
+  const float* x; int x_pitch, x_c0;
+  float* out; int layout, out_cin_total, out_c0, accumulate;
+  const float* scale_ptr; float scale;
+  int B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad, groups;
+  int splits; float* ws; size_t ws_bytes;
+} gdn_wgrad_args;
+int gdn_conv2d_wgrad(const gdn_wgrad_args* a, gdn_stream_t s);
+/* suggested split counts (pure host functions) */
+int gdn_conv2d_suggest_splits(const gdn_conv_args* a);
+int gdn_wgrad_suggest_splits(const gdn_wgrad_args* a);
+
+/* ------------------------------------------------------------ elementwise */
+/* per-channel sums over M rows of an NHWC slice: out[0..C) = sum x, out[C..2C) = sum x*x (double).  BN statistics
+ * (generator.py:32,61,149,189,219,223) and bias gradients.  ws: gdn_colstats_ws_bytes(M, C). */
+size_t gdn_colstats_ws_bytes(long long M, int C);
+int gdn_colstats(const float* x, int pitch, int c0, long long M, int C, double* out, void* ws, gdn_stream_t s);
+/* BatchNorm2d train-mode finalize: sums -> mean/biased var -> scale = w*rsqrt(var+eps), shift = b - mean*scale;
+ * saves mean and invstd; updates running stats (momentum, unbiased var). */
+int gdn_bn_finalize(const double* sums, long long M, int C, const float* weight, const float* bias, float eps, float momentum,
+                    float* running_mean, float* running_var, float* mean, float* invstd, float* scale, float* shift, gdn_stream_t s);
+/* eval-mode: scale/shift from running statistics */
+int gdn_bn_eval_coeffs(const float* weight, const float* bias, const float* running_mean, const float* running_var, float eps,
+                       int C, float* scale, float* shift, gdn_stream_t s);
+/* y = act(x*scale[c] + shift[c]) on NHWC slices */
+int gdn_affine_act(const float* x, int x_pitch, int x_c0, float* y, int y_pitch, int y_c0, long long M, int C,
+                   const float* scale, const float* shift, int act, float slope, gdn_stream_t s);
+/* BN(+act) backward, stage 1: g = dy * act'(x*scale+shift); sums[0..C) = sum g, sums[C..2C) = sum g*xhat (double) */
+int gdn_bn_bwd_reduce(const float* dy, int dy_pitch, int dy_c0, const float* x, int x_pitch, int x_c0, long long M, int C,
+                      const float* mean, const float* invstd, const float* scale, const float* shift, int act, float slope,
+                      double* sums, void* ws, gdn_stream_t s);
+/* stage 2: dx (+)= w*invstd*(g - sum_g/M - xhat*sum_gx/M); dweight = sum_gx; dbias = sum_g */
+int gdn_bn_bwd_apply(const float* dy, int dy_pitch, int dy_c0, const float* x, int x_pitch, int x_c0,
+                     float* dx, int dx_pitch, int dx_c0, int accumulate, long long M, int C,
+                     const float* mean, const float* invstd, const float* weight, const float* scale, const float* shift,
+                     int act, float slope, const double* sums, float* dweight, float* dbias, gdn_stream_t s);
+/* dz = dy * act'(y) given the activation OUTPUT y (ReLU / LeakyReLU) */
+int gdn_act_bwd(const float* dy, int dy_pitch, int dy_c0, const float* y, int y_pitch, int y_c0,
+                float* dz, int dz_pitch, int dz_c0, long long M, int C, int act, float slope, gdn_stream_t s);
+/* y (+)= alpha * x on NHWC slices */
+int gdn_axpy(const float* x, int x_pitch, int x_c0, float* y, int y_pitch, int y_c0, long long M, int C, float alpha, int accumulate, gdn_stream_t s);
+/* double sums -> float vector */
+int gdn_sums_to_float(const double* sums, float* out, int n, float scale, gdn_stream_t s);
+
+/* ------------------------------------------------------------- resampling */
+/* nn.Upsample(scale_factor=2, mode='bicubic', align_corners=False), generator.py:221,225 (A=-0.75, clamped taps) */
+int gdn_bicubic_up2_fwd(const float* x, float* y, int B, int H, int W, int C, gdn_stream_t s);
+int gdn_bicubic_up2_bwd(const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s);
+/* F.interpolate(size=(Ho,Wo), mode='bilinear', align_corners=False), generator.py:244: y (+)= resize(x) */
+int gdn_bilinear_fwd(const float* x, float* y, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s);
+int gdn_bilinear_bwd(const float* dy, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s);
+/* F.interpolate(scale_factor=1/f, mode='bicubic') for f = 2 or 4 (GAN_DANet_train.ipynb:226,231): NCHW in -> NHWC slice out */
+int gdn_bicubic_down_nchw_to_nhwc(const float* x, float* y, int y_pitch, int y_c0, int B, int C, int Hi, int Wi, int f, gdn_stream_t s);
+/* 2x2/2 max pool (VGG19 features idx 4,9,18; losses.py:58) */
+int gdn_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, gdn_stream_t s);
+int gdn_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s);
+
+/* ---------------------------------------------------------------- attention */
+/*
+ * Position attention core (generator.py:115-122), flash-style: the NxN map never reaches HBM.
+ *   S = q k^T (no scaling), P = softmax_row(S), O = P v, y = gamma*O + x, lse = logsumexp_row(S)
+ * q,k: [B,N,d] (pitch qk_pitch); v,x,o,y: [B,N,C].  precision: GDN_PREC_FP32 = CUDA-core parity kernel.
+ */
+typedef struct {
+  const float* q; const float* k; int qk_pitch; int d;
+  const float* v; int v_pitch;
+  const float* x; int x_pitch; const float* gamma;
+  float* o; float* y; int y_pitch; float* lse;
+  int B, N, C; int precision;
+} gdn_pam_fwd_args;
+int gdn_pam_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s);
+/*
+ * Backward of the core: given dy computes dq, dk, dv and rowdot[b,n] = sum_c dy*o (dgamma = sum rowdot; delta = gamma*rowdot).
+ * dx of the residual is dy itself and is left to the caller.
+ */
+typedef struct {
+  const float* q; const float* k; int qk_pitch; int d;
+  const float* v; int v_pitch;
+  const float* o; const float* lse; const float* gamma;
+  const float* dy; int dy_pitch;
+  float* dq; float* dk; float* dv; float* rowdot;
+  int B, N, C; int precision;
+} gdn_pam_bwd_args;
+int gdn_pam_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s);
+/* CAM softmax (generator.py:135-136): attn = softmax_row(rowmax(E) - E) for [rows][C] */
+int gdn_cam_softmax(const float* e, float* attn, int rows, int C, gdn_stream_t s);
+/* CAM backward glue: dE = -A * (dA - rowsum(A*dA)); g = dE + dE^T  per [C][C] matrix */
+int gdn_cam_de(const float* attn, const float* da, float* g, int B, int C, gdn_stream_t s);
+/* out[0] (+)= sum over M*C of a*b  (deterministic two-stage; dgamma of PAM/CAM) */
+size_t gdn_dot_ws_bytes(long long n);
+int gdn_dot(const float* a, int a_pitch, int a_c0, const float* b, int b_pitch, int b_c0, long long M, int C, float* out, void* ws, gdn_stream_t s);
+
+/* -------------------------------------------------------------------- losses */
+/* All loss kernels are deterministic two-stage reductions; ws via gdn_dot_ws_bytes(numel). */
+/* MSELoss (GAN_DANet_train.ipynb:262): loss[0] = mean((a-b)^2); if grad != NULL: grad (+)= gscale * 2(a-b)/n */
+int gdn_mse(const float* a, const float* b, long long n, float* loss, float* grad, float gscale, int accumulate, void* ws, gdn_stream_t s);
+/* F.l1_loss mean (losses.py:72): loss[0] (+)= mean|a-b|; grad_a (+)= gscale*sign(a-b)/n */
+int gdn_l1(const float* a, const float* b, long long n, float* loss, int loss_accumulate, float* grad, float gscale, int accumulate, void* ws, gdn_stream_t s);
+/* TVLoss (losses.py:81-87) on [B,H,W] single-channel fields */
+int gdn_tv(const float* x, int B, int H, int W, float weight, float* loss, float* grad, float gscale, int accumulate, void* ws, gdn_stream_t s);
+/* BCEWithLogitsLoss mean vs constant target (GAN_DANet_train.ipynb:252-253,261): loss[0] = mean(...); grad = gscale*(sigmoid(z)-t)/n */
+int gdn_bce_logits(const float* z, int n, float target, float* loss, float* grad, float gscale, gdn_stream_t s);
+/* SSIM (losses.py:98-136) forward only, single channel [B,H,W]: out[0] = mean ssim map.  ws: 5*B*H*W floats + dot ws */
+size_t gdn_ssim_ws_bytes(int B, int H, int W);
+int gdn_ssim(const float* a, const float* b, int B, int H, int W, float* out, void* ws, gdn_stream_t s);
+
+/* ----------------------------------------------------------------- optimiser */
+/* torch.optim.AdamW (GAN_DANet_train.ipynb:182-183) over a flat arena; grad_scale folds the 1/world of DP. step is 1-based. */
+int gdn_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd,
+              int step, float grad_scale, gdn_stream_t s);
+int gdn_fill(float* p, long long n, float value, gdn_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANDANET_H_ */
