@@ -1,0 +1,310 @@
+// DANet attention, fp32 "parity" engine: position attention (PAM) and channel attention (CAM), forward and backward.
+// Reference: PAMModule.forward /root/reference/models/generator.py:113-122, CAMModule.forward generator.py:128-139.
+// The parity engine evaluates the reference formulation sample-chunk by sample-chunk on the fp32 implicit-GEMM
+// kernels of igemm_simt.cu (the NxN map lives only in the caller's workspace, a few samples at a time); the
+// tensor-core flash kernels live in pam_tc.cu and are selected with precision = GDN_PREC_FP16.
+// Backward formulas: SURVEY appendix C.
+#include "common.cuh"
+
+extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s);
+extern "C" size_t gdn_pam_tc_fwd_ws_bytes(const gdn_pam_fwd_args* a);
+extern "C" int gdn_pam_tc_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s);
+extern "C" size_t gdn_pam_tc_bwd_ws_bytes(const gdn_pam_bwd_args* a);
+
+namespace gdn {
+
+// in-place row softmax of a [rows][n] matrix, one CTA per row; lse[row] = logsumexp (optional).
+// negate != 0 evaluates softmax(-x) (CAM: softmax(rowmax(E)-E) == softmax(-E), generator.py:135-136).
+__global__ void __launch_bounds__(256) row_softmax_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int n, int negate, float* __restrict__ lse) {
+  __shared__ float sh[32];
+  const float sgn = negate ? -1.f : 1.f;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float* p = in + (size_t)row * n;
+    float* q = out + (size_t)row * n;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, sgn * p[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : -INFINITY;
+    m = warp_max(m);
+    m = __shfl_sync(0xffffffffu, m, 0);
+    if ((threadIdx.x >> 5) == 0 && (threadIdx.x & 31) == 0) sh[0] = m;
+    __syncthreads();
+    m = sh[0];
+    __syncthreads();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += expf(sgn * p[i] - m);
+    s = block_sum<float>(s, sh);
+    if (threadIdx.x == 0) sh[0] = s;
+    __syncthreads();
+    s = sh[0];
+    __syncthreads();
+    const float inv = 1.f / s;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) q[i] = expf(sgn * p[i] - m) * inv;
+    if (lse && threadIdx.x == 0) lse[row] = m + logf(s);
+  }
+}
+
+// y = gamma[0]*o + x  on [M][C] slices
+__global__ void __launch_bounds__(256) gamma_residual_kernel(const float* __restrict__ o, int o_pitch, const float* __restrict__ x, int x_pitch,
+                                                             const float* __restrict__ gamma, float* __restrict__ y, int y_pitch, long long M, int C) {
+  const float g = __ldg(gamma);
+  const long long total = M * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long m = idx / C; int c = (int)(idx - m * C);
+    y[(size_t)m * y_pitch + c] = fmaf(g, o[(size_t)m * o_pitch + c], x[(size_t)m * x_pitch + c]);
+  }
+}
+
+// rowdot[m] = sum_c a[m][c]*b[m][c]; one warp per row
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ a, int a_pitch, const float* __restrict__ b, int b_pitch, long long M, int C, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long m = warp; m < M; m += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(a[(size_t)m * a_pitch + c], b[(size_t)m * b_pitch + c], s);
+    s = warp_sum(s);
+    if (lane == 0) out[m] = s;
+  }
+}
+
+// P = exp(S - lse[row]) (overwrites S);  dS = P * (dP - gamma*rowdot[row]) (overwrites dP)
+__global__ void __launch_bounds__(256) pam_ds_kernel(float* __restrict__ S, float* __restrict__ dP, const float* __restrict__ lse, const float* __restrict__ rowdot,
+                                                      const float* __restrict__ gamma, long long rows, int n) {
+  const float g = __ldg(gamma);
+  const long long total = rows * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx / n;
+    float p = expf(S[idx] - lse[r]);
+    S[idx] = p;
+    dP[idx] = p * (dP[idx] - g * rowdot[r]);
+  }
+}
+
+// CAM backward glue per [C][C] matrix: dE = -A*(dA - rowsum(A*dA)); G = dE + dE^T; AT = A^T.  One CTA per sample.
+__global__ void __launch_bounds__(256) cam_de_kernel(const float* __restrict__ attn, const float* __restrict__ da, float* __restrict__ G, float* __restrict__ AT,
+                                                      float* __restrict__ rowsum_ws, int C) {
+  const int b = blockIdx.x;
+  const float* A = attn + (size_t)b * C * C;
+  const float* dA = da + (size_t)b * C * C;
+  float* rs = rowsum_ws + (size_t)b * C;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = wid; i < C; i += nw) {
+    float s = 0.f;
+    for (int j = lane; j < C; j += 32) s = fmaf(A[(size_t)i * C + j], dA[(size_t)i * C + j], s);
+    s = warp_sum(s);
+    if (lane == 0) rs[i] = s;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    int i = idx / C, j = idx - i * C;
+    float e_ij = -A[(size_t)i * C + j] * (dA[(size_t)i * C + j] - rs[i]);
+    float e_ji = -A[(size_t)j * C + i] * (dA[(size_t)j * C + i] - rs[j]);
+    G[(size_t)b * C * C + idx] = e_ij + e_ji;
+    if (AT) AT[(size_t)b * C * C + idx] = A[(size_t)j * C + i];
+  }
+}
+
+static inline int ew_grid(long long total) {
+  long long b = cdiv(total, 256);
+  return (int)(b < 16 * kNumSMs ? (b > 0 ? b : 1) : 16 * kNumSMs);
+}
+
+static int pam_chunk(int B, int N, int requested) {
+  if (requested > 0) return requested < B ? requested : B;
+  long long per = (long long)N * N * 4;
+  long long g = (1ll << 30) / (per > 0 ? per : 1);   // keep each NxN scratch <= 1 GiB
+  if (g < 1) g = 1;
+  if (g > B) g = B;
+  return (int)g;
+}
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+}  // namespace gdn
+
+using namespace gdn;
+
+extern "C" int gdn_row_softmax(const float* in, float* out, long long rows, int n, int negate, float* lse, gdn_stream_t s) {
+  GDN_CHECK_ARG(in && out && rows > 0 && n > 0);
+  int blocks = (int)(rows < 64 * kNumSMs ? rows : 64 * kNumSMs);
+  row_softmax_kernel<<<blocks, 256, 0, as_stream(s)>>>(in, out, rows, n, negate, lse);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_cam_softmax(const float* e, float* attn, int rows, int C, gdn_stream_t s) { return gdn_row_softmax(e, attn, rows, C, 1, nullptr, s); }
+
+extern "C" int gdn_gamma_residual(const float* o, int o_pitch, const float* x, int x_pitch, const float* gamma, float* y, int y_pitch, long long M, int C, gdn_stream_t s) {
+  GDN_CHECK_ARG(o && x && gamma && y && M > 0 && C > 0 && o_pitch >= C && x_pitch >= C && y_pitch >= C);
+  gamma_residual_kernel<<<ew_grid(M * C), 256, 0, as_stream(s)>>>(o, o_pitch, x, x_pitch, gamma, y, y_pitch, M, C);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_rowdot(const float* a, int a_pitch, const float* b, int b_pitch, long long M, int C, float* out, gdn_stream_t s) {
+  GDN_CHECK_ARG(a && b && out && M > 0 && C > 0 && a_pitch >= C && b_pitch >= C);
+  rowdot_kernel<<<ew_grid(M * 32), 256, 0, as_stream(s)>>>(a, a_pitch, b, b_pitch, M, C, out);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ PAM
+extern "C" size_t gdn_pam_fwd_ws_bytes(const gdn_pam_fwd_args* a) {
+  if (!a) return 0;
+  if (a->precision != GDN_PREC_FP32) return gdn_pam_tc_fwd_ws_bytes(a);
+  int g = pam_chunk(a->B, a->N, a->chunk);
+  return align256((size_t)g * a->N * a->N * 4) + align256((size_t)g * a->C * a->N * 4);
+}
+extern "C" size_t gdn_pam_bwd_ws_bytes(const gdn_pam_bwd_args* a) {
+  if (!a) return 0;
+  if (a->precision != GDN_PREC_FP32) return gdn_pam_tc_bwd_ws_bytes(a);
+  int g = pam_chunk(a->B, a->N, a->chunk);
+  return 2 * align256((size_t)g * a->N * a->N * 4) + align256((size_t)g * a->d * a->N * 4);
+}
+
+extern "C" int gdn_pam_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
+  GDN_CHECK_ARG(a && a->q && a->k && a->v && a->x && a->gamma && a->o && a->y && a->lse);
+  GDN_CHECK_ARG(a->B > 0 && a->N > 0 && a->C > 0 && a->d > 0 && a->qk_pitch >= a->d && a->v_pitch >= a->C && a->x_pitch >= a->C && a->y_pitch >= a->C);
+  if (a->precision != GDN_PREC_FP32) return gdn_pam_tc_fwd(a, s);
+  const int B = a->B, N = a->N, C = a->C, d = a->d;
+  const int g = pam_chunk(B, N, a->chunk);
+  if (!a->ws || a->ws_bytes < gdn_pam_fwd_ws_bytes(a)) { set_error("gdn_pam_fwd: workspace too small"); return GDN_EWORKSPACE; }
+  float* S = reinterpret_cast<float*>(a->ws);
+  float* VT = reinterpret_cast<float*>(reinterpret_cast<char*>(a->ws) + align256((size_t)g * N * N * 4));
+  for (int b0 = 0; b0 < B; b0 += g) {
+    const int gb = (B - b0 < g) ? B - b0 : g;
+    int rc;
+    // S[b][i][j] = q_i . k_j  (generator.py:115-117, no scaling)
+    gdn_conv_args c = {};
+    c.x = a->q + (size_t)b0 * N * a->qk_pitch; c.x_pitch = a->qk_pitch;
+    c.w = a->k + (size_t)b0 * N * a->qk_pitch; c.w_k_pitch = a->qk_pitch; c.w_group_stride = (long long)N * a->qk_pitch; c.groups = gb;
+    c.y = S; c.y_pitch = N;
+    c.B = gb; c.Hi = N; c.Wi = 1; c.Cin = d; c.Ho = N; c.Wo = 1; c.Cout = N; c.kh = c.kw = 1; c.stride = 1; c.splits = 1;
+    if ((rc = gdn_conv2d(&c, s)) != GDN_OK) return rc;
+    // attention = softmax(energy, dim=-1)  (:118)
+    if ((rc = gdn_row_softmax(S, S, (long long)gb * N, N, 0, a->lse + (size_t)b0 * N, s)) != GDN_OK) return rc;
+    // out = bmm(value, attention^T)  (:119-120): o[i][c] = sum_j P[i][j] v[j][c]; weights = v^T per sample
+    if ((rc = gdn_nhwc_to_nchw(a->v + (size_t)b0 * N * a->v_pitch, a->v_pitch, 0, VT, gb, C, N, 1, s)) != GDN_OK) return rc;
+    gdn_conv_args o = {};
+    o.x = S; o.x_pitch = N;
+    o.w = VT; o.w_k_pitch = N; o.w_group_stride = (long long)C * N; o.groups = gb;
+    o.y = a->o + (size_t)b0 * N * C; o.y_pitch = C;
+    o.B = gb; o.Hi = N; o.Wi = 1; o.Cin = N; o.Ho = N; o.Wo = 1; o.Cout = C; o.kh = o.kw = 1; o.stride = 1; o.splits = 1;
+    if ((rc = gdn_conv2d(&o, s)) != GDN_OK) return rc;
+  }
+  // gamma * out + x  (:122)
+  return gdn_gamma_residual(a->o, C, a->x, a->x_pitch, a->gamma, a->y, a->y_pitch, (long long)B * N, C, s);
+}
+
+extern "C" int gdn_pam_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s) {
+  GDN_CHECK_ARG(a && a->q && a->k && a->v && a->o && a->lse && a->gamma && a->dy && a->dq && a->dk && a->dv && a->rowdot);
+  GDN_CHECK_ARG(a->B > 0 && a->N > 0 && a->C > 0 && a->d > 0 && a->qk_pitch >= a->d && a->v_pitch >= a->C && a->dy_pitch >= a->C);
+  const int B = a->B, N = a->N, C = a->C, d = a->d;
+  int rc;
+  if ((rc = gdn_rowdot(a->dy, a->dy_pitch, a->o, C, (long long)B * N, C, a->rowdot, s)) != GDN_OK) return rc;
+  if (a->precision != GDN_PREC_FP32) return gdn_pam_tc_bwd(a, s);
+  const int g = pam_chunk(B, N, a->chunk);
+  if (!a->ws || a->ws_bytes < gdn_pam_bwd_ws_bytes(a)) { set_error("gdn_pam_bwd: workspace too small"); return GDN_EWORKSPACE; }
+  const size_t nn = align256((size_t)g * N * N * 4);
+  float* S = reinterpret_cast<float*>(a->ws);
+  float* dP = reinterpret_cast<float*>(reinterpret_cast<char*>(a->ws) + nn);
+  float* KT = reinterpret_cast<float*>(reinterpret_cast<char*>(a->ws) + 2 * nn);
+  for (int b0 = 0; b0 < B; b0 += g) {
+    const int gb = (B - b0 < g) ? B - b0 : g;
+    const float* qb = a->q + (size_t)b0 * N * a->qk_pitch;
+    const float* kb = a->k + (size_t)b0 * N * a->qk_pitch;
+    const float* vb = a->v + (size_t)b0 * N * a->v_pitch;
+    const float* dyb = a->dy + (size_t)b0 * N * a->dy_pitch;
+    gdn_conv_args c = {};
+    c.x = qb; c.x_pitch = a->qk_pitch; c.w = kb; c.w_k_pitch = a->qk_pitch; c.w_group_stride = (long long)N * a->qk_pitch; c.groups = gb;
+    c.y = S; c.y_pitch = N; c.B = gb; c.Hi = N; c.Wi = 1; c.Cin = d; c.Ho = N; c.Wo = 1; c.Cout = N; c.kh = c.kw = 1; c.stride = 1; c.splits = 1;
+    if ((rc = gdn_conv2d(&c, s)) != GDN_OK) return rc;
+    // dP = dO V^T with dO = gamma*dy
+    gdn_conv_args p = {};
+    p.x = dyb; p.x_pitch = a->dy_pitch; p.w = vb; p.w_k_pitch = a->v_pitch; p.w_group_stride = (long long)N * a->v_pitch; p.groups = gb;
+    p.y = dP; p.y_pitch = N; p.alpha_ptr = a->gamma;
+    p.B = gb; p.Hi = N; p.Wi = 1; p.Cin = C; p.Ho = N; p.Wo = 1; p.Cout = N; p.kh = p.kw = 1; p.stride = 1; p.splits = 1;
+    if ((rc = gdn_conv2d(&p, s)) != GDN_OK) return rc;
+    pam_ds_kernel<<<ew_grid((long long)gb * N * N), 256, 0, as_stream(s)>>>(S, dP, a->lse + (size_t)b0 * N, a->rowdot + (size_t)b0 * N, a->gamma, (long long)gb * N, N);
+    GDN_CHECK_LAUNCH();
+    // dV[j][c] = sum_i P[i][j] * gamma*dy[i][c]
+    gdn_wgrad_args wv = {};
+    wv.dy = S; wv.dy_pitch = N; wv.x = dyb; wv.x_pitch = a->dy_pitch; wv.out = a->dv + (size_t)b0 * N * C; wv.layout = 0;
+    wv.scale_ptr = a->gamma; wv.scale = 1.f;
+    wv.B = gb; wv.Hi = N; wv.Wi = 1; wv.Cin = C; wv.Ho = N; wv.Wo = 1; wv.Cout = N; wv.kh = wv.kw = 1; wv.stride = 1; wv.groups = gb; wv.splits = 1;
+    if ((rc = gdn_conv2d_wgrad(&wv, s)) != GDN_OK) return rc;
+    // dQ = dS K : weights K^T per sample
+    if ((rc = gdn_nhwc_to_nchw(kb, a->qk_pitch, 0, KT, gb, d, N, 1, s)) != GDN_OK) return rc;
+    gdn_conv_args dq = {};
+    dq.x = dP; dq.x_pitch = N; dq.w = KT; dq.w_k_pitch = N; dq.w_group_stride = (long long)d * N; dq.groups = gb;
+    dq.y = a->dq + (size_t)b0 * N * d; dq.y_pitch = d;
+    dq.B = gb; dq.Hi = N; dq.Wi = 1; dq.Cin = N; dq.Ho = N; dq.Wo = 1; dq.Cout = d; dq.kh = dq.kw = 1; dq.stride = 1; dq.splits = 1;
+    if ((rc = gdn_conv2d(&dq, s)) != GDN_OK) return rc;
+    // dK[j][:] = sum_i dS[i][j] q[i][:]
+    gdn_wgrad_args wk = {};
+    wk.dy = dP; wk.dy_pitch = N; wk.x = qb; wk.x_pitch = a->qk_pitch; wk.out = a->dk + (size_t)b0 * N * d; wk.layout = 0; wk.scale = 1.f;
+    wk.B = gb; wk.Hi = N; wk.Wi = 1; wk.Cin = d; wk.Ho = N; wk.Wo = 1; wk.Cout = N; wk.kh = wk.kw = 1; wk.stride = 1; wk.groups = gb; wk.splits = 1;
+    if ((rc = gdn_conv2d_wgrad(&wk, s)) != GDN_OK) return rc;
+  }
+  return GDN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ CAM
+extern "C" size_t gdn_cam_bwd_ws_bytes(int B, int N, int C) {
+  return align256((size_t)B * N * C * 4) + 3 * align256((size_t)B * C * C * 4) + align256((size_t)B * C * 4);
+}
+
+// y = gamma * (softmax(-X X^T) X) + x ; attn [B][C][C] is written for the backward pass.
+extern "C" int gdn_cam_fwd(const float* x, int x_pitch, const float* gamma, float* attn, float* y, int y_pitch, int B, int N, int C, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && gamma && attn && y && B > 0 && N > 0 && C > 0 && x_pitch >= C && y_pitch >= C);
+  int rc;
+  gdn_wgrad_args e = {};   // energy = bmm(x, x^T)  (generator.py:131-132)
+  e.dy = x; e.dy_pitch = x_pitch; e.x = x; e.x_pitch = x_pitch; e.out = attn; e.layout = 0; e.scale = 1.f;
+  e.B = B; e.Hi = N; e.Wi = 1; e.Cin = C; e.Ho = N; e.Wo = 1; e.Cout = C; e.kh = e.kw = 1; e.stride = 1; e.groups = B; e.splits = 1;
+  if ((rc = gdn_conv2d_wgrad(&e, s)) != GDN_OK) return rc;
+  if ((rc = gdn_row_softmax(attn, attn, (long long)B * C, C, 1, nullptr, s)) != GDN_OK) return rc;   // (:135-136)
+  gdn_conv_args o = {};    // out = bmm(attention, value); gamma*out + x  (:138-139)
+  o.x = x; o.x_pitch = x_pitch; o.w = attn; o.w_k_pitch = C; o.w_group_stride = (long long)C * C; o.groups = B;
+  o.y = y; o.y_pitch = y_pitch; o.alpha_ptr = gamma; o.res = x; o.res_pitch = x_pitch;
+  o.B = B; o.Hi = N; o.Wi = 1; o.Cin = C; o.Ho = N; o.Wo = 1; o.Cout = C; o.kh = o.kw = 1; o.stride = 1; o.splits = 1;
+  return gdn_conv2d(&o, s);
+}
+
+// dx (+)= dy + gamma*A^T dy + (dE+dE^T) x ; dgamma[0] = sum dy*O
+extern "C" int gdn_cam_bwd(const float* x, int x_pitch, const float* gamma, const float* attn, const float* dy, int dy_pitch,
+                           float* dx, int dx_pitch, int accumulate, float* dgamma, int B, int N, int C, void* ws, size_t ws_bytes, void* dot_ws, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && gamma && attn && dy && dx && dgamma && ws && dot_ws && B > 0 && N > 0 && C > 0);
+  GDN_CHECK_ARG(x_pitch >= C && dy_pitch >= C && dx_pitch >= C);
+  if (ws_bytes < gdn_cam_bwd_ws_bytes(B, N, C)) { set_error("gdn_cam_bwd: workspace too small"); return GDN_EWORKSPACE; }
+  char* w = reinterpret_cast<char*>(ws);
+  float* O = reinterpret_cast<float*>(w); w += align256((size_t)B * N * C * 4);
+  float* dA = reinterpret_cast<float*>(w); w += align256((size_t)B * C * C * 4);
+  float* G = reinterpret_cast<float*>(w); w += align256((size_t)B * C * C * 4);
+  float* AT = reinterpret_cast<float*>(w); w += align256((size_t)B * C * C * 4);
+  float* rs = reinterpret_cast<float*>(w);
+  int rc;
+  gdn_conv_args o = {};
+  o.x = x; o.x_pitch = x_pitch; o.w = attn; o.w_k_pitch = C; o.w_group_stride = (long long)C * C; o.groups = B; o.y = O; o.y_pitch = C;
+  o.B = B; o.Hi = N; o.Wi = 1; o.Cin = C; o.Ho = N; o.Wo = 1; o.Cout = C; o.kh = o.kw = 1; o.stride = 1; o.splits = 1;
+  if ((rc = gdn_conv2d(&o, s)) != GDN_OK) return rc;
+  if ((rc = gdn_dot(dy, dy_pitch, 0, O, C, 0, (long long)B * N, C, dgamma, dot_ws, s)) != GDN_OK) return rc;
+  gdn_wgrad_args a = {};   // dA[i][j] = gamma * sum_n dy[n][i] x[n][j]
+  a.dy = dy; a.dy_pitch = dy_pitch; a.x = x; a.x_pitch = x_pitch; a.out = dA; a.layout = 0; a.scale_ptr = gamma; a.scale = 1.f;
+  a.B = B; a.Hi = N; a.Wi = 1; a.Cin = C; a.Ho = N; a.Wo = 1; a.Cout = C; a.kh = a.kw = 1; a.stride = 1; a.groups = B; a.splits = 1;
+  if ((rc = gdn_conv2d_wgrad(&a, s)) != GDN_OK) return rc;
+  cam_de_kernel<<<B, 256, 0, as_stream(s)>>>(attn, dA, G, AT, rs, C);
+  GDN_CHECK_LAUNCH();
+  // O (scratch) = dy + gamma * dy A   [weights A^T: out[n][c] = sum_i AT[c][i] dy[n][i]]
+  gdn_conv_args t = {};
+  t.x = dy; t.x_pitch = dy_pitch; t.w = AT; t.w_k_pitch = C; t.w_group_stride = (long long)C * C; t.groups = B; t.y = O; t.y_pitch = C;
+  t.alpha_ptr = gamma; t.res = dy; t.res_pitch = dy_pitch;
+  t.B = B; t.Hi = N; t.Wi = 1; t.Cin = C; t.Ho = N; t.Wo = 1; t.Cout = C; t.kh = t.kw = 1; t.stride = 1; t.splits = 1;
+  if ((rc = gdn_conv2d(&t, s)) != GDN_OK) return rc;
+  // dx (+)= O + G x
+  gdn_conv_args u = {};
+  u.x = x; u.x_pitch = x_pitch; u.w = G; u.w_k_pitch = C; u.w_group_stride = (long long)C * C; u.groups = B; u.y = O; u.y_pitch = C;
+  u.res = O; u.res_pitch = C;
+  u.B = B; u.Hi = N; u.Wi = 1; u.Cin = C; u.Ho = N; u.Wo = 1; u.Cout = C; u.kh = u.kw = 1; u.stride = 1; u.splits = 1;
+  if ((rc = gdn_conv2d(&u, s)) != GDN_OK) return rc;
+  return gdn_axpy(O, C, 0, dx, dx_pitch, 0, (long long)B * N, C, 1.f, accumulate, s);
+}
+

@@ -1,0 +1,301 @@
+// HBM-bound NHWC kernels: per-channel statistics, train-mode BatchNorm forward/backward, activations, axpy.
+// Reference call sites: nn.BatchNorm2d + nn.ReLU at /root/reference/models/generator.py:32-33,61-62,149-150,
+// 189-190,219-220,223-224; nn.LeakyReLU(0.2) at models/discriminator.py:68; nn.ReLU of VGG19 (models/losses.py:58).
+// All reductions are deterministic two-stage sums accumulated in double.
+#include "common.cuh"
+
+namespace gdn {
+
+constexpr int kMaxStatBlocks = 4 * kNumSMs;
+
+struct StatPlan { int blocks; long long rows_per_block; };
+static StatPlan stat_plan(long long M) {
+  StatPlan p;
+  long long rpb = cdiv(M, kMaxStatBlocks);
+  if (rpb < 64) rpb = 64;
+  p.rows_per_block = rpb;
+  p.blocks = (int)cdiv(M, rpb);
+  return p;
+}
+
+// MODE 0: (sum x, sum x^2).  MODE 1: g = dy*act'(x*scale+shift): (sum g, sum g*xhat).
+template <int MODE>
+__global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ dy, int dy_pitch,
+                                                        long long M, int C, long long rows_per_block,
+                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                        int act, float slope, double* __restrict__ partial) {
+  __shared__ double sh[2][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long r0 = blockIdx.x * rows_per_block;
+  const long long r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
+  for (int cb = 0; cb < C; cb += 32) {
+    const int c = cb + tx;
+    double a0 = 0.0, a1 = 0.0;
+    if (c < C) {
+      float mu = 0.f, is = 0.f, sc = 0.f, sf = 0.f;
+      if (MODE == 1) { mu = mean[c]; is = invstd[c]; sc = scale[c]; sf = shift[c]; }
+      long long r = r0 + ty;
+      while (r < r1) {
+        float f0 = 0.f, f1 = 0.f;
+#pragma unroll 4
+        for (int u = 0; u < 16 && r < r1; ++u, r += 8) {
+          float xv = x[(size_t)r * x_pitch + c];
+          if (MODE == 0) {
+            f0 += xv; f1 = fmaf(xv, xv, f1);
+          } else {
+            float g = dy[(size_t)r * dy_pitch + c] * act_grad(fmaf(xv, sc, sf), act, slope);
+            f0 += g; f1 = fmaf(g, (xv - mu) * is, f1);
+          }
+        }
+        a0 += (double)f0; a1 += (double)f1;
+      }
+    }
+    sh[0][ty][tx] = a0; sh[1][ty][tx] = a1;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s0 += sh[0][j][tx]; s1 += sh[1][j][tx]; }
+      partial[(size_t)blockIdx.x * 2 * C + c] = s0;
+      partial[(size_t)blockIdx.x * 2 * C + C + c] = s1;
+    }
+    __syncthreads();
+  }
+}
+
+// out[j] = sum_b partial[b][j], j < n2 ; one warp per 32 columns, 8 row lanes
+__global__ void __launch_bounds__(256) colreduce_final_kernel(const double* __restrict__ partial, int nblocks, int n2, double* __restrict__ out) {
+  __shared__ double sh[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  double a = 0.0;
+  if (j < n2) for (int b = ty; b < nblocks; b += 8) a += partial[(size_t)b * n2 + j];
+  sh[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && j < n2) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sh[k][tx];
+    out[j] = s;
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M, int C, const float* __restrict__ weight,
+                                   const float* __restrict__ bias, float eps, float momentum, float* running_mean, float* running_var,
+                                   float* mean_o, float* invstd_o, float* scale_o, float* shift_o) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m = sums[c] / (double)M;
+  double var = sums[C + c] / (double)M - m * m;
+  if (var < 0.0) var = 0.0;
+  float is = (float)(1.0 / sqrt(var + (double)eps));
+  float w = weight ? weight[c] : 1.f, b = bias ? bias[c] : 0.f;
+  float sc = w * is;
+  mean_o[c] = (float)m; invstd_o[c] = is; scale_o[c] = sc; shift_o[c] = b - (float)m * sc;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+  if (running_var) {
+    double unbiased = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_eval_coeffs_kernel(const float* weight, const float* bias, const float* rm, const float* rv, float eps, int C,
+                                      float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sc = (weight ? weight[c] : 1.f) / sqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = (bias ? bias[c] : 0.f) - rm[c] * sc;
+}
+
+// ---- generic NHWC elementwise drivers: VEC = 4 when C, pitches and offsets allow 128-bit access, else 1
+enum { EW_AFFINE = 0, EW_BN_BWD = 1, EW_ACT_BWD = 2, EW_AXPY = 3 };
+struct EwP {
+  const float* a; int a_pitch;      // x / dy / dy / x
+  const float* b; int b_pitch;      // - / x  / y  / -
+  float* o; int o_pitch; int accumulate;
+  long long M; int C;
+  const float* mean; const float* invstd; const float* weight; const float* scale; const float* shift;
+  const double* sums; float alpha; int act; float slope;
+};
+
+template <int OP>
+__device__ __forceinline__ float ew_apply(const EwP& p, float a, float b, int c, float invM) {
+  if (OP == EW_AFFINE) return apply_act(fmaf(a, __ldg(p.scale + c), __ldg(p.shift + c)), p.act, p.slope);
+  if (OP == EW_ACT_BWD) return a * act_grad(b, p.act, p.slope);
+  if (OP == EW_AXPY) return a * p.alpha;
+  // EW_BN_BWD: a = dy, b = x
+  float sc = __ldg(p.scale + c), sf = __ldg(p.shift + c), mu = __ldg(p.mean + c), is = __ldg(p.invstd + c);
+  float g = a * act_grad(fmaf(b, sc, sf), p.act, p.slope);
+  float xhat = (b - mu) * is;
+  float sg = (float)(p.sums[c] * (double)invM), sgx = (float)(p.sums[p.C + c] * (double)invM);
+  float w = p.weight ? __ldg(p.weight + c) : 1.f;
+  return w * is * (g - sg - xhat * sgx);
+}
+
+template <int OP, int VEC>
+__global__ void __launch_bounds__(256) ew_kernel(const EwP p) {
+  const int Cv = p.C / VEC;
+  const long long total = p.M * Cv;
+  const float invM = 1.f / (float)p.M;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long m = idx / Cv;
+    int c = (int)(idx - m * Cv) * VEC;
+    if (VEC == 4) {
+      float4 a = *reinterpret_cast<const float4*>(p.a + (size_t)m * p.a_pitch + c);
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (OP == EW_BN_BWD || OP == EW_ACT_BWD) b = *reinterpret_cast<const float4*>(p.b + (size_t)m * p.b_pitch + c);
+      float4 r;
+      r.x = ew_apply<OP>(p, a.x, b.x, c, invM); r.y = ew_apply<OP>(p, a.y, b.y, c + 1, invM);
+      r.z = ew_apply<OP>(p, a.z, b.z, c + 2, invM); r.w = ew_apply<OP>(p, a.w, b.w, c + 3, invM);
+      float4* op = reinterpret_cast<float4*>(p.o + (size_t)m * p.o_pitch + c);
+      if (p.accumulate) { float4 o = *op; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+      *op = r;
+    } else {
+      float a = p.a[(size_t)m * p.a_pitch + c];
+      float b = (OP == EW_BN_BWD || OP == EW_ACT_BWD) ? p.b[(size_t)m * p.b_pitch + c] : 0.f;
+      float r = ew_apply<OP>(p, a, b, c, invM);
+      float* op = p.o + (size_t)m * p.o_pitch + c;
+      if (p.accumulate) r += *op;
+      *op = r;
+    }
+  }
+}
+
+static bool vec4_ok(const EwP& p) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  bool ok = (p.C % 4 == 0) && (p.a_pitch % 4 == 0) && (p.o_pitch % 4 == 0) && al(p.a) && al(p.o);
+  if (p.b) ok = ok && (p.b_pitch % 4 == 0) && al(p.b);
+  return ok;
+}
+
+template <int OP>
+static int ew_launch(const EwP& p, cudaStream_t st) {
+  if (p.M == 0) return GDN_OK;
+  const bool v4 = vec4_ok(p);
+  long long total = p.M * (v4 ? p.C / 4 : p.C);
+  int blocks = (int)(cdiv(total, 256) < 16 * kNumSMs ? cdiv(total, 256) : 16 * kNumSMs);
+  if (v4) ew_kernel<OP, 4><<<blocks, 256, 0, st>>>(p);
+  else ew_kernel<OP, 1><<<blocks, 256, 0, st>>>(p);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+__global__ void bn_param_grads_kernel(const double* sums, int C, float* dweight, float* dbias) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbias) dbias[c] = (float)sums[c];
+  if (dweight) dweight[c] = (float)sums[C + c];
+}
+__global__ void sums_to_float_kernel(const double* sums, float* out, int n, float scale) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)(sums[i] * (double)scale);
+}
+
+__global__ void __launch_bounds__(256) scale_dev_kernel(const float* __restrict__ x, const float* __restrict__ sc, float* __restrict__ y, long long n, int accumulate) {
+  const float a = __ldg(sc);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = a * x[i];
+    y[i] = accumulate ? y[i] + v : v;
+  }
+}
+
+template <int MODE>
+static int colreduce(const float* x, int x_pitch, const float* dy, int dy_pitch, long long M, int C, const float* mean, const float* invstd,
+                     const float* scale, const float* shift, int act, float slope, double* out, void* ws, cudaStream_t st) {
+  StatPlan pl = stat_plan(M);
+  double* partial = reinterpret_cast<double*>(ws);
+  colreduce_kernel<MODE><<<pl.blocks, 256, 0, st>>>(x, x_pitch, dy, dy_pitch, M, C, pl.rows_per_block, mean, invstd, scale, shift, act, slope, partial);
+  GDN_CHECK_LAUNCH();
+  colreduce_final_kernel<<<(unsigned)cdiv(2 * C, 32), 256, 0, st>>>(partial, pl.blocks, 2 * C, out);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+}  // namespace gdn
+
+using namespace gdn;
+
+extern "C" size_t gdn_colstats_ws_bytes(long long M, int C) {
+  StatPlan pl = stat_plan(M > 0 ? M : 1);
+  return (size_t)pl.blocks * 2 * (size_t)C * sizeof(double);
+}
+extern "C" int gdn_colstats(const float* x, int pitch, int c0, long long M, int C, double* out, void* ws, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && out && ws && M > 0 && C > 0 && pitch >= c0 + C);
+  return colreduce<0>(x + c0, pitch, nullptr, 0, M, C, nullptr, nullptr, nullptr, nullptr, 0, 0.f, out, ws, as_stream(s));
+}
+extern "C" int gdn_bn_finalize(const double* sums, long long M, int C, const float* weight, const float* bias, float eps, float momentum,
+                               float* running_mean, float* running_var, float* mean, float* invstd, float* scale, float* shift, gdn_stream_t s) {
+  GDN_CHECK_ARG(sums && M > 0 && C > 0 && mean && invstd && scale && shift);
+  bn_finalize_kernel<<<(unsigned)cdiv(C, 128), 128, 0, as_stream(s)>>>(sums, M, C, weight, bias, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_bn_eval_coeffs(const float* weight, const float* bias, const float* running_mean, const float* running_var, float eps,
+                                  int C, float* scale, float* shift, gdn_stream_t s) {
+  GDN_CHECK_ARG(running_mean && running_var && scale && shift && C > 0);
+  bn_eval_coeffs_kernel<<<(unsigned)cdiv(C, 128), 128, 0, as_stream(s)>>>(weight, bias, running_mean, running_var, eps, C, scale, shift);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_affine_act(const float* x, int x_pitch, int x_c0, float* y, int y_pitch, int y_c0, long long M, int C,
+                              const float* scale, const float* shift, int act, float slope, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && y && scale && shift && M >= 0 && C > 0 && x_pitch >= x_c0 + C && y_pitch >= y_c0 + C);
+  EwP p = {};
+  p.a = x + x_c0; p.a_pitch = x_pitch; p.o = y + y_c0; p.o_pitch = y_pitch; p.M = M; p.C = C;
+  p.scale = scale; p.shift = shift; p.act = act; p.slope = slope;
+  return ew_launch<EW_AFFINE>(p, as_stream(s));
+}
+extern "C" int gdn_bn_bwd_reduce(const float* dy, int dy_pitch, int dy_c0, const float* x, int x_pitch, int x_c0, long long M, int C,
+                                 const float* mean, const float* invstd, const float* scale, const float* shift, int act, float slope,
+                                 double* sums, void* ws, gdn_stream_t s) {
+  GDN_CHECK_ARG(dy && x && mean && invstd && scale && shift && sums && ws && M > 0 && C > 0);
+  GDN_CHECK_ARG(dy_pitch >= dy_c0 + C && x_pitch >= x_c0 + C);
+  return colreduce<1>(x + x_c0, x_pitch, dy + dy_c0, dy_pitch, M, C, mean, invstd, scale, shift, act, slope, sums, ws, as_stream(s));
+}
+extern "C" int gdn_bn_bwd_apply(const float* dy, int dy_pitch, int dy_c0, const float* x, int x_pitch, int x_c0,
+                                float* dx, int dx_pitch, int dx_c0, int accumulate, long long M, int C,
+                                const float* mean, const float* invstd, const float* weight, const float* scale, const float* shift,
+                                int act, float slope, const double* sums, float* dweight, float* dbias, gdn_stream_t s) {
+  GDN_CHECK_ARG(dy && x && dx && mean && invstd && scale && shift && sums && M > 0 && C > 0);
+  GDN_CHECK_ARG(dy_pitch >= dy_c0 + C && x_pitch >= x_c0 + C && dx_pitch >= dx_c0 + C);
+  EwP p = {};
+  p.a = dy + dy_c0; p.a_pitch = dy_pitch; p.b = x + x_c0; p.b_pitch = x_pitch; p.o = dx + dx_c0; p.o_pitch = dx_pitch;
+  p.accumulate = accumulate; p.M = M; p.C = C; p.mean = mean; p.invstd = invstd; p.weight = weight; p.scale = scale; p.shift = shift;
+  p.sums = sums; p.act = act; p.slope = slope;
+  int rc = ew_launch<EW_BN_BWD>(p, as_stream(s));
+  if (rc != GDN_OK) return rc;
+  if (dweight || dbias) {
+    bn_param_grads_kernel<<<(unsigned)cdiv(C, 128), 128, 0, as_stream(s)>>>(sums, C, dweight, dbias);
+    GDN_CHECK_LAUNCH();
+  }
+  return GDN_OK;
+}
+extern "C" int gdn_act_bwd(const float* dy, int dy_pitch, int dy_c0, const float* y, int y_pitch, int y_c0,
+                           float* dz, int dz_pitch, int dz_c0, long long M, int C, int act, float slope, gdn_stream_t s) {
+  GDN_CHECK_ARG(dy && y && dz && M >= 0 && C > 0 && dy_pitch >= dy_c0 + C && y_pitch >= y_c0 + C && dz_pitch >= dz_c0 + C);
+  EwP p = {};
+  p.a = dy + dy_c0; p.a_pitch = dy_pitch; p.b = y + y_c0; p.b_pitch = y_pitch; p.o = dz + dz_c0; p.o_pitch = dz_pitch;
+  p.M = M; p.C = C; p.act = act; p.slope = slope;
+  return ew_launch<EW_ACT_BWD>(p, as_stream(s));
+}
+extern "C" int gdn_axpy(const float* x, int x_pitch, int x_c0, float* y, int y_pitch, int y_c0, long long M, int C, float alpha, int accumulate, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && y && M >= 0 && C > 0 && x_pitch >= x_c0 + C && y_pitch >= y_c0 + C);
+  EwP p = {};
+  p.a = x + x_c0; p.a_pitch = x_pitch; p.o = y + y_c0; p.o_pitch = y_pitch; p.accumulate = accumulate; p.M = M; p.C = C; p.alpha = alpha;
+  return ew_launch<EW_AXPY>(p, as_stream(s));
+}
+extern "C" int gdn_sums_to_float(const double* sums, float* out, int n, float scale, gdn_stream_t s) {
+  GDN_CHECK_ARG(sums && out && n > 0);
+  sums_to_float_kernel<<<(unsigned)cdiv(n, 128), 128, 0, as_stream(s)>>>(sums, out, n, scale);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_scale_dev(const float* x, const float* scalar, float* y, long long n, int accumulate, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && scalar && y && n >= 0);
+  if (n == 0) return GDN_OK;
+  int blocks = (int)(cdiv(n, 256) < 16 * kNumSMs ? cdiv(n, 256) : 16 * kNumSMs);
+  scale_dev_kernel<<<blocks, 256, 0, as_stream(s)>>>(x, scalar, y, n, accumulate);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}

@@ -1,0 +1,271 @@
+// Scalar losses (+ their gradients in the same pass), dot products and the fused AdamW update.
+// Reference call sites: nn.MSELoss / nn.BCEWithLogitsLoss at /root/reference/GAN_DANet_train.ipynb:190-191,252-253,261-262;
+// TVLoss models/losses.py:76-87; SSIM models/losses.py:90-147; F.l1_loss models/losses.py:72;
+// torch.optim.AdamW GAN_DANet_train.ipynb:182-183,256,269.
+// All reductions: per-block partial sums in double -> one finishing block (fixed order => bitwise deterministic).
+#include <math.h>
+#include "common.cuh"
+
+namespace gdn {
+
+constexpr int kRedBlocks = 8 * kNumSMs;   // upper bound on stage-1 blocks
+constexpr int kRedSlots = 4;              // doubles per block
+
+static inline int red_blocks(long long n, int per_thread = 8) {
+  long long b = cdiv(n, 256ll * per_thread);
+  if (b < 1) b = 1;
+  return (int)(b < kRedBlocks ? b : kRedBlocks);
+}
+
+__device__ __forceinline__ void block_store_partials(double v0, double v1, double* partial) {
+  __shared__ double sh[32];
+  double s0 = block_sum<double>(v0, sh);
+  double s1 = block_sum<double>(v1, sh);
+  if (threadIdx.x == 0) { partial[(size_t)blockIdx.x * kRedSlots] = s0; partial[(size_t)blockIdx.x * kRedSlots + 1] = s1; }
+}
+
+// loss[0] (+)= c0*sum(slot0) + c1*sum(slot1)
+__global__ void __launch_bounds__(256) finish_kernel(const double* __restrict__ partial, int nblocks, double c0, double c1, float* loss, int accumulate) {
+  __shared__ double sh[32];
+  double a0 = 0.0, a1 = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) { a0 += partial[(size_t)b * kRedSlots]; a1 += partial[(size_t)b * kRedSlots + 1]; }
+  a0 = block_sum<double>(a0, sh);
+  a1 = block_sum<double>(a1, sh);
+  if (threadIdx.x == 0) {
+    float v = (float)(c0 * a0 + c1 * a1);
+    loss[0] = accumulate ? loss[0] + v : v;
+  }
+}
+
+// MODE 0: MSE, MODE 1: L1
+template <int MODE>
+__global__ void __launch_bounds__(256) pair_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ grad,
+                                                        float gcoef, int accumulate, double* __restrict__ partial) {
+  float acc = 0.f; double dacc = 0.0; int cnt = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = a[i] - b[i];
+    float g;
+    if (MODE == 0) { acc = fmaf(d, d, acc); g = d * gcoef; }
+    else { acc += fabsf(d); g = (d > 0.f ? gcoef : (d < 0.f ? -gcoef : 0.f)); }
+    if (grad) grad[i] = accumulate ? grad[i] + g : g;
+    if (++cnt == 32) { dacc += (double)acc; acc = 0.f; cnt = 0; }
+  }
+  dacc += (double)acc;
+  block_store_partials(dacc, 0.0, partial);
+}
+
+__global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, int B, int H, int W, float* __restrict__ grad, float ch, float cw,
+                                                  int accumulate, double* __restrict__ partial) {
+  const long long n = (long long)B * H * W;
+  double dh = 0.0, dw = 0.0; float fh = 0.f, fw = 0.f; int cnt = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(i % W); int h = (int)((i / W) % H);
+    float c = x[i];
+    float up = h > 0 ? c - x[i - W] : 0.f;        // x[h]-x[h-1]
+    float dn = h < H - 1 ? x[i + W] - c : 0.f;    // x[h+1]-x[h]
+    float lf = w > 0 ? c - x[i - 1] : 0.f;
+    float rt = w < W - 1 ? x[i + 1] - c : 0.f;
+    fh = fmaf(dn, dn, fh); fw = fmaf(rt, rt, fw);
+    if (grad) { float g = ch * (up - dn) + cw * (lf - rt); grad[i] = accumulate ? grad[i] + g : g; }
+    if (++cnt == 32) { dh += (double)fh; dw += (double)fw; fh = fw = 0.f; cnt = 0; }
+  }
+  dh += (double)fh; dw += (double)fw;
+  block_store_partials(dh, dw, partial);
+}
+
+__global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ z, int n, const float* __restrict__ target_ptr, float target_const, float* loss, float* grad, float gscale) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = z[i];
+    const float target = target_ptr ? target_ptr[i] : target_const;
+    acc += (double)(fmaxf(v, 0.f) - v * target + log1pf(expf(-fabsf(v))));
+    if (grad) grad[i] = gscale * (1.f / (1.f + expf(-v)) - target) / (float)n;
+  }
+  acc = block_sum<double>(acc, sh);
+  if (threadIdx.x == 0) loss[0] = (float)(acc / (double)n);
+}
+
+__global__ void __launch_bounds__(256) dot_kernel(const float* __restrict__ a, int a_pitch, const float* __restrict__ b, int b_pitch, long long M, int C,
+                                                   double* __restrict__ partial) {
+  const long long n = M * C;
+  float acc = 0.f; double dacc = 0.0; int cnt = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long m = i / C; int c = (int)(i - m * C);
+    acc = fmaf(a[(size_t)m * a_pitch + c], b[(size_t)m * b_pitch + c], acc);
+    if (++cnt == 32) { dacc += (double)acc; acc = 0.f; cnt = 0; }
+  }
+  dacc += (double)acc;
+  block_store_partials(dacc, 0.0, partial);
+}
+
+// ---- SSIM forward: 32x16 output tile, 11x11 separable-by-outer-product Gaussian taps from shared memory
+struct SsimWin { float g[11]; };
+constexpr int ST_W = 32, ST_H = 16, SHALO = 5;
+__global__ void __launch_bounds__(ST_W* ST_H) ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int B, int H, int W, SsimWin win,
+                                                           double* __restrict__ partial) {
+  __shared__ float sa[ST_H + 2 * SHALO][ST_W + 2 * SHALO + 1];
+  __shared__ float sb[ST_H + 2 * SHALO][ST_W + 2 * SHALO + 1];
+  const int tilesx = (W + ST_W - 1) / ST_W, tilesy = (H + ST_H - 1) / ST_H;
+  const long long ntiles = (long long)B * tilesx * tilesy;
+  const int tx = threadIdx.x % ST_W, ty = threadIdx.x / ST_W;
+  double dacc = 0.0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int bx = (int)(tile % tilesx); long long r = tile / tilesx; int by = (int)(r % tilesy); int bb = (int)(r / tilesy);
+    const float* pa = a + (size_t)bb * H * W; const float* pb = b + (size_t)bb * H * W;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (ST_H + 2 * SHALO) * (ST_W + 2 * SHALO); i += blockDim.x) {
+      int ly = i / (ST_W + 2 * SHALO), lx = i % (ST_W + 2 * SHALO);
+      int gy = by * ST_H + ly - SHALO, gx = bx * ST_W + lx - SHALO;
+      bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;   // zero padding (F.conv2d padding=5)
+      sa[ly][lx] = ok ? pa[(size_t)gy * W + gx] : 0.f;
+      sb[ly][lx] = ok ? pb[(size_t)gy * W + gx] : 0.f;
+    }
+    __syncthreads();
+    int oy = by * ST_H + ty, ox = bx * ST_W + tx;
+    if (oy < H && ox < W) {
+      float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 11; ++i) {
+#pragma unroll
+        for (int j = 0; j < 11; ++j) {
+          float wgt = win.g[i] * win.g[j];
+          float u = sa[ty + i][tx + j], v = sb[ty + i][tx + j];
+          m1 = fmaf(wgt, u, m1); m2 = fmaf(wgt, v, m2);
+          s11 = fmaf(wgt, u * u, s11); s22 = fmaf(wgt, v * v, s22); s12 = fmaf(wgt, u * v, s12);
+        }
+      }
+      float mu1sq = m1 * m1, mu2sq = m2 * m2, mu12 = m1 * m2;
+      float sig1 = s11 - mu1sq, sig2 = s22 - mu2sq, sig12 = s12 - mu12;
+      const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;
+      float v = ((2.f * mu12 + c1) * (2.f * sig12 + c2)) / ((mu1sq + mu2sq + c1) * (sig1 + sig2 + c2));
+      dacc += (double)v;
+    }
+  }
+  block_store_partials(dacc, 0.0, partial);
+}
+
+// ---- AdamW (decoupled weight decay), torch.optim.AdamW single-tensor formula
+struct AdamP { float lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, grad_scale; };
+template <int VEC>
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, AdamP a) {
+  const long long nv = n / VEC;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float pv[VEC], gv[VEC], mv[VEC], vv[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(pv) = reinterpret_cast<const float4*>(p)[i];
+      *reinterpret_cast<float4*>(gv) = reinterpret_cast<const float4*>(g)[i];
+      *reinterpret_cast<float4*>(mv) = reinterpret_cast<const float4*>(m)[i];
+      *reinterpret_cast<float4*>(vv) = reinterpret_cast<const float4*>(v)[i];
+    } else { pv[0] = p[i]; gv[0] = g[i]; mv[0] = m[i]; vv[0] = v[i]; }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float gr = gv[k] * a.grad_scale;
+      float pp = pv[k] * (1.f - a.lr * a.wd);
+      float mm = mv[k] + (gr - mv[k]) * (1.f - a.beta1);
+      float v2 = vv[k] * a.beta2 + (1.f - a.beta2) * gr * gr;
+      float denom = sqrtf(v2) / a.bc2_sqrt + a.eps;
+      pv[k] = pp - a.step_size * (mm / denom);
+      mv[k] = mm; vv[k] = v2;
+    }
+    if (VEC == 4) {
+      reinterpret_cast<float4*>(p)[i] = *reinterpret_cast<float4*>(pv);
+      reinterpret_cast<float4*>(m)[i] = *reinterpret_cast<float4*>(mv);
+      reinterpret_cast<float4*>(v)[i] = *reinterpret_cast<float4*>(vv);
+    } else { p[i] = pv[0]; m[i] = mv[0]; v[i] = vv[0]; }
+  }
+}
+}  // namespace gdn
+
+using namespace gdn;
+
+extern "C" size_t gdn_dot_ws_bytes(long long n) { (void)n; return (size_t)kRedBlocks * kRedSlots * sizeof(double); }
+
+extern "C" int gdn_dot(const float* a, int a_pitch, int a_c0, const float* b, int b_pitch, int b_c0, long long M, int C, float* out, void* ws, gdn_stream_t s) {
+  GDN_CHECK_ARG(a && b && out && ws && M > 0 && C > 0 && a_pitch >= a_c0 + C && b_pitch >= b_c0 + C);
+  int blocks = red_blocks(M * C);
+  double* partial = reinterpret_cast<double*>(ws);
+  dot_kernel<<<blocks, 256, 0, as_stream(s)>>>(a + a_c0, a_pitch, b + b_c0, b_pitch, M, C, partial);
+  GDN_CHECK_LAUNCH();
+  finish_kernel<<<1, 256, 0, as_stream(s)>>>(partial, blocks, 1.0, 0.0, out, 0);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" int gdn_mse(const float* a, const float* b, long long n, float* loss, float* grad, float gscale, int accumulate, void* ws, gdn_stream_t s) {
+  GDN_CHECK_ARG(a && b && loss && ws && n > 0);
+  int blocks = red_blocks(n);
+  double* partial = reinterpret_cast<double*>(ws);
+  pair_loss_kernel<0><<<blocks, 256, 0, as_stream(s)>>>(a, b, n, grad, gscale * 2.f / (float)n, accumulate, partial);
+  GDN_CHECK_LAUNCH();
+  finish_kernel<<<1, 256, 0, as_stream(s)>>>(partial, blocks, 1.0 / (double)n, 0.0, loss, 0);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_l1(const float* a, const float* b, long long n, float* loss, int loss_accumulate, float* grad, float gscale, int accumulate, void* ws, gdn_stream_t s) {
+  GDN_CHECK_ARG(a && b && loss && ws && n > 0);
+  int blocks = red_blocks(n);
+  double* partial = reinterpret_cast<double*>(ws);
+  pair_loss_kernel<1><<<blocks, 256, 0, as_stream(s)>>>(a, b, n, grad, gscale / (float)n, accumulate, partial);
+  GDN_CHECK_LAUNCH();
+  finish_kernel<<<1, 256, 0, as_stream(s)>>>(partial, blocks, 1.0 / (double)n, 0.0, loss, loss_accumulate);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_tv(const float* x, int B, int H, int W, float weight, float* loss, float* grad, float gscale, int accumulate, void* ws, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && loss && ws && B > 0 && H > 1 && W > 1);
+  long long n = (long long)B * H * W;
+  int blocks = red_blocks(n);
+  double* partial = reinterpret_cast<double*>(ws);
+  double count_h = (double)B * (H - 1) * W, count_w = (double)B * H * (W - 1);
+  double kh = (double)weight * 2.0 / count_h / (double)B, kw = (double)weight * 2.0 / count_w / (double)B;
+  tv_kernel<<<blocks, 256, 0, as_stream(s)>>>(x, B, H, W, grad, (float)(2.0 * kh * gscale), (float)(2.0 * kw * gscale), accumulate, partial);
+  GDN_CHECK_LAUNCH();
+  finish_kernel<<<1, 256, 0, as_stream(s)>>>(partial, blocks, kh, kw, loss, 0);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_bce_logits(const float* z, int n, const float* target_ptr, float target, float* loss, float* grad, float gscale, gdn_stream_t s) {
+  GDN_CHECK_ARG(z && loss && n > 0);
+  bce_kernel<<<1, 256, 0, as_stream(s)>>>(z, n, target_ptr, target, loss, grad, gscale);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" size_t gdn_ssim_ws_bytes(int B, int H, int W) { (void)B; (void)H; (void)W; return (size_t)kRedBlocks * kRedSlots * sizeof(double); }
+extern "C" int gdn_ssim(const float* a, const float* b, int B, int H, int W, float* out, void* ws, gdn_stream_t s) {
+  GDN_CHECK_ARG(a && b && out && ws && B > 0 && H > 0 && W > 0);
+  SsimWin win;
+  float sum = 0.f;
+  for (int i = 0; i < 11; ++i) { win.g[i] = expf(-(float)((i - 5) * (i - 5)) / (2.f * 1.5f * 1.5f)); sum += win.g[i]; }
+  for (int i = 0; i < 11; ++i) win.g[i] /= sum;
+  long long ntiles = (long long)B * cdiv(W, ST_W) * cdiv(H, ST_H);
+  int blocks = (int)(ntiles < kRedBlocks ? ntiles : kRedBlocks);
+  double* partial = reinterpret_cast<double*>(ws);
+  ssim_kernel<<<blocks, ST_W * ST_H, 0, as_stream(s)>>>(a, b, B, H, W, win, partial);
+  GDN_CHECK_LAUNCH();
+  finish_kernel<<<1, 256, 0, as_stream(s)>>>(partial, blocks, 1.0 / ((double)B * H * W), 0.0, out, 0);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" int gdn_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd,
+                         int step, float grad_scale, gdn_stream_t s) {
+  GDN_CHECK_ARG(p && g && m && v && n > 0 && step >= 1);
+  AdamP a;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = wd; a.grad_scale = grad_scale;
+  double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  a.step_size = (float)((double)lr / bc1);
+  a.bc2_sqrt = (float)sqrt(bc2);
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  cudaStream_t st = as_stream(s);
+  if (n % 4 == 0 && al(p) && al(g) && al(m) && al(v)) {
+    long long nv = n / 4;
+    int blocks = (int)(cdiv(nv, 256) < 16 * kNumSMs ? cdiv(nv, 256) : 16 * kNumSMs);
+    adamw_kernel<4><<<blocks, 256, 0, st>>>(p, g, m, v, n, a);
+  } else {
+    int blocks = (int)(cdiv(n, 256) < 16 * kNumSMs ? cdiv(n, 256) : 16 * kNumSMs);
+    adamw_kernel<1><<<blocks, 256, 0, st>>>(p, g, m, v, n, a);
+  }
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}

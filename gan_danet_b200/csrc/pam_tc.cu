@@ -1,0 +1,424 @@
+// Position-attention core as ONE fused flash-style kernel for sm_100a:
+//   TMA (cp.async.bulk.tensor) -> shared memory -> tcgen05.mma (kind::f16, fp32 accumulate in TMEM) -> online softmax
+//   on tcgen05.ld'ed score tiles -> P (fp16) -> tcgen05.mma P.V -> epilogue  y = gamma * O / l + x,  lse.
+// The N x N attention map of the reference (torch.bmm + softmax + torch.bmm at /root/reference/models/generator.py:115-122)
+// never leaves the SM.
+//
+// One CTA = one sample x one tile of 128 query positions; it walks all N/128 key tiles.
+//   warp 0      : TMA producer for Q and the K ring (4 stages)
+//   warp 3      : TMA producer for the V^T ring (3 stages)
+//   warp 1      : tcgen05.mma issuer (one lane):  S[b] = Q K_j^T   and   O += P_j V_j
+//   warp 2      : TMEM allocator
+//   warps 4-7   : softmax group 0 -- thread = query row, key columns  0..63  of every score tile, O columns 0..95
+//   warps 8-11  : softmax group 1 -- thread = query row, key columns 64..127 of every score tile, O columns 96..191
+// TMEM columns: S0 [0,128) S1 [128,256) (ping-pong so Q.K_{j+1}^T overlaps softmax(j)), O [256,448).
+// The running row maximum is raised lazily (only when a tile exceeds it by > 8 in log2 units, so P <= 256 in fp16)
+// and O is then rescaled in TMEM by the softmax threads themselves; in steady state no rescale happens.
+// Operands: fp16 (bf16 logits are 8x worse), d zero-padded to 32, C zero-padded to 192.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace gdn {
+namespace pamtc {
+
+constexpr int TQ = 128, TK = 128, DPAD = 32, CPAD = 192;
+constexpr int KS = 4, VS = 3;
+constexpr int Q_BYTES = TQ * DPAD * 2;          // 8 KB, 64-byte rows, SWIZZLE_64B
+constexpr int K_BYTES = TK * DPAD * 2;          // 8 KB
+constexpr int V_BLK = CPAD * 128;               // 24 KB: [192 channels][64 keys] fp16, 128-byte rows, SWIZZLE_128B
+constexpr int V_BYTES = 2 * V_BLK;              // keys 0..63 | 64..127
+constexpr int P_BLK = TQ * 128;                 // 16 KB: [128 rows][64 keys] fp16
+constexpr int P_BYTES = 2 * P_BLK;
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + Q_BYTES;
+constexpr int OFF_V = OFF_K + KS * K_BYTES;     // 40960 (1024-aligned)
+constexpr int OFF_P = OFF_V + VS * V_BYTES;     // 188416
+constexpr int OFF_BAR = OFF_P + P_BYTES;        // 221184
+constexpr int OFF_HM = OFF_BAR + 256;           // float [2][2][128]
+constexpr int OFF_LS = OFF_HM + 2 * 2 * 128 * 4; // float [2][128]
+constexpr int OFF_TMEM = OFF_LS + 2 * 128 * 4;  // uint32 tmem base
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024; // + alignment slack
+constexpr int NTHREADS = 384;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr float RESCALE_TAU = 8.f;
+
+// barrier slots (8 bytes each) inside OFF_BAR
+enum { BAR_Q = 0, BAR_KFULL = 1, BAR_KEMPTY = BAR_KFULL + KS, BAR_VFULL = BAR_KEMPTY + KS, BAR_VEMPTY = BAR_VFULL + VS,
+       BAR_SFULL = BAR_VEMPTY + VS, BAR_PFULL = BAR_SFULL + 2, BAR_PVDONE = BAR_PFULL + 1, BAR_COUNT = BAR_PVDONE + 1 };
+static_assert(BAR_COUNT * 8 <= 256, "barrier area");
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) { printf("pam_tc: mbarrier timeout bar=%u parity=%u block=%d thread=%d\n", bar, parity, blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+#define TM_REGS32(v) \
+  v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], v[17], v[18], v[19], v[20], v[21], v[22], \
+      v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets TMEM lane (lane_base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+        "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO | SBO | version 1 | swizzle
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
+}
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
+// kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+struct FwdParams {
+  const float* x; int x_pitch; const float* gamma;
+  float* o; float* y; int y_pitch; float* lse;
+  int B, N, C, tiles_per_sample;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sample = blockIdx.x / p.tiles_per_sample, qtile = blockIdx.x % p.tiles_per_sample;
+  const int T = p.N / TK;
+  auto bar = [&](int i) { return base + OFF_BAR + 8 * i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + OFF_TMEM);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(BAR_Q), 1);
+    for (int i = 0; i < KS; ++i) { mbar_init(bar(BAR_KFULL + i), 1); mbar_init(bar(BAR_KEMPTY + i), 1); }
+    for (int i = 0; i < VS; ++i) { mbar_init(bar(BAR_VFULL + i), 1); mbar_init(bar(BAR_VEMPTY + i), 1); }
+    mbar_init(bar(BAR_SFULL), 1); mbar_init(bar(BAR_SFULL + 1), 1);
+    mbar_init(bar(BAR_PFULL), 256);
+    mbar_init(bar(BAR_PVDONE), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + OFF_TMEM), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- Q + K producer
+      mbar_expect_tx(bar(BAR_Q), Q_BYTES);
+      tma_load_2d(base + OFF_Q, &mapQ, bar(BAR_Q), 0, sample * p.N + qtile * TQ);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % KS;
+        if (j >= KS) mbar_wait(bar(BAR_KEMPTY + st), ((j / KS) - 1) & 1);
+        mbar_expect_tx(bar(BAR_KFULL + st), K_BYTES);
+        tma_load_2d(base + OFF_K + st * K_BYTES, &mapK, bar(BAR_KFULL + st), 0, sample * p.N + j * TK);
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {   // ---- V^T producer
+      for (int j = 0; j < T; ++j) {
+        const int st = j % VS;
+        if (j >= VS) mbar_wait(bar(BAR_VEMPTY + st), ((j / VS) - 1) & 1);
+        mbar_expect_tx(bar(BAR_VFULL + st), V_BYTES);
+        tma_load_2d(base + OFF_V + st * V_BYTES, &mapV, bar(BAR_VFULL + st), j * TK, sample * CPAD);
+        tma_load_2d(base + OFF_V + st * V_BYTES + V_BLK, &mapV, bar(BAR_VFULL + st), j * TK + 64, sample * CPAD);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---- MMA issuer
+      constexpr uint32_t IDESC_QK = idesc_f16(TQ, TK), IDESC_PV = idesc_f16(TQ, CPAD);
+      auto issue_qk = [&](int j) {
+        const int st = j % KS;
+        mbar_wait(bar(BAR_KFULL + st), (j / KS) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < DPAD / 16; ++ks) {
+          uint64_t ad = smem_desc(base + OFF_Q + ks * 32, 512, LAYOUT_SW64);
+          uint64_t bd = smem_desc(base + OFF_K + st * K_BYTES + ks * 32, 512, LAYOUT_SW64);
+          umma_f16(tmem + (j & 1) * TK, ad, bd, IDESC_QK, ks > 0);
+        }
+        tc_commit(bar(BAR_KEMPTY + st));
+        tc_commit(bar(BAR_SFULL + (j & 1)));
+      };
+      mbar_wait(bar(BAR_Q), 0);
+      issue_qk(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_qk(j + 1);
+        const int st = j % VS;
+        mbar_wait(bar(BAR_PFULL), j & 1);
+        mbar_wait(bar(BAR_VFULL + st), (j / VS) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < TK / 16; ++ks) {
+          uint64_t ad = smem_desc(base + OFF_P + (ks >> 2) * P_BLK + (ks & 3) * 32, 1024, LAYOUT_SW128);
+          uint64_t bd = smem_desc(base + OFF_V + st * V_BYTES + (ks >> 2) * V_BLK + (ks & 3) * 32, 1024, LAYOUT_SW128);
+          umma_f16(tmem + 2 * TK, ad, bd, IDESC_PV, (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc_commit(bar(BAR_VEMPTY + st));
+        tc_commit(bar(BAR_PVDONE));
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- softmax groups
+    const int wg = (warp - 4) >> 2;                 // 0: key columns 0..63, 1: 64..127
+    const int row = (warp & 3) * 32 + lane;         // TMEM lane == query row of the tile
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    float* hm = reinterpret_cast<float*>(sm + OFF_HM);
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1;
+      mbar_wait(bar(BAR_SFULL + b), (j >> 1) & 1);
+      tc_fence_after();
+      float s[64];
+      tmem_ld32(tmem + lane_addr + b * TK + wg * 64, s);
+      tmem_ld32(tmem + lane_addr + b * TK + wg * 64 + 32, s + 32);
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int i = 4; i < 64; i += 4) { mx0 = fmaxf(mx0, s[i]); mx1 = fmaxf(mx1, s[i + 1]); mx2 = fmaxf(mx2, s[i + 2]); mx3 = fmaxf(mx3, s[i + 3]); }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      hm[(b * 2 + wg) * 128 + row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mt = fmaxf(mx, hm[(b * 2 + (wg ^ 1)) * 128 + row]) * LOG2E;
+      bool waited_pv = false;
+      if (j == 0) {
+        m_ref = mt;
+      } else {
+        const bool changed = mt > m_ref + RESCALE_TAU;
+        if (__any_sync(0xffffffffu, changed)) {
+          // raise the reference maximum: rescale this group's half of O (after P_{j-1} V_{j-1} has landed)
+          const float m_new = changed ? mt : m_ref;
+          const float f = ex2(m_ref - m_new);
+          mbar_wait(bar(BAR_PVDONE), (j - 1) & 1);
+          waited_pv = true;
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < CPAD / 2; c += 32) {
+            float ov[32];
+            const uint32_t ta = tmem + lane_addr + 2 * TK + wg * (CPAD / 2) + c;
+            tmem_ld32(ta, ov);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] *= f;
+            tmem_st32(ta, ov);
+          }
+          tmem_wait_st();
+          l *= f;
+          m_ref = m_new;
+        }
+      }
+      // P = exp2(S*log2e - m_ref), fp16; row-sum in fp32
+      uint32_t packed[32];
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        float p0 = ex2(fmaf(s[i], LOG2E, -m_ref)), p1 = ex2(fmaf(s[i + 1], LOG2E, -m_ref));
+        l0 += p0; l1 += p1;
+        __half2 h = __floats2half2_rn(p0, p1);
+        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      l += l0 + l1;
+      if (j > 0 && !waited_pv) mbar_wait(bar(BAR_PVDONE), (j - 1) & 1);   // P buffer free again
+      // K-major SWIZZLE_128B tile: row r at r*128 B inside 1024-B groups of 8 rows, 16-B chunk index XOR (r & 7)
+      uint8_t* prow = sm + OFF_P + wg * P_BLK + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = val;
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar(BAR_PFULL));
+    }
+    // ---- epilogue: o = O / l, y = gamma*o + x, lse
+    float* ls = reinterpret_cast<float*>(sm + OFF_LS);
+    ls[wg * 128 + row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float ltot = l + ls[(wg ^ 1) * 128 + row];
+    const float inv = 1.f / ltot;
+    mbar_wait(bar(BAR_PVDONE), (T - 1) & 1);
+    tc_fence_after();
+    const float g = __ldg(p.gamma);
+    const size_t grow = (size_t)sample * p.N + (size_t)qtile * TQ + row;
+    if (wg == 0) p.lse[grow] = (m_ref + log2f(ltot)) * LN2;
+#pragma unroll 1
+    for (int c = 0; c < CPAD / 2; c += 32) {
+      float ov[32];
+      const int c0 = wg * (CPAD / 2) + c;
+      tmem_ld32(tmem + lane_addr + 2 * TK + c0, ov);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const int ch = c0 + i;
+        if (ch < p.C) {   // C is a multiple of 4 on this path (checked on the host)
+          float4 on = make_float4(ov[i] * inv, ov[i + 1] * inv, ov[i + 2] * inv, ov[i + 3] * inv);
+          float4 xv = *reinterpret_cast<const float4*>(p.x + grow * p.x_pitch + ch);
+          *reinterpret_cast<float4*>(p.o + grow * p.C + ch) = on;
+          *reinterpret_cast<float4*>(p.y + grow * p.y_pitch + ch) = make_float4(fmaf(g, on.x, xv.x), fmaf(g, on.y, xv.y), fmaf(g, on.z, xv.z), fmaf(g, on.w, xv.w));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ---- operand packing: fp32 NHWC slices -> fp16 tensor-core operands
+__global__ void __launch_bounds__(256) pack_qk_kernel(const float* __restrict__ src, int pitch, int d, __half* __restrict__ dst, long long rows) {
+  const long long total = rows * DPAD;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx / DPAD; int c = (int)(idx % DPAD);
+    dst[idx] = __float2half_rn(c < d ? src[(size_t)r * pitch + c] : 0.f);
+  }
+}
+// V [B][N][C] (pitch) -> V^T fp16 [B][CPAD][N], zero rows for c >= C
+__global__ void __launch_bounds__(256) pack_vt_kernel(const float* __restrict__ v, int pitch, int C, int N, __half* __restrict__ vt) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    int n = n0 + i, c = c0 + tx;
+    tile[i][tx] = (n < N && c < C) ? v[((size_t)b * N + n) * pitch + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int c = c0 + i, n = n0 + tx;
+    if (c < CPAD && n < N) vt[((size_t)b * CPAD + c) * N + n] = __float2half_rn(tile[tx][i]);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// 2-D fp16 row-major tensor [rows][cols]; box = [box_rows][box_cols]
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("pam_tc: cuTensorMapEncodeTiled unavailable"); return GDN_ECUDA; }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("pam_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return GDN_ECUDA; }
+  return GDN_OK;
+}
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+}  // namespace pamtc
+}  // namespace gdn
+
+using namespace gdn;
+using namespace gdn::pamtc;
+
+extern "C" int gdn_pam_tc_init(void) {
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return GDN_OK;
+}
+
+extern "C" size_t gdn_pam_tc_fwd_ws_bytes(const gdn_pam_fwd_args* a) {
+  size_t rows = (size_t)a->B * a->N;
+  return 2 * align256(rows * DPAD * 2) + align256((size_t)a->B * CPAD * a->N * 2);
+}
+
+extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
+  GDN_CHECK_ARG(a->precision == GDN_PREC_FP16);
+  GDN_CHECK_ARG(a->N % TK == 0 && a->d <= DPAD && a->C <= CPAD && a->C % 4 == 0);
+  GDN_CHECK_ARG(a->x_pitch % 4 == 0 && a->y_pitch % 4 == 0);
+  GDN_CHECK_ARG(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->y & 15) == 0 && ((uintptr_t)a->o & 15) == 0);
+  if (!a->ws || a->ws_bytes < gdn_pam_tc_fwd_ws_bytes(a)) { set_error("gdn_pam_fwd(fp16): workspace too small"); return GDN_EWORKSPACE; }
+  const size_t rows = (size_t)a->B * a->N;
+  char* w = reinterpret_cast<char*>(a->ws);
+  __half* Qh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
+  __half* Kh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
+  __half* Vt = reinterpret_cast<__half*>(w);
+  cudaStream_t st = as_stream(s);
+  const int pg = (int)(cdiv((long long)rows * DPAD, 256) < 16 * kNumSMs ? cdiv((long long)rows * DPAD, 256) : 16 * kNumSMs);
+  pack_qk_kernel<<<pg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, Qh, (long long)rows);
+  GDN_CHECK_LAUNCH();
+  pack_qk_kernel<<<pg, 256, 0, st>>>(a->k, a->qk_pitch, a->d, Kh, (long long)rows);
+  GDN_CHECK_LAUNCH();
+  dim3 tg((unsigned)cdiv(a->N, 32), CPAD / 32, (unsigned)a->B);
+  pack_vt_kernel<<<tg, 256, 0, st>>>(a->v, a->v_pitch, a->C, a->N, Vt);
+  GDN_CHECK_LAUNCH();
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_map(&mq, Qh, rows, DPAD, TQ, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
+  if ((rc = make_map(&mk, Kh, rows, DPAD, TK, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
+  if ((rc = make_map(&mv, Vt, (uint64_t)a->B * CPAD, (uint64_t)a->N, CPAD, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  FwdParams p;
+  p.x = a->x; p.x_pitch = a->x_pitch; p.gamma = a->gamma; p.o = a->o; p.y = a->y; p.y_pitch = a->y_pitch; p.lse = a->lse;
+  p.B = a->B; p.N = a->N; p.C = a->C; p.tiles_per_sample = a->N / TQ;
+  pam_flash_fwd_kernel<<<a->B * p.tiles_per_sample, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" size_t gdn_pam_tc_bwd_ws_bytes(const gdn_pam_bwd_args* a) { (void)a; return 0; }
+extern "C" int gdn_pam_tc_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s) {
+  (void)a; (void)s;
+  set_error("gdn_pam_bwd: tensor-core backward not built yet; use GDN_PREC_FP32");
+  return GDN_EINVAL;
+}

@@ -1,0 +1,325 @@
+// Resampling kernels (NHWC fp32, HBM/L2-bound gathers; backward passes are atomics-free gathers => deterministic).
+// Reference call sites: nn.Upsample(scale_factor=2, mode='bicubic', align_corners=False) at
+// /root/reference/models/generator.py:221,225; F.interpolate(size=..., mode='bilinear') at generator.py:244;
+// F.interpolate(scale_factor=0.5|0.25, mode='bicubic') at GAN_DANet_train.ipynb:226,231; MaxPool2d(2,2) of
+// torchvision vgg19.features used by models/losses.py:58.
+// Semantics: source index (dst+0.5)*ratio-0.5, cubic A=-0.75 with border-clamped taps,
+// bilinear source clamped at 0.
+#include "common.cuh"
+
+namespace gdn {
+
+__device__ __forceinline__ void cubic_coeffs(float t, float w[4]) {
+  const float A = -0.75f;
+  float u = t + 1.f;  w[0] = ((A * u - 5.f * A) * u + 8.f * A) * u - 4.f * A;
+  u = t;              w[1] = ((A + 2.f) * u - (A + 3.f)) * u * u + 1.f;
+  u = 1.f - t;        w[2] = ((A + 2.f) * u - (A + 3.f)) * u * u + 1.f;
+  u = 2.f - t;        w[3] = ((A * u - 5.f * A) * u + 8.f * A) * u - 4.f * A;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// source position of output o for ratio = in/out (or 1/scale_factor)
+__device__ __forceinline__ void cubic_src(int o, float ratio, int& i0, float& t) {
+  float s = (o + 0.5f) * ratio - 0.5f;
+  float f = floorf(s);
+  i0 = (int)f; t = s - f;
+}
+__device__ __forceinline__ void linear_src(int o, float ratio, int n_in, int& i0, int& i1, float& t) {
+  float s = (o + 0.5f) * ratio - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s; if (i0 > n_in - 1) i0 = n_in - 1;
+  i1 = i0 + 1 < n_in ? i0 + 1 : n_in - 1;
+  t = s - (float)i0;
+}
+
+// ------------------------------------------------------------------ bicubic x2 up-sampling
+template <int VEC>
+__global__ void __launch_bounds__(256) bicubic_up2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Cv = C / VEC, Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)B * Ho * Wo * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % Cv) * VEC; long long r = idx / Cv;
+    int ox = (int)(r % Wo); r /= Wo; int oy = (int)(r % Ho); int b = (int)(r / Ho);
+    int y0, x0; float ty, tx, wy[4], wx[4];
+    cubic_src(oy, 0.5f, y0, ty); cubic_src(ox, 0.5f, x0, tx);
+    cubic_coeffs(ty, wy); cubic_coeffs(tx, wx);
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int iy = clampi(y0 - 1 + i, 0, H - 1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int ix = clampi(x0 - 1 + j, 0, W - 1);
+        const float* p = x + (((size_t)b * H + iy) * W + ix) * C + c;
+        float wgt = wy[i] * wx[j];
+        if (VEC == 4) { float4 q = *reinterpret_cast<const float4*>(p); acc[0] = fmaf(wgt, q.x, acc[0]); acc[1] = fmaf(wgt, q.y, acc[1]); acc[2] = fmaf(wgt, q.z, acc[2]); acc[3] = fmaf(wgt, q.w, acc[3]); }
+        else acc[0] = fmaf(wgt, *p, acc[0]);
+      }
+    }
+    float* o = y + (((size_t)b * Ho + oy) * Wo + ox) * C + c;
+    if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else *o = acc[0];
+  }
+}
+
+// total weight with which output o (of 2n outputs) reads input i (border clamping folds several taps onto one input)
+__device__ __forceinline__ float cubic_up2_weight(int o, int i, int n) {
+  int i0; float t, w[4];
+  cubic_src(o, 0.5f, i0, t); cubic_coeffs(t, w);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (clampi(i0 - 1 + k, 0, n - 1) == i) s += w[k];
+  return s;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) bicubic_up2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
+  const int Cv = C / VEC, Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)B * H * W * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % Cv) * VEC; long long r = idx / Cv;
+    int ix = (int)(r % W); r /= W; int iy = (int)(r % H); int b = (int)(r / H);
+    float wy[8], wx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int oy = 2 * iy - 3 + k, ox = 2 * ix - 3 + k;
+      wy[k] = (oy >= 0 && oy < Ho) ? cubic_up2_weight(oy, iy, H) : 0.f;
+      wx[k] = (ox >= 0 && ox < Wo) ? cubic_up2_weight(ox, ix, W) : 0.f;
+    }
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (wy[i] == 0.f) continue;
+      int oy = 2 * iy - 3 + i;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (wx[j] == 0.f) continue;
+        int ox = 2 * ix - 3 + j;
+        const float* p = dy + (((size_t)b * Ho + oy) * Wo + ox) * C + c;
+        float wgt = wy[i] * wx[j];
+        if (VEC == 4) { float4 q = *reinterpret_cast<const float4*>(p); acc[0] = fmaf(wgt, q.x, acc[0]); acc[1] = fmaf(wgt, q.y, acc[1]); acc[2] = fmaf(wgt, q.z, acc[2]); acc[3] = fmaf(wgt, q.w, acc[3]); }
+        else acc[0] = fmaf(wgt, *p, acc[0]);
+      }
+    }
+    float* o = dx + (((size_t)b * H + iy) * W + ix) * C + c;
+    if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else *o = acc[0];
+  }
+}
+
+// ------------------------------------------------------------------ bilinear resize to (Ho, Wo)
+template <int VEC>
+__global__ void __launch_bounds__(256) bilinear_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                                                            float ry, float rx, int accumulate) {
+  const int Cv = C / VEC;
+  const long long total = (long long)B * Ho * Wo * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % Cv) * VEC; long long r = idx / Cv;
+    int ox = (int)(r % Wo); r /= Wo; int oy = (int)(r % Ho); int b = (int)(r / Ho);
+    int y0, y1, x0, x1; float ty, tx;
+    linear_src(oy, ry, Hi, y0, y1, ty); linear_src(ox, rx, Wi, x0, x1, tx);
+    const float w00 = (1.f - ty) * (1.f - tx), w01 = (1.f - ty) * tx, w10 = ty * (1.f - tx), w11 = ty * tx;
+    const float* base = x + (size_t)b * Hi * Wi * C + c;
+    const float* p00 = base + ((size_t)y0 * Wi + x0) * C; const float* p01 = base + ((size_t)y0 * Wi + x1) * C;
+    const float* p10 = base + ((size_t)y1 * Wi + x0) * C; const float* p11 = base + ((size_t)y1 * Wi + x1) * C;
+    float* o = y + (((size_t)b * Ho + oy) * Wo + ox) * C + c;
+    if (VEC == 4) {
+      float4 a = *reinterpret_cast<const float4*>(p00), bb = *reinterpret_cast<const float4*>(p01);
+      float4 cc = *reinterpret_cast<const float4*>(p10), d = *reinterpret_cast<const float4*>(p11);
+      float4 rr;
+      rr.x = w00 * a.x + w01 * bb.x + w10 * cc.x + w11 * d.x; rr.y = w00 * a.y + w01 * bb.y + w10 * cc.y + w11 * d.y;
+      rr.z = w00 * a.z + w01 * bb.z + w10 * cc.z + w11 * d.z; rr.w = w00 * a.w + w01 * bb.w + w10 * cc.w + w11 * d.w;
+      if (accumulate) { float4 q = *reinterpret_cast<float4*>(o); rr.x += q.x; rr.y += q.y; rr.z += q.z; rr.w += q.w; }
+      *reinterpret_cast<float4*>(o) = rr;
+    } else {
+      float rr = w00 * *p00 + w01 * *p01 + w10 * *p10 + w11 * *p11;
+      if (accumulate) rr += *o;
+      *o = rr;
+    }
+  }
+}
+
+__device__ __forceinline__ float linear_weight(int o, int i, float ratio, int n_in) {
+  int i0, i1; float t;
+  linear_src(o, ratio, n_in, i0, i1, t);
+  float s = 0.f;
+  if (i0 == i) s += 1.f - t;
+  if (i1 == i) s += t;
+  return s;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                                                            float ry, float rx, int accumulate) {
+  const int Cv = C / VEC;
+  const long long total = (long long)B * Hi * Wi * Cv;
+  const float iry = 1.f / ry, irx = 1.f / rx;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % Cv) * VEC; long long r = idx / Cv;
+    int ix = (int)(r % Wi); r /= Wi; int iy = (int)(r % Hi); int b = (int)(r / Hi);
+    // outputs whose source lies in (i-1, i+1): o in ((i-0.5)/ratio-0.5, (i+1.5)/ratio-0.5); widen by one and test exactly
+    int oy_lo = (int)floorf((iy - 0.5f) * iry - 0.5f) - 1, oy_hi = (int)ceilf((iy + 1.5f) * iry - 0.5f) + 1;
+    int ox_lo = (int)floorf((ix - 0.5f) * irx - 0.5f) - 1, ox_hi = (int)ceilf((ix + 1.5f) * irx - 0.5f) + 1;
+    if (iy == 0) oy_lo = 0;          // the source clamp at 0 folds every earlier output onto row 0
+    if (ix == 0) ox_lo = 0;
+    oy_lo = oy_lo < 0 ? 0 : oy_lo; ox_lo = ox_lo < 0 ? 0 : ox_lo;
+    oy_hi = oy_hi > Ho - 1 ? Ho - 1 : oy_hi; ox_hi = ox_hi > Wo - 1 ? Wo - 1 : ox_hi;
+    if (iy == Hi - 1) oy_hi = Ho - 1;  // and the i1 clamp folds the tail onto the last row
+    if (ix == Wi - 1) ox_hi = Wo - 1;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      float wy = linear_weight(oy, iy, ry, Hi);
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        float wx = linear_weight(ox, ix, rx, Wi);
+        if (wx == 0.f) continue;
+        const float* p = dy + (((size_t)b * Ho + oy) * Wo + ox) * C + c;
+        float wgt = wy * wx;
+        if (VEC == 4) { float4 q = *reinterpret_cast<const float4*>(p); acc[0] = fmaf(wgt, q.x, acc[0]); acc[1] = fmaf(wgt, q.y, acc[1]); acc[2] = fmaf(wgt, q.z, acc[2]); acc[3] = fmaf(wgt, q.w, acc[3]); }
+        else acc[0] = fmaf(wgt, *p, acc[0]);
+      }
+    }
+    float* o = dx + (((size_t)b * Hi + iy) * Wi + ix) * C + c;
+    if (VEC == 4) {
+      float4 rr = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      if (accumulate) { float4 q = *reinterpret_cast<float4*>(o); rr.x += q.x; rr.y += q.y; rr.z += q.z; rr.w += q.w; }
+      *reinterpret_cast<float4*>(o) = rr;
+    } else {
+      float rr = acc[0];
+      if (accumulate) rr += *o;
+      *o = rr;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ bicubic 1/f down-sampling, NCHW -> NHWC slice
+__global__ void __launch_bounds__(256) bicubic_down_kernel(const float* __restrict__ x, float* __restrict__ y, int y_pitch, int B, int C, int Hi, int Wi,
+                                                            int Ho, int Wo, float ratio) {
+  const long long total = (long long)B * C * Ho * Wo;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int ox = (int)(idx % Wo); long long r = idx / Wo;
+    int oy = (int)(r % Ho); r /= Ho; int c = (int)(r % C); int b = (int)(r / C);
+    int y0, x0; float ty, tx, wy[4], wx[4];
+    cubic_src(oy, ratio, y0, ty); cubic_src(ox, ratio, x0, tx);
+    cubic_coeffs(ty, wy); cubic_coeffs(tx, wx);
+    const float* plane = x + ((size_t)b * C + c) * Hi * Wi;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int iy = clampi(y0 - 1 + i, 0, Hi - 1);
+      float rowacc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rowacc = fmaf(wx[j], __ldg(plane + (size_t)iy * Wi + clampi(x0 - 1 + j, 0, Wi - 1)), rowacc);
+      acc = fmaf(wy[i], rowacc, acc);
+    }
+    y[(((size_t)b * Ho + oy) * Wo + ox) * y_pitch + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ 2x2/2 max pooling
+template <int VEC>
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Cv = C / VEC, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % Cv) * VEC; long long r = idx / Cv;
+    int ox = (int)(r % Wo); r /= Wo; int oy = (int)(r % Ho); int b = (int)(r / Ho);
+    const float* p = x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + c;
+    float* o = y + (((size_t)b * Ho + oy) * Wo + ox) * C + c;
+    if (VEC == 4) {
+      float4 a = *reinterpret_cast<const float4*>(p), bb = *reinterpret_cast<const float4*>(p + C);
+      float4 cc = *reinterpret_cast<const float4*>(p + (size_t)W * C), d = *reinterpret_cast<const float4*>(p + (size_t)W * C + C);
+      *reinterpret_cast<float4*>(o) = make_float4(fmaxf(fmaxf(a.x, bb.x), fmaxf(cc.x, d.x)), fmaxf(fmaxf(a.y, bb.y), fmaxf(cc.y, d.y)),
+                                                  fmaxf(fmaxf(a.z, bb.z), fmaxf(cc.z, d.z)), fmaxf(fmaxf(a.w, bb.w), fmaxf(cc.w, d.w)));
+    } else {
+      *o = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(size_t)W * C], p[(size_t)W * C + C]));
+    }
+  }
+}
+// gradient goes to the first maximum in scan order (ATen max_pool2d backward)
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * H * W * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C); long long r = idx / C;
+    int ix = (int)(r % W); r /= W; int iy = (int)(r % H); int b = (int)(r / H);
+    int oy = iy >> 1, ox = ix >> 1;
+    float g = 0.f;
+    if (oy < Ho && ox < Wo) {
+      const float* p = x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + c;
+      float v[4] = {p[0], p[C], p[(size_t)W * C], p[(size_t)W * C + C]};
+      int arg = 0; float m = v[0];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) if (v[k] > m) { m = v[k]; arg = k; }
+      if (arg == ((iy & 1) * 2 + (ix & 1))) g = dy[(((size_t)b * Ho + oy) * Wo + ox) * C + c];
+    }
+    dx[idx] = g;
+  }
+}
+
+static inline int grid_for(long long total) {
+  long long b = cdiv(total, 256);
+  return (int)(b < 16 * kNumSMs ? (b > 0 ? b : 1) : 16 * kNumSMs);
+}
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+}  // namespace gdn
+
+using namespace gdn;
+
+extern "C" int gdn_bicubic_up2_fwd(const float* x, float* y, int B, int H, int W, int C, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0);
+  if (C % 4 == 0 && al16(x) && al16(y)) bicubic_up2_fwd_kernel<4><<<grid_for((long long)B * 4 * H * W * (C / 4)), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
+  else bicubic_up2_fwd_kernel<1><<<grid_for((long long)B * 4 * H * W * C), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_bicubic_up2_bwd(const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s) {
+  GDN_CHECK_ARG(dy && dx && B > 0 && H > 0 && W > 0 && C > 0);
+  if (C % 4 == 0 && al16(dy) && al16(dx)) bicubic_up2_bwd_kernel<4><<<grid_for((long long)B * H * W * (C / 4)), 256, 0, as_stream(s)>>>(dy, dx, B, H, W, C);
+  else bicubic_up2_bwd_kernel<1><<<grid_for((long long)B * H * W * C), 256, 0, as_stream(s)>>>(dy, dx, B, H, W, C);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_bilinear_fwd(const float* x, float* y, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && y && B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0);
+  float ry = (float)Hi / (float)Ho, rx = (float)Wi / (float)Wo;
+  if (C % 4 == 0 && al16(x) && al16(y)) bilinear_fwd_kernel<4><<<grid_for((long long)B * Ho * Wo * (C / 4)), 256, 0, as_stream(s)>>>(x, y, B, Hi, Wi, Ho, Wo, C, ry, rx, accumulate);
+  else bilinear_fwd_kernel<1><<<grid_for((long long)B * Ho * Wo * C), 256, 0, as_stream(s)>>>(x, y, B, Hi, Wi, Ho, Wo, C, ry, rx, accumulate);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_bilinear_bwd(const float* dy, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s) {
+  GDN_CHECK_ARG(dy && dx && B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0);
+  float ry = (float)Hi / (float)Ho, rx = (float)Wi / (float)Wo;
+  if (C % 4 == 0 && al16(dy) && al16(dx)) bilinear_bwd_kernel<4><<<grid_for((long long)B * Hi * Wi * (C / 4)), 256, 0, as_stream(s)>>>(dy, dx, B, Hi, Wi, Ho, Wo, C, ry, rx, accumulate);
+  else bilinear_bwd_kernel<1><<<grid_for((long long)B * Hi * Wi * C), 256, 0, as_stream(s)>>>(dy, dx, B, Hi, Wi, Ho, Wo, C, ry, rx, accumulate);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_bicubic_down_nchw_to_nhwc(const float* x, float* y, int y_pitch, int y_c0, int B, int C, int Hi, int Wi, int f, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && y && B > 0 && C > 0 && Hi > 0 && Wi > 0 && (f == 2 || f == 4) && y_pitch >= y_c0 + C);
+  int Ho = Hi / f, Wo = Wi / f;   // floor(in * 1/f)
+  GDN_CHECK_ARG(Ho > 0 && Wo > 0);
+  bicubic_down_kernel<<<grid_for((long long)B * C * Ho * Wo), 256, 0, as_stream(s)>>>(x, y + y_c0, y_pitch, B, C, Hi, Wi, Ho, Wo, (float)f);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && y && B > 0 && H >= 2 && W >= 2 && C > 0);
+  if (C % 4 == 0 && al16(x) && al16(y)) maxpool2_fwd_kernel<4><<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 4)), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
+  else maxpool2_fwd_kernel<1><<<grid_for((long long)B * (H / 2) * (W / 2) * C), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && dy && dx && B > 0 && H >= 2 && W >= 2 && C > 0);
+  maxpool2_bwd_kernel<<<grid_for((long long)B * H * W * C), 256, 0, as_stream(s)>>>(x, dy, dx, B, H, W, C);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}

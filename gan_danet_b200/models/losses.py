@@ -1,0 +1,347 @@
+"""Loss functions of GAN-DANet on the B200 kernels (reference ``models/losses.py:13-150``).
+
+``TVLoss``, ``SSIM`` and ``PerceptualLoss`` keep the reference constructor signatures.  ``MSELoss`` and
+``BCEWithLogitsLoss`` are kernel-backed stand-ins for the ``torch.nn`` losses the training notebook builds at
+``GAN_DANet_train.ipynb:190-191``.  Every loss evaluates value and input-gradient in a single pass; autograd's upstream
+scalar is applied with ``gdn_scale_dev`` (device scalar, no host sync).
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Dict, List, Optional, Sequence, Set, Tuple
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .. import engine as E
+from .._lib import ACT_NONE, ACT_RELU
+
+
+def _scale_by(g: torch.Tensor, scalar: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(g)
+    s = scalar.reshape(1).to(torch.float32).contiguous()
+    L.check(E._lib(g).gdn_scale_dev(g.data_ptr(), s.data_ptr(), out.data_ptr(), g.numel(), 0, E._stream()), "gdn_scale_dev")
+    return out
+
+
+class _PairLoss(torch.autograd.Function):
+    """mean((a-b)^2) (mode 0) or mean|a-b| (mode 1); gradient w.r.t. both arguments."""
+
+    @staticmethod
+    def forward(ctx, a: torch.Tensor, b: torch.Tensor, mode: int):
+        a_c, b_c = a.detach().contiguous(), b.detach().contiguous()
+        lib = E._lib(a_c)
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        grad = torch.empty_like(a_c) if need else None
+        ws = E.dot_ws(a.device)
+        if mode == 0:
+            L.check(lib.gdn_mse(a_c.data_ptr(), b_c.data_ptr(), a_c.numel(), loss.data_ptr(), E._ptr(grad), 1.0, 0, ws.data_ptr(), E._stream()), "gdn_mse")
+        else:
+            L.check(lib.gdn_l1(a_c.data_ptr(), b_c.data_ptr(), a_c.numel(), loss.data_ptr(), 0, E._ptr(grad), 1.0, 0, ws.data_ptr(), E._stream()), "gdn_l1")
+        ctx.grad = grad
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dout):
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = _scale_by(ctx.grad, dout)
+        if ctx.needs_input_grad[1]:
+            gb = _scale_by(ctx.grad, -dout)
+        return ga, gb, None
+
+
+class MSELoss(nn.Module):
+    """nn.MSELoss() (mean), GAN_DANet_train.ipynb:191,262."""
+
+    def forward(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        return _PairLoss.apply(a, b, 0)
+
+
+class L1Loss(nn.Module):
+    def forward(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        return _PairLoss.apply(a, b, 1)
+
+
+class _BCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z: torch.Tensor, target: torch.Tensor):
+        zc = z.detach().contiguous()
+        tc = target.detach().to(torch.float32).expand_as(zc).contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=z.device)
+        grad = torch.empty_like(zc) if ctx.needs_input_grad[0] else None
+        L.check(E._lib(zc).gdn_bce_logits(zc.data_ptr(), zc.numel(), tc.data_ptr(), 0.0, loss.data_ptr(), E._ptr(grad), 1.0, E._stream()), "gdn_bce_logits")
+        ctx.grad = grad
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dout):
+        return (_scale_by(ctx.grad, dout) if ctx.needs_input_grad[0] else None), None
+
+
+class BCEWithLogitsLoss(nn.Module):
+    """nn.BCEWithLogitsLoss() (mean), GAN_DANet_train.ipynb:190,252-253,261."""
+
+    def forward(self, z: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return _BCEFn.apply(z, target)
+
+
+class _TVFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: float):
+        xc = x.detach().contiguous()
+        B, Cc, H, W = xc.shape
+        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        # the reference divides by the batch size only (losses.py:87); the kernel treats B*C planes as its batch
+        L.check(E._lib(xc).gdn_tv(xc.data_ptr(), B * Cc, H, W, float(weight) * Cc, loss.data_ptr(), E._ptr(grad), 1.0, 0,
+                                  E.dot_ws(x.device).data_ptr(), E._stream()), "gdn_tv")
+        ctx.grad = grad
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dout):
+        return (_scale_by(ctx.grad, dout) if ctx.needs_input_grad[0] else None), None
+
+
+class TVLoss(nn.Module):
+    """Reference losses.py:76-87."""
+
+    def __init__(self, weight: float = 1.0) -> None:
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return _TVFn.apply(x, self.weight)
+
+
+class SSIM(nn.Module):
+    """Reference losses.py:90-147 (single-scale, 11x11 Gaussian window, sigma 1.5).  Forward only: the training loop
+    evaluates it without adding it to the objective (GAN_DANet_train.ipynb:263 vs :267), so the result is detached."""
+
+    def __init__(self, window_size: int = 11, size_average: bool = True) -> None:
+        super().__init__()
+        if window_size != 11:
+            raise NotImplementedError("the SSIM kernel is specialised for the reference's 11x11 window")
+        self.window_size = window_size
+        self.size_average = size_average
+        self.channel = 1
+        self.register_buffer("window", self._create_window(window_size, self.channel))
+
+    def _gaussian(self, window_size: int, sigma: float) -> torch.Tensor:
+        coords = torch.arange(window_size, dtype=torch.float32)
+        gauss = torch.exp(-((coords - window_size // 2) ** 2) / (2 * sigma ** 2))
+        return (gauss / gauss.sum()).unsqueeze(1)
+
+    def _create_window(self, window_size: int, channel: int) -> torch.Tensor:
+        _1d = self._gaussian(window_size, 1.5)
+        _2d = _1d @ _1d.t()
+        window = _2d.float().unsqueeze(0).unsqueeze(0)
+        return window.expand(channel, 1, window_size, window_size).contiguous()
+
+    def forward(self, img1: torch.Tensor, img2: torch.Tensor) -> torch.Tensor:
+        a, b = img1.detach().contiguous(), img2.detach().contiguous()
+        B, Cc, H, W = a.shape
+        lib = E._lib(a)
+        ws = E.workspace("dot", lib.gdn_ssim_ws_bytes(B * Cc, H, W), a.device)
+        if self.size_average:
+            out = torch.empty(1, dtype=torch.float32, device=a.device)
+            L.check(lib.gdn_ssim(a.data_ptr(), b.data_ptr(), B * Cc, H, W, out.data_ptr(), ws.data_ptr(), E._stream()), "gdn_ssim")
+            return out.reshape(())
+        out = torch.empty(B, dtype=torch.float32, device=a.device)
+        for i in range(B):
+            L.check(lib.gdn_ssim(a[i].data_ptr(), b[i].data_ptr(), Cc, H, W, out[i:i + 1].data_ptr(), ws.data_ptr(), E._stream()), "gdn_ssim")
+        return out
+
+
+# torchvision vgg19.features: conv indices and max-pool indices
+_VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
+
+
+def _make_vgg19_features() -> nn.Sequential:
+    """Architecture of torchvision.models.vgg19().features (conv3x3+ReLU(inplace) / MaxPool2d(2,2)), default-initialised
+    exactly as torchvision does (kaiming_normal_ fan_out, zero bias) when torchvision itself is unavailable."""
+    layers: List[nn.Module] = []
+    cin = 3
+    for v in _VGG_CFG:
+        if v == "M":
+            layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+        else:
+            conv = nn.Conv2d(cin, int(v), kernel_size=3, padding=1)
+            nn.init.kaiming_normal_(conv.weight, mode="fan_out", nonlinearity="relu")
+            nn.init.constant_(conv.bias, 0)
+            layers += [conv, nn.ReLU(inplace=True)]
+            cin = int(v)
+    return nn.Sequential(*layers)
+
+
+class PerceptualLoss(nn.Module):
+    """VGG-based perceptual loss with optional offline weights (reference losses.py:13-73).
+
+    sum over ``feature_layers`` of mean|phi_i(x3) - phi_i(y3)| with phi = vgg19.features, inputs repeated to three
+    channels, no ImageNet normalisation.  VGG is frozen: only the data gradient w.r.t. ``x`` is computed."""
+
+    def __init__(self, feature_layers: Sequence[int] = (1, 6, 11, 20), weights_path: Optional[str] = None, pretrained: bool = True,
+                 device: Optional[torch.device] = None, use_gpu: Optional[bool] = None) -> None:
+        super().__init__()
+        self.feature_layers: Set[int] = set(feature_layers)
+        if not self.feature_layers:
+            raise ValueError("feature_layers must contain at least one index")
+        max_layer = max(self.feature_layers)
+        if device is None:
+            # ``use_gpu=`` is what GAN_DANet_train.ipynb:194 passes (the reference signature rejects it)
+            want_gpu = torch.cuda.is_available() if use_gpu is None else bool(use_gpu)
+            device = torch.device("cuda" if want_gpu and torch.cuda.is_available() else "cpu")
+        self.device = torch.device(device)
+
+        vgg_features = None
+        if weights_path is None and pretrained:
+            try:
+                from torchvision import models
+                vgg_features = models.vgg19(weights=models.VGG19_Weights.DEFAULT).features
+            except Exception:
+                warnings.warn("Falling back to randomly initialised VGG19 features. "
+                              "Pass pretrained=False or provide weights_path to silence this warning.", RuntimeWarning)
+        if vgg_features is None:
+            try:
+                from torchvision import models
+                vgg_features = models.vgg19(weights=None).features
+            except Exception:
+                vgg_features = _make_vgg19_features()
+        if weights_path is not None:
+            state_dict = torch.load(weights_path, map_location=self.device)
+            missing, unexpected = vgg_features.load_state_dict(state_dict, strict=False)
+            if unexpected:
+                warnings.warn(f"Unexpected keys when loading VGG weights: {unexpected}", RuntimeWarning)
+            if missing:
+                warnings.warn(f"Missing keys when loading VGG weights: {missing}", RuntimeWarning)
+        self.vgg = nn.Sequential(*list(vgg_features)[: max_layer + 1]).to(self.device)
+        self.vgg.eval()
+        for param in self.vgg.parameters():
+            param.requires_grad_(False)
+        self._wcache: Dict[Tuple[int, int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def _weights(self, idx: int, conv: nn.Conv2d, cin: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(OHWI, IHWO) kernel operands of a frozen conv; a 1-channel input into conv1_1 uses the channel-summed
+        weight (x.repeat(1,3,1,1) == 1-channel conv with sum_c W[:, c], SURVEY appendix A identity 5)."""
+        key = (idx, cin, conv.weight._version)
+        hit = self._wcache.get(key)
+        if hit is None:
+            w = conv.weight.detach()
+            if cin != w.shape[1]:
+                w = w.sum(dim=1, keepdim=True)      # frozen weights: done once, cached
+            hit = (E.weight_ohwi(w.contiguous()), E.weight_ihwo(w.contiguous()))
+            self._wcache[key] = hit
+        return hit
+
+    def _features(self, tape: E.Tape, x: E.Var, on_feature) -> None:
+        cur = x
+        for idx, layer in enumerate(self.vgg):
+            if isinstance(layer, nn.Conv2d):
+                fuse_relu = idx + 1 < len(self.vgg) and isinstance(self.vgg[idx + 1], nn.ReLU) and idx not in self.feature_layers
+                cur = _frozen_conv(tape, cur, self._weights(idx, layer, cur.t.shape[-1]), layer.bias.detach(), relu=fuse_relu)
+                cur_fused = fuse_relu
+            elif isinstance(layer, nn.ReLU):
+                if not cur_fused:
+                    cur = _relu(tape, cur)
+                cur_fused = False
+            elif isinstance(layer, nn.MaxPool2d):
+                cur = E.op_maxpool2(tape, cur)
+            else:
+                raise NotImplementedError(type(layer))
+            if idx in self.feature_layers:
+                on_feature(idx, cur)
+
+    def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        return _PerceptualFn.apply(self, x, y)
+
+
+def _frozen_conv(tape: E.Tape, x: E.Var, w: Tuple[torch.Tensor, torch.Tensor], bias: torch.Tensor, relu: bool) -> E.Var:
+    w4, wt = w
+    O, kh, kw, _ = w4.shape
+    B, H, W, _ = x.t.shape
+    y = E.Var(E.new_nhwc(B, H, W, O, x.t))
+    act = ACT_RELU if relu else ACT_NONE
+    E.conv_raw(x.t, w4, y.t, kh=kh, kw=kw, pad=1, bias=bias, act=act)
+
+    def bwd():
+        if y.g is None or not x.needs_grad:
+            return
+        dz = y.g
+        if relu:
+            dz = torch.empty_like(y.g)
+            E.act_bwd(y.g, y.t, dz, ACT_RELU, 0.0)
+        tgt, acc = x.grad_target()
+        E.conv_raw(dz, wt, tgt, kh=kh, kw=kw, pad=1, transposed=True, res=tgt if acc else None)
+
+    tape.push(bwd)
+    return y
+
+
+def _relu(tape: E.Tape, x: E.Var) -> E.Var:
+    """Stand-alone ReLU (only where a feature is tapped between a conv and its ReLU)."""
+    Cc = x.t.shape[-1]
+    one = torch.empty(Cc, dtype=torch.float32, device=x.t.device)
+    zero = torch.empty(Cc, dtype=torch.float32, device=x.t.device)
+    E.fill_(one, 1.0)
+    E.fill_(zero, 0.0)
+    y = E.Var(torch.empty_like(x.t))
+    E.affine_act(x.t, y.t, one, zero, ACT_RELU)
+
+    def bwd():
+        if y.g is None or not x.needs_grad:
+            return
+        dz = torch.empty_like(y.g)
+        E.act_bwd(y.g, y.t, dz, ACT_RELU, 0.0)
+        x.add_grad(dz)
+
+    tape.push(bwd)
+    return y
+
+
+class _PerceptualFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod: PerceptualLoss, x: torch.Tensor, y: torch.Tensor):
+        need = ctx.needs_input_grad[1]
+        dev = x.device
+        lib = E._lib(x.detach())
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        E.fill_(loss, 0.0)
+        ws = E.dot_ws(dev)
+        # target branch: forward only
+        ytape = E.Tape(record=False)
+        yfeat: Dict[int, torch.Tensor] = {}
+        yin = E.op_from_nchw(ytape, y.detach(), False)
+        mod._features(ytape, yin, lambda i, f: yfeat.__setitem__(i, f.t))
+        # generated branch: recorded; L1 terms add value and d/dfeature in one pass
+        tape = E.Tape(record=need)
+        xin = E.op_from_nchw(tape, x.detach(), need)
+
+        def on_feature(i: int, f: E.Var) -> None:
+            t = yfeat[i]
+            assert f.t.is_contiguous() and t.is_contiguous()
+            g = torch.empty_like(f.t) if need else None
+            L.check(lib.gdn_l1(f.t.data_ptr(), t.data_ptr(), f.t.numel(), loss.data_ptr(), 1, E._ptr(g), 1.0, 0, ws.data_ptr(), E._stream()), "gdn_l1")
+            if need:
+                def bwd():
+                    f.add_grad(g)
+                tape.push(bwd)
+
+        mod._features(tape, xin, on_feature)
+        ctx.tape, ctx.xin = tape, xin
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dout):
+        if not ctx.needs_input_grad[1]:
+            return None, None, None
+        ctx.tape.backward()
+        g = ctx.xin.g
+        gx = E.to_nchw(g)
+        ctx.tape = ctx.xin = None
+        return None, _scale_by(gx, dout), None
+
+
+__all__ = ["PerceptualLoss", "TVLoss", "SSIM"]

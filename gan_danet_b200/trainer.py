@@ -1,0 +1,233 @@
+"""The GAN-DANet generator/discriminator training step on the B200 kernels.
+
+Restates the hot loop of the reference's ``ModelTrainer.train`` (``/root/reference/GAN_DANet_train.ipynb:205-308``; the
+same class is duplicated in ``deep_ensemble.ipynb:52-295``): input preparation (:226-232), G forward (:243), the D step
+(:246-256), the G step (:259-269) with ``loss_G = (1-w)*MSE + w*BCE + TV + Perceptual`` and ``w = epoch/epochs``
+(:266-267), AdamW for both nets (:182-183) and per-epoch ``CosineAnnealingWarmRestarts`` (:186-187,294-295).
+
+Exact, work-saving deviations from the notebook (SURVEY appendix A identities):
+  * the real and the detached fake batch go through D as one 2B batch in the D step (fc1's weight is streamed once);
+    ``(BCE(real,1)+BCE(fake,0))/2`` equals the mean BCE over the 2B logits with targets [1..1,0..0];
+  * D's parameters do not require grad during the G step: the notebook computes those gradients at :268 and discards
+    them at :246 of the next iteration;
+  * SSIM (:263) is evaluated only when ``eval_ssim=True`` -- it never enters the objective (:267).
+Data-parallel training (not in the reference) all-reduces gradients over NCCL, see ``GradientAllReduce``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import engine as E
+from .models import Discriminator1, FlexibleUpsamplingModule, PerceptualLoss, SSIM, TVLoss
+from .models.generator import BuildCtx
+from .models.losses import BCEWithLogitsLoss, MSELoss
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics (decoupled weight decay, bias correction, eps outside the sqrt) with one fused
+    sm_100a kernel per parameter tensor (``gdn_adamw``).  ``grad_scale`` folds the 1/world of data parallelism."""
+
+    def __init__(self, params, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.grad_scale = 1.0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                assert p.is_contiguous()
+                L.check(E._lib(p).gdn_adamw(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                                            float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                                            int(st["step"]), float(self.grad_scale), E._stream()), "gdn_adamw")
+        return loss
+
+
+class GradientAllReduce:
+    """Sums gradients over the data-parallel group (NCCL over NVLink 5 / NVSwitch on B200; gloo in CPU tests).
+
+    Tensors above ``big`` elements are reduced in place one by one (D's fc1 gradient is ~1 GB and is its own bucket);
+    the rest are packed into one flat bucket per call.  The 1/world factor is applied by the optimizer (``grad_scale``)."""
+
+    def __init__(self, group=None, big: int = 1 << 20):
+        import torch.distributed as dist
+        self.dist, self.group, self.big = dist, group, big
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def __call__(self, params: Iterable[torch.nn.Parameter]) -> None:
+        if self.world == 1:
+            return
+        grads = [p.grad for p in params if p.grad is not None]
+        small = [g for g in grads if g.numel() <= self.big]
+        handles = [self.dist.all_reduce(g, group=self.group, async_op=True) for g in grads if g.numel() > self.big]
+        if small:
+            flat = torch.cat([g.reshape(-1) for g in small])
+            self.dist.all_reduce(flat, group=self.group)
+            off = 0
+            for g in small:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        for h in handles:
+            h.wait()
+
+
+def prepare_input_nhwc(lr_grace_05: torch.Tensor, hr_aux: torch.Tensor) -> torch.Tensor:
+    """GAN_DANet_train.ipynb:226-232 fused: bicubic x0.5 of the 0.5-degree field and bicubic x0.25 of the aux stack,
+    written straight into the channel slices of one NHWC generator input [B, h, w, 1 + C_aux]."""
+    B, _, H2, W2 = lr_grace_05.shape
+    _, Ca, H4, W4 = hr_aux.shape
+    h, w = H2 // 2, W2 // 2
+    assert (H4 // 4, W4 // 4) == (h, w), "lr_grace_05 and hr_aux grids are inconsistent"
+    lib = E._lib(hr_aux)
+    x = torch.empty((B, h, w, 1 + Ca), dtype=torch.float32, device=hr_aux.device)
+    a, g = hr_aux.contiguous(), lr_grace_05.contiguous()
+    L.check(lib.gdn_bicubic_down_nchw_to_nhwc(g.data_ptr(), x.data_ptr(), 1 + Ca, 0, B, 1, H2, W2, 2, E._stream()), "bicubic_down(grace)")
+    L.check(lib.gdn_bicubic_down_nchw_to_nhwc(a.data_ptr(), x.data_ptr(), 1 + Ca, 1, B, Ca, H4, W4, 4, E._stream()), "bicubic_down(aux)")
+    return x
+
+
+def generator_forward_nhwc(G: FlexibleUpsamplingModule, x_nhwc: torch.Tensor) -> torch.Tensor:
+    """G on an already NHWC input (skips the NCHW->NHWC boundary conversion); returns NCHW [B,1,4h,4w]."""
+    params = list(G.parameters())
+
+    def build(tape, xt, x_needs_grad, pvars):
+        ctx = BuildCtx(tape, {id(p): v for p, v in zip(params, pvars)})
+        xin = E.Var(xt, x_needs_grad)
+        return G._build_nhwc(ctx, xin), xin
+
+    return E.TapeFunction.apply(build, x_nhwc, *params)
+
+
+def cosine_warm_restarts_lr(epoch: int, base_lr: float, t0: int = 10, t_mult: int = 2, eta_min: float = 1e-6) -> float:
+    """CosineAnnealingWarmRestarts(T_0=10, T_mult=2, eta_min=1e-6) stepped per epoch (GAN_DANet_train.ipynb:186-187)."""
+    t_i, t_cur = t0, epoch
+    while t_cur >= t_i:
+        t_cur -= t_i
+        t_i *= t_mult
+    return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * t_cur / t_i)) / 2
+
+
+class GANTrainer:
+    """One object = the notebook's ``ModelTrainer`` state: G, D, both AdamW optimizers, schedulers and losses."""
+
+    def __init__(self, G: FlexibleUpsamplingModule, D: Discriminator1, perceptual: Optional[PerceptualLoss], *, epochs: int = 150,
+                 lr_g: float = 2e-4, lr_d: float = 4e-4, betas: Tuple[float, float] = (0.5, 0.999), weight_decay: float = 1e-4,
+                 tv_weight: float = 1e-5, fused_adamw: bool = True, eval_ssim: bool = False, allreduce: Optional[GradientAllReduce] = None):
+        self.G, self.D, self.perceptual = G, D, perceptual
+        self.epochs, self.epoch = epochs, 0
+        self.lr_g, self.lr_d, self.betas, self.weight_decay = lr_g, lr_d, betas, weight_decay
+        self.fused_adamw = fused_adamw
+        self.opt_G = self._make_opt(G.parameters(), lr_g)
+        self.opt_D: Optional[torch.optim.Optimizer] = None      # created after fc1 is materialised by the first D forward
+        self.bce, self.mse, self.tv, self.ssim = BCEWithLogitsLoss(), MSELoss(), TVLoss(tv_weight), SSIM()
+        self.eval_ssim = eval_ssim
+        self.allreduce = allreduce
+        if allreduce is not None and fused_adamw:
+            self.opt_G.grad_scale = 1.0 / allreduce.world
+
+    def _make_opt(self, params, lr):
+        cls = FusedAdamW if self.fused_adamw else torch.optim.AdamW
+        return cls(params, lr=lr, betas=self.betas, weight_decay=self.weight_decay)
+
+    def _ensure_opt_D(self, sample: torch.Tensor) -> None:
+        if self.opt_D is None:
+            self.D._materialise_fc1(sample)
+            self.opt_D = self._make_opt(self.D.parameters(), self.lr_d)
+            if self.allreduce is not None and self.fused_adamw:
+                self.opt_D.grad_scale = 1.0 / self.allreduce.world
+
+    def end_epoch(self) -> None:
+        """scheduler_D.step(); scheduler_U.step() (GAN_DANet_train.ipynb:294-295)."""
+        self.epoch += 1
+        for opt, base in ((self.opt_D, self.lr_d), (self.opt_G, self.lr_g)):
+            if opt is not None:
+                for g in opt.param_groups:
+                    g["lr"] = cosine_warm_restarts_lr(self.epoch, base)
+
+    def _reduce(self, params) -> None:
+        if self.allreduce is not None:
+            self.allreduce(params)
+            if not self.fused_adamw and self.allreduce.world > 1:
+                for p in params:
+                    if p.grad is not None:
+                        p.grad.mul_(1.0 / self.allreduce.world)
+
+    def train_step(self, lr_grace_05: torch.Tensor, lr_grace_025: torch.Tensor, hr_aux: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """One iteration of the hot loop.  Inputs are device tensors (NCHW, as ``CustomDataset`` yields them).
+        Returns the scalar losses as 0-dim device tensors (no host sync)."""
+        G, D = self.G, self.D
+        real = lr_grace_025
+        B = real.shape[0]
+        self._ensure_opt_D(real)
+        x = prepare_input_nhwc(lr_grace_05, hr_aux)                       # :226-232
+        hr = generator_forward_nhwc(G, x)                                 # :243
+
+        # ---- discriminator step (:246-256)
+        self.opt_D.zero_grad(set_to_none=True)
+        both = torch.cat([real, hr.detach()], dim=0)
+        logits = D(both)
+        target = torch.cat([torch.ones(B, 1, device=real.device), torch.zeros(B, 1, device=real.device)], dim=0)
+        loss_D = self.bce(logits, target)
+        loss_D.backward()
+        d_params = list(D.parameters())
+        self._reduce(d_params)
+        self.opt_D.step()
+
+        # ---- generator step (:259-269); D already updated, its parameter gradients are not needed here
+        self.opt_G.zero_grad(set_to_none=True)
+        for p in d_params:
+            p.requires_grad_(False)
+        try:
+            fake_out = D(hr)
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
+        loss_adv = self.bce(fake_out, torch.ones_like(fake_out))
+        loss_pix = self.mse(hr, real)
+        out: Dict[str, torch.Tensor] = {}
+        if self.eval_ssim:
+            out["ssim"] = 1 - self.ssim(hr, real)
+        loss_tv = self.tv(hr)
+        w = self.epoch / self.epochs
+        loss_G = (1 - w) * loss_pix + w * loss_adv + loss_tv
+        loss_perc = None
+        if self.perceptual is not None:
+            loss_perc = self.perceptual(hr, real)
+            loss_G = loss_G + loss_perc
+        loss_G.backward()
+        g_params = list(G.parameters())
+        self._reduce(g_params)
+        self.opt_G.step()
+        out.update({"loss_D": loss_D.detach(), "loss_G": loss_G.detach(), "adv": loss_adv.detach(), "pixel": loss_pix.detach(),
+                    "tv": loss_tv.detach()})
+        if loss_perc is not None:
+            out["perceptual"] = loss_perc.detach()
+        out["hr"] = hr.detach()
+        return out
+
+
+def init_like_reference(G: FlexibleUpsamplingModule, D: Discriminator1, sample_real: torch.Tensor, seed: Optional[int] = None) -> None:
+    """The notebook's initialisation (GAN_DANet_train.ipynb:164-165) with the authors' effective behaviour:
+    ``weights_init_normal`` on every conv / BN / materialised Linear; the lazy ``fc1`` keeps nn.Linear's default init."""
+    from .models import weights_init_normal
+    if seed is not None:
+        torch.manual_seed(seed)
+    G.apply(weights_init_normal)
+    D.apply(weights_init_normal)
+    D._materialise_fc1(sample_real)

@@ -132,6 +132,8 @@ int gdn_act_bwd(const float* dy, int dy_pitch, int dy_c0, const float* y, int y_
                 float* dz, int dz_pitch, int dz_c0, long long M, int C, int act, float slope, gdn_stream_t s);
 /* y (+)= alpha * x on NHWC slices */
 int gdn_axpy(const float* x, int x_pitch, int x_c0, float* y, int y_pitch, int y_c0, long long M, int C, float alpha, int accumulate, gdn_stream_t s);
+/* y (+)= scalar[0] * x with a DEVICE scalar (autograd's upstream gradient of a scalar loss) */
+int gdn_scale_dev(const float* x, const float* scalar, float* y, long long n, int accumulate, gdn_stream_t s);
 /* double sums -> float vector */
 int gdn_sums_to_float(const double* sums, float* out, int n, float scale, gdn_stream_t s);
 
@@ -150,21 +152,29 @@ int gdn_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, i
 
 /* ---------------------------------------------------------------- attention */
 /*
- * Position attention core (generator.py:115-122), flash-style: the NxN map never reaches HBM.
+ * Position attention core (generator.py:115-122), the NxN map never reaches the caller:
  *   S = q k^T (no scaling), P = softmax_row(S), O = P v, y = gamma*O + x, lse = logsumexp_row(S)
- * q,k: [B,N,d] (pitch qk_pitch); v,x,o,y: [B,N,C].  precision: GDN_PREC_FP32 = CUDA-core parity kernel.
+ * q,k: [B,N,d] (pitch qk_pitch); v: [B,N,C] (pitch v_pitch); x,y: [B,N,C] slices; o: [B,N,C] dense; lse: [B,N].
+ * precision: GDN_PREC_FP32 = fp32 CUDA-core parity engine (reference formulation, `chunk` samples of NxN scratch at a
+ *            time in `ws`; chunk 0 = auto);
+ *            GDN_PREC_FP16 = fused flash-style tcgen05/TMEM kernel fed by TMA (fp16 operands, fp32 accumulate,
+ *            online softmax); N must be a multiple of 128, d <= 32, C <= 192.
+ * ws: gdn_pam_fwd_ws_bytes(a) bytes (operand packing for the tensor-core path, NxN scratch for the parity path).
  */
 typedef struct {
   const float* q; const float* k; int qk_pitch; int d;
   const float* v; int v_pitch;
   const float* x; int x_pitch; const float* gamma;
   float* o; float* y; int y_pitch; float* lse;
-  int B, N, C; int precision;
+  int B, N, C; int precision; int chunk;
+  void* ws; size_t ws_bytes;
 } gdn_pam_fwd_args;
+size_t gdn_pam_fwd_ws_bytes(const gdn_pam_fwd_args* a);
 int gdn_pam_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s);
 /*
- * Backward of the core: given dy computes dq, dk, dv and rowdot[b,n] = sum_c dy*o (dgamma = sum rowdot; delta = gamma*rowdot).
- * dx of the residual is dy itself and is left to the caller.
+ * Backward of the core (autograd of generator.py:115-122): given dy computes dq, dk, dv (dense [B,N,d] / [B,N,C]) and
+ * rowdot[b,n] = sum_c dy*o (dgamma = sum rowdot; delta = gamma*rowdot).  dx of the residual is dy itself and is left
+ * to the caller.
  */
 typedef struct {
   const float* q; const float* k; int qk_pitch; int d;
@@ -172,14 +182,29 @@ typedef struct {
   const float* o; const float* lse; const float* gamma;
   const float* dy; int dy_pitch;
   float* dq; float* dk; float* dv; float* rowdot;
-  int B, N, C; int precision;
+  int B, N, C; int precision; int chunk;
+  void* ws; size_t ws_bytes;
 } gdn_pam_bwd_args;
+size_t gdn_pam_bwd_ws_bytes(const gdn_pam_bwd_args* a);
 int gdn_pam_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s);
+/*
+ * Channel attention (generator.py:125-139): attn = softmax_row(rowmax(E) - E), E = X X^T per sample ([C][C]),
+ * y = gamma * (attn X) + x.  x,y: [B,N,C] slices.  attn [B][C][C] is kept for the backward pass.
+ */
+int gdn_cam_fwd(const float* x, int x_pitch, const float* gamma, float* attn, float* y, int y_pitch, int B, int N, int C, gdn_stream_t s);
+/* dx (+)= dy + gamma*A^T dy + (dE+dE^T) x with dE = -A*(dA - rowsum(A*dA)), dA = gamma dy^T x; dgamma[0] = sum dy*(A x) */
+size_t gdn_cam_bwd_ws_bytes(int B, int N, int C);
+int gdn_cam_bwd(const float* x, int x_pitch, const float* gamma, const float* attn, const float* dy, int dy_pitch,
+                float* dx, int dx_pitch, int accumulate, float* dgamma, int B, int N, int C, void* ws, size_t ws_bytes, void* dot_ws, gdn_stream_t s);
+/* in-place-capable row softmax of [rows][n] (negate: softmax(-x)); lse optional.  torch.softmax at generator.py:118,136 */
+int gdn_row_softmax(const float* in, float* out, long long rows, int n, int negate, float* lse, gdn_stream_t s);
 /* CAM softmax (generator.py:135-136): attn = softmax_row(rowmax(E) - E) for [rows][C] */
 int gdn_cam_softmax(const float* e, float* attn, int rows, int C, gdn_stream_t s);
-/* CAM backward glue: dE = -A * (dA - rowsum(A*dA)); g = dE + dE^T  per [C][C] matrix */
-int gdn_cam_de(const float* attn, const float* da, float* g, int B, int C, gdn_stream_t s);
-/* out[0] (+)= sum over M*C of a*b  (deterministic two-stage; dgamma of PAM/CAM) */
+/* y = gamma[0]*o + x on [M][C] slices (generator.py:122,139) */
+int gdn_gamma_residual(const float* o, int o_pitch, const float* x, int x_pitch, const float* gamma, float* y, int y_pitch, long long M, int C, gdn_stream_t s);
+/* out[m] = sum_c a[m][c]*b[m][c] */
+int gdn_rowdot(const float* a, int a_pitch, const float* b, int b_pitch, long long M, int C, float* out, gdn_stream_t s);
+/* out[0] = sum over M*C of a*b  (deterministic two-stage; dgamma of PAM/CAM) */
 size_t gdn_dot_ws_bytes(long long n);
 int gdn_dot(const float* a, int a_pitch, int a_c0, const float* b, int b_pitch, int b_c0, long long M, int C, float* out, void* ws, gdn_stream_t s);
 
@@ -191,9 +216,10 @@ int gdn_mse(const float* a, const float* b, long long n, float* loss, float* gra
 int gdn_l1(const float* a, const float* b, long long n, float* loss, int loss_accumulate, float* grad, float gscale, int accumulate, void* ws, gdn_stream_t s);
 /* TVLoss (losses.py:81-87) on [B,H,W] single-channel fields */
 int gdn_tv(const float* x, int B, int H, int W, float weight, float* loss, float* grad, float gscale, int accumulate, void* ws, gdn_stream_t s);
-/* BCEWithLogitsLoss mean vs constant target (GAN_DANet_train.ipynb:252-253,261): loss[0] = mean(...); grad = gscale*(sigmoid(z)-t)/n */
-int gdn_bce_logits(const float* z, int n, float target, float* loss, float* grad, float gscale, gdn_stream_t s);
-/* SSIM (losses.py:98-136) forward only, single channel [B,H,W]: out[0] = mean ssim map.  ws: 5*B*H*W floats + dot ws */
+/* BCEWithLogitsLoss mean (GAN_DANet_train.ipynb:252-253,261) against target_ptr[i] (or the constant `target` when
+ * target_ptr is NULL): loss[0] = mean(max(z,0) - z*t + log1p(exp(-|z|))); grad = gscale*(sigmoid(z)-t)/n */
+int gdn_bce_logits(const float* z, int n, const float* target_ptr, float target, float* loss, float* grad, float gscale, gdn_stream_t s);
+/* SSIM (losses.py:98-136) forward only, single channel [B,H,W]: out[0] = mean ssim map.  ws: gdn_ssim_ws_bytes */
 size_t gdn_ssim_ws_bytes(int B, int H, int W);
 int gdn_ssim(const float* a, const float* b, int B, int H, int W, float* out, void* ws, gdn_stream_t s);
 

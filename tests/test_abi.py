@@ -1,0 +1,62 @@
+"""The C-ABI library loads and exports every symbol include/gandanet.h declares (no GPU, no compute calls)."""
+import os
+import re
+
+from conftest import ROOT
+
+
+def _header_prototypes():
+    src = open(os.path.join(ROOT, "include", "gandanet.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
+    src = re.sub(r"typedef\s+enum\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
+    src = re.sub(r"enum\s*\{.*?\}\s*;", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"(?:int|size_t|const char\*)\s+(gdn_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        protos[m.group(1)] = n
+    return protos
+
+
+def test_library_is_built_and_loads():
+    from gan_danet_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "run python -m gan_danet_b200.build"
+    lib = _lib.load()
+    assert lib.gdn_version() >= 100
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    from gan_danet_b200 import _lib
+    lib = _lib.load()
+    protos = _header_prototypes()
+    assert len(protos) >= 45
+    for name, nargs in protos.items():
+        assert hasattr(lib, name), f"{name} declared in gandanet.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+        assert len(_lib.SIGNATURES[name][1]) == nargs, f"{name}: header has {nargs} args, binding {len(_lib.SIGNATURES[name][1])}"
+    for name in _lib.SIGNATURES:
+        assert name in protos, f"{name} bound but not declared in gandanet.h"
+
+
+def test_sass_contains_blackwell_instructions():
+    """tcgen05.mma / TMA / tcgen05.ld of the PAM kernel must be in the shipped binary (UTCHMMA, UTMALDG, LDTM)."""
+    import shutil
+    import subprocess
+    from gan_danet_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    import gan_danet_b200 as g
+    G = g.FlexibleUpsamplingModule(4, growth_rate=4, num_blocks=1, num_layers_per_block=1)
+    with pytest.raises(g._lib.GdnError if hasattr(g, "_lib") else Exception):
+        G(torch.zeros(1, 4, 4, 4))
