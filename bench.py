@@ -1,0 +1,281 @@
+"""Headline benchmark: GAN-DANet generator+discriminator training step, samples/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (input preparation, G forward, D step, G step incl. TV + perceptual loss, both
+AdamW updates) over one synthetic batch.  N = 1 runs BASELINE.json configs[1] (per-GPU batch 32, generator grid 64x128
+=> PAM over 8192 positions, output 256x512); N > 1 (torchrun, one rank per GPU, NCCL) is configs[2]: the same per-GPU
+batch with gradient all-reduce (weak scaling).  Rank 0 prints ONE JSON line.
+
+  value     : samples/s with the batch resident in HBM (CUDA events, barrier + synchronize on both sides, max over ranks)
+  e2e       : same metric through the public trainer API with the step's inputs copied from pinned host memory and the
+              two scalar losses read back inside the timed region
+  roofline  : the fused tcgen05 PAM forward kernel -- algorithmic FLOPs 2*B*N^2*(d+C) per launch / mean launch time
+              (CUDA events on the launching stream inside the timed steps) against MEASURED_PEAKS.json bf16 (sustained)
+  cpu_baseline : the CPU oracle port of the reference step (oracle/gan_danet_oracle.py, fp32, all host threads) on a
+              bounded sample (batch 1 of the same grid), rank 0 at N = 1 only
+--impl reference times that same CPU port as the reference arm (the reference is pure PyTorch, /root/reference does not
+exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "G+D train samples/sec"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--grid", default="64x128", help="generator-input / PAM grid h x w")
+    ap.add_argument("--pam-precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--no-perceptual", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args, h, w):
+    return (f"GAN-DANet G+D train step, per-GPU batch {args.batch}, C_in 46, generator grid {h}x{w} (PAM over {h * w} positions), "
+            f"output {4 * h}x{4 * w}, losses MSE+BCE+TV" + ("" if args.no_perceptual else "+perceptual(VGG19[:21], random init)"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (profiling recipe's clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step_rate(h, w, batch, steps, warmup, perceptual=True):
+    """The reference's algorithm on the host cores: oracle port of the G+D step, fp32, all torch threads."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gan_danet_oracle as oracle
+    import gan_danet_b200 as P
+    from gan_danet_b200.synthetic import fast_batch
+    torch.manual_seed(0)
+    G = P.FlexibleUpsamplingModule(46)
+    D = P.Discriminator1()
+    lr05, real, aux = fast_batch(123, batch, h, w)
+    G.apply(P.weights_init_normal)
+    for mod in (D.conv1, D.conv2, D.conv3, D.conv4, D.fc2):
+        mod.apply(P.weights_init_normal)
+    D._materialise_fc1(real)
+    torch.manual_seed(2)
+    vgg = P.PerceptualLoss(pretrained=False, device=torch.device("cpu")).vgg.state_dict() if perceptual else None
+    if vgg is None:
+        raise SystemExit("the CPU port always evaluates the perceptual term")
+    st = oracle.TrainState({k: v.clone() for k, v in G.state_dict().items()}, {k: v.clone() for k, v in D.state_dict().items()}, dict(vgg))
+    for _ in range(warmup):
+        oracle.train_step(st, lr05, real, aux, 3, 150)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.train_step(st, lr05, real, aux, 3, 150)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    h, w = (int(v) for v in args.grid.split("x"))
+    b = args.cpu_sample_batch
+    rate, spt, threads = cpu_reference_step_rate(h, w, b, args.steps, min(args.warmup, 1))
+    sample = f"{args.steps} steps of batch {b} (bounded sample of the batch-{args.batch} workload, same grid), fp32, CPU oracle port of the reference step"
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": workload_name(args, h, w), "sample_batch": b},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gan_danet_b200 as P
+    from gan_danet_b200 import _lib, engine as E
+    from gan_danet_b200.synthetic import fast_batch
+    from gan_danet_b200.trainer import GANTrainer, GradientAllReduce, init_like_reference
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h, w = (int(v) for v in args.grid.split("x"))
+    B = args.batch
+
+    torch.manual_seed(0)
+    G = P.FlexibleUpsamplingModule(46)
+    D = P.Discriminator1()
+    lr05_h, real_h, aux_h = fast_batch(1000 + rank, B, h, w)
+    init_like_reference(G, D, real_h)
+    with torch.no_grad():
+        for n, p in G.named_parameters():
+            if n.endswith("gamma"):
+                p.fill_(0.05)
+    perc = None
+    if not args.no_perceptual:
+        torch.manual_seed(2)
+        perc = P.PerceptualLoss(pretrained=False, device=torch.device("cpu"))
+        perc.vgg.to(dev)
+        perc.device = dev
+    G, D = G.to(dev), D.to(dev)
+    G.set_pam_precision(args.pam_precision)
+    if world > 1:
+        for p in list(G.parameters()) + list(D.parameters()):
+            dist.broadcast(p.data, 0)
+    tr = GANTrainer(G, D, perc, epochs=150, allreduce=GradientAllReduce() if world > 1 else None)
+    tr.epoch = 3
+    pinned = [t.pin_memory() for t in (lr05_h, real_h, aux_h)]
+    resident = [t.to(dev) for t in pinned]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        tr.train_step(*resident)
+    sync_all()
+
+    # ---- timed: inputs resident in HBM
+    clocks = ClockSampler(local)
+    E.pam_timing = []
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = tr.train_step(*resident)
+    e1.record()
+    sync_all()
+    launches = _lib.launch_count - launches0
+    ms = e0.elapsed_time(e1)
+    pam_events, E.pam_timing = E.pam_timing, None
+    clk = clocks.stop()
+
+    # ---- timed: end to end through the trainer API with host buffers
+    h2d = sum(t.numel() * t.element_size() for t in pinned)
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last = None
+    for _ in range(args.steps):
+        dev_in = [t.to(dev, non_blocking=True) for t in pinned]
+        out = tr.train_step(*dev_in)
+        last = torch.stack([out["loss_D"], out["loss_G"]]).cpu()      # device -> host read of the step's result
+    e3.record()
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    value = world * B * args.steps / (ms * 1e-3)
+    value_e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the fused PAM forward kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf, peak_src = (peaks.get("bf16_tflops_sustained"), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)") if peaks else (1590.0, "fallback")
+    tc = [(a.elapsed_time(b), f) for a, b, f, prec in pam_events if prec == _lib.PREC_FP16]
+    roofline = None
+    if tc:
+        tot_ms = sum(t for t, _ in tc)
+        ach = sum(f for _, f in tc) / (tot_ms * 1e-3) / 1e12
+        roofline = {"kernel": "pam_flash_fwd_kernel (tcgen05/TMEM/TMA, incl. fp16 operand packing)", "bound": "tensor", "achieved": ach, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src, "launches": len(tc),
+                    "mean_launch_ms": tot_ms / len(tc), "share_of_step": tot_ms / ms}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp32 (PAM core: fp16 operands, fp32 accumulate)" if args.pam_precision == "fp16" else "fp32",
+                "data": "synthetic (seeded smooth random fields, random-init weights, random-init VGG19)",
+                "config": {"workload": workload_name(args, h, w), "global_batch": world * B, "parallelism": f"dp{world}",
+                           "pam": "fused tcgen05 flash forward + fp32 backward" if args.pam_precision == "fp16" else "fp32 engine",
+                           "l2": "inputs larger than L2 (the aux stack alone is %.0f MB per step)" % (aux_h.numel() * 4 / 1e6)},
+                "clocks": clk, "gpu_launches": launches,
+                "e2e": {"value": value_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(last.numel() * 4),
+                        "ms_per_step": ms_e2e / args.steps},
+                "roofline": roofline,
+                "losses": {k: float(out[k]) for k in ("loss_D", "loss_G")}}
+        if world == 1 and not args.skip_cpu_baseline:
+            b = args.cpu_sample_batch
+            rate, spt, threads = cpu_reference_step_rate(h, w, b, 1, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"1 warm-up + 1 timed step of batch {b} (bounded sample of the batch-{B} workload, same grid), fp32, CPU oracle port"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -41,6 +41,7 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 
 
 _workspaces: Dict[Tuple[int, str], Tensor] = {}
+pam_timing: Optional[list] = None   # set to [] by bench.py to collect (start, end, flops, precision) per PAM forward
 
 
 def workspace(name: str, nbytes: int, device) -> Tensor:
@@ -220,10 +221,23 @@ def dot_ws(device) -> Tensor:
 
 class Var:
     """A tensor on the tape plus its (lazily created) gradient.  ``parent`` marks a channel slice of a wider buffer."""
-    __slots__ = ("t", "g", "needs_grad", "parent", "c0", "c1")
+    __slots__ = ("t", "_g", "needs_grad", "parent", "c0", "c1")
 
     def __init__(self, t: Tensor, needs_grad: bool = True, parent: Optional["Var"] = None, c0: int = 0, c1: int = 0):
-        self.t, self.g, self.needs_grad, self.parent, self.c0, self.c1 = t, None, needs_grad, parent, c0, c1
+        self.t, self._g, self.needs_grad, self.parent, self.c0, self.c1 = t, None, needs_grad, parent, c0, c1
+
+    @property
+    def g(self) -> Optional[Tensor]:
+        """The gradient; a channel slice sees whatever has been accumulated into its parent's gradient buffer."""
+        if self._g is None and self.parent is not None:
+            pg = self.parent.g
+            if pg is not None:
+                self._g = pg[..., self.c0:self.c1]
+        return self._g
+
+    @g.setter
+    def g(self, value: Optional[Tensor]) -> None:
+        self._g = value
 
     def slice(self, c0: int, c1: int) -> "Var":
         return Var(self.t[..., c0:c1], self.needs_grad, self, c0, c1)
@@ -439,7 +453,14 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
     need = lib.gdn_pam_fwd_ws_bytes(C.byref(a))
     buf = workspace("pam", need, dev)
     a.ws, a.ws_bytes = buf.data_ptr(), buf.numel()
-    L.check(lib.gdn_pam_fwd(C.byref(a), _stream()), "gdn_pam_fwd")
+    if pam_timing is not None:          # bench.py: CUDA events on the launching stream around the fused kernel
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(lib.gdn_pam_fwd(C.byref(a), _stream()), "gdn_pam_fwd")
+        e1.record()
+        pam_timing.append((e0, e1, 2.0 * B * N * N * (d + Cc), precision))
+    else:
+        L.check(lib.gdn_pam_fwd(C.byref(a), _stream()), "gdn_pam_fwd")
     y = out
 
     def bwd():

@@ -158,7 +158,7 @@ def test_fused_adamw_matches_torch():
         pg.grad = g.to(DEV)
         opt_g.step()
     assert rel_err(pg, pr) < 1e-6
-    assert rel_err(pg.detach().cpu().double() - p0.double(), pr.detach() - p0.double()) < 1e-4
+    assert rel_err(pg.detach().cpu().double() - p0.double(), pr.detach() - p0.double()) < 1e-3
 
 
 # ------------------------------------------------------------------------------------------------ modules vs golden
