@@ -70,16 +70,14 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ a
   }
 }
 
-// P = exp(S - lse[row]) (overwrites S);  dS = P * (dP - gamma*rowdot[row]) (overwrites dP)
-__global__ void __launch_bounds__(256) pam_ds_kernel(float* __restrict__ S, float* __restrict__ dP, const float* __restrict__ lse, const float* __restrict__ rowdot,
+// dS = P * (dP - gamma*rowdot[row]) (overwrites dP); P is the row softmax recomputed by this engine
+__global__ void __launch_bounds__(256) pam_ds_kernel(const float* __restrict__ P, float* __restrict__ dP, const float* __restrict__ rowdot,
                                                       const float* __restrict__ gamma, long long rows, int n) {
   const float g = __ldg(gamma);
   const long long total = rows * n;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long r = idx / n;
-    float p = expf(S[idx] - lse[r]);
-    S[idx] = p;
-    dP[idx] = p * (dP[idx] - g * rowdot[r]);
+    dP[idx] = P[idx] * (dP[idx] - g * rowdot[r]);
   }
 }
 
@@ -224,7 +222,9 @@ extern "C" int gdn_pam_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s) {
     p.y = dP; p.y_pitch = N; p.alpha_ptr = a->gamma;
     p.B = gb; p.Hi = N; p.Wi = 1; p.Cin = C; p.Ho = N; p.Wo = 1; p.Cout = N; p.kh = p.kw = 1; p.stride = 1; p.splits = 1;
     if ((rc = gdn_conv2d(&p, s)) != GDN_OK) return rc;
-    pam_ds_kernel<<<ew_grid((long long)gb * N * N), 256, 0, as_stream(s)>>>(S, dP, a->lse + (size_t)b0 * N, a->rowdot + (size_t)b0 * N, a->gamma, (long long)gb * N, N);
+    // the parity engine renormalises its own fp32 logits (the saved lse may come from the fp16 tensor-core forward)
+    if ((rc = gdn_row_softmax(S, S, (long long)gb * N, N, 0, nullptr, s)) != GDN_OK) return rc;
+    pam_ds_kernel<<<ew_grid((long long)gb * N * N), 256, 0, as_stream(s)>>>(S, dP, a->rowdot + (size_t)b0 * N, a->gamma, (long long)gb * N, N);
     GDN_CHECK_LAUNCH();
     // dV[j][c] = sum_i P[i][j] * gamma*dy[i][c]
     gdn_wgrad_args wv = {};

@@ -1,0 +1,90 @@
+"""Host-side logic that needs no GPU: schedules, API mirror, data-parallel gradient exchange (gloo, world_size 2)."""
+import math
+import os
+import socket
+
+import pytest
+import torch
+
+
+def test_cosine_warm_restarts_matches_torch():
+    """CosineAnnealingWarmRestarts(T_0=10, T_mult=2, eta_min=1e-6) stepped per epoch (GAN_DANet_train.ipynb:186-187)."""
+    from gan_danet_b200.trainer import cosine_warm_restarts_lr
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=2e-4)
+    sch = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0=10, T_mult=2, eta_min=1e-6)
+    for epoch in range(0, 75):
+        assert math.isclose(opt.param_groups[0]["lr"], cosine_warm_restarts_lr(epoch, 2e-4), rel_tol=1e-9, abs_tol=1e-15), epoch
+        opt.step()
+        sch.step()
+
+
+def test_api_mirror_of_reference_models():
+    """Same exports, constructor signatures and state_dict keys as models/__init__.py:12-23, generator.py:178-185."""
+    import inspect
+    import gan_danet_b200.models as M
+    assert set(M.__all__) == {"CBAMBlock", "FlexibleUpsamplingModule", "OriginalRelationshipLearner", "SqueezeExcitation", "Discriminator1",
+                              "SRGAND", "PerceptualLoss", "SSIM", "TVLoss", "weights_init_normal"}
+    sig = inspect.signature(M.FlexibleUpsamplingModule.__init__)
+    assert [(k, v.default) for k, v in list(sig.parameters.items())[1:]] == [
+        ("input_channels", 40), ("growth_rate", 24), ("num_blocks", 3), ("num_layers_per_block", 4), ("attention_type", "danet")]
+    G = M.FlexibleUpsamplingModule()
+    assert len(G.state_dict()) == 163 and sum(p.numel() for p in G.parameters()) == 2268537
+    assert G.feature_channels == [160, 176, 184]
+    with pytest.warns(RuntimeWarning):
+        G2 = M.FlexibleUpsamplingModule(attention_type="senet")       # aliases to DANet (generator.py:166-171)
+    assert list(G2.state_dict().keys()) == list(G.state_dict().keys())
+    assert M.FlexibleUpsamplingModule(attention_type=None).attention_modules[0] is None
+    with pytest.raises(ValueError):
+        M.FlexibleUpsamplingModule(attention_type="bogus")
+    D = M.Discriminator1()
+    D.apply(M.weights_init_normal)                                      # lazy fc1 is skipped, as on the authors' torch
+    D._materialise_fc1(torch.zeros(1, 1, 180, 88))
+    assert D.fc1.weight.shape == (1024, 512 * 12 * 6) and sum(p.numel() for p in D.parameters()) == 39300609
+    assert list(M.SRGAND().state_dict().keys())[0] == "conv1.weight"
+    M.PerceptualLoss(pretrained=False, use_gpu=False)                   # notebook passes use_gpu= (GAN_DANet_train.ipynb:194)
+
+
+def test_pitch_of_slices():
+    from gan_danet_b200.engine import pitch_of, rows_of
+    buf = torch.zeros(2, 3, 5, 16)
+    assert pitch_of(buf) == 16 and pitch_of(buf[..., 4:8]) == 16 and rows_of(buf[..., 4:8]) == 30
+    assert pitch_of(torch.zeros(4, 1, 1, 7)) == 7
+    assert pitch_of(torch.zeros(1, 9, 1, 4)) == 4
+    with pytest.raises(Exception):
+        pitch_of(buf.permute(0, 2, 1, 3))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gan_danet_b200.trainer import GradientAllReduce
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 2_000_000, 17, 3)]      # one "big" tensor, three bucketed ones
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+    params.append(torch.nn.Parameter(torch.zeros(4)))                                 # no grad: must be skipped
+    ar = GradientAllReduce()
+    ar(params)
+    ok = all(torch.all(p.grad == float(sum(r + 1 for r in range(world)) * (i + 1))) for i, p in enumerate(params[:4]))
+    out[rank] = bool(ok) and ar.world == world
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_gloo_world2():
+    """The N > 1 path: gradients are summed over ranks (bucketed small tensors + in-place large ones)."""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
+        assert out[0] and out[1]
