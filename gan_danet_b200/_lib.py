@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgandanet_sm100.so")
 
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
-PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_FP16, PREC_BF16X3 = 0, 1, 2, 3
 
 _vp, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 
@@ -37,6 +37,24 @@ class WgradArgs(C.Structure):
                 ("B", _i), ("Hi", _i), ("Wi", _i), ("Cin", _i), ("Ho", _i), ("Wo", _i), ("Cout", _i),
                 ("kh", _i), ("kw", _i), ("stride", _i), ("pad", _i), ("groups", _i),
                 ("splits", _i), ("ws", _vp), ("ws_bytes", _sz)]
+
+
+class ConvTcArgs(C.Structure):
+    _fields_ = [("x_hi", _vp), ("x_lo", _vp), ("w_hi", _vp), ("w_lo", _vp),
+                ("y", _vp), ("y_pitch", _i), ("y_c0", _i),
+                ("bias", _vp),
+                ("res", _vp), ("res_pitch", _i), ("res_c0", _i),
+                ("B", _i), ("Hi", _i), ("Wi", _i), ("Cin", _i), ("Ho", _i), ("Wo", _i), ("Cout", _i),
+                ("kh", _i), ("kw", _i), ("stride", _i), ("pad", _i), ("transposed", _i),
+                ("act", _i), ("slope", _f), ("precision", _i)]
+
+
+class WgradTcArgs(C.Structure):
+    _fields_ = [("dy_hi", _vp), ("dy_lo", _vp), ("x_hi", _vp), ("x_lo", _vp),
+                ("out", _vp), ("out_cin_total", _i), ("out_c0", _i), ("accumulate", _i), ("scale", _f),
+                ("B", _i), ("Hi", _i), ("Wi", _i), ("Cin", _i), ("Ho", _i), ("Wo", _i), ("Cout", _i),
+                ("kh", _i), ("kw", _i), ("stride", _i), ("pad", _i),
+                ("precision", _i), ("ws", _vp), ("ws_bytes", _sz)]
 
 
 class PamFwdArgs(C.Structure):
@@ -71,6 +89,12 @@ SIGNATURES = {
     "gdn_conv2d_wgrad": (_i, [C.POINTER(WgradArgs), _vp]),
     "gdn_conv2d_suggest_splits": (_i, [C.POINTER(ConvArgs)]),
     "gdn_wgrad_suggest_splits": (_i, [C.POINTER(WgradArgs)]),
+    "gdn_pack_act_bf16": (_i, [_vp, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _i, _f, _vp]),
+    "gdn_pack_weight_bf16_elems": (_sz, [_i, _i, _i, _i, _i]),
+    "gdn_pack_weight_bf16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "gdn_conv2d_tc": (_i, [C.POINTER(ConvTcArgs), _vp]),
+    "gdn_conv2d_wgrad_tc_ws_bytes": (_sz, [C.POINTER(WgradTcArgs)]),
+    "gdn_conv2d_wgrad_tc": (_i, [C.POINTER(WgradTcArgs), _vp]),
     "gdn_colstats_ws_bytes": (_sz, [_ll, _i]),
     "gdn_colstats": (_i, [_vp, _i, _i, _ll, _i, _vp, _vp, _vp]),
     "gdn_bn_finalize": (_i, [_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

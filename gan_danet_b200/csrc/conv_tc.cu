@@ -1,0 +1,594 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, 4-D tiled maps over the NHWC activation: the box is a Ht x Wt patch of pixels x 64 channels,
+//   the zero padding of the convolution is the TMA out-of-bounds fill, the stride of a strided convolution is the TMA
+//   element stride) -> 128-byte-swizzled shared memory -> tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate in TMEM)
+//   -> tcgen05.ld epilogue with fused bias / activation / residual.
+// Replaces nn.Conv2d at /root/reference/models/generator.py:34,63,108-110,148,188,214,218,222, discriminator.py:63-65 and the
+// VGG19 convolutions of losses.py:58 in the `bf16` / `bf16x3` precision modes; the fp32 CUDA-core engine (igemm_simt.cu)
+// stays the `fp32` mode.
+//
+// One K-iteration = one filter tap x one 64-channel chunk:   D[128 px, n_tile] += A[128 px, 64 ch] * W[n_tile, 64 ch]^T
+//   forward           : A = x at (ho*stride - pad + kh, wo*stride - pad + kw),            W = w[:, :, kh, kw]
+//   data gradient s=1 : A = dy at (h + pad - kh, w + pad - kw),                            W = w[:, :, kh, kw]^T
+//   data gradient s=2 : the four output-parity classes (h%2, w%2) are four launches, each a dense stride-1 problem over
+//                       the dy grid with its own subset of taps, scattered to the strided output pixels.
+// Precision `bf16x3` (bf16 hi+lo split): every operand is hi = bf16(v), lo = bf16(v - hi) and the K loop runs
+// the three products hi*hi + lo*hi + hi*lo into the same fp32 accumulator (~16 mantissa bits; 3x the MMA work).
+//
+// Weight gradient (second kernel): out[co, tap, ci] = sum_px dy[px, co] * x[px + tap, ci] is a GEMM whose K dimension is the
+// pixel index, i.e. both operands are "MN-major" in shared memory ([pixel][channel] tiles exactly as TMA delivers them);
+// tcgen05 takes them through the a_major/b_major bits of the instruction descriptor, so no transpose pass exists.
+// The pixel range is split over CTAs; partial sums go to a workspace and a deterministic reduction writes the OIHW gradient.
+#include <cuda_bf16.h>
+#include "tc_common.cuh"
+
+namespace gdn {
+namespace convtc {
+using namespace gdn::tc;
+
+constexpr int BM = 128;             // pixels per tile (UMMA M)
+constexpr int BK = 64;              // channels per K-iteration: 64 bf16 = one 128-byte swizzled row
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int NTHREADS = 256;
+constexpr int MAX_STAGES = 6;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+// kind::f16 instruction descriptor for bf16 operands: D fp32 (bit 4), A/B format bf16 (1 at [7,10) and [10,13)),
+// a_major bit 15 / b_major bit 16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// shared-memory matrix descriptor with explicit leading-dimension byte offset (needed by MN-major operands wider than 64)
+__device__ __forceinline__ uint64_t smem_desc_lbo(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+struct TapList { int n; int dh[9], dw[9], widx[9]; };
+
+struct FwdParams {
+  float* y; int y_pitch; const float* bias; const float* res; int res_pitch;
+  int B, Ho, Wo, Cout;        // output tensor (pixels are written at (i*os + oh0, j*os + ow0))
+  int Hc, Wc, os, oh0, ow0;   // extent of the tile grid and the output scatter
+  int Wt, Ht, tiles_w, tiles_h;
+  int cs;                     // input coordinate = tile coordinate * cs + tap offset (cs = conv stride = TMA element stride)
+  int kchunks, n_tile, nsplit, stages, tmem_cols;
+  int act; float slope; int vec4;
+  TapList taps;
+};
+
+__global__ void __launch_bounds__(NTHREADS)
+conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_constant__ CUtensorMap mapXlo,
+                   const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b_bytes = p.n_tile * 128;
+  const int stage_bytes = A_BYTES + b_bytes;
+  const uint32_t bar_base = base + p.stages * stage_bytes;
+  auto full = [&](int s) { return bar_base + 8 * s; };
+  auto empty = [&](int s) { return bar_base + 8 * (MAX_STAGES + s); };
+  const uint32_t acc_bar = bar_base + 8 * (2 * MAX_STAGES);
+  const uint32_t tmem_slot_addr = bar_base + 8 * (2 * MAX_STAGES + 1);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot_addr - smem_u32(smem_raw)));
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int img = t;
+  const int n0 = blockIdx.y * p.n_tile;
+  const int IT = p.taps.n * p.nsplit * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- TMA producer
+      int it = 0;
+      for (int tp = 0; tp < p.taps.n; ++tp) {
+        const int cw = tw * p.Wt * p.cs + p.taps.dw[tp], ch = th * p.Ht * p.cs + p.taps.dh[tp];
+        for (int comp = 0; comp < p.nsplit; ++comp) {
+          const CUtensorMap* mx = comp == 1 ? &mapXlo : &mapXhi;
+          const CUtensorMap* mw = comp == 2 ? &mapWlo : &mapWhi;
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            const int s = it % p.stages;
+            if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
+            mbar_expect_tx(full(s), stage_bytes);
+            tma_load_4d(base + s * stage_bytes, mx, full(s), kc * BK, cw, ch, img);
+            tma_load_3d(base + s * stage_bytes + A_BYTES, mw, full(s), kc * BK, n0, p.taps.widx[tp]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---- MMA issuer
+      const uint32_t idesc = idesc_bf16(BM, p.n_tile, 0, 0);
+      for (int it = 0; it < IT; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(full(s), (it / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t a0 = base + s * stage_bytes, b0 = a0 + A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ++ks) {
+          umma_f16(tmem, smem_desc(a0 + ks * 32, 1024, LAYOUT_SW128), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc_commit(empty(s));
+      }
+      tc_commit(acc_bar);
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: thread = one pixel of the tile (TMEM lane), 32 output channels at a time
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int i = th * p.Ht + row / p.Wt, j = tw * p.Wt + row % p.Wt;
+    const bool pix_ok = i < p.Hc && j < p.Wc;
+    const size_t pix = ((size_t)img * p.Ho + (size_t)(i * p.os + p.oh0)) * p.Wo + (size_t)(j * p.os + p.ow0);
+    float* yrow = p.y + pix * p.y_pitch;
+    const float* rrow = p.res ? p.res + pix * p.res_pitch : nullptr;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    for (int c = 0; c < p.n_tile; c += 32) {
+      float v[32];
+      // n_tile is a multiple of 16: the last chunk may be half wide; TMEM columns up to the power-of-two allocation exist
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, v);
+      if (!pix_ok) continue;
+      const int nb = n0 + c;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const int n = nb + e;
+        if (n >= p.Cout || c + e >= p.n_tile) break;
+        if (p.vec4) {   // Cout, pitches and channel offsets are multiples of 4
+          float4 o = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          if (p.bias) { const float4 bb = *reinterpret_cast<const float4*>(p.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+          o.x = apply_act(o.x, p.act, p.slope); o.y = apply_act(o.y, p.act, p.slope); o.z = apply_act(o.z, p.act, p.slope); o.w = apply_act(o.w, p.act, p.slope);
+          if (rrow) { const float4 rr = *reinterpret_cast<const float4*>(rrow + n); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+          *reinterpret_cast<float4*>(yrow + n) = o;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (n + u < p.Cout) {
+              float o = v[e + u] + (p.bias ? __ldg(p.bias + n + u) : 0.f);
+              o = apply_act(o, p.act, p.slope);
+              if (rrow) o += rrow[n + u];
+              yrow[n + u] = o;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+constexpr int WG_DY_SLOTS = 2, WG_X_SLOTS = 4;
+constexpr int WG_DY_BYTES = 2 * A_BYTES;    // [128 px][64 co] x 2 channel boxes (UMMA M = 128 output channels)
+
+struct WgParams {
+  float* ws;                   // [splits][Cout][taps][cin_w] fp32 partial sums
+  int Cout, cin_w, taps_total;
+  int tiles_w, tiles_h, tiles_total, tiles_per_split;
+  int Wt, Ht, cs, pad, kw;
+  int ci_tile, ci_tiles, co_tiles, tap_groups, taps_per_cta, nsplit, tmem_cols;
+};
+
+__global__ void __launch_bounds__(NTHREADS)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDYhi, const __grid_constant__ CUtensorMap mapDYlo,
+                     const __grid_constant__ CUtensorMap mapXhi, const __grid_constant__ CUtensorMap mapXlo, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nbox = p.ci_tile / 64;
+  const int x_bytes = nbox * A_BYTES;
+  const uint32_t dy_base = base, x_base = base + WG_DY_SLOTS * WG_DY_BYTES;
+  const uint32_t bar_base = x_base + WG_X_SLOTS * x_bytes;
+  auto dyfull = [&](int s) { return bar_base + 8 * s; };
+  auto dyempty = [&](int s) { return bar_base + 8 * (WG_DY_SLOTS + s); };
+  auto xfull = [&](int s) { return bar_base + 8 * (2 * WG_DY_SLOTS + s); };
+  auto xempty = [&](int s) { return bar_base + 8 * (2 * WG_DY_SLOTS + WG_X_SLOTS + s); };
+  const uint32_t acc_bar = bar_base + 8 * (2 * WG_DY_SLOTS + 2 * WG_X_SLOTS);
+  const uint32_t tmem_slot_addr = acc_bar + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot_addr - smem_u32(smem_raw)));
+
+  int u = blockIdx.x;
+  const int tg = u % p.tap_groups; u /= p.tap_groups;
+  const int cit = u % p.ci_tiles; u /= p.ci_tiles;
+  const int cot = u;
+  const int split = blockIdx.y;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(t_begin + p.tiles_per_split, p.tiles_total);
+  const int ntiles = t_end - t_begin;          // > 0 by construction of the grid
+  const int tap0 = tg * p.taps_per_cta;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_DY_SLOTS; ++s) { mbar_init(dyfull(s), 1); mbar_init(dyempty(s), 1); }
+    for (int s = 0; s < WG_X_SLOTS; ++s) { mbar_init(xfull(s), 1); mbar_init(xempty(s), 1); }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- TMA producer for dy tiles: one (pixel tile, precision component) per slot
+      int n = 0;
+      for (int ti = 0; ti < ntiles; ++ti) {
+        int t = t_begin + ti;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        for (int comp = 0; comp < p.nsplit; ++comp, ++n) {
+          const int s = n % WG_DY_SLOTS;
+          if (n >= WG_DY_SLOTS) mbar_wait(dyempty(s), ((n / WG_DY_SLOTS) - 1) & 1);
+          const CUtensorMap* m = comp == 1 ? &mapDYlo : &mapDYhi;
+          mbar_expect_tx(dyfull(s), WG_DY_BYTES);
+          tma_load_4d(dy_base + s * WG_DY_BYTES, m, dyfull(s), cot * 128, tw * p.Wt, th * p.Ht, t);
+          tma_load_4d(dy_base + s * WG_DY_BYTES + A_BYTES, m, dyfull(s), cot * 128 + 64, tw * p.Wt, th * p.Ht, t);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {   // ---- TMA producer for the shifted x tiles: one (pixel tile, component, tap) per slot
+      int n = 0;
+      for (int ti = 0; ti < ntiles; ++ti) {
+        int t = t_begin + ti;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        for (int comp = 0; comp < p.nsplit; ++comp) {
+          const CUtensorMap* m = comp == 2 ? &mapXlo : &mapXhi;
+          for (int tl = 0; tl < p.taps_per_cta; ++tl, ++n) {
+            const int tap = tap0 + tl;
+            const int dh = tap / p.kw - p.pad, dw = tap % p.kw - p.pad;
+            const int s = n % WG_X_SLOTS;
+            if (n >= WG_X_SLOTS) mbar_wait(xempty(s), ((n / WG_X_SLOTS) - 1) & 1);
+            mbar_expect_tx(xfull(s), x_bytes);
+            for (int bx = 0; bx < nbox; ++bx)
+              tma_load_4d(x_base + s * x_bytes + bx * A_BYTES, m, xfull(s), cit * p.ci_tile + bx * 64, tw * p.Wt * p.cs + dw, th * p.Ht * p.cs + dh, t);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---- MMA issuer: acc[tap] (128 co x ci_tile) += dy^T (MN-major A) * x (MN-major B), K = 128 pixels per tile
+      const uint32_t idesc = idesc_bf16(128, p.ci_tile, 1, 1);
+      int nd = 0, nx = 0;
+      for (int ti = 0; ti < ntiles; ++ti) {
+        for (int comp = 0; comp < p.nsplit; ++comp, ++nd) {
+          const int sd = nd % WG_DY_SLOTS;
+          mbar_wait(dyfull(sd), (nd / WG_DY_SLOTS) & 1);
+          for (int tl = 0; tl < p.taps_per_cta; ++tl, ++nx) {
+            const int sx = nx % WG_X_SLOTS;
+            mbar_wait(xfull(sx), (nx / WG_X_SLOTS) & 1);
+            tc_fence_after();
+            const uint32_t a0 = dy_base + sd * WG_DY_BYTES, b0 = x_base + sx * x_bytes;
+#pragma unroll
+            for (int ks = 0; ks < BM / 16; ++ks) {   // 16 pixels = two 8-row swizzle atoms (SBO = 1024 B); channel groups of 64 are LBO = 16 KB apart
+              umma_f16(tmem + tl * p.ci_tile, smem_desc_lbo(a0 + ks * 2048, A_BYTES, 1024, LAYOUT_SW128), smem_desc_lbo(b0 + ks * 2048, A_BYTES, 1024, LAYOUT_SW128), idesc,
+                       (ti > 0 || comp > 0 || ks > 0) ? 1u : 0u);
+            }
+            tc_commit(xempty(sx));
+          }
+          tc_commit(dyempty(sd));
+        }
+      }
+      tc_commit(acc_bar);
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: thread = output channel (TMEM lane); partial sums to the workspace
+    const int q = warp & 3;
+    const int co = cot * 128 + q * 32 + lane;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    for (int tl = 0; tl < p.taps_per_cta; ++tl) {
+      float* dst = p.ws + (((size_t)split * p.Cout + co) * p.taps_total + (tap0 + tl)) * p.cin_w + (size_t)cit * p.ci_tile;
+      for (int c = 0; c < p.ci_tile; c += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tl * p.ci_tile + c, v);
+        if (co < p.Cout) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(dst + c + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// out[co][out_c0+ci][tap] (OIHW) (+)= scale * sum_s ws[s][co][tap][ci]   -- fixed summation order => deterministic
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ ws, int splits, int Cout, int Cin, int taps, int cin_w,
+                                       float* __restrict__ out, int out_cin_total, int out_c0, int accumulate, float scale) {
+  const long long total = (long long)Cout * taps * Cin;
+  const size_t split_stride = (size_t)Cout * taps * cin_w;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % Cin); long long r = idx / Cin;
+    const int tap = (int)(r % taps); const int co = (int)(r / taps);
+    const float* src = ws + ((size_t)co * taps + tap) * cin_w + ci;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
+    float* o = out + ((size_t)co * out_cin_total + out_c0 + ci) * taps + tap;
+    *o = accumulate ? *o + acc * scale : acc * scale;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ operand packing
+// fp32 NHWC slice -> bf16 [M][Cp] (Cp = round_up(C, 8), zero padded): hi = bf16(v), lo = bf16(v - hi); v = act(x*scale+shift)
+__global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, int pitch, long long M, int C, int Cp, __nv_bfloat16* __restrict__ hi,
+                                                       __nv_bfloat16* __restrict__ lo, const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope) {
+  const int groups = Cp >> 3;
+  const long long total = M * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / groups; const int c0 = (int)(idx % groups) * 8;
+    const float* src = x + (size_t)m * pitch + c0;
+    __align__(16) __nv_bfloat16 h[8];
+    __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = 0.f;
+      if (c0 + e < C) {
+        v = __ldg(src + e);
+        if (scale) v = apply_act(fmaf(v, __ldg(scale + c0 + e), __ldg(shift + c0 + e)), act, slope);
+      }
+      h[e] = __float2bfloat16_rn(v);
+      l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e]));
+    }
+    *reinterpret_cast<uint4*>(hi + (size_t)m * Cp + c0) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + (size_t)m * Cp + c0) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+// OIHW fp32 -> bf16 [taps][R][Kp]: transposed == 0: R = O, K = I (forward operand); transposed == 1: R = I, K = O (data-gradient operand)
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int O, int I_total, int i_c0, int I, int taps, int transposed,
+                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int R = transposed ? I : O, K = transposed ? O : I, Kp = (K + 7) & ~7;
+  const long long total = (long long)taps * R * Kp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Kp); long long r2 = idx / Kp;
+    const int r = (int)(r2 % R); const int t = (int)(r2 / R);
+    float v = 0.f;
+    if (k < K) {
+      const int o = transposed ? k : r, i = transposed ? r : k;
+      v = __ldg(w + ((size_t)o * I_total + i_c0 + i) * taps + t);
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[idx] = h;
+    if (lo) lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// 4-D bf16 NHWC activation map: dims (Cp, W, H, B), box (64, Wt*cs, Ht*cs, 1) traversed with element stride cs
+static int make_act_map(CUtensorMap* m, const void* ptr, int Cp, int W, int H, int B, int Wt, int Ht, int cs) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return GDN_ECUDA; }
+  cuuint64_t gdim[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstride[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(Wt * cs), (cuuint32_t)(Ht * cs), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)cs, (cuuint32_t)cs, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(activation Cp=%d W=%d H=%d B=%d box %dx%d cs=%d) failed (%d)", Cp, W, H, B, Wt, Ht, cs, (int)r); return GDN_ECUDA; }
+  return GDN_OK;
+}
+// 3-D packed weight map: dims (Kp, R, taps), box (64, n_tile, 1)
+static int make_weight_map(CUtensorMap* m, const void* ptr, int Kp, int R, int taps, int n_tile) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return GDN_ECUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)R, (cuuint64_t)taps};
+  cuuint64_t gstride[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)R * Kp * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)n_tile, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(weight Kp=%d R=%d taps=%d n_tile=%d) failed (%d)", Kp, R, taps, n_tile, (int)r); return GDN_ECUDA; }
+  return GDN_OK;
+}
+
+// pixel tile shape: Wt = smallest power of two >= min(W, 128) (>= 8), Ht = 128 / Wt
+static void tile_shape(int W, int* Wt, int* Ht) {
+  int wt = 8;
+  while (wt < W && wt < 128) wt <<= 1;
+  *Wt = wt; *Ht = BM / wt;
+}
+static int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+}  // namespace convtc
+}  // namespace gdn
+
+using namespace gdn;
+using namespace gdn::convtc;
+
+extern "C" int gdn_conv_tc_init(void) {
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  return GDN_OK;
+}
+
+extern "C" int gdn_pack_act_bf16(const float* x, int x_pitch, int x_c0, long long M, int C, uint16_t* hi, uint16_t* lo, const float* scale, const float* shift,
+                                 int act, float slope, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && hi && M > 0 && C > 0 && x_pitch >= x_c0 + C);
+  GDN_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && (scale == nullptr) == (shift == nullptr));
+  const int Cp = (C + 7) & ~7;
+  const long long total = M * (Cp / 8);
+  const int blocks = (int)(cdiv(total, 256) < 16 * kNumSMs ? cdiv(total, 256) : 16 * kNumSMs);
+  pack_act_kernel<<<blocks, 256, 0, as_stream(s)>>>(x + x_c0, x_pitch, M, C, Cp, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), scale, shift, act, slope);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" size_t gdn_pack_weight_bf16_elems(int O, int I, int kh, int kw, int transposed) {
+  const int R = transposed ? I : O, K = transposed ? O : I;
+  return (size_t)kh * kw * R * ((K + 7) & ~7);
+}
+extern "C" int gdn_pack_weight_bf16(const float* w, int O, int I_total, int i_c0, int I, int kh, int kw, int transposed, uint16_t* hi, uint16_t* lo, gdn_stream_t s) {
+  GDN_CHECK_ARG(w && hi && O > 0 && I > 0 && kh > 0 && kw > 0 && I_total >= i_c0 + I);
+  const long long total = (long long)gdn_pack_weight_bf16_elems(O, I, kh, kw, transposed);
+  const int blocks = (int)(cdiv(total, 256) < 8 * kNumSMs ? cdiv(total, 256) : 8 * kNumSMs);
+  pack_weight_kernel<<<blocks, 256, 0, as_stream(s)>>>(w, O, I_total, i_c0, I, kh * kw, transposed, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
+  GDN_CHECK_ARG(a && a->x_hi && a->w_hi && a->y);
+  GDN_CHECK_ARG(a->B > 0 && a->Cin > 0 && a->Cout > 0 && a->kh > 0 && a->kw > 0 && a->kh * a->kw <= 9);
+  GDN_CHECK_ARG(a->Hi > 0 && a->Wi > 0 && a->Ho > 0 && a->Wo > 0 && (a->stride == 1 || a->stride == 2));
+  GDN_CHECK_ARG(a->y_pitch >= a->y_c0 + a->Cout && (!a->res || a->res_pitch >= a->res_c0 + a->Cout));
+  GDN_CHECK_ARG(a->precision == GDN_PREC_BF16 || (a->precision == GDN_PREC_BF16X3 && a->x_lo && a->w_lo));
+  GDN_CHECK_ARG(((uintptr_t)a->x_hi & 15) == 0 && ((uintptr_t)a->w_hi & 15) == 0 && ((uintptr_t)a->x_lo & 15) == 0 && ((uintptr_t)a->w_lo & 15) == 0);
+  const int nsplit = a->precision == GDN_PREC_BF16X3 ? 3 : 1;
+  const int Cp = (a->Cin + 7) & ~7;         // channel pitch of the packed activation AND K pitch of the packed weight
+  const int taps = a->kh * a->kw;
+  FwdParams p;
+  p.y = a->y + a->y_c0; p.y_pitch = a->y_pitch; p.bias = a->bias;
+  p.res = a->res ? a->res + a->res_c0 : nullptr; p.res_pitch = a->res_pitch;
+  p.B = a->B; p.Ho = a->Ho; p.Wo = a->Wo; p.Cout = a->Cout;
+  p.kchunks = (int)cdiv(a->Cin, BK);
+  p.n_tile = a->Cout <= 256 ? (int)cdiv(a->Cout, 16) * 16 : 256;
+  p.nsplit = nsplit;
+  p.tmem_cols = pow2_cols(p.n_tile);
+  p.act = a->act; p.slope = a->slope;
+  p.vec4 = (a->Cout % 4 == 0 && a->y_pitch % 4 == 0 && a->y_c0 % 4 == 0 && ((uintptr_t)a->y & 15) == 0 && (!a->bias || ((uintptr_t)a->bias & 15) == 0) &&
+            (!a->res || (a->res_pitch % 4 == 0 && a->res_c0 % 4 == 0 && ((uintptr_t)a->res & 15) == 0))) ? 1 : 0;
+  const int stage_bytes = A_BYTES + p.n_tile * 128;
+  int stages = (SMEM_LIMIT - 2048) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  // narrow tiles: stay under half of the shared memory so that two CTAs are resident (one's epilogue overlaps the other's main loop)
+  const int half = (SMEM_LIMIT / 2 - 2048) / stage_bytes;
+  if (half >= 3) stages = half > 4 ? 4 : half;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * MAX_STAGES + 2) + 1024;
+  const int n_tiles = (int)cdiv(a->Cout, p.n_tile);
+  cudaStream_t st = as_stream(s);
+  int rc;
+
+  // the (transposed ? Cout : Cin)-channel operand lives on the INPUT grid (Hi, Wi) of this launch
+  const int nclass = (a->transposed && a->stride == 2) ? 4 : 1;
+  for (int cls = 0; cls < nclass; ++cls) {
+    const int ph = cls >> 1, pw = cls & 1;
+    p.taps.n = 0;
+    if (!a->transposed) {
+      p.cs = a->stride; p.os = 1; p.oh0 = p.ow0 = 0; p.Hc = a->Ho; p.Wc = a->Wo;
+      for (int kh = 0; kh < a->kh; ++kh)
+        for (int kw = 0; kw < a->kw; ++kw) { int n = p.taps.n++; p.taps.dh[n] = kh - a->pad; p.taps.dw[n] = kw - a->pad; p.taps.widx[n] = kh * a->kw + kw; }
+    } else if (a->stride == 1) {
+      p.cs = 1; p.os = 1; p.oh0 = p.ow0 = 0; p.Hc = a->Ho; p.Wc = a->Wo;
+      for (int kh = 0; kh < a->kh; ++kh)
+        for (int kw = 0; kw < a->kw; ++kw) { int n = p.taps.n++; p.taps.dh[n] = a->pad - kh; p.taps.dw[n] = a->pad - kw; p.taps.widx[n] = kh * a->kw + kw; }
+    } else {
+      // output pixel (2i+ph, 2j+pw) <- dy pixel (i + (ph+pad-kh)/2, j + (pw+pad-kw)/2) for the taps where the division is exact
+      p.cs = 1; p.os = 2; p.oh0 = ph; p.ow0 = pw;
+      p.Hc = (a->Ho - ph + 1) / 2; p.Wc = (a->Wo - pw + 1) / 2;
+      for (int kh = 0; kh < a->kh; ++kh)
+        for (int kw = 0; kw < a->kw; ++kw) {
+          const int eh = ph + a->pad - kh, ew = pw + a->pad - kw;
+          if ((eh & 1) || (ew & 1)) continue;
+          int n = p.taps.n++; p.taps.dh[n] = eh / 2; p.taps.dw[n] = ew / 2; p.taps.widx[n] = kh * a->kw + kw;
+        }
+      if (p.Hc <= 0 || p.Wc <= 0) continue;
+      if (p.taps.n == 0) { set_error("gdn_conv2d_tc: parity class without taps is not supported (kernel smaller than stride)"); return GDN_EINVAL; }
+    }
+    tile_shape(p.Wc, &p.Wt, &p.Ht);
+    p.tiles_w = (int)cdiv(p.Wc, p.Wt); p.tiles_h = (int)cdiv(p.Hc, p.Ht);
+    CUtensorMap mxh, mxl, mwh, mwl;
+    if ((rc = make_act_map(&mxh, a->x_hi, Cp, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
+    mxl = mxh;
+    if (nsplit == 3 && (rc = make_act_map(&mxl, a->x_lo, Cp, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
+    if ((rc = make_weight_map(&mwh, a->w_hi, Cp, a->Cout, taps, p.n_tile)) != GDN_OK) return rc;
+    mwl = mwh;
+    if (nsplit == 3 && (rc = make_weight_map(&mwl, a->w_lo, Cp, a->Cout, taps, p.n_tile)) != GDN_OK) return rc;
+    dim3 grid((unsigned)((long long)a->B * p.tiles_h * p.tiles_w), (unsigned)n_tiles);
+    GDN_CHECK_ARG(grid.y <= 65535);
+    conv_tc_fwd_kernel<<<grid, NTHREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);
+    GDN_CHECK_LAUNCH();
+  }
+  return GDN_OK;
+}
+
+static void wgrad_plan(const gdn_wgrad_tc_args* a, WgParams* p) {
+  const int taps = a->kh * a->kw;
+  p->Cout = a->Cout; p->taps_total = taps; p->kw = a->kw; p->pad = a->pad; p->cs = a->stride;
+  p->ci_tile = a->Cin > 64 ? 128 : 64;
+  p->ci_tiles = (int)cdiv(a->Cin, p->ci_tile);
+  p->cin_w = p->ci_tiles * p->ci_tile;
+  p->co_tiles = (int)cdiv(a->Cout, 128);
+  p->taps_per_cta = a->kw;                       // one filter row per CTA: kw accumulators of ci_tile columns
+  p->tap_groups = a->kh;
+  p->tmem_cols = pow2_cols(p->taps_per_cta * p->ci_tile);
+  tile_shape(a->Wo, &p->Wt, &p->Ht);
+  p->tiles_w = (int)cdiv(a->Wo, p->Wt); p->tiles_h = (int)cdiv(a->Ho, p->Ht);
+  p->tiles_total = a->B * p->tiles_h * p->tiles_w;
+  const int units = p->co_tiles * p->ci_tiles * p->tap_groups;
+  int splits = (int)cdiv(2 * kNumSMs, units);
+  const int max_splits = p->tiles_total / 8 > 0 ? p->tiles_total / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
+  p->tiles_per_split = (int)cdiv(p->tiles_total, splits);
+  p->nsplit = a->precision == GDN_PREC_BF16X3 ? 3 : 1;
+}
+static int wgrad_splits(const WgParams* p) { return (int)cdiv(p->tiles_total, p->tiles_per_split); }
+
+extern "C" size_t gdn_conv2d_wgrad_tc_ws_bytes(const gdn_wgrad_tc_args* a) {
+  WgParams p;
+  wgrad_plan(a, &p);
+  return (size_t)wgrad_splits(&p) * a->Cout * p.taps_total * p.cin_w * sizeof(float);
+}
+
+extern "C" int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s) {
+  GDN_CHECK_ARG(a && a->dy_hi && a->x_hi && a->out && a->ws);
+  GDN_CHECK_ARG(a->B > 0 && a->Cin > 0 && a->Cout > 0 && a->kh > 0 && a->kw > 0 && a->kw <= 3 && a->kh <= 3 && (a->stride == 1 || a->stride == 2));
+  GDN_CHECK_ARG(a->out_cin_total >= a->out_c0 + a->Cin);
+  GDN_CHECK_ARG(a->precision == GDN_PREC_BF16 || (a->precision == GDN_PREC_BF16X3 && a->dy_lo && a->x_lo));
+  WgParams p;
+  wgrad_plan(a, &p);
+  const int splits = wgrad_splits(&p);
+  if (a->ws_bytes < gdn_conv2d_wgrad_tc_ws_bytes(a)) { set_error("gdn_conv2d_wgrad_tc: workspace too small"); return GDN_EWORKSPACE; }
+  GDN_CHECK_ARG(((uintptr_t)a->ws & 15) == 0);
+  p.ws = a->ws;
+  const int Cop = (a->Cout + 7) & ~7, Cip = (a->Cin + 7) & ~7;
+  CUtensorMap mdh, mdl, mxh, mxl;
+  int rc;
+  if ((rc = make_act_map(&mdh, a->dy_hi, Cop, a->Wo, a->Ho, a->B, p.Wt, p.Ht, 1)) != GDN_OK) return rc;
+  mdl = mdh;
+  if (p.nsplit == 3 && (rc = make_act_map(&mdl, a->dy_lo, Cop, a->Wo, a->Ho, a->B, p.Wt, p.Ht, 1)) != GDN_OK) return rc;
+  if ((rc = make_act_map(&mxh, a->x_hi, Cip, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
+  mxl = mxh;
+  if (p.nsplit == 3 && (rc = make_act_map(&mxl, a->x_lo, Cip, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
+  const size_t smem = (size_t)WG_DY_SLOTS * WG_DY_BYTES + (size_t)WG_X_SLOTS * (p.ci_tile / 64) * A_BYTES + 8 * (2 * WG_DY_SLOTS + 2 * WG_X_SLOTS + 2) + 1024;
+  dim3 grid((unsigned)(p.co_tiles * p.ci_tiles * p.tap_groups), (unsigned)splits);
+  GDN_CHECK_ARG(grid.y <= 65535);
+  cudaStream_t st = as_stream(s);
+  conv_tc_wgrad_kernel<<<grid, NTHREADS, smem, st>>>(mdh, mdl, mxh, mxl, p);
+  GDN_CHECK_LAUNCH();
+  const long long total = (long long)a->Cout * p.taps_total * a->Cin;
+  const int blocks = (int)(cdiv(total, 256) < 4 * kNumSMs ? cdiv(total, 256) : 4 * kNumSMs);
+  wgrad_tc_reduce_kernel<<<blocks, 256, 0, st>>>(a->ws, splits, a->Cout, a->Cin, p.taps_total, p.cin_w, a->out, a->out_cin_total, a->out_c0, a->accumulate, a->scale);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}

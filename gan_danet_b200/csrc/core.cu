@@ -75,7 +75,8 @@ using namespace gdn;
 extern "C" int gdn_version(void) { return 100; }
 extern "C" const char* gdn_last_error(void) { return g_err; }
 
-extern "C" int gdn_pam_tc_init(void);  // pam_tc.cu: opts the tcgen05 kernels into large dynamic shared memory
+extern "C" int gdn_pam_tc_init(void);   // pam_tc.cu: opts the tcgen05 kernels into large dynamic shared memory
+extern "C" int gdn_conv_tc_init(void);  // conv_tc.cu
 
 extern "C" int gdn_init(int device) {
   GDN_CHECK_CUDA(cudaSetDevice(device));
@@ -85,7 +86,9 @@ extern "C" int gdn_init(int device) {
     set_error("gdn_init: device %d is sm_%d%d, this library is sm_100a only", device, prop.major, prop.minor);
     return GDN_EARCH;
   }
-  return gdn_pam_tc_init();
+  int rc = gdn_pam_tc_init();
+  if (rc != GDN_OK) return rc;
+  return gdn_conv_tc_init();
 }
 
 extern "C" int gdn_nchw_to_nhwc(const float* src, float* dst, int dst_pitch, int dst_c0, int B, int C, int H, int W, gdn_stream_t s) {

@@ -12,12 +12,13 @@ PyTorch is used for memory, streams and autograd plumbing only; every arithmetic
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib as L
-from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, PREC_FP16, PREC_FP32
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, PREC_BF16, PREC_BF16X3, PREC_FP16, PREC_FP32
 
 Tensor = torch.Tensor
 
@@ -179,6 +180,164 @@ def wgrad_raw(dy: Tensor, x: Tensor, out: Tensor, *, kh: int, kw: int, stride: i
     L.check(lib.gdn_conv2d_wgrad(C.byref(a), _stream()), "gdn_conv2d_wgrad")
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# convolution precision: 'fp32' = CUDA-core engine (igemm_simt.cu); 'bf16' / 'bf16x3' = tcgen05 implicit GEMM (conv_tc.cu)
+# ----------------------------------------------------------------------------------------------------------------
+
+conv_precision: str = os.environ.get("GDN_CONV_PRECISION", "fp32").lower()
+_PREC = {"bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
+
+
+def set_conv_precision(p: str) -> None:
+    """'fp32' (CUDA-core parity engine), 'bf16' (tensor cores, bf16 operands) or 'bf16x3' (tensor cores, hi+lo split)."""
+    global conv_precision
+    p = p.lower()
+    if p not in ("fp32", "bf16", "bf16x3"):
+        raise ValueError(f"unknown conv precision {p!r}")
+    conv_precision = p
+
+
+def tc_eligible(cin: int, cout: int, kh: int, kw: int, stride: int, ho: int, wo: int) -> bool:
+    """Shapes the tensor-core kernel takes; the rest (fully connected layers, 1- and 3-channel inputs) stay on the
+    fp32 CUDA-core engine, which is HBM-bound there anyway."""
+    return (conv_precision in _PREC and kh == kw and kh in (1, 3) and stride in (1, 2) and cin >= 16 and ho * wo >= 32)
+
+
+class Packed:
+    """bf16 tensor-core operand: hi (and lo for the split precision), [rows, round_up(C, 8)]."""
+    __slots__ = ("hi", "lo", "C")
+
+    def __init__(self, hi: Tensor, lo: Optional[Tensor], Cc: int):
+        self.hi, self.lo, self.C = hi, lo, Cc
+
+
+def pack_act(x: Tensor, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0) -> Packed:
+    """fp32 NHWC view -> bf16 operand (optionally with a fused per-channel affine + activation, i.e. BatchNorm+ReLU)."""
+    M, Cc = rows_of(x), x.shape[-1]
+    Cp = (Cc + 7) // 8 * 8
+    split = conv_precision == "bf16x3"
+    hi = torch.empty((M, Cp), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((M, Cp), dtype=torch.bfloat16, device=x.device) if split else None
+    L.check(_lib(x).gdn_pack_act_bf16(x.data_ptr(), pitch_of(x), 0, M, Cc, hi.data_ptr(), _ptr(lo), _ptr(scale), _ptr(shift), act, slope, _stream()),
+            "gdn_pack_act_bf16")
+    return Packed(hi, lo, Cc)
+
+
+_frozen_weights: Dict[Tuple, Packed] = {}
+
+
+def pack_weight(w: Tensor, transposed: bool, frozen_key: Optional[Tuple] = None) -> Packed:
+    """OIHW fp32 weight -> bf16 GEMM operand [taps][rows][K_p8].  ``frozen_key`` caches the result (VGG19 weights)."""
+    split = conv_precision == "bf16x3"
+    key = None
+    if frozen_key is not None:
+        key = (frozen_key, transposed, split, w.data_ptr(), w._version)
+        hit = _frozen_weights.get(key)
+        if hit is not None:
+            return hit
+    O, I, kh, kw = w.shape
+    lib = _lib(w)
+    n = lib.gdn_pack_weight_bf16_elems(O, I, kh, kw, int(transposed))
+    hi = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty(n, dtype=torch.bfloat16, device=w.device) if split else None
+    wc = w.detach().contiguous()
+    L.check(lib.gdn_pack_weight_bf16(wc.data_ptr(), O, I, 0, I, kh, kw, int(transposed), hi.data_ptr(), _ptr(lo), _stream()), "gdn_pack_weight_bf16")
+    out = Packed(hi, lo, O if transposed else I)
+    if key is not None:
+        _frozen_weights[key] = out
+    return out
+
+
+def conv_tc_raw(xp: Packed, wp: Packed, y: Tensor, in_hw: Tuple[int, int], *, cin: int, kh: int, kw: int, stride: int = 1, pad: int = 0,
+                transposed: bool = False, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0, res: Optional[Tensor] = None) -> None:
+    """Tensor-core convolution on packed operands.  ``in_hw`` is the grid of the packed input operand; y: [B,Ho,Wo,Cout] view."""
+    a = L.ConvTcArgs()
+    B, Ho, Wo, Cout = y.shape
+    a.x_hi, a.x_lo, a.w_hi, a.w_lo = xp.hi.data_ptr(), _ptr(xp.lo), wp.hi.data_ptr(), _ptr(wp.lo)
+    a.y, a.y_pitch, a.y_c0 = y.data_ptr(), pitch_of(y), 0
+    a.bias = _ptr(bias)
+    if res is not None:
+        a.res, a.res_pitch, a.res_c0 = res.data_ptr(), pitch_of(res), 0
+    a.B, a.Hi, a.Wi, a.Cin, a.Ho, a.Wo, a.Cout = B, in_hw[0], in_hw[1], cin, Ho, Wo, Cout
+    a.kh, a.kw, a.stride, a.pad, a.transposed = kh, kw, stride, pad, int(transposed)
+    a.act, a.slope, a.precision = act, slope, _PREC[conv_precision]
+    L.check(_lib(y).gdn_conv2d_tc(C.byref(a), _stream()), "gdn_conv2d_tc")
+
+
+def wgrad_tc_raw(dyp: Packed, xp: Packed, out: Tensor, *, B: int, in_hw: Tuple[int, int], out_hw: Tuple[int, int], cin: int, cout: int, kh: int, kw: int,
+                 stride: int = 1, pad: int = 0, accumulate: bool = False) -> None:
+    """Tensor-core weight gradient into an OIHW tensor."""
+    lib = _lib(out)
+    a = L.WgradTcArgs()
+    a.dy_hi, a.dy_lo, a.x_hi, a.x_lo = dyp.hi.data_ptr(), _ptr(dyp.lo), xp.hi.data_ptr(), _ptr(xp.lo)
+    a.out, a.out_cin_total, a.out_c0, a.accumulate, a.scale = out.data_ptr(), cin, 0, int(accumulate), 1.0
+    a.B, a.Hi, a.Wi, a.Cin, a.Ho, a.Wo, a.Cout = B, in_hw[0], in_hw[1], cin, out_hw[0], out_hw[1], cout
+    a.kh, a.kw, a.stride, a.pad, a.precision = kh, kw, stride, pad, _PREC[conv_precision]
+    need = lib.gdn_conv2d_wgrad_tc_ws_bytes(C.byref(a))
+    buf = workspace("wgrad_tc", need, out.device)
+    a.ws, a.ws_bytes = buf.data_ptr(), buf.numel()
+    L.check(lib.gdn_conv2d_wgrad_tc(C.byref(a), _stream()), "gdn_conv2d_wgrad_tc")
+
+
+class ConvCtx:
+    """What a convolution keeps from its forward pass for the backward pass (the packed input on the tensor-core path)."""
+    __slots__ = ("tc", "xp")
+
+    def __init__(self, tc: bool, xp: Optional[Packed]):
+        self.tc, self.xp = tc, xp
+
+
+def conv_forward(x: Tensor, w: Tensor, y: Tensor, *, stride: int = 1, pad: int = 0, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0,
+                 res: Optional[Tensor] = None, frozen_key: Optional[Tuple] = None, keep: bool = True) -> ConvCtx:
+    """y = act(conv(x, w) + bias) + res for an OIHW weight; dispatches on ``conv_precision``."""
+    O, I, kh, kw = w.shape
+    B, Hi, Wi, Cin = x.shape
+    _, Ho, Wo, _ = y.shape
+    if tc_eligible(Cin, O, kh, kw, stride, Ho, Wo):
+        xp = pack_act(x)
+        conv_tc_raw(xp, pack_weight(w, False, frozen_key), y, (Hi, Wi), cin=Cin, kh=kh, kw=kw, stride=stride, pad=pad, bias=bias, act=act, slope=slope, res=res)
+        return ConvCtx(True, xp if keep else None)
+    if frozen_key is not None:
+        key = (frozen_key, "ohwi", w.data_ptr(), w._version)
+        w4 = _frozen_weights.get(key)
+        if w4 is None:
+            w4 = _frozen_weights[key] = weight_ohwi(w)
+    else:
+        w4 = weight_ohwi(w)
+    conv_raw(x, w4, y, kh=kh, kw=kw, stride=stride, pad=pad, bias=bias, act=act, slope=slope, res=res)
+    return ConvCtx(False, None)
+
+
+def conv_backward(ctx: ConvCtx, dz: Tensor, x: Tensor, w: Tensor, *, stride: int = 1, pad: int = 0, gw: Optional[Tensor] = None,
+                  gx: Optional[Tensor] = None, gx_accumulate: bool = False, frozen_key: Optional[Tuple] = None) -> None:
+    """Weight gradient into ``gw`` (OIHW, overwritten) and data gradient into ``gx`` (NHWC view; accumulated when asked)."""
+    O, I, kh, kw = w.shape
+    B, Hi, Wi, Cin = x.shape
+    _, Ho, Wo, _ = dz.shape
+    dzp: Optional[Packed] = None
+    if ctx.tc:
+        dzp = pack_act(dz)
+    if gw is not None:
+        if ctx.tc and O >= 16:
+            xp = ctx.xp if ctx.xp is not None else pack_act(x)
+            wgrad_tc_raw(dzp, xp, gw, B=B, in_hw=(Hi, Wi), out_hw=(Ho, Wo), cin=Cin, cout=O, kh=kh, kw=kw, stride=stride, pad=pad)
+        else:
+            wgrad_raw(dz, x, gw, kh=kh, kw=kw, stride=stride, pad=pad)
+    if gx is not None:
+        res = gx if gx_accumulate else None
+        if ctx.tc and tc_eligible(O, Cin, kh, kw, stride, Hi, Wi):
+            conv_tc_raw(dzp, pack_weight(w, True, frozen_key), gx, (Ho, Wo), cin=O, kh=kh, kw=kw, stride=stride, pad=pad, transposed=True, res=res)
+        else:
+            if frozen_key is not None:
+                key = (frozen_key, "ihwo", w.data_ptr(), w._version)
+                wt = _frozen_weights.get(key)
+                if wt is None:
+                    wt = _frozen_weights[key] = weight_ihwo(w)
+            else:
+                wt = weight_ihwo(w)
+            conv_raw(dz, wt, gx, kh=kh, kw=kw, stride=stride, pad=pad, transposed=True, res=res)
+
+
 def colstats(x: Tensor) -> Tensor:
     """double[2C]: per-channel sum and sum of squares over all rows of an NHWC view."""
     lib = _lib(x)
@@ -298,14 +457,13 @@ def op_conv(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, stride: int = 1,
     """nn.Conv2d (+ fused bias and activation).  ``w`` holds the OIHW parameter."""
     O, I, kh, kw = w.t.shape
     B, Hi, Wi, Cin = x.t.shape
-    w_eff = w.t
     assert Cin == I, f"conv: input has {Cin} channels, weight expects {I}"
     Ho = (Hi + 2 * pad - kh) // stride + 1
     Wo = (Wi + 2 * pad - kw) // stride + 1
     if out is None:
         out = Var(new_nhwc(B, Ho, Wo, O, x.t))
-    w4 = weight_ohwi(w_eff)
-    conv_raw(x.t, w4, out.t, kh=kh, kw=kw, stride=stride, pad=pad, bias=None if bias is None else bias.t.detach(), act=act, slope=slope)
+    cctx = conv_forward(x.t, w.t.detach(), out.t, stride=stride, pad=pad, bias=None if bias is None else bias.t.detach(), act=act, slope=slope,
+                        keep=tape.record and w.needs_grad)
     y = out
 
     def bwd():
@@ -319,14 +477,11 @@ def op_conv(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, stride: int = 1,
             dz = dy
         if bias is not None and bias.needs_grad:
             bias.add_grad(sums_to_float(colstats(dz), O))
-        if w.needs_grad:
-            gw = torch.empty_like(w.t)
-            wgrad_raw(dz, x.t, gw, kh=kh, kw=kw, stride=stride, pad=pad)
+        gw = torch.empty_like(w.t) if w.needs_grad else None
+        tgt, acc = x.grad_target() if x.needs_grad else (None, False)
+        conv_backward(cctx, dz, x.t, w.t.detach(), stride=stride, pad=pad, gw=gw, gx=tgt, gx_accumulate=acc)
+        if gw is not None:
             w.add_grad(gw)
-        if x.needs_grad:
-            tgt, acc = x.grad_target()
-            wt = weight_ihwo(w_eff)
-            conv_raw(dz, wt, tgt, kh=kh, kw=kw, stride=stride, pad=pad, transposed=True, res=tgt if acc else None)
 
     tape.push(bwd)
     return y
@@ -581,20 +736,17 @@ def op_conv_accumulate(tape: Tape, x: Var, w: Var, acc: Optional[Var]) -> Var:
     first = acc is None
     if first:
         acc = Var(new_nhwc(B, H, W, O, x.t))
-    w4 = weight_ohwi(w.t)
-    conv_raw(x.t, w4, acc.t, kh=kh, kw=kw, res=None if first else acc.t)
+    cctx = conv_forward(x.t, w.t.detach(), acc.t, res=None if first else acc.t, keep=tape.record and w.needs_grad)
     y = acc
 
     def bwd():
         if y.g is None:
             return
-        if w.needs_grad:
-            gw = torch.empty_like(w.t)
-            wgrad_raw(y.g, x.t, gw, kh=kh, kw=kw)
+        gw = torch.empty_like(w.t) if w.needs_grad else None
+        tgt, a2 = x.grad_target() if x.needs_grad else (None, False)
+        conv_backward(cctx, y.g, x.t, w.t.detach(), gw=gw, gx=tgt, gx_accumulate=a2)
+        if gw is not None:
             w.add_grad(gw)
-        if x.needs_grad:
-            tgt, a2 = x.grad_target()
-            conv_raw(y.g, weight_ihwo(w.t), tgt, kh=kh, kw=kw, transposed=True, res=tgt if a2 else None)
 
     tape.push(bwd)
     return y

@@ -221,18 +221,19 @@ class PerceptualLoss(nn.Module):
         self.vgg.eval()
         for param in self.vgg.parameters():
             param.requires_grad_(False)
-        self._wcache: Dict[Tuple[int, int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._wcache: Dict[Tuple, Tuple[torch.Tensor, Tuple]] = {}
 
-    def _weights(self, idx: int, conv: nn.Conv2d, cin: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(OHWI, IHWO) kernel operands of a frozen conv; a 1-channel input into conv1_1 uses the channel-summed
-        weight (x.repeat(1,3,1,1) == 1-channel conv with sum_c W[:, c], SURVEY appendix A identity 5)."""
-        key = (idx, cin, conv.weight._version)
+    def _weights(self, idx: int, conv: nn.Conv2d, cin: int) -> Tuple[torch.Tensor, Tuple]:
+        """(OIHW weight, cache key) of a frozen conv; a 1-channel input into conv1_1 uses the channel-summed weight
+        (x.repeat(1,3,1,1) == 1-channel conv with sum_c W[:, c], SURVEY appendix A identity 5).  The engine caches the
+        kernel operands (permuted fp32 or packed bf16) under the key."""
+        key = (id(self), idx, cin, conv.weight._version)
         hit = self._wcache.get(key)
         if hit is None:
             w = conv.weight.detach()
             if cin != w.shape[1]:
                 w = w.sum(dim=1, keepdim=True)      # frozen weights: done once, cached
-            hit = (E.weight_ohwi(w.contiguous()), E.weight_ihwo(w.contiguous()))
+            hit = (w.contiguous(), key)
             self._wcache[key] = hit
         return hit
 
@@ -258,13 +259,13 @@ class PerceptualLoss(nn.Module):
         return _PerceptualFn.apply(self, x, y)
 
 
-def _frozen_conv(tape: E.Tape, x: E.Var, w: Tuple[torch.Tensor, torch.Tensor], bias: torch.Tensor, relu: bool) -> E.Var:
-    w4, wt = w
-    O, kh, kw, _ = w4.shape
+def _frozen_conv(tape: E.Tape, x: E.Var, wk: Tuple[torch.Tensor, Tuple], bias: torch.Tensor, relu: bool) -> E.Var:
+    w, key = wk
+    O = w.shape[0]
     B, H, W, _ = x.t.shape
     y = E.Var(E.new_nhwc(B, H, W, O, x.t))
     act = ACT_RELU if relu else ACT_NONE
-    E.conv_raw(x.t, w4, y.t, kh=kh, kw=kw, pad=1, bias=bias, act=act)
+    cctx = E.conv_forward(x.t, w, y.t, pad=1, bias=bias, act=act, frozen_key=key, keep=False)
 
     def bwd():
         if y.g is None or not x.needs_grad:
@@ -274,7 +275,7 @@ def _frozen_conv(tape: E.Tape, x: E.Var, w: Tuple[torch.Tensor, torch.Tensor], b
             dz = torch.empty_like(y.g)
             E.act_bwd(y.g, y.t, dz, ACT_RELU, 0.0)
         tgt, acc = x.grad_target()
-        E.conv_raw(dz, wt, tgt, kh=kh, kw=kw, pad=1, transposed=True, res=tgt if acc else None)
+        E.conv_backward(cctx, dz, x.t, w, pad=1, gx=tgt, gx_accumulate=acc, frozen_key=key)
 
     tape.push(bwd)
     return y

@@ -38,7 +38,7 @@ typedef enum {
 } gdn_status;
 
 enum { GDN_ACT_NONE = 0, GDN_ACT_RELU = 1, GDN_ACT_LRELU = 2 };
-enum { GDN_PREC_FP32 = 0, GDN_PREC_BF16 = 1, GDN_PREC_FP16 = 2 };
+enum { GDN_PREC_FP32 = 0, GDN_PREC_BF16 = 1, GDN_PREC_FP16 = 2, GDN_PREC_BF16X3 = 3 };
 
 int gdn_version(void);
 const char* gdn_last_error(void);
@@ -102,6 +102,57 @@ int gdn_conv2d_wgrad(const gdn_wgrad_args* a, gdn_stream_t s);
 /* suggested split counts (pure host functions) */
 int gdn_conv2d_suggest_splits(const gdn_conv_args* a);
 int gdn_wgrad_suggest_splits(const gdn_wgrad_args* a);
+
+/* ------------------------------------------- tensor-core convolution (tcgen05) */
+/*
+ * The same convolutions as gdn_conv2d / gdn_conv2d_wgrad (nn.Conv2d at generator.py:34,63,108-110,148,188,214,218,222,
+ * discriminator.py:63-65, VGG19 of losses.py:58 and their autograd), as implicit GEMMs on the sm_100a tensor cores:
+ * TMA-tiled bf16 NHWC operands, tcgen05.mma with fp32 accumulation in TMEM, fused bias / activation / residual epilogue.
+ * precision GDN_PREC_BF16   : operands rounded to bf16 (the *_lo pointers are ignored)
+ *           GDN_PREC_BF16X3 : operands split hi = bf16(v), lo = bf16(v - hi); hi*hi + lo*hi + hi*lo (about 16 mantissa bits)
+ * Operands are produced by the two pack calls below; the caller owns them.
+ */
+/* fp32 NHWC slice -> bf16 [M][Cp], Cp = round_up(C, 8), zero padded.  v = act(x*scale[c] + shift[c]) when scale != NULL
+ * (BatchNorm + ReLU applied while packing), else v = x.  lo may be NULL. */
+int gdn_pack_act_bf16(const float* x, int x_pitch, int x_c0, long long M, int C, uint16_t* hi, uint16_t* lo,
+                      const float* scale, const float* shift, int act, float slope, gdn_stream_t s);
+/* OIHW fp32 weight (input channels [i_c0, i_c0+I) of I_total) -> bf16 [kh*kw][R][Kp]:
+ * transposed == 0: R = O, Kp = round_up(I, 8) (forward operand); transposed == 1: R = I, Kp = round_up(O, 8) (data gradient). */
+size_t gdn_pack_weight_bf16_elems(int O, int I, int kh, int kw, int transposed);
+int gdn_pack_weight_bf16(const float* w, int O, int I_total, int i_c0, int I, int kh, int kw, int transposed,
+                         uint16_t* hi, uint16_t* lo, gdn_stream_t s);
+/*
+ * y[b,ho,wo,n] = act(sum_{kh,kw,c} xin(b,ho,wo,kh,kw,c) * w[kh,kw][n][c] + bias[n]) + res[b,ho,wo,n]
+ * transposed == 0: forward, x is [B,Hi,Wi,Cin_p8] packed, w packed with transposed = 0.
+ * transposed == 1: data gradient: x is the packed OUTPUT gradient [B,Hi,Wi,(conv Cout)_p8] (so Cin here = conv Cout,
+ *                  Cout here = conv Cin, (Ho,Wo) = conv input grid), w packed with transposed = 1.  stride 1 or 2.
+ * res may alias y (accumulation).
+ */
+typedef struct {
+  const uint16_t* x_hi; const uint16_t* x_lo;
+  const uint16_t* w_hi; const uint16_t* w_lo;
+  float* y; int y_pitch, y_c0;
+  const float* bias;
+  const float* res; int res_pitch, res_c0;
+  int B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad, transposed;
+  int act; float slope;
+  int precision;
+} gdn_conv_tc_args;
+int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s);
+/*
+ * Weight gradient: out[co][out_c0+ci][kh][kw] (OIHW, out_cin_total input channels) (+)= scale * sum_pixels dy * x.
+ * dy: packed [B,Ho,Wo,Cout_p8]; x: packed [B,Hi,Wi,Cin_p8].  Deterministic (split-K through ws, fixed-order reduction).
+ */
+typedef struct {
+  const uint16_t* dy_hi; const uint16_t* dy_lo;
+  const uint16_t* x_hi; const uint16_t* x_lo;
+  float* out; int out_cin_total, out_c0, accumulate; float scale;
+  int B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad;
+  int precision;
+  float* ws; size_t ws_bytes;
+} gdn_wgrad_tc_args;
+size_t gdn_conv2d_wgrad_tc_ws_bytes(const gdn_wgrad_tc_args* a);
+int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s);
 
 /* ------------------------------------------------------------ elementwise */
 /* per-channel sums over M rows of an NHWC slice: out[0..C) = sum x, out[C..2C) = sum x*x (double).  BN statistics

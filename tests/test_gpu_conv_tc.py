@@ -1,0 +1,84 @@
+"""tcgen05 implicit-GEMM convolution (conv_tc.cu) against a float64 convolution of the same operands.
+
+``bf16``  : the kernel rounds x, w (and dy) to bf16 and accumulates in fp32, so it must agree with the float64 result computed
+            from the SAME bf16-rounded operands to fp32-accumulation accuracy (1e-5), and with the unrounded one to ~1e-2.
+``bf16x3``: hi+lo split operands; must agree with the float64 result of the UNROUNDED operands to 5e-5.
+Shapes: the reference's layer shapes (generator.py:34,63,148,188; discriminator.py:63-65) on small and ragged grids
+(45x22 is the authors' real grid).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+CASES = [
+    # B, Cin, Cout, H, W, k, stride, pad
+    (2, 46, 64, 16, 32, 3, 1, 1),
+    (1, 88, 24, 45, 22, 3, 1, 1),
+    (2, 320, 160, 8, 16, 3, 1, 1),
+    (2, 160, 80, 8, 16, 1, 1, 0),
+    (3, 184, 64, 64, 128, 1, 1, 0),
+    (2, 64, 128, 32, 64, 3, 2, 1),
+    (1, 128, 256, 45, 22, 3, 2, 1),
+    (2, 256, 512, 16, 32, 3, 2, 1),
+    (2, 64, 1, 32, 64, 3, 1, 1),
+    (1, 64, 64, 128, 256, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("case", CASES, ids=[f"b{c[0]}_{c[1]}to{c[2]}_{c[3]}x{c[4]}_k{c[5]}s{c[6]}" for c in CASES])
+def test_conv_tc(case, precision):
+    from gan_danet_b200 import engine as E
+    from gan_danet_b200._lib import ACT_LRELU, ACT_NONE
+    B, Cin, Cout, H, W, k, stride, pad = case
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(hash(case) & 0xFFFF)
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev)
+    bias = torch.randn(Cout, generator=g).to(dev)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = torch.randn(B, Ho, Wo, Cout, generator=g).to(dev)
+    dy = torch.randn(B, Ho, Wo, Cout, generator=g).to(dev)
+    old = E.conv_precision
+    E.set_conv_precision(precision)
+    try:
+        assert E.tc_eligible(Cin, Cout, k, k, stride, Ho, Wo)
+        y = torch.empty(B, Ho, Wo, Cout, device=dev)
+        ctx = E.conv_forward(x, w, y, stride=stride, pad=pad, bias=bias, act=ACT_LRELU, slope=0.2, res=res)
+        assert ctx.tc
+        y2 = torch.empty(B, Ho, Wo, Cout, device=dev)
+        ctx2 = E.conv_forward(x, w, y2, stride=stride, pad=pad)
+        gw = torch.empty_like(w)
+        gx = torch.randn(B, H, W, Cin, generator=g).to(dev)
+        gx0 = gx.clone()
+        E.conv_backward(ctx2, dy, x, w, stride=stride, pad=pad, gw=gw, gx=gx, gx_accumulate=True)
+        torch.cuda.synchronize()
+    finally:
+        E.set_conv_precision(old)
+
+    rnd = bf16_round if precision == "bf16" else (lambda t: t)
+    xr, wr, dyr = rnd(x).double(), rnd(w).double(), rnd(dy).double()
+    xn = xr.permute(0, 3, 1, 2).requires_grad_(True)
+    wn = wr.clone().requires_grad_(True)
+    yref = F.conv2d(xn, wn, None, stride=stride, padding=pad)
+    yref.backward(dyr.permute(0, 3, 1, 2))
+    y_plain = yref.detach().permute(0, 2, 3, 1)
+    y_full = F.leaky_relu(y_plain + bias.double(), 0.2) + res.double()
+    tol = 2e-5 if precision == "bf16" else 5e-5
+    assert rel(y2, y_plain) < tol, ("fwd", rel(y2, y_plain))
+    assert rel(y, y_full) < tol, ("fwd+epilogue", rel(y, y_full))
+    wtol = tol if Cout >= 16 else 1e-2      # Cout < 16: the weight gradient stays on the fp32 CUDA-core engine (unrounded operands)
+    assert rel(gw, wn.grad) < wtol, ("wgrad", rel(gw, wn.grad))
+    gx_ref = xn.grad.permute(0, 2, 3, 1) + gx0.double()
+    assert rel(gx, gx_ref) < tol, ("dgrad", rel(gx, gx_ref))
