@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--grid", default="64x128", help="generator-input / PAM grid h x w")
     ap.add_argument("--pam-precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--conv-precision", default="bf16", choices=["fp32", "bf16", "bf16x3"],
+                    help="convolutions: bf16 = tcgen05 tensor cores (BASELINE config dtype), bf16x3 = hi+lo split on tensor cores, fp32 = CUDA-core parity engine")
     ap.add_argument("--no-perceptual", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -179,6 +181,7 @@ def run_ours(args):
         perc.device = dev
     G, D = G.to(dev), D.to(dev)
     G.set_pam_precision(args.pam_precision)
+    E.set_conv_precision(args.conv_precision)
     if world > 1:
         for p in list(G.parameters()) + list(D.parameters()):
             dist.broadcast(p.data, 0)
@@ -252,9 +255,10 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "fp32 (PAM core: fp16 operands, fp32 accumulate)" if args.pam_precision == "fp16" else "fp32",
+                "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (hi+lo split)", "fp32": "fp32"}[args.conv_precision] + " operands, fp32 accumulate; fp32 activation storage"
+                         + ("; PAM core fp16 operands" if args.pam_precision == "fp16" else ""),
                 "data": "synthetic (seeded smooth random fields, random-init weights, random-init VGG19)",
-                "config": {"workload": workload_name(args, h, w), "global_batch": world * B, "parallelism": f"dp{world}",
+                "config": {"workload": workload_name(args, h, w), "global_batch": world * B, "parallelism": f"dp{world}", "conv": args.conv_precision,
                            "pam": "fused tcgen05 flash forward + fp32 backward" if args.pam_precision == "fp16" else "fp32 engine",
                            "l2": "inputs larger than L2 (the aux stack alone is %.0f MB per step)" % (aux_h.numel() * 4 / 1e6)},
                 "clocks": clk, "gpu_launches": launches,

@@ -81,4 +81,4 @@ def test_conv_tc(case, precision):
     wtol = tol if Cout >= 16 else 1e-2      # Cout < 16: the weight gradient stays on the fp32 CUDA-core engine (unrounded operands)
     assert rel(gw, wn.grad) < wtol, ("wgrad", rel(gw, wn.grad))
     gx_ref = xn.grad.permute(0, 2, 3, 1) + gx0.double()
-    assert rel(gx, gx_ref) < tol, ("dgrad", rel(gx, gx_ref))
+    assert rel(gx, gx_ref) < wtol, ("dgrad", rel(gx, gx_ref))   # Cout < 16: data gradient on the fp32 engine as well
