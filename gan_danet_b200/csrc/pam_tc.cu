@@ -15,6 +15,7 @@
 // The running row maximum is raised lazily (only when a tile exceeds it by > 8 in log2 units, so P <= 256 in fp16)
 // and O is then rescaled in TMEM by the softmax threads themselves; in steady state no rescale happens.
 // Operands: fp16 (bf16 logits are 8x worse), d zero-padded to 32, C zero-padded to 192.
+#include <cuda_bf16.h>
 #include "tc_common.cuh"
 
 namespace gdn {
@@ -288,9 +289,10 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 using namespace gdn;
 using namespace gdn::pamtc;
 
+extern "C" int gdn_pam_tc_bwd_init(void);
 extern "C" int gdn_pam_tc_init(void) {
   GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  return GDN_OK;
+  return gdn_pam_tc_bwd_init();
 }
 
 extern "C" size_t gdn_pam_tc_fwd_ws_bytes(const gdn_pam_fwd_args* a) {
@@ -331,9 +333,362 @@ extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
   return GDN_OK;
 }
 
-extern "C" size_t gdn_pam_tc_bwd_ws_bytes(const gdn_pam_bwd_args* a) { (void)a; return 0; }
+// =====================================================================================================================
+// Fused backward of the position-attention core (autograd of generator.py:115-122; formulas: SURVEY appendix C).
+// Two launches of ONE kernel template, both flash-style (the N x N maps P, dP, dS never leave the SM):
+//   MODE 0 (dQ)    : CTA = one sample x 128 query rows, loops over 64-key blocks
+//                    X = Q_i K_j^T, Y = dy_i V_j^T, P = exp(X - L_i), dS = P*(Y - rowdot_i), dQ_i += dS K_j
+//   MODE 1 (dK,dV) : CTA = one sample x 128 key rows, loops over 64-query blocks (everything transposed, so that the TMEM
+//                    lane is the key): X = K_j Q_i^T, Y = V_j dy_i^T, P^T, dS^T, dK_j += dS^T Q_i, dV_j += P^T dy_i
+//                    (dy_i is consumed from ONE shared-memory tile both as K-major B operand of Y and as MN-major B
+//                    operand of dV -- no transposed copy of dy exists).
+// gamma is folded into the epilogue (dO = gamma*dy): dQ, dK, dV are scaled by gamma on the way out.
+// Each CTA owns its output rows: no atomics, bitwise deterministic.
+// Operand precision: logits fp16 x fp16 (identical to the forward kernel, so P matches the saved log-sum-exp);
+// everything that carries gradient magnitude (dy, dS, P for dV) is bf16 (fp32 exponent range: no underflow of small gradients).
+//   warp 0: TMA producer   warp 1: tcgen05.mma issuer   warp 2: TMEM allocator   warps 4-11: softmax/dS (thread = TMEM lane = row)
+// TMEM: X0 X1 [0,128)  Y0 Y1 [128,256)  small accumulator (dQ | dK) [256,288)  dV [288,480)
+namespace gdn {
+namespace pamtc {
+namespace bwd {
+constexpr int TO = 128, TI = 64, NCH = CPAD / 64, ST = 3;
+constexpr int OQK_BYTES = TO * DPAD * 2;              // 8 KB  fp16 [128][32], SWIZZLE_64B
+constexpr int OC_CHUNK = TO * 128;                    // 16 KB bf16 [128][64], SWIZZLE_128B
+constexpr int IQK_BYTES = TI * DPAD * 2;              // 4 KB
+constexpr int IT_BYTES = DPAD * TI * 2;               // 4 KB  bf16 [32][64]
+constexpr int IC_CHUNK = TI * 128;                    // 8 KB  bf16 [64][64]
+constexpr int LR_BYTES = 2 * TI * 4;                  // lse | rowdot of the 64 inner rows (MODE 1)
+constexpr int OFF_OQK = 0;
+constexpr int OFF_OC = OFF_OQK + OQK_BYTES;           // 8192
+constexpr int OFF_IN = OFF_OC + NCH * OC_CHUNK;       // 57344
+constexpr int IN_IQK = 0, IN_IT = IQK_BYTES, IN_IC = IN_IT + IT_BYTES, IN_LR = IN_IC + NCH * IC_CHUNK;   // 0, 4096, 8192, 32768
+constexpr int IN_BYTES = 33 * 1024;                   // 33280 rounded up to a multiple of 1024
+constexpr int TILE_BYTES = TO * TI * 2;               // 16 KB bf16 [128][64]
+constexpr int OFF_PS = OFF_IN + ST * IN_BYTES;        // 158720
+constexpr int OFF_DS = OFF_PS + 2 * TILE_BYTES;       // 191488
+constexpr int OFF_BARS = OFF_DS + 2 * TILE_BYTES;     // 224256
+constexpr int OFF_TSLOT = OFF_BARS + 256;
+constexpr int SMEM = OFF_TSLOT + 16 + 1024;
+static_assert(SMEM <= 227 * 1024, "shared memory budget");
+enum { B_OUT = 0, B_INFULL = 1, B_INEMPTY = B_INFULL + ST, B_XFULL = B_INEMPTY + ST, B_YFULL = B_XFULL + 2, B_XFREE = B_YFULL + 2, B_YFREE = B_XFREE + 2,
+       B_DSFULL = B_YFREE + 2, B_DSFREE = B_DSFULL + 2, B_ACC = B_DSFREE + 2, B_COUNT = B_ACC + 1 };
+static_assert(B_COUNT * 8 <= 256, "barrier area");
+constexpr uint32_t COL_X = 0, COL_Y = 128, COL_SMALL = 256, COL_BIG = 288;
+
+// kind::f16 instruction descriptor for bf16 operands (see conv_tc.cu): b_mn = 1 makes B MN-major
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t smem_desc_lbo(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct Params {
+  const float* lse; const float* rowdot; const float* gamma;
+  float* dq; float* dk; float* dv;
+  int B, N, C, d;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_constant__ CUtensorMap mapKh, const __grid_constant__ CUtensorMap mapV,
+                     const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapQt, const __grid_constant__ CUtensorMap mapKt, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blocks_per_sample = p.N / TO;
+  const int sample = blockIdx.x / blocks_per_sample, oblk = blockIdx.x % blocks_per_sample;
+  const int T = p.N / TI;
+  const int row0 = sample * p.N + oblk * TO;           // first outer row in the flattened [B*N] row space
+  auto bar = [&](int i) { return base + OFF_BARS + 8 * i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + OFF_TSLOT);
+  const CUtensorMap* m_oqk = MODE == 0 ? &mapQh : &mapKh;
+  const CUtensorMap* m_iqk = MODE == 0 ? &mapKh : &mapQh;
+  const CUtensorMap* m_oc = MODE == 0 ? &mapDY : &mapV;
+  const CUtensorMap* m_ic = MODE == 0 ? &mapV : &mapDY;
+  const CUtensorMap* m_it = MODE == 0 ? &mapKt : &mapQt;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(B_OUT), 1);
+    for (int i = 0; i < ST; ++i) { mbar_init(bar(B_INFULL + i), 1); mbar_init(bar(B_INEMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(B_XFULL + i), 1); mbar_init(bar(B_YFULL + i), 1);
+      mbar_init(bar(B_XFREE + i), 8); mbar_init(bar(B_YFREE + i), 8);
+      mbar_init(bar(B_DSFULL + i), 8); mbar_init(bar(B_DSFREE + i), 1);
+    }
+    mbar_init(bar(B_ACC), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + OFF_TSLOT), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- TMA producer
+      mbar_expect_tx(bar(B_OUT), OQK_BYTES + NCH * OC_CHUNK);
+      tma_load_2d(base + OFF_OQK, m_oqk, bar(B_OUT), 0, row0);
+      tma_load_2d(base + OFF_OQK + OQK_BYTES / 2, m_oqk, bar(B_OUT), 0, row0 + 64);
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_2d(base + OFF_OC + c * OC_CHUNK, m_oc, bar(B_OUT), c * 64, row0);
+        tma_load_2d(base + OFF_OC + c * OC_CHUNK + OC_CHUNK / 2, m_oc, bar(B_OUT), c * 64, row0 + 64);
+      }
+      for (int t = 0; t < T; ++t) {
+        const int s = t % ST;
+        if (t >= ST) mbar_wait(bar(B_INEMPTY + s), ((t / ST) - 1) & 1);
+        const uint32_t st = base + OFF_IN + s * IN_BYTES;
+        const int irow = sample * p.N + t * TI;
+        mbar_expect_tx(bar(B_INFULL + s), IQK_BYTES + IT_BYTES + NCH * IC_CHUNK + (MODE == 1 ? LR_BYTES : 0));
+        tma_load_2d(st + IN_IQK, m_iqk, bar(B_INFULL + s), 0, irow);
+        tma_load_2d(st + IN_IT, m_it, bar(B_INFULL + s), t * TI, sample * DPAD);
+        for (int c = 0; c < NCH; ++c) tma_load_2d(st + IN_IC + c * IC_CHUNK, m_ic, bar(B_INFULL + s), c * 64, irow);
+        if (MODE == 1) {
+          bulk_load(st + IN_LR, p.lse + irow, TI * 4, bar(B_INFULL + s));
+          bulk_load(st + IN_LR + TI * 4, p.rowdot + irow, TI * 4, bar(B_INFULL + s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---- MMA issuer
+      constexpr uint32_t ID_X = idesc_f16(TO, TI), ID_Y = idesc_bf16(TO, TI, 0), ID_S = idesc_bf16(TO, DPAD, 0), ID_B = idesc_bf16(TO, CPAD, 1);
+      auto issue_xy = [&](int t) {
+        const int s = t % ST, b = t & 1;
+        const uint32_t st = base + OFF_IN + s * IN_BYTES;
+        mbar_wait(bar(B_INFULL + s), (t / ST) & 1);
+        if (t >= 2) { mbar_wait(bar(B_XFREE + b), ((t >> 1) - 1) & 1); mbar_wait(bar(B_YFREE + b), ((t >> 1) - 1) & 1); }
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < DPAD / 16; ++ks)
+          umma_f16(tmem + COL_X + b * TI, smem_desc(base + OFF_OQK + ks * 32, 512, LAYOUT_SW64), smem_desc(st + IN_IQK + ks * 32, 512, LAYOUT_SW64), ID_X, ks > 0);
+        tc_commit(bar(B_XFULL + b));
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(tmem + COL_Y + b * TI, smem_desc(base + OFF_OC + c * OC_CHUNK + ks * 32, 1024, LAYOUT_SW128),
+                     smem_desc(st + IN_IC + c * IC_CHUNK + ks * 32, 1024, LAYOUT_SW128), ID_Y, (c > 0 || ks > 0) ? 1u : 0u);
+        tc_commit(bar(B_YFULL + b));
+      };
+      mbar_wait(bar(B_OUT), 0);
+      issue_xy(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) issue_xy(t + 1);
+        const int s = t % ST, b = t & 1;
+        const uint32_t st = base + OFF_IN + s * IN_BYTES;
+        mbar_wait(bar(B_DSFULL + b), (t >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < TI / 16; ++ks)   // small accumulator += dS (K-major over the 64 inner rows) x inner^T tile [32][64]
+          umma_f16(tmem + COL_SMALL, smem_desc(base + OFF_DS + b * TILE_BYTES + ks * 32, 1024, LAYOUT_SW128), smem_desc(st + IN_IT + ks * 32, 1024, LAYOUT_SW128), ID_S,
+                   (t > 0 || ks > 0) ? 1u : 0u);
+        if (MODE == 1) {
+#pragma unroll
+          for (int ks = 0; ks < TI / 16; ++ks)   // dV += P^T x dy_i: B = the [64 q][192 ch] dy tile read MN-major (16 rows per step, 64-channel groups 8 KB apart)
+            umma_f16(tmem + COL_BIG, smem_desc(base + OFF_PS + b * TILE_BYTES + ks * 32, 1024, LAYOUT_SW128),
+                     smem_desc_lbo(st + IN_IC + ks * 2048, IC_CHUNK, 1024, LAYOUT_SW128), ID_B, (t > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc_commit(bar(B_DSFREE + b));
+        tc_commit(bar(B_INEMPTY + s));
+      }
+      tc_commit(bar(B_ACC));
+    }
+  } else if (warp >= 4) {
+    const int wg = (warp - 4) >> 2;                  // inner columns [wg*32, wg*32+32)
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;                  // TMEM lane = outer row
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const int col0 = wg * 32;
+    float L_row = 0.f, rd_row = 0.f;
+    if (MODE == 0) { L_row = __ldg(p.lse + row0 + row) * LOG2E; rd_row = __ldg(p.rowdot + row0 + row); }
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1, s = t % ST;
+      const float* lr = reinterpret_cast<const float*>(sm + OFF_IN + s * IN_BYTES + IN_LR);
+      if (MODE == 1) mbar_wait(bar(B_INFULL + s), (t / ST) & 1);   // lse/rowdot of the inner rows are in this stage
+      mbar_wait(bar(B_XFULL + b), (t >> 1) & 1);
+      tc_fence_after();
+      float x[32];
+      tmem_ld32(tmem + lane_addr + COL_X + b * TI + col0, x);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_XFREE + b));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float L = MODE == 0 ? L_row : lr[col0 + i] * LOG2E;
+        x[i] = ex2(fmaf(x[i], LOG2E, -L));            // P (<= 1)
+      }
+      mbar_wait(bar(B_YFULL + b), (t >> 1) & 1);
+      tc_fence_after();
+      float y[32];
+      tmem_ld32(tmem + lane_addr + COL_Y + b * TI + col0, y);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_YFREE + b));
+      uint32_t ds_pk[16], p_pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float r0 = MODE == 0 ? rd_row : lr[TI + col0 + i], r1 = MODE == 0 ? rd_row : lr[TI + col0 + i + 1];
+        __nv_bfloat162 dsv = __floats2bfloat162_rn(x[i] * (y[i] - r0), x[i + 1] * (y[i + 1] - r1));
+        ds_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&dsv);
+        if (MODE == 1) { __nv_bfloat162 pv = __floats2bfloat162_rn(x[i], x[i + 1]); p_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pv); }
+      }
+      if (t >= 2) mbar_wait(bar(B_DSFREE + b), ((t >> 1) - 1) & 1);
+      // K-major SWIZZLE_128B tile [128 rows][64]: row r at (r>>3)*1024 + (r&7)*128, 16-byte chunk index XOR (r&7)
+      uint8_t* drow = sm + OFF_DS + b * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+      uint8_t* prow = sm + OFF_PS + b * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int ch = ((wg * 4 + c) ^ (row & 7)) << 4;
+        *reinterpret_cast<uint4*>(drow + ch) = make_uint4(ds_pk[4 * c], ds_pk[4 * c + 1], ds_pk[4 * c + 2], ds_pk[4 * c + 3]);
+        if (MODE == 1) *reinterpret_cast<uint4*>(prow + ch) = make_uint4(p_pk[4 * c], p_pk[4 * c + 1], p_pk[4 * c + 2], p_pk[4 * c + 3]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_DSFULL + b));
+    }
+    // ---- epilogue
+    mbar_wait(bar(B_ACC), 0);
+    tc_fence_after();
+    const float g = __ldg(p.gamma);
+    const size_t grow = (size_t)row0 + row;
+    if (wg == 0) {
+      float a[32];
+      tmem_ld32(tmem + lane_addr + COL_SMALL, a);
+      float* dst = (MODE == 0 ? p.dq : p.dk) + grow * p.d;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < p.d) dst[i] = g * a[i];
+    }
+    if (MODE == 1) {
+#pragma unroll 1
+      for (int c = 0; c < CPAD / 2; c += 32) {
+        float a[32];
+        const int c0 = wg * (CPAD / 2) + c;
+        tmem_ld32(tmem + lane_addr + COL_BIG + c0, a);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const int ch = c0 + i;
+          if (ch < p.C) *reinterpret_cast<float4*>(p.dv + grow * p.C + ch) = make_float4(g * a[i], g * a[i + 1], g * a[i + 2], g * a[i + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// fp32 [rows][pitch] -> bf16 [rows][CPAD], zero padded
+__global__ void __launch_bounds__(256) pack_rows_bf16_kernel(const float* __restrict__ src, int pitch, int C, long long rows, __nv_bfloat16* __restrict__ dst) {
+  const long long total = rows * (CPAD / 8);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / (CPAD / 8); const int c0 = (int)(idx % (CPAD / 8)) * 8;
+    __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __float2bfloat16_rn(c0 + e < C ? __ldg(src + (size_t)r * pitch + c0 + e) : 0.f);
+    *reinterpret_cast<uint4*>(dst + (size_t)r * CPAD + c0) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+// fp32 [B][N][d] (pitch) -> bf16 [B][DPAD][N], zero rows for c >= d
+__global__ void __launch_bounds__(256) pack_t_bf16_kernel(const float* __restrict__ v, int pitch, int d, int N, __nv_bfloat16* __restrict__ vt) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i;
+    tile[i][tx] = (n < N && tx < d) ? v[((size_t)b * N + n) * pitch + tx] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + tx;
+    if (n < N) vt[((size_t)b * DPAD + i) * N + n] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+static int make_map_t(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("pam_tc: cuTensorMapEncodeTiled unavailable"); return GDN_ECUDA; }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("pam_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return GDN_ECUDA; }
+  return GDN_OK;
+}
+}  // namespace bwd
+}  // namespace pamtc
+}  // namespace gdn
+
+using namespace gdn::pamtc::bwd;
+
+extern "C" int gdn_pam_tc_bwd_init(void) {
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM));
+  return GDN_OK;
+}
+
+extern "C" size_t gdn_pam_tc_bwd_ws_bytes(const gdn_pam_bwd_args* a) {
+  const size_t rows = (size_t)a->B * a->N;
+  return 2 * align256(rows * DPAD * 2) + 2 * align256(rows * CPAD * 2) + 2 * align256((size_t)a->B * DPAD * a->N * 2);
+}
+
+// rowdot (= sum_c dy*o per row) has been computed by the caller (gdn_pam_bwd in attention.cu)
 extern "C" int gdn_pam_tc_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s) {
-  (void)a; (void)s;
-  set_error("gdn_pam_bwd: tensor-core backward not built yet; use GDN_PREC_FP32");
-  return GDN_EINVAL;
+  GDN_CHECK_ARG(a->precision == GDN_PREC_FP16);
+  GDN_CHECK_ARG(a->N % TO == 0 && a->d <= DPAD && a->C <= CPAD && a->C % 4 == 0);
+  GDN_CHECK_ARG(((uintptr_t)a->dv & 15) == 0 && ((uintptr_t)a->lse & 15) == 0 && ((uintptr_t)a->rowdot & 15) == 0);
+  if (!a->ws || a->ws_bytes < gdn_pam_tc_bwd_ws_bytes(a)) { set_error("gdn_pam_bwd(fp16): workspace too small"); return GDN_EWORKSPACE; }
+  const size_t rows = (size_t)a->B * a->N;
+  char* w = reinterpret_cast<char*>(a->ws);
+  __half* Qh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
+  __half* Kh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
+  __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(w); w += align256(rows * CPAD * 2);
+  __nv_bfloat16* DYb = reinterpret_cast<__nv_bfloat16*>(w); w += align256(rows * CPAD * 2);
+  __nv_bfloat16* Qt = reinterpret_cast<__nv_bfloat16*>(w); w += align256((size_t)a->B * DPAD * a->N * 2);
+  __nv_bfloat16* Kt = reinterpret_cast<__nv_bfloat16*>(w);
+  cudaStream_t st = as_stream(s);
+  const int pg = (int)(cdiv((long long)rows * DPAD, 256) < 16 * kNumSMs ? cdiv((long long)rows * DPAD, 256) : 16 * kNumSMs);
+  pack_qk_kernel<<<pg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, Qh, (long long)rows);
+  GDN_CHECK_LAUNCH();
+  pack_qk_kernel<<<pg, 256, 0, st>>>(a->k, a->qk_pitch, a->d, Kh, (long long)rows);
+  GDN_CHECK_LAUNCH();
+  const int rg = (int)(cdiv((long long)rows * (CPAD / 8), 256) < 16 * kNumSMs ? cdiv((long long)rows * (CPAD / 8), 256) : 16 * kNumSMs);
+  pack_rows_bf16_kernel<<<rg, 256, 0, st>>>(a->v, a->v_pitch, a->C, (long long)rows, Vb);
+  GDN_CHECK_LAUNCH();
+  pack_rows_bf16_kernel<<<rg, 256, 0, st>>>(a->dy, a->dy_pitch, a->C, (long long)rows, DYb);
+  GDN_CHECK_LAUNCH();
+  dim3 tg((unsigned)cdiv(a->N, 32), 1, (unsigned)a->B);
+  pack_t_bf16_kernel<<<tg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, a->N, Qt);
+  GDN_CHECK_LAUNCH();
+  pack_t_bf16_kernel<<<tg, 256, 0, st>>>(a->k, a->qk_pitch, a->d, a->N, Kt);
+  GDN_CHECK_LAUNCH();
+  CUtensorMap mq, mk, mv, mdy, mqt, mkt;
+  int rc;
+  if ((rc = make_map_t(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Qh, rows, DPAD, 64, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Kh, rows, DPAD, 64, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, Vb, rows, CPAD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, DYb, rows, CPAD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mqt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, Qt, (uint64_t)a->B * DPAD, (uint64_t)a->N, DPAD, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mkt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, Kt, (uint64_t)a->B * DPAD, (uint64_t)a->N, DPAD, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  bwd::Params p;
+  p.lse = a->lse; p.rowdot = a->rowdot; p.gamma = a->gamma; p.dq = a->dq; p.dk = a->dk; p.dv = a->dv;
+  p.B = a->B; p.N = a->N; p.C = a->C; p.d = a->d;
+  const int grid = a->B * (a->N / TO);
+  pam_flash_bwd_kernel<0><<<grid, NTHREADS, bwd::SMEM, st>>>(mq, mk, mv, mdy, mqt, mkt, p);
+  GDN_CHECK_LAUNCH();
+  pam_flash_bwd_kernel<1><<<grid, NTHREADS, bwd::SMEM, st>>>(mq, mk, mv, mdy, mqt, mkt, p);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
 }

@@ -42,6 +42,7 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 
 
 _workspaces: Dict[Tuple[int, str], Tensor] = {}
+pam_bwd_tensor_core: bool = os.environ.get("GDN_PAM_BWD", "tc").lower() != "fp32"   # fused tcgen05 backward when the forward ran on tensor cores
 pam_timing: Optional[list] = None   # set to [] by bench.py to collect (start, end, flops, precision) per PAM forward
 
 
@@ -632,7 +633,7 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
         b.o, b.lse, b.gamma = o.data_ptr(), lse.data_ptr(), gamma.t.data_ptr()
         b.dy, b.dy_pitch = dy.data_ptr(), pitch_of(dy)
         b.dq, b.dk, b.dv, b.rowdot = dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), rowdot.data_ptr()
-        b.B, b.N, b.C, b.precision, b.chunk = B, N, Cc, PREC_FP32, 0
+        b.B, b.N, b.C, b.precision, b.chunk = B, N, Cc, (precision if pam_bwd_tensor_core else PREC_FP32), 0
         need_b = lib.gdn_pam_bwd_ws_bytes(C.byref(b))
         wsb = workspace("pam", need_b, dev)
         b.ws, b.ws_bytes = wsb.data_ptr(), wsb.numel()
