@@ -315,18 +315,20 @@ def conv_backward(ctx: ConvCtx, dz: Tensor, x: Tensor, w: Tensor, *, stride: int
     O, I, kh, kw = w.shape
     B, Hi, Wi, Cin = x.shape
     _, Ho, Wo, _ = dz.shape
-    dzp: Optional[Packed] = None
-    if ctx.tc:
-        dzp = pack_act(dz)
+    # the backward GEMMs pick the tensor-core path on their own shapes: a 1-channel input (D conv1, VGG conv1_1) keeps its
+    # forward on the CUDA cores but its gradients have 64-channel operands
+    tc_w = gw is not None and tc_eligible(O, O, kh, kw, stride, Ho, Wo) and O >= 16
+    tc_x = gx is not None and tc_eligible(O, Cin, kh, kw, stride, Hi, Wi)
+    dzp: Optional[Packed] = pack_act(dz) if (tc_w or tc_x) else None
     if gw is not None:
-        if ctx.tc and O >= 16:
+        if tc_w:
             xp = ctx.xp if ctx.xp is not None else pack_act(x)
             wgrad_tc_raw(dzp, xp, gw, B=B, in_hw=(Hi, Wi), out_hw=(Ho, Wo), cin=Cin, cout=O, kh=kh, kw=kw, stride=stride, pad=pad)
         else:
             wgrad_raw(dz, x, gw, kh=kh, kw=kw, stride=stride, pad=pad)
     if gx is not None:
         res = gx if gx_accumulate else None
-        if ctx.tc and tc_eligible(O, Cin, kh, kw, stride, Hi, Wi):
+        if tc_x:
             conv_tc_raw(dzp, pack_weight(w, True, frozen_key), gx, (Ho, Wo), cin=O, kh=kh, kw=kw, stride=stride, pad=pad, transposed=True, res=res)
         else:
             if frozen_key is not None:
