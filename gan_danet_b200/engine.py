@@ -317,7 +317,7 @@ def conv_backward(ctx: ConvCtx, dz: Tensor, x: Tensor, w: Tensor, *, stride: int
     _, Ho, Wo, _ = dz.shape
     # the backward GEMMs pick the tensor-core path on their own shapes: a 1-channel input (D conv1, VGG conv1_1) keeps its
     # forward on the CUDA cores but its gradients have 64-channel operands
-    tc_w = gw is not None and tc_eligible(O, O, kh, kw, stride, Ho, Wo) and O >= 16
+    tc_w = gw is not None and tc_eligible(max(O, 16), O, kh, kw, stride, Ho, Wo)     # any Cout/Cin: narrow operands are zero-filled by TMA
     tc_x = gx is not None and tc_eligible(O, Cin, kh, kw, stride, Hi, Wi)
     dzp: Optional[Packed] = pack_act(dz) if (tc_w or tc_x) else None
     if gw is not None:

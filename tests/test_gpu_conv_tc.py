@@ -80,7 +80,7 @@ def test_conv_tc(case, precision):
     ftol = tol if fwd_tc else 1e-2          # Cin < 16: the forward stays on the fp32 CUDA-core engine (unrounded operands)
     assert rel(y2, y_plain) < ftol, ("fwd", rel(y2, y_plain))
     assert rel(y, y_full) < ftol, ("fwd+epilogue", rel(y, y_full))
-    wtol = tol if Cout >= 16 else 1e-2      # Cout < 16: the weight gradient stays on the fp32 CUDA-core engine (unrounded operands)
-    assert rel(gw, wn.grad) < wtol, ("wgrad", rel(gw, wn.grad))
+    assert rel(gw, wn.grad) < tol, ("wgrad", rel(gw, wn.grad))
+    wtol = tol if Cout >= 16 else 1e-2      # Cout < 16: the data gradient stays on the fp32 CUDA-core engine (unrounded operands)
     gx_ref = xn.grad.permute(0, 2, 3, 1) + gx0.double()
     assert rel(gx, gx_ref) < wtol, ("dgrad", rel(gx, gx_ref))   # Cout < 16: data gradient on the fp32 engine as well
