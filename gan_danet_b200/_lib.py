@@ -46,7 +46,7 @@ class ConvTcArgs(C.Structure):
                 ("res", _vp), ("res_pitch", _i), ("res_c0", _i),
                 ("B", _i), ("Hi", _i), ("Wi", _i), ("Cin", _i), ("Ho", _i), ("Wo", _i), ("Cout", _i),
                 ("kh", _i), ("kw", _i), ("stride", _i), ("pad", _i), ("transposed", _i),
-                ("act", _i), ("slope", _f), ("precision", _i)]
+                ("act", _i), ("slope", _f), ("precision", _i), ("alpha_ptr", _vp), ("groups", _i)]
 
 
 class WgradTcArgs(C.Structure):
@@ -54,7 +54,7 @@ class WgradTcArgs(C.Structure):
                 ("out", _vp), ("out_cin_total", _i), ("out_c0", _i), ("accumulate", _i), ("scale", _f),
                 ("B", _i), ("Hi", _i), ("Wi", _i), ("Cin", _i), ("Ho", _i), ("Wo", _i), ("Cout", _i),
                 ("kh", _i), ("kw", _i), ("stride", _i), ("pad", _i),
-                ("precision", _i), ("ws", _vp), ("ws_bytes", _sz)]
+                ("precision", _i), ("ws", _vp), ("ws_bytes", _sz), ("groups", _i), ("scale_ptr", _vp)]
 
 
 class PamFwdArgs(C.Structure):
@@ -120,6 +120,9 @@ SIGNATURES = {
     "gdn_cam_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_cam_bwd_ws_bytes": (_sz, [_i, _i, _i]),
     "gdn_cam_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
+    "gdn_cam_tc_ws_bytes": (_sz, [_i, _i, _i]),
+    "gdn_cam_fwd_tc": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "gdn_cam_bwd_tc": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "gdn_row_softmax": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
     "gdn_cam_softmax": (_i, [_vp, _vp, _i, _i, _vp]),
     "gdn_gamma_residual": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _ll, _i, _vp]),

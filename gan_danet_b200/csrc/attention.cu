@@ -308,3 +308,86 @@ extern "C" int gdn_cam_bwd(const float* x, int x_pitch, const float* gamma, cons
   return gdn_axpy(O, C, 0, dx, dx_pitch, 0, (long long)B * N, C, 1.f, accumulate, s);
 }
 
+// ------------------------------------------------------------------------------------------------ CAM on tensor cores
+// The same algebra as gdn_cam_fwd / gdn_cam_bwd with every contraction on tcgen05 (conv_tc.cu): the C x C energy and dA are
+// per-sample Gram matrices (grouped weight-gradient kernel, K = the N pixels, MN-major operands), the re-projections are
+// 1x1 convolutions with per-sample weights.  Operands are ALWAYS the hi+lo bf16 split (bf16x3): the energy reaches 1e4 and
+// softmax(-E) is nearly one-hot, plain bf16 is 2-7e-3 off.
+static inline size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
+extern "C" size_t gdn_cam_tc_ws_bytes(int B, int N, int C) {
+  const size_t Cp = (size_t)((C + 7) & ~7);
+  return 4 * a256((size_t)B * N * Cp * 2) + 4 * a256((size_t)B * C * Cp * 2) + a256((size_t)B * N * C * 4) + 3 * a256((size_t)B * C * C * 4) + a256((size_t)B * C * 4);
+}
+namespace {
+struct CamWs {
+  uint16_t *xh, *xl, *dyh, *dyl, *w1h, *w1l, *w2h, *w2l;
+  float *O, *dA, *G, *AT, *rs;
+};
+CamWs cam_carve(void* ws, int B, int N, int C) {
+  const size_t Cp = (size_t)((C + 7) & ~7);
+  char* w = reinterpret_cast<char*>(ws);
+  CamWs r;
+  auto take = [&](size_t bytes) { char* p = w; w += a256(bytes); return p; };
+  r.xh = (uint16_t*)take((size_t)B * N * Cp * 2); r.xl = (uint16_t*)take((size_t)B * N * Cp * 2);
+  r.dyh = (uint16_t*)take((size_t)B * N * Cp * 2); r.dyl = (uint16_t*)take((size_t)B * N * Cp * 2);
+  r.w1h = (uint16_t*)take((size_t)B * C * Cp * 2); r.w1l = (uint16_t*)take((size_t)B * C * Cp * 2);
+  r.w2h = (uint16_t*)take((size_t)B * C * Cp * 2); r.w2l = (uint16_t*)take((size_t)B * C * Cp * 2);
+  r.O = (float*)take((size_t)B * N * C * 4);
+  r.dA = (float*)take((size_t)B * C * C * 4); r.G = (float*)take((size_t)B * C * C * 4); r.AT = (float*)take((size_t)B * C * C * 4);
+  r.rs = (float*)take((size_t)B * C * 4);
+  return r;
+}
+// out[b] (C x C) = scale * A_b^T B_b over the N pixels
+int cam_gram(const uint16_t* ah, const uint16_t* al, const uint16_t* bh, const uint16_t* bl, float* out, const float* scale_ptr, int B, int N, int C, gdn_stream_t s) {
+  gdn_wgrad_tc_args g = {};
+  g.dy_hi = ah; g.dy_lo = al; g.x_hi = bh; g.x_lo = bl; g.out = out; g.out_cin_total = C; g.scale = 1.f;
+  g.B = B; g.Hi = 1; g.Wi = N; g.Cin = C; g.Ho = 1; g.Wo = N; g.Cout = C; g.kh = g.kw = 1; g.stride = 1; g.pad = 0;
+  g.precision = GDN_PREC_BF16X3; g.groups = B; g.scale_ptr = scale_ptr;
+  return gdn_conv2d_wgrad_tc(&g, s);
+}
+// y[b][n][:] = alpha * W_b x[b][n][:] + res   with W_b = w[b] ([C][C] row-major fp32, packed here)
+int cam_project(const uint16_t* xh, const uint16_t* xl, const float* w, uint16_t* wh, uint16_t* wl, float* y, int y_pitch, const float* alpha_ptr,
+                const float* res, int res_pitch, int B, int N, int C, gdn_stream_t s) {
+  int rc = gdn_pack_weight_bf16(w, B * C, C, 0, C, 1, 1, 0, wh, wl, s);
+  if (rc != GDN_OK) return rc;
+  gdn_conv_tc_args c = {};
+  c.x_hi = xh; c.x_lo = xl; c.w_hi = wh; c.w_lo = wl; c.y = y; c.y_pitch = y_pitch; c.res = res; c.res_pitch = res_pitch;
+  c.B = B; c.Hi = 1; c.Wi = N; c.Cin = C; c.Ho = 1; c.Wo = N; c.Cout = C; c.kh = c.kw = 1; c.stride = 1; c.pad = 0;
+  c.precision = GDN_PREC_BF16X3; c.alpha_ptr = alpha_ptr; c.groups = B;
+  return gdn_conv2d_tc(&c, s);
+}
+}  // namespace
+
+extern "C" int gdn_cam_fwd_tc(const float* x, int x_pitch, const float* gamma, float* attn, float* y, int y_pitch, int B, int N, int C,
+                              void* ws, size_t ws_bytes, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && gamma && attn && y && ws && B > 0 && N > 0 && C > 0 && C % 4 == 0 && x_pitch >= C && y_pitch >= C);
+  if (ws_bytes < gdn_cam_tc_ws_bytes(B, N, C)) { set_error("gdn_cam_fwd_tc: workspace too small"); return GDN_EWORKSPACE; }
+  CamWs w = cam_carve(ws, B, N, C);
+  int rc;
+  if ((rc = gdn_pack_act_bf16(x, x_pitch, 0, (long long)B * N, C, w.xh, w.xl, nullptr, nullptr, GDN_ACT_NONE, 0.f, s)) != GDN_OK) return rc;
+  if ((rc = cam_gram(w.xh, w.xl, w.xh, w.xl, attn, nullptr, B, N, C, s)) != GDN_OK) return rc;              // energy = bmm(x, x^T)   (generator.py:131-132)
+  if ((rc = gdn_row_softmax(attn, attn, (long long)B * C, C, 1, nullptr, s)) != GDN_OK) return rc;           // softmax(rowmax - E)     (:135-136)
+  return cam_project(w.xh, w.xl, attn, w.w1h, w.w1l, y, y_pitch, gamma, x, x_pitch, B, N, C, s);             // gamma*bmm(attn, x) + x  (:138-139)
+}
+
+extern "C" int gdn_cam_bwd_tc(const float* x, int x_pitch, const float* gamma, const float* attn, const float* dy, int dy_pitch,
+                              float* dx, int dx_pitch, int accumulate, float* dgamma, int B, int N, int C, void* ws, size_t ws_bytes, void* dot_ws, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && gamma && attn && dy && dx && dgamma && ws && dot_ws && B > 0 && N > 0 && C > 0 && C % 4 == 0);
+  GDN_CHECK_ARG(x_pitch >= C && dy_pitch >= C && dx_pitch >= C);
+  if (ws_bytes < gdn_cam_tc_ws_bytes(B, N, C)) { set_error("gdn_cam_bwd_tc: workspace too small"); return GDN_EWORKSPACE; }
+  CamWs w = cam_carve(ws, B, N, C);
+  int rc;
+  if ((rc = gdn_pack_act_bf16(x, x_pitch, 0, (long long)B * N, C, w.xh, w.xl, nullptr, nullptr, GDN_ACT_NONE, 0.f, s)) != GDN_OK) return rc;
+  if ((rc = gdn_pack_act_bf16(dy, dy_pitch, 0, (long long)B * N, C, w.dyh, w.dyl, nullptr, nullptr, GDN_ACT_NONE, 0.f, s)) != GDN_OK) return rc;
+  // O = attn x (recomputed); dgamma = sum dy*O
+  if ((rc = cam_project(w.xh, w.xl, attn, w.w1h, w.w1l, w.O, C, nullptr, nullptr, 0, B, N, C, s)) != GDN_OK) return rc;
+  if ((rc = gdn_dot(dy, dy_pitch, 0, w.O, C, 0, (long long)B * N, C, dgamma, dot_ws, s)) != GDN_OK) return rc;
+  // dA[i][j] = gamma * sum_n dy[n][i] x[n][j]
+  if ((rc = cam_gram(w.dyh, w.dyl, w.xh, w.xl, w.dA, gamma, B, N, C, s)) != GDN_OK) return rc;
+  cam_de_kernel<<<B, 256, 0, as_stream(s)>>>(attn, w.dA, w.G, w.AT, w.rs, C);
+  GDN_CHECK_LAUNCH();
+  // O = dy + gamma * dy A ; O += G x ; dx (+)= O
+  if ((rc = cam_project(w.dyh, w.dyl, w.AT, w.w1h, w.w1l, w.O, C, gamma, dy, dy_pitch, B, N, C, s)) != GDN_OK) return rc;
+  if ((rc = cam_project(w.xh, w.xl, w.G, w.w2h, w.w2l, w.O, C, nullptr, w.O, C, B, N, C, s)) != GDN_OK) return rc;
+  return gdn_axpy(w.O, C, 0, dx, dx_pitch, 0, (long long)B * N, C, 1.f, accumulate, s);
+}

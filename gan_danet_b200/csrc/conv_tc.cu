@@ -51,7 +51,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 struct TapList { int n; int dh[9], dw[9], widx[9]; };
 
 struct FwdParams {
-  float* y; int y_pitch; const float* bias; const float* res; int res_pitch;
+  float* y; int y_pitch; const float* bias; const float* res; int res_pitch; const float* alpha_ptr;
+  int imgs_per_group, taps_total;   // per-sample weights (CAM): weight tap coordinate = tap + (img / imgs_per_group) * taps_total
   int B, Ho, Wo, Cout;        // output tensor (pixels are written at (i*os + oh0, j*os + ow0))
   int Hc, Wc, os, oh0, ow0;   // extent of the tile grid and the output scatter
   int Wt, Ht, tiles_w, tiles_h;
@@ -111,7 +112,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
             if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
             mbar_expect_tx(full(s), stage_bytes);
             tma_load_4d(base + s * stage_bytes, mx, full(s), kc * BK, cw, ch, img);
-            tma_load_3d(base + s * stage_bytes + A_BYTES, mw, full(s), kc * BK, n0, p.taps.widx[tp]);
+            tma_load_3d(base + s * stage_bytes + A_BYTES, mw, full(s), kc * BK, n0, p.taps.widx[tp] + (img / p.imgs_per_group) * p.taps_total);
           }
         }
       }
@@ -143,6 +144,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
     const float* rrow = p.res ? p.res + pix * p.res_pitch : nullptr;
     mbar_wait(acc_bar, 0);
     tc_fence_after();
+    const float alpha = p.alpha_ptr ? __ldg(p.alpha_ptr) : 1.f;
     for (int c = 0; c < p.n_tile; c += 32) {
       float v[32];
       // n_tile is a multiple of 16: the last chunk may be half wide; TMEM columns up to the power-of-two allocation exist
@@ -154,7 +156,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
         const int n = nb + e;
         if (n >= p.Cout || c + e >= p.n_tile) break;
         if (p.vec4) {   // Cout, pitches and channel offsets are multiples of 4
-          float4 o = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          float4 o = make_float4(alpha * v[e], alpha * v[e + 1], alpha * v[e + 2], alpha * v[e + 3]);
           if (p.bias) { const float4 bb = *reinterpret_cast<const float4*>(p.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
           o.x = apply_act(o.x, p.act, p.slope); o.y = apply_act(o.y, p.act, p.slope); o.z = apply_act(o.z, p.act, p.slope); o.w = apply_act(o.w, p.act, p.slope);
           if (rrow) { const float4 rr = *reinterpret_cast<const float4*>(rrow + n); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
@@ -163,7 +165,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (n + u < p.Cout) {
-              float o = v[e + u] + (p.bias ? __ldg(p.bias + n + u) : 0.f);
+              float o = alpha * v[e + u] + (p.bias ? __ldg(p.bias + n + u) : 0.f);
               o = apply_act(o, p.act, p.slope);
               if (rrow) o += rrow[n + u];
               yrow[n + u] = o;
@@ -186,6 +188,7 @@ constexpr int WG_DY_SLOTS = 2, WG_X_SLOTS = 4;
 constexpr int WG_DY_BYTES = 2 * A_BYTES;    // [128 px][64 co] x 2 channel boxes (UMMA M = 128 output channels)
 
 struct WgParams {
+  float* direct; int direct_pitch, Cin; const float* scale_ptr;   // grouped mode (one split per sample): out[split][co][ci] = scale * acc, no reduction pass
   float* ws;                   // [splits][Cout][taps][cin_w] fp32 partial sums
   int Cout, cin_w, taps_total;
   int tiles_w, tiles_h, tiles_total, tiles_per_split;
@@ -305,14 +308,19 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDYhi, const __grid_c
     const int co = cot * 128 + q * 32 + lane;
     mbar_wait(acc_bar, 0);
     tc_fence_after();
+    const float scale = (p.direct && p.scale_ptr) ? __ldg(p.scale_ptr) : 1.f;
     for (int tl = 0; tl < p.taps_per_cta; ++tl) {
-      float* dst = p.ws + (((size_t)split * p.Cout + co) * p.taps_total + (tap0 + tl)) * p.cin_w + (size_t)cit * p.ci_tile;
+      float* dst = p.direct ? p.direct + ((size_t)split * p.Cout + co) * p.direct_pitch + (size_t)cit * p.ci_tile
+                            : p.ws + (((size_t)split * p.Cout + co) * p.taps_total + (tap0 + tl)) * p.cin_w + (size_t)cit * p.ci_tile;
       for (int c = 0; c < p.ci_tile; c += 32) {
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tl * p.ci_tile + c, v);
         if (co < p.Cout) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(dst + c + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          for (int e = 0; e < 32; e += 4) {
+            if (p.direct && cit * p.ci_tile + c + e >= p.Cin) break;      // Cin is a multiple of 4 in direct mode
+            *reinterpret_cast<float4*>(dst + c + e) = make_float4(scale * v[e], scale * v[e + 1], scale * v[e + 2], scale * v[e + 3]);
+          }
         }
       }
     }
@@ -469,9 +477,16 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
   FwdParams p;
   p.y = a->y + a->y_c0; p.y_pitch = a->y_pitch; p.bias = a->bias;
   p.res = a->res ? a->res + a->res_c0 : nullptr; p.res_pitch = a->res_pitch;
+  p.alpha_ptr = a->alpha_ptr;
+  const int groups = a->groups > 1 ? a->groups : 1;
+  GDN_CHECK_ARG(a->B % groups == 0);
+  p.imgs_per_group = a->B / groups; p.taps_total = a->kh * a->kw;
   p.B = a->B; p.Ho = a->Ho; p.Wo = a->Wo; p.Cout = a->Cout;
   p.kchunks = (int)cdiv(a->Cin, BK);
-  p.n_tile = a->Cout <= 256 ? (int)cdiv(a->Cout, 16) * 16 : 256;
+  {  // balanced N tiles: 368 output channels -> 2 x 192 instead of 256 + 112
+    const int nt = (int)cdiv(a->Cout, 256);
+    p.n_tile = (int)cdiv(cdiv(a->Cout, nt), 16) * 16;
+  }
   p.nsplit = nsplit;
   p.tmem_cols = pow2_cols(p.n_tile);
   p.act = a->act; p.slope = a->slope;
@@ -521,9 +536,9 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     if ((rc = make_act_map(&mxh, a->x_hi, Cp, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
     mxl = mxh;
     if (nsplit == 3 && (rc = make_act_map(&mxl, a->x_lo, Cp, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
-    if ((rc = make_weight_map(&mwh, a->w_hi, Cp, a->Cout, taps, p.n_tile)) != GDN_OK) return rc;
+    if ((rc = make_weight_map(&mwh, a->w_hi, Cp, a->Cout, taps * groups, p.n_tile)) != GDN_OK) return rc;
     mwl = mwh;
-    if (nsplit == 3 && (rc = make_weight_map(&mwl, a->w_lo, Cp, a->Cout, taps, p.n_tile)) != GDN_OK) return rc;
+    if (nsplit == 3 && (rc = make_weight_map(&mwl, a->w_lo, Cp, a->Cout, taps * groups, p.n_tile)) != GDN_OK) return rc;
     dim3 grid((unsigned)((long long)a->B * p.tiles_h * p.tiles_w), (unsigned)n_tiles);
     GDN_CHECK_ARG(grid.y <= 65535);
     conv_tc_fwd_kernel<<<grid, NTHREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);
@@ -534,6 +549,7 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
 
 static void wgrad_plan(const gdn_wgrad_tc_args* a, WgParams* p) {
   const int taps = a->kh * a->kw;
+  p->direct = nullptr; p->direct_pitch = 0; p->Cin = a->Cin; p->scale_ptr = nullptr;
   p->Cout = a->Cout; p->taps_total = taps; p->kw = a->kw; p->pad = a->pad; p->cs = a->stride;
   p->ci_tile = a->Cin > 64 ? 128 : 64;
   p->ci_tiles = (int)cdiv(a->Cin, p->ci_tile);
@@ -550,18 +566,21 @@ static void wgrad_plan(const gdn_wgrad_tc_args* a, WgParams* p) {
   const int max_splits = p->tiles_total / 8 > 0 ? p->tiles_total / 8 : 1;
   if (splits > max_splits) splits = max_splits;
   p->tiles_per_split = (int)cdiv(p->tiles_total, splits);
+  if (a->groups > 1) p->tiles_per_split = p->tiles_total / a->groups;     // grouped: exactly one split per sample
   p->nsplit = a->precision == GDN_PREC_BF16X3 ? 3 : 1;
 }
 static int wgrad_splits(const WgParams* p) { return (int)cdiv(p->tiles_total, p->tiles_per_split); }
 
 extern "C" size_t gdn_conv2d_wgrad_tc_ws_bytes(const gdn_wgrad_tc_args* a) {
+  if (a->groups > 1) return 0;
   WgParams p;
   wgrad_plan(a, &p);
   return (size_t)wgrad_splits(&p) * a->Cout * p.taps_total * p.cin_w * sizeof(float);
 }
 
 extern "C" int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s) {
-  GDN_CHECK_ARG(a && a->dy_hi && a->x_hi && a->out && a->ws);
+  GDN_CHECK_ARG(a && a->dy_hi && a->x_hi && a->out && (a->ws || a->groups > 1));
+  GDN_CHECK_ARG(a->groups <= 1 || (a->groups == a->B && a->kh == 1 && a->kw == 1 && a->Cin % 4 == 0 && !a->accumulate && ((uintptr_t)a->out & 15) == 0));
   GDN_CHECK_ARG(a->B > 0 && a->Cin > 0 && a->Cout > 0 && a->kh > 0 && a->kw > 0 && a->kw <= 3 && a->kh <= 3 && (a->stride == 1 || a->stride == 2));
   GDN_CHECK_ARG(a->out_cin_total >= a->out_c0 + a->Cin);
   GDN_CHECK_ARG(a->precision == GDN_PREC_BF16 || (a->precision == GDN_PREC_BF16X3 && a->dy_lo && a->x_lo));
@@ -571,6 +590,7 @@ extern "C" int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s) {
   if (a->ws_bytes < gdn_conv2d_wgrad_tc_ws_bytes(a)) { set_error("gdn_conv2d_wgrad_tc: workspace too small"); return GDN_EWORKSPACE; }
   GDN_CHECK_ARG(((uintptr_t)a->ws & 15) == 0);
   p.ws = a->ws;
+  if (a->groups > 1) { p.direct = a->out; p.direct_pitch = a->Cin; p.scale_ptr = a->scale_ptr; }
   const int Cop = (a->Cout + 7) & ~7, Cip = (a->Cin + 7) & ~7;
   CUtensorMap mdh, mdl, mxh, mxl;
   int rc;
@@ -586,6 +606,7 @@ extern "C" int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s) {
   cudaStream_t st = as_stream(s);
   conv_tc_wgrad_kernel<<<grid, NTHREADS, smem, st>>>(mdh, mdl, mxh, mxl, p);
   GDN_CHECK_LAUNCH();
+  if (a->groups > 1) return GDN_OK;
   const long long total = (long long)a->Cout * p.taps_total * a->Cin;
   const int blocks = (int)(cdiv(total, 256) < 4 * kNumSMs ? cdiv(total, 256) : 4 * kNumSMs);
   wgrad_tc_reduce_kernel<<<blocks, 256, 0, st>>>(a->ws, splits, a->Cout, a->Cin, p.taps_total, p.cin_w, a->out, a->out_cin_total, a->out_c0, a->accumulate, a->scale);

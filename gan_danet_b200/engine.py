@@ -661,6 +661,14 @@ def _accumulate(x: Var, g: Tensor) -> None:
     axpy(g, tgt, 1.0, acc)
 
 
+cam_tensor_core: Optional[bool] = None     # None: follow conv_precision (tensor cores unless 'fp32'); True / False force it
+
+
+def _cam_tc(Cc: int) -> bool:
+    use = cam_tensor_core if cam_tensor_core is not None else conv_precision in _PREC
+    return bool(use) and Cc % 4 == 0
+
+
 def op_cam(tape: Tape, x: Var, gamma: Var, *, out: Optional[Var] = None) -> Var:
     """Channel attention: y = gamma * softmax(rowmax(E)-E) X + x with E = X X^T  (generator.py:128-139)."""
     lib = _lib(x.t)
@@ -670,19 +678,30 @@ def op_cam(tape: Tape, x: Var, gamma: Var, *, out: Optional[Var] = None) -> Var:
     if out is None:
         out = Var(torch.empty(x.t.shape, dtype=torch.float32, device=dev))
     attn = torch.empty((B, Cc, Cc), dtype=torch.float32, device=dev)
-    L.check(lib.gdn_cam_fwd(x.t.data_ptr(), pitch_of(x.t), gamma.t.data_ptr(), attn.data_ptr(), out.t.data_ptr(), pitch_of(out.t), B, N, Cc, _stream()), "gdn_cam_fwd")
+    tc = _cam_tc(Cc)
+    if tc:
+        buf = workspace("cam_tc", lib.gdn_cam_tc_ws_bytes(B, N, Cc), dev)
+        L.check(lib.gdn_cam_fwd_tc(x.t.data_ptr(), pitch_of(x.t), gamma.t.data_ptr(), attn.data_ptr(), out.t.data_ptr(), pitch_of(out.t), B, N, Cc,
+                                   buf.data_ptr(), buf.numel(), _stream()), "gdn_cam_fwd_tc")
+    else:
+        L.check(lib.gdn_cam_fwd(x.t.data_ptr(), pitch_of(x.t), gamma.t.data_ptr(), attn.data_ptr(), out.t.data_ptr(), pitch_of(out.t), B, N, Cc, _stream()), "gdn_cam_fwd")
     y = out
 
     def bwd():
         if y.g is None:
             return
         dy = y.g
-        need = lib.gdn_cam_bwd_ws_bytes(B, N, Cc)
-        buf = workspace("cam", need, dev)
         dgamma = torch.empty(1, dtype=torch.float32, device=dev)
         tgt, acc = x.grad_target()
-        L.check(lib.gdn_cam_bwd(x.t.data_ptr(), pitch_of(x.t), gamma.t.data_ptr(), attn.data_ptr(), dy.data_ptr(), pitch_of(dy), tgt.data_ptr(), pitch_of(tgt),
-                                int(acc), dgamma.data_ptr(), B, N, Cc, buf.data_ptr(), buf.numel(), dot_ws(dev).data_ptr(), _stream()), "gdn_cam_bwd")
+        if tc:
+            buf = workspace("cam_tc", lib.gdn_cam_tc_ws_bytes(B, N, Cc), dev)
+            L.check(lib.gdn_cam_bwd_tc(x.t.data_ptr(), pitch_of(x.t), gamma.t.data_ptr(), attn.data_ptr(), dy.data_ptr(), pitch_of(dy), tgt.data_ptr(), pitch_of(tgt),
+                                       int(acc), dgamma.data_ptr(), B, N, Cc, buf.data_ptr(), buf.numel(), dot_ws(dev).data_ptr(), _stream()), "gdn_cam_bwd_tc")
+        else:
+            need = lib.gdn_cam_bwd_ws_bytes(B, N, Cc)
+            buf = workspace("cam", need, dev)
+            L.check(lib.gdn_cam_bwd(x.t.data_ptr(), pitch_of(x.t), gamma.t.data_ptr(), attn.data_ptr(), dy.data_ptr(), pitch_of(dy), tgt.data_ptr(), pitch_of(tgt),
+                                    int(acc), dgamma.data_ptr(), B, N, Cc, buf.data_ptr(), buf.numel(), dot_ws(dev).data_ptr(), _stream()), "gdn_cam_bwd")
         if gamma.needs_grad:
             gamma.add_grad(dgamma)
 

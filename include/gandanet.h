@@ -122,7 +122,7 @@ size_t gdn_pack_weight_bf16_elems(int O, int I, int kh, int kw, int transposed);
 int gdn_pack_weight_bf16(const float* w, int O, int I_total, int i_c0, int I, int kh, int kw, int transposed,
                          uint16_t* hi, uint16_t* lo, gdn_stream_t s);
 /*
- * y[b,ho,wo,n] = act(sum_{kh,kw,c} xin(b,ho,wo,kh,kw,c) * w[kh,kw][n][c] + bias[n]) + res[b,ho,wo,n]
+ * y[b,ho,wo,n] = act(alpha * sum_{kh,kw,c} xin(b,ho,wo,kh,kw,c) * w[kh,kw][n][c] + bias[n]) + res[b,ho,wo,n]
  * transposed == 0: forward, x is [B,Hi,Wi,Cin_p8] packed, w packed with transposed = 0.
  * transposed == 1: data gradient: x is the packed OUTPUT gradient [B,Hi,Wi,(conv Cout)_p8] (so Cin here = conv Cout,
  *                  Cout here = conv Cin, (Ho,Wo) = conv input grid), w packed with transposed = 1.  stride 1 or 2.
@@ -137,6 +137,8 @@ typedef struct {
   int B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad, transposed;
   int act; float slope;
   int precision;
+  const float* alpha_ptr; /* device scalar multiplying the accumulator (gamma of CAM, generator.py:139); NULL = 1 */
+  int groups;             /* > 1: per-sample weights [groups][kh*kw][R][Kp] for B/groups consecutive samples each (CAM's bmm) */
 } gdn_conv_tc_args;
 int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s);
 /*
@@ -150,6 +152,9 @@ typedef struct {
   int B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad;
   int precision;
   float* ws; size_t ws_bytes;
+  int groups;              /* == B (1x1 only): per-sample Gram matrices out[b][Cout][Cin] = scale_ptr[0] * dy_b^T x_b, written directly
+                              (the C x C energy of CAM, generator.py:132, and dA of its backward); ws unused */
+  const float* scale_ptr;  /* device scalar for the grouped mode; NULL = 1 */
 } gdn_wgrad_tc_args;
 size_t gdn_conv2d_wgrad_tc_ws_bytes(const gdn_wgrad_tc_args* a);
 int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s);
@@ -247,6 +252,13 @@ int gdn_cam_fwd(const float* x, int x_pitch, const float* gamma, float* attn, fl
 size_t gdn_cam_bwd_ws_bytes(int B, int N, int C);
 int gdn_cam_bwd(const float* x, int x_pitch, const float* gamma, const float* attn, const float* dy, int dy_pitch,
                 float* dx, int dx_pitch, int accumulate, float* dgamma, int B, int N, int C, void* ws, size_t ws_bytes, void* dot_ws, gdn_stream_t s);
+/* The same two operations with every contraction on the tensor cores (tcgen05, bf16 hi+lo split operands): Gram matrices by the
+ * grouped weight-gradient kernel, re-projections as 1x1 convolutions with per-sample weights.  C % 4 == 0. */
+size_t gdn_cam_tc_ws_bytes(int B, int N, int C);
+int gdn_cam_fwd_tc(const float* x, int x_pitch, const float* gamma, float* attn, float* y, int y_pitch, int B, int N, int C,
+                   void* ws, size_t ws_bytes, gdn_stream_t s);
+int gdn_cam_bwd_tc(const float* x, int x_pitch, const float* gamma, const float* attn, const float* dy, int dy_pitch,
+                   float* dx, int dx_pitch, int accumulate, float* dgamma, int B, int N, int C, void* ws, size_t ws_bytes, void* dot_ws, gdn_stream_t s);
 /* in-place-capable row softmax of [rows][n] (negate: softmax(-x)); lse optional.  torch.softmax at generator.py:118,136 */
 int gdn_row_softmax(const float* in, float* out, long long rows, int n, int negate, float* lse, gdn_stream_t s);
 /* CAM softmax (generator.py:135-136): attn = softmax_row(rowmax(E) - E) for [rows][C] */
