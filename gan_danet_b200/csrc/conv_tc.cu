@@ -57,37 +57,41 @@ struct FwdParams {
   int Hc, Wc, os, oh0, ow0;   // extent of the tile grid and the output scatter
   int Wt, Ht, tiles_w, tiles_h;
   int cs;                     // input coordinate = tile coordinate * cs + tap offset (cs = conv stride = TMA element stride)
-  int kchunks, n_tile, nsplit, stages, tmem_cols;
+  int kchunks, n_tile, n_tiles, total_tiles, nsplit, stages, tmem_cols, wt_shift;
   int act; float slope; int vec4;
   TapList taps;
 };
 
-__global__ void __launch_bounds__(NTHREADS)
+// Persistent kernel: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = pixel tile x output-channel tile).
+//   warp 0: TMA producer (smem ring runs across tile boundaries)      warp 1: tcgen05.mma issuer      warp 2: TMEM allocator
+//   warps 4-7: epilogue.  Two accumulator buffers in TMEM: the epilogue of tile i overlaps the main loop of tile i+1.
+// Epilogue: tcgen05.ld gives every thread 32 consecutive channels of ONE pixel; the warp transposes its 32x32 block through a
+// swizzled shared-memory stage so that each store instruction writes 4 pixels x 128 contiguous bytes (full sectors).
+constexpr int EPI_STAGE_BYTES = 32 * 128;      // per epilogue warp: [32 pixels][32 channels] fp32
+
+__global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_constant__ CUtensorMap mapXlo,
                    const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b_bytes = p.n_tile * 128;
   const int stage_bytes = A_BYTES + b_bytes;
-  const uint32_t bar_base = base + p.stages * stage_bytes;
+  const uint32_t epi_off = p.stages * stage_bytes;
+  const uint32_t bar_base = base + epi_off + 4 * EPI_STAGE_BYTES;
   auto full = [&](int s) { return bar_base + 8 * s; };
   auto empty = [&](int s) { return bar_base + 8 * (MAX_STAGES + s); };
-  const uint32_t acc_bar = bar_base + 8 * (2 * MAX_STAGES);
-  const uint32_t tmem_slot_addr = bar_base + 8 * (2 * MAX_STAGES + 1);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot_addr - smem_u32(smem_raw)));
-
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h; t /= p.tiles_h;
-  const int img = t;
-  const int n0 = blockIdx.y * p.n_tile;
-  const int IT = p.taps.n * p.nsplit * p.kchunks;
+  auto acc_full = [&](int b) { return bar_base + 8 * (2 * MAX_STAGES + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8 * (2 * MAX_STAGES + 2 + b); };
+  const uint32_t tmem_slot_addr = bar_base + 8 * (2 * MAX_STAGES + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot_addr - base));
+  const int KI = p.taps.n * p.nsplit * p.kchunks;          // K-iterations per tile
+  const int acc_stride = p.tmem_cols >> 1;                 // column distance of the two accumulator buffers
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(acc_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -102,17 +106,25 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {   // ---- TMA producer
       int it = 0;
-      for (int tp = 0; tp < p.taps.n; ++tp) {
-        const int cw = tw * p.Wt * p.cs + p.taps.dw[tp], ch = th * p.Ht * p.cs + p.taps.dh[tp];
-        for (int comp = 0; comp < p.nsplit; ++comp) {
-          const CUtensorMap* mx = comp == 1 ? &mapXlo : &mapXhi;
-          const CUtensorMap* mw = comp == 2 ? &mapWlo : &mapWhi;
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-            const int s = it % p.stages;
-            if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
-            mbar_expect_tx(full(s), stage_bytes);
-            tma_load_4d(base + s * stage_bytes, mx, full(s), kc * BK, cw, ch, img);
-            tma_load_3d(base + s * stage_bytes + A_BYTES, mw, full(s), kc * BK, n0, p.taps.widx[tp] + (img / p.imgs_per_group) * p.taps_total);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int t = tile / p.n_tiles;
+        const int n0 = (tile % p.n_tiles) * p.n_tile;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int img = t;
+        const int wgrp = (img / p.imgs_per_group) * p.taps_total;
+        for (int tp = 0; tp < p.taps.n; ++tp) {
+          const int cw = tw * p.Wt * p.cs + p.taps.dw[tp], ch = th * p.Ht * p.cs + p.taps.dh[tp];
+          for (int comp = 0; comp < p.nsplit; ++comp) {
+            const CUtensorMap* mx = comp == 1 ? &mapXlo : &mapXhi;
+            const CUtensorMap* mw = comp == 2 ? &mapWlo : &mapWhi;
+            for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+              const int s = it % p.stages;
+              if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
+              mbar_expect_tx(full(s), stage_bytes);
+              tma_load_4d(base + s * stage_bytes, mx, full(s), kc * BK, cw, ch, img);
+              tma_load_3d(base + s * stage_bytes + A_BYTES, mw, full(s), kc * BK, n0, p.taps.widx[tp] + wgrp);
+            }
           }
         }
       }
@@ -120,61 +132,86 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
   } else if (warp == 1) {
     if (lane == 0) {   // ---- MMA issuer
       const uint32_t idesc = idesc_bf16(BM, p.n_tile, 0, 0);
-      for (int it = 0; it < IT; ++it) {
-        const int s = it % p.stages;
-        mbar_wait(full(s), (it / p.stages) & 1);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int ab = lt & 1;
+        if (lt >= 2) mbar_wait(acc_empty(ab), ((lt >> 1) - 1) & 1);     // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t a0 = base + s * stage_bytes, b0 = a0 + A_BYTES;
+        const uint32_t d_tmem = tmem + ab * acc_stride;
+        for (int k = 0; k < KI; ++k, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(full(s), (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t a0 = base + s * stage_bytes, b0 = a0 + A_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < BK / 16; ++ks) {
-          umma_f16(tmem, smem_desc(a0 + ks * 32, 1024, LAYOUT_SW128), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < BK / 16; ++ks)
+            umma_f16(d_tmem, smem_desc(a0 + ks * 32, 1024, LAYOUT_SW128), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (k > 0 || ks > 0) ? 1u : 0u);
+          tc_commit(empty(s));
         }
-        tc_commit(empty(s));
+        tc_commit(acc_full(ab));
       }
-      tc_commit(acc_bar);
     }
   } else if (warp >= 4) {
-    // ---- epilogue: thread = one pixel of the tile (TMEM lane), 32 output channels at a time
+    // ---- epilogue
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int i = th * p.Ht + row / p.Wt, j = tw * p.Wt + row % p.Wt;
-    const bool pix_ok = i < p.Hc && j < p.Wc;
-    const size_t pix = ((size_t)img * p.Ho + (size_t)(i * p.os + p.oh0)) * p.Wo + (size_t)(j * p.os + p.ow0);
-    float* yrow = p.y + pix * p.y_pitch;
-    const float* rrow = p.res ? p.res + pix * p.res_pitch : nullptr;
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(sm + epi_off + q * EPI_STAGE_BYTES);
     const float alpha = p.alpha_ptr ? __ldg(p.alpha_ptr) : 1.f;
-    for (int c = 0; c < p.n_tile; c += 32) {
-      float v[32];
-      // n_tile is a multiple of 16: the last chunk may be half wide; TMEM columns up to the power-of-two allocation exist
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, v);
-      if (!pix_ok) continue;
-      const int nb = n0 + c;
+    const int rsub = lane >> 3, cj = lane & 7;               // store phase: 4 pixel rows per instruction, 8 lanes x 16 B per row
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      int t = tile / p.n_tiles;
+      const int n0 = (tile % p.n_tiles) * p.n_tile;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int img = t;
+      const int ab = lt & 1;
+      mbar_wait(acc_full(ab), (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t src = tmem + ab * acc_stride + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < p.n_tile; c += 32) {
+        float v[32];
+        // n_tile is a multiple of 16: the last chunk may be half wide; the columns up to the next multiple of 32 are allocated
+        tmem_ld32(src + c, v);
+        // transpose through shared memory: row = lane, 16-byte chunk j stored at j ^ (lane & 7)  (conflict-free both ways)
 #pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        const int n = nb + e;
-        if (n >= p.Cout || c + e >= p.n_tile) break;
-        if (p.vec4) {   // Cout, pitches and channel offsets are multiples of 4
-          float4 o = make_float4(alpha * v[e], alpha * v[e + 1], alpha * v[e + 2], alpha * v[e + 3]);
-          if (p.bias) { const float4 bb = *reinterpret_cast<const float4*>(p.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-          o.x = apply_act(o.x, p.act, p.slope); o.y = apply_act(o.y, p.act, p.slope); o.z = apply_act(o.z, p.act, p.slope); o.w = apply_act(o.w, p.act, p.slope);
-          if (rrow) { const float4 rr = *reinterpret_cast<const float4*>(rrow + n); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-          *reinterpret_cast<float4*>(yrow + n) = o;
-        } else {
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int n = n0 + c + cj * 4;
+        const bool n_ok = n < p.Cout && c + cj * 4 < p.n_tile;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && n_ok) {
+          if (p.vec4) bb = *reinterpret_cast<const float4*>(p.bias + n);
+          else { bb.x = __ldg(p.bias + n); if (n + 1 < p.Cout) bb.y = __ldg(p.bias + n + 1); if (n + 2 < p.Cout) bb.z = __ldg(p.bias + n + 2); if (n + 3 < p.Cout) bb.w = __ldg(p.bias + n + 3); }
+        }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (n + u < p.Cout) {
-              float o = alpha * v[e + u] + (p.bias ? __ldg(p.bias + n + u) : 0.f);
-              o = apply_act(o, p.act, p.slope);
-              if (rrow) o += rrow[n + u];
-              yrow[n + u] = o;
-            }
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const int r = 4 * i8 + rsub;                       // row of this warp's 32-pixel block
+          const int row = q * 32 + r;
+          const int i = th * p.Ht + (row >> p.wt_shift), j = tw * p.Wt + (row & (p.Wt - 1));
+          if (!(n_ok && i < p.Hc && j < p.Wc)) continue;
+          const size_t pix = ((size_t)img * p.Ho + (size_t)(i * p.os + p.oh0)) * p.Wo + (size_t)(j * p.os + p.ow0);
+          float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((cj ^ (r & 7)) << 2));
+          o.x = apply_act(fmaf(alpha, o.x, bb.x), p.act, p.slope); o.y = apply_act(fmaf(alpha, o.y, bb.y), p.act, p.slope);
+          o.z = apply_act(fmaf(alpha, o.z, bb.z), p.act, p.slope); o.w = apply_act(fmaf(alpha, o.w, bb.w), p.act, p.slope);
+          float* yp = p.y + pix * p.y_pitch + n;
+          if (p.vec4) {
+            if (p.res) { const float4 rr = *reinterpret_cast<const float4*>(p.res + pix * p.res_pitch + n); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+            *reinterpret_cast<float4*>(yp) = o;
+          } else {
+            const float* rp = p.res ? p.res + pix * p.res_pitch + n : nullptr;
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (n + u < p.Cout) yp[u] = ov[u] + (rp ? rp[u] : 0.f);
           }
         }
+        __syncwarp();
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(ab));
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 2) {
@@ -488,18 +525,15 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     p.n_tile = (int)cdiv(cdiv(a->Cout, nt), 16) * 16;
   }
   p.nsplit = nsplit;
-  p.tmem_cols = pow2_cols(p.n_tile);
+  p.tmem_cols = 2 * pow2_cols(p.n_tile);        // two accumulator buffers
   p.act = a->act; p.slope = a->slope;
   p.vec4 = (a->Cout % 4 == 0 && a->y_pitch % 4 == 0 && a->y_c0 % 4 == 0 && ((uintptr_t)a->y & 15) == 0 && (!a->bias || ((uintptr_t)a->bias & 15) == 0) &&
             (!a->res || (a->res_pitch % 4 == 0 && a->res_c0 % 4 == 0 && ((uintptr_t)a->res & 15) == 0))) ? 1 : 0;
   const int stage_bytes = A_BYTES + p.n_tile * 128;
-  int stages = (SMEM_LIMIT - 2048) / stage_bytes;
+  int stages = (SMEM_LIMIT - 2048 - 4 * EPI_STAGE_BYTES) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  // narrow tiles: stay under half of the shared memory so that two CTAs are resident (one's epilogue overlaps the other's main loop)
-  const int half = (SMEM_LIMIT / 2 - 2048) / stage_bytes;
-  if (half >= 3) stages = half > 4 ? 4 : half;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 8 * (2 * MAX_STAGES + 2) + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 4 * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 6) + 1024;
   const int n_tiles = (int)cdiv(a->Cout, p.n_tile);
   cudaStream_t st = as_stream(s);
   int rc;
@@ -531,7 +565,13 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
       if (p.taps.n == 0) { set_error("gdn_conv2d_tc: parity class without taps is not supported (kernel smaller than stride)"); return GDN_EINVAL; }
     }
     tile_shape(p.Wc, &p.Wt, &p.Ht);
+    p.wt_shift = 0;
+    while ((1 << p.wt_shift) < p.Wt) ++p.wt_shift;
     p.tiles_w = (int)cdiv(p.Wc, p.Wt); p.tiles_h = (int)cdiv(p.Hc, p.Ht);
+    p.n_tiles = n_tiles;
+    const long long total = (long long)a->B * p.tiles_h * p.tiles_w * n_tiles;
+    GDN_CHECK_ARG(total < (1ll << 31));
+    p.total_tiles = (int)total;
     CUtensorMap mxh, mxl, mwh, mwl;
     if ((rc = make_act_map(&mxh, a->x_hi, Cp, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
     mxl = mxh;
@@ -539,8 +579,7 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     if ((rc = make_weight_map(&mwh, a->w_hi, Cp, a->Cout, taps * groups, p.n_tile)) != GDN_OK) return rc;
     mwl = mwh;
     if (nsplit == 3 && (rc = make_weight_map(&mwl, a->w_lo, Cp, a->Cout, taps * groups, p.n_tile)) != GDN_OK) return rc;
-    dim3 grid((unsigned)((long long)a->B * p.tiles_h * p.tiles_w), (unsigned)n_tiles);
-    GDN_CHECK_ARG(grid.y <= 65535);
+    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;     // persistent: one CTA per SM
     conv_tc_fwd_kernel<<<grid, NTHREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);
     GDN_CHECK_LAUNCH();
   }
