@@ -43,7 +43,7 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 
 _workspaces: Dict[Tuple[int, str], Tensor] = {}
 pam_bwd_tensor_core: bool = os.environ.get("GDN_PAM_BWD", "tc").lower() != "fp32"   # fused tcgen05 backward when the forward ran on tensor cores
-pam_timing: Optional[list] = None   # set to [] by bench.py to collect (start, end, flops, precision) per PAM forward
+kernel_timing: Optional[dict] = None   # set to {} by bench.py: family -> [(start event, end event, algorithmic FLOPs)] on the launching stream
 
 
 def workspace(name: str, nbytes: int, device) -> Tensor:
@@ -53,6 +53,18 @@ def workspace(name: str, nbytes: int, device) -> Tensor:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
+
+
+def _timed(family: str, flops: float, fn: Callable[[], None]) -> None:
+    """Runs ``fn`` (one C-ABI call); when bench.py collects timings, brackets it with CUDA events on the current stream."""
+    if kernel_timing is None:
+        fn()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    kernel_timing.setdefault(family, []).append((e0, e1, flops))
 
 
 def _f32(t: Tensor) -> None:
@@ -185,7 +197,7 @@ def wgrad_raw(dy: Tensor, x: Tensor, out: Tensor, *, kh: int, kw: int, stride: i
 # convolution precision: 'fp32' = CUDA-core engine (igemm_simt.cu); 'bf16' / 'bf16x3' = tcgen05 implicit GEMM (conv_tc.cu)
 # ----------------------------------------------------------------------------------------------------------------
 
-conv_precision: str = os.environ.get("GDN_CONV_PRECISION", "fp32").lower()
+conv_precision: str = os.environ.get("GDN_CONV_PRECISION", "bf16x3").lower()
 _PREC = {"bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 
 
@@ -262,7 +274,8 @@ def conv_tc_raw(xp: Packed, wp: Packed, y: Tensor, in_hw: Tuple[int, int], *, ci
     a.B, a.Hi, a.Wi, a.Cin, a.Ho, a.Wo, a.Cout = B, in_hw[0], in_hw[1], cin, Ho, Wo, Cout
     a.kh, a.kw, a.stride, a.pad, a.transposed = kh, kw, stride, pad, int(transposed)
     a.act, a.slope, a.precision = act, slope, _PREC[conv_precision]
-    L.check(_lib(y).gdn_conv2d_tc(C.byref(a), _stream()), "gdn_conv2d_tc")
+    _timed("conv_tc_fwd_kernel", 2.0 * B * Ho * Wo * Cout * cin * kh * kw / (stride * stride if transposed else 1),
+           lambda: L.check(_lib(y).gdn_conv2d_tc(C.byref(a), _stream()), "gdn_conv2d_tc"))
 
 
 def wgrad_tc_raw(dyp: Packed, xp: Packed, out: Tensor, *, B: int, in_hw: Tuple[int, int], out_hw: Tuple[int, int], cin: int, cout: int, kh: int, kw: int,
@@ -277,7 +290,8 @@ def wgrad_tc_raw(dyp: Packed, xp: Packed, out: Tensor, *, B: int, in_hw: Tuple[i
     need = lib.gdn_conv2d_wgrad_tc_ws_bytes(C.byref(a))
     buf = workspace("wgrad_tc", need, out.device)
     a.ws, a.ws_bytes = buf.data_ptr(), buf.numel()
-    L.check(lib.gdn_conv2d_wgrad_tc(C.byref(a), _stream()), "gdn_conv2d_wgrad_tc")
+    _timed("conv_tc_wgrad_kernel", 2.0 * B * out_hw[0] * out_hw[1] * cout * cin * kh * kw,
+           lambda: L.check(lib.gdn_conv2d_wgrad_tc(C.byref(a), _stream()), "gdn_conv2d_wgrad_tc"))
 
 
 class ConvCtx:
@@ -611,14 +625,8 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
     need = lib.gdn_pam_fwd_ws_bytes(C.byref(a))
     buf = workspace("pam", need, dev)
     a.ws, a.ws_bytes = buf.data_ptr(), buf.numel()
-    if pam_timing is not None:          # bench.py: CUDA events on the launching stream around the fused kernel
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        L.check(lib.gdn_pam_fwd(C.byref(a), _stream()), "gdn_pam_fwd")
-        e1.record()
-        pam_timing.append((e0, e1, 2.0 * B * N * N * (d + Cc), precision))
-    else:
-        L.check(lib.gdn_pam_fwd(C.byref(a), _stream()), "gdn_pam_fwd")
+    fam = "pam_flash_fwd_kernel" if precision == PREC_FP16 else "pam_fwd_fp32"
+    _timed(fam, 2.0 * B * N * N * (d + Cc), lambda: L.check(lib.gdn_pam_fwd(C.byref(a), _stream()), "gdn_pam_fwd"))
     y = out
 
     def bwd():
@@ -639,7 +647,8 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
         need_b = lib.gdn_pam_bwd_ws_bytes(C.byref(b))
         wsb = workspace("pam", need_b, dev)
         b.ws, b.ws_bytes = wsb.data_ptr(), wsb.numel()
-        L.check(lib.gdn_pam_bwd(C.byref(b), _stream()), "gdn_pam_bwd")
+        famb = "pam_flash_bwd_kernel" if b.precision == PREC_FP16 else "pam_bwd_fp32"
+        _timed(famb, 4.0 * B * N * N * (d + Cc), lambda: L.check(lib.gdn_pam_bwd(C.byref(b), _stream()), "gdn_pam_bwd"))
         if gamma.needs_grad:
             gamma.add_grad(sums_to_float(colstats(rowdot), 1))
         if q.needs_grad:

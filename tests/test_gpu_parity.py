@@ -24,6 +24,18 @@ def _require_gpu():
     _lib.lib_for_device(0)     # raises loudly if the library is missing or the device is not sm_100
 
 
+@pytest.fixture(autouse=True)
+def _fp32_engine_by_default():
+    """The parity tests of this file run on the fp32 engine unless a test selects a tensor-core precision itself."""
+    from gan_danet_b200 import engine as E
+    old, old_cam = E.conv_precision, E.cam_tensor_core
+    E.set_conv_precision("fp32")
+    E.cam_tensor_core = None
+    yield
+    E.set_conv_precision(old)
+    E.cam_tensor_core = old_cam
+
+
 def _to(sd, dev=DEV):
     return {k: v.to(dev) for k, v in sd.items()}
 
