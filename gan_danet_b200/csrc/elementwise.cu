@@ -64,6 +64,87 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict_
   }
 }
 
+
+// 128-bit variant: a thread owns 4 consecutive channels and walks rows ty, ty + RP, ... of its block's row range with 8
+// independent float4 loads in flight; fp32 partial sums over 8 rows are folded into double accumulators (same numerics as
+// the scalar kernel); fixed summation order => deterministic.  Requires C % 4 == 0 and 16-byte aligned rows.
+template <int MODE>
+__global__ void __launch_bounds__(256) colreduce_v4_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ dy, int dy_pitch,
+                                                           long long M, int C, long long rows_per_block,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           int act, float slope, double* __restrict__ partial) {
+  __shared__ double sh[256][9];
+  const int Cv = C >> 2;
+  const long long r0 = blockIdx.x * rows_per_block;
+  const long long r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
+  for (int cg0 = 0; cg0 < Cv; cg0 += 256) {
+    const int cw = (Cv - cg0 < 256) ? Cv - cg0 : 256;      // column groups in this pass
+    const int RP = 256 / cw;                               // rows handled per pass by the block
+    const int ty = threadIdx.x / cw, cg = threadIdx.x - ty * cw;
+    const bool active = ty < RP;
+    const int c = (cg0 + cg) << 2;
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+    if (active) {
+      float4 mu = make_float4(0, 0, 0, 0), is = mu, sc = mu, sf = mu;
+      if (MODE == 1) {
+        mu = *reinterpret_cast<const float4*>(mean + c); is = *reinterpret_cast<const float4*>(invstd + c);
+        sc = *reinterpret_cast<const float4*>(scale + c); sf = *reinterpret_cast<const float4*>(shift + c);
+      }
+      for (long long r = r0 + ty; r < r1; r += 8ll * RP) {
+        float4 xv[8], gv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const long long rr = r + (long long)u * RP;
+          if (rr < r1) {
+            xv[u] = *reinterpret_cast<const float4*>(x + (size_t)rr * x_pitch + c);
+            if (MODE == 1) gv[u] = *reinterpret_cast<const float4*>(dy + (size_t)rr * dy_pitch + c);
+          } else {
+            xv[u] = make_float4(0, 0, 0, 0);
+            if (MODE == 1) gv[u] = make_float4(0, 0, 0, 0);
+            if (MODE == 1) xv[u] = mu;          // xhat = 0 and g = 0 for the padding rows
+          }
+        }
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (MODE == 0) {
+            f[0] += xv[u].x; f[1] += xv[u].y; f[2] += xv[u].z; f[3] += xv[u].w;
+            f[4] = fmaf(xv[u].x, xv[u].x, f[4]); f[5] = fmaf(xv[u].y, xv[u].y, f[5]); f[6] = fmaf(xv[u].z, xv[u].z, f[6]); f[7] = fmaf(xv[u].w, xv[u].w, f[7]);
+          } else {
+            const float g0 = gv[u].x * act_grad(fmaf(xv[u].x, sc.x, sf.x), act, slope), g1 = gv[u].y * act_grad(fmaf(xv[u].y, sc.y, sf.y), act, slope);
+            const float g2 = gv[u].z * act_grad(fmaf(xv[u].z, sc.z, sf.z), act, slope), g3 = gv[u].w * act_grad(fmaf(xv[u].w, sc.w, sf.w), act, slope);
+            f[0] += g0; f[1] += g1; f[2] += g2; f[3] += g3;
+            f[4] = fmaf(g0, (xv[u].x - mu.x) * is.x, f[4]); f[5] = fmaf(g1, (xv[u].y - mu.y) * is.y, f[5]);
+            f[6] = fmaf(g2, (xv[u].z - mu.z) * is.z, f[6]); f[7] = fmaf(g3, (xv[u].w - mu.w) * is.w, f[7]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += (double)f[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sh[threadIdx.x][k] = acc[k];
+    __syncthreads();
+    if (threadIdx.x < cw) {          // thread cg sums the RP row lanes of its column group
+      double s[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] = 0.0;
+      for (int j = 0; j < RP; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] += sh[j * cw + threadIdx.x][k];
+      double* dst = partial + (size_t)blockIdx.x * 2 * C + ((cg0 + threadIdx.x) << 2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { dst[k] = s[k]; dst[C + k] = s[4 + k]; }
+    }
+    __syncthreads();
+  }
+}
+
 // out[j] = sum_b partial[b][j], j < n2 ; one warp per 32 columns, 8 row lanes
 __global__ void __launch_bounds__(256) colreduce_final_kernel(const double* __restrict__ partial, int nblocks, int n2, double* __restrict__ out) {
   __shared__ double sh[8][33];
@@ -129,7 +210,8 @@ __device__ __forceinline__ float ew_apply(const EwP& p, float a, float b, int c,
   float sc = __ldg(p.scale + c), sf = __ldg(p.shift + c), mu = __ldg(p.mean + c), is = __ldg(p.invstd + c);
   float g = a * act_grad(fmaf(b, sc, sf), p.act, p.slope);
   float xhat = (b - mu) * is;
-  float sg = (float)(p.sums[c] * (double)invM), sgx = (float)(p.sums[p.C + c] * (double)invM);
+  extern __shared__ float ew_coef[];       // [2C]: sum_g / M, sum_g_xhat / M (filled once per block)
+  float sg = ew_coef[c], sgx = ew_coef[p.C + c];
   float w = p.weight ? __ldg(p.weight + c) : 1.f;
   return w * is * (g - sg - xhat * sgx);
 }
@@ -139,6 +221,12 @@ __global__ void __launch_bounds__(256) ew_kernel(const EwP p) {
   const int Cv = p.C / VEC;
   const long long total = p.M * Cv;
   const float invM = 1.f / (float)p.M;
+  if (OP == EW_BN_BWD) {
+    extern __shared__ float ew_coef[];
+    const double inv = 1.0 / (double)p.M;
+    for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) ew_coef[i] = (float)(p.sums[i] * inv);
+    __syncthreads();
+  }
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long m = idx / Cv;
     int c = (int)(idx - m * Cv) * VEC;
@@ -176,8 +264,10 @@ static int ew_launch(const EwP& p, cudaStream_t st) {
   const bool v4 = vec4_ok(p);
   long long total = p.M * (v4 ? p.C / 4 : p.C);
   int blocks = (int)(cdiv(total, 256) < 16 * kNumSMs ? cdiv(total, 256) : 16 * kNumSMs);
-  if (v4) ew_kernel<OP, 4><<<blocks, 256, 0, st>>>(p);
-  else ew_kernel<OP, 1><<<blocks, 256, 0, st>>>(p);
+  const size_t smem = OP == EW_BN_BWD ? (size_t)2 * p.C * sizeof(float) : 0;
+  if (smem > 48 * 1024) { set_error("elementwise: BatchNorm backward supports at most 6144 channels"); return GDN_EINVAL; }
+  if (v4) ew_kernel<OP, 4><<<blocks, 256, smem, st>>>(p);
+  else ew_kernel<OP, 1><<<blocks, 256, smem, st>>>(p);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
@@ -206,7 +296,10 @@ static int colreduce(const float* x, int x_pitch, const float* dy, int dy_pitch,
                      const float* scale, const float* shift, int act, float slope, double* out, void* ws, cudaStream_t st) {
   StatPlan pl = stat_plan(M);
   double* partial = reinterpret_cast<double*>(ws);
-  colreduce_kernel<MODE><<<pl.blocks, 256, 0, st>>>(x, x_pitch, dy, dy_pitch, M, C, pl.rows_per_block, mean, invstd, scale, shift, act, slope, partial);
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool v4 = C % 4 == 0 && x_pitch % 4 == 0 && al(x) && (MODE == 0 || (dy_pitch % 4 == 0 && al(dy) && al(mean) && al(invstd) && al(scale) && al(shift)));
+  if (v4) colreduce_v4_kernel<MODE><<<pl.blocks, 256, 0, st>>>(x, x_pitch, dy, dy_pitch, M, C, pl.rows_per_block, mean, invstd, scale, shift, act, slope, partial);
+  else colreduce_kernel<MODE><<<pl.blocks, 256, 0, st>>>(x, x_pitch, dy, dy_pitch, M, C, pl.rows_per_block, mean, invstd, scale, shift, act, slope, partial);
   GDN_CHECK_LAUNCH();
   colreduce_final_kernel<<<(unsigned)cdiv(2 * C, 32), 256, 0, st>>>(partial, pl.blocks, 2 * C, out);
   GDN_CHECK_LAUNCH();

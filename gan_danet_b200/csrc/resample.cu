@@ -111,6 +111,128 @@ __global__ void __launch_bounds__(256) bicubic_up2_bwd_kernel(const float* __res
   }
 }
 
+
+// ---- 128-bit fast paths ------------------------------------------------------------------------------------------------
+// x2 bicubic: output rows 2i / 2i+1 read input rows i-2..i+1 (t = 0.75) / i-1..i+2 (t = 0.25); one thread produces the 2x2
+// output block of input pixel (i, j) from the 5x5 clamped neighbourhood, separably (25 loads for 4 outputs instead of 64).
+__global__ void __launch_bounds__(256) bicubic_up2_fwd_v4_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Cv = C >> 2, Wo = 2 * W;
+  const long long total = (long long)B * H * W * Cv;
+  float w75[4], w25[4];
+  cubic_coeffs(0.75f, w75); cubic_coeffs(0.25f, w25);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cv) << 2; long long r = idx / Cv;
+    const int j = (int)(r % W); r /= W; const int i = (int)(r % H); const int b = (int)(r / H);
+    float4 o[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) o[a][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float* row = x + (((size_t)b * H + clampi(i - 2 + k, 0, H - 1)) * W) * C + c;
+      float4 v[5];
+#pragma unroll
+      for (int m = 0; m < 5; ++m) v[m] = *reinterpret_cast<const float4*>(row + (size_t)clampi(j - 2 + m, 0, W - 1) * C);
+      float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        h0.x = fmaf(w75[m], v[m].x, h0.x); h0.y = fmaf(w75[m], v[m].y, h0.y); h0.z = fmaf(w75[m], v[m].z, h0.z); h0.w = fmaf(w75[m], v[m].w, h0.w);
+        h1.x = fmaf(w25[m], v[m + 1].x, h1.x); h1.y = fmaf(w25[m], v[m + 1].y, h1.y); h1.z = fmaf(w25[m], v[m + 1].z, h1.z); h1.w = fmaf(w25[m], v[m + 1].w, h1.w);
+      }
+      if (k < 4) {
+        const float wv = w75[k];
+        o[0][0].x = fmaf(wv, h0.x, o[0][0].x); o[0][0].y = fmaf(wv, h0.y, o[0][0].y); o[0][0].z = fmaf(wv, h0.z, o[0][0].z); o[0][0].w = fmaf(wv, h0.w, o[0][0].w);
+        o[0][1].x = fmaf(wv, h1.x, o[0][1].x); o[0][1].y = fmaf(wv, h1.y, o[0][1].y); o[0][1].z = fmaf(wv, h1.z, o[0][1].z); o[0][1].w = fmaf(wv, h1.w, o[0][1].w);
+      }
+      if (k >= 1) {
+        const float wv = w25[k - 1];
+        o[1][0].x = fmaf(wv, h0.x, o[1][0].x); o[1][0].y = fmaf(wv, h0.y, o[1][0].y); o[1][0].z = fmaf(wv, h0.z, o[1][0].z); o[1][0].w = fmaf(wv, h0.w, o[1][0].w);
+        o[1][1].x = fmaf(wv, h1.x, o[1][1].x); o[1][1].y = fmaf(wv, h1.y, o[1][1].y); o[1][1].z = fmaf(wv, h1.z, o[1][1].z); o[1][1].w = fmaf(wv, h1.w, o[1][1].w);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        *reinterpret_cast<float4*>(y + (((size_t)b * 2 * H + 2 * i + a) * Wo + 2 * j + e) * C + c) = o[a][e];
+  }
+}
+
+// weights with which the 8 outputs 2i-3 .. 2i+4 read input i (interior: constants; borders: clamped taps fold together)
+__device__ __forceinline__ void up2_bwd_weights(int i, int n, const float w75[4], const float w25[4], float w[8]) {
+  if (i >= 3 && i <= n - 4) {
+    w[0] = w25[3]; w[1] = w75[3]; w[2] = w25[2]; w[3] = w75[2]; w[4] = w25[1]; w[5] = w75[1]; w[6] = w25[0]; w[7] = w75[0];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int o = 2 * i - 3 + k;
+      w[k] = (o >= 0 && o < 2 * n) ? cubic_up2_weight(o, i, n) : 0.f;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) bicubic_up2_bwd_v4_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
+  const int Cv = C >> 2, Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)B * H * W * Cv;
+  float w75[4], w25[4];
+  cubic_coeffs(0.75f, w75); cubic_coeffs(0.25f, w25);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cv) << 2; long long r = idx / Cv;
+    const int ix = (int)(r % W); r /= W; const int iy = (int)(r % H); const int b = (int)(r / H);
+    float wy[8], wx[8];
+    up2_bwd_weights(iy, H, w75, w25, wy);
+    up2_bwd_weights(ix, W, w75, w25, wx);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int oy = 2 * iy - 3 + i;
+      if (oy < 0 || oy >= Ho) continue;
+      const float* row = dy + ((size_t)b * Ho + oy) * Wo * C + c;
+      float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ox = 2 * ix - 3 + j;
+        if (ox < 0 || ox >= Wo) continue;
+        const float4 q = *reinterpret_cast<const float4*>(row + (size_t)ox * C);
+        h.x = fmaf(wx[j], q.x, h.x); h.y = fmaf(wx[j], q.y, h.y); h.z = fmaf(wx[j], q.z, h.z); h.w = fmaf(wx[j], q.w, h.w);
+      }
+      acc.x = fmaf(wy[i], h.x, acc.x); acc.y = fmaf(wy[i], h.y, acc.y); acc.z = fmaf(wy[i], h.z, acc.z); acc.w = fmaf(wy[i], h.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(dx + (((size_t)b * H + iy) * W + ix) * C + c) = acc;
+  }
+}
+
+// 2x2/2 max-pool backward: one thread per pooling window and 4 channels; the gradient goes to the first maximum in scan order
+__global__ void __launch_bounds__(256) maxpool2_bwd_v4_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
+  const int Cv = C >> 2, Ho = H / 2, Wo = W / 2, Hc = (H + 1) / 2, Wc = (W + 1) / 2;
+  const long long total = (long long)B * Hc * Wc * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cv) << 2; long long r = idx / Cv;
+    const int ox = (int)(r % Wc); r /= Wc; const int oy = (int)(r % Hc); const int b = (int)(r / Hc);
+    const size_t p00 = (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + c;
+    const bool has_x1 = 2 * ox + 1 < W, has_y1 = 2 * oy + 1 < H;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (oy < Ho && ox < Wo) {
+      const float4 v0 = *reinterpret_cast<const float4*>(x + p00), v1 = *reinterpret_cast<const float4*>(x + p00 + C);
+      const float4 v2 = *reinterpret_cast<const float4*>(x + p00 + (size_t)W * C), v3 = *reinterpret_cast<const float4*>(x + p00 + (size_t)W * C + C);
+      const float4 g = *reinterpret_cast<const float4*>(dy + (((size_t)b * Ho + oy) * Wo + ox) * C + c);
+      float4 d0 = z, d1 = z, d2 = z, d3 = z;
+#define GDN_POOL_ROUTE(f)                                                                       \
+      { float m = v0.f; int a = 0; if (v1.f > m) { m = v1.f; a = 1; } if (v2.f > m) { m = v2.f; a = 2; } if (v3.f > m) { a = 3; } \
+        d0.f = a == 0 ? g.f : 0.f; d1.f = a == 1 ? g.f : 0.f; d2.f = a == 2 ? g.f : 0.f; d3.f = a == 3 ? g.f : 0.f; }
+      GDN_POOL_ROUTE(x) GDN_POOL_ROUTE(y) GDN_POOL_ROUTE(z) GDN_POOL_ROUTE(w)
+#undef GDN_POOL_ROUTE
+      *reinterpret_cast<float4*>(dx + p00) = d0; *reinterpret_cast<float4*>(dx + p00 + C) = d1;
+      *reinterpret_cast<float4*>(dx + p00 + (size_t)W * C) = d2; *reinterpret_cast<float4*>(dx + p00 + (size_t)W * C + C) = d3;
+    } else {   // odd H / W: the last row / column belongs to no window
+      *reinterpret_cast<float4*>(dx + p00) = z;
+      if (has_x1) *reinterpret_cast<float4*>(dx + p00 + C) = z;
+      if (has_y1) *reinterpret_cast<float4*>(dx + p00 + (size_t)W * C) = z;
+      if (has_x1 && has_y1) *reinterpret_cast<float4*>(dx + p00 + (size_t)W * C + C) = z;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ bilinear resize to (Ho, Wo)
 template <int VEC>
 __global__ void __launch_bounds__(256) bilinear_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C,
@@ -274,14 +396,14 @@ using namespace gdn;
 
 extern "C" int gdn_bicubic_up2_fwd(const float* x, float* y, int B, int H, int W, int C, gdn_stream_t s) {
   GDN_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0);
-  if (C % 4 == 0 && al16(x) && al16(y)) bicubic_up2_fwd_kernel<4><<<grid_for((long long)B * 4 * H * W * (C / 4)), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
+  if (C % 4 == 0 && al16(x) && al16(y)) bicubic_up2_fwd_v4_kernel<<<grid_for((long long)B * H * W * (C / 4)), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
   else bicubic_up2_fwd_kernel<1><<<grid_for((long long)B * 4 * H * W * C), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
 extern "C" int gdn_bicubic_up2_bwd(const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s) {
   GDN_CHECK_ARG(dy && dx && B > 0 && H > 0 && W > 0 && C > 0);
-  if (C % 4 == 0 && al16(dy) && al16(dx)) bicubic_up2_bwd_kernel<4><<<grid_for((long long)B * H * W * (C / 4)), 256, 0, as_stream(s)>>>(dy, dx, B, H, W, C);
+  if (C % 4 == 0 && al16(dy) && al16(dx)) bicubic_up2_bwd_v4_kernel<<<grid_for((long long)B * H * W * (C / 4)), 256, 0, as_stream(s)>>>(dy, dx, B, H, W, C);
   else bicubic_up2_bwd_kernel<1><<<grid_for((long long)B * H * W * C), 256, 0, as_stream(s)>>>(dy, dx, B, H, W, C);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
@@ -319,7 +441,10 @@ extern "C" int gdn_maxpool2_fwd(const float* x, float* y, int B, int H, int W, i
 }
 extern "C" int gdn_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s) {
   GDN_CHECK_ARG(x && dy && dx && B > 0 && H >= 2 && W >= 2 && C > 0);
-  maxpool2_bwd_kernel<<<grid_for((long long)B * H * W * C), 256, 0, as_stream(s)>>>(x, dy, dx, B, H, W, C);
+  if (C % 4 == 0 && al16(x) && al16(dy) && al16(dx))
+    maxpool2_bwd_v4_kernel<<<grid_for((long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4)), 256, 0, as_stream(s)>>>(x, dy, dx, B, H, W, C);
+  else
+    maxpool2_bwd_kernel<<<grid_for((long long)B * H * W * C), 256, 0, as_stream(s)>>>(x, dy, dx, B, H, W, C);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

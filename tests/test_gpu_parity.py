@@ -433,3 +433,35 @@ def test_pam_properties_full_size():
     v2 = torch.randn(B, H, W, C, generator=gen).to(DEV)
     y1, y2, y12 = run(v1) - x, run(v2) - x, run(v1 + v2) - x
     assert rel_err(y12, y1 + y2) < 3e-3
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 9, 13, 8), (1, 16, 32, 64), (1, 3, 4, 4)])
+def test_resample_vector_paths(B, H, W, C):
+    """128-bit kernels (C % 4 == 0) for nn.Upsample(2,'bicubic') (generator.py:221,225) and MaxPool2d(2,2) (VGG19 of
+    losses.py:58), forward and backward, against ATen on the same device in float64 (same formulas as the CPU oracle)."""
+    import torch.nn.functional as F
+    from gan_danet_b200 import engine as E
+    g = torch.Generator().manual_seed(H * 100 + W)
+    x = torch.randn(B, H, W, C, generator=g).to(DEV)
+    tape = E.Tape()
+    xv = E.Var(x)
+    up = E.op_bicubic_up2(tape, xv)
+    r = torch.randn(up.t.shape, generator=g).to(DEV)
+    up.g = r
+    tape.backward()
+    xd = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.interpolate(xd, scale_factor=2, mode="bicubic", align_corners=False)
+    ref.backward(r.double().permute(0, 3, 1, 2))
+    assert rel_err(up.t.permute(0, 3, 1, 2), ref) < 1e-6
+    assert rel_err(xv.g.permute(0, 3, 1, 2), xd.grad) < 1e-6
+    tape = E.Tape()
+    xv = E.Var(x)
+    mp = E.op_maxpool2(tape, xv)
+    r2 = torch.randn(mp.t.shape, generator=g).to(DEV)
+    mp.g = r2
+    tape.backward()
+    xd = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.max_pool2d(xd, 2, 2)
+    ref.backward(r2.double().permute(0, 3, 1, 2))
+    assert torch.equal(mp.t.permute(0, 3, 1, 2).double(), ref.detach())
+    assert rel_err(xv.g.permute(0, 3, 1, 2), xd.grad) < 1e-7
