@@ -392,18 +392,26 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
                                                        __nv_bfloat16* __restrict__ lo, const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope) {
   const int groups = Cp >> 3;
   const long long total = M * groups;
+  const bool vec = (pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long m = idx / groups; const int c0 = (int)(idx % groups) * 8;
+    long long m; int c0;
+    if (total < (1ll << 31)) { const unsigned i32 = (unsigned)idx, m32 = i32 / (unsigned)groups; m = m32; c0 = (int)(i32 - m32 * (unsigned)groups) * 8; }
+    else { m = idx / groups; c0 = (int)(idx % groups) * 8; }
     const float* src = x + (size_t)m * pitch + c0;
     __align__(16) __nv_bfloat16 h[8];
     __align__(16) __nv_bfloat16 l[8];
+    float vals[8];
+    if (vec && c0 + 8 <= C) {     // 16-byte aligned rows: two 128-bit loads
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(src)), q1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      vals[0] = q0.x; vals[1] = q0.y; vals[2] = q0.z; vals[3] = q0.w; vals[4] = q1.x; vals[5] = q1.y; vals[6] = q1.z; vals[7] = q1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) vals[e] = c0 + e < C ? __ldg(src + e) : 0.f;
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float v = 0.f;
-      if (c0 + e < C) {
-        v = __ldg(src + e);
-        if (scale) v = apply_act(fmaf(v, __ldg(scale + c0 + e), __ldg(shift + c0 + e)), act, slope);
-      }
+      float v = vals[e];
+      if (scale && c0 + e < C) v = apply_act(fmaf(v, __ldg(scale + c0 + e), __ldg(shift + c0 + e)), act, slope);
       h[e] = __float2bfloat16_rn(v);
       l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e]));
     }

@@ -227,9 +227,13 @@ __global__ void __launch_bounds__(256) ew_kernel(const EwP p) {
     for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) ew_coef[i] = (float)(p.sums[i] * inv);
     __syncthreads();
   }
+  // 32-bit index arithmetic when the element count allows it (64-bit division costs more than the memory access it addresses)
+  const bool small = total < (1ll << 31);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    long long m = idx / Cv;
-    int c = (int)(idx - m * Cv) * VEC;
+    long long m;
+    int c;
+    if (small) { const unsigned i32 = (unsigned)idx, m32 = i32 / (unsigned)Cv; m = m32; c = (int)(i32 - m32 * (unsigned)Cv) * VEC; }
+    else { m = idx / Cv; c = (int)(idx - m * Cv) * VEC; }
     if (VEC == 4) {
       float4 a = *reinterpret_cast<const float4*>(p.a + (size_t)m * p.a_pitch + c);
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -263,7 +267,8 @@ static int ew_launch(const EwP& p, cudaStream_t st) {
   if (p.M == 0) return GDN_OK;
   const bool v4 = vec4_ok(p);
   long long total = p.M * (v4 ? p.C / 4 : p.C);
-  int blocks = (int)(cdiv(total, 256) < 16 * kNumSMs ? cdiv(total, 256) : 16 * kNumSMs);
+  const int cap = (OP == EW_BN_BWD ? 6 : 16) * kNumSMs;      // BN backward fills a per-block coefficient table first: fewer, longer blocks
+  int blocks = (int)(cdiv(total, 256) < cap ? cdiv(total, 256) : cap);
   const size_t smem = OP == EW_BN_BWD ? (size_t)2 * p.C * sizeof(float) : 0;
   if (smem > 48 * 1024) { set_error("elementwise: BatchNorm backward supports at most 6144 channels"); return GDN_EINVAL; }
   if (v4) ew_kernel<OP, 4><<<blocks, 256, smem, st>>>(p);
