@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-perceptual", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-detail", action="store_true", help="print a per-shape table of the tensor-core launches to stderr")
     return ap.parse_args()
 
 
@@ -245,8 +246,8 @@ def run_ours(args):
     peak_tf, peak_src = (peaks.get("bf16_tflops_sustained"), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)") if peaks else (1400.0, "fallback (sustained)")
     fams = {}
     for fam, evs in timing.items():
-        tot_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
-        fl = sum(f for _, _, f in evs)
+        tot_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+        fl = sum(e[2] for e in evs)
         fams[fam] = {"launches": len(evs), "ms_per_step": tot_ms / args.steps, "tflops": fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else None,
                      "share_of_step": tot_ms / ms}
     notes = {"conv_tc_fwd_kernel": "tcgen05 implicit-GEMM convolution, forward + data gradient (all layers of G, D, VGG19)",
@@ -262,6 +263,15 @@ def run_ours(args):
                 "frac": f["tflops"] / peak_tf, "traffic": None, "peak_source": peak_src, "launches": f["launches"],
                 "mean_launch_ms": f["ms_per_step"] * args.steps / f["launches"], "share_of_step": f["share_of_step"]}
 
+    if args.kernel_detail and rank == 0:
+        import collections
+        det = collections.defaultdict(lambda: [0, 0.0, 0.0])
+        for fam, evs in timing.items():
+            for e in evs:
+                d = det[(fam, e[3])]
+                d[0] += 1; d[1] += e[0].elapsed_time(e[1]); d[2] += e[2]
+        for (fam, name), (n, t, f) in sorted(det.items(), key=lambda kv: -kv[1][1]):
+            print(f"[detail] {t / args.steps:8.3f} ms/step {n // args.steps:3d}x {f / (t * 1e-3) / 1e12:7.1f} TF/s  {fam} {name}", file=sys.stderr)
     tc_fams = [f for f in fams if f in notes]
     dominant = max(tc_fams, key=lambda f: fams[f]["ms_per_step"]) if tc_fams else None
     roofline = roof(dominant) if dominant else None

@@ -29,7 +29,9 @@ using namespace gdn::tc;
 constexpr int BM = 128;             // pixels per tile (UMMA M)
 constexpr int BK = 64;              // channels per K-iteration: 64 bf16 = one 128-byte swizzled row
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 256;          // weight-gradient kernel
+constexpr int FWD_THREADS = 384;       // forward kernel: 4 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -64,12 +66,12 @@ struct FwdParams {
 
 // Persistent kernel: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = pixel tile x output-channel tile).
 //   warp 0: TMA producer (smem ring runs across tile boundaries)      warp 1: tcgen05.mma issuer      warp 2: TMEM allocator
-//   warps 4-7: epilogue.  Two accumulator buffers in TMEM: the epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 4-11: epilogue.  Two accumulator buffers in TMEM: the epilogue of tile i overlaps the main loop of tile i+1.
 // Epilogue: tcgen05.ld gives every thread 32 consecutive channels of ONE pixel; the warp transposes its 32x32 block through a
 // swizzled shared-memory stage so that each store instruction writes 4 pixels x 128 contiguous bytes (full sectors).
 constexpr int EPI_STAGE_BYTES = 32 * 128;      // per epilogue warp: [32 pixels][32 channels] fp32
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_constant__ CUtensorMap mapXlo,
                    const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -79,7 +81,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
   const int b_bytes = p.n_tile * 128;
   const int stage_bytes = A_BYTES + b_bytes;
   const uint32_t epi_off = p.stages * stage_bytes;
-  const uint32_t bar_base = base + epi_off + 4 * EPI_STAGE_BYTES;
+  const uint32_t bar_base = base + epi_off + EPI_WARPS * EPI_STAGE_BYTES;
   auto full = [&](int s) { return bar_base + 8 * s; };
   auto empty = [&](int s) { return bar_base + 8 * (MAX_STAGES + s); };
   auto acc_full = [&](int b) { return bar_base + 8 * (2 * MAX_STAGES + b); };
@@ -91,7 +93,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -152,9 +154,10 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    // ---- epilogue
-    const int q = warp & 3;
-    float* stg = reinterpret_cast<float*>(sm + epi_off + q * EPI_STAGE_BYTES);
+    // ---- epilogue: 8 warps; warp w drains TMEM lanes [32*(w&3), +32) (the hardware's lane quarter of a warp) and the 32-column
+    // chunks of parity (w-4)>>2.  Per tile every lane precomputes the output offsets of its 8 store rows once.
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    float* stg = reinterpret_cast<float*>(sm + epi_off + (warp - 4) * EPI_STAGE_BYTES);
     const float alpha = p.alpha_ptr ? __ldg(p.alpha_ptr) : 1.f;
     const int rsub = lane >> 3, cj = lane & 7;               // store phase: 4 pixel rows per instruction, 8 lanes x 16 B per row
     int lt = 0;
@@ -165,10 +168,20 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int img = t;
       const int ab = lt & 1;
+      long long yoff[8], roff[8];                              // element offsets of this lane's 8 rows (-1: outside the image)
+#pragma unroll
+      for (int i8 = 0; i8 < 8; ++i8) {
+        const int row = q * 32 + 4 * i8 + rsub;
+        const int i = th * p.Ht + (row >> p.wt_shift), j = tw * p.Wt + (row & (p.Wt - 1));
+        const long long pix = ((long long)img * p.Ho + (i * p.os + p.oh0)) * p.Wo + (j * p.os + p.ow0);
+        const bool ok = i < p.Hc && j < p.Wc;
+        yoff[i8] = ok ? pix * p.y_pitch : -1;
+        roff[i8] = pix * p.res_pitch;
+      }
       mbar_wait(acc_full(ab), (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t src = tmem + ab * acc_stride + ((uint32_t)(q * 32) << 16);
-      for (int c = 0; c < p.n_tile; c += 32) {
+      for (int c = half * 32; c < p.n_tile; c += 64) {
         float v[32];
         // n_tile is a multiple of 16: the last chunk may be half wide; the columns up to the next multiple of 32 are allocated
         tmem_ld32(src + c, v);
@@ -184,26 +197,34 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
           if (p.vec4) bb = *reinterpret_cast<const float4*>(p.bias + n);
           else { bb.x = __ldg(p.bias + n); if (n + 1 < p.Cout) bb.y = __ldg(p.bias + n + 1); if (n + 2 < p.Cout) bb.z = __ldg(p.bias + n + 2); if (n + 3 < p.Cout) bb.w = __ldg(p.bias + n + 3); }
         }
+        if (p.vec4) {
+          float4 rr[8];
+          if (p.res) {     // all residual loads first (res may alias y: they must not be serialised behind the stores)
 #pragma unroll
-        for (int i8 = 0; i8 < 8; ++i8) {
-          const int r = 4 * i8 + rsub;                       // row of this warp's 32-pixel block
-          const int row = q * 32 + r;
-          const int i = th * p.Ht + (row >> p.wt_shift), j = tw * p.Wt + (row & (p.Wt - 1));
-          if (!(n_ok && i < p.Hc && j < p.Wc)) continue;
-          const size_t pix = ((size_t)img * p.Ho + (size_t)(i * p.os + p.oh0)) * p.Wo + (size_t)(j * p.os + p.ow0);
-          float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((cj ^ (r & 7)) << 2));
-          o.x = apply_act(fmaf(alpha, o.x, bb.x), p.act, p.slope); o.y = apply_act(fmaf(alpha, o.y, bb.y), p.act, p.slope);
-          o.z = apply_act(fmaf(alpha, o.z, bb.z), p.act, p.slope); o.w = apply_act(fmaf(alpha, o.w, bb.w), p.act, p.slope);
-          float* yp = p.y + pix * p.y_pitch + n;
-          if (p.vec4) {
-            if (p.res) { const float4 rr = *reinterpret_cast<const float4*>(p.res + pix * p.res_pitch + n); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-            *reinterpret_cast<float4*>(yp) = o;
-          } else {
-            const float* rp = p.res ? p.res + pix * p.res_pitch + n : nullptr;
-            const float ov[4] = {o.x, o.y, o.z, o.w};
+            for (int i8 = 0; i8 < 8; ++i8)
+              rr[i8] = (n_ok && yoff[i8] >= 0) ? *reinterpret_cast<const float4*>(p.res + roff[i8] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int r = 4 * i8 + rsub;
+            float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((cj ^ (r & 7)) << 2));
+            o.x = apply_act(fmaf(alpha, o.x, bb.x), p.act, p.slope); o.y = apply_act(fmaf(alpha, o.y, bb.y), p.act, p.slope);
+            o.z = apply_act(fmaf(alpha, o.z, bb.z), p.act, p.slope); o.w = apply_act(fmaf(alpha, o.w, bb.w), p.act, p.slope);
+            if (p.res) { o.x += rr[i8].x; o.y += rr[i8].y; o.z += rr[i8].z; o.w += rr[i8].w; }
+            if (n_ok && yoff[i8] >= 0) *reinterpret_cast<float4*>(p.y + yoff[i8] + n) = o;
+          }
+        } else {
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int r = 4 * i8 + rsub;
+            const float4 o4 = *reinterpret_cast<const float4*>(stg + r * 32 + ((cj ^ (r & 7)) << 2));
+            if (!(n_ok && yoff[i8] >= 0)) continue;
+            const float ov[4] = {o4.x, o4.y, o4.z, o4.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+            float* yp = p.y + yoff[i8] + n;
+            const float* rp = p.res ? p.res + roff[i8] + n : nullptr;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-              if (n + u < p.Cout) yp[u] = ov[u] + (rp ? rp[u] : 0.f);
+              if (n + u < p.Cout) yp[u] = apply_act(fmaf(alpha, ov[u], bv[u]), p.act, p.slope) + (rp ? rp[u] : 0.f);
           }
         }
         __syncwarp();
@@ -538,10 +559,10 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
   p.vec4 = (a->Cout % 4 == 0 && a->y_pitch % 4 == 0 && a->y_c0 % 4 == 0 && ((uintptr_t)a->y & 15) == 0 && (!a->bias || ((uintptr_t)a->bias & 15) == 0) &&
             (!a->res || (a->res_pitch % 4 == 0 && a->res_c0 % 4 == 0 && ((uintptr_t)a->res & 15) == 0))) ? 1 : 0;
   const int stage_bytes = A_BYTES + p.n_tile * 128;
-  int stages = (SMEM_LIMIT - 2048 - 4 * EPI_STAGE_BYTES) / stage_bytes;
+  int stages = (SMEM_LIMIT - 2048 - EPI_WARPS * EPI_STAGE_BYTES) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 4 * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 6) + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 6) + 1024;
   const int n_tiles = (int)cdiv(a->Cout, p.n_tile);
   cudaStream_t st = as_stream(s);
   int rc;
@@ -588,7 +609,7 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     mwl = mwh;
     if (nsplit == 3 && (rc = make_weight_map(&mwl, a->w_lo, Cp, a->Cout, taps * groups, p.n_tile)) != GDN_OK) return rc;
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;     // persistent: one CTA per SM
-    conv_tc_fwd_kernel<<<grid, NTHREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);
+    conv_tc_fwd_kernel<<<grid, FWD_THREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);
     GDN_CHECK_LAUNCH();
   }
   return GDN_OK;

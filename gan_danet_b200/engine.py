@@ -55,7 +55,7 @@ def workspace(name: str, nbytes: int, device) -> Tensor:
     return buf
 
 
-def _timed(family: str, flops: float, fn: Callable[[], None]) -> None:
+def _timed(family: str, flops: float, fn: Callable[[], None], detail: str = "") -> None:
     """Runs ``fn`` (one C-ABI call); when bench.py collects timings, brackets it with CUDA events on the current stream."""
     if kernel_timing is None:
         fn()
@@ -64,7 +64,7 @@ def _timed(family: str, flops: float, fn: Callable[[], None]) -> None:
     e0.record()
     fn()
     e1.record()
-    kernel_timing.setdefault(family, []).append((e0, e1, flops))
+    kernel_timing.setdefault(family, []).append((e0, e1, flops, detail))
 
 
 def _f32(t: Tensor) -> None:
@@ -275,7 +275,8 @@ def conv_tc_raw(xp: Packed, wp: Packed, y: Tensor, in_hw: Tuple[int, int], *, ci
     a.kh, a.kw, a.stride, a.pad, a.transposed = kh, kw, stride, pad, int(transposed)
     a.act, a.slope, a.precision = act, slope, _PREC[conv_precision]
     _timed("conv_tc_fwd_kernel", 2.0 * B * Ho * Wo * Cout * cin * kh * kw / (stride * stride if transposed else 1),
-           lambda: L.check(_lib(y).gdn_conv2d_tc(C.byref(a), _stream()), "gdn_conv2d_tc"))
+           lambda: L.check(_lib(y).gdn_conv2d_tc(C.byref(a), _stream()), "gdn_conv2d_tc"),
+           f"{'dgrad' if transposed else 'fwd'} B{B} {in_hw[0]}x{in_hw[1]}->{Ho}x{Wo} C{cin}->{Cout} k{kh} s{stride}")
 
 
 def wgrad_tc_raw(dyp: Packed, xp: Packed, out: Tensor, *, B: int, in_hw: Tuple[int, int], out_hw: Tuple[int, int], cin: int, cout: int, kh: int, kw: int,
@@ -291,7 +292,8 @@ def wgrad_tc_raw(dyp: Packed, xp: Packed, out: Tensor, *, B: int, in_hw: Tuple[i
     buf = workspace("wgrad_tc", need, out.device)
     a.ws, a.ws_bytes = buf.data_ptr(), buf.numel()
     _timed("conv_tc_wgrad_kernel", 2.0 * B * out_hw[0] * out_hw[1] * cout * cin * kh * kw,
-           lambda: L.check(lib.gdn_conv2d_wgrad_tc(C.byref(a), _stream()), "gdn_conv2d_wgrad_tc"))
+           lambda: L.check(lib.gdn_conv2d_wgrad_tc(C.byref(a), _stream()), "gdn_conv2d_wgrad_tc"),
+           f"wgrad B{B} {in_hw[0]}x{in_hw[1]}->{out_hw[0]}x{out_hw[1]} C{cin}->{cout} k{kh} s{stride}")
 
 
 class ConvCtx:
