@@ -93,6 +93,7 @@ SIGNATURES = {
     "gdn_pack_weight_bf16_elems": (_sz, [_i, _i, _i, _i, _i]),
     "gdn_pack_weight_bf16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "gdn_conv2d_tc": (_i, [C.POINTER(ConvTcArgs), _vp]),
+    "gdn_conv_tc_set_halo": (_i, [_i]),
     "gdn_conv2d_wgrad_tc_ws_bytes": (_sz, [C.POINTER(WgradTcArgs)]),
     "gdn_conv2d_wgrad_tc": (_i, [C.POINTER(WgradTcArgs), _vp]),
     "gdn_colstats_ws_bytes": (_sz, [_ll, _i]),

@@ -20,6 +20,7 @@
 // tcgen05 takes them through the a_major/b_major bits of the instruction descriptor, so no transpose pass exists.
 // The pixel range is split over CTAs; partial sums go to a workspace and a deterministic reduction writes the OIHW gradient.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace gdn {
@@ -60,7 +61,7 @@ struct FwdParams {
   int Wt, Ht, tiles_w, tiles_h;
   int cs;                     // input coordinate = tile coordinate * cs + tap offset (cs = conv stride = TMA element stride)
   int kchunks, n_tile, n_tiles, total_tiles, nsplit, stages, tmem_cols, wt_shift;
-  int act; float slope; int vec4;
+  int act; float slope; int vec4; int halo_bo;
   TapList taps;
 };
 
@@ -71,6 +72,20 @@ struct FwdParams {
 // swizzled shared-memory stage so that each store instruction writes 4 pixels x 128 contiguous bytes (full sectors).
 constexpr int EPI_STAGE_BYTES = 32 * 128;      // per epilogue warp: [32 pixels][32 channels] fp32
 
+// HALO variant (stride-1 3x3 problems with narrow output tiles, which are L2-bound when every tap re-reads its own A tile): the
+// tile is one image row of 128 pixels; per 64-channel chunk ONE TMA box of 3 rows x 130 pixels is loaded and the 9 taps are 9
+// shifted 128-row windows of it, addressed by moving the start address of the shared-memory descriptor by whole 128-byte rows
+// (the descriptor's base-offset field carries the start row's phase inside the 8-row swizzle atom).  A traffic drops 9x -> 3.05x.
+constexpr int HALO_W = BM + 2, HALO_ROWS = 3;
+constexpr int HALO_TX = HALO_ROWS * HALO_W * 128;          // 49920 bytes per box
+constexpr int HALO_SLOT = 50 * 1024;                       // slot pitch (1024-aligned)
+constexpr int HALO_SLOTS = 2;
+__device__ __forceinline__ uint64_t smem_desc_bo(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type, uint32_t use_bo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)(use_bo ? ((addr >> 7) & 7) : 0) << 49) | ((uint64_t)layout_type << 61);
+}
+
+template <bool HALO>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_constant__ CUtensorMap mapXlo,
                    const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const FwdParams p) {
@@ -79,21 +94,25 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b_bytes = p.n_tile * 128;
-  const int stage_bytes = A_BYTES + b_bytes;
-  const uint32_t epi_off = p.stages * stage_bytes;
+  // !HALO: ring of (A tile | W tile) stages.  HALO: ring of HALO_SLOTS halo boxes, then a ring of p.stages W tiles (full/empty barriers).
+  const int stage_bytes = HALO ? b_bytes : A_BYTES + b_bytes;
+  const uint32_t ring_off = HALO ? HALO_SLOTS * HALO_SLOT : 0;
+  const uint32_t epi_off = ring_off + p.stages * stage_bytes;
   const uint32_t bar_base = base + epi_off + EPI_WARPS * EPI_STAGE_BYTES;
   auto full = [&](int s) { return bar_base + 8 * s; };
   auto empty = [&](int s) { return bar_base + 8 * (MAX_STAGES + s); };
   auto acc_full = [&](int b) { return bar_base + 8 * (2 * MAX_STAGES + b); };
   auto acc_empty = [&](int b) { return bar_base + 8 * (2 * MAX_STAGES + 2 + b); };
-  const uint32_t tmem_slot_addr = bar_base + 8 * (2 * MAX_STAGES + 4);
+  auto afull = [&](int b) { return bar_base + 8 * (2 * MAX_STAGES + 4 + b); };
+  auto aempty = [&](int b) { return bar_base + 8 * (2 * MAX_STAGES + 6 + b); };
+  const uint32_t tmem_slot_addr = bar_base + 8 * (2 * MAX_STAGES + 8);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot_addr - base));
   const int KI = p.taps.n * p.nsplit * p.kchunks;          // K-iterations per tile
   const int acc_stride = p.tmem_cols >> 1;                 // column distance of the two accumulator buffers
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_WARPS); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_WARPS); mbar_init(afull(b), 1); mbar_init(aempty(b), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -107,7 +126,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {   // ---- TMA producer
-      int it = 0;
+      int it = 0, na = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int t = tile / p.n_tiles;
         const int n0 = (tile % p.n_tiles) * p.n_tile;
@@ -115,6 +134,25 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
         const int th = t % p.tiles_h; t /= p.tiles_h;
         const int img = t;
         const int wgrp = (img / p.imgs_per_group) * p.taps_total;
+        if (HALO) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            for (int comp = 0; comp < p.nsplit; ++comp, ++na) {
+              const CUtensorMap* mx = comp == 1 ? &mapXlo : &mapXhi;
+              const CUtensorMap* mw = comp == 2 ? &mapWlo : &mapWhi;
+              const int sa = na % HALO_SLOTS;
+              if (na >= HALO_SLOTS) mbar_wait(aempty(sa), ((na / HALO_SLOTS) - 1) & 1);
+              mbar_expect_tx(afull(sa), HALO_TX);
+              tma_load_4d(base + sa * HALO_SLOT, mx, afull(sa), kc * BK, tw * BM - 1, th - 1, img);
+              for (int tp = 0; tp < p.taps.n; ++tp, ++it) {
+                const int s = it % p.stages;
+                if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
+                mbar_expect_tx(full(s), b_bytes);
+                tma_load_3d(base + ring_off + s * stage_bytes, mw, full(s), kc * BK, n0, p.taps.widx[tp] + wgrp);
+              }
+            }
+          }
+          continue;
+        }
         for (int tp = 0; tp < p.taps.n; ++tp) {
           const int cw = tw * p.Wt * p.cs + p.taps.dw[tp], ch = th * p.Ht * p.cs + p.taps.dh[tp];
           for (int comp = 0; comp < p.nsplit; ++comp) {
@@ -134,21 +172,41 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
   } else if (warp == 1) {
     if (lane == 0) {   // ---- MMA issuer
       const uint32_t idesc = idesc_bf16(BM, p.n_tile, 0, 0);
-      int it = 0, lt = 0;
+      int it = 0, lt = 0, na = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const int ab = lt & 1;
         if (lt >= 2) mbar_wait(acc_empty(ab), ((lt >> 1) - 1) & 1);     // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem + ab * acc_stride;
-        for (int k = 0; k < KI; ++k, ++it) {
-          const int s = it % p.stages;
-          mbar_wait(full(s), (it / p.stages) & 1);
-          tc_fence_after();
-          const uint32_t a0 = base + s * stage_bytes, b0 = a0 + A_BYTES;
+        if (HALO) {
+          for (int kk = 0; kk < p.kchunks * p.nsplit; ++kk, ++na) {
+            const int sa = na % HALO_SLOTS;
+            mbar_wait(afull(sa), (na / HALO_SLOTS) & 1);
+            for (int tp = 0; tp < p.taps.n; ++tp, ++it) {
+              const int s = it % p.stages;
+              mbar_wait(full(s), (it / p.stages) & 1);
+              tc_fence_after();
+              // window of tap (dh, dw): halo rows (dh+1)*130 + (dw+1) ... +127, one 128-byte row per pixel
+              const uint32_t a0 = base + sa * HALO_SLOT + (uint32_t)((p.taps.dh[tp] + 1) * HALO_W + (p.taps.dw[tp] + 1)) * 128u;
+              const uint32_t b0 = base + ring_off + s * stage_bytes;
 #pragma unroll
-          for (int ks = 0; ks < BK / 16; ++ks)
-            umma_f16(d_tmem, smem_desc(a0 + ks * 32, 1024, LAYOUT_SW128), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (k > 0 || ks > 0) ? 1u : 0u);
-          tc_commit(empty(s));
+              for (int ks = 0; ks < BK / 16; ++ks)
+                umma_f16(d_tmem, smem_desc_bo(a0 + ks * 32, 1024, LAYOUT_SW128, p.halo_bo), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (kk > 0 || tp > 0 || ks > 0) ? 1u : 0u);
+              tc_commit(empty(s));
+            }
+            tc_commit(aempty(sa));
+          }
+        } else {
+          for (int k = 0; k < KI; ++k, ++it) {
+            const int s = it % p.stages;
+            mbar_wait(full(s), (it / p.stages) & 1);
+            tc_fence_after();
+            const uint32_t a0 = base + s * stage_bytes, b0 = a0 + A_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks)
+              umma_f16(d_tmem, smem_desc(a0 + ks * 32, 1024, LAYOUT_SW128), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (k > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(empty(s));
+          }
         }
         tc_commit(acc_full(ab));
       }
@@ -460,7 +518,7 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 }
 
 // 4-D bf16 NHWC activation map: dims (Cp, W, H, B), box (64, Wt*cs, Ht*cs, 1) traversed with element stride cs
-static int make_act_map(CUtensorMap* m, const void* ptr, int Cp, int W, int H, int B, int Wt, int Ht, int cs) {
+static int make_act_map(CUtensorMap* m, const void* ptr, int Cp, int W, int H, int B, int Wt, int Ht, int cs) {   // box = Wt x Ht pixels (halo: 130 x 3)
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return GDN_ECUDA; }
   cuuint64_t gdim[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -499,8 +557,13 @@ static int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 using namespace gdn;
 using namespace gdn::convtc;
 
+static bool g_halo_enabled = true;
+/* test hook: switch the halo-reuse variant of the forward kernel off (returns the previous setting) */
+extern "C" int gdn_conv_tc_set_halo(int enabled) { const int old = g_halo_enabled; g_halo_enabled = enabled != 0; return old; }
+
 extern "C" int gdn_conv_tc_init(void) {
-  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   return GDN_OK;
 }
@@ -562,7 +625,7 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
   int stages = (SMEM_LIMIT - 2048 - EPI_WARPS * EPI_STAGE_BYTES) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 6) + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 10) + 1024;
   const int n_tiles = (int)cdiv(a->Cout, p.n_tile);
   cudaStream_t st = as_stream(s);
   int rc;
@@ -601,15 +664,27 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     const long long total = (long long)a->B * p.tiles_h * p.tiles_w * n_tiles;
     GDN_CHECK_ARG(total < (1ll << 31));
     p.total_tiles = (int)total;
+    // halo mode: stride-1 3x3 neighbourhood, one-row tiles of 128 pixels, narrow output tile (otherwise the MMA, not L2, is the limit)
+    bool halo = g_halo_enabled && p.cs == 1 && p.os == 1 && p.Wt == BM && p.Ht == 1 && p.taps.n == 9 && p.n_tile <= 64;
+    for (int tp = 0; tp < p.taps.n && halo; ++tp) halo = p.taps.dh[tp] >= -1 && p.taps.dh[tp] <= 1 && p.taps.dw[tp] >= -1 && p.taps.dw[tp] <= 1;
     CUtensorMap mxh, mxl, mwh, mwl;
-    if ((rc = make_act_map(&mxh, a->x_hi, Cp, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
+    const int bw = halo ? HALO_W : p.Wt, bh = halo ? HALO_ROWS : p.Ht;
+    if ((rc = make_act_map(&mxh, a->x_hi, Cp, a->Wi, a->Hi, a->B, bw, bh, p.cs)) != GDN_OK) return rc;
     mxl = mxh;
-    if (nsplit == 3 && (rc = make_act_map(&mxl, a->x_lo, Cp, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
+    if (nsplit == 3 && (rc = make_act_map(&mxl, a->x_lo, Cp, a->Wi, a->Hi, a->B, bw, bh, p.cs)) != GDN_OK) return rc;
     if ((rc = make_weight_map(&mwh, a->w_hi, Cp, a->Cout, taps * groups, p.n_tile)) != GDN_OK) return rc;
     mwl = mwh;
     if (nsplit == 3 && (rc = make_weight_map(&mwl, a->w_lo, Cp, a->Cout, taps * groups, p.n_tile)) != GDN_OK) return rc;
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;     // persistent: one CTA per SM
-    conv_tc_fwd_kernel<<<grid, FWD_THREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);
+    if (halo) {
+      FwdParams ph = p;
+      ph.stages = MAX_STAGES;
+      { const char* e = getenv("GDN_HALO_BO"); ph.halo_bo = e ? atoi(e) : 1; }
+      const size_t smem_h = (size_t)HALO_SLOTS * HALO_SLOT + (size_t)MAX_STAGES * p.n_tile * 128 + EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 10) + 1024;
+      conv_tc_fwd_kernel<true><<<grid, FWD_THREADS, smem_h, st>>>(mxh, mxl, mwh, mwl, ph);
+    } else {
+      conv_tc_fwd_kernel<false><<<grid, FWD_THREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);
+    }
     GDN_CHECK_LAUNCH();
   }
   return GDN_OK;

@@ -141,6 +141,8 @@ typedef struct {
   int groups;             /* > 1: per-sample weights [groups][kh*kw][R][Kp] for B/groups consecutive samples each (CAM's bmm) */
 } gdn_conv_tc_args;
 int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s);
+/* test hook: enable/disable the halo-reuse variant of the forward kernel (stride-1 3x3, narrow output tiles); returns the old setting */
+int gdn_conv_tc_set_halo(int enabled);
 /*
  * Weight gradient: out[co][out_c0+ci][kh][kw] (OIHW, out_cin_total input channels) (+)= scale * sum_pixels dy * x.
  * dy: packed [B,Ho,Wo,Cout_p8]; x: packed [B,Hi,Wi,Cin_p8].  Deterministic (split-K through ws, fixed-order reduction).

@@ -33,7 +33,10 @@ CASES = [
     (2, 256, 512, 16, 32, 3, 2, 1),
     (2, 64, 1, 32, 64, 3, 1, 1),
     (1, 64, 64, 128, 256, 3, 1, 1),
-    (2, 1, 64, 64, 128, 3, 2, 1),     # Discriminator1.conv1: forward on the CUDA cores, gradients on tensor cores
+    (2, 1, 64, 64, 128, 3, 2, 1),
+    (1, 136, 24, 16, 128, 3, 1, 1),   # halo-reuse variant of the forward kernel (one-row tiles of 128 pixels, narrow N)
+    (2, 64, 1, 8, 256, 3, 1, 1),
+    (1, 88, 24, 5, 200, 3, 1, 1),     # Discriminator1.conv1: forward on the CUDA cores, gradients on tensor cores
 ]
 
 
