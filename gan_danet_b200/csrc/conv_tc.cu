@@ -61,7 +61,7 @@ struct FwdParams {
   int Wt, Ht, tiles_w, tiles_h;
   int cs;                     // input coordinate = tile coordinate * cs + tap offset (cs = conv stride = TMA element stride)
   int kchunks, n_tile, n_tiles, total_tiles, nsplit, stages, tmem_cols, wt_shift;
-  int act; float slope; int vec4; int halo_bo;
+  int act; float slope; int vec4; int halo_bo, kgroup;
   TapList taps;
 };
 
@@ -96,7 +96,8 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b_bytes = p.n_tile * 128;
   // !HALO: ring of (A tile | W tile) stages.  HALO: ring of HALO_SLOTS halo boxes, then a ring of p.stages W tiles (full/empty barriers).
-  const int stage_bytes = HALO ? b_bytes : A_BYTES + b_bytes;
+  const int sub_bytes = A_BYTES + b_bytes;
+  const int stage_bytes = p.kgroup * (HALO ? b_bytes : sub_bytes);
   const uint32_t ring_off = HALO ? HALO_SLOTS * HALO_SLOT : 0;
   const uint32_t epi_off = ring_off + p.stages * stage_bytes;
   const uint32_t bar_base = base + epi_off + EPI_WARPS * EPI_STAGE_BYTES;
@@ -135,6 +136,8 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
         const int th = t % p.tiles_h; t /= p.tiles_h;
         const int img = t;
         const int wgrp = (img / p.imgs_per_group) * p.taps_total;
+        // one mbarrier round trip per GROUP of p.kgroup K-iterations: with narrow output tiles an MMA K-iteration is only
+        // 2*n_tile cycles, far less than a producer/issuer hand-shake
         if (HALO) {
           for (int kc = 0; kc < p.kchunks; ++kc) {
             for (int comp = 0; comp < p.nsplit; ++comp, ++na) {
@@ -144,28 +147,31 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
               if (na >= HALO_SLOTS) mbar_wait(aempty(sa), ((na / HALO_SLOTS) - 1) & 1);
               mbar_expect_tx(afull(sa), HALO_TX);
               tma_load_4d(base + sa * HALO_SLOT, mx, afull(sa), kc * BK, tw * BM - 1, th - 1, img);
-              for (int tp = 0; tp < p.taps.n; ++tp, ++it) {
+              for (int tp0 = 0; tp0 < p.taps.n; tp0 += p.kgroup, ++it) {
                 const int s = it % p.stages;
                 if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
-                mbar_expect_tx(full(s), b_bytes);
-                tma_load_3d(base + ring_off + s * stage_bytes, mw, full(s), kc * BK, n0, p.taps.widx[tp] + wgrp);
+                const int cnt = min(p.kgroup, p.taps.n - tp0);
+                mbar_expect_tx(full(s), cnt * b_bytes);
+                for (int g = 0; g < cnt; ++g)
+                  tma_load_3d(base + ring_off + s * stage_bytes + g * b_bytes, mw, full(s), kc * BK, n0, p.taps.widx[tp0 + g] + wgrp);
               }
             }
           }
           continue;
         }
-        for (int tp = 0; tp < p.taps.n; ++tp) {
-          const int cw = tw * p.Wt * p.cs + p.taps.dw[tp], ch = th * p.Ht * p.cs + p.taps.dh[tp];
-          for (int comp = 0; comp < p.nsplit; ++comp) {
+        const int per_tap = p.nsplit * p.kchunks;
+        for (int k0 = 0; k0 < KI; k0 += p.kgroup, ++it) {
+          const int s = it % p.stages;
+          if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
+          const int cnt = min(p.kgroup, KI - k0);
+          mbar_expect_tx(full(s), cnt * sub_bytes);
+          for (int g = 0; g < cnt; ++g) {
+            const int k = k0 + g, tp = k / per_tap, r = k - tp * per_tap, comp = r / p.kchunks, kc = r - comp * p.kchunks;
             const CUtensorMap* mx = comp == 1 ? &mapXlo : &mapXhi;
             const CUtensorMap* mw = comp == 2 ? &mapWlo : &mapWhi;
-            for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-              const int s = it % p.stages;
-              if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
-              mbar_expect_tx(full(s), stage_bytes);
-              tma_load_4d(base + s * stage_bytes, mx, full(s), kc * BK, cw, ch, img);
-              tma_load_3d(base + s * stage_bytes + A_BYTES, mw, full(s), kc * BK, n0, p.taps.widx[tp] + wgrp);
-            }
+            const uint32_t dst = base + s * stage_bytes + g * sub_bytes;
+            tma_load_4d(dst, mx, full(s), kc * BK, tw * p.Wt * p.cs + p.taps.dw[tp], th * p.Ht * p.cs + p.taps.dh[tp], img);
+            tma_load_3d(dst + A_BYTES, mw, full(s), kc * BK, n0, p.taps.widx[tp] + wgrp);
           }
         }
       }
@@ -183,29 +189,36 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
           for (int kk = 0; kk < p.kchunks * p.nsplit; ++kk, ++na) {
             const int sa = na % HALO_SLOTS;
             mbar_wait(afull(sa), (na / HALO_SLOTS) & 1);
-            for (int tp = 0; tp < p.taps.n; ++tp, ++it) {
+            for (int tp0 = 0; tp0 < p.taps.n; tp0 += p.kgroup, ++it) {
               const int s = it % p.stages;
               mbar_wait(full(s), (it / p.stages) & 1);
               tc_fence_after();
-              // window of tap (dh, dw): halo rows (dh+1)*130 + (dw+1) ... +127, one 128-byte row per pixel
-              const uint32_t a0 = base + sa * HALO_SLOT + (uint32_t)((p.taps.dh[tp] + 1) * HALO_W + (p.taps.dw[tp] + 1)) * 128u;
-              const uint32_t b0 = base + ring_off + s * stage_bytes;
+              const int cnt = min(p.kgroup, p.taps.n - tp0);
+              for (int g = 0; g < cnt; ++g) {
+                const int tp = tp0 + g;
+                // window of tap (dh, dw): halo rows (dh+1)*130 + (dw+1) ... +127, one 128-byte row per pixel
+                const uint32_t a0 = base + sa * HALO_SLOT + (uint32_t)((p.taps.dh[tp] + 1) * HALO_W + (p.taps.dw[tp] + 1)) * 128u;
+                const uint32_t b0 = base + ring_off + s * stage_bytes + g * b_bytes;
 #pragma unroll
-              for (int ks = 0; ks < BK / 16; ++ks)
-                umma_f16(d_tmem, smem_desc_bo(a0 + ks * 32, 1024, LAYOUT_SW128, p.halo_bo), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (kk > 0 || tp > 0 || ks > 0) ? 1u : 0u);
+                for (int ks = 0; ks < BK / 16; ++ks)
+                  umma_f16(d_tmem, smem_desc_bo(a0 + ks * 32, 1024, LAYOUT_SW128, p.halo_bo), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (kk > 0 || tp > 0 || ks > 0) ? 1u : 0u);
+              }
               tc_commit(empty(s));
             }
             tc_commit(aempty(sa));
           }
         } else {
-          for (int k = 0; k < KI; ++k, ++it) {
+          for (int k0 = 0; k0 < KI; k0 += p.kgroup, ++it) {
             const int s = it % p.stages;
             mbar_wait(full(s), (it / p.stages) & 1);
             tc_fence_after();
-            const uint32_t a0 = base + s * stage_bytes, b0 = a0 + A_BYTES;
+            const int cnt = min(p.kgroup, KI - k0);
+            for (int g = 0; g < cnt; ++g) {
+              const uint32_t a0 = base + s * stage_bytes + g * sub_bytes, b0 = a0 + A_BYTES;
 #pragma unroll
-            for (int ks = 0; ks < BK / 16; ++ks)
-              umma_f16(d_tmem, smem_desc(a0 + ks * 32, 1024, LAYOUT_SW128), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (k > 0 || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < BK / 16; ++ks)
+                umma_f16(d_tmem, smem_desc(a0 + ks * 32, 1024, LAYOUT_SW128), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (k0 + g > 0 || ks > 0) ? 1u : 0u);
+            }
             tc_commit(empty(s));
           }
         }
@@ -622,10 +635,18 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
   p.act = a->act; p.slope = a->slope;
   p.vec4 = (a->Cout % 4 == 0 && a->y_pitch % 4 == 0 && a->y_c0 % 4 == 0 && ((uintptr_t)a->y & 15) == 0 && (!a->bias || ((uintptr_t)a->bias & 15) == 0) &&
             (!a->res || (a->res_pitch % 4 == 0 && a->res_c0 % 4 == 0 && ((uintptr_t)a->res & 15) == 0))) ? 1 : 0;
-  const int stage_bytes = A_BYTES + p.n_tile * 128;
-  int stages = (SMEM_LIMIT - 2048 - EPI_WARPS * EPI_STAGE_BYTES) / stage_bytes;
+  const int ring_budget = SMEM_LIMIT - 2048 - EPI_WARPS * EPI_STAGE_BYTES;     // bytes for the operand ring(s)
+  const int sub_bytes = A_BYTES + p.n_tile * 128;
+  // K-iterations per pipeline stage: narrow tiles (2*n_tile MMA cycles per K-iteration) amortise the mbarrier round trip over a group
+  int kgroup = p.n_tile <= 64 ? (int)cdiv(256, p.n_tile) : 1;
+  if (kgroup * sub_bytes > ring_budget / 3) kgroup = ring_budget / 3 / sub_bytes;      // at least three stages stay in flight
+  if (kgroup < 1) kgroup = 1;
+  p.kgroup = kgroup;
+  const int stage_bytes = kgroup * sub_bytes;
+  int stages = ring_budget / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.stages = stages;
+  p.halo_bo = 0;
   const size_t smem = (size_t)stages * stage_bytes + EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 10) + 1024;
   const int n_tiles = (int)cdiv(a->Cout, p.n_tile);
   cudaStream_t st = as_stream(s);
@@ -679,9 +700,12 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;     // persistent: one CTA per SM
     if (halo) {
       FwdParams ph = p;
-      ph.stages = MAX_STAGES;
+      const int b_bytes = p.n_tile * 128, w_budget = ring_budget - HALO_SLOTS * HALO_SLOT;
+      ph.kgroup = 9 * b_bytes * 2 <= w_budget ? 9 : 3;             // taps per weight stage (all 9, or one filter row)
+      ph.stages = w_budget / (ph.kgroup * b_bytes);
+      if (ph.stages > MAX_STAGES) ph.stages = MAX_STAGES;
       { const char* e = getenv("GDN_HALO_BO"); ph.halo_bo = e ? atoi(e) : 0; }   // measured on B200: the swizzle phase comes from the absolute smem address, base_offset must stay 0
-      const size_t smem_h = (size_t)HALO_SLOTS * HALO_SLOT + (size_t)MAX_STAGES * p.n_tile * 128 + EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 10) + 1024;
+      const size_t smem_h = (size_t)HALO_SLOTS * HALO_SLOT + (size_t)ph.stages * ph.kgroup * b_bytes + EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 10) + 1024;
       conv_tc_fwd_kernel<true><<<grid, FWD_THREADS, smem_h, st>>>(mxh, mxl, mwh, mwl, ph);
     } else {
       conv_tc_fwd_kernel<false><<<grid, FWD_THREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);

@@ -87,6 +87,36 @@ class GradientAllReduce:
             h.wait()
 
 
+class HostBatchPipeline:
+    """Double-buffered host -> device input pipeline (the DataLoader -> ``.to(device)`` hand-off of
+    GAN_DANet_train.ipynb:225-228): the pinned host batch of step i+1 is copied on a side stream while step i computes, so
+    the 24 MB/sample aux stack never stalls the kernels.  ``next()`` returns device tensors that are safe to use on the
+    current stream."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self._pending = None
+
+    def submit(self, host_tensors) -> None:
+        """Start the asynchronous copy of one (pinned) host batch."""
+        with torch.cuda.stream(self.copy_stream):
+            dev = [t.to(self.device, non_blocking=True) for t in host_tensors]
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._pending = (dev, ev)
+
+    def next(self):
+        """Device tensors of the batch submitted last (waits for its copy on the current stream, not on the host)."""
+        dev, ev = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in dev:
+            t.record_stream(cur)
+        return dev
+
+
 def prepare_input_nhwc(lr_grace_05: torch.Tensor, hr_aux: torch.Tensor) -> torch.Tensor:
     """GAN_DANet_train.ipynb:226-232 fused: bicubic x0.5 of the 0.5-degree field and bicubic x0.25 of the aux stack,
     written straight into the channel slices of one NHWC generator input [B, h, w, 1 + C_aux]."""
