@@ -159,19 +159,36 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
           }
           continue;
         }
-        const int per_tap = p.nsplit * p.kchunks;
+        if (p.kgroup == 1) {                               // wide tiles: one K-iteration per stage, plain nested loops
+          for (int tp = 0; tp < p.taps.n; ++tp) {
+            const int cw = tw * p.Wt * p.cs + p.taps.dw[tp], ch = th * p.Ht * p.cs + p.taps.dh[tp];
+            for (int comp = 0; comp < p.nsplit; ++comp) {
+              const CUtensorMap* mx = comp == 1 ? &mapXlo : &mapXhi;
+              const CUtensorMap* mw = comp == 2 ? &mapWlo : &mapWhi;
+              for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+                const int s = it % p.stages;
+                if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
+                mbar_expect_tx(full(s), sub_bytes);
+                tma_load_4d(base + s * sub_bytes, mx, full(s), kc * BK, cw, ch, img);
+                tma_load_3d(base + s * sub_bytes + A_BYTES, mw, full(s), kc * BK, n0, p.taps.widx[tp] + wgrp);
+              }
+            }
+          }
+          continue;
+        }
+        int tp = 0, comp = 0, kc = 0;                      // K-iteration order: tap, precision component, channel chunk
         for (int k0 = 0; k0 < KI; k0 += p.kgroup, ++it) {
           const int s = it % p.stages;
           if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
           const int cnt = min(p.kgroup, KI - k0);
           mbar_expect_tx(full(s), cnt * sub_bytes);
           for (int g = 0; g < cnt; ++g) {
-            const int k = k0 + g, tp = k / per_tap, r = k - tp * per_tap, comp = r / p.kchunks, kc = r - comp * p.kchunks;
             const CUtensorMap* mx = comp == 1 ? &mapXlo : &mapXhi;
             const CUtensorMap* mw = comp == 2 ? &mapWlo : &mapWhi;
             const uint32_t dst = base + s * stage_bytes + g * sub_bytes;
             tma_load_4d(dst, mx, full(s), kc * BK, tw * p.Wt * p.cs + p.taps.dw[tp], th * p.Ht * p.cs + p.taps.dh[tp], img);
             tma_load_3d(dst + A_BYTES, mw, full(s), kc * BK, n0, p.taps.widx[tp] + wgrp);
+            if (++kc == p.kchunks) { kc = 0; if (++comp == p.nsplit) { comp = 0; ++tp; } }
           }
         }
       }
@@ -206,6 +223,17 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
               tc_commit(empty(s));
             }
             tc_commit(aempty(sa));
+          }
+        } else if (p.kgroup == 1) {
+          for (int k = 0; k < KI; ++k, ++it) {
+            const int s = it % p.stages;
+            mbar_wait(full(s), (it / p.stages) & 1);
+            tc_fence_after();
+            const uint32_t a0 = base + s * sub_bytes, b0 = a0 + A_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks)
+              umma_f16(d_tmem, smem_desc(a0 + ks * 32, 1024, LAYOUT_SW128), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (k > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(empty(s));
           }
         } else {
           for (int k0 = 0; k0 < KI; k0 += p.kgroup, ++it) {
@@ -687,7 +715,7 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     GDN_CHECK_ARG(total < (1ll << 31));
     p.total_tiles = (int)total;
     // halo mode: stride-1 3x3 neighbourhood, one-row tiles of 128 pixels, narrow output tile (otherwise the MMA, not L2, is the limit)
-    bool halo = g_halo_enabled && p.cs == 1 && p.os == 1 && p.Wt == BM && p.Ht == 1 && p.taps.n == 9 && p.n_tile <= 64;
+    bool halo = g_halo_enabled && p.cs == 1 && p.os == 1 && p.Wt == BM && p.Ht == 1 && p.taps.n == 9 && p.n_tile <= 128;
     for (int tp = 0; tp < p.taps.n && halo; ++tp) halo = p.taps.dh[tp] >= -1 && p.taps.dh[tp] <= 1 && p.taps.dw[tp] >= -1 && p.taps.dw[tp] <= 1;
     CUtensorMap mxh, mxl, mwh, mwl;
     const int bw = halo ? HALO_W : p.Wt, bh = halo ? HALO_ROWS : p.Ht;
@@ -701,7 +729,7 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     if (halo) {
       FwdParams ph = p;
       const int b_bytes = p.n_tile * 128, w_budget = ring_budget - HALO_SLOTS * HALO_SLOT;
-      ph.kgroup = 9 * b_bytes * 2 <= w_budget ? 9 : 3;             // taps per weight stage (all 9, or one filter row)
+      ph.kgroup = 9 * b_bytes * 2 <= w_budget ? 9 : (3 * b_bytes * 2 <= w_budget ? 3 : 1);   // taps per weight stage: all 9, one filter row, or one
       ph.stages = w_budget / (ph.kgroup * b_bytes);
       if (ph.stages > MAX_STAGES) ph.stages = MAX_STAGES;
       { const char* e = getenv("GDN_HALO_BO"); ph.halo_bo = e ? atoi(e) : 0; }   // measured on B200: the swizzle phase comes from the absolute smem address, base_offset must stay 0
