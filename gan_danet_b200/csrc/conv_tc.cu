@@ -715,7 +715,7 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     GDN_CHECK_ARG(total < (1ll << 31));
     p.total_tiles = (int)total;
     // halo mode: stride-1 3x3 neighbourhood, one-row tiles of 128 pixels, narrow output tile (otherwise the MMA, not L2, is the limit)
-    bool halo = g_halo_enabled && p.cs == 1 && p.os == 1 && p.Wt == BM && p.Ht == 1 && p.taps.n == 9 && p.n_tile <= 128;
+    bool halo = g_halo_enabled && p.cs == 1 && p.os == 1 && p.Wt == BM && p.Ht == 1 && p.taps.n == 9 && p.n_tile <= 64;
     for (int tp = 0; tp < p.taps.n && halo; ++tp) halo = p.taps.dh[tp] >= -1 && p.taps.dh[tp] <= 1 && p.taps.dw[tp] >= -1 && p.taps.dw[tp] <= 1;
     CUtensorMap mxh, mxl, mwh, mwl;
     const int bw = halo ? HALO_W : p.Wt, bh = halo ? HALO_ROWS : p.Ht;

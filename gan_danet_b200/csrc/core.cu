@@ -77,6 +77,7 @@ extern "C" const char* gdn_last_error(void) { return g_err; }
 
 extern "C" int gdn_pam_tc_init(void);   // pam_tc.cu: opts the tcgen05 kernels into large dynamic shared memory
 extern "C" int gdn_conv_tc_init(void);  // conv_tc.cu
+extern "C" int gdn_linear_tc_init(void);  // linear_tc.cu
 
 extern "C" int gdn_init(int device) {
   GDN_CHECK_CUDA(cudaSetDevice(device));
@@ -88,7 +89,8 @@ extern "C" int gdn_init(int device) {
   }
   int rc = gdn_pam_tc_init();
   if (rc != GDN_OK) return rc;
-  return gdn_conv_tc_init();
+  if ((rc = gdn_conv_tc_init()) != GDN_OK) return rc;
+  return gdn_linear_tc_init();
 }
 
 extern "C" int gdn_nchw_to_nhwc(const float* src, float* dst, int dst_pitch, int dst_c0, int B, int C, int H, int W, gdn_stream_t s) {

@@ -1,0 +1,285 @@
+// nn.Linear on the tensor cores in TF32, for Discriminator1.fc1 (/root/reference/models/discriminator.py:66,75): a
+// [B, 262144] x [262144 -> 1024] layer whose 1 GB fp32 weight makes all three GEMMs HBM-bound.  The fp32
+// weight is consumed AS IT IS by tcgen05.mma kind::tf32 through TMA (no packed copy exists: any conversion pass would double the
+// traffic of a layer that is pure weight streaming); the skinny operand (activations / output gradient, <= 64 rows) rides along.
+//   forward   y[m][n]  = act(sum_k x[m][k] W[n][k] + b[n]) : D[n][m], A = W tile (K-major), B = x tile (K-major), split-K over CTAs
+//   dgrad     dx[m][k] = sum_n dz[m][n] W[n][k]            : D[k][m], A = W tile read MN-major (k contiguous), B = dz (K-major)
+//   wgrad     dW[n][k] = sum_m dz[m][n] x[m][k]            : D[n][k], A = dz read MN-major, B = x read MN-major, K = the batch rows
+// All three: persistent CTAs, warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue, two accumulator
+// buffers in TMEM (the epilogue of one tile overlaps the main loop of the next).
+#include "tc_common.cuh"
+
+namespace gdn {
+namespace lintc {
+using namespace gdn::tc;
+
+constexpr int NT = 256;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int BOXK = 32;                       // fp32 elements per 128-byte swizzled row
+enum { MODE_FWD = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
+
+// kind::tf32 instruction descriptor: D fp32 (bit 4), A/B tf32 (2 at [7,10), [10,13)), a_major bit 15, b_major bit 16 (1 = MN-major)
+__host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t desc_lbo(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)LAYOUT_SW128 << 61);
+}
+
+struct Params {
+  int Mb;            // batch rows (multiple of 16, <= 64)
+  int N, K;          // out features, in features
+  int stages, stage_bytes, a_bytes;
+  int tiles, ksteps; // persistent tile count; pipeline stages per tile
+  int ksplit;        // forward: K splits
+  float* out;        // forward: partial sums [ksplit][N][Mb]; dgrad: dx [Mb][K]; wgrad: dW [N][K]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NT, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDZ, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int MAXS = 8;
+  const uint32_t epi_off = p.stages * p.stage_bytes;                 // 4 epilogue warps x [32][32] fp32 transpose stages
+  const uint32_t bar_base = base + epi_off + 4 * 4096;
+  auto full = [&](int s) { return bar_base + 8 * s; };
+  auto empty = [&](int s) { return bar_base + 8 * (MAXS + s); };
+  auto acc_full = [&](int b) { return bar_base + 8 * (2 * MAXS + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8 * (2 * MAXS + 2 + b); };
+  const uint32_t tslot = bar_base + 8 * (2 * MAXS + 4);
+  const int NW = MODE == MODE_WGRAD ? 256 : p.Mb;                    // accumulator width (UMMA N)
+  const uint32_t tmem_cols = MODE == MODE_WGRAD ? 512u : 128u;
+  const uint32_t acc_stride = tmem_cols / 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + (tslot - base));
+  const int row_bytes = p.Mb * 128;          // one [Mb rows][32 fp32] box
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- TMA producer
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
+          const int s = it % p.stages;
+          if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
+          const uint32_t a = base + s * p.stage_bytes, b = a + p.a_bytes;
+          mbar_expect_tx(full(s), p.stage_bytes);
+          if (MODE == MODE_FWD) {            // tile = (n block, K split); stage = 64 k: 2 W boxes [128 n][32 k] + 2 x boxes [Mb][32 k]
+            const int nb = tile / p.ksplit, sp = tile % p.ksplit;
+            const int k0 = (sp * p.ksteps + ks) * 64;
+            for (int j = 0; j < 2; ++j) {
+              tma_load_2d(a + j * 16384, &mapW, full(s), k0 + j * BOXK, nb * 128);
+              tma_load_2d(b + j * row_bytes, &mapX, full(s), k0 + j * BOXK, 0);
+            }
+          } else if (MODE == MODE_DGRAD) {   // tile = 128 k; stage = 64 n: 4 W boxes [64 n][32 k] + 2 dz boxes [Mb][32 n]
+            const int k0 = tile * 128, n0 = ks * 64;
+            for (int j = 0; j < 4; ++j) tma_load_2d(a + j * 8192, &mapW, full(s), k0 + j * BOXK, n0);
+            for (int j = 0; j < 2; ++j) tma_load_2d(b + j * row_bytes, &mapDZ, full(s), n0 + j * BOXK, 0);
+          } else {                           // tile = (n block, 256-k block); one stage: 4 dz boxes [Mb][32 n] + 8 x boxes [Mb][32 k]
+            const int nb = tile % (p.N / 128), kb = tile / (p.N / 128);
+            for (int j = 0; j < 4; ++j) tma_load_2d(a + j * row_bytes, &mapDZ, full(s), nb * 128 + j * BOXK, 0);
+            for (int j = 0; j < 8; ++j) tma_load_2d(b + j * row_bytes, &mapX, full(s), kb * 256 + j * BOXK, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---- MMA issuer
+      const uint32_t id = MODE == MODE_FWD ? idesc(128, NW, 0, 0) : (MODE == MODE_DGRAD ? idesc(128, NW, 1, 0) : idesc(128, NW, 1, 1));
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+        const int ab = lt & 1;
+        if (lt >= 2) mbar_wait(acc_empty(ab), ((lt >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem + ab * acc_stride;
+        for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(full(s), (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t a = base + s * p.stage_bytes, b = a + p.a_bytes;
+          if (MODE == MODE_FWD) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)      // 64 k = 2 boxes x 4 steps of 8 (32 bytes along the swizzled row)
+              umma_tf32(d, smem_desc(a + (i >> 2) * 16384 + (i & 3) * 32, 1024, LAYOUT_SW128), smem_desc(b + (i >> 2) * row_bytes + (i & 3) * 32, 1024, LAYOUT_SW128), id,
+                        (ks > 0 || i > 0) ? 1u : 0u);
+          } else if (MODE == MODE_DGRAD) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)      // 64 n = 8 steps of 8 rows of the W boxes (MN-major A: 32-k groups 8 KB apart); dz K-major
+              umma_tf32(d, desc_lbo(a + i * 1024, 8192, 1024), smem_desc(b + (i >> 2) * row_bytes + (i & 3) * 32, 1024, LAYOUT_SW128), id, (ks > 0 || i > 0) ? 1u : 0u);
+          } else {
+            for (int i = 0; i < p.Mb / 8; ++i)   // K = batch rows, 8 per step; both operands MN-major, 32-column groups one box apart
+              umma_tf32(d, desc_lbo(a + i * 1024, row_bytes, 1024), desc_lbo(b + i * 1024, row_bytes, 1024), id, i > 0 ? 1u : 0u);
+          }
+          tc_commit(empty(s));
+        }
+        tc_commit(acc_full(ab));
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: thread = accumulator row (TMEM lane)
+    const int q = warp & 3;
+    float* stg = reinterpret_cast<float*>(sm + epi_off + q * 4096);
+    const int rsub = lane >> 3, cj = lane & 7;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      mbar_wait(acc_full(ab), (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t src = tmem + ab * acc_stride + ((uint32_t)(q * 32) << 16);
+      const int row = q * 32 + lane;
+      for (int c = 0; c < NW; c += 32) {
+        float v[32];
+        tmem_ld32(src + c, v);
+        if (MODE == MODE_FWD) {              // partial[split][n][m]: the thread's row is contiguous
+          const int nb = tile / p.ksplit, sp = tile % p.ksplit;
+          float* dst = p.out + ((size_t)sp * p.N + nb * 128 + row) * p.Mb + c;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            if (c + e < p.Mb) *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        } else if (MODE == MODE_DGRAD) {     // dx[m][k0 + row]: a warp writes 32 consecutive k per m
+          float* dst = p.out + (size_t)tile * 128 + row;
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c + e < p.Mb) dst[(size_t)(c + e) * p.K] = v[e];
+        } else {                             // dW[n0 + row][k0 + c ..]: transpose through smem so a store covers 4 rows x 128 B
+          const int nb = tile % (p.N / 128), kb = tile / (p.N / 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int r = 4 * i8 + rsub;
+            const float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((cj ^ (r & 7)) << 2));
+            *reinterpret_cast<float4*>(p.out + (size_t)(nb * 128 + q * 32 + r) * p.K + (size_t)kb * 256 + c + cj * 4) = o;
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(ab));
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+  }
+}
+
+// y[m][n] = act(sum_s partial[s][n][m] + bias[n])  (fixed order: deterministic)
+__global__ void linear_fwd_reduce_kernel(const float* __restrict__ partial, int ksplit, int N, int Mb, const float* __restrict__ bias, int act, float slope,
+                                         float* __restrict__ y) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * Mb) return;
+  const int n = idx / Mb, m = idx - n * Mb;
+  float acc = 0.f;
+  for (int s = 0; s < ksplit; ++s) acc += partial[((size_t)s * N + n) * Mb + m];
+  y[(size_t)m * N + n] = apply_act(acc + (bias ? bias[n] : 0.f), act, slope);
+}
+
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("linear_tc: cuTensorMapEncodeTiled unavailable"); return GDN_ECUDA; }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BOXK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("linear_tc: cuTensorMapEncodeTiled(rows=%llu cols=%llu box_rows=%u) failed (%d)", (unsigned long long)rows, (unsigned long long)cols, box_rows, (int)r); return GDN_ECUDA; }
+  return GDN_OK;
+}
+static size_t smem_bytes(const Params& p) { return (size_t)p.stages * p.stage_bytes + 4 * 4096 + 8 * (2 * 8 + 6) + 1024; }
+}  // namespace lintc
+}  // namespace gdn
+
+using namespace gdn;
+using namespace gdn::lintc;
+
+extern "C" int gdn_linear_tc_init(void) {
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<MODE_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<MODE_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  return GDN_OK;
+}
+
+// shapes the kernels take: batch rows multiple of 16 and <= 64, out features multiple of 128, in features multiple of 256
+extern "C" int gdn_linear_tc_supported(int Mb, int N, int K) { return Mb >= 16 && Mb <= 64 && Mb % 16 == 0 && N % 128 == 0 && K % 256 == 0 && K >= 4096; }
+
+static int fwd_ksplit(int N, int K) {
+  int s = kNumSMs / (N / 128);
+  if (s < 1) s = 1;
+  while (s > 1 && (K / 64) % s != 0) --s;       // equal K ranges
+  return s;
+}
+extern "C" size_t gdn_linear_tc_fwd_ws_bytes(int Mb, int N, int K) { return (size_t)fwd_ksplit(N, K) * N * Mb * sizeof(float); }
+
+extern "C" int gdn_linear_tc_fwd(const float* x, const float* w, const float* bias, float* y, int Mb, int N, int K, int act, float slope, float* ws, size_t ws_bytes,
+                                 gdn_stream_t s) {
+  GDN_CHECK_ARG(x && w && y && ws && gdn_linear_tc_supported(Mb, N, K));
+  if (ws_bytes < gdn_linear_tc_fwd_ws_bytes(Mb, N, K)) { set_error("gdn_linear_tc_fwd: workspace too small"); return GDN_EWORKSPACE; }
+  Params p = {};
+  p.Mb = Mb; p.N = N; p.K = K; p.ksplit = fwd_ksplit(N, K);
+  p.a_bytes = 2 * 16384; p.stage_bytes = p.a_bytes + 2 * Mb * 128;
+  p.stages = (SMEM_LIMIT - 20 * 1024) / p.stage_bytes; if (p.stages > 8) p.stages = 8;
+  p.tiles = (N / 128) * p.ksplit; p.ksteps = K / 64 / p.ksplit; p.out = ws;
+  CUtensorMap mw, mx;
+  int rc;
+  if ((rc = make_map(&mw, w, N, K, 128)) != GDN_OK) return rc;
+  if ((rc = make_map(&mx, x, Mb, K, Mb)) != GDN_OK) return rc;
+  cudaStream_t st = as_stream(s);
+  linear_tc_kernel<MODE_FWD><<<p.tiles < kNumSMs ? p.tiles : kNumSMs, NT, smem_bytes(p), st>>>(mw, mx, mx, p);
+  GDN_CHECK_LAUNCH();
+  linear_fwd_reduce_kernel<<<(unsigned)cdiv((long long)N * Mb, 256), 256, 0, st>>>(ws, p.ksplit, N, Mb, bias, act, slope, y);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" int gdn_linear_tc_dgrad(const float* dz, const float* w, float* dx, int Mb, int N, int K, gdn_stream_t s) {
+  GDN_CHECK_ARG(dz && w && dx && gdn_linear_tc_supported(Mb, N, K));
+  Params p = {};
+  p.Mb = Mb; p.N = N; p.K = K;
+  p.a_bytes = 4 * 8192; p.stage_bytes = p.a_bytes + 2 * Mb * 128;
+  p.stages = (SMEM_LIMIT - 20 * 1024) / p.stage_bytes; if (p.stages > 8) p.stages = 8;
+  p.tiles = K / 128; p.ksteps = N / 64; p.out = dx;
+  CUtensorMap mw, mz;
+  int rc;
+  if ((rc = make_map(&mw, w, N, K, 64)) != GDN_OK) return rc;
+  if ((rc = make_map(&mz, dz, Mb, N, Mb)) != GDN_OK) return rc;
+  linear_tc_kernel<MODE_DGRAD><<<p.tiles < kNumSMs ? p.tiles : kNumSMs, NT, smem_bytes(p), as_stream(s)>>>(mw, mz, mz, p);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" int gdn_linear_tc_wgrad(const float* dz, const float* x, float* dw, int Mb, int N, int K, gdn_stream_t s) {
+  GDN_CHECK_ARG(dz && x && dw && gdn_linear_tc_supported(Mb, N, K) && ((uintptr_t)dw & 15) == 0);
+  Params p = {};
+  p.Mb = Mb; p.N = N; p.K = K;
+  p.a_bytes = 4 * Mb * 128; p.stage_bytes = 12 * Mb * 128;
+  p.stages = (SMEM_LIMIT - 20 * 1024) / p.stage_bytes; if (p.stages > 8) p.stages = 8;
+  p.tiles = (N / 128) * (K / 256); p.ksteps = 1; p.out = dw;
+  CUtensorMap mx, mz;
+  int rc;
+  if ((rc = make_map(&mx, x, Mb, K, Mb)) != GDN_OK) return rc;
+  if ((rc = make_map(&mz, dz, Mb, N, Mb)) != GDN_OK) return rc;
+  linear_tc_kernel<MODE_WGRAD><<<p.tiles < kNumSMs ? p.tiles : kNumSMs, NT, smem_bytes(p), as_stream(s)>>>(mx, mx, mz, p);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}

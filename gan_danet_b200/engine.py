@@ -506,15 +506,32 @@ def op_conv(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, stride: int = 1,
     return y
 
 
+linear_tensor_core: Optional[bool] = None     # None: TF32 tensor cores in the 'bf16' conv precision mode only; True / False force it
+
+
+def _linear_tc(lib, Bn: int, Fout: int, Fin: int) -> bool:
+    use = linear_tensor_core if linear_tensor_core is not None else conv_precision == "bf16"
+    return bool(use) and bool(lib.gdn_linear_tc_supported(Bn, Fout, Fin))
+
+
 def op_linear(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, act: int = ACT_NONE, slope: float = 0.0) -> Var:
-    """nn.Linear on a [B, F] matrix (+ fused activation).  Runs on the implicit-GEMM engine as a 1x1 convolution over a
-    B x 1 x 1 grid; the data gradient uses the reduction-form kernel so the [out,in] weight is never transposed."""
+    """nn.Linear on a [B, F] matrix (+ fused activation).  Large layers (Discriminator1.fc1) stream their fp32 weight through the
+    TF32 tcgen05 kernels of linear_tc.cu; the rest runs on the fp32 implicit-GEMM engine as a 1x1 convolution over a B x 1 x 1
+    grid (the data gradient uses the reduction-form kernel so the [out,in] weight is never transposed)."""
     Bn, Fin = x.t.shape
     Fout = w.t.shape[0]
+    lib = _lib(x.t)
+    tc = _linear_tc(lib, Bn, Fout, Fin) and x.t.is_contiguous() and w.t.is_contiguous()
     x4 = x.t.view(Bn, 1, 1, Fin)
     y = Var(torch.empty((Bn, Fout), dtype=torch.float32, device=x.t.device))
-    conv_raw(x4, w.t.detach().view(Fout, 1, 1, Fin), y.t.view(Bn, 1, 1, Fout), kh=1, kw=1,
-             bias=None if bias is None else bias.t.detach(), act=act, slope=slope)
+    if tc:
+        buf = workspace("linear_tc", lib.gdn_linear_tc_fwd_ws_bytes(Bn, Fout, Fin), x.t.device)
+        _timed("linear_tc_kernel", 2.0 * Bn * Fout * Fin,
+               lambda: L.check(lib.gdn_linear_tc_fwd(x.t.data_ptr(), w.t.data_ptr(), None if bias is None else bias.t.data_ptr(), y.t.data_ptr(), Bn, Fout, Fin, act, slope,
+                                                     buf.data_ptr(), buf.numel(), _stream()), "gdn_linear_tc_fwd"), f"fwd {Bn}x{Fin}->{Fout}")
+    else:
+        conv_raw(x4, w.t.detach().view(Fout, 1, 1, Fin), y.t.view(Bn, 1, 1, Fout), kh=1, kw=1,
+                 bias=None if bias is None else bias.t.detach(), act=act, slope=slope)
 
     def bwd():
         if y.g is None:
@@ -525,19 +542,28 @@ def op_linear(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, act: int = ACT
             act_bwd(dy, y.t, dz, act, slope)
         else:
             dz = dy
+        dz = dz.contiguous()
         dz4 = dz.view(Bn, 1, 1, Fout)
         if bias is not None and bias.needs_grad:
             bias.add_grad(sums_to_float(colstats(dz), Fout))
         if w.needs_grad:
             gw = torch.empty_like(w.t)
-            wgrad_raw(dz4, x4, gw.view(Fout, Fin, 1, 1), kh=1, kw=1)
+            if tc:
+                _timed("linear_tc_kernel", 2.0 * Bn * Fout * Fin,
+                       lambda: L.check(lib.gdn_linear_tc_wgrad(dz.data_ptr(), x.t.data_ptr(), gw.data_ptr(), Bn, Fout, Fin, _stream()), "gdn_linear_tc_wgrad"), f"wgrad {Bn}x{Fin}->{Fout}")
+            else:
+                wgrad_raw(dz4, x4, gw.view(Fout, Fin, 1, 1), kh=1, kw=1)
             w.add_grad(gw)
         if x.needs_grad:
-            # dx[b][j] = sum_o dz[b][o] W[o][j]: "pixels" = output features o, dy' = dz^T [Fout][Bn], x' = W [Fout][Fin]
-            dzt = torch.empty((Fout, Bn), dtype=torch.float32, device=dz.device)
-            nhwc_to_nchw(dz.view(1, Bn, 1, Fout), dzt.view(1, Fout, Bn, 1))
             gx = torch.empty((Bn, Fin), dtype=torch.float32, device=dz.device)
-            wgrad_raw(dzt.view(1, Fout, 1, Bn), w.t.detach().view(1, Fout, 1, Fin), gx, kh=1, kw=1, layout=0)
+            if tc:
+                _timed("linear_tc_kernel", 2.0 * Bn * Fout * Fin,
+                       lambda: L.check(lib.gdn_linear_tc_dgrad(dz.data_ptr(), w.t.data_ptr(), gx.data_ptr(), Bn, Fout, Fin, _stream()), "gdn_linear_tc_dgrad"), f"dgrad {Bn}x{Fin}->{Fout}")
+            else:
+                # dx[b][j] = sum_o dz[b][o] W[o][j]: "pixels" = output features o, dy' = dz^T [Fout][Bn], x' = W [Fout][Fin]
+                dzt = torch.empty((Fout, Bn), dtype=torch.float32, device=dz.device)
+                nhwc_to_nchw(dz.view(1, Bn, 1, Fout), dzt.view(1, Fout, Bn, 1))
+                wgrad_raw(dzt.view(1, Fout, 1, Bn), w.t.detach().view(1, Fout, 1, Fin), gx, kh=1, kw=1, layout=0)
             x.add_grad(gx)
 
     tape.push(bwd)

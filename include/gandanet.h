@@ -161,6 +161,23 @@ typedef struct {
 size_t gdn_conv2d_wgrad_tc_ws_bytes(const gdn_wgrad_tc_args* a);
 int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s);
 
+/* ----------------------------------------------- linear layer on tensor cores (TF32) */
+/*
+ * nn.Linear for Discriminator1.fc1 (discriminator.py:66,75: [B, 512*H/16*W/16] -> 1024, LeakyReLU) and its autograd, as
+ * tcgen05.mma kind::tf32 GEMMs that stream the fp32 weight exactly once through TMA (HBM-bound: the weight is 1 GB at the
+ * 256x512 output grid).  x: [Mb][K], w: [N][K], y/dz: [Mb][N], all fp32 row-major, 16-byte aligned.
+ * Supported: Mb in {16,32,48,64}, N % 128 == 0, K % 256 == 0 (gdn_linear_tc_supported); everything else uses gdn_conv2d.
+ */
+int gdn_linear_tc_supported(int Mb, int N, int K);
+size_t gdn_linear_tc_fwd_ws_bytes(int Mb, int N, int K);
+/* y = act(x w^T + bias) */
+int gdn_linear_tc_fwd(const float* x, const float* w, const float* bias, float* y, int Mb, int N, int K, int act, float slope,
+                      float* ws, size_t ws_bytes, gdn_stream_t s);
+/* dx = dz w */
+int gdn_linear_tc_dgrad(const float* dz, const float* w, float* dx, int Mb, int N, int K, gdn_stream_t s);
+/* dw = dz^T x (overwrites) */
+int gdn_linear_tc_wgrad(const float* dz, const float* x, float* dw, int Mb, int N, int K, gdn_stream_t s);
+
 /* ------------------------------------------------------------ elementwise */
 /* per-channel sums over M rows of an NHWC slice: out[0..C) = sum x, out[C..2C) = sum x*x (double).  BN statistics
  * (generator.py:32,61,149,189,219,223) and bias gradients.  ws: gdn_colstats_ws_bytes(M, C). */

@@ -1,0 +1,40 @@
+"""TF32 tcgen05 linear-layer kernels (linear_tc.cu: Discriminator1.fc1, discriminator.py:66,75) against float64.
+TF32 operands (10-bit mantissa) with fp32 accumulation over K >= 8192 terms: 2e-3 relative L2."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("Mb,N,K", [(16, 128, 8192), (64, 256, 16384), (32, 1024, 32768)])
+def test_linear_tc(Mb, N, K):
+    from gan_danet_b200 import engine as E
+    from gan_danet_b200._lib import ACT_LRELU
+    g = torch.Generator().manual_seed(Mb + N)
+    x = torch.randn(Mb, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    r = torch.randn(Mb, N, generator=g).to(DEV)
+    old = E.linear_tensor_core
+    E.linear_tensor_core = True
+    try:
+        tape = E.Tape()
+        xv, wv, bv = E.Var(x), E.Var(w), E.Var(b)
+        y = E.op_linear(tape, xv, wv, bv, act=ACT_LRELU, slope=0.2)
+        y.g = r.clone()
+        tape.backward()
+        torch.cuda.synchronize()
+    finally:
+        E.linear_tensor_core = old
+    xd, wd, bd = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yref = torch.nn.functional.leaky_relu(xd @ wd.t() + bd, 0.2)
+    yref.backward(r.double())
+    assert rel(y.t, yref) < 2e-3, rel(y.t, yref)
+    assert rel(xv.g, xd.grad) < 2e-3, rel(xv.g, xd.grad)
+    assert rel(wv.g, wd.grad) < 2e-3, rel(wv.g, wd.grad)
+    assert rel(bv.g, bd.grad) < 1e-5
