@@ -4,7 +4,8 @@
 // traffic of a layer that is pure weight streaming); the skinny operand (activations / output gradient, <= 64 rows) rides along.
 //   forward   y[m][n]  = act(sum_k x[m][k] W[n][k] + b[n]) : D[n][m], A = W tile (K-major), B = x tile (K-major), split-K over CTAs
 //   dgrad     dx[m][k] = sum_n dz[m][n] W[n][k]            : D[k][m], A = W tile read MN-major (k contiguous), B = dz (K-major)
-//   wgrad     dW[n][k] = sum_m dz[m][n] x[m][k]            : D[n][k], A = dz read MN-major, B = x read MN-major, K = the batch rows
+//   wgrad     dW[n][k] = sum_m dz[m][n] x[m][k]            : D[k][n], A = x read MN-major, B = dz^T [n][m] (K-major; a 256 KB transpose), K = batch rows
+//             (measured on B200: kind::tf32 with an MN-major *B* operand returns zeros, MN-major A is fine -- hence the transposed form)
 // All three: persistent CTAs, warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue, two accumulator
 // buffers in TMEM (the epilogue of one tile overlaps the main loop of the next).
 #include "tc_common.cuh"
@@ -90,17 +91,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             const int k0 = tile * 128, n0 = ks * 64;
             for (int j = 0; j < 4; ++j) tma_load_2d(a + j * 8192, &mapW, full(s), k0 + j * BOXK, n0);
             for (int j = 0; j < 2; ++j) tma_load_2d(b + j * row_bytes, &mapDZ, full(s), n0 + j * BOXK, 0);
-          } else {                           // tile = (n block, 256-k block); one stage: 4 dz boxes [Mb][32 n] + 8 x boxes [Mb][32 k]
-            const int nb = tile % (p.N / 128), kb = tile / (p.N / 128);
-            for (int j = 0; j < 4; ++j) tma_load_2d(a + j * row_bytes, &mapDZ, full(s), nb * 128 + j * BOXK, 0);
-            for (int j = 0; j < 8; ++j) tma_load_2d(b + j * row_bytes, &mapX, full(s), kb * 256 + j * BOXK, 0);
+          } else {                           // tile = (256-n block, 128-k block); one stage: 4 x boxes [Mb][32 k] + Mb/32 dz^T boxes [256 n][32 m]
+            const int nb = tile % (p.N / 256), kb = tile / (p.N / 256);
+            for (int j = 0; j < 4; ++j) tma_load_2d(a + j * row_bytes, &mapX, full(s), kb * 128 + j * BOXK, 0);
+            for (int j = 0; j < p.Mb / 32; ++j) tma_load_2d(b + j * 32768, &mapDZ, full(s), j * BOXK, nb * 256);
           }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ---- MMA issuer
-      const uint32_t id = MODE == MODE_FWD ? idesc(128, NW, 0, 0) : (MODE == MODE_DGRAD ? idesc(128, NW, 1, 0) : idesc(128, NW, 1, 1));
+      const uint32_t id = MODE == MODE_FWD ? idesc(128, NW, 0, 0) : idesc(128, NW, 1, 0);
       int it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
         const int ab = lt & 1;
@@ -122,8 +123,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             for (int i = 0; i < 8; ++i)      // 64 n = 8 steps of 8 rows of the W boxes (MN-major A: 32-k groups 8 KB apart); dz K-major
               umma_tf32(d, desc_lbo(a + i * 1024, 8192, 1024), smem_desc(b + (i >> 2) * row_bytes + (i & 3) * 32, 1024, LAYOUT_SW128), id, (ks > 0 || i > 0) ? 1u : 0u);
           } else {
-            for (int i = 0; i < p.Mb / 8; ++i)   // K = batch rows, 8 per step; both operands MN-major, 32-column groups one box apart
-              umma_tf32(d, desc_lbo(a + i * 1024, row_bytes, 1024), desc_lbo(b + i * 1024, row_bytes, 1024), id, i > 0 ? 1u : 0u);
+            for (int i = 0; i < p.Mb / 8; ++i)   // K = batch rows, 8 per step: x MN-major (32-k groups one box apart), dz^T K-major
+              umma_tf32(d, desc_lbo(a + i * 1024, row_bytes, 1024), smem_desc(b + (i >> 2) * 32768 + (i & 3) * 32, 1024, LAYOUT_SW128), id, i > 0 ? 1u : 0u);
           }
           tc_commit(empty(s));
         }
@@ -133,8 +134,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
   } else if (warp >= 4) {
     // ---- epilogue: thread = accumulator row (TMEM lane)
     const int q = warp & 3;
-    float* stg = reinterpret_cast<float*>(sm + epi_off + q * 4096);
-    const int rsub = lane >> 3, cj = lane & 7;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
       const int ab = lt & 1;
@@ -156,19 +155,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
 #pragma unroll
           for (int e = 0; e < 32; ++e)
             if (c + e < p.Mb) dst[(size_t)(c + e) * p.K] = v[e];
-        } else {                             // dW[n0 + row][k0 + c ..]: transpose through smem so a store covers 4 rows x 128 B
-          const int nb = tile % (p.N / 128), kb = tile / (p.N / 128);
+        } else {                             // dW[n0 + c + e][k0 + row]: a warp writes 32 consecutive k per n
+          const int nb = tile % (p.N / 256), kb = tile / (p.N / 256);
+          float* dst = p.out + (size_t)(nb * 256 + c) * p.K + (size_t)kb * 128 + row;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const int r = 4 * i8 + rsub;
-            const float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((cj ^ (r & 7)) << 2));
-            *reinterpret_cast<float4*>(p.out + (size_t)(nb * 128 + q * 32 + r) * p.K + (size_t)kb * 256 + c + cj * 4) = o;
-          }
-          __syncwarp();
+          for (int e = 0; e < 32; ++e) dst[(size_t)e * p.K] = v[e];
         }
       }
       tc_fence_before();
@@ -268,18 +259,31 @@ extern "C" int gdn_linear_tc_dgrad(const float* dz, const float* w, float* dx, i
   return GDN_OK;
 }
 
-extern "C" int gdn_linear_tc_wgrad(const float* dz, const float* x, float* dw, int Mb, int N, int K, gdn_stream_t s) {
-  GDN_CHECK_ARG(dz && x && dw && gdn_linear_tc_supported(Mb, N, K) && ((uintptr_t)dw & 15) == 0);
+extern "C" size_t gdn_linear_tc_wgrad_ws_bytes(int Mb, int N, int K) { (void)K; return (size_t)N * Mb * sizeof(float); }
+
+__global__ void transpose_small_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {   // out[c][r] = in[r][c]
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int c = idx / rows, r = idx - c * rows;
+  out[idx] = in[(size_t)r * cols + c];
+}
+
+extern "C" int gdn_linear_tc_wgrad(const float* dz, const float* x, float* dw, int Mb, int N, int K, float* ws, size_t ws_bytes, gdn_stream_t s) {
+  GDN_CHECK_ARG(dz && x && dw && ws && gdn_linear_tc_supported(Mb, N, K) && Mb % 32 == 0 && N % 256 == 0 && ((uintptr_t)ws & 15) == 0);
+  if (ws_bytes < gdn_linear_tc_wgrad_ws_bytes(Mb, N, K)) { set_error("gdn_linear_tc_wgrad: workspace too small"); return GDN_EWORKSPACE; }
+  cudaStream_t st = as_stream(s);
+  transpose_small_kernel<<<(unsigned)cdiv((long long)N * Mb, 256), 256, 0, st>>>(dz, ws, Mb, N);     // dz^T [N][Mb]
+  GDN_CHECK_LAUNCH();
   Params p = {};
   p.Mb = Mb; p.N = N; p.K = K;
-  p.a_bytes = 4 * Mb * 128; p.stage_bytes = 12 * Mb * 128;
+  p.a_bytes = 4 * Mb * 128; p.stage_bytes = p.a_bytes + (Mb / 32) * 32768;
   p.stages = (SMEM_LIMIT - 20 * 1024) / p.stage_bytes; if (p.stages > 8) p.stages = 8;
-  p.tiles = (N / 128) * (K / 256); p.ksteps = 1; p.out = dw;
+  p.tiles = (N / 256) * (K / 128); p.ksteps = 1; p.out = dw;
   CUtensorMap mx, mz;
   int rc;
   if ((rc = make_map(&mx, x, Mb, K, Mb)) != GDN_OK) return rc;
-  if ((rc = make_map(&mz, dz, Mb, N, Mb)) != GDN_OK) return rc;
-  linear_tc_kernel<MODE_WGRAD><<<p.tiles < kNumSMs ? p.tiles : kNumSMs, NT, smem_bytes(p), as_stream(s)>>>(mx, mx, mz, p);
+  if ((rc = make_map(&mz, ws, N, Mb, 256)) != GDN_OK) return rc;
+  linear_tc_kernel<MODE_WGRAD><<<p.tiles < kNumSMs ? p.tiles : kNumSMs, NT, smem_bytes(p), st>>>(mx, mx, mz, p);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

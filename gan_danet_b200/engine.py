@@ -548,9 +548,11 @@ def op_linear(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, act: int = ACT
             bias.add_grad(sums_to_float(colstats(dz), Fout))
         if w.needs_grad:
             gw = torch.empty_like(w.t)
-            if tc:
+            if tc and Bn % 32 == 0 and Fout % 256 == 0:
+                wbuf = workspace("linear_tc_w", lib.gdn_linear_tc_wgrad_ws_bytes(Bn, Fout, Fin), dz.device)
                 _timed("linear_tc_kernel", 2.0 * Bn * Fout * Fin,
-                       lambda: L.check(lib.gdn_linear_tc_wgrad(dz.data_ptr(), x.t.data_ptr(), gw.data_ptr(), Bn, Fout, Fin, _stream()), "gdn_linear_tc_wgrad"), f"wgrad {Bn}x{Fin}->{Fout}")
+                       lambda: L.check(lib.gdn_linear_tc_wgrad(dz.data_ptr(), x.t.data_ptr(), gw.data_ptr(), Bn, Fout, Fin, wbuf.data_ptr(), wbuf.numel(), _stream()),
+                                       "gdn_linear_tc_wgrad"), f"wgrad {Bn}x{Fin}->{Fout}")
             else:
                 wgrad_raw(dz4, x4, gw.view(Fout, Fin, 1, 1), kh=1, kw=1)
             w.add_grad(gw)

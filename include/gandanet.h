@@ -175,8 +175,9 @@ int gdn_linear_tc_fwd(const float* x, const float* w, const float* bias, float* 
                       float* ws, size_t ws_bytes, gdn_stream_t s);
 /* dx = dz w */
 int gdn_linear_tc_dgrad(const float* dz, const float* w, float* dx, int Mb, int N, int K, gdn_stream_t s);
-/* dw = dz^T x (overwrites) */
-int gdn_linear_tc_wgrad(const float* dz, const float* x, float* dw, int Mb, int N, int K, gdn_stream_t s);
+/* dw = dz^T x (overwrites); additionally Mb % 32 == 0 and N % 256 == 0; ws holds dz^T */
+size_t gdn_linear_tc_wgrad_ws_bytes(int Mb, int N, int K);
+int gdn_linear_tc_wgrad(const float* dz, const float* x, float* dw, int Mb, int N, int K, float* ws, size_t ws_bytes, gdn_stream_t s);
 
 /* ------------------------------------------------------------ elementwise */
 /* per-channel sums over M rows of an NHWC slice: out[0..C) = sum x, out[C..2C) = sum x*x (double).  BN statistics
