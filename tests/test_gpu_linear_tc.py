@@ -11,7 +11,8 @@ def rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("Mb,N,K", [(16, 128, 8192), (64, 256, 16384), (32, 1024, 32768)]   # (16,128): weight gradient stays on the fp32 engine)
+# (16, 128, .): the weight gradient stays on the fp32 engine (its tensor-core form needs Mb % 32 == 0 and N % 256 == 0)
+@pytest.mark.parametrize("Mb,N,K", [(16, 128, 8192), (64, 256, 16384), (32, 1024, 32768)])
 def test_linear_tc(Mb, N, K):
     from gan_danet_b200 import engine as E
     from gan_danet_b200._lib import ACT_LRELU
