@@ -5,7 +5,7 @@
 //   forward   y[m][n]  = act(sum_k x[m][k] W[n][k] + b[n]) : D[n][m], A = W tile (K-major), B = x tile (K-major), split-K over CTAs
 //   dgrad     dx[m][k] = sum_n dz[m][n] W[n][k]            : D[k][m], A = W tile read MN-major (k contiguous), B = dz (K-major)
 //   wgrad     dW[n][k] = sum_m dz[m][n] x[m][k]            : D[k][n], A = x read MN-major, B = dz^T [n][m] (K-major; a 256 KB transpose), K = batch rows
-//             (measured on B200: kind::tf32 with an MN-major *B* operand returns zeros, MN-major A is fine -- hence the transposed form)
+//             (both gradients read a 32-bit operand MN-major: this needs the 128B-swizzle-with-32-byte-atom layout, see desc_mn32)
 // All three: persistent CTAs, warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue, two accumulator
 // buffers in TMEM (the epilogue of one tile overlaps the main loop of the next).
 #include "tc_common.cuh"
@@ -23,9 +23,13 @@ enum { MODE_FWD = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
 __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ uint64_t desc_lbo(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)LAYOUT_SW128 << 61);
+// MN-major operand of a 32-bit type: the transposing read needs the "128B swizzle with 32-byte atomicity" layout (UMMA layout type 1,
+// cute's Layout_MN_SW128_32B_Atom = Swizzle<2,5,2>, 4 K-rows per atom; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  Measured on B200:
+// with the plain 128B swizzle (layout type 2) kind::tf32 returns zeros for an MN-major operand.
+constexpr uint32_t LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t desc_mn32(uint32_t addr, uint32_t lbo_bytes) {     // one MMA step = 8 K-rows = two 4-row atoms 512 B apart
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((512u >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)LAYOUT_SW128_BASE32B << 61);
 }
 
 struct Params {
@@ -121,10 +125,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
           } else if (MODE == MODE_DGRAD) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)      // 64 n = 8 steps of 8 rows of the W boxes (MN-major A: 32-k groups 8 KB apart); dz K-major
-              umma_tf32(d, desc_lbo(a + i * 1024, 8192, 1024), smem_desc(b + (i >> 2) * row_bytes + (i & 3) * 32, 1024, LAYOUT_SW128), id, (ks > 0 || i > 0) ? 1u : 0u);
+              umma_tf32(d, desc_mn32(a + i * 1024, 8192), smem_desc(b + (i >> 2) * row_bytes + (i & 3) * 32, 1024, LAYOUT_SW128), id, (ks > 0 || i > 0) ? 1u : 0u);
           } else {
             for (int i = 0; i < p.Mb / 8; ++i)   // K = batch rows, 8 per step: x MN-major (32-k groups one box apart), dz^T K-major
-              umma_tf32(d, desc_lbo(a + i * 1024, row_bytes, 1024), smem_desc(b + (i >> 2) * 32768 + (i & 3) * 32, 1024, LAYOUT_SW128), id, i > 0 ? 1u : 0u);
+              umma_tf32(d, desc_mn32(a + i * 1024, row_bytes), smem_desc(b + (i >> 2) * 32768 + (i & 3) * 32, 1024, LAYOUT_SW128), id, i > 0 ? 1u : 0u);
           }
           tc_commit(empty(s));
         }
@@ -185,15 +189,15 @@ __global__ void linear_fwd_reduce_kernel(const float* __restrict__ partial, int 
   y[(size_t)m * N + n] = apply_act(acc + (bias ? bias[n] : 0.f), act, slope);
 }
 
-static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, bool mn32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("linear_tc: cuTensorMapEncodeTiled unavailable"); return GDN_ECUDA; }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {cols * 4};
   cuuint32_t box[2] = {(cuuint32_t)BOXK, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("linear_tc: cuTensorMapEncodeTiled(rows=%llu cols=%llu box_rows=%u) failed (%d)", (unsigned long long)rows, (unsigned long long)cols, box_rows, (int)r); return GDN_ECUDA; }
   return GDN_OK;
 }
@@ -252,7 +256,7 @@ extern "C" int gdn_linear_tc_dgrad(const float* dz, const float* w, float* dx, i
   p.tiles = K / 128; p.ksteps = N / 64; p.out = dx;
   CUtensorMap mw, mz;
   int rc;
-  if ((rc = make_map(&mw, w, N, K, 64)) != GDN_OK) return rc;
+  if ((rc = make_map(&mw, w, N, K, 64, true)) != GDN_OK) return rc;
   if ((rc = make_map(&mz, dz, Mb, N, Mb)) != GDN_OK) return rc;
   linear_tc_kernel<MODE_DGRAD><<<p.tiles < kNumSMs ? p.tiles : kNumSMs, NT, smem_bytes(p), as_stream(s)>>>(mw, mz, mz, p);
   GDN_CHECK_LAUNCH();
@@ -281,7 +285,7 @@ extern "C" int gdn_linear_tc_wgrad(const float* dz, const float* x, float* dw, i
   p.tiles = (N / 256) * (K / 128); p.ksteps = 1; p.out = dw;
   CUtensorMap mx, mz;
   int rc;
-  if ((rc = make_map(&mx, x, Mb, K, Mb)) != GDN_OK) return rc;
+  if ((rc = make_map(&mx, x, Mb, K, Mb, true)) != GDN_OK) return rc;
   if ((rc = make_map(&mz, ws, N, Mb, 256)) != GDN_OK) return rc;
   linear_tc_kernel<MODE_WGRAD><<<p.tiles < kNumSMs ? p.tiles : kNumSMs, NT, smem_bytes(p), st>>>(mx, mx, mz, p);
   GDN_CHECK_LAUNCH();
