@@ -102,6 +102,11 @@ SIGNATURES = {
     "gdn_linear_tc_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "gdn_linear_tc_wgrad_ws_bytes": (_sz, [_i, _i, _i]),
     "gdn_linear_tc_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "gdn_thin_conv_supported": (_i, [_i, _i, _i]),
+    "gdn_thin_conv_expand": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "gdn_thin_conv_reduce": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "gdn_thin_conv_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i]),
+    "gdn_thin_conv_wgrad": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "gdn_colstats_ws_bytes": (_sz, [_ll, _i]),
     "gdn_colstats": (_i, [_vp, _i, _i, _ll, _i, _vp, _vp, _vp]),
     "gdn_bn_finalize": (_i, [_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -296,6 +296,23 @@ def wgrad_tc_raw(dyp: Packed, xp: Packed, out: Tensor, *, B: int, in_hw: Tuple[i
            f"wgrad B{B} {in_hw[0]}x{in_hw[1]}->{out_hw[0]}x{out_hw[1]} C{cin}->{cout} k{kh} s{stride}")
 
 
+thin_conv_enabled: bool = os.environ.get("GDN_THIN_CONV", "1") != "0"
+
+
+def _thin_kind(Cin: int, O: int, kh: int, kw: int, stride: int, x: Tensor, y: Tensor, act: int = ACT_NONE, bias=None, res=None) -> Optional[str]:
+    """'expand' (1 -> C) / 'reduce' (C -> 1) when the HBM-bound thin-convolution kernels (thin_conv.cu) apply, else None."""
+    if not thin_conv_enabled or kh != 3 or kw != 3:
+        return None
+    ok = L.load().gdn_thin_conv_supported
+    if Cin == 1 and ok(O, kh, kw) and x.is_contiguous() and pitch_of(y) % 4 == 0 and y.data_ptr() % 16 == 0 \
+            and (res is None or (pitch_of(res) % 4 == 0 and res.data_ptr() % 16 == 0)):
+        return "expand"
+    if O == 1 and stride == 1 and act == ACT_NONE and ok(Cin, kh, kw) and y.is_contiguous() and pitch_of(x) % 4 == 0 and x.data_ptr() % 16 == 0 \
+            and (res is None or res.is_contiguous()):
+        return "reduce"
+    return None
+
+
 class ConvCtx:
     """What a convolution keeps from its forward pass for the backward pass (the packed input on the tensor-core path)."""
     __slots__ = ("tc", "xp")
@@ -310,6 +327,15 @@ def conv_forward(x: Tensor, w: Tensor, y: Tensor, *, stride: int = 1, pad: int =
     O, I, kh, kw = w.shape
     B, Hi, Wi, Cin = x.shape
     _, Ho, Wo, _ = y.shape
+    thin = _thin_kind(Cin, O, kh, kw, stride, x, y, act, bias, res)
+    if thin == "expand":          # 1 -> C (Discriminator1.conv1, VGG19 conv1_1 on the channel-summed weight)
+        L.check(_lib(x).gdn_thin_conv_expand(x.data_ptr(), w.contiguous().data_ptr(), _ptr(bias), y.data_ptr(), pitch_of(y), _ptr(res), pitch_of(res) if res is not None else 0,
+                                             B, Ho, Wo, O, Hi, Wi, stride, pad, 0, act, slope, _stream()), "gdn_thin_conv_expand")
+        return ConvCtx(False, None)
+    if thin == "reduce":          # C -> 1 (the generator's final conv)
+        L.check(_lib(x).gdn_thin_conv_reduce(x.data_ptr(), pitch_of(x), w.contiguous().data_ptr(), _ptr(bias), y.data_ptr(), _ptr(res),
+                                             B, Hi, Wi, Cin, Ho, Wo, 1, pad, 0, _stream()), "gdn_thin_conv_reduce")
+        return ConvCtx(False, None)
     if tc_eligible(Cin, O, kh, kw, stride, Ho, Wo):
         xp = pack_act(x)
         conv_tc_raw(xp, pack_weight(w, False, frozen_key), y, (Hi, Wi), cin=Cin, kh=kh, kw=kw, stride=stride, pad=pad, bias=bias, act=act, slope=slope, res=res)
@@ -331,6 +357,25 @@ def conv_backward(ctx: ConvCtx, dz: Tensor, x: Tensor, w: Tensor, *, stride: int
     O, I, kh, kw = w.shape
     B, Hi, Wi, Cin = x.shape
     _, Ho, Wo, _ = dz.shape
+    thin = _thin_kind(Cin, O, kh, kw, stride, x, dz)
+    if thin is not None and (gx is None or (gx.is_contiguous() if thin == "expand" else (pitch_of(gx) % 4 == 0 and gx.data_ptr() % 16 == 0))):
+        lib = _lib(x)
+        wc = w.contiguous()
+        wide, field, C_w = (dz, x, O) if thin == "expand" else (x, dz, Cin)          # wide tensor V / single-channel field S
+        Hv, Wv = wide.shape[1], wide.shape[2]
+        Hs, Ws = field.shape[1], field.shape[2]
+        if gw is not None:
+            buf = workspace("thin_wgrad", lib.gdn_thin_conv_wgrad_ws_bytes(B, Hv, Wv, C_w), x.device)
+            L.check(lib.gdn_thin_conv_wgrad(wide.data_ptr(), pitch_of(wide), field.data_ptr(), gw.data_ptr(), 0, B, Hv, Wv, C_w, Hs, Ws, stride if thin == "expand" else 1, pad,
+                                            0 if thin == "expand" else 1, buf.data_ptr(), buf.numel(), _stream()), "gdn_thin_conv_wgrad")
+        if gx is not None:
+            if thin == "expand":      # data gradient of the 1 -> C conv: gather-reduce of dz into the single-channel input
+                L.check(lib.gdn_thin_conv_reduce(dz.data_ptr(), pitch_of(dz), wc.data_ptr(), None, gx.data_ptr(), gx.data_ptr() if gx_accumulate else None,
+                                                 B, Ho, Wo, O, Hi, Wi, stride, pad, 1, _stream()), "gdn_thin_conv_reduce")
+            else:                     # data gradient of the C -> 1 conv: scatter of the single-channel dz through the flipped taps
+                L.check(lib.gdn_thin_conv_expand(dz.data_ptr(), wc.data_ptr(), None, gx.data_ptr(), pitch_of(gx), gx.data_ptr() if gx_accumulate else None, pitch_of(gx),
+                                                 B, Hi, Wi, Cin, Ho, Wo, 1, pad, 1, ACT_NONE, 0.0, _stream()), "gdn_thin_conv_expand")
+        return
     # the backward GEMMs pick the tensor-core path on their own shapes: a 1-channel input (D conv1, VGG conv1_1) keeps its
     # forward on the CUDA cores but its gradients have 64-channel operands
     tc_w = gw is not None and tc_eligible(max(O, 16), O, kh, kw, stride, Ho, Wo)     # any Cout/Cin: narrow operands are zero-filled by TMA

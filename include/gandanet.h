@@ -179,6 +179,25 @@ int gdn_linear_tc_dgrad(const float* dz, const float* w, float* dx, int Mb, int 
 size_t gdn_linear_tc_wgrad_ws_bytes(int Mb, int N, int K);
 int gdn_linear_tc_wgrad(const float* dz, const float* x, float* dw, int Mb, int N, int K, float* ws, size_t ws_bytes, gdn_stream_t s);
 
+/* ------------------------------------------------------------ thin convolutions */
+/*
+ * 3x3 convolutions with ONE channel on one side and C on the other (C a power of two, 4..128): Discriminator1.conv1
+ * (discriminator.py:62), the generator's final conv (generator.py:228), VGG19 conv1_1 on the channel-summed weight
+ * (losses.py:58,64-65) and their gradients.  HBM-bound: coalesced fp32 CUDA-core kernels that read the wide tensor once.
+ * Geometry: wide tensor V [B,Hv,Wv,C] (pitch), single-channel field S [B,Hs,Ws] dense; s = v*stride + k - pad.  w: [C][9].
+ */
+int gdn_thin_conv_supported(int C, int kh, int kw);
+/* V = act(sum_k S[v*stride + k - pad] w[c][k] + bias[c]) + res   (flip != 0: S at v + pad - k: data gradient of the C->1 conv) */
+int gdn_thin_conv_expand(const float* s_in, const float* w, const float* bias, float* v_out, int v_pitch, const float* res, int res_pitch,
+                         int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int flip, int act, float slope, gdn_stream_t st);
+/* S = sum_k sum_c V w[c][k] + bias[0] + res   (transposed == 0: C->1 forward, v = s + k - pad; 1: data gradient of the 1->C conv) */
+int gdn_thin_conv_reduce(const float* v_in, int v_pitch, const float* w, const float* bias, float* s_out, const float* res,
+                         int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int transposed, gdn_stream_t st);
+/* dw[c][k] (+)= sum_v V[v][c] S[v*stride + k - pad]   (flip: S at v + pad - k).  Deterministic two-stage reduction. */
+size_t gdn_thin_conv_wgrad_ws_bytes(int B, int Hv, int Wv, int C);
+int gdn_thin_conv_wgrad(const float* v, int v_pitch, const float* s_in, float* dw, int accumulate, int B, int Hv, int Wv, int C, int Hs, int Ws,
+                        int stride, int pad, int flip, float* ws, size_t ws_bytes, gdn_stream_t st);
+
 /* ------------------------------------------------------------ elementwise */
 /* per-channel sums over M rows of an NHWC slice: out[0..C) = sum x, out[C..2C) = sum x*x (double).  BN statistics
  * (generator.py:32,61,149,189,219,223) and bias gradients.  ws: gdn_colstats_ws_bytes(M, C). */
