@@ -1,14 +1,16 @@
-// "Thin" 3x3 convolutions: one side has a single channel, the other C channels (C % 4 == 0, C <= 128).  They are HBM-bound
+// "Thin" 3x3 convolutions: one side has a single channel, the other C channels (C = 32, 64 or 128).  They are HBM-bound
 // (D conv1 1->64, VGG19 conv1_1 on the channel-summed weight, the generator's final 64->1 conv, and their
-// gradients), so they run as coalesced CUDA-core kernels that read the wide tensor exactly once instead of as padded tensor-core tiles.
-// Call sites in the reference: models/discriminator.py:62 (conv1), models/generator.py:228 (final), models/losses.py:58,64-65 (conv1_1
-// on x.repeat(1,3,1,1)).  All three kernels share one geometry: a "wide" NHWC tensor V [B,Hv,Wv,C] and a single-channel field S
-// [B,Hs,Ws], related by  s-coordinate = v-coordinate * stride + (k - pad)  for tap k (forward conv with S as input and V as output,
-// or its transpose).
+// gradients), so they run as coalesced CUDA-core kernels that read or write the wide tensor exactly once instead of as padded
+// tensor-core tiles.  Call sites in the reference: models/discriminator.py:62 (conv1), models/generator.py:228 (final),
+// models/losses.py:58,64-65 (conv1_1 on x.repeat(1,3,1,1)).  All kernels share one geometry: a "wide" NHWC tensor V [B,Hv,Wv,C]
+// and a single-channel field S [B,Hs,Ws], related by  s-coordinate = v-coordinate * stride + (k - pad)  for tap k.
 //   expand : V[p][c]  = act(sum_k S[p*stride + k - pad] * w[c][k] + bias[c]) (+ res)         1 -> C forward; data gradient of C -> 1
 //   reduce : S[q]     = sum_k sum_c V[p(q,k)][c] * w[c][k] (+ bias) (+ res)                  C -> 1 forward; data gradient of 1 -> C
 //   wgrad  : dw[c][k] = sum_p V[p][c] * S[p*stride + k - pad]                                weight gradient of both
-// Threads: C/4 lanes per pixel, one float4 of channels each (a warp covers 128/C... pixels x 128..512 contiguous bytes).
+// Design rules: a thread's channel group is fixed, so its filter taps live in registers; each thread handles 4 x-adjacent pixels per
+// iteration (four independent 16-byte transactions in flight, S window shared); all index arithmetic is 32-bit.
+// A flipped tap order (the "transposed" uses) is folded into the register copy of the weights:  tap k at offset pad - k  ==  tap
+// 8 - k at offset k - (2 - pad).
 #include "common.cuh"
 
 namespace gdn {
@@ -16,122 +18,245 @@ namespace thin {
 
 struct Geo { int B, Hv, Wv, C, Hs, Ws, stride, pad; };
 
-// V = act(conv(S, w) + bias) + res.  w: [C][9] (row-major taps kh*3+kw).  flip: use tap (2-kh, 2-kw) offsets (data gradient of C -> 1)
+// ---------------------------------------------------------------------------------------------------------------- expand
+// STRIDE == 0: run-time stride, one pixel per iteration.  C/4 lanes per pixel, one float4 of channels each.
+template <int STRIDE, int PX>
 __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ S, const float* __restrict__ w, const float* __restrict__ bias, float* V, int v_pitch,
                                                      const float* res, int res_pitch,   /* res may alias V */ Geo g, int flip, int act, float slope) {
+  constexpr int NC = STRIDE ? (PX - 1) * STRIDE + 3 : 3;
   const int lanes = g.C >> 2;
-  const long long total = (long long)g.B * g.Hv * g.Wv * lanes;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % lanes) << 2; long long p = idx / lanes;
-    const int x = (int)(p % g.Wv); long long r = p / g.Wv; const int y = (int)(r % g.Hv); const int b = (int)(r / g.Hv);
-    float4 acc = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int c = (threadIdx.x % lanes) << 2;
+  const int stride = STRIDE ? STRIDE : g.stride;
+  const int pad = flip ? 2 - g.pad : g.pad;
+  float wr[4][9];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[i][k] = __ldg(w + (c + i) * 9 + (flip ? 8 - k : k));
+  const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int gx = g.Wv / PX;
+  const int total = g.B * g.Hv * gx;
+  const int gpp = 256 / lanes;                                  // pixel groups per block pass
+  for (int gi = blockIdx.x * gpp + threadIdx.x / lanes; gi < total; gi += gridDim.x * gpp) {
+    const int xg = gi % gx, r = gi / gx, y = r % g.Hv, b = r / g.Hv;
+    const int x0 = xg * PX;
     const float* sb = S + (size_t)b * g.Hs * g.Ws;
+    const int sx0 = x0 * stride - pad;
+    float sw[3][NC];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      const int sy = y * g.stride + (flip ? g.pad - kh : kh - g.pad);
-      if (sy < 0 || sy >= g.Hs) continue;
+      const int sy = y * stride + kh - pad;
+      const bool rowok = sy >= 0 && sy < g.Hs;
+      const float* sr = sb + (size_t)(rowok ? sy : 0) * g.Ws;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int sx = x * g.stride + (flip ? g.pad - kw : kw - g.pad);
-        if (sx < 0 || sx >= g.Ws) continue;
-        const float s = __ldg(sb + (size_t)sy * g.Ws + sx);
-        const int k = kh * 3 + kw;
-        acc.x = fmaf(s, __ldg(w + (c + 0) * 9 + k), acc.x); acc.y = fmaf(s, __ldg(w + (c + 1) * 9 + k), acc.y);
-        acc.z = fmaf(s, __ldg(w + (c + 2) * 9 + k), acc.z); acc.w = fmaf(s, __ldg(w + (c + 3) * 9 + k), acc.w);
+      for (int j = 0; j < NC; ++j) {
+        const int sx = sx0 + j;
+        sw[kh][j] = (rowok && sx >= 0 && sx < g.Ws) ? __ldg(sr + sx) : 0.f;
       }
     }
-    acc.x = apply_act(acc.x, act, slope); acc.y = apply_act(acc.y, act, slope); acc.z = apply_act(acc.z, act, slope); acc.w = apply_act(acc.w, act, slope);
-    if (res) { const float4 rr = *reinterpret_cast<const float4*>(res + (size_t)p * res_pitch + c); acc.x += rr.x; acc.y += rr.y; acc.z += rr.z; acc.w += rr.w; }
-    *reinterpret_cast<float4*>(V + (size_t)p * v_pitch + c) = acc;
+    const size_t p = ((size_t)b * g.Hv + y) * g.Wv + x0;
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+      float4 acc = bv;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float s = sw[kh][(STRIDE ? i * STRIDE : 0) + kw];
+          const int k = kh * 3 + kw;
+          acc.x = fmaf(s, wr[0][k], acc.x); acc.y = fmaf(s, wr[1][k], acc.y); acc.z = fmaf(s, wr[2][k], acc.z); acc.w = fmaf(s, wr[3][k], acc.w);
+        }
+      acc.x = apply_act(acc.x, act, slope); acc.y = apply_act(acc.y, act, slope); acc.z = apply_act(acc.z, act, slope); acc.w = apply_act(acc.w, act, slope);
+      if (res) { const float4 rr = *reinterpret_cast<const float4*>(res + (p + i) * res_pitch + c); acc.x += rr.x; acc.y += rr.y; acc.z += rr.z; acc.w += rr.w; }
+      *reinterpret_cast<float4*>(V + (p + i) * v_pitch + c) = acc;
+    }
   }
 }
 
-// S[q] = sum over taps and channels of V * w (+ bias) (+ res).  transposed == 0: C -> 1 forward conv (V is the input, stride 1 only):
-// v = q + k - pad.  transposed == 1: data gradient of the 1 -> C conv: v = (q + pad - k) / stride when divisible.
-__global__ void __launch_bounds__(256) reduce_kernel(const float* __restrict__ V, int v_pitch, const float* __restrict__ w, const float* __restrict__ bias, float* S,
-                                                     const float* res, Geo g, int transposed) {   /* res may alias S */
-  const int lanes = g.C >> 2;                    // power of two <= 32 (checked on the host)
-  const long long total = (long long)g.B * g.Hs * g.Ws * lanes;
-  const long long stride_all = (long long)gridDim.x * blockDim.x;     // a multiple of 32, so lane groups stay intact
-  // whole warps iterate together (the lane-group reduction below uses full-warp shuffles)
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx - (threadIdx.x & 31) < total; idx += stride_all) {
-    const bool live = idx < total;
-    const long long ii = live ? idx : total - 1;
-    const int c = (int)(ii % lanes) << 2; long long q = ii / lanes;
-    const int x = (int)(q % g.Ws); long long r = q / g.Ws; const int y = (int)(r % g.Hs); const int b = (int)(r / g.Hs);
+// ---------------------------------------------------------------------------------------------------------------- reduce
+// One block = one 16 x 32 tile of S.  Phase 1: every V pixel that feeds the tile is read ONCE (8 lanes per pixel, C/8 channels per
+// lane as 128-byte coalesced float4 groups); its nine per-tap channel dot products  t[k] = sum_c V[p][c] w[c][k]  are reduced over
+// the 8 lanes with a 10-shuffle reduce-scatter and parked in shared memory (zero for pixels outside the image).  Phase 2: each
+// output pixel gathers its nine taps.  transposed == 0: C -> 1 forward conv, stride 1: v = q + k - pad.  transposed == 1: data
+// gradient of the 1 -> C conv: v = (q + pad - k) / stride when divisible.  Fixed summation order: deterministic.
+constexpr int RT_H = 16, RT_W = 32, R_MAXPIX = (RT_H + 2) * (RT_W + 2);
+
+template <int CPL>   // channels per lane: C = 8 * CPL
+__global__ void __launch_bounds__(256, CPL <= 8 ? 2 : 1) reduce_kernel(const float* __restrict__ V, int v_pitch, const float* __restrict__ w, const float* __restrict__ bias,
+                                                                       float* S, const float* res /* may alias S */, Geo g, int transposed, int tiles_x, int tiles_y) {
+  __shared__ float Ts[9][R_MAXPIX + 4];
+  constexpr int NJ = CPL / 4;
+  const int lane8 = threadIdx.x & 7, slot = threadIdx.x >> 3;   // 32 pixel slots per pass
+  float wr[NJ][4][9];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) wr[j][e][k] = __ldg(w + (j * 32 + lane8 * 4 + e) * 9 + k);
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y, b = t / tiles_y;
+  const int qy0 = ty * RT_H, qx0 = tx * RT_W;
+  int vy_lo, vx_lo, vy_n, vx_n;
+  if (!transposed) { vy_lo = qy0 - g.pad; vx_lo = qx0 - g.pad; vy_n = RT_H + 2; vx_n = RT_W + 2; }
+  else {
+    const int ey = qy0 + g.pad - 2, ex = qx0 + g.pad - 2;
+    vy_lo = ((ey > 0 ? ey : 0) + g.stride - 1) / g.stride; vx_lo = ((ex > 0 ? ex : 0) + g.stride - 1) / g.stride;
+    vy_n = (qy0 + RT_H - 1 + g.pad) / g.stride - vy_lo + 1; vx_n = (qx0 + RT_W - 1 + g.pad) / g.stride - vx_lo + 1;
+  }
+  const int n = vy_n * vx_n;
+  const int passes = (n + 31) >> 5;
+  const float* vb = V + (size_t)b * g.Hv * g.Wv * v_pitch + lane8 * 4;
+  auto load = [&](int i, float4* dst) {
+    const int ry = i / vx_n, rx = i - ry * vx_n;
+    const int vy = vy_lo + ry, vx = vx_lo + rx;
+    const bool ok = i < n && vy >= 0 && vy < g.Hv && vx >= 0 && vx < g.Wv;
+    const float* src = vb + (size_t)(ok ? vy * g.Wv + vx : 0) * v_pitch;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) dst[j] = ok ? __ldg(reinterpret_cast<const float4*>(src + j * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  const bool b2 = lane8 & 4, b1 = lane8 & 2, b0 = lane8 & 1;
+  float4 cur[NJ], nxt[NJ];
+  load(slot, cur);
+  for (int ps = 0; ps < passes; ++ps) {
+    const int i = ps * 32 + slot;
+    load(i + 32, nxt);                      // next pass in flight while this one is reduced (i + 32 >= n loads nothing)
+    float tk[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) tk[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        tk[k] = fmaf(cur[j].x, wr[j][0][k], tk[k]); tk[k] = fmaf(cur[j].y, wr[j][1][k], tk[k]);
+        tk[k] = fmaf(cur[j].z, wr[j][2][k], tk[k]); tk[k] = fmaf(cur[j].w, wr[j][3][k], tk[k]);
+      }
+    // reduce-scatter over the 8 lanes of the pixel: lane l ends up with the full sum of tap l; tap 8 is reduced everywhere
+    float u[4], v2[2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float send = b2 ? tk[q] : tk[q + 4], keep = b2 ? tk[q + 4] : tk[q];
+      u[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    float t8 = tk[8] + __shfl_xor_sync(0xffffffffu, tk[8], 4);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float send = b1 ? u[q] : u[q + 2], keep = b1 ? u[q + 2] : u[q];
+      v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    t8 += __shfl_xor_sync(0xffffffffu, t8, 2);
+    const float send = b0 ? v2[0] : v2[1], keep = b0 ? v2[1] : v2[0];
+    const float own = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    t8 += __shfl_xor_sync(0xffffffffu, t8, 1);
+    if (i < n) {
+      Ts[lane8][i] = own;
+      if (lane8 == 0) Ts[8][i] = t8;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) cur[j] = nxt[j];
+  }
+  __syncthreads();
+  const float bs = bias ? __ldg(bias) : 0.f;
+  for (int o = threadIdx.x; o < RT_H * RT_W; o += 256) {
+    const int oy = o / RT_W, ox = o % RT_W;
+    const int qy = qy0 + oy, qx = qx0 + ox;
+    if (qy >= g.Hs || qx >= g.Ws) continue;
     float acc = 0.f;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      int vy;
-      if (!transposed) vy = y + kh - g.pad;
-      else { const int e = y + g.pad - kh; if (e < 0 || e % g.stride) continue; vy = e / g.stride; }
-      if (vy < 0 || vy >= g.Hv) continue;
+      int ry;
+      if (!transposed) ry = oy + kh;
+      else { const int e = qy + g.pad - kh; if (e < 0 || e % g.stride) continue; ry = e / g.stride - vy_lo; }
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        int vx;
-        if (!transposed) vx = x + kw - g.pad;
-        else { const int e = x + g.pad - kw; if (e < 0 || e % g.stride) continue; vx = e / g.stride; }
-        if (vx < 0 || vx >= g.Wv) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(V + (((size_t)b * g.Hv + vy) * g.Wv + vx) * v_pitch + c));
-        const int k = kh * 3 + kw;
-        acc = fmaf(v.x, __ldg(w + (c + 0) * 9 + k), acc); acc = fmaf(v.y, __ldg(w + (c + 1) * 9 + k), acc);
-        acc = fmaf(v.z, __ldg(w + (c + 2) * 9 + k), acc); acc = fmaf(v.w, __ldg(w + (c + 3) * 9 + k), acc);
+        int rx;
+        if (!transposed) rx = ox + kw;
+        else { const int e = qx + g.pad - kw; if (e < 0 || e % g.stride) continue; rx = e / g.stride - vx_lo; }
+        acc += Ts[kh * 3 + kw][ry * vx_n + rx];
       }
     }
-    for (int o = lanes >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);      // fixed tree: deterministic
-    if (live && (idx % lanes) == 0) S[q] = acc + (bias ? __ldg(bias) : 0.f) + (res ? res[q] : 0.f);
+    const size_t q = ((size_t)b * g.Hs + qy) * g.Ws + qx;
+    S[q] = acc + bs + (res ? res[q] : 0.f);
   }
 }
 
-// partial[block][c][k] = sum over the block's pixels p of V[p][c] * S[p*stride + k - pad]
-// flip: S is read at p + pad - k (weight gradient of the C -> 1 convolution, stride 1)
-__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ V, int v_pitch, const float* __restrict__ S, float* __restrict__ partial, Geo g, long long px_per_block, int flip) {
-  extern __shared__ float sh[];                  // [256 threads][36] then reduced
+// ---------------------------------------------------------------------------------------------------------------- wgrad
+// partial[block][c][k] = sum over the block's pixel groups of V[p][c] * S[p*stride + k - pad]   (flip: S at p + pad - k)
+template <int STRIDE, int PX>
+__global__ void __launch_bounds__(256, 2) wgrad_kernel(const float* __restrict__ V, int v_pitch, const float* __restrict__ S, float* __restrict__ partial, Geo g,
+                                                       int groups_per_block, int flip) {
+  extern __shared__ float sh[];                  // [256 threads][37]
+  constexpr int NC = STRIDE ? (PX - 1) * STRIDE + 3 : 3;
   const int lanes = g.C >> 2;
-  const int ppb = 256 / lanes;                   // pixels handled per pass by the block
+  const int gpp = 256 / lanes;
   const int lane_c = threadIdx.x % lanes, prow = threadIdx.x / lanes;
   const int c = lane_c << 2;
-  const long long P = (long long)g.B * g.Hv * g.Wv;
-  const long long p0 = blockIdx.x * px_per_block, p1 = (p0 + px_per_block < P) ? p0 + px_per_block : P;
+  const int stride = STRIDE ? STRIDE : g.stride;
+  const int pad = flip ? 2 - g.pad : g.pad;
+  const int gx = g.Wv / PX;
+  const int total = g.B * g.Hv * gx;
+  const int g0 = blockIdx.x * groups_per_block, g1 = (g0 + groups_per_block < total) ? g0 + groups_per_block : total;
   float acc[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) acc[i] = 0.f;
-  if (prow < ppb) {
-    for (long long p = p0 + prow; p < p1; p += ppb) {
-      const int x = (int)(p % g.Wv); long long r = p / g.Wv; const int y = (int)(r % g.Hv); const int b = (int)(r / g.Hv);
-      const float4 v = __ldg(reinterpret_cast<const float4*>(V + (size_t)p * v_pitch + c));
-      const float* sb = S + (size_t)b * g.Hs * g.Ws;
+  for (int gi = g0 + prow; gi < g1; gi += gpp) {
+    const int xg = gi % gx, r = gi / gx, y = r % g.Hv, b = r / g.Hv;
+    const int x0 = xg * PX;
+    const size_t p = ((size_t)b * g.Hv + y) * g.Wv + x0;
+    float4 v[PX];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int sy = y * g.stride + (flip ? g.pad - kh : kh - g.pad);
+    for (int i = 0; i < PX; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(V + (p + i) * v_pitch + c));
+    const float* sb = S + (size_t)b * g.Hs * g.Ws;
+    const int sx0 = x0 * stride - pad;
+    float sw[3][NC];
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int sx = x * g.stride + (flip ? g.pad - kw : kw - g.pad);
-          const float s = (sy >= 0 && sy < g.Hs && sx >= 0 && sx < g.Ws) ? __ldg(sb + (size_t)sy * g.Ws + sx) : 0.f;
-          const int k = kh * 3 + kw;
-          acc[k] = fmaf(v.x, s, acc[k]); acc[9 + k] = fmaf(v.y, s, acc[9 + k]); acc[18 + k] = fmaf(v.z, s, acc[18 + k]); acc[27 + k] = fmaf(v.w, s, acc[27 + k]);
-        }
+    for (int kh = 0; kh < 3; ++kh) {
+      const int sy = y * stride + kh - pad;
+      const bool rowok = sy >= 0 && sy < g.Hs;
+      const float* sr = sb + (size_t)(rowok ? sy : 0) * g.Ws;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int sx = sx0 + j;
+        sw[kh][j] = (rowok && sx >= 0 && sx < g.Ws) ? __ldg(sr + sx) : 0.f;
       }
     }
+#pragma unroll
+    for (int i = 0; i < PX; ++i)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float s = sw[kh][(STRIDE ? i * STRIDE : 0) + kw];
+          const int k = kh * 3 + kw;
+          acc[k] = fmaf(v[i].x, s, acc[k]); acc[9 + k] = fmaf(v[i].y, s, acc[9 + k]); acc[18 + k] = fmaf(v[i].z, s, acc[18 + k]); acc[27 + k] = fmaf(v[i].w, s, acc[27 + k]);
+        }
   }
 #pragma unroll
   for (int i = 0; i < 36; ++i) sh[threadIdx.x * 37 + i] = acc[i];
   __syncthreads();
-  // thread t < lanes*36 sums the ppb pixel rows of (lane_c = t / 36, i = t % 36)
+  // thread t < lanes*36 sums the gpp pixel rows of (lane_c = t / 36, i = t % 36)
   for (int t = threadIdx.x; t < lanes * 36; t += 256) {
     const int lc = t / 36, i = t % 36;
     float s = 0.f;
-    for (int rws = 0; rws < ppb; ++rws) s += sh[(rws * lanes + lc) * 37 + i];
-    partial[(size_t)blockIdx.x * g.C * 9 + ((lc << 2) + i / 9) * 9 + (i % 9)] = s;
+    for (int rws = 0; rws < gpp; ++rws) s += sh[(rws * lanes + lc) * 37 + i];
+    const int k = i % 9;
+    partial[(size_t)blockIdx.x * g.C * 9 + ((lc << 2) + i / 9) * 9 + (flip ? 8 - k : k)] = s;
   }
 }
-// out[c][k] (+)= scale * sum_b partial[b][c][k]  (double accumulation, fixed order)
-__global__ void wgrad_final_kernel(const float* __restrict__ partial, int blocks, int n, float* __restrict__ out, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// out[i] (+)= sum_b partial[b][i]: one block per output element, double accumulation in a fixed order
+__global__ void __launch_bounds__(128) wgrad_final_kernel(const float* __restrict__ partial, int blocks, int n, float* __restrict__ out, int accumulate) {
+  __shared__ double red[128];
+  const int i = blockIdx.x;
   double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += (double)partial[(size_t)b * n + i];
-  out[i] = accumulate ? out[i] + (float)s : (float)s;
+  for (int b = threadIdx.x; b < blocks; b += 128) s += (double)partial[(size_t)b * n + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[i] = accumulate ? out[i] + (float)red[0] : (float)red[0];
 }
 }  // namespace thin
 }  // namespace gdn
@@ -139,8 +264,7 @@ __global__ void wgrad_final_kernel(const float* __restrict__ partial, int blocks
 using namespace gdn;
 using namespace gdn::thin;
 
-static bool thin_ok(int C) { return C >= 4 && C <= 128 && (C & (C - 1)) == 0; }    // C/4 lanes per pixel: a power of two <= 32
-static int thin_grid(long long total) { long long b = cdiv(total, 256); return (int)(b < 16 * kNumSMs ? (b > 0 ? b : 1) : 16 * kNumSMs); }
+static bool thin_ok(int C) { return C == 32 || C == 64 || C == 128; }
 
 extern "C" int gdn_thin_conv_supported(int C, int kh, int kw) { return thin_ok(C) && kh == 3 && kw == 3; }
 
@@ -148,34 +272,64 @@ extern "C" int gdn_thin_conv_expand(const float* s_in, const float* w, const flo
                                     int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int flip, int act, float slope, gdn_stream_t st) {
   GDN_CHECK_ARG(s_in && w && v_out && thin_ok(C) && v_pitch >= C && v_pitch % 4 == 0 && ((uintptr_t)v_out & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0));
   GDN_CHECK_ARG(!res || (res_pitch % 4 == 0 && ((uintptr_t)res & 15) == 0));
+  GDN_CHECK_ARG((long long)B * Hv * Wv < (1ll << 31) && stride >= 1);
   Geo g = {B, Hv, Wv, C, Hs, Ws, stride, pad};
-  expand_kernel<<<thin_grid((long long)B * Hv * Wv * (C / 4)), 256, 0, as_stream(st)>>>(s_in, w, bias, v_out, v_pitch, res, res_pitch, g, flip, act, slope);
+  const int gpp = 256 / (C / 4);
+  const bool px4 = Wv % 4 == 0 && (stride == 1 || stride == 2);
+  const long long groups = (long long)B * Hv * (px4 ? Wv / 4 : Wv);
+  long long blocks = cdiv(groups, gpp);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  cudaStream_t s = as_stream(st);
+  if (px4 && stride == 1) expand_kernel<1, 4><<<(unsigned)blocks, 256, 0, s>>>(s_in, w, bias, v_out, v_pitch, res, res_pitch, g, flip, act, slope);
+  else if (px4) expand_kernel<2, 4><<<(unsigned)blocks, 256, 0, s>>>(s_in, w, bias, v_out, v_pitch, res, res_pitch, g, flip, act, slope);
+  else expand_kernel<0, 1><<<(unsigned)blocks, 256, 0, s>>>(s_in, w, bias, v_out, v_pitch, res, res_pitch, g, flip, act, slope);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
 
 extern "C" int gdn_thin_conv_reduce(const float* v_in, int v_pitch, const float* w, const float* bias, float* s_out, const float* res,
                                     int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int transposed, gdn_stream_t st) {
-  GDN_CHECK_ARG(v_in && w && s_out && thin_ok(C) && v_pitch >= C && v_pitch % 4 == 0 && ((uintptr_t)v_in & 15) == 0 && (transposed || stride == 1));
+  GDN_CHECK_ARG(v_in && w && s_out && thin_ok(C) && v_pitch >= C && v_pitch % 4 == 0 && ((uintptr_t)v_in & 15) == 0 && (transposed || stride == 1) && stride >= 1);
+  GDN_CHECK_ARG((long long)B * Hv * Wv < (1ll << 31) && pad >= 0 && pad <= 2);
   Geo g = {B, Hv, Wv, C, Hs, Ws, stride, pad};
-  reduce_kernel<<<thin_grid((long long)B * Hs * Ws * (C / 4)), 256, 0, as_stream(st)>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed);
+  const int tiles_x = (int)cdiv(Ws, RT_W), tiles_y = (int)cdiv(Hs, RT_H);
+  const long long blocks = (long long)B * tiles_x * tiles_y;
+  GDN_CHECK_ARG(blocks < (1ll << 31));
+  cudaStream_t s = as_stream(st);
+  if (C == 32) reduce_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y);
+  else if (C == 64) reduce_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y);
+  else reduce_kernel<16><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
 
-static int thin_wgrad_blocks(long long P) { long long b = cdiv(P, 2048); return (int)(b < 8 * kNumSMs ? (b > 0 ? b : 1) : 8 * kNumSMs); }
-extern "C" size_t gdn_thin_conv_wgrad_ws_bytes(int B, int Hv, int Wv, int C) { return (size_t)thin_wgrad_blocks((long long)B * Hv * Wv) * C * 9 * sizeof(float); }
+static int thin_wgrad_blocks(int B, int Hv, int Wv, int C) {
+  const long long groups = (long long)B * Hv * (Wv % 4 == 0 ? Wv / 4 : Wv);
+  long long b = cdiv(groups, (256 / (C / 4)) * 8);
+  return (int)(b < 4 * kNumSMs ? (b > 0 ? b : 1) : 4 * kNumSMs);
+}
+extern "C" size_t gdn_thin_conv_wgrad_ws_bytes(int B, int Hv, int Wv, int C) {
+  return thin_ok(C) ? (size_t)thin_wgrad_blocks(B, Hv, Wv, C) * C * 9 * sizeof(float) : 0;
+}
 
 extern "C" int gdn_thin_conv_wgrad(const float* v, int v_pitch, const float* s_in, float* dw, int accumulate, int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad,
                                    int flip, float* ws, size_t ws_bytes, gdn_stream_t st) {
-  GDN_CHECK_ARG(v && s_in && dw && ws && thin_ok(C) && v_pitch >= C && v_pitch % 4 == 0 && ((uintptr_t)v & 15) == 0 && (!flip || stride == 1));
+  GDN_CHECK_ARG(v && s_in && dw && ws && thin_ok(C) && v_pitch >= C && v_pitch % 4 == 0 && ((uintptr_t)v & 15) == 0 && (!flip || stride == 1) && stride >= 1);
+  GDN_CHECK_ARG((long long)B * Hv * Wv < (1ll << 31));
   if (ws_bytes < gdn_thin_conv_wgrad_ws_bytes(B, Hv, Wv, C)) { set_error("gdn_thin_conv_wgrad: workspace too small"); return GDN_EWORKSPACE; }
-  const long long P = (long long)B * Hv * Wv;
-  const int blocks = thin_wgrad_blocks(P);
+  const bool px4 = Wv % 4 == 0 && (stride == 1 || stride == 2);
+  const long long groups_run = (long long)B * Hv * (px4 ? Wv / 4 : Wv);
+  const int blocks = thin_wgrad_blocks(B, Hv, Wv, C);
+  const int gpb = (int)cdiv(groups_run, blocks);
   Geo g = {B, Hv, Wv, C, Hs, Ws, stride, pad};
-  wgrad_kernel<<<blocks, 256, 256 * 37 * sizeof(float), as_stream(st)>>>(v, v_pitch, s_in, ws, g, cdiv(P, blocks), flip);
+  cudaStream_t s = as_stream(st);
+  const size_t smem = 256 * 37 * sizeof(float);
+  if (px4 && stride == 1) wgrad_kernel<1, 4><<<blocks, 256, smem, s>>>(v, v_pitch, s_in, ws, g, gpb, flip);
+  else if (px4) wgrad_kernel<2, 4><<<blocks, 256, smem, s>>>(v, v_pitch, s_in, ws, g, gpb, flip);
+  else wgrad_kernel<0, 1><<<blocks, 256, smem, s>>>(v, v_pitch, s_in, ws, g, gpb, flip);
   GDN_CHECK_LAUNCH();
-  wgrad_final_kernel<<<(unsigned)cdiv(C * 9, 128), 128, 0, as_stream(st)>>>(ws, blocks, C * 9, dw, accumulate);
+  wgrad_final_kernel<<<C * 9, 128, 0, s>>>(ws, blocks, C * 9, dw, accumulate);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

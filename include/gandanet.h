@@ -181,7 +181,7 @@ int gdn_linear_tc_wgrad(const float* dz, const float* x, float* dw, int Mb, int 
 
 /* ------------------------------------------------------------ thin convolutions */
 /*
- * 3x3 convolutions with ONE channel on one side and C on the other (C a power of two, 4..128): Discriminator1.conv1
+ * 3x3 convolutions with ONE channel on one side and C on the other (C = 32, 64 or 128): Discriminator1.conv1
  * (discriminator.py:62), the generator's final conv (generator.py:228), VGG19 conv1_1 on the channel-summed weight
  * (losses.py:58,64-65) and their gradients.  HBM-bound: coalesced fp32 CUDA-core kernels that read the wide tensor once.
  * Geometry: wide tensor V [B,Hv,Wv,C] (pitch), single-channel field S [B,Hs,Ws] dense; s = v*stride + k - pad.  w: [C][9].
