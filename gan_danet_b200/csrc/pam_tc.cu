@@ -5,15 +5,20 @@
 // never leaves the SM.
 //
 // One CTA = one sample x one tile of 128 query positions; it walks all N/128 key tiles.
-//   warp 0      : TMA producer for Q and the K ring (4 stages)
-//   warp 3      : TMA producer for the V^T ring (3 stages)
-//   warp 1      : tcgen05.mma issuer (one lane):  S[b] = Q K_j^T   and   O += P_j V_j
+//   warp 0      : TMA producer for Q and the K ring (3 stages)
+//   warp 3      : TMA producer for the V ring (5 stages of 64 keys x 192 channels, row-major: V is the MN-major B operand)
+//   warp 1      : tcgen05.mma issuer (one lane):  S[j&1] = Q K_j^T   and   O += P_j V_j
 //   warp 2      : TMEM allocator
-//   warps 4-7   : softmax group 0 -- thread = query row, key columns  0..63  of every score tile, O columns 0..95
-//   warps 8-11  : softmax group 1 -- thread = query row, key columns 64..127 of every score tile, O columns 96..191
-// TMEM columns: S0 [0,128) S1 [128,256) (ping-pong so Q.K_{j+1}^T overlaps softmax(j)), O [256,448).
-// The running row maximum is raised lazily (only when a tile exceeds it by > 8 in log2 units, so P <= 256 in fp16)
-// and O is then rescaled in TMEM by the softmax threads themselves; in steady state no rescale happens.
+//   warps 4-7   : softmax group 0 -- EVEN key tiles; thread = query row = TMEM lane, all 128 key columns of the tile
+//   warps 8-11  : softmax group 1 -- ODD key tiles
+// The two groups ping-pong: while one is in its MUFU-bound exp phase the other does its latency-bound phase (wait for S, row
+// maximum, P store, fences), so the exp units and the tensor pipe stay busy.  A row's maximum is thread-local (no cross-group
+// exchange); what the groups share is the per-row REFERENCE maximum in shared memory, handed over warp-to-warp (mbarrier) in
+// tile order.  The reference starts 2^8 above the first tile's maximum and is raised lazily (only when a tile exceeds it by 2^15,
+// so P < 65504 in fp16; dominant terms stay fp16-normal); the raising thread rescales its row of O in TMEM after the previous
+// P.V has landed.  In steady state no rescale happens.
+// TMEM columns: S0 [0,128) S1 [128,256) O [256,448).  P is double-buffered in shared memory (one buffer per group).
+// Epilogue: O/l is staged through shared memory (the drained V ring) so that x is read and o, y are written as whole rows.
 // Operands: fp16 (bf16 logits are 8x worse), d zero-padded to 32, C zero-padded to 192.
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
@@ -23,37 +28,46 @@ namespace pamtc {
 using namespace gdn::tc;
 
 constexpr int TQ = 128, TK = 128, DPAD = 32, CPAD = 192;
-constexpr int KS = 4, VS = 3;
+constexpr int KS = 3, VH = 5;
 constexpr int Q_BYTES = TQ * DPAD * 2;          // 8 KB, 64-byte rows, SWIZZLE_64B
 constexpr int K_BYTES = TK * DPAD * 2;          // 8 KB
-constexpr int V_BLK = CPAD * 128;               // 24 KB: [192 channels][64 keys] fp16, 128-byte rows, SWIZZLE_128B
-constexpr int V_BYTES = 2 * V_BLK;              // keys 0..63 | 64..127
+constexpr int VH_CHUNK = 64 * 128;              // 8 KB: [64 keys][64 channels] fp16, 128-byte rows, SWIZZLE_128B
+constexpr int VH_BYTES = (CPAD / 64) * VH_CHUNK; // 24 KB per half tile (64 keys)
 constexpr int P_BLK = TQ * 128;                 // 16 KB: [128 rows][64 keys] fp16
 constexpr int P_BYTES = 2 * P_BLK;
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + Q_BYTES;
-constexpr int OFF_V = OFF_K + KS * K_BYTES;     // 40960 (1024-aligned)
-constexpr int OFF_P = OFF_V + VS * V_BYTES;     // 188416
-constexpr int OFF_BAR = OFF_P + P_BYTES;        // 221184
-constexpr int OFF_HM = OFF_BAR + 256;           // float [2][2][128]
-constexpr int OFF_LS = OFF_HM + 2 * 2 * 128 * 4; // float [2][128]
+constexpr int OFF_V = OFF_K + KS * K_BYTES;     // 32768 (1024-aligned)
+constexpr int OFF_P = OFF_V + VH * VH_BYTES;    // 155648
+constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;    // 221184
+constexpr int OFF_MREF = OFF_BAR + 512;         // float [128]: shared reference maximum per row (log2 units)
+constexpr int OFF_LS = OFF_MREF + 128 * 4;      // float [2][128]
 constexpr int OFF_TMEM = OFF_LS + 2 * 128 * 4;  // uint32 tmem base
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024; // + alignment slack
+constexpr int STG_STRIDE = CPAD + 4;            // floats per staged output row (conflict-free float4 column writes)
+static_assert(TQ * STG_STRIDE * 4 <= VH * VH_BYTES, "epilogue staging fits in the V ring");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int NTHREADS = 384;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
-constexpr float RESCALE_TAU = 8.f;
+constexpr float RESCALE_TAU = 15.f;    // raise the reference when a tile maximum exceeds it by 2^15 (P stays below the fp16 maximum)
+constexpr float REF_MARGIN = 8.f;      // ... and then put it 2^8 ABOVE that maximum, so that a slowly growing row maximum rarely triggers again
 
 // barrier slots (8 bytes each) inside OFF_BAR
-enum { BAR_Q = 0, BAR_KFULL = 1, BAR_KEMPTY = BAR_KFULL + KS, BAR_VFULL = BAR_KEMPTY + KS, BAR_VEMPTY = BAR_VFULL + VS,
-       BAR_SFULL = BAR_VEMPTY + VS, BAR_PFULL = BAR_SFULL + 2, BAR_PVDONE = BAR_PFULL + 1, BAR_COUNT = BAR_PVDONE + 1 };
-static_assert(BAR_COUNT * 8 <= 256, "barrier area");
+enum { BAR_Q = 0, BAR_KFULL = 1, BAR_KEMPTY = BAR_KFULL + KS, BAR_VFULL = BAR_KEMPTY + KS, BAR_VEMPTY = BAR_VFULL + VH,
+       BAR_SFULL = BAR_VEMPTY + VH, BAR_PFULL = BAR_SFULL + 2, BAR_PVDONE = BAR_PFULL + 2, BAR_MREF = BAR_PVDONE + 2, BAR_COUNT = BAR_MREF + 8 };
+static_assert(BAR_COUNT * 8 <= 512, "barrier area");
 
 struct FwdParams {
   const float* x; int x_pitch; const float* gamma;
   float* o; float* y; int y_pitch; float* lse;
   int B, N, C, tiles_per_sample;
 };
+
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)layout_type << 61);
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV, const FwdParams p) {
@@ -69,10 +83,9 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   if (threadIdx.x == 0) {
     mbar_init(bar(BAR_Q), 1);
     for (int i = 0; i < KS; ++i) { mbar_init(bar(BAR_KFULL + i), 1); mbar_init(bar(BAR_KEMPTY + i), 1); }
-    for (int i = 0; i < VS; ++i) { mbar_init(bar(BAR_VFULL + i), 1); mbar_init(bar(BAR_VEMPTY + i), 1); }
-    mbar_init(bar(BAR_SFULL), 1); mbar_init(bar(BAR_SFULL + 1), 1);
-    mbar_init(bar(BAR_PFULL), 256);
-    mbar_init(bar(BAR_PVDONE), 1);
+    for (int i = 0; i < VH; ++i) { mbar_init(bar(BAR_VFULL + i), 1); mbar_init(bar(BAR_VEMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(BAR_SFULL + i), 1); mbar_init(bar(BAR_PFULL + i), 4); mbar_init(bar(BAR_PVDONE + i), 1); }
+    for (int i = 0; i < 8; ++i) mbar_init(bar(BAR_MREF + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -96,18 +109,19 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       }
     }
   } else if (warp == 3) {
-    if (lane == 0) {   // ---- V^T producer
-      for (int j = 0; j < T; ++j) {
-        const int st = j % VS;
-        if (j >= VS) mbar_wait(bar(BAR_VEMPTY + st), ((j / VS) - 1) & 1);
-        mbar_expect_tx(bar(BAR_VFULL + st), V_BYTES);
-        tma_load_2d(base + OFF_V + st * V_BYTES, &mapV, bar(BAR_VFULL + st), j * TK, sample * CPAD);
-        tma_load_2d(base + OFF_V + st * V_BYTES + V_BLK, &mapV, bar(BAR_VFULL + st), j * TK + 64, sample * CPAD);
+    if (lane == 0) {   // ---- V producer: half tiles of 64 keys, three 64-channel chunks each
+      for (int hh = 0; hh < 2 * T; ++hh) {
+        const int st = hh % VH;
+        if (hh >= VH) mbar_wait(bar(BAR_VEMPTY + st), ((hh / VH) - 1) & 1);
+        mbar_expect_tx(bar(BAR_VFULL + st), VH_BYTES);
+#pragma unroll
+        for (int c = 0; c < CPAD / 64; ++c)
+          tma_load_2d(base + OFF_V + st * VH_BYTES + c * VH_CHUNK, &mapV, bar(BAR_VFULL + st), c * 64, sample * p.N + hh * 64);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ---- MMA issuer
-      constexpr uint32_t IDESC_QK = idesc_f16(TQ, TK), IDESC_PV = idesc_f16(TQ, CPAD);
+      constexpr uint32_t IDESC_QK = idesc_f16(TQ, TK), IDESC_PV = idesc_f16(TQ, CPAD) | (1u << 16);   // bit 16: B is MN-major
       auto issue_qk = [&](int j) {
         const int st = j % KS;
         mbar_wait(bar(BAR_KFULL + st), (j / KS) & 1);
@@ -123,120 +137,162 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       };
       mbar_wait(bar(BAR_Q), 0);
       issue_qk(0);
+      if (T > 1) issue_qk(1);
       for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_qk(j + 1);
-        const int st = j % VS;
-        mbar_wait(bar(BAR_PFULL), j & 1);
-        mbar_wait(bar(BAR_VFULL + st), (j / VS) & 1);
+        const int w = j & 1;
+        mbar_wait(bar(BAR_PFULL + w), (j >> 1) & 1);     // P_j is in shared memory and S[w] has been read completely
         tc_fence_after();
+        if (j + 2 < T) issue_qk(j + 2);                  // first, so that group w can start on its next tile at once
 #pragma unroll
-        for (int ks = 0; ks < TK / 16; ++ks) {
-          uint64_t ad = smem_desc(base + OFF_P + (ks >> 2) * P_BLK + (ks & 3) * 32, 1024, LAYOUT_SW128);
-          uint64_t bd = smem_desc(base + OFF_V + st * V_BYTES + (ks >> 2) * V_BLK + (ks & 3) * 32, 1024, LAYOUT_SW128);
-          umma_f16(tmem + 2 * TK, ad, bd, IDESC_PV, (j > 0 || ks > 0) ? 1u : 0u);
+        for (int h = 0; h < 2; ++h) {
+          const int hh = 2 * j + h, st = hh % VH;
+          mbar_wait(bar(BAR_VFULL + st), (hh / VH) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            uint64_t ad = smem_desc(base + OFF_P + w * P_BYTES + h * P_BLK + ks * 32, 1024, LAYOUT_SW128);
+            uint64_t bd = smem_desc_mn(base + OFF_V + st * VH_BYTES + ks * 2048, VH_CHUNK, 1024, LAYOUT_SW128);   // 16 keys per step; 64-channel groups 8 KB apart
+            umma_f16(tmem + 2 * TK, ad, bd, IDESC_PV, (j > 0 || h > 0 || ks > 0) ? 1u : 0u);
+          }
+          tc_commit(bar(BAR_VEMPTY + st));
         }
-        tc_commit(bar(BAR_VEMPTY + st));
-        tc_commit(bar(BAR_PVDONE));
+        tc_commit(bar(BAR_PVDONE + w));
       }
     }
   } else if (warp >= 4) {
     // ---- softmax groups
-    const int wg = (warp - 4) >> 2;                 // 0: key columns 0..63, 1: 64..127
-    const int row = (warp & 3) * 32 + lane;         // TMEM lane == query row of the tile
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    float* hm = reinterpret_cast<float*>(sm + OFF_HM);
-    float m_ref = -INFINITY, l = 0.f;
-    for (int j = 0; j < T; ++j) {
-      const int b = j & 1;
-      mbar_wait(bar(BAR_SFULL + b), (j >> 1) & 1);
+    const int w = (warp - 4) >> 2;                  // group: tiles j = w, w + 2, ...
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;                 // TMEM lane == query row of the tile
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    float* mref = reinterpret_cast<float*>(sm + OFF_MREF);
+    const uint32_t my_mref_bar = bar(BAR_MREF + w * 4 + q4), peer_mref_bar = bar(BAR_MREF + (w ^ 1) * 4 + q4);
+    uint8_t* prow = sm + OFF_P + w * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+    float m_loc = -INFINITY, l = 0.f;
+    int nwait = 0;
+    for (int j = w; j < T; j += 2) {
+      const int i = j >> 1;
+      mbar_wait(bar(BAR_SFULL + w), i & 1);
       tc_fence_after();
-      float s[64];
-      tmem_ld32(tmem + lane_addr + b * TK + wg * 64, s);
-      tmem_ld32(tmem + lane_addr + b * TK + wg * 64 + 32, s + 32);
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+      const uint32_t s_addr = tmem + lane_addr + w * TK;
+      // pass 1: row maximum of the tile
+      float mx;
+      {
+        uint32_t a[32], b[32];
+        tmem_ld32_async(s_addr, a); tmem_ld32_async(s_addr + 32, b);
+        tmem_ld_wait64(a, b);
+        float m0 = __uint_as_float(a[0]), m1 = __uint_as_float(b[0]);
 #pragma unroll
-      for (int i = 4; i < 64; i += 4) { mx0 = fmaxf(mx0, s[i]); mx1 = fmaxf(mx1, s[i + 1]); mx2 = fmaxf(mx2, s[i + 2]); mx3 = fmaxf(mx3, s[i + 3]); }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      hm[(b * 2 + wg) * 128 + row] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float mt = fmaxf(mx, hm[(b * 2 + (wg ^ 1)) * 128 + row]) * LOG2E;
-      bool waited_pv = false;
-      if (j == 0) {
-        m_ref = mt;
-      } else {
-        const bool changed = mt > m_ref + RESCALE_TAU;
+        for (int e = 1; e < 32; ++e) { m0 = fmaxf(m0, __uint_as_float(a[e])); m1 = fmaxf(m1, __uint_as_float(b[e])); }
+        tmem_ld32_async(s_addr + 64, a); tmem_ld32_async(s_addr + 96, b);
+        tmem_ld_wait64(a, b);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) { m0 = fmaxf(m0, __uint_as_float(a[e])); m1 = fmaxf(m1, __uint_as_float(b[e])); }
+        mx = fmaxf(m0, m1);
+      }
+      const float mt = mx * LOG2E;
+      // take over the shared reference from the group that decided tile j-1
+      if (j > 0) {
+        mbar_wait(my_mref_bar, nwait & 1);
+        ++nwait;
+        const float m_sh = mref[row];
+        if (m_sh != m_loc) { l *= ex2(m_loc - m_sh); m_loc = m_sh; }
+        const bool changed = mt > m_loc + RESCALE_TAU;
         if (__any_sync(0xffffffffu, changed)) {
-          // raise the reference maximum: rescale this group's half of O (after P_{j-1} V_{j-1} has landed)
-          const float m_new = changed ? mt : m_ref;
-          const float f = ex2(m_ref - m_new);
-          mbar_wait(bar(BAR_PVDONE), (j - 1) & 1);
-          waited_pv = true;
+          // raise the reference: rescale this row of O once P_{j-1} V_{j-1} (and everything before it) has landed
+          const float m_new = changed ? mt + REF_MARGIN : m_loc;
+          const float f = ex2(m_loc - m_new);
+          mbar_wait(bar(BAR_PVDONE + (w ^ 1)), ((j - 1) >> 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < CPAD / 2; c += 32) {
+          for (int c = 0; c < CPAD; c += 32) {
             float ov[32];
-            const uint32_t ta = tmem + lane_addr + 2 * TK + wg * (CPAD / 2) + c;
+            const uint32_t ta = tmem + lane_addr + 2 * TK + c;
             tmem_ld32(ta, ov);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] *= f;
+            for (int e = 0; e < 32; ++e) ov[e] *= f;
             tmem_st32(ta, ov);
           }
           tmem_wait_st();
           l *= f;
-          m_ref = m_new;
+          m_loc = m_new;
         }
+      } else {
+        m_loc = mt + REF_MARGIN;
       }
-      // P = exp2(S*log2e - m_ref), fp16; row-sum in fp32
-      uint32_t packed[32];
+      mref[row] = m_loc;
+      if (j + 1 < T) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(peer_mref_bar);
+      }
+      // pass 2: P = exp2(S*log2e - m_ref) in fp16, row sum in fp32; 64 key columns (= one K-major SWIZZLE_128B block of P) at a time
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) {
-        float p0 = ex2(fmaf(s[i], LOG2E, -m_ref)), p1 = ex2(fmaf(s[i + 1], LOG2E, -m_ref));
-        l0 += p0; l1 += p1;
-        __half2 h = __floats2half2_rn(p0, p1);
-        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+      for (int h = 0; h < 2; ++h) {
+        uint32_t a[32], b[32];
+        tmem_ld32_async(s_addr + h * 64, a); tmem_ld32_async(s_addr + h * 64 + 32, b);
+        tmem_ld_wait64(a, b);
+        uint32_t packed[32];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(a[e]), LOG2E, -m_loc)), p1 = ex2(fmaf(__uint_as_float(a[e + 1]), LOG2E, -m_loc));
+          const float p2 = ex2(fmaf(__uint_as_float(b[e]), LOG2E, -m_loc)), p3 = ex2(fmaf(__uint_as_float(b[e + 1]), LOG2E, -m_loc));
+          l0 += p0 + p1; l1 += p2 + p3;
+          __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+          packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h01);
+          packed[16 + (e >> 1)] = *reinterpret_cast<uint32_t*>(&h23);
+        }
+        // this group's P buffer must have been consumed by P_{j-2} V_{j-2}: checked as late as possible (after the first 64 exponentials)
+        if (h == 0 && i > 0) mbar_wait(bar(BAR_PVDONE + w), (i - 1) & 1);
+        // K-major SWIZZLE_128B tile: row r at r*128 B inside 1024-B groups of 8 rows, 16-B chunk index XOR (r & 7)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+          *reinterpret_cast<uint4*>(prow + h * P_BLK + ((c ^ (row & 7)) << 4)) = val;
+        }
       }
       l += l0 + l1;
-      if (j > 0 && !waited_pv) mbar_wait(bar(BAR_PVDONE), (j - 1) & 1);   // P buffer free again
-      // K-major SWIZZLE_128B tile: row r at r*128 B inside 1024-B groups of 8 rows, 16-B chunk index XOR (r & 7)
-      uint8_t* prow = sm + OFF_P + wg * P_BLK + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = val;
-      }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(bar(BAR_PFULL));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BAR_PFULL + w));
     }
     // ---- epilogue: o = O / l, y = gamma*o + x, lse
+    asm volatile("bar.sync 1, 256;" ::: "memory");           // the last reference has been published
+    const float m_fin = (((T - 1) & 1) == w) ? m_loc : mref[row];   // decided by the group that owned the last tile
+    if (m_fin != m_loc) l *= ex2(m_loc - m_fin);             // a group without tiles has m_loc = -inf, l = 0
     float* ls = reinterpret_cast<float*>(sm + OFF_LS);
-    ls[wg * 128 + row] = l;
+    ls[w * 128 + row] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float ltot = l + ls[(wg ^ 1) * 128 + row];
+    const float ltot = ls[row] + ls[128 + row];
     const float inv = 1.f / ltot;
-    mbar_wait(bar(BAR_PVDONE), (T - 1) & 1);
+    mbar_wait(bar(BAR_PVDONE + ((T - 1) & 1)), ((T - 1) >> 1) & 1);
     tc_fence_after();
-    const float g = __ldg(p.gamma);
-    const size_t grow = (size_t)sample * p.N + (size_t)qtile * TQ + row;
-    if (wg == 0) p.lse[grow] = (m_ref + log2f(ltot)) * LN2;
+    const size_t row0 = (size_t)sample * p.N + (size_t)qtile * TQ;
+    if (w == 0) p.lse[row0 + row] = (m_fin + log2f(ltot)) * LN2;
+    float* stg = reinterpret_cast<float*>(sm + OFF_V);       // the V ring is drained: all P.V products have completed
 #pragma unroll 1
     for (int c = 0; c < CPAD / 2; c += 32) {
       float ov[32];
-      const int c0 = wg * (CPAD / 2) + c;
+      const int c0 = w * (CPAD / 2) + c;
       tmem_ld32(tmem + lane_addr + 2 * TK + c0, ov);
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const int ch = c0 + i;
-        if (ch < p.C) {   // C is a multiple of 4 on this path (checked on the host)
-          float4 on = make_float4(ov[i] * inv, ov[i + 1] * inv, ov[i + 2] * inv, ov[i + 3] * inv);
-          float4 xv = *reinterpret_cast<const float4*>(p.x + grow * p.x_pitch + ch);
-          *reinterpret_cast<float4*>(p.o + grow * p.C + ch) = on;
-          *reinterpret_cast<float4*>(p.y + grow * p.y_pitch + ch) = make_float4(fmaf(g, on.x, xv.x), fmaf(g, on.y, xv.y), fmaf(g, on.z, xv.z), fmaf(g, on.w, xv.w));
-        }
-      }
+      for (int e = 0; e < 32; e += 4)
+        *reinterpret_cast<float4*>(stg + row * STG_STRIDE + c0 + e) = make_float4(ov[e] * inv, ov[e + 1] * inv, ov[e + 2] * inv, ov[e + 3] * inv);
     }
     tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float g = __ldg(p.gamma);
+    const int c4n = p.C >> 2;                                 // C is a multiple of 4 on this path (checked on the host)
+    const int total = TQ * c4n;
+    for (int idx = threadIdx.x - 128; idx < total; idx += 256) {
+      const int r = idx / c4n, ch = (idx - r * c4n) << 2;
+      const float4 on = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + ch);
+      const size_t grow = row0 + r;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + grow * p.x_pitch + ch));
+      *reinterpret_cast<float4*>(p.o + grow * p.C + ch) = on;
+      *reinterpret_cast<float4*>(p.y + grow * p.y_pitch + ch) = make_float4(fmaf(g, on.x, xv.x), fmaf(g, on.y, xv.y), fmaf(g, on.z, xv.z), fmaf(g, on.w, xv.w));
+    }
   }
   __syncthreads();
   if (warp == 2) {
@@ -245,27 +301,28 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   }
 }
 
-// ---- operand packing: fp32 NHWC slices -> fp16 tensor-core operands
+// ---- operand packing: fp32 NHWC slices -> fp16 tensor-core operands.  One warp per row: lanes 0-3 write the four 16-byte chunks of
+// Q[row][0..32), lanes 4-7 those of K, lanes 8-31 the 24 chunks of V[row][0..192) (zero beyond d / C).
+__global__ void __launch_bounds__(256) pack_qkv_kernel(const float* __restrict__ q, const float* __restrict__ k, int qk_pitch, int d, const float* __restrict__ v, int v_pitch,
+                                                       int C, __half* __restrict__ Qh, __half* __restrict__ Kh, __half* __restrict__ Vh, long long rows) {
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float* src; __half* dst; int pitch, lim, c0, width;
+  if (lane < 4) { src = q; dst = Qh; pitch = qk_pitch; lim = d; c0 = lane * 8; width = DPAD; }
+  else if (lane < 8) { src = k; dst = Kh; pitch = qk_pitch; lim = d; c0 = (lane - 4) * 8; width = DPAD; }
+  else { src = v; dst = Vh; pitch = v_pitch; lim = C; c0 = (lane - 8) * 8; width = CPAD; }
+  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(c0 + e < lim ? __ldg(src + (size_t)r * pitch + c0 + e) : 0.f);
+    *reinterpret_cast<uint4*>(dst + (size_t)r * width + c0) = *reinterpret_cast<const uint4*>(h);
+  }
+}
 __global__ void __launch_bounds__(256) pack_qk_kernel(const float* __restrict__ src, int pitch, int d, __half* __restrict__ dst, long long rows) {
   const long long total = rows * DPAD;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long r = idx / DPAD; int c = (int)(idx % DPAD);
     dst[idx] = __float2half_rn(c < d ? src[(size_t)r * pitch + c] : 0.f);
-  }
-}
-// V [B][N][C] (pitch) -> V^T fp16 [B][CPAD][N], zero rows for c >= C
-__global__ void __launch_bounds__(256) pack_vt_kernel(const float* __restrict__ v, int pitch, int C, int N, __half* __restrict__ vt) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8) {
-    int n = n0 + i, c = c0 + tx;
-    tile[i][tx] = (n < N && c < C) ? v[((size_t)b * N + n) * pitch + c] : 0.f;
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    int c = c0 + i, n = n0 + tx;
-    if (c < CPAD && n < N) vt[((size_t)b * CPAD + c) * N + n] = __float2half_rn(tile[tx][i]);
   }
 }
 
@@ -297,7 +354,7 @@ extern "C" int gdn_pam_tc_init(void) {
 
 extern "C" size_t gdn_pam_tc_fwd_ws_bytes(const gdn_pam_fwd_args* a) {
   size_t rows = (size_t)a->B * a->N;
-  return 2 * align256(rows * DPAD * 2) + align256((size_t)a->B * CPAD * a->N * 2);
+  return 2 * align256(rows * DPAD * 2) + align256(rows * CPAD * 2);
 }
 
 extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
@@ -310,21 +367,16 @@ extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
   char* w = reinterpret_cast<char*>(a->ws);
   __half* Qh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
   __half* Kh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
-  __half* Vt = reinterpret_cast<__half*>(w);
+  __half* Vh = reinterpret_cast<__half*>(w);
   cudaStream_t st = as_stream(s);
-  const int pg = (int)(cdiv((long long)rows * DPAD, 256) < 16 * kNumSMs ? cdiv((long long)rows * DPAD, 256) : 16 * kNumSMs);
-  pack_qk_kernel<<<pg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, Qh, (long long)rows);
-  GDN_CHECK_LAUNCH();
-  pack_qk_kernel<<<pg, 256, 0, st>>>(a->k, a->qk_pitch, a->d, Kh, (long long)rows);
-  GDN_CHECK_LAUNCH();
-  dim3 tg((unsigned)cdiv(a->N, 32), CPAD / 32, (unsigned)a->B);
-  pack_vt_kernel<<<tg, 256, 0, st>>>(a->v, a->v_pitch, a->C, a->N, Vt);
+  const long long pb = cdiv((long long)rows, 8);
+  pack_qkv_kernel<<<(unsigned)(pb < 16 * kNumSMs ? pb : 16 * kNumSMs), 256, 0, st>>>(a->q, a->k, a->qk_pitch, a->d, a->v, a->v_pitch, a->C, Qh, Kh, Vh, (long long)rows);
   GDN_CHECK_LAUNCH();
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_map(&mq, Qh, rows, DPAD, TQ, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
   if ((rc = make_map(&mk, Kh, rows, DPAD, TK, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
-  if ((rc = make_map(&mv, Vt, (uint64_t)a->B * CPAD, (uint64_t)a->N, CPAD, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  if ((rc = make_map(&mv, Vh, rows, CPAD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
   FwdParams p;
   p.x = a->x; p.x_pitch = a->x_pitch; p.gamma = a->gamma; p.o = a->o; p.y = a->y; p.y_pitch = a->y_pitch; p.lse = a->lse;
   p.B = a->B; p.N = a->N; p.C = a->C; p.tiles_per_sample = a->N / TQ;
