@@ -1,23 +1,29 @@
 // Position-attention core as ONE fused flash-style kernel for sm_100a:
 //   TMA (cp.async.bulk.tensor) -> shared memory -> tcgen05.mma (kind::f16, fp32 accumulate in TMEM) -> online softmax
-//   on tcgen05.ld'ed score tiles -> P (fp16) -> tcgen05.mma P.V -> epilogue  y = gamma * O / l + x,  lse.
+//   on tcgen05.ld'ed score tiles -> P (fp16, written back to TMEM) -> tcgen05.mma P.V (A operand from TMEM) -> epilogue
+//   y = gamma * O / l + x,  lse.
 // The N x N attention map of the reference (torch.bmm + softmax + torch.bmm at /root/reference/models/generator.py:115-122)
 // never leaves the SM.
 //
-// One CTA = one sample x one tile of 128 query positions; it walks all N/128 key tiles.
-//   warp 0      : TMA producer for Q and the K ring (3 stages)
-//   warp 3      : TMA producer for the V ring (5 stages of 64 keys x 192 channels, row-major: V is the MN-major B operand)
-//   warp 1      : tcgen05.mma issuer (one lane):  S[j&1] = Q K_j^T   and   O += P_j V_j
+// One CTA = one sample x one tile of 128 query positions; it walks all N/64 key tiles of 64 keys.
+//   warp 0      : TMA producer for Q and the K ring (6 stages of 64 keys)
+//   warp 3      : TMA producer for the V ring (6 stages of 64 keys x 192 channels, row-major: V is the MN-major B operand)
+//   warp 1      : tcgen05.mma issuer (one lane):  S[t&3] = Q K_t^T   and   O += P_t V_t
 //   warp 2      : TMEM allocator
-//   warps 4-7   : softmax group 0 -- EVEN key tiles; thread = query row = TMEM lane, all 128 key columns of the tile
+//   warps 4-7   : softmax group 0 -- EVEN key tiles; thread = query row = TMEM lane, all 64 key columns of the tile in registers
 //   warps 8-11  : softmax group 1 -- ODD key tiles
-// The two groups ping-pong: while one is in its MUFU-bound exp phase the other does its latency-bound phase (wait for S, row
-// maximum, P store, fences), so the exp units and the tensor pipe stay busy.  A row's maximum is thread-local (no cross-group
-// exchange); what the groups share is the per-row REFERENCE maximum in shared memory, handed over warp-to-warp (mbarrier) in
-// tile order.  The reference starts 2^8 above the first tile's maximum and is raised lazily (only when a tile exceeds it by 2^15,
-// so P < 65504 in fp16; dominant terms stay fp16-normal); the raising thread rescales its row of O in TMEM after the previous
-// P.V has landed.  In steady state no rescale happens.
-// TMEM columns: S0 [0,128) S1 [128,256) O [256,448).  P is double-buffered in shared memory (one buffer per group).
+// The two groups ping-pong: while one is in its MUFU-bound exp phase the other does its latency-bound phase (row maximum, P
+// store, fences), so the exp units and the tensor pipe stay busy.  A row's maximum is thread-local (no cross-group exchange);
+// what the groups share is the per-row REFERENCE maximum in shared memory, handed over warp-to-warp (mbarrier) in tile order.
+// The reference starts 2^8 above the first tile's maximum and is raised lazily (only when a tile exceeds it by 2^15, so
+// P < 65504 in fp16; dominant terms stay fp16-normal); the raising thread rescales its row of O in TMEM after the previous P.V
+// has landed.  In steady state no rescale happens.
+// TMEM columns: four score buffers S[u] = [64u, 64u+64), O [256,448).  P never touches shared memory: a group writes its fp16 P
+// tile back into the first 32 columns of the tile's own score buffer (tcgen05.st) and the P.V product takes its A operand from
+// TMEM (with P staged in shared memory the kernel is bound by shared-memory bandwidth: ncu showed tensor-pipe + LSU + TMA
+// wavefronts ~ 1600 of 1950 cycles per 128 keys).  Each group owns two score buffers, so Q K_{t+2}^T of its NEXT tile is
+// already in TMEM when it finishes tile t (issued right after P_{t-2} V_{t-2}): the tensor-pipe latency is off the softmax
+// groups' critical path.  Issue order per tile: P_t V_t, then Q K_{t+4}^T into the buffer P_t has just been read from.
 // Epilogue: O/l is staged through shared memory (the drained V ring) so that x is read and o, y are written as whole rows.
 // Operands: fp16 (bf16 logits are 8x worse), d zero-padded to 32, C zero-padded to 192.
 #include <cuda_bf16.h>
@@ -27,35 +33,34 @@ namespace gdn {
 namespace pamtc {
 using namespace gdn::tc;
 
-constexpr int TQ = 128, TK = 128, DPAD = 32, CPAD = 192;
-constexpr int KS = 3, VH = 5;
+constexpr int TQ = 128, TK = 64, DPAD = 32, CPAD = 192;
+constexpr int KS = 6, VS = 6;
 constexpr int Q_BYTES = TQ * DPAD * 2;          // 8 KB, 64-byte rows, SWIZZLE_64B
-constexpr int K_BYTES = TK * DPAD * 2;          // 8 KB
-constexpr int VH_CHUNK = 64 * 128;              // 8 KB: [64 keys][64 channels] fp16, 128-byte rows, SWIZZLE_128B
-constexpr int VH_BYTES = (CPAD / 64) * VH_CHUNK; // 24 KB per half tile (64 keys)
-constexpr int P_BLK = TQ * 128;                 // 16 KB: [128 rows][64 keys] fp16
-constexpr int P_BYTES = 2 * P_BLK;
+constexpr int K_BYTES = TK * DPAD * 2;          // 4 KB
+constexpr int V_CHUNK = TK * 128;               // 8 KB: [64 keys][64 channels] fp16, 128-byte rows, SWIZZLE_128B
+constexpr int V_BYTES = (CPAD / 64) * V_CHUNK;  // 24 KB per key tile
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + Q_BYTES;
 constexpr int OFF_V = OFF_K + KS * K_BYTES;     // 32768 (1024-aligned)
-constexpr int OFF_P = OFF_V + VH * VH_BYTES;    // 155648
-constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;    // 221184
+constexpr int OFF_BAR = OFF_V + VS * V_BYTES;   // 180224
 constexpr int OFF_MREF = OFF_BAR + 512;         // float [128]: shared reference maximum per row (log2 units)
 constexpr int OFF_LS = OFF_MREF + 128 * 4;      // float [2][128]
 constexpr int OFF_TMEM = OFF_LS + 2 * 128 * 4;  // uint32 tmem base
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024; // + alignment slack
 constexpr int STG_STRIDE = CPAD + 4;            // floats per staged output row (conflict-free float4 column writes)
-static_assert(TQ * STG_STRIDE * 4 <= VH * VH_BYTES, "epilogue staging fits in the V ring");
+static_assert(OFF_V % 1024 == 0, "swizzle atoms");
+static_assert(TQ * STG_STRIDE * 4 <= VS * V_BYTES, "epilogue staging fits in the V ring");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr int NTHREADS = 384;
+constexpr uint32_t COL_O = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float RESCALE_TAU = 15.f;    // raise the reference when a tile maximum exceeds it by 2^15 (P stays below the fp16 maximum)
 constexpr float REF_MARGIN = 8.f;      // ... and then put it 2^8 ABOVE that maximum, so that a slowly growing row maximum rarely triggers again
 
 // barrier slots (8 bytes each) inside OFF_BAR
-enum { BAR_Q = 0, BAR_KFULL = 1, BAR_KEMPTY = BAR_KFULL + KS, BAR_VFULL = BAR_KEMPTY + KS, BAR_VEMPTY = BAR_VFULL + VH,
-       BAR_SFULL = BAR_VEMPTY + VH, BAR_PFULL = BAR_SFULL + 2, BAR_PVDONE = BAR_PFULL + 2, BAR_MREF = BAR_PVDONE + 2, BAR_COUNT = BAR_MREF + 8 };
+enum { BAR_Q = 0, BAR_KFULL = 1, BAR_KEMPTY = BAR_KFULL + KS, BAR_VFULL = BAR_KEMPTY + KS, BAR_VEMPTY = BAR_VFULL + VS,
+       BAR_SFULL = BAR_VEMPTY + VS, BAR_PFULL = BAR_SFULL + 4, BAR_PVDONE = BAR_PFULL + 4, BAR_MREF = BAR_PVDONE + 4, BAR_COUNT = BAR_MREF + 8 };
 static_assert(BAR_COUNT * 8 <= 512, "barrier area");
 
 struct FwdParams {
@@ -83,8 +88,8 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   if (threadIdx.x == 0) {
     mbar_init(bar(BAR_Q), 1);
     for (int i = 0; i < KS; ++i) { mbar_init(bar(BAR_KFULL + i), 1); mbar_init(bar(BAR_KEMPTY + i), 1); }
-    for (int i = 0; i < VH; ++i) { mbar_init(bar(BAR_VFULL + i), 1); mbar_init(bar(BAR_VEMPTY + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(BAR_SFULL + i), 1); mbar_init(bar(BAR_PFULL + i), 4); mbar_init(bar(BAR_PVDONE + i), 1); }
+    for (int i = 0; i < VS; ++i) { mbar_init(bar(BAR_VFULL + i), 1); mbar_init(bar(BAR_VEMPTY + i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar(BAR_SFULL + i), 1); mbar_init(bar(BAR_PFULL + i), 4); mbar_init(bar(BAR_PVDONE + i), 1); }
     for (int i = 0; i < 8; ++i) mbar_init(bar(BAR_MREF + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -101,113 +106,105 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     if (lane == 0) {   // ---- Q + K producer
       mbar_expect_tx(bar(BAR_Q), Q_BYTES);
       tma_load_2d(base + OFF_Q, &mapQ, bar(BAR_Q), 0, sample * p.N + qtile * TQ);
-      for (int j = 0; j < T; ++j) {
-        const int st = j % KS;
-        if (j >= KS) mbar_wait(bar(BAR_KEMPTY + st), ((j / KS) - 1) & 1);
+      for (int t = 0; t < T; ++t) {
+        const int st = t % KS;
+        if (t >= KS) mbar_wait(bar(BAR_KEMPTY + st), ((t / KS) - 1) & 1);
         mbar_expect_tx(bar(BAR_KFULL + st), K_BYTES);
-        tma_load_2d(base + OFF_K + st * K_BYTES, &mapK, bar(BAR_KFULL + st), 0, sample * p.N + j * TK);
+        tma_load_2d(base + OFF_K + st * K_BYTES, &mapK, bar(BAR_KFULL + st), 0, sample * p.N + t * TK);
       }
     }
   } else if (warp == 3) {
-    if (lane == 0) {   // ---- V producer: half tiles of 64 keys, three 64-channel chunks each
-      for (int hh = 0; hh < 2 * T; ++hh) {
-        const int st = hh % VH;
-        if (hh >= VH) mbar_wait(bar(BAR_VEMPTY + st), ((hh / VH) - 1) & 1);
-        mbar_expect_tx(bar(BAR_VFULL + st), VH_BYTES);
+    if (lane == 0) {   // ---- V producer: three 64-channel chunks per key tile
+      for (int t = 0; t < T; ++t) {
+        const int st = t % VS;
+        if (t >= VS) mbar_wait(bar(BAR_VEMPTY + st), ((t / VS) - 1) & 1);
+        mbar_expect_tx(bar(BAR_VFULL + st), V_BYTES);
 #pragma unroll
         for (int c = 0; c < CPAD / 64; ++c)
-          tma_load_2d(base + OFF_V + st * VH_BYTES + c * VH_CHUNK, &mapV, bar(BAR_VFULL + st), c * 64, sample * p.N + hh * 64);
+          tma_load_2d(base + OFF_V + st * V_BYTES + c * V_CHUNK, &mapV, bar(BAR_VFULL + st), c * 64, sample * p.N + t * TK);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issuer
-      constexpr uint32_t IDESC_QK = idesc_f16(TQ, TK), IDESC_PV = idesc_f16(TQ, CPAD) | (1u << 16);   // bit 16: B is MN-major
-      auto issue_qk = [&](int j) {
-        const int st = j % KS;
-        mbar_wait(bar(BAR_KFULL + st), (j / KS) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < DPAD / 16; ++ks) {
-          uint64_t ad = smem_desc(base + OFF_Q + ks * 32, 512, LAYOUT_SW64);
-          uint64_t bd = smem_desc(base + OFF_K + st * K_BYTES + ks * 32, 512, LAYOUT_SW64);
-          umma_f16(tmem + (j & 1) * TK, ad, bd, IDESC_QK, ks > 0);
-        }
+    // ---- MMA issuer: the whole warp runs the loop (uniform control flow and descriptors), one elected lane issues
+    constexpr uint32_t IDESC_QK = idesc_f16(TQ, TK), IDESC_PV = idesc_f16(TQ, CPAD) | (1u << 16);   // bit 16: B is MN-major
+    const uint64_t qd0 = smem_desc(base + OFF_Q, 512, LAYOUT_SW64), qd1 = smem_desc(base + OFF_Q + 32, 512, LAYOUT_SW64);
+    const uint64_t kd_base = smem_desc(base + OFF_K, 512, LAYOUT_SW64);
+    const uint64_t vd_base = smem_desc_mn(base + OFF_V, V_CHUNK, 1024, LAYOUT_SW128);     // 64-channel groups 8 KB apart, 8-key groups 1 KB apart
+    const uint32_t tmem_o = tmem + COL_O;
+    auto issue_qk = [&](int t) {
+      const int st = t % KS;
+      mbar_wait(bar(BAR_KFULL + st), (t / KS) & 1);
+      tc_fence_after();
+      const uint64_t kd = kd_base + (uint64_t)(st * (K_BYTES >> 4));
+      const uint32_t d = tmem + (t & 3) * TK;
+      if (elect_one()) {
+        umma_f16_i<0>(d, qd0, kd, IDESC_QK);
+        umma_f16_i<1>(d, qd1, kd + 2, IDESC_QK);
         tc_commit(bar(BAR_KEMPTY + st));
-        tc_commit(bar(BAR_SFULL + (j & 1)));
-      };
-      mbar_wait(bar(BAR_Q), 0);
-      issue_qk(0);
-      if (T > 1) issue_qk(1);
-      for (int j = 0; j < T; ++j) {
-        const int w = j & 1;
-        mbar_wait(bar(BAR_PFULL + w), (j >> 1) & 1);     // P_j is in shared memory and S[w] has been read completely
-        tc_fence_after();
-        if (j + 2 < T) issue_qk(j + 2);                  // first, so that group w can start on its next tile at once
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int hh = 2 * j + h, st = hh % VH;
-          mbar_wait(bar(BAR_VFULL + st), (hh / VH) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            uint64_t ad = smem_desc(base + OFF_P + w * P_BYTES + h * P_BLK + ks * 32, 1024, LAYOUT_SW128);
-            uint64_t bd = smem_desc_mn(base + OFF_V + st * VH_BYTES + ks * 2048, VH_CHUNK, 1024, LAYOUT_SW128);   // 16 keys per step; 64-channel groups 8 KB apart
-            umma_f16(tmem + 2 * TK, ad, bd, IDESC_PV, (j > 0 || h > 0 || ks > 0) ? 1u : 0u);
-          }
-          tc_commit(bar(BAR_VEMPTY + st));
-        }
-        tc_commit(bar(BAR_PVDONE + w));
+        tc_commit(bar(BAR_SFULL + (t & 3)));
       }
+      __syncwarp();
+    };
+    mbar_wait(bar(BAR_Q), 0);
+    for (int t = 0; t < 4 && t < T; ++t) issue_qk(t);
+    for (int t = 0; t < T; ++t) {
+      const int u = t & 3, st = t % VS;
+      mbar_wait(bar(BAR_PFULL + u), (t >> 2) & 1);     // P_t is in TMEM (columns [0,32) of S[u])
+      mbar_wait(bar(BAR_VFULL + st), (t / VS) & 1);
+      tc_fence_after();
+      const uint64_t vd = vd_base + (uint64_t)(st * (V_BYTES >> 4));
+      const uint32_t pa = tmem + u * TK;
+      if (elect_one()) {
+        // A: 16 keys = 8 TMEM columns of packed fp16 pairs; B: 16 keys (2 KB) per step
+        if (t == 0) umma_f16_ts_i<0>(tmem_o, pa, vd, IDESC_PV); else umma_f16_ts_i<1>(tmem_o, pa, vd, IDESC_PV);
+        umma_f16_ts_i<1>(tmem_o, pa + 8, vd + 128, IDESC_PV);
+        umma_f16_ts_i<1>(tmem_o, pa + 16, vd + 256, IDESC_PV);
+        umma_f16_ts_i<1>(tmem_o, pa + 24, vd + 384, IDESC_PV);
+        tc_commit(bar(BAR_VEMPTY + st));
+        tc_commit(bar(BAR_PVDONE + u));
+      }
+      __syncwarp();
+      if (t + 4 < T) issue_qk(t + 4);                  // overwrites S[u] (and P_t in it) strictly after P_t V_t: same pipe, issue order
     }
   } else if (warp >= 4) {
     // ---- softmax groups
-    const int w = (warp - 4) >> 2;                  // group: tiles j = w, w + 2, ...
+    const int g = (warp - 4) >> 2;                  // group: tiles t = g, g + 2, ...
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;                 // TMEM lane == query row of the tile
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
     float* mref = reinterpret_cast<float*>(sm + OFF_MREF);
-    const uint32_t my_mref_bar = bar(BAR_MREF + w * 4 + q4), peer_mref_bar = bar(BAR_MREF + (w ^ 1) * 4 + q4);
-    uint8_t* prow = sm + OFF_P + w * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+    const uint32_t my_mref_bar = bar(BAR_MREF + g * 4 + q4), peer_mref_bar = bar(BAR_MREF + (g ^ 1) * 4 + q4);
     float m_loc = -INFINITY, l = 0.f;
     int nwait = 0;
-    for (int j = w; j < T; j += 2) {
-      const int i = j >> 1;
-      mbar_wait(bar(BAR_SFULL + w), i & 1);
+    for (int t = g; t < T; t += 2) {
+      const int u = t & 3;
+      mbar_wait(bar(BAR_SFULL + u), (t >> 2) & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem + lane_addr + w * TK;
-      // pass 1: row maximum of the tile
-      float mx;
-      {
-        uint32_t a[32], b[32];
-        tmem_ld32_async(s_addr, a); tmem_ld32_async(s_addr + 32, b);
-        tmem_ld_wait64(a, b);
-        float m0 = __uint_as_float(a[0]), m1 = __uint_as_float(b[0]);
+      const uint32_t s_addr = tmem + lane_addr + u * TK;
+      uint32_t a[32], b[32];
+      tmem_ld32_async(s_addr, a); tmem_ld32_async(s_addr + 32, b);
+      tmem_ld_wait64(a, b);
+      float m0 = __uint_as_float(a[0]), m1 = __uint_as_float(b[0]);
 #pragma unroll
-        for (int e = 1; e < 32; ++e) { m0 = fmaxf(m0, __uint_as_float(a[e])); m1 = fmaxf(m1, __uint_as_float(b[e])); }
-        tmem_ld32_async(s_addr + 64, a); tmem_ld32_async(s_addr + 96, b);
-        tmem_ld_wait64(a, b);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) { m0 = fmaxf(m0, __uint_as_float(a[e])); m1 = fmaxf(m1, __uint_as_float(b[e])); }
-        mx = fmaxf(m0, m1);
-      }
-      const float mt = mx * LOG2E;
-      // take over the shared reference from the group that decided tile j-1
-      if (j > 0) {
+      for (int e = 1; e < 32; ++e) { m0 = fmaxf(m0, __uint_as_float(a[e])); m1 = fmaxf(m1, __uint_as_float(b[e])); }
+      const float mt = fmaxf(m0, m1) * LOG2E;
+      // take over the shared reference from the group that decided tile t-1
+      if (t > 0) {
         mbar_wait(my_mref_bar, nwait & 1);
         ++nwait;
         const float m_sh = mref[row];
         if (m_sh != m_loc) { l *= ex2(m_loc - m_sh); m_loc = m_sh; }
         const bool changed = mt > m_loc + RESCALE_TAU;
         if (__any_sync(0xffffffffu, changed)) {
-          // raise the reference: rescale this row of O once P_{j-1} V_{j-1} (and everything before it) has landed
+          // raise the reference: rescale this row of O once P_{t-1} V_{t-1} (and everything before it) has landed
           const float m_new = changed ? mt + REF_MARGIN : m_loc;
           const float f = ex2(m_loc - m_new);
-          mbar_wait(bar(BAR_PVDONE + (w ^ 1)), ((j - 1) >> 1) & 1);
+          mbar_wait(bar(BAR_PVDONE + ((t - 1) & 3)), ((t - 1) >> 2) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < CPAD; c += 32) {
             float ov[32];
-            const uint32_t ta = tmem + lane_addr + 2 * TK + c;
+            const uint32_t ta = tmem + lane_addr + COL_O + c;
             tmem_ld32(ta, ov);
 #pragma unroll
             for (int e = 0; e < 32; ++e) ov[e] *= f;
@@ -221,68 +218,55 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         m_loc = mt + REF_MARGIN;
       }
       mref[row] = m_loc;
-      if (j + 1 < T) {
+      if (t + 1 < T) {
         __syncwarp();
         if (lane == 0) mbar_arrive(peer_mref_bar);
       }
-      // pass 2: P = exp2(S*log2e - m_ref) in fp16, row sum in fp32; 64 key columns (= one K-major SWIZZLE_128B block of P) at a time
+      // P = exp2(S*log2e - m_ref) in fp16 (two keys per 32-bit TMEM column), row sum in fp32
+      uint32_t packed[32];
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t a[32], b[32];
-        tmem_ld32_async(s_addr + h * 64, a); tmem_ld32_async(s_addr + h * 64 + 32, b);
-        tmem_ld_wait64(a, b);
-        uint32_t packed[32];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(a[e]), LOG2E, -m_loc)), p1 = ex2(fmaf(__uint_as_float(a[e + 1]), LOG2E, -m_loc));
-          const float p2 = ex2(fmaf(__uint_as_float(b[e]), LOG2E, -m_loc)), p3 = ex2(fmaf(__uint_as_float(b[e + 1]), LOG2E, -m_loc));
-          l0 += p0 + p1; l1 += p2 + p3;
-          __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
-          packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h01);
-          packed[16 + (e >> 1)] = *reinterpret_cast<uint32_t*>(&h23);
-        }
-        // this group's P buffer must have been consumed by P_{j-2} V_{j-2}: checked as late as possible (after the first 64 exponentials)
-        if (h == 0 && i > 0) mbar_wait(bar(BAR_PVDONE + w), (i - 1) & 1);
-        // K-major SWIZZLE_128B tile: row r at r*128 B inside 1024-B groups of 8 rows, 16-B chunk index XOR (r & 7)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-          *reinterpret_cast<uint4*>(prow + h * P_BLK + ((c ^ (row & 7)) << 4)) = val;
-        }
+      for (int e = 0; e < 32; e += 2) {
+        const float p0 = ex2(fmaf(__uint_as_float(a[e]), LOG2E, -m_loc)), p1 = ex2(fmaf(__uint_as_float(a[e + 1]), LOG2E, -m_loc));
+        const float p2 = ex2(fmaf(__uint_as_float(b[e]), LOG2E, -m_loc)), p3 = ex2(fmaf(__uint_as_float(b[e + 1]), LOG2E, -m_loc));
+        l0 += p0 + p1; l1 += p2 + p3;
+        __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+        packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h01);
+        packed[16 + (e >> 1)] = *reinterpret_cast<uint32_t*>(&h23);
       }
       l += l0 + l1;
-      fence_async_smem();
+      tmem_st32_u(s_addr, packed);                       // P columns [0,32) of S[u]: every S column has been read
+      tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BAR_PFULL + w));
+      if (lane == 0) mbar_arrive(bar(BAR_PFULL + u));
     }
     // ---- epilogue: o = O / l, y = gamma*o + x, lse
     asm volatile("bar.sync 1, 256;" ::: "memory");           // the last reference has been published
-    const float m_fin = (((T - 1) & 1) == w) ? m_loc : mref[row];   // decided by the group that owned the last tile
-    if (m_fin != m_loc) l *= ex2(m_loc - m_fin);             // a group without tiles has m_loc = -inf, l = 0
+    const float m_fin = (((T - 1) & 1) == g) ? m_loc : mref[row];   // decided by the group that owned the last tile
+    if (m_fin != m_loc) l *= ex2(m_loc - m_fin);
     float* ls = reinterpret_cast<float*>(sm + OFF_LS);
-    ls[w * 128 + row] = l;
+    ls[g * 128 + row] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float ltot = ls[row] + ls[128 + row];
     const float inv = 1.f / ltot;
-    mbar_wait(bar(BAR_PVDONE + ((T - 1) & 1)), ((T - 1) >> 1) & 1);
+    mbar_wait(bar(BAR_PVDONE + ((T - 1) & 3)), ((T - 1) >> 2) & 1);
     tc_fence_after();
     const size_t row0 = (size_t)sample * p.N + (size_t)qtile * TQ;
-    if (w == 0) p.lse[row0 + row] = (m_fin + log2f(ltot)) * LN2;
+    if (g == 0) p.lse[row0 + row] = (m_fin + log2f(ltot)) * LN2;
     float* stg = reinterpret_cast<float*>(sm + OFF_V);       // the V ring is drained: all P.V products have completed
 #pragma unroll 1
     for (int c = 0; c < CPAD / 2; c += 32) {
       float ov[32];
-      const int c0 = w * (CPAD / 2) + c;
-      tmem_ld32(tmem + lane_addr + 2 * TK + c0, ov);
+      const int c0 = g * (CPAD / 2) + c;
+      tmem_ld32(tmem + lane_addr + COL_O + c0, ov);
 #pragma unroll
       for (int e = 0; e < 32; e += 4)
         *reinterpret_cast<float4*>(stg + row * STG_STRIDE + c0 + e) = make_float4(ov[e] * inv, ov[e + 1] * inv, ov[e + 2] * inv, ov[e + 3] * inv);
     }
     tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float g = __ldg(p.gamma);
+    const float gm = __ldg(p.gamma);
     const int c4n = p.C >> 2;                                 // C is a multiple of 4 on this path (checked on the host)
     const int total = TQ * c4n;
     for (int idx = threadIdx.x - 128; idx < total; idx += 256) {
@@ -291,7 +275,7 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       const size_t grow = row0 + r;
       const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + grow * p.x_pitch + ch));
       *reinterpret_cast<float4*>(p.o + grow * p.C + ch) = on;
-      *reinterpret_cast<float4*>(p.y + grow * p.y_pitch + ch) = make_float4(fmaf(g, on.x, xv.x), fmaf(g, on.y, xv.y), fmaf(g, on.z, xv.z), fmaf(g, on.w, xv.w));
+      *reinterpret_cast<float4*>(p.y + grow * p.y_pitch + ch) = make_float4(fmaf(gm, on.x, xv.x), fmaf(gm, on.y, xv.y), fmaf(gm, on.z, xv.z), fmaf(gm, on.w, xv.w));
     }
   }
   __syncthreads();
@@ -359,7 +343,7 @@ extern "C" size_t gdn_pam_tc_fwd_ws_bytes(const gdn_pam_fwd_args* a) {
 
 extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
   GDN_CHECK_ARG(a->precision == GDN_PREC_FP16);
-  GDN_CHECK_ARG(a->N % TK == 0 && a->d <= DPAD && a->C <= CPAD && a->C % 4 == 0);
+  GDN_CHECK_ARG(a->N % TQ == 0 && a->d <= DPAD && a->C <= CPAD && a->C % 4 == 0);
   GDN_CHECK_ARG(a->x_pitch % 4 == 0 && a->y_pitch % 4 == 0);
   GDN_CHECK_ARG(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->y & 15) == 0 && ((uintptr_t)a->o & 15) == 0);
   if (!a->ws || a->ws_bytes < gdn_pam_tc_fwd_ws_bytes(a)) { set_error("gdn_pam_fwd(fp16): workspace too small"); return GDN_EWORKSPACE; }
