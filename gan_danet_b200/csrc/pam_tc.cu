@@ -8,8 +8,8 @@
 // One CTA = one sample x one tile of 128 query positions; it walks all N/64 key tiles of 64 keys.
 //   warp 0      : TMA producer for Q and the K ring (6 stages of 64 keys)
 //   warp 3      : TMA producer for the V ring (6 stages of 64 keys x 192 channels, row-major: V is the MN-major B operand)
-//   warp 1      : tcgen05.mma issuer (one lane):  S[t&3] = Q K_t^T   and   O += P_t V_t
-//   warp 2      : TMEM allocator
+//   warp 1      : tcgen05.mma issuer for  O += P_t V_t        (warp-uniform loop, one elected lane issues)
+//   warp 2      : TMEM allocator, then tcgen05.mma issuer for  S[t&3] = Q K_t^T
 //   warps 4-7   : softmax group 0 -- EVEN key tiles; thread = query row = TMEM lane, all 64 key columns of the tile in registers
 //   warps 8-11  : softmax group 1 -- ODD key tiles
 // The two groups ping-pong: while one is in its MUFU-bound exp phase the other does its latency-bound phase (row maximum, P
@@ -23,7 +23,9 @@
 // TMEM (with P staged in shared memory the kernel is bound by shared-memory bandwidth: ncu showed tensor-pipe + LSU + TMA
 // wavefronts ~ 1600 of 1950 cycles per 128 keys).  Each group owns two score buffers, so Q K_{t+2}^T of its NEXT tile is
 // already in TMEM when it finishes tile t (issued right after P_{t-2} V_{t-2}): the tensor-pipe latency is off the softmax
-// groups' critical path.  Issue order per tile: P_t V_t, then Q K_{t+4}^T into the buffer P_t has just been read from.
+// groups' critical path.  Q K_{t+4}^T goes into the buffer P_t was read from, after P_t V_t has completed (mbarrier).  The two
+// products have separate issuing warps: a single warp's serial instruction stream (waits, descriptor adds, issue, commits) was
+// the kernel's critical path at ~900 cycles per 64 keys.
 // Epilogue: O/l is staged through shared memory (the drained V ring) so that x is read and o, y are written as whole rows.
 // Operands: fp16 (bf16 logits are 8x worse), d zero-padded to 32, C zero-padded to 192.
 #include <cuda_bf16.h>
@@ -125,34 +127,17 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer: the whole warp runs the loop (uniform control flow and descriptors), one elected lane issues
-    constexpr uint32_t IDESC_QK = idesc_f16(TQ, TK), IDESC_PV = idesc_f16(TQ, CPAD) | (1u << 16);   // bit 16: B is MN-major
-    const uint64_t qd0 = smem_desc(base + OFF_Q, 512, LAYOUT_SW64), qd1 = smem_desc(base + OFF_Q + 32, 512, LAYOUT_SW64);
-    const uint64_t kd_base = smem_desc(base + OFF_K, 512, LAYOUT_SW64);
+    // ---- P.V issuer: the whole warp runs the loop (uniform control flow and descriptors), one elected lane issues
+    constexpr uint32_t IDESC_PV = idesc_f16(TQ, CPAD) | (1u << 16);   // bit 16: B is MN-major
     const uint64_t vd_base = smem_desc_mn(base + OFF_V, V_CHUNK, 1024, LAYOUT_SW128);     // 64-channel groups 8 KB apart, 8-key groups 1 KB apart
     const uint32_t tmem_o = tmem + COL_O;
-    auto issue_qk = [&](int t) {
-      const int st = t % KS;
-      mbar_wait(bar(BAR_KFULL + st), (t / KS) & 1);
-      tc_fence_after();
-      const uint64_t kd = kd_base + (uint64_t)(st * (K_BYTES >> 4));
-      const uint32_t d = tmem + (t & 3) * TK;
-      if (elect_one()) {
-        umma_f16_i<0>(d, qd0, kd, IDESC_QK);
-        umma_f16_i<1>(d, qd1, kd + 2, IDESC_QK);
-        tc_commit(bar(BAR_KEMPTY + st));
-        tc_commit(bar(BAR_SFULL + (t & 3)));
-      }
-      __syncwarp();
-    };
-    mbar_wait(bar(BAR_Q), 0);
-    for (int t = 0; t < 4 && t < T; ++t) issue_qk(t);
+    int st = 0; uint32_t ph = 0;
+    uint64_t vd = vd_base;
     for (int t = 0; t < T; ++t) {
-      const int u = t & 3, st = t % VS;
-      mbar_wait(bar(BAR_PFULL + u), (t >> 2) & 1);     // P_t is in TMEM (columns [0,32) of S[u])
-      mbar_wait(bar(BAR_VFULL + st), (t / VS) & 1);
+      const int u = t & 3;
+      mbar_wait_spin(bar(BAR_PFULL + u), (t >> 2) & 1);     // P_t is in TMEM (columns [0,32) of S[u])
+      mbar_wait_spin(bar(BAR_VFULL + st), ph);
       tc_fence_after();
-      const uint64_t vd = vd_base + (uint64_t)(st * (V_BYTES >> 4));
       const uint32_t pa = tmem + u * TK;
       if (elect_one()) {
         // A: 16 keys = 8 TMEM columns of packed fp16 pairs; B: 16 keys (2 KB) per step
@@ -164,7 +149,32 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         tc_commit(bar(BAR_PVDONE + u));
       }
       __syncwarp();
-      if (t + 4 < T) issue_qk(t + 4);                  // overwrites S[u] (and P_t in it) strictly after P_t V_t: same pipe, issue order
+      vd += V_BYTES >> 4;
+      if (++st == VS) { st = 0; ph ^= 1; vd = vd_base; }
+    }
+  } else if (warp == 2) {
+    // ---- Q.K^T issuer (after its TMEM allocation duty): S[t&3] may be overwritten once P_{t-4} V_{t-4} has read P_{t-4} from it
+    constexpr uint32_t IDESC_QK = idesc_f16(TQ, TK);
+    const uint64_t qd0 = smem_desc(base + OFF_Q, 512, LAYOUT_SW64), qd1 = smem_desc(base + OFF_Q + 32, 512, LAYOUT_SW64);
+    const uint64_t kd_base = smem_desc(base + OFF_K, 512, LAYOUT_SW64);
+    int st = 0; uint32_t ph = 0;
+    uint64_t kd = kd_base;
+    mbar_wait_spin(bar(BAR_Q), 0);
+    for (int t = 0; t < T; ++t) {
+      const int u = t & 3;
+      mbar_wait_spin(bar(BAR_KFULL + st), ph);
+      if (t >= 4) mbar_wait_spin(bar(BAR_PVDONE + u), ((t >> 2) - 1) & 1);
+      tc_fence_after();
+      const uint32_t d = tmem + u * TK;
+      if (elect_one()) {
+        umma_f16_i<0>(d, qd0, kd, IDESC_QK);
+        umma_f16_i<1>(d, qd1, kd + 2, IDESC_QK);
+        tc_commit(bar(BAR_KEMPTY + st));
+        tc_commit(bar(BAR_SFULL + u));
+      }
+      __syncwarp();
+      kd += K_BYTES >> 4;
+      if (++st == KS) { st = 0; ph ^= 1; kd = kd_base; }
     }
   } else if (warp >= 4) {
     // ---- softmax groups
