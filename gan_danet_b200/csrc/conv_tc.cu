@@ -194,64 +194,72 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issuer
-      const uint32_t idesc = idesc_bf16(BM, p.n_tile, 0, 0);
-      int it = 0, lt = 0, na = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-        const int ab = lt & 1;
-        if (lt >= 2) mbar_wait(acc_empty(ab), ((lt >> 1) - 1) & 1);     // epilogue has drained this accumulator buffer
-        tc_fence_after();
-        const uint32_t d_tmem = tmem + ab * acc_stride;
-        if (HALO) {
-          for (int kk = 0; kk < p.kchunks * p.nsplit; ++kk, ++na) {
-            const int sa = na % HALO_SLOTS;
-            mbar_wait(afull(sa), (na / HALO_SLOTS) & 1);
-            for (int tp0 = 0; tp0 < p.taps.n; tp0 += p.kgroup, ++it) {
-              const int s = it % p.stages;
-              mbar_wait(full(s), (it / p.stages) & 1);
-              tc_fence_after();
-              const int cnt = min(p.kgroup, p.taps.n - tp0);
-              for (int g = 0; g < cnt; ++g) {
-                const int tp = tp0 + g;
-                // window of tap (dh, dw): halo rows (dh+1)*130 + (dw+1) ... +127, one 128-byte row per pixel
-                const uint32_t a0 = base + sa * HALO_SLOT + (uint32_t)((p.taps.dh[tp] + 1) * HALO_W + (p.taps.dw[tp] + 1)) * 128u;
-                const uint32_t b0 = base + ring_off + s * stage_bytes + g * b_bytes;
-#pragma unroll
-                for (int ks = 0; ks < BK / 16; ++ks)
-                  umma_f16(d_tmem, smem_desc_bo(a0 + ks * 32, 1024, LAYOUT_SW128, p.halo_bo), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (kk > 0 || tp > 0 || ks > 0) ? 1u : 0u);
-              }
-              tc_commit(empty(s));
-            }
-            tc_commit(aempty(sa));
-          }
-        } else if (p.kgroup == 1) {
-          for (int k = 0; k < KI; ++k, ++it) {
-            const int s = it % p.stages;
-            mbar_wait(full(s), (it / p.stages) & 1);
+    // ---- MMA issuer.  The whole warp runs the (uniform) loops and waits; one elected lane issues the tcgen05 instructions, whose
+    // descriptors are uniform values built from a base descriptor plus 16-byte-unit offsets (see elect_one() in tc_common.cuh:
+    // an `if (lane == 0)` issue region costs ~90 cycles per tcgen05.mma, more than a 128 x n_tile x 16 MMA with n_tile <= 128 lasts).
+    const uint32_t idesc = idesc_bf16(BM, p.n_tile, 0, 0);
+    const uint64_t desc0 = smem_desc(base, 1024, LAYOUT_SW128);       // K-major SWIZZLE_128B tile at `base`; + (byte offset >> 4) moves it
+    int s = 0, lt = 0, sa = 0;
+    uint32_t ph = 0, pha = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      if (lt >= 2) mbar_wait_spin(acc_empty(ab), ((lt >> 1) - 1) & 1);     // epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + ab * acc_stride;
+      if (HALO) {
+        for (int kk = 0; kk < p.kchunks * p.nsplit; ++kk) {
+          mbar_wait_spin(afull(sa), pha);
+          for (int tp0 = 0; tp0 < p.taps.n; tp0 += p.kgroup) {
+            mbar_wait_spin(full(s), ph);
             tc_fence_after();
-            const uint32_t a0 = base + s * sub_bytes, b0 = a0 + A_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < BK / 16; ++ks)
-              umma_f16(d_tmem, smem_desc(a0 + ks * 32, 1024, LAYOUT_SW128), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (k > 0 || ks > 0) ? 1u : 0u);
-            tc_commit(empty(s));
-          }
-        } else {
-          for (int k0 = 0; k0 < KI; k0 += p.kgroup, ++it) {
-            const int s = it % p.stages;
-            mbar_wait(full(s), (it / p.stages) & 1);
-            tc_fence_after();
-            const int cnt = min(p.kgroup, KI - k0);
+            const int cnt = min(p.kgroup, p.taps.n - tp0);
             for (int g = 0; g < cnt; ++g) {
-              const uint32_t a0 = base + s * stage_bytes + g * sub_bytes, b0 = a0 + A_BYTES;
-#pragma unroll
-              for (int ks = 0; ks < BK / 16; ++ks)
-                umma_f16(d_tmem, smem_desc(a0 + ks * 32, 1024, LAYOUT_SW128), smem_desc(b0 + ks * 32, 1024, LAYOUT_SW128), idesc, (k0 + g > 0 || ks > 0) ? 1u : 0u);
+              const int tp = tp0 + g;
+              // window of tap (dh, dw): halo rows (dh+1)*130 + (dw+1) ... +127, one 128-byte row per pixel
+              const uint32_t a0 = base + sa * HALO_SLOT + (uint32_t)((p.taps.dh[tp] + 1) * HALO_W + (p.taps.dw[tp] + 1)) * 128u;
+              const uint64_t ad = smem_desc_bo(a0, 1024, LAYOUT_SW128, p.halo_bo);      // + 2 per 32-byte K step stays inside the 128-byte row
+              const uint64_t bd = desc0 + (uint64_t)((ring_off + s * stage_bytes + g * b_bytes) >> 4);
+              if (elect_one()) {
+                umma_f16(d_tmem, ad, bd, idesc, (kk > 0 || tp > 0) ? 1u : 0u);
+                umma_f16_i<1>(d_tmem, ad + 2, bd + 2, idesc);
+                umma_f16_i<1>(d_tmem, ad + 4, bd + 4, idesc);
+                umma_f16_i<1>(d_tmem, ad + 6, bd + 6, idesc);
+              }
+              __syncwarp();
             }
-            tc_commit(empty(s));
+            if (elect_one()) tc_commit(empty(s));
+            __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1; }
           }
+          if (elect_one()) tc_commit(aempty(sa));
+          __syncwarp();
+          if (++sa == HALO_SLOTS) { sa = 0; pha ^= 1; }
         }
-        tc_commit(acc_full(ab));
+      } else {
+        // a stage holds p.kgroup K-iterations (A tile | W tile) back to back; kgroup == 1 for wide tiles
+        for (int k0 = 0; k0 < KI; k0 += p.kgroup) {
+          mbar_wait_spin(full(s), ph);
+          tc_fence_after();
+          const int cnt = min(p.kgroup, KI - k0);
+          uint64_t ad = desc0 + (uint64_t)((s * stage_bytes) >> 4);
+          for (int g = 0; g < cnt; ++g) {
+            const uint64_t bd = ad + (A_BYTES >> 4);
+            if (elect_one()) {
+              umma_f16(d_tmem, ad, bd, idesc, (k0 + g > 0) ? 1u : 0u);
+              umma_f16_i<1>(d_tmem, ad + 2, bd + 2, idesc);
+              umma_f16_i<1>(d_tmem, ad + 4, bd + 4, idesc);
+              umma_f16_i<1>(d_tmem, ad + 6, bd + 6, idesc);
+            }
+            __syncwarp();
+            ad += (uint64_t)(sub_bytes >> 4);
+          }
+          if (elect_one()) tc_commit(empty(s));
+          __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
       }
+      if (elect_one()) tc_commit(acc_full(ab));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ---- epilogue: 8 warps; warp w drains TMEM lanes [32*(w&3), +32) (the hardware's lane quarter of a warp) and the 32-column
@@ -436,30 +444,38 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDYhi, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issuer: acc[tap] (128 co x ci_tile) += dy^T (MN-major A) * x (MN-major B), K = 128 pixels per tile
-      const uint32_t idesc = idesc_bf16(128, p.ci_tile, 1, 1);
-      int nd = 0, nx = 0;
-      for (int ti = 0; ti < ntiles; ++ti) {
-        for (int comp = 0; comp < p.nsplit; ++comp, ++nd) {
-          const int sd = nd % WG_DY_SLOTS;
-          mbar_wait(dyfull(sd), (nd / WG_DY_SLOTS) & 1);
-          for (int tl = 0; tl < p.taps_per_cta; ++tl, ++nx) {
-            const int sx = nx % WG_X_SLOTS;
-            mbar_wait(xfull(sx), (nx / WG_X_SLOTS) & 1);
-            tc_fence_after();
-            const uint32_t a0 = dy_base + sd * WG_DY_BYTES, b0 = x_base + sx * x_bytes;
+    // ---- MMA issuer (warp-uniform loop, one elected lane issues): acc[tap] (128 co x ci_tile) += dy^T (MN-major A) * x (MN-major B),
+    // K = 128 pixels per tile
+    const uint32_t idesc = idesc_bf16(128, p.ci_tile, 1, 1);
+    const uint64_t desc0 = smem_desc_lbo(base, A_BYTES, 1024, LAYOUT_SW128);   // channel groups of 64 are LBO = 16 KB apart, 8-pixel atoms SBO = 1 KB
+    int sd = 0, sx = 0;
+    uint32_t phd = 0, phx = 0;
+    for (int ti = 0; ti < ntiles; ++ti) {
+      for (int comp = 0; comp < p.nsplit; ++comp) {
+        mbar_wait_spin(dyfull(sd), phd);
+        const uint64_t ad = desc0 + (uint64_t)((sd * WG_DY_BYTES) >> 4);
+        for (int tl = 0; tl < p.taps_per_cta; ++tl) {
+          mbar_wait_spin(xfull(sx), phx);
+          tc_fence_after();
+          const uint64_t bd = desc0 + (uint64_t)((WG_DY_SLOTS * WG_DY_BYTES + sx * x_bytes) >> 4);
+          const uint32_t d = tmem + tl * p.ci_tile;
+          if (elect_one()) {
+            umma_f16(d, ad, bd, idesc, (ti > 0 || comp > 0) ? 1u : 0u);
 #pragma unroll
-            for (int ks = 0; ks < BM / 16; ++ks) {   // 16 pixels = two 8-row swizzle atoms (SBO = 1024 B); channel groups of 64 are LBO = 16 KB apart
-              umma_f16(tmem + tl * p.ci_tile, smem_desc_lbo(a0 + ks * 2048, A_BYTES, 1024, LAYOUT_SW128), smem_desc_lbo(b0 + ks * 2048, A_BYTES, 1024, LAYOUT_SW128), idesc,
-                       (ti > 0 || comp > 0 || ks > 0) ? 1u : 0u);
-            }
+            for (int ks = 1; ks < BM / 16; ++ks)     // 16 pixels = two 8-row swizzle atoms = 2 KB
+              umma_f16_i<1>(d, ad + ks * 128, bd + ks * 128, idesc);
             tc_commit(xempty(sx));
           }
-          tc_commit(dyempty(sd));
+          __syncwarp();
+          if (++sx == WG_X_SLOTS) { sx = 0; phx ^= 1; }
         }
+        if (elect_one()) tc_commit(dyempty(sd));
+        __syncwarp();
+        if (++sd == WG_DY_SLOTS) { sd = 0; phd ^= 1; }
       }
-      tc_commit(acc_bar);
     }
+    if (elect_one()) tc_commit(acc_bar);
+    __syncwarp();
   } else if (warp >= 4) {
     // ---- epilogue: thread = output channel (TMEM lane); partial sums to the workspace
     const int q = warp & 3;
