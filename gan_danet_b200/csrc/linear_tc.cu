@@ -104,19 +104,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issuer
-      const uint32_t id = MODE == MODE_FWD ? idesc(128, NW, 0, 0) : idesc(128, NW, 1, 0);
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
-        const int ab = lt & 1;
-        if (lt >= 2) mbar_wait(acc_empty(ab), ((lt >> 1) - 1) & 1);
+    // ---- MMA issuer: warp-uniform loop, one elected lane issues (see elect_one() in tc_common.cuh)
+    const uint32_t id = MODE == MODE_FWD ? idesc(128, NW, 0, 0) : idesc(128, NW, 1, 0);
+    int s = 0, lt = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      if (lt >= 2) mbar_wait_spin(acc_empty(ab), ((lt >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint32_t d = tmem + ab * acc_stride;
+      for (int ks = 0; ks < p.ksteps; ++ks) {
+        mbar_wait_spin(full(s), ph);
         tc_fence_after();
-        const uint32_t d = tmem + ab * acc_stride;
-        for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
-          const int s = it % p.stages;
-          mbar_wait(full(s), (it / p.stages) & 1);
-          tc_fence_after();
-          const uint32_t a = base + s * p.stage_bytes, b = a + p.a_bytes;
+        const uint32_t a = base + s * p.stage_bytes, b = a + p.a_bytes;
+        if (elect_one()) {
           if (MODE == MODE_FWD) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)      // 64 k = 2 boxes x 4 steps of 8 (32 bytes along the swizzled row)
@@ -132,8 +133,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
           }
           tc_commit(empty(s));
         }
-        tc_commit(acc_full(ab));
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
+      if (elect_one()) tc_commit(acc_full(ab));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ---- epilogue: thread = accumulator row (TMEM lane)

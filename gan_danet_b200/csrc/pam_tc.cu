@@ -504,49 +504,64 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issuer
-      constexpr uint32_t ID_X = idesc_f16(TO, TI), ID_Y = idesc_bf16(TO, TI, 0), ID_S = idesc_bf16(TO, DPAD, 0), ID_B = idesc_bf16(TO, CPAD, 1);
-      auto issue_xy = [&](int t) {
-        const int s = t % ST, b = t & 1;
-        const uint32_t st = base + OFF_IN + s * IN_BYTES;
-        mbar_wait(bar(B_INFULL + s), (t / ST) & 1);
-        if (t >= 2) { mbar_wait(bar(B_XFREE + b), ((t >> 1) - 1) & 1); mbar_wait(bar(B_YFREE + b), ((t >> 1) - 1) & 1); }
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < DPAD / 16; ++ks)
-          umma_f16(tmem + COL_X + b * TI, smem_desc(base + OFF_OQK + ks * 32, 512, LAYOUT_SW64), smem_desc(st + IN_IQK + ks * 32, 512, LAYOUT_SW64), ID_X, ks > 0);
+    // ---- MMA issuer: warp-uniform loop, one elected lane issues; descriptors are base descriptors plus 16-byte-unit offsets
+    constexpr uint32_t ID_X = idesc_f16(TO, TI), ID_Y = idesc_bf16(TO, TI, 0), ID_S = idesc_bf16(TO, DPAD, 0), ID_B = idesc_bf16(TO, CPAD, 1);
+    const uint64_t d64 = smem_desc(base, 512, LAYOUT_SW64), d128 = smem_desc(base, 1024, LAYOUT_SW128);
+    const uint64_t dmn = smem_desc_lbo(base, IC_CHUNK, 1024, LAYOUT_SW128);     // MN-major: 64-channel groups 8 KB apart, 8-row groups 1 KB apart
+    const uint64_t oqk_d = d64 + (OFF_OQK >> 4), oc_d = d128 + (OFF_OC >> 4);
+    auto issue_xy = [&](int t, int s, uint32_t ph) {
+      const int b = t & 1;
+      mbar_wait_spin(bar(B_INFULL + s), ph);
+      if (t >= 2) { mbar_wait_spin(bar(B_XFREE + b), ((t >> 1) - 1) & 1); mbar_wait_spin(bar(B_YFREE + b), ((t >> 1) - 1) & 1); }
+      tc_fence_after();
+      const uint32_t st_off = (uint32_t)(OFF_IN + s * IN_BYTES) >> 4;
+      const uint64_t iqk_d = d64 + st_off + (IN_IQK >> 4), ic_d = d128 + st_off + (IN_IC >> 4);
+      if (elect_one()) {
+        umma_f16_i<0>(tmem + COL_X + b * TI, oqk_d, iqk_d, ID_X);
+        umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d + 2, iqk_d + 2, ID_X);
         tc_commit(bar(B_XFULL + b));
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_f16(tmem + COL_Y + b * TI, smem_desc(base + OFF_OC + c * OC_CHUNK + ks * 32, 1024, LAYOUT_SW128),
-                     smem_desc(st + IN_IC + c * IC_CHUNK + ks * 32, 1024, LAYOUT_SW128), ID_Y, (c > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = oc_d + (uint64_t)(c * (OC_CHUNK >> 4) + ks * 2), bd = ic_d + (uint64_t)(c * (IC_CHUNK >> 4) + ks * 2);
+            if (c == 0 && ks == 0) umma_f16_i<0>(tmem + COL_Y + b * TI, ad, bd, ID_Y); else umma_f16_i<1>(tmem + COL_Y + b * TI, ad, bd, ID_Y);
+          }
         tc_commit(bar(B_YFULL + b));
-      };
-      mbar_wait(bar(B_OUT), 0);
-      issue_xy(0);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) issue_xy(t + 1);
-        const int s = t % ST, b = t & 1;
-        const uint32_t st = base + OFF_IN + s * IN_BYTES;
-        mbar_wait(bar(B_DSFULL + b), (t >> 1) & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    mbar_wait_spin(bar(B_OUT), 0);
+    issue_xy(0, 0, 0);
+    int s = 0, s1 = 1 % ST; uint32_t ph1 = (1 / ST) & 1;       // (stage, phase) of block t and of block t+1
+    for (int t = 0; t < T; ++t) {
+      if (t + 1 < T) issue_xy(t + 1, s1, ph1);
+      if (++s1 == ST) { s1 = 0; ph1 ^= 1; }
+      const int b = t & 1;
+      mbar_wait_spin(bar(B_DSFULL + b), (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t st_off = (uint32_t)(OFF_IN + s * IN_BYTES) >> 4;
+      const uint64_t ds_d = d128 + (uint64_t)((OFF_DS + b * TILE_BYTES) >> 4), it_d = d128 + st_off + (IN_IT >> 4);
+      if (elect_one()) {
+        // small accumulator += dS (K-major over the 64 inner rows) x inner^T tile [32][64]
+        umma_f16(tmem + COL_SMALL, ds_d, it_d, ID_S, t > 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < TI / 16; ++ks)   // small accumulator += dS (K-major over the 64 inner rows) x inner^T tile [32][64]
-          umma_f16(tmem + COL_SMALL, smem_desc(base + OFF_DS + b * TILE_BYTES + ks * 32, 1024, LAYOUT_SW128), smem_desc(st + IN_IT + ks * 32, 1024, LAYOUT_SW128), ID_S,
-                   (t > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 1; ks < TI / 16; ++ks) umma_f16_i<1>(tmem + COL_SMALL, ds_d + ks * 2, it_d + ks * 2, ID_S);
         if (MODE == 1) {
+          // dV += P^T x dy_i: B = the [64 q][192 ch] dy tile read MN-major (16 rows = 2 KB per step)
+          const uint64_t ps_d = d128 + (uint64_t)((OFF_PS + b * TILE_BYTES) >> 4), icmn_d = dmn + st_off + (IN_IC >> 4);
+          umma_f16(tmem + COL_BIG, ps_d, icmn_d, ID_B, t > 0 ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < TI / 16; ++ks)   // dV += P^T x dy_i: B = the [64 q][192 ch] dy tile read MN-major (16 rows per step, 64-channel groups 8 KB apart)
-            umma_f16(tmem + COL_BIG, smem_desc(base + OFF_PS + b * TILE_BYTES + ks * 32, 1024, LAYOUT_SW128),
-                     smem_desc_lbo(st + IN_IC + ks * 2048, IC_CHUNK, 1024, LAYOUT_SW128), ID_B, (t > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 1; ks < TI / 16; ++ks) umma_f16_i<1>(tmem + COL_BIG, ps_d + ks * 2, icmn_d + ks * 128, ID_B);
         }
         tc_commit(bar(B_DSFREE + b));
         tc_commit(bar(B_INEMPTY + s));
       }
-      tc_commit(bar(B_ACC));
+      __syncwarp();
+      if (++s == ST) s = 0;
     }
+    if (elect_one()) tc_commit(bar(B_ACC));
+    __syncwarp();
   } else if (warp >= 4) {
     const int wg = (warp - 4) >> 2;                  // inner columns [wg*32, wg*32+32)
     const int q4 = warp & 3;

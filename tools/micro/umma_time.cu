@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128) k(long long* out, int reps) {
   }
   tc_fence_before(); __syncthreads(); tc_fence_after();
   const uint32_t tmem = tslot;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
     constexpr uint32_t idesc = idesc_f16(128, N) | ((mode & 2) ? (1u << 16) : 0u);
     uint64_t ad[8], bd[8];
 #pragma unroll
@@ -35,14 +35,17 @@ __global__ void __launch_bounds__(128) k(long long* out, int reps) {
     for (int r = 0; r < reps; ++r) {
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
+        if (elect_one()) {
         if (mode & 1) asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 1;" ::"r"(tmem + 256), "r"(tmem + ks * 8), "l"(bd[ks]), "r"(idesc) : "memory");
         else asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(tmem + 256), "l"(ad[ks]), "l"(bd[ks]), "r"(idesc) : "memory");
+        }
       }
     }
-    tc_commit(bar);
+    if (elect_one()) tc_commit(bar);
+    __syncwarp();
     mbar_wait(bar, 0);
     long long t1 = clock64();
-    out[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
   }
   tc_fence_before(); __syncthreads();
   if (threadIdx.x < 32) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory"); }
