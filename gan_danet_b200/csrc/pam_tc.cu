@@ -581,10 +581,18 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_XFREE + b));
+      if (MODE == 0) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float L = MODE == 0 ? L_row : lr[col0 + i] * LOG2E;
-        x[i] = ex2(fmaf(x[i], LOG2E, -L));            // P (<= 1)
+        for (int i = 0; i < 32; ++i) x[i] = ex2(fmaf(x[i], LOG2E, -L_row));            // P (<= 1)
+      } else {
+        // lse of the 32 inner rows of this warp group: warp-uniform addresses, fetched as 8 x 128-bit broadcasts (not 32 scalar loads)
+        const float4* l4 = reinterpret_cast<const float4*>(lr + col0);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 Lv = l4[i4];
+          x[4 * i4] = ex2(fmaf(x[4 * i4], LOG2E, -Lv.x * LOG2E)); x[4 * i4 + 1] = ex2(fmaf(x[4 * i4 + 1], LOG2E, -Lv.y * LOG2E));
+          x[4 * i4 + 2] = ex2(fmaf(x[4 * i4 + 2], LOG2E, -Lv.z * LOG2E)); x[4 * i4 + 3] = ex2(fmaf(x[4 * i4 + 3], LOG2E, -Lv.w * LOG2E));
+        }
       }
       mbar_wait(bar(B_YFULL + b), (t >> 1) & 1);
       tc_fence_after();
@@ -594,12 +602,20 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_YFREE + b));
       uint32_t ds_pk[16], p_pk[16];
+      const float4* r4 = reinterpret_cast<const float4*>(lr + TI + col0);
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float r0 = MODE == 0 ? rd_row : lr[TI + col0 + i], r1 = MODE == 0 ? rd_row : lr[TI + col0 + i + 1];
-        __nv_bfloat162 dsv = __floats2bfloat162_rn(x[i] * (y[i] - r0), x[i + 1] * (y[i + 1] - r1));
-        ds_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&dsv);
-        if (MODE == 1) { __nv_bfloat162 pv = __floats2bfloat162_rn(x[i], x[i + 1]); p_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pv); }
+      for (int i = 0; i < 32; i += 4) {
+        float4 rv = make_float4(rd_row, rd_row, rd_row, rd_row);
+        if (MODE == 1) rv = r4[i >> 2];
+        __nv_bfloat162 dsa = __floats2bfloat162_rn(x[i] * (y[i] - rv.x), x[i + 1] * (y[i + 1] - rv.y));
+        __nv_bfloat162 dsb = __floats2bfloat162_rn(x[i + 2] * (y[i + 2] - rv.z), x[i + 3] * (y[i + 3] - rv.w));
+        ds_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&dsa);
+        ds_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&dsb);
+        if (MODE == 1) {
+          __nv_bfloat162 pa = __floats2bfloat162_rn(x[i], x[i + 1]), pb = __floats2bfloat162_rn(x[i + 2], x[i + 3]);
+          p_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pa);
+          p_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&pb);
+        }
       }
       if (t >= 2) mbar_wait(bar(B_DSFREE + b), ((t >> 1) - 1) & 1);
       // K-major SWIZZLE_128B tile [128 rows][64]: row r at (r>>3)*1024 + (r&7)*128, 16-byte chunk index XOR (r&7)
