@@ -1,6 +1,6 @@
 // Position-attention core as ONE fused flash-style kernel for sm_100a:
 //   TMA (cp.async.bulk.tensor) -> shared memory -> tcgen05.mma (kind::f16, fp32 accumulate in TMEM) -> online softmax
-//   on tcgen05.ld'ed score tiles -> P (fp16, written back to TMEM) -> tcgen05.mma P.V (A operand from TMEM) -> epilogue
+//   on tcgen05.ld'ed score tiles -> P (bf16, written back to TMEM) -> tcgen05.mma P.V (A operand from TMEM) -> epilogue
 //   y = gamma * O / l + x,  lse.
 // The N x N attention map of the reference (torch.bmm + softmax + torch.bmm at /root/reference/models/generator.py:115-122)
 // never leaves the SM.
@@ -15,9 +15,12 @@
 // The two groups ping-pong: while one is in its MUFU-bound exp phase the other does its latency-bound phase (row maximum, P
 // store, fences), so the exp units and the tensor pipe stay busy.  A row's maximum is thread-local (no cross-group exchange);
 // what the groups share is the per-row REFERENCE maximum in shared memory, handed over warp-to-warp (mbarrier) in tile order.
-// The reference starts 2^8 above the first tile's maximum and is raised lazily (only when a tile exceeds it by 2^15, so
-// P < 65504 in fp16; dominant terms stay fp16-normal); the raising thread rescales its row of O in TMEM after the previous P.V
-// has landed.  In steady state no rescale happens.
+// The reference starts 2^32 above the first tile's maximum and is raised lazily (only when a tile exceeds it by 2^64: P is bf16, so
+// its 8 exponent bits cover the whole window); the raising thread rescales its row of O in TMEM after the previous P.V has landed.
+// With a reference that tracked the maximum closely (fp16 P, window 2^15) the real activations of the network (|logit| ~ 100)
+// raised it in 8-14 % of the tiles and each raise stalls on the tensor pipe (ncu, profiles/r01_pam_fwd_notes.txt).
+// V carries a channel of ones at column C: the softmax denominator l is the P.V product's column C, i.e. the sum of the SAME rounded
+// bf16 weights the numerator uses (a one-hot row returns its value row exactly), and no row sum is accumulated in the softmax threads.
 // TMEM columns: four score buffers S[u] = [64u, 64u+64), O [256,448).  P never touches shared memory: a group writes its fp16 P
 // tile back into the first 32 columns of the tile's own score buffer (tcgen05.st) and the P.V product takes its A operand from
 // TMEM (with P staged in shared memory the kernel is bound by shared-memory bandwidth: ncu showed tensor-pipe + LSU + TMA
@@ -27,7 +30,7 @@
 // products have separate issuing warps: a single warp's serial instruction stream (waits, descriptor adds, issue, commits) was
 // the kernel's critical path at ~900 cycles per 64 keys.
 // Epilogue: O/l is staged through shared memory (the drained V ring) so that x is read and o, y are written as whole rows.
-// Operands: fp16 (bf16 logits are 8x worse), d zero-padded to 32, C zero-padded to 192.
+// Operands: Q, K fp16 (bf16 logits are 8x worse), d zero-padded to 32; P, V bf16, C zero-padded to 192 (C < 192).
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
 
@@ -57,8 +60,9 @@ constexpr int NTHREADS = 384;
 constexpr uint32_t COL_O = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
-constexpr float RESCALE_TAU = 15.f;    // raise the reference when a tile maximum exceeds it by 2^15 (P stays below the fp16 maximum)
-constexpr float REF_MARGIN = 8.f;      // ... and then put it 2^8 ABOVE that maximum, so that a slowly growing row maximum rarely triggers again
+constexpr float RESCALE_TAU = 64.f;    // raise the reference when a tile maximum exceeds it by 2^64 (P is bf16: 8 exponent bits)
+constexpr float REF_MARGIN = 32.f;     // ... and then put it 2^32 ABOVE that maximum: with real activations (|logit| ~ 100) a reference that
+                                       // tracks the maximum closely is raised in ~10 % of the tiles, each time stalling on the tensor pipe
 
 // barrier slots (8 bytes each) inside OFF_BAR
 enum { BAR_Q = 0, BAR_KFULL = 1, BAR_KEMPTY = BAR_KFULL + KS, BAR_VFULL = BAR_KEMPTY + KS, BAR_VEMPTY = BAR_VFULL + VS,
@@ -128,7 +132,7 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     }
   } else if (warp == 1) {
     // ---- P.V issuer: the whole warp runs the loop (uniform control flow and descriptors), one elected lane issues
-    constexpr uint32_t IDESC_PV = idesc_f16(TQ, CPAD) | (1u << 16);   // bit 16: B is MN-major
+    constexpr uint32_t IDESC_PV = idesc_f16(TQ, CPAD) | (1u << 7) | (1u << 10) | (1u << 16);   // A = P and B = V are bf16; bit 16: B is MN-major
     const uint64_t vd_base = smem_desc_mn(base + OFF_V, V_CHUNK, 1024, LAYOUT_SW128);     // 64-channel groups 8 KB apart, 8-key groups 1 KB apart
     const uint32_t tmem_o = tmem + COL_O;
     int st = 0; uint32_t ph = 0;
@@ -184,7 +188,7 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
     float* mref = reinterpret_cast<float*>(sm + OFF_MREF);
     const uint32_t my_mref_bar = bar(BAR_MREF + g * 4 + q4), peer_mref_bar = bar(BAR_MREF + (g ^ 1) * 4 + q4);
-    float m_loc = -INFINITY, l = 0.f;
+    float m_loc = -INFINITY;
     int nwait = 0;
     for (int t = g; t < T; t += 2) {
       const int u = t & 3;
@@ -203,7 +207,7 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         mbar_wait(my_mref_bar, nwait & 1);
         ++nwait;
         const float m_sh = mref[row];
-        if (m_sh != m_loc) { l *= ex2(m_loc - m_sh); m_loc = m_sh; }
+        m_loc = m_sh;
         const bool changed = mt > m_loc + RESCALE_TAU;
         if (__any_sync(0xffffffffu, changed)) {
           // raise the reference: rescale this row of O once P_{t-1} V_{t-1} (and everything before it) has landed
@@ -221,7 +225,6 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             tmem_st32(ta, ov);
           }
           tmem_wait_st();
-          l *= f;
           m_loc = m_new;
         }
       } else {
@@ -232,19 +235,18 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(peer_mref_bar);
       }
-      // P = exp2(S*log2e - m_ref) in fp16 (two keys per 32-bit TMEM column), row sum in fp32
+      // P = exp2(S*log2e - m_ref) in bf16 (two keys per 32-bit TMEM column).  The row sum is NOT accumulated here: V carries a
+      // channel of ones (column C), so l = sum of the ROUNDED P comes out of the P.V product itself -- numerator and denominator
+      // of the softmax see the same bf16 weights, and 64 additions per tile leave the softmax threads' instruction stream
       uint32_t packed[32];
-      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
         const float p0 = ex2(fmaf(__uint_as_float(a[e]), LOG2E, -m_loc)), p1 = ex2(fmaf(__uint_as_float(a[e + 1]), LOG2E, -m_loc));
         const float p2 = ex2(fmaf(__uint_as_float(b[e]), LOG2E, -m_loc)), p3 = ex2(fmaf(__uint_as_float(b[e + 1]), LOG2E, -m_loc));
-        l0 += p0 + p1; l1 += p2 + p3;
-        __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+        __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1), h23 = __floats2bfloat162_rn(p2, p3);
         packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h01);
         packed[16 + (e >> 1)] = *reinterpret_cast<uint32_t*>(&h23);
       }
-      l += l0 + l1;
       tmem_st32_u(s_addr, packed);                       // P columns [0,32) of S[u]: every S column has been read
       tmem_wait_st();
       tc_fence_before();
@@ -254,14 +256,10 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     // ---- epilogue: o = O / l, y = gamma*o + x, lse
     asm volatile("bar.sync 1, 256;" ::: "memory");           // the last reference has been published
     const float m_fin = (((T - 1) & 1) == g) ? m_loc : mref[row];   // decided by the group that owned the last tile
-    if (m_fin != m_loc) l *= ex2(m_loc - m_fin);
-    float* ls = reinterpret_cast<float*>(sm + OFF_LS);
-    ls[g * 128 + row] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float ltot = ls[row] + ls[128 + row];
-    const float inv = 1.f / ltot;
     mbar_wait(bar(BAR_PVDONE + ((T - 1) & 3)), ((T - 1) >> 2) & 1);
     tc_fence_after();
+    const float ltot = tmem_ld1(tmem + lane_addr + COL_O + p.C);    // the ones channel of V: sum of the bf16 softmax weights of this row
+    const float inv = 1.f / ltot;
     const size_t row0 = (size_t)sample * p.N + (size_t)qtile * TQ;
     if (g == 0) p.lse[row0 + row] = (m_fin + log2f(ltot)) * LN2;
     float* stg = reinterpret_cast<float*>(sm + OFF_V);       // the V ring is drained: all P.V products have completed
@@ -295,21 +293,29 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   }
 }
 
-// ---- operand packing: fp32 NHWC slices -> fp16 tensor-core operands.  One warp per row: lanes 0-3 write the four 16-byte chunks of
-// Q[row][0..32), lanes 4-7 those of K, lanes 8-31 the 24 chunks of V[row][0..192) (zero beyond d / C).
+// ---- operand packing: fp32 NHWC slices -> tensor-core operands.  One warp per row: lanes 0-3 write the four 16-byte chunks of
+// Q[row][0..32) (fp16), lanes 4-7 those of K (fp16), lanes 8-31 the 24 chunks of V[row][0..192) (bf16; zero beyond C except the
+// channel of ones at column C, which makes the P.V product deliver the softmax denominator).
 __global__ void __launch_bounds__(256) pack_qkv_kernel(const float* __restrict__ q, const float* __restrict__ k, int qk_pitch, int d, const float* __restrict__ v, int v_pitch,
-                                                       int C, __half* __restrict__ Qh, __half* __restrict__ Kh, __half* __restrict__ Vh, long long rows) {
+                                                       int C, __half* __restrict__ Qh, __half* __restrict__ Kh, __nv_bfloat16* __restrict__ Vb, long long rows) {
   const int lane = threadIdx.x & 31;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const float* src; __half* dst; int pitch, lim, c0, width;
-  if (lane < 4) { src = q; dst = Qh; pitch = qk_pitch; lim = d; c0 = lane * 8; width = DPAD; }
-  else if (lane < 8) { src = k; dst = Kh; pitch = qk_pitch; lim = d; c0 = (lane - 4) * 8; width = DPAD; }
-  else { src = v; dst = Vh; pitch = v_pitch; lim = C; c0 = (lane - 8) * 8; width = CPAD; }
   for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
-    __align__(16) __half h[8];
+    if (lane < 8) {
+      const float* src = lane < 4 ? q : k;
+      __half* dst = lane < 4 ? Qh : Kh;
+      const int c0 = (lane & 3) * 8;
+      __align__(16) __half h[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(c0 + e < lim ? __ldg(src + (size_t)r * pitch + c0 + e) : 0.f);
-    *reinterpret_cast<uint4*>(dst + (size_t)r * width + c0) = *reinterpret_cast<const uint4*>(h);
+      for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(c0 + e < d ? __ldg(src + (size_t)r * qk_pitch + c0 + e) : 0.f);
+      *reinterpret_cast<uint4*>(dst + (size_t)r * DPAD + c0) = *reinterpret_cast<const uint4*>(h);
+    } else {
+      const int c0 = (lane - 8) * 8;
+      __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = __float2bfloat16_rn(c0 + e < C ? __ldg(v + (size_t)r * v_pitch + c0 + e) : (c0 + e == C ? 1.f : 0.f));
+      *reinterpret_cast<uint4*>(Vb + (size_t)r * CPAD + c0) = *reinterpret_cast<const uint4*>(h);
+    }
   }
 }
 __global__ void __launch_bounds__(256) pack_qk_kernel(const float* __restrict__ src, int pitch, int d, __half* __restrict__ dst, long long rows) {
@@ -321,14 +327,15 @@ __global__ void __launch_bounds__(256) pack_qk_kernel(const float* __restrict__ 
 }
 
 // 2-D fp16 row-major tensor [rows][cols]; box = [box_rows][box_cols]
-static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle sw) {
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle sw,
+                    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("pam_tc: cuTensorMapEncodeTiled unavailable"); return GDN_ECUDA; }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {cols * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+  CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("pam_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return GDN_ECUDA; }
   return GDN_OK;
@@ -353,7 +360,7 @@ extern "C" size_t gdn_pam_tc_fwd_ws_bytes(const gdn_pam_fwd_args* a) {
 
 extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
   GDN_CHECK_ARG(a->precision == GDN_PREC_FP16);
-  GDN_CHECK_ARG(a->N % TQ == 0 && a->d <= DPAD && a->C <= CPAD && a->C % 4 == 0);
+  GDN_CHECK_ARG(a->N % TQ == 0 && a->d <= DPAD && a->C < CPAD && a->C % 4 == 0);      // C < CPAD: column C of V is the channel of ones
   GDN_CHECK_ARG(a->x_pitch % 4 == 0 && a->y_pitch % 4 == 0);
   GDN_CHECK_ARG(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->y & 15) == 0 && ((uintptr_t)a->o & 15) == 0);
   if (!a->ws || a->ws_bytes < gdn_pam_tc_fwd_ws_bytes(a)) { set_error("gdn_pam_fwd(fp16): workspace too small"); return GDN_EWORKSPACE; }
@@ -361,16 +368,16 @@ extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
   char* w = reinterpret_cast<char*>(a->ws);
   __half* Qh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
   __half* Kh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
-  __half* Vh = reinterpret_cast<__half*>(w);
+  __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(w);
   cudaStream_t st = as_stream(s);
   const long long pb = cdiv((long long)rows, 8);
-  pack_qkv_kernel<<<(unsigned)(pb < 16 * kNumSMs ? pb : 16 * kNumSMs), 256, 0, st>>>(a->q, a->k, a->qk_pitch, a->d, a->v, a->v_pitch, a->C, Qh, Kh, Vh, (long long)rows);
+  pack_qkv_kernel<<<(unsigned)(pb < 16 * kNumSMs ? pb : 16 * kNumSMs), 256, 0, st>>>(a->q, a->k, a->qk_pitch, a->d, a->v, a->v_pitch, a->C, Qh, Kh, Vb, (long long)rows);
   GDN_CHECK_LAUNCH();
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_map(&mq, Qh, rows, DPAD, TQ, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
   if ((rc = make_map(&mk, Kh, rows, DPAD, TK, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
-  if ((rc = make_map(&mv, Vh, rows, CPAD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  if ((rc = make_map(&mv, Vb, rows, CPAD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) != GDN_OK) return rc;
   FwdParams p;
   p.x = a->x; p.x_pitch = a->x_pitch; p.gamma = a->gamma; p.o = a->o; p.y = a->y; p.y_pitch = a->y_pitch; p.lse = a->lse;
   p.B = a->B; p.N = a->N; p.C = a->C; p.tiles_per_sample = a->N / TQ;
