@@ -90,6 +90,7 @@ SIGNATURES = {
     "gdn_conv2d_suggest_splits": (_i, [C.POINTER(ConvArgs)]),
     "gdn_wgrad_suggest_splits": (_i, [C.POINTER(WgradArgs)]),
     "gdn_pack_act_bf16": (_i, [_vp, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _i, _f, _vp]),
+    "gdn_pack_actgrad_bf16": (_i, [_vp, _i, _vp, _i, _ll, _i, _vp, _vp, _i, _f, _vp]),
     "gdn_pack_weight_bf16_elems": (_sz, [_i, _i, _i, _i, _i]),
     "gdn_pack_weight_bf16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "gdn_conv2d_tc": (_i, [C.POINTER(ConvTcArgs), _vp]),

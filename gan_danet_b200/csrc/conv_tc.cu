@@ -524,9 +524,11 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ ws, int splits,
 }
 
 // ------------------------------------------------------------------------------------------------ operand packing
-// fp32 NHWC slice -> bf16 [M][Cp] (Cp = round_up(C, 8), zero padded): hi = bf16(v), lo = bf16(v - hi); v = act(x*scale+shift)
+// fp32 NHWC slice -> bf16 [M][Cp] (Cp = round_up(C, 8), zero padded): hi = bf16(v), lo = bf16(v - hi); v = act(x*scale+shift), or with a
+// gate tensor v = x * act'(gate) (activation backward fused into the operand packing of the data/weight gradient: the fp32 dz is never stored)
 __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, int pitch, long long M, int C, int Cp, __nv_bfloat16* __restrict__ hi,
-                                                       __nv_bfloat16* __restrict__ lo, const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope) {
+                                                       __nv_bfloat16* __restrict__ lo, const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope,
+                                                       const float* __restrict__ gate, int gate_pitch) {
   const int groups = Cp >> 3;
   const long long total = M * groups;
   const bool vec = (pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
@@ -537,7 +539,17 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
     const float* src = x + (size_t)m * pitch + c0;
     __align__(16) __nv_bfloat16 h[8];
     __align__(16) __nv_bfloat16 l[8];
-    float vals[8];
+    float vals[8], gvals[8];
+    if (gate) {
+      const float* gs = gate + (size_t)m * gate_pitch + c0;
+      if ((gate_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0 && c0 + 8 <= C) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gs)), g1 = __ldg(reinterpret_cast<const float4*>(gs) + 1);
+        gvals[0] = g0.x; gvals[1] = g0.y; gvals[2] = g0.z; gvals[3] = g0.w; gvals[4] = g1.x; gvals[5] = g1.y; gvals[6] = g1.z; gvals[7] = g1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gvals[e] = c0 + e < C ? __ldg(gs + e) : 0.f;
+      }
+    }
     if (vec && c0 + 8 <= C) {     // 16-byte aligned rows: two 128-bit loads
       const float4 q0 = __ldg(reinterpret_cast<const float4*>(src)), q1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
       vals[0] = q0.x; vals[1] = q0.y; vals[2] = q0.z; vals[3] = q0.w; vals[4] = q1.x; vals[5] = q1.y; vals[6] = q1.z; vals[7] = q1.w;
@@ -549,6 +561,7 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
     for (int e = 0; e < 8; ++e) {
       float v = vals[e];
       if (scale && c0 + e < C) v = apply_act(fmaf(v, __ldg(scale + c0 + e), __ldg(shift + c0 + e)), act, slope);
+      if (gate && c0 + e < C) v *= act_grad(gvals[e], act, slope);
       h[e] = __float2bfloat16_rn(v);
       l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e]));
     }
@@ -633,7 +646,20 @@ extern "C" int gdn_pack_act_bf16(const float* x, int x_pitch, int x_c0, long lon
   const int Cp = (C + 7) & ~7;
   const long long total = M * (Cp / 8);
   const int blocks = (int)(cdiv(total, 256) < 16 * kNumSMs ? cdiv(total, 256) : 16 * kNumSMs);
-  pack_act_kernel<<<blocks, 256, 0, as_stream(s)>>>(x + x_c0, x_pitch, M, C, Cp, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), scale, shift, act, slope);
+  pack_act_kernel<<<blocks, 256, 0, as_stream(s)>>>(x + x_c0, x_pitch, M, C, Cp, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), scale, shift, act, slope, nullptr, 0);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" int gdn_pack_actgrad_bf16(const float* dy, int dy_pitch, const float* y, int y_pitch, long long M, int C, uint16_t* hi, uint16_t* lo, int act, float slope,
+                                     gdn_stream_t s) {
+  GDN_CHECK_ARG(dy && y && hi && M > 0 && C > 0 && dy_pitch >= C && y_pitch >= C);
+  GDN_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0);
+  const int Cp = (C + 7) & ~7;
+  const long long total = M * (Cp / 8);
+  const int blocks = (int)(cdiv(total, 256) < 16 * kNumSMs ? cdiv(total, 256) : 16 * kNumSMs);
+  pack_act_kernel<<<blocks, 256, 0, as_stream(s)>>>(dy, dy_pitch, M, C, Cp, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), nullptr, nullptr, act, slope,
+                                                    y, y_pitch);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

@@ -270,11 +270,17 @@ def _frozen_conv(tape: E.Tape, x: E.Var, wk: Tuple[torch.Tensor, Tuple], bias: t
     def bwd():
         if y.g is None or not x.needs_grad:
             return
+        tgt, acc = x.grad_target()
+        Cin = x.t.shape[-1]
+        if relu and E.conv_backward_tc_only(O, Cin, 3, 3, 1, H, W, H, W, False, True):
+            # ReLU backward fused into the packing of the data-gradient GEMM's operand: the fp32 dz is never stored
+            E.conv_backward(cctx, None, x.t, w, pad=1, gx=tgt, gx_accumulate=acc, frozen_key=key,
+                            dz_packed=E.pack_actgrad(y.g, y.t, ACT_RELU, 0.0), out_hw=(H, W))
+            return
         dz = y.g
         if relu:
             dz = torch.empty_like(y.g)
             E.act_bwd(y.g, y.t, dz, ACT_RELU, 0.0)
-        tgt, acc = x.grad_target()
         E.conv_backward(cctx, dz, x.t, w, pad=1, gx=tgt, gx_accumulate=acc, frozen_key=key)
 
     tape.push(bwd)

@@ -116,6 +116,10 @@ int gdn_wgrad_suggest_splits(const gdn_wgrad_args* a);
  * (BatchNorm + ReLU applied while packing), else v = x.  lo may be NULL. */
 int gdn_pack_act_bf16(const float* x, int x_pitch, int x_c0, long long M, int C, uint16_t* hi, uint16_t* lo,
                       const float* scale, const float* shift, int act, float slope, gdn_stream_t s);
+/* dz = dy * act'(y) packed directly (activation backward of a fused conv+ReLU/LeakyReLU, generator.py / losses.py:58 VGG ReLUs, fused
+ * into the operand packing of the gradient GEMMs: the fp32 dz of autograd is never materialised) */
+int gdn_pack_actgrad_bf16(const float* dy, int dy_pitch, const float* y, int y_pitch, long long M, int C, uint16_t* hi, uint16_t* lo,
+                          int act, float slope, gdn_stream_t s);
 /* OIHW fp32 weight (input channels [i_c0, i_c0+I) of I_total) -> bf16 [kh*kw][R][Kp]:
  * transposed == 0: R = O, Kp = round_up(I, 8) (forward operand); transposed == 1: R = I, Kp = round_up(O, 8) (data gradient). */
 size_t gdn_pack_weight_bf16_elems(int O, int I, int kh, int kw, int transposed);
