@@ -424,7 +424,7 @@ constexpr int OFF_TSLOT = OFF_BARS + 256;
 constexpr int SMEM = OFF_TSLOT + 16 + 1024;
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
 enum { B_OUT = 0, B_INFULL = 1, B_INEMPTY = B_INFULL + ST, B_XFULL = B_INEMPTY + ST, B_YFULL = B_XFULL + 2, B_XFREE = B_YFULL + 2, B_YFREE = B_XFREE + 2,
-       B_DSFULL = B_YFREE + 2, B_DSFREE = B_DSFULL + 2, B_ACC = B_DSFREE + 2, B_COUNT = B_ACC + 1 };
+       B_DSFULL = B_YFREE + 2, B_DSFREE = B_DSFULL + 2, B_ACC = B_DSFREE + 2, B_OCT = B_ACC + 1, B_COUNT = B_OCT + 1 };
 static_assert(B_COUNT * 8 <= 256, "barrier area");
 constexpr uint32_t COL_X = 0, COL_Y = 128, COL_SMALL = 256, COL_BIG = 288;
 
@@ -475,6 +475,7 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       mbar_init(bar(B_DSFULL + i), 8); mbar_init(bar(B_DSFREE + i), 1);
     }
     mbar_init(bar(B_ACC), 1);
+    mbar_init(bar(B_OCT), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -519,7 +520,11 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     auto issue_xy = [&](int t, int s, uint32_t ph) {
       const int b = t & 1;
       mbar_wait_spin(bar(B_INFULL + s), ph);
-      if (t >= 2) { mbar_wait_spin(bar(B_XFREE + b), ((t >> 1) - 1) & 1); mbar_wait_spin(bar(B_YFREE + b), ((t >> 1) - 1) & 1); }
+      if (t >= 2) {
+        mbar_wait_spin(bar(B_XFREE + b), ((t >> 1) - 1) & 1);
+        // MODE 0: Y[b] holds dS_{t-2} until dQ += dS_{t-2} K has read it; that product was issued before this one (same pipe, issue order)
+        if (MODE == 1) mbar_wait_spin(bar(B_YFREE + b), ((t >> 1) - 1) & 1);
+      }
       tc_fence_after();
       const uint32_t st_off = (uint32_t)(OFF_IN + s * IN_BYTES) >> 4;
       const uint64_t iqk_d = d64 + st_off + (IN_IQK >> 4), ic_d = d128 + st_off + (IN_IC >> 4);
@@ -532,13 +537,19 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t ad = oc_d + (uint64_t)(c * (OC_CHUNK >> 4) + ks * 2), bd = ic_d + (uint64_t)(c * (IC_CHUNK >> 4) + ks * 2);
-            if (c == 0 && ks == 0) umma_f16_i<0>(tmem + COL_Y + b * TI, ad, bd, ID_Y); else umma_f16_i<1>(tmem + COL_Y + b * TI, ad, bd, ID_Y);
+            if (MODE == 0) {      // A = dy_i from TMEM (copied there once per CTA): 16 channels = 8 columns per step
+              const uint32_t at = tmem + COL_BIG + (c * 4 + ks) * 8;
+              if (c == 0 && ks == 0) umma_f16_ts_i<0>(tmem + COL_Y + b * TI, at, bd, ID_Y); else umma_f16_ts_i<1>(tmem + COL_Y + b * TI, at, bd, ID_Y);
+            } else {
+              if (c == 0 && ks == 0) umma_f16_i<0>(tmem + COL_Y + b * TI, ad, bd, ID_Y); else umma_f16_i<1>(tmem + COL_Y + b * TI, ad, bd, ID_Y);
+            }
           }
         tc_commit(bar(B_YFULL + b));
       }
       __syncwarp();
     };
     mbar_wait_spin(bar(B_OUT), 0);
+    if (MODE == 0) mbar_wait_spin(bar(B_OCT), 0);           // dy_i has been copied into TMEM by the softmax warps
     issue_xy(0, 0, 0);
     int s = 0, s1 = 1 % ST; uint32_t ph1 = (1 / ST) & 1;       // (stage, phase) of block t and of block t+1
     for (int t = 0; t < T; ++t) {
@@ -551,9 +562,18 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       const uint64_t ds_d = d128 + (uint64_t)((OFF_DS + b * TILE_BYTES) >> 4), it_d = d128 + st_off + (IN_IT >> 4);
       if (elect_one()) {
         // small accumulator += dS (K-major over the 64 inner rows) x inner^T tile [32][64]
-        umma_f16(tmem + COL_SMALL, ds_d, it_d, ID_S, t > 0 ? 1u : 0u);
+        if (MODE == 0) {
+          // A = dS from TMEM, written by the softmax warps in place of Y[b]: keys [32w, 32w+32) of warp group w at columns [32w, 32w+16)
+          const uint32_t ya = tmem + COL_Y + b * TI;
+          umma_f16_ts(tmem + COL_SMALL, ya, it_d, ID_S, t > 0 ? 1u : 0u);
+          umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 8, it_d + 2, ID_S);
+          umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 32, it_d + 4, ID_S);
+          umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 40, it_d + 6, ID_S);
+        } else {
+          umma_f16(tmem + COL_SMALL, ds_d, it_d, ID_S, t > 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 1; ks < TI / 16; ++ks) umma_f16_i<1>(tmem + COL_SMALL, ds_d + ks * 2, it_d + ks * 2, ID_S);
+          for (int ks = 1; ks < TI / 16; ++ks) umma_f16_i<1>(tmem + COL_SMALL, ds_d + ks * 2, it_d + ks * 2, ID_S);
+        }
         if (MODE == 1) {
           // dV += P^T x dy_i: B = the [64 q][192 ch] dy tile read MN-major (16 rows = 2 KB per step)
           const uint64_t ps_d = d128 + (uint64_t)((OFF_PS + b * TILE_BYTES) >> 4), icmn_d = dmn + st_off + (IN_IC >> 4);
@@ -576,7 +596,28 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
     const int col0 = wg * 32;
     float L_row = 0.f, rd_row = 0.f;
-    if (MODE == 0) { L_row = __ldg(p.lse + row0 + row) * LOG2E; rd_row = __ldg(p.rowdot + row0 + row); }
+    if (MODE == 0) {
+      L_row = __ldg(p.lse + row0 + row) * LOG2E; rd_row = __ldg(p.rowdot + row0 + row);
+      // dy_i (outer tile, loop invariant, A operand of Y = dy_i V_j^T) goes to TMEM once: with A in shared memory every one of the
+      // 12 MMAs of a block re-reads its 4 KB A slice (49 instead of 33 cycles each, and the shared-memory pipe is the kernel's bound).
+      // Thread = row; warp group w copies 16-byte pieces 4w..4w+3 of each 128-byte swizzled row chunk: 8 bf16 = 4 TMEM columns per piece.
+      mbar_wait(bar(B_OUT), 0);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const uint8_t* src = sm + OFF_OC + c * OC_CHUNK + (row >> 3) * 1024 + (row & 7) * 128;
+        uint32_t v[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 q = *reinterpret_cast<const uint4*>(src + (((wg * 4 + j) ^ (row & 7)) << 4));
+          v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        }
+        tmem_st16_u(tmem + lane_addr + COL_BIG + c * 32 + wg * 16, v);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_OCT));
+    }
     for (int t = 0; t < T; ++t) {
       const int b = t & 1, s = t % ST;
       const float* lr = reinterpret_cast<const float*>(sm + OFF_IN + s * IN_BYTES + IN_LR);
@@ -607,7 +648,7 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       tmem_ld32(tmem + lane_addr + COL_Y + b * TI + col0, y);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_YFREE + b));
+      if (MODE == 1 && lane == 0) mbar_arrive(bar(B_YFREE + b));
       uint32_t ds_pk[16], p_pk[16];
       const float4* r4 = reinterpret_cast<const float4*>(lr + TI + col0);
 #pragma unroll
@@ -623,6 +664,15 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
           p_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pa);
           p_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&pb);
         }
+      }
+      if (MODE == 0) {
+        // dS goes back to TMEM over this warp group's own (already consumed) Y columns: A operand of dQ += dS K, no shared-memory round trip
+        tmem_st16_u(tmem + lane_addr + COL_Y + b * TI + col0, ds_pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_DSFULL + b));
+        continue;
       }
       if (t >= 2) mbar_wait(bar(B_DSFREE + b), ((t >> 1) - 1) & 1);
       // K-major SWIZZLE_128B tile [128 rows][64]: row r at (r>>3)*1024 + (r&7)*128, 16-byte chunk index XOR (r&7)
