@@ -471,8 +471,8 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     for (int i = 0; i < ST; ++i) { mbar_init(bar(B_INFULL + i), 1); mbar_init(bar(B_INEMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(B_XFULL + i), 1); mbar_init(bar(B_YFULL + i), 1);
-      mbar_init(bar(B_XFREE + i), 8); mbar_init(bar(B_YFREE + i), 8);
-      mbar_init(bar(B_DSFULL + i), 8); mbar_init(bar(B_DSFREE + i), 1);
+      mbar_init(bar(B_XFREE + i), 4); mbar_init(bar(B_YFREE + i), 4);          // 4 warps: buffer i belongs to softmax warp group i
+      mbar_init(bar(B_DSFULL + i), 4); mbar_init(bar(B_DSFREE + i), 1);
     }
     mbar_init(bar(B_ACC), 1);
     mbar_init(bar(B_OCT), 8);
@@ -563,12 +563,12 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       if (elect_one()) {
         // small accumulator += dS (K-major over the 64 inner rows) x inner^T tile [32][64]
         if (MODE == 0) {
-          // A = dS from TMEM, written by the softmax warps in place of Y[b]: keys [32w, 32w+32) of warp group w at columns [32w, 32w+16)
+          // A = dS from TMEM, written by the owning softmax warp group in place of Y[b]: 64 keys = columns [0, 32)
           const uint32_t ya = tmem + COL_Y + b * TI;
           umma_f16_ts(tmem + COL_SMALL, ya, it_d, ID_S, t > 0 ? 1u : 0u);
           umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 8, it_d + 2, ID_S);
-          umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 32, it_d + 4, ID_S);
-          umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 40, it_d + 6, ID_S);
+          umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 16, it_d + 4, ID_S);
+          umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 24, it_d + 6, ID_S);
         } else {
           umma_f16(tmem + COL_SMALL, ds_d, it_d, ID_S, t > 0 ? 1u : 0u);
 #pragma unroll
@@ -590,11 +590,10 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     if (elect_one()) tc_commit(bar(B_ACC));
     __syncwarp();
   } else if (warp >= 4) {
-    const int wg = (warp - 4) >> 2;                  // inner columns [wg*32, wg*32+32)
+    const int wg = (warp - 4) >> 2;                  // warp group: owns the inner blocks (and X/Y buffers) of parity wg
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;                  // TMEM lane = outer row
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    const int col0 = wg * 32;
     float L_row = 0.f, rd_row = 0.f;
     if (MODE == 0) {
       L_row = __ldg(p.lse + row0 + row) * LOG2E; rd_row = __ldg(p.rowdot + row0 + row);
@@ -618,75 +617,75 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_OCT));
     }
-    for (int t = 0; t < T; ++t) {
-      const int b = t & 1, s = t % ST;
+    // The two warp groups ping-pong on alternate inner blocks (group w owns the X/Y buffers of parity w and all 64 columns of its
+    // blocks, 32 at a time): while one group is in its MUFU-bound exp phase the other loads Y, forms dS and hands it to the MMA warp.
+    for (int t = wg; t < T; t += 2) {
+      const int b = wg, s = t % ST;
       const float* lr = reinterpret_cast<const float*>(sm + OFF_IN + s * IN_BYTES + IN_LR);
       if (MODE == 1) mbar_wait(bar(B_INFULL + s), (t / ST) & 1);   // lse/rowdot of the inner rows are in this stage
       mbar_wait(bar(B_XFULL + b), (t >> 1) & 1);
       tc_fence_after();
-      float x[32];
-      tmem_ld32(tmem + lane_addr + COL_X + b * TI + col0, x);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_XFREE + b));
-      if (MODE == 0) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = ex2(fmaf(x[i], LOG2E, -L_row));            // P (<= 1)
-      } else {
-        // lse of the 32 inner rows of this warp group: warp-uniform addresses, fetched as 8 x 128-bit broadcasts (not 32 scalar loads)
-        const float4* l4 = reinterpret_cast<const float4*>(lr + col0);
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 Lv = l4[i4];
-          x[4 * i4] = ex2(fmaf(x[4 * i4], LOG2E, -Lv.x * LOG2E)); x[4 * i4 + 1] = ex2(fmaf(x[4 * i4 + 1], LOG2E, -Lv.y * LOG2E));
-          x[4 * i4 + 2] = ex2(fmaf(x[4 * i4 + 2], LOG2E, -Lv.z * LOG2E)); x[4 * i4 + 3] = ex2(fmaf(x[4 * i4 + 3], LOG2E, -Lv.w * LOG2E));
-        }
-      }
-      mbar_wait(bar(B_YFULL + b), (t >> 1) & 1);
-      tc_fence_after();
-      float y[32];
-      tmem_ld32(tmem + lane_addr + COL_Y + b * TI + col0, y);
-      tc_fence_before();
-      __syncwarp();
-      if (MODE == 1 && lane == 0) mbar_arrive(bar(B_YFREE + b));
-      uint32_t ds_pk[16], p_pk[16];
-      const float4* r4 = reinterpret_cast<const float4*>(lr + TI + col0);
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 rv = make_float4(rd_row, rd_row, rd_row, rd_row);
-        if (MODE == 1) rv = r4[i >> 2];
-        __nv_bfloat162 dsa = __floats2bfloat162_rn(x[i] * (y[i] - rv.x), x[i + 1] * (y[i + 1] - rv.y));
-        __nv_bfloat162 dsb = __floats2bfloat162_rn(x[i + 2] * (y[i + 2] - rv.z), x[i + 3] * (y[i + 3] - rv.w));
-        ds_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&dsa);
-        ds_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&dsb);
-        if (MODE == 1) {
-          __nv_bfloat162 pa = __floats2bfloat162_rn(x[i], x[i + 1]), pb = __floats2bfloat162_rn(x[i + 2], x[i + 3]);
-          p_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pa);
-          p_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&pb);
-        }
-      }
-      if (MODE == 0) {
-        // dS goes back to TMEM over this warp group's own (already consumed) Y columns: A operand of dQ += dS K, no shared-memory round trip
-        tmem_st16_u(tmem + lane_addr + COL_Y + b * TI + col0, ds_pk);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_DSFULL + b));
-        continue;
-      }
-      if (t >= 2) mbar_wait(bar(B_DSFREE + b), ((t >> 1) - 1) & 1);
-      // K-major SWIZZLE_128B tile [128 rows][64]: row r at (r>>3)*1024 + (r&7)*128, 16-byte chunk index XOR (r&7)
+      if (MODE == 1 && t >= 2) mbar_wait(bar(B_DSFREE + b), ((t >> 1) - 1) & 1);       // the shared-memory dS / P tiles of block t-2 have been consumed
       uint8_t* drow = sm + OFF_DS + b * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
       uint8_t* prow = sm + OFF_PS + b * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int ch = ((wg * 4 + c) ^ (row & 7)) << 4;
-        *reinterpret_cast<uint4*>(drow + ch) = make_uint4(ds_pk[4 * c], ds_pk[4 * c + 1], ds_pk[4 * c + 2], ds_pk[4 * c + 3]);
-        if (MODE == 1) *reinterpret_cast<uint4*>(prow + ch) = make_uint4(p_pk[4 * c], p_pk[4 * c + 1], p_pk[4 * c + 2], p_pk[4 * c + 3]);
+      for (int h = 0; h < 2; ++h) {
+        const int col0 = h * 32;
+        float x[32];
+        tmem_ld32(tmem + lane_addr + COL_X + b * TI + col0, x);
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = ex2(fmaf(x[i], LOG2E, -L_row));            // P (<= 1)
+        } else {
+          // lse of 32 inner rows: warp-uniform addresses, fetched as 8 x 128-bit broadcasts (not 32 scalar loads)
+          const float4* l4 = reinterpret_cast<const float4*>(lr + col0);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 Lv = l4[i4];
+            x[4 * i4] = ex2(fmaf(x[4 * i4], LOG2E, -Lv.x * LOG2E)); x[4 * i4 + 1] = ex2(fmaf(x[4 * i4 + 1], LOG2E, -Lv.y * LOG2E));
+            x[4 * i4 + 2] = ex2(fmaf(x[4 * i4 + 2], LOG2E, -Lv.z * LOG2E)); x[4 * i4 + 3] = ex2(fmaf(x[4 * i4 + 3], LOG2E, -Lv.w * LOG2E));
+          }
+        }
+        if (h == 0) { mbar_wait(bar(B_YFULL + b), (t >> 1) & 1); tc_fence_after(); }
+        float y[32];
+        tmem_ld32(tmem + lane_addr + COL_Y + b * TI + col0, y);
+        uint32_t ds_pk[16], p_pk[16];
+        const float4* r4 = reinterpret_cast<const float4*>(lr + TI + col0);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 rv = make_float4(rd_row, rd_row, rd_row, rd_row);
+          if (MODE == 1) rv = r4[i >> 2];
+          __nv_bfloat162 dsa = __floats2bfloat162_rn(x[i] * (y[i] - rv.x), x[i + 1] * (y[i + 1] - rv.y));
+          __nv_bfloat162 dsb = __floats2bfloat162_rn(x[i + 2] * (y[i + 2] - rv.z), x[i + 3] * (y[i + 3] - rv.w));
+          ds_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&dsa);
+          ds_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&dsb);
+          if (MODE == 1) {
+            __nv_bfloat162 pa = __floats2bfloat162_rn(x[i], x[i + 1]), pb = __floats2bfloat162_rn(x[i + 2], x[i + 3]);
+            p_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pa);
+            p_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&pb);
+          }
+        }
+        if (MODE == 0) {
+          // dS goes back to TMEM over already consumed Y columns (keys [32h, 32h+32) -> columns [16h, 16h+16)): A operand of dQ += dS K
+          tmem_st16_u(tmem + lane_addr + COL_Y + b * TI + h * 16, ds_pk);
+        } else {
+          // K-major SWIZZLE_128B tile [128 rows][64]: row r at (r>>3)*1024 + (r&7)*128, 16-byte chunk index XOR (r&7)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int ch = ((h * 4 + c) ^ (row & 7)) << 4;
+            *reinterpret_cast<uint4*>(drow + ch) = make_uint4(ds_pk[4 * c], ds_pk[4 * c + 1], ds_pk[4 * c + 2], ds_pk[4 * c + 3]);
+            *reinterpret_cast<uint4*>(prow + ch) = make_uint4(p_pk[4 * c], p_pk[4 * c + 1], p_pk[4 * c + 2], p_pk[4 * c + 3]);
+          }
+        }
       }
-      fence_async_smem();
+      if (MODE == 0) tmem_wait_st(); else fence_async_smem();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_DSFULL + b));
+      if (lane == 0) {
+        mbar_arrive(bar(B_XFREE + b));
+        if (MODE == 1) mbar_arrive(bar(B_YFREE + b));
+        mbar_arrive(bar(B_DSFULL + b));
+      }
     }
     // ---- epilogue
     mbar_wait(bar(B_ACC), 0);
