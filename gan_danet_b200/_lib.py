@@ -149,6 +149,7 @@ SIGNATURES = {
     "gdn_ssim_ws_bytes": (_sz, [_i, _i, _i]),
     "gdn_ssim": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "gdn_adamw": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "gdn_adamw_multi": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "gdn_fill": (_i, [_vp, _ll, _f, _vp]),
 }
 

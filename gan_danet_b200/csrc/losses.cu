@@ -175,6 +175,24 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     } else { p[i] = pv[0]; m[i] = mv[0]; v[i] = vv[0]; }
   }
 }
+// Many small tensors in one launch (the generator has ~100 parameter tensors of 24 .. 500 K elements: one launch each is pure launch
+// latency).  blockIdx.y = tensor, blockIdx.x strides over it.  Same arithmetic as adamw_kernel, scalar accesses (no alignment demands).
+constexpr int kAdamMulti = 64;
+struct AdamMultiP { float* p[kAdamMulti]; const float* g[kAdamMulti]; float* m[kAdamMulti]; float* v[kAdamMulti]; int n[kAdamMulti]; };
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const __grid_constant__ AdamMultiP t, AdamP a) {
+  const int k = blockIdx.y;
+  float* __restrict__ p = t.p[k]; const float* __restrict__ g = t.g[k]; float* __restrict__ m = t.m[k]; float* __restrict__ v = t.v[k];
+  const int n = t.n[k];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float gr = g[i] * a.grad_scale;
+    const float pp = p[i] * (1.f - a.lr * a.wd);
+    const float mm = m[i] + (gr - m[i]) * (1.f - a.beta1);
+    const float v2 = v[i] * a.beta2 + (1.f - a.beta2) * gr * gr;
+    const float denom = sqrtf(v2) / a.bc2_sqrt + a.eps;
+    p[i] = pp - a.step_size * (mm / denom);
+    m[i] = mm; v[i] = v2;
+  }
+}
 }  // namespace gdn
 
 using namespace gdn;
@@ -245,6 +263,33 @@ extern "C" int gdn_ssim(const float* a, const float* b, int B, int H, int W, flo
   GDN_CHECK_LAUNCH();
   finish_kernel<<<1, 256, 0, as_stream(s)>>>(partial, blocks, 1.0 / ((double)B * H * W), 0.0, out, 0);
   GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" int gdn_adamw_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, float lr, float beta1,
+                               float beta2, float eps, float wd, int step, float grad_scale, gdn_stream_t s) {
+  GDN_CHECK_ARG(count > 0 && p && g && m && v && n && step >= 1);
+  AdamP a;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = wd; a.grad_scale = grad_scale;
+  double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  a.step_size = (float)((double)lr / bc1);
+  a.bc2_sqrt = (float)sqrt(bc2);
+  for (int i0 = 0; i0 < count; i0 += kAdamMulti) {
+    AdamMultiP t;
+    const int c = count - i0 < kAdamMulti ? count - i0 : kAdamMulti;
+    long long nmax = 0;
+    for (int i = 0; i < c; ++i) {
+      GDN_CHECK_ARG(p[i0 + i] && g[i0 + i] && m[i0 + i] && v[i0 + i] && n[i0 + i] > 0 && n[i0 + i] < (1ll << 31));
+      t.p[i] = p[i0 + i]; t.g[i] = g[i0 + i]; t.m[i] = m[i0 + i]; t.v[i] = v[i0 + i]; t.n[i] = (int)n[i0 + i];
+      if (n[i0 + i] > nmax) nmax = n[i0 + i];
+    }
+    for (int i = c; i < kAdamMulti; ++i) { t.p[i] = nullptr; t.g[i] = nullptr; t.m[i] = nullptr; t.v[i] = nullptr; t.n[i] = 0; }
+    long long bx = cdiv(nmax, 256 * 8);
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    adamw_multi_kernel<<<dim3((unsigned)bx, (unsigned)c), 256, 0, as_stream(s)>>>(t, a);
+    GDN_CHECK_LAUNCH();
+  }
   return GDN_OK;
 }
 

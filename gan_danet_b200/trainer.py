@@ -37,11 +37,15 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = 1.0
 
+    SMALL = 1 << 20
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        import ctypes as C
         for group in self.param_groups:
             b1, b2 = group["betas"]
+            small = {}          # step -> list of (p, g, m, v, n): tensors below SMALL share one launch per 64 (gdn_adamw_multi)
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -53,9 +57,18 @@ class FusedAdamW(torch.optim.Optimizer):
                 st["step"] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 assert p.is_contiguous()
+                if p.numel() < self.SMALL:
+                    small.setdefault(int(st["step"]), []).append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), p, g))
+                    continue
                 L.check(E._lib(p).gdn_adamw(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
                                             float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
                                             int(st["step"]), float(self.grad_scale), E._stream()), "gdn_adamw")
+            for step_no, items in small.items():
+                k = len(items)
+                arr = lambda j: (C.c_void_p * k)(*[it[j] for it in items])  # noqa: E731
+                ns = (C.c_longlong * k)(*[it[4] for it in items])
+                L.check(E._lib(items[0][5]).gdn_adamw_multi(k, arr(0), arr(1), arr(2), arr(3), ns, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                                            float(group["weight_decay"]), step_no, float(self.grad_scale), E._stream()), "gdn_adamw_multi")
         return loss
 
 

@@ -333,6 +333,10 @@ int gdn_ssim(const float* a, const float* b, int B, int H, int W, float* out, vo
 /* torch.optim.AdamW (GAN_DANet_train.ipynb:182-183) over a flat arena; grad_scale folds the 1/world of DP. step is 1-based. */
 int gdn_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd,
               int step, float grad_scale, gdn_stream_t s);
+/* the same update for `count` tensors (arrays of device pointers and element counts in HOST memory; each n < 2^31) with common hyper-parameters and
+ * step: one launch per 64 tensors instead of one per tensor (the generator's ~100 small parameter tensors) */
+int gdn_adamw_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, float lr, float beta1,
+                    float beta2, float eps, float wd, int step, float grad_scale, gdn_stream_t s);
 int gdn_fill(float* p, long long n, float value, gdn_stream_t s);
 
 #ifdef __cplusplus
