@@ -257,15 +257,25 @@ def run_ours(args):
                      "share_of_step": tot_ms / ms}
     notes = {"conv_tc_fwd_kernel": "tcgen05 implicit-GEMM convolution, forward + data gradient (all layers of G, D, VGG19)",
              "conv_tc_wgrad_kernel": "tcgen05 weight gradient (MN-major operands) incl. its split-K reduction",
-             "pam_flash_fwd_kernel": "fused tcgen05 PAM forward incl. fp16 operand packing",
+             "pam_flash_fwd_kernel": "fused tcgen05 PAM forward incl. operand packing (Q, K fp16; P, V bf16)",
              "pam_flash_bwd_kernel": "fused tcgen05 PAM backward (dQ launch + dK/dV launch) incl. rowdot and operand packing"}
+
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, family mean) from the committed ncu pass of the same step
+    # (profiles/r01_dram_traffic.json, written by tools/aggregate_traffic.py); null when the file or the family is missing
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+        traffic = {k: v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"] for k, v in tj["families"].items()}
+    except Exception:
+        pass
 
     def roof(fam):
         f = fams.get(fam)
         if not f or not f["tflops"]:
             return None
         return {"kernel": fam + " (" + notes.get(fam, "") + ")", "bound": "tensor", "achieved": f["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": f["tflops"] / peak_tf, "traffic": None, "peak_source": peak_src, "launches": f["launches"],
+                "frac": f["tflops"] / peak_tf, "traffic": traffic.get(fam), "traffic_unit": "bytes of DRAM traffic per launch (ncu, family mean)",
+                "peak_source": peak_src, "launches": f["launches"],
                 "mean_launch_ms": f["ms_per_step"] * args.steps / f["launches"], "share_of_step": f["share_of_step"]}
 
     if args.kernel_detail and rank == 0:
@@ -286,7 +296,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (hi+lo split)", "fp32": "fp32"}[args.conv_precision] + " operands, fp32 accumulate; fp32 activation storage"
-                         + ("; PAM core fp16 operands" if args.pam_precision == "fp16" else ""),
+                         + ("; PAM core fp16 logits, bf16 P/V" if args.pam_precision == "fp16" else ""),
                 "data": "synthetic (seeded smooth random fields, random-init weights, random-init VGG19)",
                 "config": {"workload": workload_name(args, h, w), "global_batch": world * B, "parallelism": f"dp{world}", "conv": args.conv_precision,
                            "pam": "fused tcgen05 flash forward + backward" if args.pam_precision == "fp16" else "fp32 engine",
