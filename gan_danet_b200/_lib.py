@@ -46,7 +46,7 @@ class ConvTcArgs(C.Structure):
                 ("res", _vp), ("res_pitch", _i), ("res_c0", _i),
                 ("B", _i), ("Hi", _i), ("Wi", _i), ("Cin", _i), ("Ho", _i), ("Wo", _i), ("Cout", _i),
                 ("kh", _i), ("kw", _i), ("stride", _i), ("pad", _i), ("transposed", _i),
-                ("act", _i), ("slope", _f), ("precision", _i), ("alpha_ptr", _vp), ("groups", _i)]
+                ("act", _i), ("slope", _f), ("precision", _i), ("alpha_ptr", _vp), ("groups", _i), ("y16", _vp), ("y16_pitch", _i)]
 
 
 class WgradTcArgs(C.Structure):
@@ -91,6 +91,7 @@ SIGNATURES = {
     "gdn_wgrad_suggest_splits": (_i, [C.POINTER(WgradArgs)]),
     "gdn_pack_act_bf16": (_i, [_vp, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _i, _f, _vp]),
     "gdn_pack_actgrad_bf16": (_i, [_vp, _i, _vp, _i, _ll, _i, _vp, _vp, _i, _f, _vp]),
+    "gdn_pack_actgrad_bf16g": (_i, [_vp, _i, _vp, _i, _ll, _i, _vp, _vp, _i, _f, _vp]),
     "gdn_pack_weight_bf16_elems": (_sz, [_i, _i, _i, _i, _i]),
     "gdn_pack_weight_bf16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "gdn_conv2d_tc": (_i, [C.POINTER(ConvTcArgs), _vp]),
@@ -105,6 +106,7 @@ SIGNATURES = {
     "gdn_linear_tc_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "gdn_thin_conv_supported": (_i, [_i, _i, _i]),
     "gdn_thin_conv_expand": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "gdn_thin_conv_expand_p": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "gdn_thin_conv_reduce": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_thin_conv_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "gdn_thin_conv_wgrad": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
@@ -126,6 +128,8 @@ SIGNATURES = {
     "gdn_bicubic_down_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_maxpool2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_maxpool2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "gdn_maxpool2_fwd_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "gdn_maxpool2_bwd_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_pam_fwd_ws_bytes": (_sz, [C.POINTER(PamFwdArgs)]),
     "gdn_pam_fwd": (_i, [C.POINTER(PamFwdArgs), _vp]),
     "gdn_pam_bwd_ws_bytes": (_sz, [C.POINTER(PamBwdArgs)]),

@@ -55,6 +55,7 @@ struct TapList { int n; int dh[9], dw[9], widx[9]; };
 
 struct FwdParams {
   float* y; int y_pitch; const float* bias; const float* res; int res_pitch; const float* alpha_ptr;
+  __nv_bfloat16* y16; int y16_pitch;   // optional bf16 copy of the output = the next convolution's packed operand (y may then be NULL)
   int imgs_per_group, taps_total;   // per-sample weights (CAM): weight tap coordinate = tap + (img / imgs_per_group) * taps_total
   int B, Ho, Wo, Cout;        // output tensor (pixels are written at (i*os + oh0, j*os + ow0))
   int Hc, Wc, os, oh0, ow0;   // extent of the tile grid and the output scatter
@@ -276,15 +277,13 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int img = t;
       const int ab = lt & 1;
-      long long yoff[8], roff[8];                              // element offsets of this lane's 8 rows (-1: outside the image)
+      long long pixi[8];                                       // output pixel index of this lane's 8 rows (-1: outside the image)
 #pragma unroll
       for (int i8 = 0; i8 < 8; ++i8) {
         const int row = q * 32 + 4 * i8 + rsub;
         const int i = th * p.Ht + (row >> p.wt_shift), j = tw * p.Wt + (row & (p.Wt - 1));
         const long long pix = ((long long)img * p.Ho + (i * p.os + p.oh0)) * p.Wo + (j * p.os + p.ow0);
-        const bool ok = i < p.Hc && j < p.Wc;
-        yoff[i8] = ok ? pix * p.y_pitch : -1;
-        roff[i8] = pix * p.res_pitch;
+        pixi[i8] = (i < p.Hc && j < p.Wc) ? pix : -1;
       }
       mbar_wait(acc_full(ab), (lt >> 1) & 1);
       tc_fence_after();
@@ -310,7 +309,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
           if (p.res) {     // all residual loads first (res may alias y: they must not be serialised behind the stores)
 #pragma unroll
             for (int i8 = 0; i8 < 8; ++i8)
-              rr[i8] = (n_ok && yoff[i8] >= 0) ? *reinterpret_cast<const float4*>(p.res + roff[i8] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              rr[i8] = (n_ok && pixi[i8] >= 0) ? *reinterpret_cast<const float4*>(p.res + pixi[i8] * p.res_pitch + n) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
@@ -319,17 +318,23 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
             o.x = apply_act(fmaf(alpha, o.x, bb.x), p.act, p.slope); o.y = apply_act(fmaf(alpha, o.y, bb.y), p.act, p.slope);
             o.z = apply_act(fmaf(alpha, o.z, bb.z), p.act, p.slope); o.w = apply_act(fmaf(alpha, o.w, bb.w), p.act, p.slope);
             if (p.res) { o.x += rr[i8].x; o.y += rr[i8].y; o.z += rr[i8].z; o.w += rr[i8].w; }
-            if (n_ok && yoff[i8] >= 0) *reinterpret_cast<float4*>(p.y + yoff[i8] + n) = o;
+            if (n_ok && pixi[i8] >= 0) {
+              if (p.y) *reinterpret_cast<float4*>(p.y + pixi[i8] * p.y_pitch + n) = o;
+              if (p.y16) {
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+                *reinterpret_cast<uint2*>(p.y16 + pixi[i8] * p.y16_pitch + n) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+              }
+            }
           }
         } else {
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int r = 4 * i8 + rsub;
             const float4 o4 = *reinterpret_cast<const float4*>(stg + r * 32 + ((cj ^ (r & 7)) << 2));
-            if (!(n_ok && yoff[i8] >= 0)) continue;
+            if (!(n_ok && pixi[i8] >= 0)) continue;
             const float ov[4] = {o4.x, o4.y, o4.z, o4.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
-            float* yp = p.y + yoff[i8] + n;
-            const float* rp = p.res ? p.res + roff[i8] + n : nullptr;
+            float* yp = p.y + pixi[i8] * p.y_pitch + n;
+            const float* rp = p.res ? p.res + pixi[i8] * p.res_pitch + n : nullptr;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               if (n + u < p.Cout) yp[u] = apply_act(fmaf(alpha, ov[u], bv[u]), p.act, p.slope) + (rp ? rp[u] : 0.f);
@@ -528,7 +533,7 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ ws, int splits,
 // gate tensor v = x * act'(gate) (activation backward fused into the operand packing of the data/weight gradient: the fp32 dz is never stored)
 __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, int pitch, long long M, int C, int Cp, __nv_bfloat16* __restrict__ hi,
                                                        __nv_bfloat16* __restrict__ lo, const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope,
-                                                       const float* __restrict__ gate, int gate_pitch) {
+                                                       const float* __restrict__ gate, int gate_pitch, const __nv_bfloat16* __restrict__ gate16) {
   const int groups = Cp >> 3;
   const long long total = M * groups;
   const bool vec = (pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
@@ -540,7 +545,12 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
     __align__(16) __nv_bfloat16 h[8];
     __align__(16) __nv_bfloat16 l[8];
     float vals[8], gvals[8];
-    if (gate) {
+    if (gate16) {            // bf16 gate with pitch gate_pitch (a multiple of 8, 16-byte aligned rows): only its sign / zero-ness matters
+      const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gate16 + (size_t)m * gate_pitch + c0));
+      const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&gq);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gvals[e] = __bfloat162float(gh[e]);
+    } else if (gate) {
       const float* gs = gate + (size_t)m * gate_pitch + c0;
       if ((gate_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0 && c0 + 8 <= C) {
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gs)), g1 = __ldg(reinterpret_cast<const float4*>(gs) + 1);
@@ -561,7 +571,7 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
     for (int e = 0; e < 8; ++e) {
       float v = vals[e];
       if (scale && c0 + e < C) v = apply_act(fmaf(v, __ldg(scale + c0 + e), __ldg(shift + c0 + e)), act, slope);
-      if (gate && c0 + e < C) v *= act_grad(gvals[e], act, slope);
+      if ((gate || gate16) && c0 + e < C) v *= act_grad(gvals[e], act, slope);
       h[e] = __float2bfloat16_rn(v);
       l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e]));
     }
@@ -646,7 +656,7 @@ extern "C" int gdn_pack_act_bf16(const float* x, int x_pitch, int x_c0, long lon
   const int Cp = (C + 7) & ~7;
   const long long total = M * (Cp / 8);
   const int blocks = (int)(cdiv(total, 256) < 16 * kNumSMs ? cdiv(total, 256) : 16 * kNumSMs);
-  pack_act_kernel<<<blocks, 256, 0, as_stream(s)>>>(x + x_c0, x_pitch, M, C, Cp, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), scale, shift, act, slope, nullptr, 0);
+  pack_act_kernel<<<blocks, 256, 0, as_stream(s)>>>(x + x_c0, x_pitch, M, C, Cp, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), scale, shift, act, slope, nullptr, 0, nullptr);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
@@ -659,7 +669,20 @@ extern "C" int gdn_pack_actgrad_bf16(const float* dy, int dy_pitch, const float*
   const long long total = M * (Cp / 8);
   const int blocks = (int)(cdiv(total, 256) < 16 * kNumSMs ? cdiv(total, 256) : 16 * kNumSMs);
   pack_act_kernel<<<blocks, 256, 0, as_stream(s)>>>(dy, dy_pitch, M, C, Cp, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), nullptr, nullptr, act, slope,
-                                                    y, y_pitch);
+                                                    y, y_pitch, nullptr);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" int gdn_pack_actgrad_bf16g(const float* dy, int dy_pitch, const uint16_t* y16, int y16_pitch, long long M, int C, uint16_t* hi, uint16_t* lo, int act,
+                                      float slope, gdn_stream_t s) {
+  GDN_CHECK_ARG(dy && y16 && hi && M > 0 && C > 0 && dy_pitch >= C && y16_pitch >= ((C + 7) & ~7) && y16_pitch % 8 == 0);
+  GDN_CHECK_ARG(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)y16 & 15) == 0);
+  const int Cp = (C + 7) & ~7;
+  const long long total = M * (Cp / 8);
+  const int blocks = (int)(cdiv(total, 256) < 16 * kNumSMs ? cdiv(total, 256) : 16 * kNumSMs);
+  pack_act_kernel<<<blocks, 256, 0, as_stream(s)>>>(dy, dy_pitch, M, C, Cp, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), nullptr, nullptr, act, slope,
+                                                    nullptr, y16_pitch, reinterpret_cast<const __nv_bfloat16*>(y16));
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
@@ -678,17 +701,18 @@ extern "C" int gdn_pack_weight_bf16(const float* w, int O, int I_total, int i_c0
 }
 
 extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
-  GDN_CHECK_ARG(a && a->x_hi && a->w_hi && a->y);
+  GDN_CHECK_ARG(a && a->x_hi && a->w_hi && (a->y || a->y16));
   GDN_CHECK_ARG(a->B > 0 && a->Cin > 0 && a->Cout > 0 && a->kh > 0 && a->kw > 0 && a->kh * a->kw <= 9);
   GDN_CHECK_ARG(a->Hi > 0 && a->Wi > 0 && a->Ho > 0 && a->Wo > 0 && (a->stride == 1 || a->stride == 2));
-  GDN_CHECK_ARG(a->y_pitch >= a->y_c0 + a->Cout && (!a->res || a->res_pitch >= a->res_c0 + a->Cout));
+  GDN_CHECK_ARG((!a->y || a->y_pitch >= a->y_c0 + a->Cout) && (!a->res || a->res_pitch >= a->res_c0 + a->Cout));
   GDN_CHECK_ARG(a->precision == GDN_PREC_BF16 || (a->precision == GDN_PREC_BF16X3 && a->x_lo && a->w_lo));
   GDN_CHECK_ARG(((uintptr_t)a->x_hi & 15) == 0 && ((uintptr_t)a->w_hi & 15) == 0 && ((uintptr_t)a->x_lo & 15) == 0 && ((uintptr_t)a->w_lo & 15) == 0);
   const int nsplit = a->precision == GDN_PREC_BF16X3 ? 3 : 1;
   const int Cp = (a->Cin + 7) & ~7;         // channel pitch of the packed activation AND K pitch of the packed weight
   const int taps = a->kh * a->kw;
   FwdParams p;
-  p.y = a->y + a->y_c0; p.y_pitch = a->y_pitch; p.bias = a->bias;
+  p.y = a->y ? a->y + a->y_c0 : nullptr; p.y_pitch = a->y_pitch; p.bias = a->bias;
+  p.y16 = reinterpret_cast<__nv_bfloat16*>(a->y16); p.y16_pitch = a->y16_pitch;
   p.res = a->res ? a->res + a->res_c0 : nullptr; p.res_pitch = a->res_pitch;
   p.alpha_ptr = a->alpha_ptr;
   const int groups = a->groups > 1 ? a->groups : 1;
@@ -703,8 +727,9 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
   p.nsplit = nsplit;
   p.tmem_cols = 2 * pow2_cols(p.n_tile);        // two accumulator buffers
   p.act = a->act; p.slope = a->slope;
-  p.vec4 = (a->Cout % 4 == 0 && a->y_pitch % 4 == 0 && a->y_c0 % 4 == 0 && ((uintptr_t)a->y & 15) == 0 && (!a->bias || ((uintptr_t)a->bias & 15) == 0) &&
+  p.vec4 = (a->Cout % 4 == 0 && (!a->y || (a->y_pitch % 4 == 0 && a->y_c0 % 4 == 0 && ((uintptr_t)a->y & 15) == 0)) && (!a->bias || ((uintptr_t)a->bias & 15) == 0) &&
             (!a->res || (a->res_pitch % 4 == 0 && a->res_c0 % 4 == 0 && ((uintptr_t)a->res & 15) == 0))) ? 1 : 0;
+  if (a->y16) GDN_CHECK_ARG(p.vec4 && a->y16_pitch % 4 == 0 && a->y16_pitch >= a->Cout && ((uintptr_t)a->y16 & 7) == 0);
   const int ring_budget = SMEM_LIMIT - 2048 - EPI_WARPS * EPI_STAGE_BYTES;     // bytes for the operand ring(s)
   const int sub_bytes = A_BYTES + p.n_tile * 128;
   // K-iterations per pipeline stage: narrow tiles (2*n_tile MMA cycles per K-iteration) amortise the mbarrier round trip over a group

@@ -5,6 +5,7 @@
 // torchvision vgg19.features used by models/losses.py:58.
 // Semantics: source index (dst+0.5)*ratio-0.5, cubic A=-0.75 with border-clamped taps,
 // bilinear source clamped at 0.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace gdn {
@@ -364,6 +365,61 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restri
     }
   }
 }
+// bf16 activations (the frozen VGG19 branch keeps its untapped feature maps in bf16 only): 8 channels = 16 bytes per thread
+__device__ __forceinline__ void bf16x8_to_float(const uint4& q, float* f) {
+  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(h[e]);
+}
+__global__ void __launch_bounds__(256) maxpool2_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C) {
+  const int Cv = C >> 3, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cv) << 3; long long r = idx / Cv;
+    const int ox = (int)(r % Wo); r /= Wo; const int oy = (int)(r % Ho); const int b = (int)(r / Ho);
+    const __nv_bfloat16* p = x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + c;
+    float a[8], bb[8], cc[8], d[8];
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p)), a); bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p + C)), bb);
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p + (size_t)W * C)), cc); bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p + (size_t)W * C + C)), d);
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(fmaxf(fmaxf(a[e], bb[e]), fmaxf(cc[e], d[e])));
+    *reinterpret_cast<uint4*>(y + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+// dx (fp32) of the bf16 pooling input: the gradient goes to the first maximum in scan order; even H, W
+__global__ void __launch_bounds__(256) maxpool2_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
+  const int Cv = C >> 2, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cv) << 2; long long r = idx / Cv;
+    const int ox = (int)(r % Wo); r /= Wo; const int oy = (int)(r % Ho); const int b = (int)(r / Ho);
+    const size_t p00 = (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + c;
+    float v[4][4];
+    const size_t offs[4] = {p00, p00 + (size_t)C, p00 + (size_t)W * C, p00 + (size_t)W * C + C};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(x + offs[k]));
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[k][e] = __bfloat162float(h[e]);
+    }
+    const float4 g = *reinterpret_cast<const float4*>(dy + (((size_t)b * Ho + oy) * Wo + ox) * C + c);
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+    float d[4][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float m = v[0][e]; int a = 0;
+      if (v[1][e] > m) { m = v[1][e]; a = 1; }
+      if (v[2][e] > m) { m = v[2][e]; a = 2; }
+      if (v[3][e] > m) { a = 3; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d[k][e] = a == k ? gv[e] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(dx + offs[k]) = make_float4(d[k][0], d[k][1], d[k][2], d[k][3]);
+  }
+}
 // gradient goes to the first maximum in scan order (ATen max_pool2d backward)
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2;
@@ -436,6 +492,19 @@ extern "C" int gdn_maxpool2_fwd(const float* x, float* y, int B, int H, int W, i
   GDN_CHECK_ARG(x && y && B > 0 && H >= 2 && W >= 2 && C > 0);
   if (C % 4 == 0 && al16(x) && al16(y)) maxpool2_fwd_kernel<4><<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 4)), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
   else maxpool2_fwd_kernel<1><<<grid_for((long long)B * (H / 2) * (W / 2) * C), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_maxpool2_fwd_bf16(const uint16_t* x, uint16_t* y, int B, int H, int W, int C, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && y && B > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0 && al16(x) && al16(y));
+  maxpool2_fwd_bf16_kernel<<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8)), 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                                                     reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_maxpool2_bwd_bf16(const uint16_t* x, const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && dy && dx && B > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0 && al16(x) && al16(dy) && al16(dx));
+  maxpool2_bwd_bf16_kernel<<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 4)), 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), dy, dx, B, H, W, C);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

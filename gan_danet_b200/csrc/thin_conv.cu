@@ -11,6 +11,7 @@
 // iteration (four independent 16-byte transactions in flight, S window shared); all index arithmetic is 32-bit.
 // A flipped tap order (the "transposed" uses) is folded into the register copy of the weights:  tap k at offset pad - k  ==  tap
 // 8 - k at offset k - (2 - pad).
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace gdn {
@@ -22,7 +23,8 @@ struct Geo { int B, Hv, Wv, C, Hs, Ws, stride, pad; };
 // STRIDE == 0: run-time stride, one pixel per iteration.  C/4 lanes per pixel, one float4 of channels each.
 template <int STRIDE, int PX>
 __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ S, const float* __restrict__ w, const float* __restrict__ bias, float* V, int v_pitch,
-                                                     const float* res, int res_pitch,   /* res may alias V */ Geo g, int flip, int act, float slope) {
+                                                     const float* res, int res_pitch,   /* res may alias V */ Geo g, int flip, int act, float slope,
+                                                     __nv_bfloat16* __restrict__ V16 /* optional bf16 copy [pixel][C] */) {
   constexpr int NC = STRIDE ? (PX - 1) * STRIDE + 3 : 3;
   const int lanes = g.C >> 2;
   const int c = (threadIdx.x % lanes) << 2;
@@ -69,6 +71,10 @@ __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ S
       acc.x = apply_act(acc.x, act, slope); acc.y = apply_act(acc.y, act, slope); acc.z = apply_act(acc.z, act, slope); acc.w = apply_act(acc.w, act, slope);
       if (res) { const float4 rr = *reinterpret_cast<const float4*>(res + (p + i) * res_pitch + c); acc.x += rr.x; acc.y += rr.y; acc.z += rr.z; acc.w += rr.w; }
       *reinterpret_cast<float4*>(V + (p + i) * v_pitch + c) = acc;
+      if (V16) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
+        *reinterpret_cast<uint2*>(V16 + (p + i) * g.C + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
     }
   }
 }
@@ -268,8 +274,16 @@ static bool thin_ok(int C) { return C == 32 || C == 64 || C == 128; }
 
 extern "C" int gdn_thin_conv_supported(int C, int kh, int kw) { return thin_ok(C) && kh == 3 && kw == 3; }
 
+extern "C" int gdn_thin_conv_expand_p(const float* s_in, const float* w, const float* bias, float* v_out, int v_pitch, const float* res, int res_pitch,
+                                      int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int flip, int act, float slope, uint16_t* v16, gdn_stream_t st);
 extern "C" int gdn_thin_conv_expand(const float* s_in, const float* w, const float* bias, float* v_out, int v_pitch, const float* res, int res_pitch,
                                     int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int flip, int act, float slope, gdn_stream_t st) {
+  return gdn_thin_conv_expand_p(s_in, w, bias, v_out, v_pitch, res, res_pitch, B, Hv, Wv, C, Hs, Ws, stride, pad, flip, act, slope, nullptr, st);
+}
+extern "C" int gdn_thin_conv_expand_p(const float* s_in, const float* w, const float* bias, float* v_out, int v_pitch, const float* res, int res_pitch,
+                                      int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int flip, int act, float slope, uint16_t* v16, gdn_stream_t st) {
+  GDN_CHECK_ARG(((uintptr_t)v16 & 7) == 0);
+  __nv_bfloat16* V16 = reinterpret_cast<__nv_bfloat16*>(v16);
   GDN_CHECK_ARG(s_in && w && v_out && thin_ok(C) && v_pitch >= C && v_pitch % 4 == 0 && ((uintptr_t)v_out & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0));
   GDN_CHECK_ARG(!res || (res_pitch % 4 == 0 && ((uintptr_t)res & 15) == 0));
   GDN_CHECK_ARG((long long)B * Hv * Wv < (1ll << 31) && stride >= 1);
@@ -281,9 +295,9 @@ extern "C" int gdn_thin_conv_expand(const float* s_in, const float* w, const flo
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   if (blocks < 1) blocks = 1;
   cudaStream_t s = as_stream(st);
-  if (px4 && stride == 1) expand_kernel<1, 4><<<(unsigned)blocks, 256, 0, s>>>(s_in, w, bias, v_out, v_pitch, res, res_pitch, g, flip, act, slope);
-  else if (px4) expand_kernel<2, 4><<<(unsigned)blocks, 256, 0, s>>>(s_in, w, bias, v_out, v_pitch, res, res_pitch, g, flip, act, slope);
-  else expand_kernel<0, 1><<<(unsigned)blocks, 256, 0, s>>>(s_in, w, bias, v_out, v_pitch, res, res_pitch, g, flip, act, slope);
+  if (px4 && stride == 1) expand_kernel<1, 4><<<(unsigned)blocks, 256, 0, s>>>(s_in, w, bias, v_out, v_pitch, res, res_pitch, g, flip, act, slope, V16);
+  else if (px4) expand_kernel<2, 4><<<(unsigned)blocks, 256, 0, s>>>(s_in, w, bias, v_out, v_pitch, res, res_pitch, g, flip, act, slope, V16);
+  else expand_kernel<0, 1><<<(unsigned)blocks, 256, 0, s>>>(s_in, w, bias, v_out, v_pitch, res, res_pitch, g, flip, act, slope, V16);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

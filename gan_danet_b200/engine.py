@@ -249,6 +249,24 @@ def pack_actgrad(dy: Tensor, y: Tensor, act: int, slope: float = 0.0) -> Packed:
     return Packed(hi, lo, Cc)
 
 
+def pack_actgrad16(dy: Tensor, y16: Tensor, act: int, slope: float = 0.0) -> Packed:
+    """pack_actgrad with the activation output given as bf16 [M, Cp] (bf16-only feature maps of the frozen VGG19 branch)."""
+    M, Cc = rows_of(dy), dy.shape[-1]
+    Cp = (Cc + 7) // 8 * 8
+    hi = torch.empty((M, Cp), dtype=torch.bfloat16, device=dy.device)
+    L.check(_lib(dy).gdn_pack_actgrad_bf16g(dy.data_ptr(), pitch_of(dy), y16.data_ptr(), y16.shape[-1], M, Cc, hi.data_ptr(), None, act, slope, _stream()),
+            "gdn_pack_actgrad_bf16g")
+    return Packed(hi, None, Cc)
+
+
+bf16_feature_storage: bool = os.environ.get("GDN_BF16_FEATURES", "1") != "0"
+
+
+def bf16_storage_ok() -> bool:
+    """bf16-only feature maps are used where the convolutions round their operands to bf16 anyway (conv precision 'bf16')."""
+    return bf16_feature_storage and conv_precision == "bf16"
+
+
 _frozen_weights: Dict[Tuple, Packed] = {}
 
 
@@ -275,12 +293,18 @@ def pack_weight(w: Tensor, transposed: bool, frozen_key: Optional[Tuple] = None)
 
 
 def conv_tc_raw(xp: Packed, wp: Packed, y: Tensor, in_hw: Tuple[int, int], *, cin: int, kh: int, kw: int, stride: int = 1, pad: int = 0,
-                transposed: bool = False, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0, res: Optional[Tensor] = None) -> None:
-    """Tensor-core convolution on packed operands.  ``in_hw`` is the grid of the packed input operand; y: [B,Ho,Wo,Cout] view."""
+                transposed: bool = False, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0, res: Optional[Tensor] = None,
+                y16: Optional[Tensor] = None, out_shape: Optional[Tuple[int, int, int, int]] = None) -> None:
+    """Tensor-core convolution on packed operands.  ``in_hw`` is the grid of the packed input operand; y: [B,Ho,Wo,Cout] view.
+    ``y16`` ([B*Ho*Wo, Cout] bf16, Cout % 8 == 0) additionally receives the output as the next convolution's packed operand;
+    with ``y`` None (``out_shape`` given) the fp32 output is not written at all."""
     a = L.ConvTcArgs()
-    B, Ho, Wo, Cout = y.shape
+    B, Ho, Wo, Cout = y.shape if y is not None else out_shape
     a.x_hi, a.x_lo, a.w_hi, a.w_lo = xp.hi.data_ptr(), _ptr(xp.lo), wp.hi.data_ptr(), _ptr(wp.lo)
-    a.y, a.y_pitch, a.y_c0 = y.data_ptr(), pitch_of(y), 0
+    if y is not None:
+        a.y, a.y_pitch, a.y_c0 = y.data_ptr(), pitch_of(y), 0
+    if y16 is not None:
+        a.y16, a.y16_pitch = y16.data_ptr(), y16.shape[-1]
     a.bias = _ptr(bias)
     if res is not None:
         a.res, a.res_pitch, a.res_c0 = res.data_ptr(), pitch_of(res), 0
@@ -288,7 +312,7 @@ def conv_tc_raw(xp: Packed, wp: Packed, y: Tensor, in_hw: Tuple[int, int], *, ci
     a.kh, a.kw, a.stride, a.pad, a.transposed = kh, kw, stride, pad, int(transposed)
     a.act, a.slope, a.precision = act, slope, _PREC[conv_precision]
     _timed("conv_tc_fwd_kernel", 2.0 * B * Ho * Wo * Cout * cin * kh * kw / (stride * stride if transposed else 1),
-           lambda: L.check(_lib(y).gdn_conv2d_tc(C.byref(a), _stream()), "gdn_conv2d_tc"),
+           lambda: L.check(_lib(xp.hi).gdn_conv2d_tc(C.byref(a), _stream()), "gdn_conv2d_tc"),
            f"{'dgrad' if transposed else 'fwd'} B{B} {in_hw[0]}x{in_hw[1]}->{Ho}x{Wo} C{cin}->{Cout} k{kh} s{stride}")
 
 
@@ -334,16 +358,25 @@ class ConvCtx:
         self.tc, self.xp = tc, xp
 
 
-def conv_forward(x: Tensor, w: Tensor, y: Tensor, *, stride: int = 1, pad: int = 0, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0,
-                 res: Optional[Tensor] = None, frozen_key: Optional[Tuple] = None, keep: bool = True) -> ConvCtx:
-    """y = act(conv(x, w) + bias) + res for an OIHW weight; dispatches on ``conv_precision``."""
+def conv_forward(x: Tensor, w: Tensor, y: Optional[Tensor], *, stride: int = 1, pad: int = 0, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0,
+                 res: Optional[Tensor] = None, frozen_key: Optional[Tuple] = None, keep: bool = True, x_packed: Optional[Packed] = None,
+                 y16: Optional[Tensor] = None) -> ConvCtx:
+    """y = act(conv(x, w) + bias) + res for an OIHW weight; dispatches on ``conv_precision``.
+    bf16 feature-map storage (frozen VGG19 branch): ``x_packed`` is the already packed input (then ``x`` only supplies the shape),
+    ``y16`` receives the output as bf16 [B*Ho*Wo, O]; ``y`` may be None when only the bf16 copy is wanted (tensor-core path only)."""
     O, I, kh, kw = w.shape
     B, Hi, Wi, Cin = x.shape
-    _, Ho, Wo, _ = y.shape
+    Ho, Wo = (Hi + 2 * pad - kh) // stride + 1, (Wi + 2 * pad - kw) // stride + 1
+    if y is None or x_packed is not None:
+        assert tc_eligible(Cin, O, kh, kw, stride, Ho, Wo) and conv_precision == "bf16" and (y16 is not None or y is not None)
+        xp = x_packed if x_packed is not None else pack_act(x)
+        conv_tc_raw(xp, pack_weight(w, False, frozen_key), y, (Hi, Wi), cin=Cin, kh=kh, kw=kw, stride=stride, pad=pad, bias=bias, act=act, slope=slope, res=res,
+                    y16=y16, out_shape=(B, Ho, Wo, O))
+        return ConvCtx(True, xp if keep else None)
     thin = _thin_kind(Cin, O, kh, kw, stride, x, y, act, bias, res)
     if thin == "expand":          # 1 -> C (Discriminator1.conv1, VGG19 conv1_1 on the channel-summed weight)
-        L.check(_lib(x).gdn_thin_conv_expand(x.data_ptr(), w.contiguous().data_ptr(), _ptr(bias), y.data_ptr(), pitch_of(y), _ptr(res), pitch_of(res) if res is not None else 0,
-                                             B, Ho, Wo, O, Hi, Wi, stride, pad, 0, act, slope, _stream()), "gdn_thin_conv_expand")
+        L.check(_lib(x).gdn_thin_conv_expand_p(x.data_ptr(), w.contiguous().data_ptr(), _ptr(bias), y.data_ptr(), pitch_of(y), _ptr(res), pitch_of(res) if res is not None else 0,
+                                               B, Ho, Wo, O, Hi, Wi, stride, pad, 0, act, slope, _ptr(y16), _stream()), "gdn_thin_conv_expand_p")
         return ConvCtx(False, None)
     if thin == "reduce":          # C -> 1 (the generator's final conv)
         L.check(_lib(x).gdn_thin_conv_reduce(x.data_ptr(), pitch_of(x), w.contiguous().data_ptr(), _ptr(bias), y.data_ptr(), _ptr(res),
@@ -351,7 +384,8 @@ def conv_forward(x: Tensor, w: Tensor, y: Tensor, *, stride: int = 1, pad: int =
         return ConvCtx(False, None)
     if tc_eligible(Cin, O, kh, kw, stride, Ho, Wo):
         xp = pack_act(x)
-        conv_tc_raw(xp, pack_weight(w, False, frozen_key), y, (Hi, Wi), cin=Cin, kh=kh, kw=kw, stride=stride, pad=pad, bias=bias, act=act, slope=slope, res=res)
+        conv_tc_raw(xp, pack_weight(w, False, frozen_key), y, (Hi, Wi), cin=Cin, kh=kh, kw=kw, stride=stride, pad=pad, bias=bias, act=act, slope=slope, res=res,
+                    y16=y16 if conv_precision == "bf16" else None)
         return ConvCtx(True, xp if keep else None)
     if frozen_key is not None:
         key = (frozen_key, "ohwi", w.data_ptr(), w._version)
@@ -916,6 +950,25 @@ def op_maxpool2(tape: Tape, x: Var) -> Var:
 
     tape.push(bwd)
     return y
+
+
+def op_maxpool2_bf16(tape: Tape, x: Var, x16: Tensor) -> Tuple[Var, Tensor]:
+    """MaxPool2d(2, 2) on a bf16-only feature map (x.t is a shape-only placeholder; the gradients of x and y stay fp32)."""
+    lib = _lib(x16)
+    B, H, W, Cc = x.t.shape
+    y = Var(new_nhwc(B, H // 2, W // 2, Cc, x.t), needs_grad=x.needs_grad)
+    y16 = torch.empty((B * (H // 2) * (W // 2), Cc), dtype=torch.bfloat16, device=x16.device)
+    L.check(lib.gdn_maxpool2_fwd_bf16(x16.data_ptr(), y16.data_ptr(), B, H, W, Cc, _stream()), "gdn_maxpool2_fwd_bf16")
+
+    def bwd():
+        if y.g is None or not x.needs_grad:
+            return
+        gx = new_nhwc(B, H, W, Cc, x.t)
+        L.check(lib.gdn_maxpool2_bwd_bf16(x16.data_ptr(), y.g.data_ptr(), gx.data_ptr(), B, H, W, Cc, _stream()), "gdn_maxpool2_bwd_bf16")
+        x.add_grad(gx)
+
+    tape.push(bwd)
+    return y, y16
 
 
 def op_copy(tape: Tape, x: Var, out: Var) -> Var:

@@ -237,7 +237,59 @@ class PerceptualLoss(nn.Module):
             self._wcache[key] = hit
         return hit
 
+    def _bf16_plan(self):
+        """Layer structure check for the bf16 feature-map path: every conv is followed by a ReLU and every tap is such a ReLU.
+        Returns (conv indices whose output must also exist in fp32, index of the last conv) or None."""
+        layers = list(self.vgg)
+        convs = [i for i, l in enumerate(layers) if isinstance(l, nn.Conv2d)]
+        if not convs or any(i + 1 >= len(layers) or not isinstance(layers[i + 1], nn.ReLU) for i in convs):
+            return None
+        if any(not (t >= 1 and isinstance(layers[t], nn.ReLU) and isinstance(layers[t - 1], nn.Conv2d)) for t in self.feature_layers):
+            return None
+        if any(not isinstance(l, (nn.Conv2d, nn.ReLU, nn.MaxPool2d)) for l in layers):
+            return None
+        return {t - 1 for t in self.feature_layers}, convs[-1]
+
+    def _features_bf16(self, tape: E.Tape, x: E.Var, on_feature, plan) -> None:
+        """Same features with bf16-only storage of the untapped maps (conv precision 'bf16': the next conv would round them to bf16
+        anyway): every conv epilogue writes the next conv's packed operand, max-pool runs on bf16, only tapped maps exist in fp32."""
+        fp32_convs, last_conv = plan
+        layers = list(self.vgg)
+        cur, cur16 = x, None
+        for idx, layer in enumerate(layers):
+            if isinstance(layer, nn.Conv2d):
+                # a recorded (gradient-carrying) max-pool routes the gradient to the arg-max of the fp32 map: bf16 rounding creates ties
+                # that "first maximum in scan order" would break differently (measured: 4 % change of dL/dx), so the maps feeding a
+                # pool stay fp32 on the generated branch; the forward-only target branch needs only max VALUES (max and rounding commute)
+                feeds_pool = idx + 2 < len(layers) and isinstance(layers[idx + 2], nn.MaxPool2d)
+                keep32 = idx in fp32_convs or (tape.record and feeds_pool)
+                cur, cur16 = _frozen_conv16(tape, cur, cur16, self._weights(idx, layer, cur.t.shape[-1]), layer.bias.detach(),
+                                            want_fp32=keep32, want_16=idx != last_conv and not (tape.record and feeds_pool))
+            elif isinstance(layer, nn.MaxPool2d):
+                if cur16 is not None:
+                    cur, cur16 = E.op_maxpool2_bf16(tape, cur, cur16)
+                else:
+                    cur = E.op_maxpool2(tape, cur)
+            if idx in self.feature_layers:
+                on_feature(idx, cur)
+
     def _features(self, tape: E.Tape, x: E.Var, on_feature) -> None:
+        plan = self._bf16_plan() if E.bf16_storage_ok() else None
+        if plan is not None:
+            # every conv after the first must take the tensor-core path at its resolution (bf16-only maps have no fp32 fallback)
+            _, H, W, cin = x.t.shape
+            for layer in self.vgg:
+                if isinstance(layer, nn.MaxPool2d):
+                    H, W = H // 2, W // 2
+                elif isinstance(layer, nn.Conv2d):
+                    if cin != 1 and not (E.tc_eligible(cin, layer.out_channels, 3, 3, 1, H, W) and layer.out_channels % 8 == 0 and H % 2 == 0 and W % 2 == 0):
+                        plan = None
+                        break
+                    cin = layer.out_channels
+            if cin == x.t.shape[-1]:
+                plan = None
+        if plan is not None:
+            return self._features_bf16(tape, x, on_feature, plan)
         cur = x
         for idx, layer in enumerate(self.vgg):
             if isinstance(layer, nn.Conv2d):
@@ -285,6 +337,39 @@ def _frozen_conv(tape: E.Tape, x: E.Var, wk: Tuple[torch.Tensor, Tuple], bias: t
 
     tape.push(bwd)
     return y
+
+
+def _frozen_conv16(tape: E.Tape, x: E.Var, x16, wk: Tuple[torch.Tensor, Tuple], bias: torch.Tensor, want_fp32: bool, want_16: bool):
+    """Frozen 3x3 conv + ReLU of the bf16 feature-map path.  x16: the input as bf16 [B*H*W, Cin] (None: pack x.t, or the 1-channel
+    thin kernel).  Returns (Var, bf16 copy or None); without want_fp32 the Var's tensor is a shape-only placeholder that is never
+    written or read (its gradient is a real fp32 tensor)."""
+    w, key = wk
+    O = w.shape[0]
+    B, H, W, Cin = x.t.shape
+    y = E.Var(E.new_nhwc(B, H, W, O, x.t))
+    y16 = torch.empty((B * H * W, O), dtype=torch.bfloat16, device=x.t.device) if want_16 else None
+    thin = Cin == 1
+    if thin:                       # conv1_1 on the channel-summed weight: fp32 thin kernel, optionally emitting the bf16 copy as well
+        want_fp32 = True
+        cctx = E.conv_forward(x.t, w, y.t, pad=1, bias=bias, act=ACT_RELU, frozen_key=key, keep=False, y16=y16)
+    else:
+        cctx = E.conv_forward(x.t, w, y.t if want_fp32 else None, pad=1, bias=bias, act=ACT_RELU, frozen_key=key, keep=False,
+                              x_packed=E.Packed(x16, None, Cin) if x16 is not None else None, y16=y16)
+
+    def bwd():
+        if y.g is None or not x.needs_grad:
+            return
+        tgt, acc = x.grad_target()
+        if thin or not E.conv_backward_tc_only(O, Cin, 3, 3, 1, H, W, H, W, False, True):
+            dz = torch.empty_like(y.g)
+            E.act_bwd(y.g, y.t, dz, ACT_RELU, 0.0)
+            E.conv_backward(cctx, dz, x.t, w, pad=1, gx=tgt, gx_accumulate=acc, frozen_key=key)
+            return
+        dzp = E.pack_actgrad(y.g, y.t, ACT_RELU, 0.0) if want_fp32 else E.pack_actgrad16(y.g, y16, ACT_RELU, 0.0)
+        E.conv_backward(cctx, None, x.t, w, pad=1, gx=tgt, gx_accumulate=acc, frozen_key=key, dz_packed=dzp, out_hw=(H, W))
+
+    tape.push(bwd)
+    return y, y16
 
 
 def _relu(tape: E.Tape, x: E.Var) -> E.Var:

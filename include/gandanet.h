@@ -120,6 +120,9 @@ int gdn_pack_act_bf16(const float* x, int x_pitch, int x_c0, long long M, int C,
  * into the operand packing of the gradient GEMMs: the fp32 dz of autograd is never materialised) */
 int gdn_pack_actgrad_bf16(const float* dy, int dy_pitch, const float* y, int y_pitch, long long M, int C, uint16_t* hi, uint16_t* lo,
                           int act, float slope, gdn_stream_t s);
+/* same with the activation output given as bf16 [M][y16_pitch] (only its sign matters) */
+int gdn_pack_actgrad_bf16g(const float* dy, int dy_pitch, const uint16_t* y16, int y16_pitch, long long M, int C, uint16_t* hi, uint16_t* lo,
+                           int act, float slope, gdn_stream_t s);
 /* OIHW fp32 weight (input channels [i_c0, i_c0+I) of I_total) -> bf16 [kh*kw][R][Kp]:
  * transposed == 0: R = O, Kp = round_up(I, 8) (forward operand); transposed == 1: R = I, Kp = round_up(O, 8) (data gradient). */
 size_t gdn_pack_weight_bf16_elems(int O, int I, int kh, int kw, int transposed);
@@ -143,6 +146,8 @@ typedef struct {
   int precision;
   const float* alpha_ptr; /* device scalar multiplying the accumulator (gamma of CAM, generator.py:139); NULL = 1 */
   int groups;             /* > 1: per-sample weights [groups][kh*kw][R][Kp] for B/groups consecutive samples each (CAM's bmm) */
+  uint16_t* y16; int y16_pitch; /* optional: the output also (or, with y == NULL, only) as bf16 [pixel][y16_pitch] = the packed operand of the
+                                   next convolution (frozen VGG19 branch of losses.py:58-73: untapped feature maps never exist in fp32) */
 } gdn_conv_tc_args;
 int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s);
 /* test hook: enable/disable the halo-reuse variant of the forward kernel (stride-1 3x3, narrow output tiles); returns the old setting */
@@ -194,6 +199,9 @@ int gdn_thin_conv_supported(int C, int kh, int kw);
 /* V = act(sum_k S[v*stride + k - pad] w[c][k] + bias[c]) + res   (flip != 0: S at v + pad - k: data gradient of the C->1 conv) */
 int gdn_thin_conv_expand(const float* s_in, const float* w, const float* bias, float* v_out, int v_pitch, const float* res, int res_pitch,
                          int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int flip, int act, float slope, gdn_stream_t st);
+/* same, additionally writing V as bf16 [pixel][C] when v16 != NULL (packed operand of the next convolution) */
+int gdn_thin_conv_expand_p(const float* s_in, const float* w, const float* bias, float* v_out, int v_pitch, const float* res, int res_pitch,
+                           int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int flip, int act, float slope, uint16_t* v16, gdn_stream_t st);
 /* S = sum_k sum_c V w[c][k] + bias[0] + res   (transposed == 0: C->1 forward, v = s + k - pad; 1: data gradient of the 1->C conv) */
 int gdn_thin_conv_reduce(const float* v_in, int v_pitch, const float* w, const float* bias, float* s_out, const float* res,
                          int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int transposed, gdn_stream_t st);
@@ -248,6 +256,9 @@ int gdn_bicubic_down_nchw_to_nhwc(const float* x, float* y, int y_pitch, int y_c
 /* 2x2/2 max pool (VGG19 features idx 4,9,18; losses.py:58) */
 int gdn_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, gdn_stream_t s);
 int gdn_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s);
+/* the same pooling (VGG19 of losses.py:58) on bf16 feature maps [B,H,W,C], C % 8 == 0; the gradient stays fp32 (even H, W) */
+int gdn_maxpool2_fwd_bf16(const uint16_t* x, uint16_t* y, int B, int H, int W, int C, gdn_stream_t s);
+int gdn_maxpool2_bwd_bf16(const uint16_t* x, const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s);
 
 /* ---------------------------------------------------------------- attention */
 /*

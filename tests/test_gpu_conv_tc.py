@@ -88,3 +88,36 @@ def test_conv_tc(case, precision):
     wtol = tol
     gx_ref = xn.grad.permute(0, 2, 3, 1) + gx0.double()
     assert rel(gx, gx_ref) < wtol, ("dgrad", rel(gx, gx_ref))   # Cout < 16: data gradient on the fp32 engine as well
+
+
+def test_perceptual_bf16_feature_storage():
+    """Frozen VGG19 branch (losses.py:58-73) in conv precision 'bf16': keeping the untapped feature maps in bf16 only (conv epilogue
+    writes the next conv's packed operand, bf16 max-pool, ReLU backward gated by the bf16 map) must reproduce the fp32-storage path:
+    both round the same fp32 values to bf16 at the same places, so loss and input gradient agree to fp32 round-off."""
+    import gan_danet_b200 as P
+    from gan_danet_b200 import engine as E
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    perc = P.PerceptualLoss(pretrained=False, device=torch.device("cpu"))
+    perc.vgg.to(dev)
+    perc.device = dev
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(2, 1, 64, 128, generator=g).to(dev)
+    y = torch.randn(2, 1, 64, 128, generator=g).to(dev)
+    old_prec, old_flag = E.conv_precision, E.bf16_feature_storage
+    res = []
+    try:
+        E.set_conv_precision("bf16")
+        for flag in (False, True):
+            E.bf16_feature_storage = flag
+            x = x0.clone().requires_grad_(True)
+            loss = perc(x, y)
+            loss.backward()
+            torch.cuda.synchronize()
+            res.append((float(loss), x.grad.detach().clone()))
+    finally:
+        E.set_conv_precision(old_prec)
+        E.bf16_feature_storage = old_flag
+    (l0, g0), (l1, g1) = res
+    assert abs(l1 - l0) <= 1e-5 * abs(l0), (l0, l1)
+    assert rel(g1, g0) < 1e-5, rel(g1, g0)
