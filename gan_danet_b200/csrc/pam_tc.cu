@@ -404,7 +404,7 @@ extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
 namespace gdn {
 namespace pamtc {
 namespace bwd {
-constexpr int TO = 128, TI = 64, NCH = CPAD / 64, ST = 3;
+constexpr int TO = 128, TI = 64, NCH = CPAD / 64, ST = 4;
 constexpr int OQK_BYTES = TO * DPAD * 2;              // 8 KB  fp16 [128][32], SWIZZLE_64B
 constexpr int OC_CHUNK = TO * 128;                    // 16 KB bf16 [128][64], SWIZZLE_128B
 constexpr int IQK_BYTES = TI * DPAD * 2;              // 4 KB
@@ -416,15 +416,12 @@ constexpr int OFF_OC = OFF_OQK + OQK_BYTES;           // 8192
 constexpr int OFF_IN = OFF_OC + NCH * OC_CHUNK;       // 57344
 constexpr int IN_IQK = 0, IN_IT = IQK_BYTES, IN_IC = IN_IT + IT_BYTES, IN_LR = IN_IC + NCH * IC_CHUNK;   // 0, 4096, 8192, 32768
 constexpr int IN_BYTES = 33 * 1024;                   // 33280 rounded up to a multiple of 1024
-constexpr int TILE_BYTES = TO * TI * 2;               // 16 KB bf16 [128][64]
-constexpr int OFF_PS = OFF_IN + ST * IN_BYTES;        // 158720
-constexpr int OFF_DS = OFF_PS + 2 * TILE_BYTES;       // 191488
-constexpr int OFF_BARS = OFF_DS + 2 * TILE_BYTES;     // 224256
+constexpr int OFF_BARS = OFF_IN + ST * IN_BYTES;      // 192512 (P and dS never touch shared memory: they go back to TMEM over the consumed X / Y columns)
 constexpr int OFF_TSLOT = OFF_BARS + 256;
 constexpr int SMEM = OFF_TSLOT + 16 + 1024;
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
-enum { B_OUT = 0, B_INFULL = 1, B_INEMPTY = B_INFULL + ST, B_XFULL = B_INEMPTY + ST, B_YFULL = B_XFULL + 2, B_XFREE = B_YFULL + 2, B_YFREE = B_XFREE + 2,
-       B_DSFULL = B_YFREE + 2, B_DSFREE = B_DSFULL + 2, B_ACC = B_DSFREE + 2, B_OCT = B_ACC + 1, B_COUNT = B_OCT + 1 };
+enum { B_OUT = 0, B_INFULL = 1, B_INEMPTY = B_INFULL + ST, B_XFULL = B_INEMPTY + ST, B_YFULL = B_XFULL + 2, B_DSFULL = B_YFULL + 2, B_ACC = B_DSFULL + 2,
+       B_OCT = B_ACC + 1, B_COUNT = B_OCT + 1 };
 static_assert(B_COUNT * 8 <= 256, "barrier area");
 constexpr uint32_t COL_X = 0, COL_Y = 128, COL_SMALL = 256, COL_BIG = 288;
 
@@ -471,8 +468,7 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     for (int i = 0; i < ST; ++i) { mbar_init(bar(B_INFULL + i), 1); mbar_init(bar(B_INEMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(B_XFULL + i), 1); mbar_init(bar(B_YFULL + i), 1);
-      mbar_init(bar(B_XFREE + i), 4); mbar_init(bar(B_YFREE + i), 4);          // 4 warps: buffer i belongs to softmax warp group i
-      mbar_init(bar(B_DSFULL + i), 4); mbar_init(bar(B_DSFREE + i), 1);
+      mbar_init(bar(B_DSFULL + i), 4);                                         // 4 warps: buffer i belongs to softmax warp group i
     }
     mbar_init(bar(B_ACC), 1);
     mbar_init(bar(B_OCT), 8);
@@ -520,11 +516,8 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     auto issue_xy = [&](int t, int s, uint32_t ph) {
       const int b = t & 1;
       mbar_wait_spin(bar(B_INFULL + s), ph);
-      if (t >= 2) {
-        mbar_wait_spin(bar(B_XFREE + b), ((t >> 1) - 1) & 1);
-        // MODE 0: Y[b] holds dS_{t-2} until dQ += dS_{t-2} K has read it; that product was issued before this one (same pipe, issue order)
-        if (MODE == 1) mbar_wait_spin(bar(B_YFREE + b), ((t >> 1) - 1) & 1);
-      }
+      // X[b] / Y[b] hold P_{t-2} / dS_{t-2} until the accumulating products of block t-2 have read them; those were issued before
+      // this call (same thread, same pipe: issue order), after the softmax group's DSFULL hand-over -- no separate "free" barriers
       tc_fence_after();
       const uint32_t st_off = (uint32_t)(OFF_IN + s * IN_BYTES) >> 4;
       const uint64_t iqk_d = d64 + st_off + (IN_IQK >> 4), ic_d = d128 + st_off + (IN_IC >> 4);
@@ -559,29 +552,24 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       mbar_wait_spin(bar(B_DSFULL + b), (t >> 1) & 1);
       tc_fence_after();
       const uint32_t st_off = (uint32_t)(OFF_IN + s * IN_BYTES) >> 4;
-      const uint64_t ds_d = d128 + (uint64_t)((OFF_DS + b * TILE_BYTES) >> 4), it_d = d128 + st_off + (IN_IT >> 4);
+      const uint64_t it_d = d128 + st_off + (IN_IT >> 4);
       if (elect_one()) {
-        // small accumulator += dS (K-major over the 64 inner rows) x inner^T tile [32][64]
-        if (MODE == 0) {
-          // A = dS from TMEM, written by the owning softmax warp group in place of Y[b]: 64 keys = columns [0, 32)
-          const uint32_t ya = tmem + COL_Y + b * TI;
-          umma_f16_ts(tmem + COL_SMALL, ya, it_d, ID_S, t > 0 ? 1u : 0u);
-          umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 8, it_d + 2, ID_S);
-          umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 16, it_d + 4, ID_S);
-          umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 24, it_d + 6, ID_S);
-        } else {
-          umma_f16(tmem + COL_SMALL, ds_d, it_d, ID_S, t > 0 ? 1u : 0u);
-#pragma unroll
-          for (int ks = 1; ks < TI / 16; ++ks) umma_f16_i<1>(tmem + COL_SMALL, ds_d + ks * 2, it_d + ks * 2, ID_S);
-        }
+        // small accumulator += dS x inner^T tile [32][64]; A = dS from TMEM, written by the owning softmax warp group over the consumed
+        // Y[b] columns: 64 inner rows = columns [0, 32), 16 per step
+        const uint32_t ya = tmem + COL_Y + b * TI;
+        umma_f16_ts(tmem + COL_SMALL, ya, it_d, ID_S, t > 0 ? 1u : 0u);
+        umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 8, it_d + 2, ID_S);
+        umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 16, it_d + 4, ID_S);
+        umma_f16_ts_i<1>(tmem + COL_SMALL, ya + 24, it_d + 6, ID_S);
         if (MODE == 1) {
-          // dV += P^T x dy_i: B = the [64 q][192 ch] dy tile read MN-major (16 rows = 2 KB per step)
-          const uint64_t ps_d = d128 + (uint64_t)((OFF_PS + b * TILE_BYTES) >> 4), icmn_d = dmn + st_off + (IN_IC >> 4);
-          umma_f16(tmem + COL_BIG, ps_d, icmn_d, ID_B, t > 0 ? 1u : 0u);
-#pragma unroll
-          for (int ks = 1; ks < TI / 16; ++ks) umma_f16_i<1>(tmem + COL_BIG, ps_d + ks * 2, icmn_d + ks * 128, ID_B);
+          // dV += P^T x dy_i: A = P^T from TMEM (over the consumed X[b] columns), B = the [64 q][192 ch] dy tile read MN-major (2 KB per step)
+          const uint32_t xa = tmem + COL_X + b * TI;
+          const uint64_t icmn_d = dmn + st_off + (IN_IC >> 4);
+          umma_f16_ts(tmem + COL_BIG, xa, icmn_d, ID_B, t > 0 ? 1u : 0u);
+          umma_f16_ts_i<1>(tmem + COL_BIG, xa + 8, icmn_d + 128, ID_B);
+          umma_f16_ts_i<1>(tmem + COL_BIG, xa + 16, icmn_d + 256, ID_B);
+          umma_f16_ts_i<1>(tmem + COL_BIG, xa + 24, icmn_d + 384, ID_B);
         }
-        tc_commit(bar(B_DSFREE + b));
         tc_commit(bar(B_INEMPTY + s));
       }
       __syncwarp();
@@ -625,9 +613,6 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       if (MODE == 1) mbar_wait(bar(B_INFULL + s), (t / ST) & 1);   // lse/rowdot of the inner rows are in this stage
       mbar_wait(bar(B_XFULL + b), (t >> 1) & 1);
       tc_fence_after();
-      if (MODE == 1 && t >= 2) mbar_wait(bar(B_DSFREE + b), ((t >> 1) - 1) & 1);       // the shared-memory dS / P tiles of block t-2 have been consumed
-      uint8_t* drow = sm + OFF_DS + b * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
-      uint8_t* prow = sm + OFF_PS + b * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int col0 = h * 32;
@@ -665,27 +650,15 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
             p_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&pb);
           }
         }
-        if (MODE == 0) {
-          // dS goes back to TMEM over already consumed Y columns (keys [32h, 32h+32) -> columns [16h, 16h+16)): A operand of dQ += dS K
-          tmem_st16_u(tmem + lane_addr + COL_Y + b * TI + h * 16, ds_pk);
-        } else {
-          // K-major SWIZZLE_128B tile [128 rows][64]: row r at (r>>3)*1024 + (r&7)*128, 16-byte chunk index XOR (r&7)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int ch = ((h * 4 + c) ^ (row & 7)) << 4;
-            *reinterpret_cast<uint4*>(drow + ch) = make_uint4(ds_pk[4 * c], ds_pk[4 * c + 1], ds_pk[4 * c + 2], ds_pk[4 * c + 3]);
-            *reinterpret_cast<uint4*>(prow + ch) = make_uint4(p_pk[4 * c], p_pk[4 * c + 1], p_pk[4 * c + 2], p_pk[4 * c + 3]);
-          }
-        }
+        // dS (and P) go back to TMEM over already consumed Y (X) columns -- inner rows [32h, 32h+32) -> columns [16h, 16h+16) -- as the A
+        // operands of the accumulating products: no shared-memory round trip, no proxy fence
+        tmem_st16_u(tmem + lane_addr + COL_Y + b * TI + h * 16, ds_pk);
+        if (MODE == 1) tmem_st16_u(tmem + lane_addr + COL_X + b * TI + h * 16, p_pk);
       }
-      if (MODE == 0) tmem_wait_st(); else fence_async_smem();
+      tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar(B_XFREE + b));
-        if (MODE == 1) mbar_arrive(bar(B_YFREE + b));
-        mbar_arrive(bar(B_DSFULL + b));
-      }
+      if (lane == 0) mbar_arrive(bar(B_DSFULL + b));
     }
     // ---- epilogue
     mbar_wait(bar(B_ACC), 0);
