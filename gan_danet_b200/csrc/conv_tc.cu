@@ -782,7 +782,11 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     GDN_CHECK_ARG(total < (1ll << 31));
     p.total_tiles = (int)total;
     // halo mode: stride-1 3x3 neighbourhood, one-row tiles of 128 pixels, narrow output tile (otherwise the MMA, not L2, is the limit)
-    bool halo = g_halo_enabled && p.cs == 1 && p.os == 1 && p.Wt == BM && p.Ht == 1 && p.taps.n == 9 && p.n_tile <= 64;
+    // measured on B200 (tools/bench_conv.py): the halo box also pays off for wider output tiles when the K extent is short -- one channel
+    // chunk (DenseBlock data gradients 24 -> C, n_tile <= 160: 0.15 -> 0.11 ms) or three chunks with 128 < n_tile <= 192 (DANet fuse
+    // data gradients 184 -> 368: 0.46 -> 0.38 ms); it loses for 128 -> 128 and 368 -> 184, which stay on the per-tap variant
+    const bool halo_shape = p.n_tile <= 64 || (p.kchunks == 1 && p.n_tile <= 160) || (p.kchunks <= 3 && p.n_tile > 128 && p.n_tile <= 192);
+    bool halo = g_halo_enabled && p.cs == 1 && p.os == 1 && p.Wt == BM && p.Ht == 1 && p.taps.n == 9 && halo_shape;
     for (int tp = 0; tp < p.taps.n && halo; ++tp) halo = p.taps.dh[tp] >= -1 && p.taps.dh[tp] <= 1 && p.taps.dw[tp] >= -1 && p.taps.dw[tp] <= 1;
     CUtensorMap mxh, mxl, mwh, mwl;
     const int bw = halo ? HALO_W : p.Wt, bh = halo ? HALO_ROWS : p.Ht;

@@ -37,6 +37,8 @@ CASES = [
     (1, 136, 24, 16, 128, 3, 1, 1),   # halo-reuse variant of the forward kernel (one-row tiles of 128 pixels, narrow N)
     (2, 64, 1, 8, 256, 3, 1, 1),
     (1, 88, 24, 5, 200, 3, 1, 1),     # Discriminator1.conv1: forward on the CUDA cores, gradients on tensor cores
+    (1, 352, 176, 4, 128, 3, 1, 1),   # data gradient 176 -> 352: halo variant with a wide output tile (n_tile 176, three channel chunks)
+    (1, 112, 24, 3, 256, 3, 1, 1),    # data gradient 24 -> 112: halo variant with one channel chunk
 ]
 
 

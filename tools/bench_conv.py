@@ -20,6 +20,9 @@ SHAPES = {  # name: (B, Cin, Cout, H, W, k, stride)
     "up4_64to64": (32, 64, 64, 128, 256, 3, 1),
     "dconv2_64to128_s2": (64, 64, 128, 128, 256, 3, 2),
     "qkv_184to184_1x1": (32, 184, 184, 64, 128, 1, 1),
+    "dense_dgrad_24to136": (32, 24, 136, 64, 128, 3, 1),
+    "dense_dgrad_24to88": (32, 24, 88, 64, 128, 3, 1),
+    "fuse_dgrad_184to368": (32, 184, 368, 64, 128, 3, 1),
 }
 ap = argparse.ArgumentParser()
 ap.add_argument("--only", default=None)
