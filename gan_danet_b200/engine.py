@@ -27,8 +27,16 @@ Tensor = torch.Tensor
 # ----------------------------------------------------------------------------------------------------------------
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_get_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Raw handle of PyTorch's current stream on the current device.  torch.cuda.current_stream() builds a Python Stream object
+    (~15 us; ~600 launches per step = 8 ms of the host's 48 ms): the raw-handle query is two plain C calls."""
+    if _raw_stream is None or _get_device is None:
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(_raw_stream(_get_device()))
 
 
 def _lib(t: Tensor):
