@@ -318,11 +318,23 @@ __global__ void __launch_bounds__(256) pack_qkv_kernel(const float* __restrict__
     }
   }
 }
-__global__ void __launch_bounds__(256) pack_qk_kernel(const float* __restrict__ src, int pitch, int d, __half* __restrict__ dst, long long rows) {
+// aug == nullptr: columns d, d+1 = 1 (the K side); else columns d, d+1 = -aug[row] split into fp16 hi + lo (the Q side: -lse), so that the
+// logit product of the backward kernels comes out of the tensor core as S - lse (exact to 2^-22 |lse|) and no thread ever loads lse.
+__global__ void __launch_bounds__(256) pack_qk_kernel(const float* __restrict__ src, int pitch, int d, __half* __restrict__ dst, long long rows,
+                                                      const float* __restrict__ aug, int augment) {
   const long long total = rows * DPAD;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long r = idx / DPAD; int c = (int)(idx % DPAD);
-    dst[idx] = __float2half_rn(c < d ? src[(size_t)r * pitch + c] : 0.f);
+    float v = c < d ? src[(size_t)r * pitch + c] : 0.f;
+    if (augment && (c == d || c == d + 1)) {
+      if (!aug) v = 1.f;
+      else {
+        const float a = -__ldg(aug + r);
+        const float hi = __half2float(__float2half_rn(a));
+        v = c == d ? hi : a - hi;
+      }
+    }
+    dst[idx] = __float2half_rn(v);
   }
 }
 
@@ -397,6 +409,10 @@ extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
 //                    operand of dV -- no transposed copy of dy exists).
 // gamma is folded into the epilogue (dO = gamma*dy): dQ, dK, dV are scaled by gamma on the way out.
 // Each CTA owns its output rows: no atomics, bitwise deterministic.
+// lse and rowdot never reach the threads: the Q rows carry -lse (fp16 hi + lo) and the K rows 1 in two spare columns of the padded logit
+// operands, the dy rows carry -rowdot (bf16 hi + lo) and the V rows 1 in two spare channel columns, so the tensor core delivers
+// X = S - lse and Y = dP - rowdot directly (ncu before: the per-column lse / rowdot broadcasts of the dK/dV launch were 39 % of the
+// shared-memory data pipe next to 57 % tensor-core operand reads).
 // Operand precision: logits fp16 x fp16 (identical to the forward kernel, so P matches the saved log-sum-exp);
 // everything that carries gradient magnitude (dy, dS, P for dV) is bf16 (fp32 exponent range: no underflow of small gradients).
 //   warp 0: TMA producer   warp 1: tcgen05.mma issuer   warp 2: TMEM allocator   warps 4-11: softmax/dS (thread = TMEM lane = row)
@@ -497,14 +513,10 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
         if (t >= ST) mbar_wait(bar(B_INEMPTY + s), ((t / ST) - 1) & 1);
         const uint32_t st = base + OFF_IN + s * IN_BYTES;
         const int irow = sample * p.N + t * TI;
-        mbar_expect_tx(bar(B_INFULL + s), IQK_BYTES + IT_BYTES + NCH * IC_CHUNK + (MODE == 1 ? LR_BYTES : 0));
+        mbar_expect_tx(bar(B_INFULL + s), IQK_BYTES + IT_BYTES + NCH * IC_CHUNK);
         tma_load_2d(st + IN_IQK, m_iqk, bar(B_INFULL + s), 0, irow);
         tma_load_2d(st + IN_IT, m_it, bar(B_INFULL + s), t * TI, sample * DPAD);
         for (int c = 0; c < NCH; ++c) tma_load_2d(st + IN_IC + c * IC_CHUNK, m_ic, bar(B_INFULL + s), c * 64, irow);
-        if (MODE == 1) {
-          bulk_load(st + IN_LR, p.lse + irow, TI * 4, bar(B_INFULL + s));
-          bulk_load(st + IN_LR + TI * 4, p.rowdot + irow, TI * 4, bar(B_INFULL + s));
-        }
       }
     }
   } else if (warp == 1) {
@@ -582,9 +594,7 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;                  // TMEM lane = outer row
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    float L_row = 0.f, rd_row = 0.f;
     if (MODE == 0) {
-      L_row = __ldg(p.lse + row0 + row) * LOG2E; rd_row = __ldg(p.rowdot + row0 + row);
       // dy_i (outer tile, loop invariant, A operand of Y = dy_i V_j^T) goes to TMEM once: with A in shared memory every one of the
       // 12 MMAs of a block re-reads its 4 KB A slice (49 instead of 33 cycles each, and the shared-memory pipe is the kernel's bound).
       // Thread = row; warp group w copies 16-byte pieces 4w..4w+3 of each 128-byte swizzled row chunk: 8 bf16 = 4 TMEM columns per piece.
@@ -609,8 +619,6 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     // blocks, 32 at a time): while one group is in its MUFU-bound exp phase the other loads Y, forms dS and hands it to the MMA warp.
     for (int t = wg; t < T; t += 2) {
       const int b = wg, s = t % ST;
-      const float* lr = reinterpret_cast<const float*>(sm + OFF_IN + s * IN_BYTES + IN_LR);
-      if (MODE == 1) mbar_wait(bar(B_INFULL + s), (t / ST) & 1);   // lse/rowdot of the inner rows are in this stage
       mbar_wait(bar(B_XFULL + b), (t >> 1) & 1);
       tc_fence_after();
 #pragma unroll
@@ -618,30 +626,18 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
         const int col0 = h * 32;
         float x[32];
         tmem_ld32(tmem + lane_addr + COL_X + b * TI + col0, x);
-        if (MODE == 0) {
+        // X already is S - lse (the operands carry -lse and 1 in two spare columns of the logit product): P = exp(X) <= 1
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = ex2(fmaf(x[i], LOG2E, -L_row));            // P (<= 1)
-        } else {
-          // lse of 32 inner rows: warp-uniform addresses, fetched as 8 x 128-bit broadcasts (not 32 scalar loads)
-          const float4* l4 = reinterpret_cast<const float4*>(lr + col0);
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 Lv = l4[i4];
-            x[4 * i4] = ex2(fmaf(x[4 * i4], LOG2E, -Lv.x * LOG2E)); x[4 * i4 + 1] = ex2(fmaf(x[4 * i4 + 1], LOG2E, -Lv.y * LOG2E));
-            x[4 * i4 + 2] = ex2(fmaf(x[4 * i4 + 2], LOG2E, -Lv.z * LOG2E)); x[4 * i4 + 3] = ex2(fmaf(x[4 * i4 + 3], LOG2E, -Lv.w * LOG2E));
-          }
-        }
+        for (int i = 0; i < 32; ++i) x[i] = ex2(x[i] * LOG2E);
         if (h == 0) { mbar_wait(bar(B_YFULL + b), (t >> 1) & 1); tc_fence_after(); }
         float y[32];
         tmem_ld32(tmem + lane_addr + COL_Y + b * TI + col0, y);
         uint32_t ds_pk[16], p_pk[16];
-        const float4* r4 = reinterpret_cast<const float4*>(lr + TI + col0);
+        // Y already is dy V^T - rowdot (same trick: -rowdot and 1 in two spare channel columns): dS = P * Y
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          float4 rv = make_float4(rd_row, rd_row, rd_row, rd_row);
-          if (MODE == 1) rv = r4[i >> 2];
-          __nv_bfloat162 dsa = __floats2bfloat162_rn(x[i] * (y[i] - rv.x), x[i + 1] * (y[i + 1] - rv.y));
-          __nv_bfloat162 dsb = __floats2bfloat162_rn(x[i + 2] * (y[i + 2] - rv.z), x[i + 3] * (y[i + 3] - rv.w));
+          __nv_bfloat162 dsa = __floats2bfloat162_rn(x[i] * y[i], x[i + 1] * y[i + 1]);
+          __nv_bfloat162 dsb = __floats2bfloat162_rn(x[i + 2] * y[i + 2], x[i + 3] * y[i + 3]);
           ds_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&dsa);
           ds_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&dsb);
           if (MODE == 1) {
@@ -696,13 +692,27 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
 }
 
 // fp32 [rows][pitch] -> bf16 [rows][CPAD], zero padded
-__global__ void __launch_bounds__(256) pack_rows_bf16_kernel(const float* __restrict__ src, int pitch, int C, long long rows, __nv_bfloat16* __restrict__ dst) {
+// columns C, C+1: 1 (aug == nullptr, the V side) or -aug[row] split into bf16 hi + lo (the dy side: -rowdot), so that dy V^T comes out as Y - rowdot
+__global__ void __launch_bounds__(256) pack_rows_bf16_kernel(const float* __restrict__ src, int pitch, int C, long long rows, __nv_bfloat16* __restrict__ dst,
+                                                             const float* __restrict__ aug) {
   const long long total = rows * (CPAD / 8);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long r = idx / (CPAD / 8); const int c0 = (int)(idx % (CPAD / 8)) * 8;
     __align__(16) __nv_bfloat16 h[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) h[e] = __float2bfloat16_rn(c0 + e < C ? __ldg(src + (size_t)r * pitch + c0 + e) : 0.f);
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      float v = c < C ? __ldg(src + (size_t)r * pitch + c) : 0.f;
+      if (c == C || c == C + 1) {
+        if (!aug) v = 1.f;
+        else {
+          const float a = -__ldg(aug + r);
+          const float hi = __bfloat162float(__float2bfloat16_rn(a));
+          v = c == C ? hi : a - hi;
+        }
+      }
+      h[e] = __float2bfloat16_rn(v);
+    }
     *reinterpret_cast<uint4*>(dst + (size_t)r * CPAD + c0) = *reinterpret_cast<const uint4*>(h);
   }
 }
@@ -753,7 +763,7 @@ extern "C" size_t gdn_pam_tc_bwd_ws_bytes(const gdn_pam_bwd_args* a) {
 // rowdot (= sum_c dy*o per row) has been computed by the caller (gdn_pam_bwd in attention.cu)
 extern "C" int gdn_pam_tc_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s) {
   GDN_CHECK_ARG(a->precision == GDN_PREC_FP16);
-  GDN_CHECK_ARG(a->N % TO == 0 && a->d <= DPAD && a->C <= CPAD && a->C % 4 == 0);
+  GDN_CHECK_ARG(a->N % TO == 0 && a->d + 2 <= DPAD && a->C + 2 <= CPAD && a->C % 4 == 0);    // two spare operand columns carry -lse / -rowdot
   GDN_CHECK_ARG(((uintptr_t)a->dv & 15) == 0 && ((uintptr_t)a->lse & 15) == 0 && ((uintptr_t)a->rowdot & 15) == 0);
   if (!a->ws || a->ws_bytes < gdn_pam_tc_bwd_ws_bytes(a)) { set_error("gdn_pam_bwd(fp16): workspace too small"); return GDN_EWORKSPACE; }
   const size_t rows = (size_t)a->B * a->N;
@@ -766,14 +776,14 @@ extern "C" int gdn_pam_tc_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s) {
   __nv_bfloat16* Kt = reinterpret_cast<__nv_bfloat16*>(w);
   cudaStream_t st = as_stream(s);
   const int pg = (int)(cdiv((long long)rows * DPAD, 256) < 16 * kNumSMs ? cdiv((long long)rows * DPAD, 256) : 16 * kNumSMs);
-  pack_qk_kernel<<<pg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, Qh, (long long)rows);
+  pack_qk_kernel<<<pg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, Qh, (long long)rows, a->lse, 1);       // columns d, d+1: -lse (hi, lo)
   GDN_CHECK_LAUNCH();
-  pack_qk_kernel<<<pg, 256, 0, st>>>(a->k, a->qk_pitch, a->d, Kh, (long long)rows);
+  pack_qk_kernel<<<pg, 256, 0, st>>>(a->k, a->qk_pitch, a->d, Kh, (long long)rows, nullptr, 1);      // columns d, d+1: 1
   GDN_CHECK_LAUNCH();
   const int rg = (int)(cdiv((long long)rows * (CPAD / 8), 256) < 16 * kNumSMs ? cdiv((long long)rows * (CPAD / 8), 256) : 16 * kNumSMs);
-  pack_rows_bf16_kernel<<<rg, 256, 0, st>>>(a->v, a->v_pitch, a->C, (long long)rows, Vb);
+  pack_rows_bf16_kernel<<<rg, 256, 0, st>>>(a->v, a->v_pitch, a->C, (long long)rows, Vb, nullptr);          // columns C, C+1: 1
   GDN_CHECK_LAUNCH();
-  pack_rows_bf16_kernel<<<rg, 256, 0, st>>>(a->dy, a->dy_pitch, a->C, (long long)rows, DYb);
+  pack_rows_bf16_kernel<<<rg, 256, 0, st>>>(a->dy, a->dy_pitch, a->C, (long long)rows, DYb, a->rowdot);      // columns C, C+1: -rowdot (hi, lo)
   GDN_CHECK_LAUNCH();
   dim3 tg((unsigned)cdiv(a->N, 32), 1, (unsigned)a->B);
   pack_t_bf16_kernel<<<tg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, a->N, Qt);
