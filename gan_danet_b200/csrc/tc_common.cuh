@@ -60,6 +60,18 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 }
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// 2^x on the FMA / integer pipes (no MUFU): round-to-nearest split x = n + f with the 1.5*2^23 trick, cubic minimax-style polynomial for 2^f on
+// [-0.5, 0.5] (max relative error 7.7e-5, below the 2^-9 rounding of a bf16 result), n added to the exponent field.  Valid for x >= -125.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float xf = x + 12582912.f;
+  const float f = x - (xf - 12582912.f);
+  float p = fmaf(0.05508868f, f, 0.24260405f);
+  p = fmaf(p, f, 0.69327624f);
+  p = fmaf(p, f, 0.99992894f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
+
 #define TM_REGS32(v) \
   v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], v[17], v[18], v[19], v[20], v[21], v[22], \
       v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
