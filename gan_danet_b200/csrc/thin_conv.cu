@@ -39,36 +39,52 @@ __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ S
   const int gx = g.Wv / PX;
   const int total = g.B * g.Hv * gx;
   const int gpp = 256 / lanes;                                  // pixel groups per block pass
+  // the kernel was instruction-issue bound (ncu: 75 % issue slots, 3.3 TB/s): packed fp32x2 FMAs (sm_100 FFMA2), an interior fast path
+  // without per-element bounds checks and 32-bit offsets take it to the write bandwidth
+  float2 w01[9], w23[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { w01[k] = make_float2(wr[0][k], wr[1][k]); w23[k] = make_float2(wr[2][k], wr[3][k]); }
   for (int gi = blockIdx.x * gpp + threadIdx.x / lanes; gi < total; gi += gridDim.x * gpp) {
     const int xg = gi % gx, r = gi / gx, y = r % g.Hv, b = r / g.Hv;
     const int x0 = xg * PX;
     const float* sb = S + (size_t)b * g.Hs * g.Ws;
-    const int sx0 = x0 * stride - pad;
+    const int sx0 = x0 * stride - pad, sy0 = y * stride - pad;
     float sw[3][NC];
+    if (sy0 >= 0 && sy0 + 2 < g.Hs && sx0 >= 0 && sx0 + NC <= g.Ws) {          // interior: the whole window is inside the field
+      const float* s0 = sb + (size_t)sy0 * g.Ws + sx0;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int sy = y * stride + kh - pad;
-      const bool rowok = sy >= 0 && sy < g.Hs;
-      const float* sr = sb + (size_t)(rowok ? sy : 0) * g.Ws;
+      for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        const int sx = sx0 + j;
-        sw[kh][j] = (rowok && sx >= 0 && sx < g.Ws) ? __ldg(sr + sx) : 0.f;
+        for (int j = 0; j < NC; ++j) sw[kh][j] = __ldg(s0 + kh * g.Ws + j);
+    } else {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int sy = sy0 + kh;
+        const bool rowok = sy >= 0 && sy < g.Hs;
+        const float* sr = sb + (size_t)(rowok ? sy : 0) * g.Ws;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const int sx = sx0 + j;
+          sw[kh][j] = (rowok && sx >= 0 && sx < g.Ws) ? __ldg(sr + sx) : 0.f;
+        }
       }
     }
     const size_t p = ((size_t)b * g.Hv + y) * g.Wv + x0;
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
-      float4 acc = bv;
+      float2 a01 = make_float2(bv.x, bv.y), a23 = make_float2(bv.z, bv.w);
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const float s = sw[kh][(STRIDE ? i * STRIDE : 0) + kw];
-          const int k = kh * 3 + kw;
-          acc.x = fmaf(s, wr[0][k], acc.x); acc.y = fmaf(s, wr[1][k], acc.y); acc.z = fmaf(s, wr[2][k], acc.z); acc.w = fmaf(s, wr[3][k], acc.w);
+          const float sv = sw[kh][(STRIDE ? i * STRIDE : 0) + kw];
+          const float2 s2 = make_float2(sv, sv);
+          a01 = __ffma2_rn(s2, w01[kh * 3 + kw], a01);
+          a23 = __ffma2_rn(s2, w23[kh * 3 + kw], a23);
         }
-      acc.x = apply_act(acc.x, act, slope); acc.y = apply_act(acc.y, act, slope); acc.z = apply_act(acc.z, act, slope); acc.w = apply_act(acc.w, act, slope);
+      float4 acc = make_float4(a01.x, a01.y, a23.x, a23.y);
+      if (act == GDN_ACT_RELU) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+      else if (act == GDN_ACT_LRELU) { acc.x = fmaxf(acc.x, acc.x * slope); acc.y = fmaxf(acc.y, acc.y * slope); acc.z = fmaxf(acc.z, acc.z * slope); acc.w = fmaxf(acc.w, acc.w * slope); }
       if (res) { const float4 rr = *reinterpret_cast<const float4*>(res + (p + i) * res_pitch + c); acc.x += rr.x; acc.y += rr.y; acc.z += rr.z; acc.w += rr.w; }
       *reinterpret_cast<float4*>(V + (p + i) * v_pitch + c) = acc;
       if (V16) {
@@ -128,16 +144,21 @@ __global__ void __launch_bounds__(256, CPL <= 8 ? 2 : 1) reduce_kernel(const flo
   for (int ps = 0; ps < passes; ++ps) {
     const int i = ps * 32 + slot;
     load(i + 32, nxt);                      // next pass in flight while this one is reduced (i + 32 >= n loads nothing)
-    float tk[9];
+    // nine per-tap dot products over this lane's channels: taps in pairs on the packed fp32x2 FMA (5 instead of 9 instructions per channel)
+    float2 t2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float t8s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) tk[k] = 0.f;
+    for (int j = 0; j < NJ; ++j) {
+      const float cv[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
 #pragma unroll
-    for (int j = 0; j < NJ; ++j)
+      for (int e = 0; e < 4; ++e) {
+        const float2 v2 = make_float2(cv[e], cv[e]);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        tk[k] = fmaf(cur[j].x, wr[j][0][k], tk[k]); tk[k] = fmaf(cur[j].y, wr[j][1][k], tk[k]);
-        tk[k] = fmaf(cur[j].z, wr[j][2][k], tk[k]); tk[k] = fmaf(cur[j].w, wr[j][3][k], tk[k]);
+        for (int q = 0; q < 4; ++q) t2[q] = __ffma2_rn(v2, make_float2(wr[j][e][2 * q], wr[j][e][2 * q + 1]), t2[q]);
+        t8s = fmaf(cv[e], wr[j][e][8], t8s);
       }
+    }
+    const float tk[9] = {t2[0].x, t2[0].y, t2[1].x, t2[1].y, t2[2].x, t2[2].y, t2[3].x, t2[3].y, t8s};
     // reduce-scatter over the 8 lanes of the pixel: lane l ends up with the full sum of tap l; tap 8 is reduced everywhere
     float u[4], v2[2];
 #pragma unroll
