@@ -365,6 +365,88 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restri
     }
   }
 }
+// Same gradient for a vertical strip of T input rows per thread: the horizontally filtered dy rows are shared by the T outputs of the strip
+// (2T + 6 rows of 8 loads instead of T x 64 loads: 22 instead of 64 128-bit loads per output at T = 8; the one-pixel kernel is bound by
+// L1 requests, 1.2 TB/s).  Strips that touch the top / bottom border (clamped taps fold together there) take the generic per-pixel path.
+template <int T>
+__global__ void __launch_bounds__(256) bicubic_up2_bwd_strip_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
+  const int Cv = C >> 2, Ho = 2 * H, Wo = 2 * W, strips = (H + T - 1) / T;
+  const long long total = (long long)B * strips * W * Cv;
+  float w75[4], w25[4];
+  cubic_coeffs(0.75f, w75); cubic_coeffs(0.25f, w25);
+  const float wyc[8] = {w25[3], w75[3], w25[2], w75[2], w25[1], w75[1], w25[0], w75[0]};     // interior rows (see up2_bwd_weights)
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cv) << 2; long long r = idx / Cv;
+    const int ix = (int)(r % W); r /= W; const int st = (int)(r % strips); const int b = (int)(r / strips);
+    const int iy0 = st * T;
+    float wx[8];
+    up2_bwd_weights(ix, W, w75, w25, wx);
+    const float* base = dy + (size_t)b * Ho * Wo * C + c;
+    if (iy0 >= 3 && iy0 + T - 1 <= H - 4) {
+      float4 acc[T];
+#pragma unroll
+      for (int k = 0; k < T; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // rows are software-pipelined two deep: the kernel is bound by DRAM latency x the 2T+6 sequential rows of a strip (ncu: 24 % warps
+      // active, every FMA waiting on its loads), so the loads of the next two rows are in flight while a row is filtered
+      const float* row0 = base + (size_t)(2 * iy0 - 3) * Wo * C;
+      const size_t rstride = (size_t)Wo * C;
+      bool okx[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int ox = 2 * ix - 3 + j; okx[j] = ox >= 0 && ox < Wo; }
+      const float* col0 = row0 + (ptrdiff_t)(2 * ix - 3) * C;
+      float4 q[3][8];
+#pragma unroll
+      for (int pre = 0; pre < 2; ++pre)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[pre][j] = okx[j] ? __ldg(reinterpret_cast<const float4*>(col0 + pre * rstride + (size_t)j * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int rr = 0; rr < 2 * T + 6; ++rr) {
+        if (rr + 2 < 2 * T + 6) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            q[(rr + 2) % 3][j] = okx[j] ? __ldg(reinterpret_cast<const float4*>(col0 + (rr + 2) * rstride + (size_t)j * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = q[rr % 3][j];
+          h.x = fmaf(wx[j], v.x, h.x); h.y = fmaf(wx[j], v.y, h.y); h.z = fmaf(wx[j], v.z, h.z); h.w = fmaf(wx[j], v.w, h.w);
+        }
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+          const int i = rr - 2 * k;                      // compile-time after unrolling
+          if (i >= 0 && i < 8) { acc[k].x = fmaf(wyc[i], h.x, acc[k].x); acc[k].y = fmaf(wyc[i], h.y, acc[k].y); acc[k].z = fmaf(wyc[i], h.z, acc[k].z); acc[k].w = fmaf(wyc[i], h.w, acc[k].w); }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < T; ++k) *reinterpret_cast<float4*>(dx + (((size_t)b * H + iy0 + k) * W + ix) * C + c) = acc[k];
+    } else {
+      for (int k = 0; k < T && iy0 + k < H; ++k) {
+        const int iy = iy0 + k;
+        float wy[8];
+        up2_bwd_weights(iy, H, w75, w25, wy);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int oy = 2 * iy - 3 + i;
+          if (oy < 0 || oy >= Ho) continue;
+          const float* row = base + (size_t)oy * Wo * C;
+          float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int ox = 2 * ix - 3 + j;
+            if (ox < 0 || ox >= Wo) continue;
+            const float4 q = __ldg(reinterpret_cast<const float4*>(row + (size_t)ox * C));
+            h.x = fmaf(wx[j], q.x, h.x); h.y = fmaf(wx[j], q.y, h.y); h.z = fmaf(wx[j], q.z, h.z); h.w = fmaf(wx[j], q.w, h.w);
+          }
+          acc.x = fmaf(wy[i], h.x, acc.x); acc.y = fmaf(wy[i], h.y, acc.y); acc.z = fmaf(wy[i], h.z, acc.z); acc.w = fmaf(wy[i], h.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(dx + (((size_t)b * H + iy) * W + ix) * C + c) = acc;
+      }
+    }
+  }
+}
+
 // bf16 activations (the frozen VGG19 branch keeps its untapped feature maps in bf16 only): 8 channels = 16 bytes per thread
 __device__ __forceinline__ void bf16x8_to_float(const uint4& q, float* f) {
   const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
@@ -459,7 +541,9 @@ extern "C" int gdn_bicubic_up2_fwd(const float* x, float* y, int B, int H, int W
 }
 extern "C" int gdn_bicubic_up2_bwd(const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s) {
   GDN_CHECK_ARG(dy && dx && B > 0 && H > 0 && W > 0 && C > 0);
-  if (C % 4 == 0 && al16(dy) && al16(dx)) bicubic_up2_bwd_v4_kernel<<<grid_for((long long)B * H * W * (C / 4)), 256, 0, as_stream(s)>>>(dy, dx, B, H, W, C);
+  if (C % 4 == 0 && al16(dy) && al16(dx) && H >= 24)
+    bicubic_up2_bwd_strip_kernel<8><<<grid_for((long long)B * ((H + 7) / 8) * W * (C / 4)), 256, 0, as_stream(s)>>>(dy, dx, B, H, W, C);
+  else if (C % 4 == 0 && al16(dy) && al16(dx)) bicubic_up2_bwd_v4_kernel<<<grid_for((long long)B * H * W * (C / 4)), 256, 0, as_stream(s)>>>(dy, dx, B, H, W, C);
   else bicubic_up2_bwd_kernel<1><<<grid_for((long long)B * H * W * C), 256, 0, as_stream(s)>>>(dy, dx, B, H, W, C);
   GDN_CHECK_LAUNCH();
   return GDN_OK;

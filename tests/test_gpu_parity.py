@@ -484,7 +484,7 @@ def test_pam_properties_full_size():
     assert rel_err(y12, y1 + y2) < 3e-3
 
 
-@pytest.mark.parametrize("B,H,W,C", [(2, 9, 13, 8), (1, 16, 32, 64), (1, 3, 4, 4), (2, 4, 6, 4), (1, 2, 2, 8), (1, 6, 2, 4)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 9, 13, 8), (1, 16, 32, 64), (1, 3, 4, 4), (2, 4, 6, 4), (1, 2, 2, 8), (1, 6, 2, 4), (1, 29, 7, 8), (2, 40, 16, 4)])
 def test_resample_vector_paths(B, H, W, C):
     """128-bit kernels (C % 4 == 0) for nn.Upsample(2,'bicubic') (generator.py:221,225) and MaxPool2d(2,2) (VGG19 of
     losses.py:58), forward and backward, against ATen on the same device in float64 (same formulas as the CPU oracle)."""
