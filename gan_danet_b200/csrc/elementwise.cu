@@ -207,14 +207,12 @@ __device__ __forceinline__ float ew_apply(const EwP& p, float a, float b, int c,
   if (OP == EW_AFFINE) return apply_act(fmaf(a, __ldg(p.scale + c), __ldg(p.shift + c)), p.act, p.slope);
   if (OP == EW_ACT_BWD) return a * act_grad(b, p.act, p.slope);
   if (OP == EW_AXPY) return a * p.alpha;
-  // EW_BN_BWD: a = dy, b = x
-  float sc = __ldg(p.scale + c), sf = __ldg(p.shift + c), mu = __ldg(p.mean + c), is = __ldg(p.invstd + c);
-  float g = a * act_grad(fmaf(b, sc, sf), p.act, p.slope);
-  float xhat = (b - mu) * is;
-  extern __shared__ float ew_coef[];       // [2C]: sum_g / M, sum_g_xhat / M (filled once per block)
-  float sg = ew_coef[c], sgx = ew_coef[p.C + c];
-  float w = p.weight ? __ldg(p.weight + c) : 1.f;
-  return w * is * (g - sg - xhat * sgx);
+  // EW_BN_BWD: a = dy, b = x.  dx = w*is*(g - sg - xhat*sgx) with g = dy*act'(x*sc+sf), xhat = (x-mu)*is, folded per channel into
+  // dx = k1*g + k2*x + k3; the block's coefficient table [5][C] = sc | sf | k1 | k2 | k3 lives in shared memory (one 128-bit read per
+  // coefficient and channel quad instead of five global and two shared scalar loads per element: the kernel was load-issue bound)
+  extern __shared__ __align__(16) float ew_coef[];
+  const float g = a * act_grad(fmaf(b, ew_coef[c], ew_coef[p.C + c]), p.act, p.slope);
+  return fmaf(ew_coef[2 * p.C + c], g, fmaf(ew_coef[3 * p.C + c], b, ew_coef[4 * p.C + c]));
 }
 
 template <int OP, int VEC>
@@ -223,9 +221,15 @@ __global__ void __launch_bounds__(256) ew_kernel(const EwP p) {
   const long long total = p.M * Cv;
   const float invM = 1.f / (float)p.M;
   if (OP == EW_BN_BWD) {
-    extern __shared__ float ew_coef[];
+    extern __shared__ __align__(16) float ew_coef[];
     const double inv = 1.0 / (double)p.M;
-    for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) ew_coef[i] = (float)(p.sums[i] * inv);
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      const float sg = (float)(p.sums[c] * inv), sgx = (float)(p.sums[p.C + c] * inv);
+      const float is = p.invstd[c], mu = p.mean[c], w = p.weight ? p.weight[c] : 1.f;
+      const float k1 = w * is, k2 = -k1 * sgx * is;
+      ew_coef[c] = p.scale[c]; ew_coef[p.C + c] = p.shift[c];
+      ew_coef[2 * p.C + c] = k1; ew_coef[3 * p.C + c] = k2; ew_coef[4 * p.C + c] = -k1 * sg - k2 * mu;
+    }
     __syncthreads();
   }
   // 32-bit index arithmetic when the element count allows it (64-bit division costs more than the memory access it addresses)
@@ -240,8 +244,23 @@ __global__ void __launch_bounds__(256) ew_kernel(const EwP p) {
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (OP == EW_BN_BWD || OP == EW_ACT_BWD) b = *reinterpret_cast<const float4*>(p.b + (size_t)m * p.b_pitch + c);
       float4 r;
-      r.x = ew_apply<OP>(p, a.x, b.x, c, invM); r.y = ew_apply<OP>(p, a.y, b.y, c + 1, invM);
-      r.z = ew_apply<OP>(p, a.z, b.z, c + 2, invM); r.w = ew_apply<OP>(p, a.w, b.w, c + 3, invM);
+      if (OP == EW_BN_BWD) {
+        extern __shared__ __align__(16) float ew_coef[];
+        const float4 sc = *reinterpret_cast<const float4*>(ew_coef + c), sf = *reinterpret_cast<const float4*>(ew_coef + p.C + c);
+        const float4 k1 = *reinterpret_cast<const float4*>(ew_coef + 2 * p.C + c), k2 = *reinterpret_cast<const float4*>(ew_coef + 3 * p.C + c);
+        const float4 k3 = *reinterpret_cast<const float4*>(ew_coef + 4 * p.C + c);
+        r.x = fmaf(k1.x, a.x * act_grad(fmaf(b.x, sc.x, sf.x), p.act, p.slope), fmaf(k2.x, b.x, k3.x));
+        r.y = fmaf(k1.y, a.y * act_grad(fmaf(b.y, sc.y, sf.y), p.act, p.slope), fmaf(k2.y, b.y, k3.y));
+        r.z = fmaf(k1.z, a.z * act_grad(fmaf(b.z, sc.z, sf.z), p.act, p.slope), fmaf(k2.z, b.z, k3.z));
+        r.w = fmaf(k1.w, a.w * act_grad(fmaf(b.w, sc.w, sf.w), p.act, p.slope), fmaf(k2.w, b.w, k3.w));
+      } else if (OP == EW_AFFINE) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c)), sf = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+        r.x = apply_act(fmaf(a.x, sc.x, sf.x), p.act, p.slope); r.y = apply_act(fmaf(a.y, sc.y, sf.y), p.act, p.slope);
+        r.z = apply_act(fmaf(a.z, sc.z, sf.z), p.act, p.slope); r.w = apply_act(fmaf(a.w, sc.w, sf.w), p.act, p.slope);
+      } else {
+        r.x = ew_apply<OP>(p, a.x, b.x, c, invM); r.y = ew_apply<OP>(p, a.y, b.y, c + 1, invM);
+        r.z = ew_apply<OP>(p, a.z, b.z, c + 2, invM); r.w = ew_apply<OP>(p, a.w, b.w, c + 3, invM);
+      }
       float4* op = reinterpret_cast<float4*>(p.o + (size_t)m * p.o_pitch + c);
       if (p.accumulate) { float4 o = *op; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
       *op = r;
@@ -260,6 +279,7 @@ static bool vec4_ok(const EwP& p) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   bool ok = (p.C % 4 == 0) && (p.a_pitch % 4 == 0) && (p.o_pitch % 4 == 0) && al(p.a) && al(p.o);
   if (p.b) ok = ok && (p.b_pitch % 4 == 0) && al(p.b);
+  if (p.scale) ok = ok && al(p.scale) && al(p.shift);
   return ok;
 }
 
@@ -270,8 +290,8 @@ static int ew_launch(const EwP& p, cudaStream_t st) {
   long long total = p.M * (v4 ? p.C / 4 : p.C);
   const int cap = (OP == EW_BN_BWD ? 6 : 16) * kNumSMs;      // BN backward fills a per-block coefficient table first: fewer, longer blocks
   int blocks = (int)(cdiv(total, 256) < cap ? cdiv(total, 256) : cap);
-  const size_t smem = OP == EW_BN_BWD ? (size_t)2 * p.C * sizeof(float) : 0;
-  if (smem > 48 * 1024) { set_error("elementwise: BatchNorm backward supports at most 6144 channels"); return GDN_EINVAL; }
+  const size_t smem = OP == EW_BN_BWD ? (size_t)5 * p.C * sizeof(float) : 0;
+  if (smem > 48 * 1024) { set_error("elementwise: BatchNorm backward supports at most 2457 channels"); return GDN_EINVAL; }
   if (v4) ew_kernel<OP, 4><<<blocks, 256, smem, st>>>(p);
   else ew_kernel<OP, 1><<<blocks, 256, smem, st>>>(p);
   GDN_CHECK_LAUNCH();

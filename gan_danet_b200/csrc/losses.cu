@@ -199,11 +199,38 @@ using namespace gdn;
 
 extern "C" size_t gdn_dot_ws_bytes(long long n) { (void)n; return (size_t)kRedBlocks * kRedSlots * sizeof(double); }
 
+// 128-bit variant (C, pitches and offsets multiples of 4, 16-byte aligned bases, M*C/4 < 2^31): two independent float4 pairs in flight per thread
+namespace gdn {
+__global__ void __launch_bounds__(256) dot_v4_kernel(const float* __restrict__ a, int a_pitch, const float* __restrict__ b, int b_pitch, int M, int Cv,
+                                                      double* __restrict__ partial) {
+  const int n = M * Cv;
+  const int stride = gridDim.x * blockDim.x;
+  float acc0 = 0.f, acc1 = 0.f; double dacc = 0.0; int cnt = 0;
+  auto term = [&](int i) {
+    const int m = i / Cv, c = (i - m * Cv) << 2;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a + (size_t)m * a_pitch + c)), y = __ldg(reinterpret_cast<const float4*>(b + (size_t)m * b_pitch + c));
+    return fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, x.w * y.w)));
+  };
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n; i += 2 * stride) {
+    const float t0 = term(i), t1 = term(i + stride);
+    acc0 += t0; acc1 += t1;
+    if (++cnt == 8) { dacc += (double)acc0 + (double)acc1; acc0 = acc1 = 0.f; cnt = 0; }
+  }
+  if (i < n) acc0 += term(i);
+  dacc += (double)acc0 + (double)acc1;
+  block_store_partials(dacc, 0.0, partial);
+}
+}  // namespace gdn
+
 extern "C" int gdn_dot(const float* a, int a_pitch, int a_c0, const float* b, int b_pitch, int b_c0, long long M, int C, float* out, void* ws, gdn_stream_t s) {
   GDN_CHECK_ARG(a && b && out && ws && M > 0 && C > 0 && a_pitch >= a_c0 + C && b_pitch >= b_c0 + C);
   int blocks = red_blocks(M * C);
   double* partial = reinterpret_cast<double*>(ws);
-  dot_kernel<<<blocks, 256, 0, as_stream(s)>>>(a + a_c0, a_pitch, b + b_c0, b_pitch, M, C, partial);
+  const bool v4 = C % 4 == 0 && a_pitch % 4 == 0 && b_pitch % 4 == 0 && a_c0 % 4 == 0 && b_c0 % 4 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 &&
+                  M * (C / 4) < (1ll << 30);
+  if (v4) dot_v4_kernel<<<blocks, 256, 0, as_stream(s)>>>(a + a_c0, a_pitch, b + b_c0, b_pitch, (int)M, C / 4, partial);
+  else dot_kernel<<<blocks, 256, 0, as_stream(s)>>>(a + a_c0, a_pitch, b + b_c0, b_pitch, M, C, partial);
   GDN_CHECK_LAUNCH();
   finish_kernel<<<1, 256, 0, as_stream(s)>>>(partial, blocks, 1.0, 0.0, out, 0);
   GDN_CHECK_LAUNCH();
