@@ -54,6 +54,31 @@ __global__ void __launch_bounds__(256) pair_loss_kernel(const float* __restrict_
   block_store_partials(dacc, 0.0, partial);
 }
 
+// 128-bit variant (n % 4 == 0, 16-byte aligned pointers): the scalar kernel is instruction bound on the 1 GB VGG feature maps (4.2 TB/s)
+template <int MODE>
+__global__ void __launch_bounds__(256) pair_loss_v4_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4, float* __restrict__ grad,
+                                                           float gcoef, int accumulate, double* __restrict__ partial) {
+  float acc = 0.f; double dacc = 0.0; int cnt = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    const float d[4] = {x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w};
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (MODE == 0) { acc = fmaf(d[e], d[e], acc); g[e] = d[e] * gcoef; }
+      else { acc += fabsf(d[e]); g[e] = (d[e] > 0.f ? gcoef : (d[e] < 0.f ? -gcoef : 0.f)); }
+    }
+    if (grad) {
+      float4* gp = reinterpret_cast<float4*>(grad) + i;
+      if (accumulate) { const float4 o = *gp; g[0] += o.x; g[1] += o.y; g[2] += o.z; g[3] += o.w; }
+      *gp = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    if (++cnt == 8) { dacc += (double)acc; acc = 0.f; cnt = 0; }
+  }
+  dacc += (double)acc;
+  block_store_partials(dacc, 0.0, partial);
+}
+
 __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ x, int B, int H, int W, float* __restrict__ grad, float ch, float cw,
                                                   int accumulate, double* __restrict__ partial) {
   const long long n = (long long)B * H * W;
@@ -237,11 +262,14 @@ extern "C" int gdn_dot(const float* a, int a_pitch, int a_c0, const float* b, in
   return GDN_OK;
 }
 
+static inline bool al16p(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
 extern "C" int gdn_mse(const float* a, const float* b, long long n, float* loss, float* grad, float gscale, int accumulate, void* ws, gdn_stream_t s) {
   GDN_CHECK_ARG(a && b && loss && ws && n > 0);
   int blocks = red_blocks(n);
   double* partial = reinterpret_cast<double*>(ws);
-  pair_loss_kernel<0><<<blocks, 256, 0, as_stream(s)>>>(a, b, n, grad, gscale * 2.f / (float)n, accumulate, partial);
+  if (n % 4 == 0 && al16p(a) && al16p(b) && al16p(grad)) pair_loss_v4_kernel<0><<<blocks, 256, 0, as_stream(s)>>>(a, b, n / 4, grad, gscale * 2.f / (float)n, accumulate, partial);
+  else pair_loss_kernel<0><<<blocks, 256, 0, as_stream(s)>>>(a, b, n, grad, gscale * 2.f / (float)n, accumulate, partial);
   GDN_CHECK_LAUNCH();
   finish_kernel<<<1, 256, 0, as_stream(s)>>>(partial, blocks, 1.0 / (double)n, 0.0, loss, 0);
   GDN_CHECK_LAUNCH();
@@ -251,7 +279,8 @@ extern "C" int gdn_l1(const float* a, const float* b, long long n, float* loss, 
   GDN_CHECK_ARG(a && b && loss && ws && n > 0);
   int blocks = red_blocks(n);
   double* partial = reinterpret_cast<double*>(ws);
-  pair_loss_kernel<1><<<blocks, 256, 0, as_stream(s)>>>(a, b, n, grad, gscale / (float)n, accumulate, partial);
+  if (n % 4 == 0 && al16p(a) && al16p(b) && al16p(grad)) pair_loss_v4_kernel<1><<<blocks, 256, 0, as_stream(s)>>>(a, b, n / 4, grad, gscale / (float)n, accumulate, partial);
+  else pair_loss_kernel<1><<<blocks, 256, 0, as_stream(s)>>>(a, b, n, grad, gscale / (float)n, accumulate, partial);
   GDN_CHECK_LAUNCH();
   finish_kernel<<<1, 256, 0, as_stream(s)>>>(partial, blocks, 1.0 / (double)n, 0.0, loss, loss_accumulate);
   GDN_CHECK_LAUNCH();
