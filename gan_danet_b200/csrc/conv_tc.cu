@@ -63,6 +63,7 @@ struct FwdParams {
   int cs;                     // input coordinate = tile coordinate * cs + tap offset (cs = conv stride = TMA element stride)
   int kchunks, n_tile, n_tiles, total_tiles, nsplit, stages, tmem_cols, wt_shift;
   int act; float slope; int vec4; int halo_bo, kgroup;
+  int w_resident;             // HALO: all weight tiles of the layer stay in shared memory for the CTA's lifetime (loaded once)
   TapList taps;
 };
 
@@ -130,6 +131,16 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {   // ---- TMA producer
       int it = 0, na = 0;
+      if (HALO && p.w_resident) {
+        // small layers (e.g. 64 -> 64: 9 x 8 KB): the weights are the same for every tile of this persistent CTA -- load them once instead
+        // of once per tile (ncu on the 64 -> 64 layer at 256x512: L2 -> SM traffic 122 KB per tile, 72 KB of it weights; tensor pipe 28 %)
+        const int nk = p.kchunks * p.nsplit;
+        mbar_expect_tx(full(0), nk * p.taps.n * b_bytes);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int comp = 0; comp < p.nsplit; ++comp)
+            for (int tp = 0; tp < p.taps.n; ++tp)
+              tma_load_3d(base + ring_off + ((kc * p.nsplit + comp) * p.taps.n + tp) * b_bytes, comp == 2 ? &mapWlo : &mapWhi, full(0), kc * BK, 0, p.taps.widx[tp]);
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int t = tile / p.n_tiles;
         const int n0 = (tile % p.n_tiles) * p.n_tile;
@@ -148,6 +159,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
               if (na >= HALO_SLOTS) mbar_wait(aempty(sa), ((na / HALO_SLOTS) - 1) & 1);
               mbar_expect_tx(afull(sa), HALO_TX);
               tma_load_4d(base + sa * HALO_SLOT, mx, afull(sa), kc * BK, tw * BM - 1, th - 1, img);
+              if (p.w_resident) continue;
               for (int tp0 = 0; tp0 < p.taps.n; tp0 += p.kgroup, ++it) {
                 const int s = it % p.stages;
                 if (it >= p.stages) mbar_wait(empty(s), ((it / p.stages) - 1) & 1);
@@ -202,12 +214,33 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
     const uint64_t desc0 = smem_desc(base, 1024, LAYOUT_SW128);       // K-major SWIZZLE_128B tile at `base`; + (byte offset >> 4) moves it
     int s = 0, lt = 0, sa = 0;
     uint32_t ph = 0, pha = 0;
+    if (HALO && p.w_resident) mbar_wait_spin(full(0), 0);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int ab = lt & 1;
       if (lt >= 2) mbar_wait_spin(acc_empty(ab), ((lt >> 1) - 1) & 1);     // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t d_tmem = tmem + ab * acc_stride;
-      if (HALO) {
+      if (HALO && p.w_resident) {
+        for (int kk = 0; kk < p.kchunks * p.nsplit; ++kk) {
+          mbar_wait_spin(afull(sa), pha);
+          tc_fence_after();
+          for (int tp = 0; tp < p.taps.n; ++tp) {
+            const uint32_t a0 = base + sa * HALO_SLOT + (uint32_t)((p.taps.dh[tp] + 1) * HALO_W + (p.taps.dw[tp] + 1)) * 128u;
+            const uint64_t ad = smem_desc_bo(a0, 1024, LAYOUT_SW128, p.halo_bo);
+            const uint64_t bd = desc0 + (uint64_t)((ring_off + (kk * p.taps.n + tp) * b_bytes) >> 4);
+            if (elect_one()) {
+              umma_f16(d_tmem, ad, bd, idesc, (kk > 0 || tp > 0) ? 1u : 0u);
+              umma_f16_i<1>(d_tmem, ad + 2, bd + 2, idesc);
+              umma_f16_i<1>(d_tmem, ad + 4, bd + 4, idesc);
+              umma_f16_i<1>(d_tmem, ad + 6, bd + 6, idesc);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) tc_commit(aempty(sa));
+          __syncwarp();
+          if (++sa == HALO_SLOTS) { sa = 0; pha ^= 1; }
+        }
+      } else if (HALO) {
         for (int kk = 0; kk < p.kchunks * p.nsplit; ++kk) {
           mbar_wait_spin(afull(sa), pha);
           for (int tp0 = 0; tp0 < p.taps.n; tp0 += p.kgroup) {
@@ -742,6 +775,7 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.stages = stages;
   p.halo_bo = 0;
+  p.w_resident = 0;
   const size_t smem = (size_t)stages * stage_bytes + EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 10) + 1024;
   const int n_tiles = (int)cdiv(a->Cout, p.n_tile);
   cudaStream_t st = as_stream(s);
@@ -800,11 +834,15 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     if (halo) {
       FwdParams ph = p;
       const int b_bytes = p.n_tile * 128, w_budget = ring_budget - HALO_SLOTS * HALO_SLOT;
+      const long long w_all = (long long)p.kchunks * nsplit * 9 * b_bytes;
+      ph.w_resident = (n_tiles == 1 && groups == 1 && w_all <= w_budget && w_all < (1 << 20) && p.kchunks * nsplit <= MAX_STAGES) ? 1 : 0;
       ph.kgroup = 9 * b_bytes * 2 <= w_budget ? 9 : (3 * b_bytes * 2 <= w_budget ? 3 : 1);   // taps per weight stage: all 9, one filter row, or one
       ph.stages = w_budget / (ph.kgroup * b_bytes);
       if (ph.stages > MAX_STAGES) ph.stages = MAX_STAGES;
       { const char* e = getenv("GDN_HALO_BO"); ph.halo_bo = e ? atoi(e) : 0; }   // measured on B200: the swizzle phase comes from the absolute smem address, base_offset must stay 0
-      const size_t smem_h = (size_t)HALO_SLOTS * HALO_SLOT + (size_t)ph.stages * ph.kgroup * b_bytes + EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 10) + 1024;
+      if (ph.w_resident) { ph.kgroup = 9; ph.stages = p.kchunks * nsplit; if (ph.stages > MAX_STAGES) ph.stages = MAX_STAGES; }   // ring area = the resident weight block
+      const size_t smem_h = (size_t)HALO_SLOTS * HALO_SLOT + (ph.w_resident ? (size_t)w_all : (size_t)ph.stages * ph.kgroup * b_bytes) + EPI_WARPS * EPI_STAGE_BYTES +
+                            8 * (2 * MAX_STAGES + 10) + 1024;
       conv_tc_fwd_kernel<true><<<grid, FWD_THREADS, smem_h, st>>>(mxh, mxl, mwh, mwl, ph);
     } else {
       conv_tc_fwd_kernel<false><<<grid, FWD_THREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);
