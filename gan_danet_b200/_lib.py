@@ -155,6 +155,12 @@ SIGNATURES = {
     "gdn_adamw": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "gdn_adamw_multi": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "gdn_fill": (_i, [_vp, _ll, _f, _vp]),
+    "gdn_destandardise": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _f, _f, _vp]),
+    "gdn_masked_spatial_mean": (_i, [_vp, _vp, _ll, _ll, _f, _f, _vp, _vp]),
+    "gdn_ensemble_stats": (_i, [_vp, _ll, _i, _ll, _f, _f, _vp, _vp, _vp]),
+    "gdn_hist_match": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "gdn_bicubic_resize": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _f, _f, _vp]),
+    "gdn_blend_region": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

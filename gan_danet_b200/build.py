@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libgandanet_sm100.so")
-SOURCES = ["core.cu", "igemm_simt.cu", "elementwise.cu", "resample.cu", "attention.cu", "losses.cu", "pam_tc.cu", "conv_tc.cu", "linear_tc.cu", "thin_conv.cu"]
+SOURCES = ["core.cu", "igemm_simt.cu", "elementwise.cu", "resample.cu", "attention.cu", "losses.cu", "pam_tc.cu", "conv_tc.cu", "linear_tc.cu", "thin_conv.cu", "ensemble.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

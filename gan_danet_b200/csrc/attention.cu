@@ -314,14 +314,29 @@ extern "C" int gdn_cam_bwd(const float* x, int x_pitch, const float* gamma, cons
 // 1x1 convolutions with per-sample weights.  Operands are ALWAYS the hi+lo bf16 split (bf16x3): the energy reaches 1e4 and
 // softmax(-E) is nearly one-hot, plain bf16 is 2-7e-3 off.
 static inline size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
+// A single sample (cfg4: B = 1, N = 51200) has no per-sample grouping to spread over the SMs: its Gram matrix is a split-K weight gradient.
+static void cam_gram_args(gdn_wgrad_tc_args* g, int B, int N, int C) {
+  *g = gdn_wgrad_tc_args{};
+  g->out_cin_total = C; g->scale = 1.f;
+  g->B = B; g->Hi = 1; g->Wi = N; g->Cin = C; g->Ho = 1; g->Wo = N; g->Cout = C; g->kh = g->kw = 1; g->stride = 1; g->pad = 0;
+  g->precision = GDN_PREC_BF16X3; g->groups = B;
+}
+static size_t cam_gram_ws_bytes(int B, int N, int C) {
+  if (B > 1) return 0;
+  gdn_wgrad_tc_args g;
+  cam_gram_args(&g, B, N, C);
+  return gdn_conv2d_wgrad_tc_ws_bytes(&g);
+}
 extern "C" size_t gdn_cam_tc_ws_bytes(int B, int N, int C) {
   const size_t Cp = (size_t)((C + 7) & ~7);
-  return 4 * a256((size_t)B * N * Cp * 2) + 4 * a256((size_t)B * C * Cp * 2) + a256((size_t)B * N * C * 4) + 3 * a256((size_t)B * C * C * 4) + a256((size_t)B * C * 4);
+  return 4 * a256((size_t)B * N * Cp * 2) + 4 * a256((size_t)B * C * Cp * 2) + a256((size_t)B * N * C * 4) + 3 * a256((size_t)B * C * C * 4) + a256((size_t)B * C * 4) +
+         a256(cam_gram_ws_bytes(B, N, C));
 }
 namespace {
 struct CamWs {
   uint16_t *xh, *xl, *dyh, *dyl, *w1h, *w1l, *w2h, *w2l;
-  float *O, *dA, *G, *AT, *rs;
+  float *O, *dA, *G, *AT, *rs, *gram_ws;
+  size_t gram_ws_bytes;
 };
 CamWs cam_carve(void* ws, int B, int N, int C) {
   const size_t Cp = (size_t)((C + 7) & ~7);
@@ -335,14 +350,17 @@ CamWs cam_carve(void* ws, int B, int N, int C) {
   r.O = (float*)take((size_t)B * N * C * 4);
   r.dA = (float*)take((size_t)B * C * C * 4); r.G = (float*)take((size_t)B * C * C * 4); r.AT = (float*)take((size_t)B * C * C * 4);
   r.rs = (float*)take((size_t)B * C * 4);
+  r.gram_ws_bytes = cam_gram_ws_bytes(B, N, C);
+  r.gram_ws = (float*)take(r.gram_ws_bytes);
   return r;
 }
 // out[b] (C x C) = scale * A_b^T B_b over the N pixels
-int cam_gram(const uint16_t* ah, const uint16_t* al, const uint16_t* bh, const uint16_t* bl, float* out, const float* scale_ptr, int B, int N, int C, gdn_stream_t s) {
-  gdn_wgrad_tc_args g = {};
-  g.dy_hi = ah; g.dy_lo = al; g.x_hi = bh; g.x_lo = bl; g.out = out; g.out_cin_total = C; g.scale = 1.f;
-  g.B = B; g.Hi = 1; g.Wi = N; g.Cin = C; g.Ho = 1; g.Wo = N; g.Cout = C; g.kh = g.kw = 1; g.stride = 1; g.pad = 0;
-  g.precision = GDN_PREC_BF16X3; g.groups = B; g.scale_ptr = scale_ptr;
+int cam_gram(const CamWs& w, const uint16_t* ah, const uint16_t* al, const uint16_t* bh, const uint16_t* bl, float* out, const float* scale_ptr, int B, int N, int C,
+             gdn_stream_t s) {
+  gdn_wgrad_tc_args g;
+  cam_gram_args(&g, B, N, C);
+  g.dy_hi = ah; g.dy_lo = al; g.x_hi = bh; g.x_lo = bl; g.out = out; g.scale_ptr = scale_ptr;
+  g.ws = w.gram_ws; g.ws_bytes = w.gram_ws_bytes;
   return gdn_conv2d_wgrad_tc(&g, s);
 }
 // y[b][n][:] = alpha * W_b x[b][n][:] + res   with W_b = w[b] ([C][C] row-major fp32, packed here)
@@ -365,7 +383,7 @@ extern "C" int gdn_cam_fwd_tc(const float* x, int x_pitch, const float* gamma, f
   CamWs w = cam_carve(ws, B, N, C);
   int rc;
   if ((rc = gdn_pack_act_bf16(x, x_pitch, 0, (long long)B * N, C, w.xh, w.xl, nullptr, nullptr, GDN_ACT_NONE, 0.f, s)) != GDN_OK) return rc;
-  if ((rc = cam_gram(w.xh, w.xl, w.xh, w.xl, attn, nullptr, B, N, C, s)) != GDN_OK) return rc;              // energy = bmm(x, x^T)   (generator.py:131-132)
+  if ((rc = cam_gram(w, w.xh, w.xl, w.xh, w.xl, attn, nullptr, B, N, C, s)) != GDN_OK) return rc;              // energy = bmm(x, x^T)   (generator.py:131-132)
   if ((rc = gdn_row_softmax(attn, attn, (long long)B * C, C, 1, nullptr, s)) != GDN_OK) return rc;           // softmax(rowmax - E)     (:135-136)
   return cam_project(w.xh, w.xl, attn, w.w1h, w.w1l, y, y_pitch, gamma, x, x_pitch, B, N, C, s);             // gamma*bmm(attn, x) + x  (:138-139)
 }
@@ -383,7 +401,7 @@ extern "C" int gdn_cam_bwd_tc(const float* x, int x_pitch, const float* gamma, c
   if ((rc = cam_project(w.xh, w.xl, attn, w.w1h, w.w1l, w.O, C, nullptr, nullptr, 0, B, N, C, s)) != GDN_OK) return rc;
   if ((rc = gdn_dot(dy, dy_pitch, 0, w.O, C, 0, (long long)B * N, C, dgamma, dot_ws, s)) != GDN_OK) return rc;
   // dA[i][j] = gamma * sum_n dy[n][i] x[n][j]
-  if ((rc = cam_gram(w.dyh, w.dyl, w.xh, w.xl, w.dA, gamma, B, N, C, s)) != GDN_OK) return rc;
+  if ((rc = cam_gram(w, w.dyh, w.dyl, w.xh, w.xl, w.dA, gamma, B, N, C, s)) != GDN_OK) return rc;
   cam_de_kernel<<<B, 256, 0, as_stream(s)>>>(attn, w.dA, w.G, w.AT, w.rs, C);
   GDN_CHECK_LAUNCH();
   // O = dy + gamma * dy A ; O += G x ; dx (+)= O

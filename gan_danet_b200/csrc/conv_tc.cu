@@ -547,7 +547,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDYhi, const __grid_c
 
 // out[co][out_c0+ci][tap] (OIHW) (+)= scale * sum_s ws[s][co][tap][ci]   -- fixed summation order => deterministic
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ ws, int splits, int Cout, int Cin, int taps, int cin_w,
-                                       float* __restrict__ out, int out_cin_total, int out_c0, int accumulate, float scale) {
+                                       float* __restrict__ out, int out_cin_total, int out_c0, int accumulate, float scale,
+                                       const float* __restrict__ scale_ptr) {
+  if (scale_ptr) scale *= __ldg(scale_ptr);
   const long long total = (long long)Cout * taps * Cin;
   const size_t split_stride = (size_t)Cout * taps * cin_w;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -914,7 +916,8 @@ extern "C" int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s) {
   if (a->groups > 1) return GDN_OK;
   const long long total = (long long)a->Cout * p.taps_total * a->Cin;
   const int blocks = (int)(cdiv(total, 256) < 4 * kNumSMs ? cdiv(total, 256) : 4 * kNumSMs);
-  wgrad_tc_reduce_kernel<<<blocks, 256, 0, st>>>(a->ws, splits, a->Cout, a->Cin, p.taps_total, p.cin_w, a->out, a->out_cin_total, a->out_c0, a->accumulate, a->scale);
+  wgrad_tc_reduce_kernel<<<blocks, 256, 0, st>>>(a->ws, splits, a->Cout, a->Cin, p.taps_total, p.cin_w, a->out, a->out_cin_total, a->out_c0, a->accumulate, a->scale,
+                                                 a->scale_ptr);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

@@ -165,7 +165,8 @@ typedef struct {
   float* ws; size_t ws_bytes;
   int groups;              /* == B (1x1 only): per-sample Gram matrices out[b][Cout][Cin] = scale_ptr[0] * dy_b^T x_b, written directly
                               (the C x C energy of CAM, generator.py:132, and dA of its backward); ws unused */
-  const float* scale_ptr;  /* device scalar for the grouped mode; NULL = 1 */
+  const float* scale_ptr;  /* optional device scalar multiplied into the result (both modes); NULL = 1.  groups == B == 1 (one sample, cfg4)
+                              is the ordinary split-K path and needs ws */
 } gdn_wgrad_tc_args;
 size_t gdn_conv2d_wgrad_tc_ws_bytes(const gdn_wgrad_tc_args* a);
 int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s);
@@ -349,6 +350,29 @@ int gdn_adamw(float* p, const float* g, float* m, float* v, long long n, float l
 int gdn_adamw_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, float lr, float beta1,
                     float beta2, float eps, float wd, int step, float grad_scale, gdn_stream_t s);
 int gdn_fill(float* p, long long n, float value, gdn_stream_t s);
+
+/* ------------------------------------------- deep-ensemble statistics and inference post-processing (f1, f3) */
+/* out = keep ? (x + trend) * scale + shift : NaN on [rows][HW] fields: "+ trend", StandardScaler.inverse_transform and the
+ * tpb_h == 0 -> NaN masking of test.ipynb:180-191 / deep_ensemble.ipynb:415-416,450-457.  trend ([rows][HW]) and keep
+ * ([HW] bytes, 0 = masked) may be NULL. */
+int gdn_destandardise(const float* x, const float* trend, const unsigned char* keep, float* out, long long rows, long long HW, float scale, float shift,
+                      gdn_stream_t s);
+/* out[r] = np.nanmean over the kept pixels of x[r]*scale + shift (deep_ensemble.ipynb:459-460: spatial mean per member and
+ * month after masking); NaN inputs are skipped, a row without a valid pixel gives NaN.  keep may be NULL. */
+int gdn_masked_spatial_mean(const float* x, const unsigned char* keep, long long rows, long long HW, float scale, float shift, float* out, gdn_stream_t s);
+/* np.nanmean / np.nanstd (ddof 0) over M members (deep_ensemble.ipynb:463-464), member m at preds + m*member_stride, n
+ * elements each, values de-standardised by scale/shift first.  stdev may be NULL. */
+int gdn_ensemble_stats(const float* preds, long long member_stride, int M, long long n, float scale, float shift, float* mean, float* stdev, gdn_stream_t s);
+/* mild_histogram_matching (test.ipynb:115-125; weight 1 = simple_histogram_matching :104-113) per sample: src [B][ns],
+ * src_sorted / ref_sorted = ascending copies of the sample's source and reference values ([B][ns], [B][nt]),
+ * out = (1-weight)*src + weight*np.interp(cdf_src(src), cdf_ref, ref_values), CDF arithmetic in float64 as numpy's. */
+int gdn_hist_match(const float* src, const float* src_sorted, const float* ref_sorted, float* out, int B, int ns, int nt, float weight, gdn_stream_t s);
+/* F.interpolate(scale_factor=(scale_h, scale_w), mode='bicubic', align_corners=False) on [rows][Hi][Wi] planes
+ * (test.ipynb:553 x1.25, :559 x4); Ho = floor(Hi*scale_h), Wo = floor(Wi*scale_w) are passed by the caller. */
+int gdn_bicubic_resize(const float* x, float* y, long long rows, int Hi, int Wi, int Ho, int Wo, float scale_h, float scale_w, gdn_stream_t s);
+/* smooth_blend (test.ipynb:482-496): out = a*(1-mask) + b*mask inside the rectangle (r0, c0, h, w) of every [H][W] plane,
+ * a elsewhere; mask [h][w] is the caller's feather mask; out may alias a. */
+int gdn_blend_region(const float* a, const float* b, const float* mask, float* out, long long rows, int H, int W, int r0, int c0, int h, int w, gdn_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -178,12 +178,29 @@ def pam_blocked(x: Tensor, wq, bq, wk, bk, wv, bv, gamma, block: int = 1024) -> 
     k = conv2d(x, wk, bk).reshape(b, -1, n)
     v = conv2d(x, wv, bv).reshape(b, -1, n)
     outs = []
+    vt = v.transpose(1, 2).contiguous()                              # [B, N, C]
     for i0 in range(0, n, block):
-        e = torch.einsum("bdi,bdj->bij", q[:, :, i0:i0 + block], k)
-        a = softmax_lastdim(e)
-        outs.append(torch.einsum("bcj,bij->bci", v, a))
+        qb = q[:, :, i0:i0 + block].transpose(1, 2).contiguous()      # [B, blk, d]; plain matmuls: einsum on the strided slice is 10x slower
+        a = softmax_lastdim(qb @ k)                                   # energy rows i0.., generator.py:115-116
+        outs.append((a @ vt).transpose(1, 2))                         # out[b, c, i] = sum_j v[b, c, j] attn[b, i, j], :120
     out = torch.cat(outs, dim=2).reshape(b, c, h, w)
     return gamma * out + x
+
+
+def pam_rows(x: Tensor, wq, bq, wk, bk, wv, bv, gamma, rows: Tensor) -> Tensor:
+    """Rows ``rows`` (flat positions i = y*W + x) of :func:`pam`'s output: [B, C, len(rows)].  The same mathematics as
+    generator.py:113-122 restricted to those query positions (every key/value position still enters their softmax), so
+    the oracle of the high-resolution variant (N = 51200, BASELINE configs[3]) costs len(rows)*N instead of N*N.
+    Differentiable: a loss that only reads these rows has exactly the gradients of the full module under a cotangent
+    that is zero elsewhere."""
+    b, c, h, w = x.shape
+    n = h * w
+    q = conv2d(x, wq, bq).reshape(b, -1, n)[:, :, rows]
+    k = conv2d(x, wk, bk).reshape(b, -1, n)
+    v = conv2d(x, wv, bv).reshape(b, -1, n)
+    attn = softmax_lastdim(torch.einsum("bdi,bdj->bij", q, k))
+    out = torch.einsum("bcj,bij->bci", v, attn)
+    return gamma * out + x.reshape(b, c, n)[:, :, rows]
 
 
 def pam_core_flash(q: Tensor, k: Tensor, v: Tensor, block: int = 128) -> Tuple[Tensor, Tensor]:
@@ -271,9 +288,11 @@ def generator_structure(sd: SD) -> Tuple[int, int, bool]:
 
 
 def generator_forward(sd: SD, x: Tensor, training: bool = True, buffers_out: Optional[SD] = None,
-                      taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+                      taps: Optional[Dict[str, Tensor]] = None, pam_block: Optional[int] = None) -> Tensor:
     """FlexibleUpsamplingModule.forward, generator.py:230-247.  ``taps`` (if given)
-    receives named intermediate activations for per-stage parity checks."""
+    receives named intermediate activations for per-stage parity checks.  ``pam_block``: evaluate the position attention
+    in query blocks of that many rows (:func:`pam_blocked`, forward only) -- the 160x320 grid of BASELINE configs[3]."""
+    pam = globals()["pam"] if pam_block is None else (lambda *a: pam_blocked(*a, block=pam_block))
     blocks, layers, has_attn = generator_structure(sd)
 
     def tap(name, t):

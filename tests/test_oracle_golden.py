@@ -38,6 +38,27 @@ def test_pam(golden, oracle, name):
             assert rel_err(gr, g["grads"][k]) < 5e-6, k
 
 
+@pytest.mark.parametrize("name", ["pam_c160_8x16", "pam_c184_4x8"])
+def test_pam_rows(golden, oracle, name):
+    """Row-restricted restatement used as the oracle of the 160x320 grid (BASELINE configs[3]): its rows equal the
+    reference's output rows, and its gradients equal the reference's under a cotangent that is zero on the other rows."""
+    g = golden(name)
+    sd = {k: v.double().requires_grad_(True) for k, v in g["sd"].items()}
+    x = g["x"].double().requires_grad_(True)
+    args = [sd["query.weight"], sd["query.bias"], sd["key.weight"], sd["key.bias"], sd["value.weight"], sd["value.bias"], sd["gamma"]]
+    b, c, h, w = x.shape
+    rows = torch.tensor([0, 3, h * w // 2, h * w - 1])
+    yr = oracle.pam_rows(x, *args, rows)
+    assert rel_err(yr, g["y"].reshape(b, c, -1)[:, :, rows]) < TOL
+    r = torch.zeros(b, c, h * w, dtype=torch.float64)
+    r[:, :, rows] = g["r"].double().reshape(b, c, -1)[:, :, rows]
+    full = oracle.pam(x, *args)
+    want = torch.autograd.grad((full.reshape(b, c, -1) * r).sum(), [x] + args[:-1])
+    got = torch.autograd.grad((yr * r[:, :, rows]).sum(), [x] + args[:-1])
+    for a_, b_ in zip(got, want):
+        assert (a_ - b_).abs().max() < 1e-9 * b_.abs().max().clamp_min(1.0)
+
+
 @pytest.mark.parametrize("name", ["pam_c160_8x16"])
 def test_pam_flash_restatement(golden, oracle, name):
     """The online-softmax forward/backward restatement the CUDA kernels implement."""
