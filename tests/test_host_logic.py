@@ -88,3 +88,44 @@ def test_gradient_allreduce_gloo_world2():
         out = mgr.dict()
         mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
         assert out[0] and out[1]
+
+
+# ------------------------------------------------------------------------------------------------ ensemble sharding
+def test_member_placement():
+    from gan_danet_b200.ensemble import EnsembleTrainer, member_ranks
+    assert member_ranks(8, 8) == [[i] for i in range(8)]                        # BASELINE configs[4]: one member per B200
+    assert member_ranks(5, 2) == [[0, 2, 4], [1, 3]]
+    assert member_ranks(3, 1) == [[0, 1, 2]]
+    import tempfile
+    ens = EnsembleTrainer(5, {"epochs": 2}, ensemble_dir=tempfile.mkdtemp())
+    assert ens.seeds == [42, 43, 44, 45, 46]                                    # deep_ensemble.ipynb:312
+    assert ens.member_path(0).endswith("best_model_member_1.pth")               # :338
+    assert ens.local_members() == [0, 1, 2, 3, 4]
+    with pytest.raises(FileNotFoundError):
+        ens.load_ensemble_models(None, "cpu", 46)
+
+
+def _ens_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gan_danet_b200.ensemble import EnsembleTrainer, gather_members
+    import tempfile
+    M = 5
+    ens = EnsembleTrainer(M, {}, ensemble_dir=tempfile.mkdtemp())
+    mine = ens.local_members()
+    local = torch.stack([torch.full((2, 3), float(i)) for i in mine])          # member i's "field" is the constant i
+    full = gather_members(local, M)
+    ok = full.shape == (M, 2, 3) and all(bool((full[i] == float(i)).all()) for i in range(M)) and not torch.isnan(full).any()
+    out[rank] = bool(ok) and mine == ([0, 2, 4] if rank == 0 else [1, 3])
+    dist.destroy_process_group()
+
+
+def test_ensemble_gather_gloo_world2():
+    """Uneven ensemble (5 members on 2 ranks): NaN-padded all_gather, members back in index order on every rank."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_ens_worker, args=(2, port, out), nprocs=2, join=True)
+        assert out[0] and out[1]

@@ -281,3 +281,46 @@ def test_oracle_vs_live_reference(oracle):
     y_ref = G(x)
     y = oracle.generator_forward(sd, x, training=True)
     assert rel_err(y, y_ref) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------ rows after the step
+@pytest.fixture(scope="module")
+def post_oracle():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import postprocess_oracle
+    return postprocess_oracle
+
+
+def test_post_hist_match(golden, post_oracle):
+    """oracle hist_match == the reference's apply_mild_histogram_matching / simple_histogram_matching (test.ipynb:104-131)
+    on continuous, tied and unequal-size samples; the reference forms (1-w)*source in float32, hence 1e-6."""
+    import numpy as np
+    g = golden("postprocess")
+    for case in g["hist"]:
+        got = np.stack([post_oracle.hist_match(s, r, case["weight"]) for s, r in zip(case["src"].numpy(), case["ref"].numpy())])
+        assert np.abs(got - case["out"].numpy()).max() < 1e-6 * max(1.0, float(case["out"].abs().max())), case["weight"]
+    one = g["hist_simple"]
+    assert np.abs(post_oracle.hist_match(one["src"].numpy(), one["ref"].numpy(), 1.0) - one["out"].numpy()).max() < 1e-12
+
+
+def test_post_blend_and_uncertainty(golden, post_oracle):
+    import numpy as np
+    g = golden("postprocess")
+    for case in g["blend"]:
+        got = post_oracle.smooth_blend(case["a"].numpy(), case["b"].numpy(), tuple(case["region"]), case["sigma"])
+        assert np.abs(got - case["out"].numpy()).max() < 1e-6
+    u = g["uncertainty"]
+    _, mean_preds, std_preds, r2 = post_oracle.compute_uncertainty(u["preds"].numpy(), u["trues"].numpy(), u["keep"].numpy())
+    assert np.abs(mean_preds - u["mean_preds"].numpy()).max() < 1e-6
+    assert np.abs(std_preds - u["std_preds"].numpy()).max() < 1e-6
+    assert abs(r2 - u["r2"]) < 1e-6          # the reference averages in float32
+
+
+def test_post_resize(golden, oracle):
+    """The oracle's separable resampling matrices at the inference pipeline's scale factors (x1.25, x4: test.ipynb:553,559)."""
+    g = golden("postprocess")
+    for case in g["resize"]:
+        x = case["x"].double()
+        ho, wo = case["out"].shape[-2:]
+        got = oracle.resample2d(x, (ho, wo), "bicubic", scale=float(case["scale"]))
+        assert rel_err(got, case["out"]) < 1e-12, case["scale"]
