@@ -157,3 +157,47 @@ def test_ensemble_sweep_vs_oracle(oracle, post_oracle, tmp_path):
     _, wm, wsd, wr2 = post_oracle.compute_uncertainty(want.numpy(), (lr025.double() * scale + mean).numpy(), keep.numpy())
     assert np.abs(mean_preds - wm).max() < 1e-3 * np.abs(wm).max() and np.abs(std_preds - wsd).max() < 2e-3 * np.abs(wsd).max() + 1e-5
     assert abs(r2 - wr2) < 1e-3 * max(1.0, abs(wr2))      # the standardised targets have nearly constant spatial means: r2 is large and negative
+
+
+@pytest.mark.parametrize("hw,conv", [((8, 16), "fp32"), ((64, 128), "bf16")])
+def test_graphed_generator_matches_eager(hw, conv):
+    """the eval forward captured as one CUDA graph replays bit-identically to the eager launches, for new inputs
+    copied into the static buffers and after an in-place weight update."""
+    import gan_danet_b200 as P
+    from gan_danet_b200 import engine as E
+    from gan_danet_b200.inference import GraphedGenerator
+    from gan_danet_b200.synthetic import fast_batch
+    from gan_danet_b200.trainer import generator_forward_nhwc, prepare_input_nhwc
+    torch.manual_seed(0)
+    G = P.FlexibleUpsamplingModule(46)
+    G.apply(P.weights_init_normal)
+    with torch.no_grad():
+        for n, p in G.named_parameters():
+            if n.endswith("gamma"):
+                p.fill_(0.05)
+    G = G.to(DEV).eval()
+    old = E.conv_precision
+    E.set_conv_precision(conv)
+    try:
+        a = [t.to(DEV) for t in fast_batch(1, 2, *hw)]
+        b = [t.to(DEV) for t in fast_batch(2, 2, *hw)]
+        gg = GraphedGenerator(G, a[0], a[2])
+        assert gg.launches_captured > 100
+
+        def eager(lr05, aux):
+            with torch.no_grad():
+                return generator_forward_nhwc(G, prepare_input_nhwc(lr05, aux))
+
+        assert torch.equal(gg(a[0], a[2]), eager(a[0], a[2]))
+        assert torch.equal(gg(b[0], b[2]), eager(b[0], b[2]))
+        with torch.no_grad():
+            G.final.weight.mul_(1.5)
+        yb = gg(b[0], b[2])
+        assert torch.equal(yb, eager(b[0], b[2])) and torch.isfinite(yb).all()
+        with pytest.raises(Exception):
+            gg(a[0][:1], a[2][:1])
+        G.train()
+        with pytest.raises(Exception):
+            GraphedGenerator(G, a[0], a[2])
+    finally:
+        E.set_conv_precision(old)
