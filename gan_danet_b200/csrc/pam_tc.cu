@@ -299,7 +299,7 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 // Q[row][0..32) (fp16), lanes 4-7 those of K (fp16), lanes 8-31 the 24 chunks of V[row][0..192) (bf16; zero beyond C except the
 // channel of ones at column C, which makes the P.V product deliver the softmax denominator).
 __global__ void __launch_bounds__(256) pack_qkv_kernel(const float* __restrict__ q, const float* __restrict__ k, int qk_pitch, int d, const float* __restrict__ v, int v_pitch,
-                                                       int C, __half* __restrict__ Qh, __half* __restrict__ Kh, __nv_bfloat16* __restrict__ Vb, long long rows) {
+                                                       int C, __half* __restrict__ Qh, __half* __restrict__ Kh, __nv_bfloat16* __restrict__ Vb, long long rows, int vec4) {
   const int lane = threadIdx.x & 31;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
@@ -314,8 +314,18 @@ __global__ void __launch_bounds__(256) pack_qkv_kernel(const float* __restrict__
     } else {
       const int c0 = (lane - 8) * 8;
       __align__(16) __nv_bfloat16 h[8];
+      if (vec4) {     // C % 4 == 0, 16-byte aligned rows: a group of four channels is entirely inside or entirely outside the C valid ones
 #pragma unroll
-      for (int e = 0; e < 8; ++e) h[e] = __float2bfloat16_rn(c0 + e < C ? __ldg(v + (size_t)r * v_pitch + c0 + e) : (c0 + e == C ? 1.f : 0.f));
+        for (int g = 0; g < 2; ++g) {
+          const int c = c0 + 4 * g;
+          float4 f = c < C ? __ldg(reinterpret_cast<const float4*>(v + (size_t)r * v_pitch + c)) : make_float4(c == C ? 1.f : 0.f, 0.f, 0.f, 0.f);
+          h[4 * g + 0] = __float2bfloat16_rn(f.x); h[4 * g + 1] = __float2bfloat16_rn(f.y);
+          h[4 * g + 2] = __float2bfloat16_rn(f.z); h[4 * g + 3] = __float2bfloat16_rn(f.w);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) h[e] = __float2bfloat16_rn(c0 + e < C ? __ldg(v + (size_t)r * v_pitch + c0 + e) : (c0 + e == C ? 1.f : 0.f));
+      }
       *reinterpret_cast<uint4*>(Vb + (size_t)r * CPAD + c0) = *reinterpret_cast<const uint4*>(h);
     }
   }
@@ -385,7 +395,8 @@ extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
   __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(w);
   cudaStream_t st = as_stream(s);
   const long long pb = cdiv((long long)rows, 8);
-  pack_qkv_kernel<<<(unsigned)(pb < 16 * kNumSMs ? pb : 16 * kNumSMs), 256, 0, st>>>(a->q, a->k, a->qk_pitch, a->d, a->v, a->v_pitch, a->C, Qh, Kh, Vb, (long long)rows);
+  pack_qkv_kernel<<<(unsigned)(pb < 16 * kNumSMs ? pb : 16 * kNumSMs), 256, 0, st>>>(a->q, a->k, a->qk_pitch, a->d, a->v, a->v_pitch, a->C, Qh, Kh, Vb, (long long)rows,
+                                                                                     a->C % 4 == 0 && a->v_pitch % 4 == 0 && ((uintptr_t)a->v & 15) == 0);
   GDN_CHECK_LAUNCH();
   CUtensorMap mq, mk, mv;
   int rc;
