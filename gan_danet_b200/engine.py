@@ -768,7 +768,9 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
     B, H, W, Cc = x.t.shape
     N, d = H * W, q.t.shape[-1]
     dev = x.t.device
-    if precision == PREC_FP16 and (N % 128 != 0 or d > 32 or Cc > 192 or Cc % 4 != 0):
+    if precision == PREC_FP16 and N % 128 != 0 and pam_pad_to_tiles and d < 32 and Cc < 192 and Cc % 4 == 0:
+        return _op_pam_core_padded(tape, x, q, k, v, gamma, out)
+    if precision == PREC_FP16 and (N % 128 != 0 or d > 32 or Cc >= 192 or Cc % 4 != 0):
         precision = PREC_FP32      # shape outside the tensor-core kernel's tiling: fp32 CUDA-core engine
     if out is None:
         out = Var(torch.empty(x.t.shape, dtype=torch.float32, device=dev))
@@ -816,6 +818,53 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
             k.add_grad(dk)
         if v.needs_grad:
             v.add_grad(dv)
+        if x.needs_grad:
+            _accumulate(x, dy)
+
+    tape.push(bwd)
+    return y
+
+
+pam_pad_to_tiles: bool = os.environ.get("GDN_PAM_PAD", "1") != "0"   # N % 128 != 0 (the authors' 45x22 grid, N = 990) on the tensor-core kernels
+PAM_KEY_MASK = -30000.0     # exactly representable in fp16; exp2((q.k + PAM_KEY_MASK) * log2e - m) underflows to 0 (2^-125 on the polynomial lanes)
+
+
+def _op_pam_core_padded(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, out: Optional[Var], pad_to: Optional[int] = None) -> Var:
+    """The fused tcgen05 kernels tile N in blocks of 128.  Other grids are padded to the next multiple per sample and the
+    padded KEYS are masked through a spare column of the zero-padded logit operands (d < 32): q gets a column of ones, k a column
+    that is 0 on real positions and PAM_KEY_MASK on padded ones, so every padded logit is S = -30000 and its softmax weight is 0.
+    Padded QUERY rows are computed and dropped; in the backward their cotangent is zero, so they contribute nothing to dK / dV."""
+    B, H, W, Cc = x.t.shape
+    N, d = H * W, q.t.shape[-1]
+    Np = (N + 127) // 128 * 128 if pad_to is None else int(pad_to)      # pad_to: tests force padding on an already aligned grid
+    assert Np % 128 == 0 and Np >= N
+    dev = x.t.device
+
+    def padded(t: Tensor, width: int) -> Tensor:
+        buf = torch.zeros((B, 1, Np, width), dtype=torch.float32, device=dev)
+        buf[:, 0, :N, :t.shape[-1]].copy_(t.reshape(B, N, t.shape[-1]))
+        return buf
+
+    qp, kp = padded(q.t, d + 1), padded(k.t, d + 1)
+    qp[..., d] = 1.0
+    kp[:, 0, N:, d] = PAM_KEY_MASK
+    sub = Tape(record=tape.record)
+    vars_p = [Var(padded(x.t, Cc), False), Var(qp, q.needs_grad), Var(kp, k.needs_grad), Var(padded(v.t, Cc), v.needs_grad)]
+    yp = op_pam_core(sub, *vars_p, gamma, precision=PREC_FP16)
+    if out is None:
+        out = Var(torch.empty(x.t.shape, dtype=torch.float32, device=dev))
+    out.t.view(B, N, Cc).copy_(yp.t[:, 0, :N])          # view(): a channel slice of a concat buffer merges H and W without a copy
+    y = out
+
+    def bwd():
+        if y.g is None:
+            return
+        dy = y.g
+        yp.g = padded(dy, Cc)
+        sub.backward()                       # dq / dk / dv of the padded problem; gamma's gradient lands on the shared Var
+        for var, pv, width in ((q, vars_p[1], d), (k, vars_p[2], d), (v, vars_p[3], Cc)):
+            if var.needs_grad and pv.g is not None:
+                var.add_grad(pv.g[:, 0, :N, :width].reshape(B, H, W, width).contiguous())
         if x.needs_grad:
             _accumulate(x, dy)
 
