@@ -156,7 +156,8 @@ SIGNATURES = {
     "gdn_adamw_multi": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "gdn_fill": (_i, [_vp, _ll, _f, _vp]),
     "gdn_destandardise": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _f, _f, _vp]),
-    "gdn_masked_spatial_mean": (_i, [_vp, _vp, _ll, _ll, _f, _f, _vp, _vp]),
+    "gdn_masked_spatial_mean_ws_bytes": (_sz, [_ll, _ll]),
+    "gdn_masked_spatial_mean": (_i, [_vp, _vp, _ll, _ll, _f, _f, _vp, _vp, _sz, _vp]),
     "gdn_ensemble_stats": (_i, [_vp, _ll, _i, _ll, _f, _f, _vp, _vp, _vp]),
     "gdn_hist_match": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "gdn_bicubic_resize": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _f, _f, _vp]),

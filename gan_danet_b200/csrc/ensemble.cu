@@ -16,75 +16,149 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------ de-standardise (+ trend, + mask)
 // out[b][p] = keep[p] ? (x[b][p] + trend[b][p]) * scale + shift : NaN       (trend, keep optional)
+template <int V>
 __global__ void __launch_bounds__(256) destandardise_kernel(const float* __restrict__ x, const float* __restrict__ trend, const unsigned char* __restrict__ keep,
                                                             float* __restrict__ out, long long rows, long long HW, float scale, float shift) {
-  const long long total = rows * HW;
+  const long long total = rows * HW / V;
   const float nanv = __int_as_float(0x7fc00000);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    float v = __ldg(x + i);
-    if (trend) v += __ldg(trend + i);
-    v = fmaf(v, scale, shift);
-    if (keep && !keep[i % HW]) v = nanv;
-    out[i] = v;
+    float v[V];
+    if (V == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      if (trend) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(trend) + i);
+        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+      }
+    } else {
+      v[0] = __ldg(x + i);
+      if (trend) v[0] += __ldg(trend + i);
+    }
+    const long long p0 = (i * V) % HW;                  // V divides HW on the vector path: the V pixels are in one field
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      v[e] = fmaf(v[e], scale, shift);
+      if (keep && !keep[p0 + e]) v[e] = nanv;
+    }
+    if (V == 4) reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    else out[i] = v[0];
   }
 }
 
 // ------------------------------------------------------------------------------------------------ masked spatial mean
 // out[r] = nanmean_p { x[r][p]*scale + shift : keep[p] != 0 }  (NaN inputs are skipped like np.nanmean; no valid pixel -> NaN).
-// One CTA per row: 256 threads stride the H*W pixels (coalesced), per-thread partial sums in double, fixed-order block reduction.
-__global__ void __launch_bounds__(256) masked_spatial_mean_kernel(const float* __restrict__ x, const unsigned char* __restrict__ keep, long long HW, float scale,
-                                                                  float shift, float* __restrict__ out) {
+// Grid (rows, splits): every CTA reduces one contiguous chunk of one row (128-bit loads when the chunk allows, per-thread partial sums in
+// double, fixed-order block reduction) into ws[row][split] = (sum, count); the finish kernel adds the splits in order.  Bitwise reproducible.
+__global__ void __launch_bounds__(256) masked_spatial_mean_kernel(const float* __restrict__ x, const unsigned char* __restrict__ keep, long long HW, long long chunk,
+                                                                  float scale, float shift, double2* __restrict__ ws, int vec4) {
   __shared__ double red[32];
   const float* row = x + (long long)blockIdx.x * HW;
+  const long long p0 = (long long)blockIdx.y * chunk;
+  const long long p1 = p0 + chunk < HW ? p0 + chunk : HW;
   double s = 0.0, c = 0.0;
-  for (long long p = threadIdx.x; p < HW; p += blockDim.x) {
-    const float v = __ldg(row + p);
-    if ((keep == nullptr || keep[p]) && v == v) { s += (double)fmaf(v, scale, shift); c += 1.0; }
+  if (vec4) {
+    for (long long p = p0 + 4LL * threadIdx.x; p < p1; p += 4LL * blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(row + p));
+      const float f[4] = {v.x, v.y, v.z, v.w};
+      unsigned k4 = 0x01010101u;
+      if (keep) k4 = __ldg(reinterpret_cast<const unsigned*>(keep + p));
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (((k4 >> (8 * e)) & 0xffu) && f[e] == f[e]) { s += (double)fmaf(f[e], scale, shift); c += 1.0; }
+    }
+  } else {
+    for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+      const float v = __ldg(row + p);
+      if ((keep == nullptr || keep[p]) && v == v) { s += (double)fmaf(v, scale, shift); c += 1.0; }
+    }
   }
   s = block_sum(s, red);
   c = block_sum(c, red);
-  if (threadIdx.x == 0) out[blockIdx.x] = c > 0.0 ? (float)(s / c) : __int_as_float(0x7fc00000);
+  if (threadIdx.x == 0) ws[(long long)blockIdx.x * gridDim.y + blockIdx.y] = make_double2(s, c);
+}
+__global__ void masked_spatial_mean_finish_kernel(const double2* __restrict__ ws, int splits, long long rows, float* __restrict__ out) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double s = 0.0, c = 0.0;
+  for (int k = 0; k < splits; ++k) { const double2 v = ws[r * splits + k]; s += v.x; c += v.y; }
+  out[r] = c > 0.0 ? (float)(s / c) : __int_as_float(0x7fc00000);
 }
 
 // ------------------------------------------------------------------------------------------------ statistics over the members
 // preds: M fields of n elements (member m at preds + m*stride).  mean[i], std[i] over the non-NaN members (ddof = 0, np.nanstd);
 // two passes over the members held in registers for M <= 16 (the one-per-GPU ensemble), re-read otherwise.
-template <int MAXM>
+template <int MAXM, int V>
 __global__ void __launch_bounds__(256) ensemble_stats_kernel(const float* __restrict__ preds, long long stride, int M, long long n, float scale, float shift,
                                                              float* __restrict__ mean, float* __restrict__ stdev) {
   const float nanv = __int_as_float(0x7fc00000);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float v[MAXM > 0 ? MAXM : 1];
-    double s = 0.0;
-    int c = 0;
+  const long long total = n / V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v[MAXM > 0 ? MAXM : 1][V];
+    double s[V];
+    int c[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { s[e] = 0.0; c[e] = 0; }
+    auto load = [&](int m, float* dst) {
+      if (V == 4) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(preds + m * stride) + i);
+        dst[0] = f.x; dst[1] = f.y; dst[2] = f.z; dst[3] = f.w;
+      } else {
+        dst[0] = __ldg(preds + m * stride + i);
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) dst[e] = fmaf(dst[e], scale, shift);
+    };
     if (MAXM > 0) {
 #pragma unroll
       for (int m = 0; m < MAXM; ++m) {
-        v[m] = m < M ? fmaf(__ldg(preds + m * stride + i), scale, shift) : nanv;
-        if (v[m] == v[m]) { s += (double)v[m]; ++c; }
-      }
-    } else {
-      for (int m = 0; m < M; ++m) {
-        const float t = fmaf(__ldg(preds + m * stride + i), scale, shift);
-        if (t == t) { s += (double)t; ++c; }
-      }
-    }
-    if (c == 0) { mean[i] = nanv; if (stdev) stdev[i] = nanv; continue; }
-    const double mu = s / c;
-    mean[i] = (float)mu;
-    if (!stdev) continue;
-    double q = 0.0;
-    if (MAXM > 0) {
+        if (m < M) load(m, v[m]);
+        else {
 #pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (v[m] == v[m]) { const double dlt = (double)v[m] - mu; q += dlt * dlt; }
+          for (int e = 0; e < V; ++e) v[m][e] = nanv;
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          if (v[m][e] == v[m][e]) { s[e] += (double)v[m][e]; ++c[e]; }
+      }
     } else {
       for (int m = 0; m < M; ++m) {
-        const float t = fmaf(__ldg(preds + m * stride + i), scale, shift);
-        if (t == t) { const double dlt = (double)t - mu; q += dlt * dlt; }
+        float t[V];
+        load(m, t);
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          if (t[e] == t[e]) { s[e] += (double)t[e]; ++c[e]; }
       }
     }
-    stdev[i] = (float)sqrt(q / c);
+    double mu[V], q[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { mu[e] = c[e] ? s[e] / c[e] : 0.0; q[e] = 0.0; }
+    if (stdev) {
+      if (MAXM > 0) {
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m)
+#pragma unroll
+          for (int e = 0; e < V; ++e)
+            if (v[m][e] == v[m][e]) { const double dlt = (double)v[m][e] - mu[e]; q[e] += dlt * dlt; }
+      } else {
+        for (int m = 0; m < M; ++m) {
+          float t[V];
+          load(m, t);
+#pragma unroll
+          for (int e = 0; e < V; ++e)
+            if (t[e] == t[e]) { const double dlt = (double)t[e] - mu[e]; q[e] += dlt * dlt; }
+        }
+      }
+    }
+    float om[V], os[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { om[e] = c[e] ? (float)mu[e] : nanv; os[e] = c[e] ? (float)sqrt(q[e] / c[e]) : nanv; }
+    if (V == 4) {
+      reinterpret_cast<float4*>(mean)[i] = make_float4(om[0], om[1], om[2], om[3]);
+      if (stdev) reinterpret_cast<float4*>(stdev)[i] = make_float4(os[0], os[1], os[2], os[3]);
+    } else {
+      mean[i] = om[0];
+      if (stdev) stdev[i] = os[0];
+    }
   }
 }
 
@@ -112,6 +186,10 @@ __global__ void __launch_bounds__(256) hist_match_kernel(const float* __restrict
   const float* T = ref_sorted + (long long)blockIdx.y * nt;
   const float* x = src + (long long)blockIdx.y * ns;
   float* o = out + (long long)blockIdx.y * ns;
+  __shared__ int first_knot_s;                                                  // end of the first run of T: once per CTA, not per element
+  if (threadIdx.x == 0) first_knot_s = upper_bound(T, nt, T[0]) - 1;
+  __syncthreads();
+  const int first_knot = first_knot_s;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
     const float v = x[i];
     const double sq = (double)upper_bound(S, ns, v) / (double)ns;
@@ -120,15 +198,15 @@ __global__ void __launch_bounds__(256) hist_match_kernel(const float* __restrict
     while (j0 + 1 < nt && (double)(j0 + 2) / (double)nt <= sq) ++j0;          // guard the floor against rounding
     while (j0 >= 0 && (double)(j0 + 1) / (double)nt > sq) --j0;
     double m;
-    const int first_knot = upper_bound(T, nt, T[0]) - 1;
     if (j0 < first_knot) {
       m = (double)T[0];                                                       // np.interp: left of the first knot -> f_0
     } else {
-      const int jl = (j0 + 1 < nt && T[j0] == T[j0 + 1]) ? lower_bound(T, nt, T[j0]) - 1 : j0;   // j0 inside a run: the previous run's end
+      // j0 inside a run of equal values: the previous run's end.  Distinct neighbours (the common case for continuous fields) need no search.
+      const int jl = (j0 + 1 < nt && T[j0] == T[j0 + 1]) ? lower_bound(T, nt, T[j0]) - 1 : j0;
       if (jl + 1 >= nt) {
         m = (double)T[nt - 1];
       } else {
-        const int jh = upper_bound(T, nt, T[jl + 1]) - 1;
+        const int jh = (jl + 2 < nt && T[jl + 1] == T[jl + 2]) ? upper_bound(T, nt, T[jl + 1]) - 1 : jl + 1;
         const double xl = (double)(jl + 1) / (double)nt, xh = (double)(jh + 1) / (double)nt;
         const double fl = (double)T[jl], fh = (double)T[jh];
         m = sq >= xh ? fh : fl + (sq - xl) * ((fh - fl) / (xh - xl));        // numpy: slope*(x - xp[j]) + fp[j]
@@ -194,7 +272,7 @@ __global__ void __launch_bounds__(256) blend_region_kernel(const float* __restri
 
 int grid_for(long long total, int threads) {
   long long b = cdiv(total, threads);
-  const long long cap = 8LL * kNumSMs;
+  const long long cap = 32LL * kNumSMs;        // 8 resident CTAs of 256 threads per SM x 4 waves of grid-stride work
   if (b > cap) b = cap;
   return (int)(b < 1 ? 1 : b);
 }
@@ -204,31 +282,61 @@ int grid_for(long long total, int threads) {
 extern "C" int gdn_destandardise(const float* x, const float* trend, const unsigned char* keep, float* out, long long rows, long long HW, float scale, float shift,
                                  gdn_stream_t s) {
   GDN_CHECK_ARG(x && out && rows > 0 && HW > 0);
-  destandardise_kernel<<<grid_for(rows * HW, 256), 256, 0, as_stream(s)>>>(x, trend, keep, out, rows, HW, scale, shift);
+  const bool v4 = HW % 4 == 0 && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)trend) & 15) == 0;
+  if (v4) destandardise_kernel<4><<<grid_for(rows * HW / 4, 256), 256, 0, as_stream(s)>>>(x, trend, keep, out, rows, HW, scale, shift);
+  else destandardise_kernel<1><<<grid_for(rows * HW, 256), 256, 0, as_stream(s)>>>(x, trend, keep, out, rows, HW, scale, shift);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
 
-extern "C" int gdn_masked_spatial_mean(const float* x, const unsigned char* keep, long long rows, long long HW, float scale, float shift, float* out, gdn_stream_t s) {
-  GDN_CHECK_ARG(x && out && rows > 0 && rows < (1LL << 31) && HW > 0);
-  masked_spatial_mean_kernel<<<(unsigned)rows, 256, 0, as_stream(s)>>>(x, keep, HW, scale, shift, out);
+static int masked_mean_splits(long long rows, long long HW) {
+  long long want = cdiv(8LL * kNumSMs, rows);                  // >= 8 CTAs per SM in flight
+  const long long most = cdiv(HW, 4096);                       // a chunk is at least 4096 pixels (16 per thread)
+  if (want > most) want = most;
+  return (int)(want < 1 ? 1 : want);
+}
+extern "C" size_t gdn_masked_spatial_mean_ws_bytes(long long rows, long long HW) { return (size_t)rows * masked_mean_splits(rows, HW) * sizeof(double2); }
+extern "C" int gdn_masked_spatial_mean(const float* x, const unsigned char* keep, long long rows, long long HW, float scale, float shift, float* out, void* ws,
+                                       size_t ws_bytes, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && out && ws && rows > 0 && rows < (1LL << 31) && HW > 0 && ((uintptr_t)ws & 15) == 0);
+  if (ws_bytes < gdn_masked_spatial_mean_ws_bytes(rows, HW)) { set_error("gdn_masked_spatial_mean: workspace too small"); return GDN_EWORKSPACE; }
+  const int splits = masked_mean_splits(rows, HW);
+  long long chunk = cdiv(HW, splits);
+  chunk = (chunk + 3) & ~3LL;
+  const int vec4 = HW % 4 == 0 && ((uintptr_t)x & 15) == 0 && (keep == nullptr || ((uintptr_t)keep & 3) == 0);
+  dim3 grid((unsigned)rows, (unsigned)splits);
+  GDN_CHECK_ARG(splits <= 65535);
+  masked_spatial_mean_kernel<<<grid, 256, 0, as_stream(s)>>>(x, keep, HW, chunk, scale, shift, reinterpret_cast<double2*>(ws), vec4);
+  GDN_CHECK_LAUNCH();
+  masked_spatial_mean_finish_kernel<<<(unsigned)cdiv(rows, 256), 256, 0, as_stream(s)>>>(reinterpret_cast<const double2*>(ws), splits, rows, out);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
 
 extern "C" int gdn_ensemble_stats(const float* preds, long long member_stride, int M, long long n, float scale, float shift, float* mean, float* stdev, gdn_stream_t s) {
   GDN_CHECK_ARG(preds && mean && M > 0 && n > 0 && member_stride >= 0);
-  const int grid = grid_for(n, 256);
-  if (M <= 8) ensemble_stats_kernel<8><<<grid, 256, 0, as_stream(s)>>>(preds, member_stride, M, n, scale, shift, mean, stdev);
-  else if (M <= 16) ensemble_stats_kernel<16><<<grid, 256, 0, as_stream(s)>>>(preds, member_stride, M, n, scale, shift, mean, stdev);
-  else ensemble_stats_kernel<0><<<grid, 256, 0, as_stream(s)>>>(preds, member_stride, M, n, scale, shift, mean, stdev);
+  const bool v4 = n % 4 == 0 && member_stride % 4 == 0 && (((uintptr_t)preds | (uintptr_t)mean | (uintptr_t)stdev) & 15) == 0;
+  cudaStream_t st = as_stream(s);
+  if (v4) {
+    const int grid = grid_for(n / 4, 256);
+    if (M <= 8) ensemble_stats_kernel<8, 4><<<grid, 256, 0, st>>>(preds, member_stride, M, n, scale, shift, mean, stdev);
+    else ensemble_stats_kernel<0, 4><<<grid, 256, 0, st>>>(preds, member_stride, M, n, scale, shift, mean, stdev);
+  } else {
+    const int grid = grid_for(n, 256);
+    if (M <= 8) ensemble_stats_kernel<8, 1><<<grid, 256, 0, st>>>(preds, member_stride, M, n, scale, shift, mean, stdev);
+    else if (M <= 16) ensemble_stats_kernel<16, 1><<<grid, 256, 0, st>>>(preds, member_stride, M, n, scale, shift, mean, stdev);
+    else ensemble_stats_kernel<0, 1><<<grid, 256, 0, st>>>(preds, member_stride, M, n, scale, shift, mean, stdev);
+  }
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
 
 extern "C" int gdn_hist_match(const float* src, const float* src_sorted, const float* ref_sorted, float* out, int B, int ns, int nt, float weight, gdn_stream_t s) {
   GDN_CHECK_ARG(src && src_sorted && ref_sorted && out && B > 0 && B <= 65535 && ns > 0 && nt > 0);
-  dim3 grid((unsigned)grid_for(ns, 256), (unsigned)B);
+  long long per_sample = cdiv(16LL * kNumSMs, B);                  // ~16 CTAs per SM over all samples, at least 4 elements per thread
+  const long long most = cdiv(ns, 1024);
+  if (per_sample > most) per_sample = most;
+  dim3 grid((unsigned)(per_sample < 1 ? 1 : per_sample), (unsigned)B);
   hist_match_kernel<<<grid, 256, 0, as_stream(s)>>>(src, src_sorted, ref_sorted, out, ns, nt, weight);
   GDN_CHECK_LAUNCH();
   return GDN_OK;

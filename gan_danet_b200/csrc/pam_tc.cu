@@ -133,7 +133,7 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     }
   } else if (warp == 1) {
     // ---- P.V issuer: the whole warp runs the loop (uniform control flow and descriptors), one elected lane issues
-    // A = P and B = V are bf16; bit 16: B is MN-major.  N = n_pv: C = 160 needs 176 of the 192 padded channel columns (8 % fewer tensor-core cycles)
+    // A = P and B = V are bf16; bit 16: B is MN-major.  N = n_pv: C = 160 needs 176 of the 192 padded channel columns (measured: no change, 806 TFLOP/s either way -- the tensor pipe is not this kernel's limiter)
     const uint32_t IDESC_PV = idesc_f16(TQ, p.n_pv) | (1u << 7) | (1u << 10) | (1u << 16);
     const uint64_t vd_base = smem_desc_mn(base + OFF_V, V_CHUNK, 1024, LAYOUT_SW128);     // 64-channel groups 8 KB apart, 8-key groups 1 KB apart
     const uint32_t tmem_o = tmem + COL_O;

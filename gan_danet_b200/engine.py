@@ -376,7 +376,7 @@ def conv_forward(x: Tensor, w: Tensor, y: Optional[Tensor], *, stride: int = 1, 
     B, Hi, Wi, Cin = x.shape
     Ho, Wo = (Hi + 2 * pad - kh) // stride + 1, (Wi + 2 * pad - kw) // stride + 1
     if y is None or x_packed is not None:
-        assert tc_eligible(Cin, O, kh, kw, stride, Ho, Wo) and conv_precision == "bf16" and (y16 is not None or y is not None)
+        assert tc_eligible(Cin, O, kh, kw, stride, Ho, Wo) and (conv_precision == "bf16" or (y is not None and y16 is None)) and (y16 is not None or y is not None)
         xp = x_packed if x_packed is not None else pack_act(x)
         conv_tc_raw(xp, pack_weight(w, False, frozen_key), y, (Hi, Wi), cin=Cin, kh=kh, kw=kw, stride=stride, pad=pad, bias=bias, act=act, slope=slope, res=res,
                     y16=y16, out_shape=(B, Ho, Wo, O))
@@ -520,10 +520,11 @@ def dot_ws(device) -> Tensor:
 
 class Var:
     """A tensor on the tape plus its (lazily created) gradient.  ``parent`` marks a channel slice of a wider buffer."""
-    __slots__ = ("t", "_g", "needs_grad", "parent", "c0", "c1")
+    __slots__ = ("t", "_g", "needs_grad", "parent", "c0", "c1", "packed")
 
     def __init__(self, t: Tensor, needs_grad: bool = True, parent: Optional["Var"] = None, c0: int = 0, c1: int = 0):
         self.t, self._g, self.needs_grad, self.parent, self.c0, self.c1 = t, None, needs_grad, parent, c0, c1
+        self.packed: Optional["Packed"] = None      # set by op_bn_act(packed_only=True): the value exists ONLY as a bf16 tensor-core operand (t is a shape carrier)
 
     @property
     def g(self) -> Optional[Tensor]:
@@ -603,7 +604,7 @@ def op_conv(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, stride: int = 1,
     if out is None:
         out = Var(new_nhwc(B, Ho, Wo, O, x.t))
     cctx = conv_forward(x.t, w.t.detach(), out.t, stride=stride, pad=pad, bias=None if bias is None else bias.t.detach(), act=act, slope=slope,
-                        keep=tape.record and w.needs_grad)
+                        keep=tape.record and w.needs_grad, x_packed=x.packed)
     y = out
 
     def bwd():
@@ -711,9 +712,27 @@ class BNState:
         self.num_batches_tracked, self.eps, self.momentum = num_batches_tracked, eps, momentum
 
 
+fuse_bn_into_pack: bool = os.environ.get("GDN_FUSE_BN_PACK", "1") != "0"
+
+
+def op_bn_act_conv(tape: Tape, x: Var, bn: BNState, w: Var, bias: Optional[Var], *, training: bool, act: int = ACT_RELU, slope: float = 0.0,
+                   stride: int = 1, pad: int = 0, out: Optional[Var] = None) -> Var:
+    """conv(act(BN(x))) (DenseLayer generator.py:32-34, TransitionLayer :61-63).  On the tensor-core path the normalised activation is
+    never stored in fp32: the per-channel affine + ReLU is applied while the convolution's bf16 operand is packed (x read once, 2 B/element
+    written, instead of 4 + 4 for the BN output and 4 + 2 for its packing); the backward needs x, the coefficients and the packed operand only."""
+    O, _, kh, kw = w.t.shape
+    _, Hi, Wi, Cin = x.t.shape
+    Ho, Wo = (Hi + 2 * pad - kh) // stride + 1, (Wi + 2 * pad - kw) // stride + 1
+    fused = (fuse_bn_into_pack and tc_eligible(Cin, O, kh, kw, stride, Ho, Wo) and not (thin_conv_enabled and kh == 3 and (Cin == 1 or O == 1)))
+    h = op_bn_act(tape, x, bn, training=training, act=act, slope=slope, packed_only=fused)
+    return op_conv(tape, h, w, bias, stride=stride, pad=pad, out=out)
+
+
 def op_bn_act(tape: Tape, x: Var, bn: BNState, *, training: bool, act: int = ACT_RELU, slope: float = 0.0, out: Optional[Var] = None,
-              update_running: bool = True) -> Var:
-    """nn.BatchNorm2d (train: batch statistics + running-stat update; eval: running statistics) followed by an activation."""
+              update_running: bool = True, packed_only: bool = False) -> Var:
+    """nn.BatchNorm2d (train: batch statistics + running-stat update; eval: running statistics) followed by an activation.
+    ``packed_only``: the result is produced as the bf16 operand of the one tensor-core convolution that consumes it (``Var.packed``);
+    the returned Var's tensor is x's own (shape carrier, never read)."""
     lib = _lib(x.t)
     Cc = x.t.shape[-1]
     M = rows_of(x.t)
@@ -731,9 +750,14 @@ def op_bn_act(tape: Tape, x: Var, bn: BNState, *, training: bool, act: int = ACT
     else:
         L.check(lib.gdn_bn_eval_coeffs(bn.weight.t.data_ptr(), bn.bias.t.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                        bn.eps, Cc, scale.data_ptr(), shift.data_ptr(), _stream()), "gdn_bn_eval_coeffs")
-    if out is None:
-        out = Var(torch.empty(x.t.shape, dtype=torch.float32, device=dev))
-    affine_act(x.t, out.t, scale, shift, act, slope)
+    if packed_only:
+        assert out is None
+        out = Var(x.t)
+        out.packed = pack_act(x.t, scale, shift, act, slope)
+    else:
+        if out is None:
+            out = Var(torch.empty(x.t.shape, dtype=torch.float32, device=dev))
+        affine_act(x.t, out.t, scale, shift, act, slope)
     y = out
 
     def bwd():

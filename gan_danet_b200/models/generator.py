@@ -142,8 +142,8 @@ class DenseLayer(TapeModule):
     def _build_into(self, ctx: BuildCtx, buf: E.Var, cin: int) -> None:
         """buf[..., :cin] holds x; writes the new features into buf[..., cin:cin+growth]."""
         x = buf.slice(0, cin)
-        h = E.op_bn_act(ctx.tape, x, ctx.bn(self.bn), training=self.bn.training, act=ACT_RELU)
-        _conv(ctx, h, self.conv, out=buf.slice(cin, cin + self.conv.out_channels))
+        E.op_bn_act_conv(ctx.tape, x, ctx.bn(self.bn), ctx.v(self.conv.weight), ctx.v(self.conv.bias), training=self.bn.training, act=ACT_RELU,
+                         stride=self.conv.stride[0], pad=self.conv.padding[0], out=buf.slice(cin, cin + self.conv.out_channels))
 
     def _build(self, ctx: BuildCtx, x: E.Var) -> E.Var:
         B, H, W, Cc = x.t.shape
@@ -191,8 +191,9 @@ class TransitionLayer(TapeModule):
         self.layer = nn.Sequential(nn.BatchNorm2d(in_channels), nn.ReLU(inplace=True), nn.Conv2d(in_channels, out_channels, kernel_size=1))
 
     def _build(self, ctx: BuildCtx, x: E.Var, out: Optional[E.Var] = None) -> E.Var:
-        h = E.op_bn_act(ctx.tape, x, ctx.bn(self.layer[0]), training=self.layer[0].training, act=ACT_RELU)
-        return _conv(ctx, h, self.layer[2], out=out)
+        conv = self.layer[2]
+        return E.op_bn_act_conv(ctx.tape, x, ctx.bn(self.layer[0]), ctx.v(conv.weight), ctx.v(conv.bias), training=self.layer[0].training, act=ACT_RELU,
+                                stride=conv.stride[0], pad=conv.padding[0], out=out)
 
 
 class PAMModule(TapeModule):

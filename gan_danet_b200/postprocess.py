@@ -53,8 +53,10 @@ def masked_spatial_mean(x: torch.Tensor, keep: Optional[torch.Tensor] = None, sc
     hw = x.shape[-1] * x.shape[-2]
     k = _keep_bytes(keep, x, hw)
     out = torch.empty(x.shape[:-2], dtype=torch.float32, device=x.device)
-    L.check(E._lib(x).gdn_masked_spatial_mean(x.data_ptr(), k.data_ptr() if k is not None else None, x.numel() // hw, hw, float(scale), float(shift),
-                                              out.data_ptr(), E._stream()), "gdn_masked_spatial_mean")
+    lib, rows = E._lib(x), x.numel() // hw
+    ws = E.workspace("spatial_mean", lib.gdn_masked_spatial_mean_ws_bytes(rows, hw), x.device)
+    L.check(lib.gdn_masked_spatial_mean(x.data_ptr(), k.data_ptr() if k is not None else None, rows, hw, float(scale), float(shift),
+                                        out.data_ptr(), ws.data_ptr(), ws.numel(), E._stream()), "gdn_masked_spatial_mean")
     return out
 
 

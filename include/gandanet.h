@@ -358,8 +358,11 @@ int gdn_fill(float* p, long long n, float value, gdn_stream_t s);
 int gdn_destandardise(const float* x, const float* trend, const unsigned char* keep, float* out, long long rows, long long HW, float scale, float shift,
                       gdn_stream_t s);
 /* out[r] = np.nanmean over the kept pixels of x[r]*scale + shift (deep_ensemble.ipynb:459-460: spatial mean per member and
- * month after masking); NaN inputs are skipped, a row without a valid pixel gives NaN.  keep may be NULL. */
-int gdn_masked_spatial_mean(const float* x, const unsigned char* keep, long long rows, long long HW, float scale, float shift, float* out, gdn_stream_t s);
+ * month after masking); NaN inputs are skipped, a row without a valid pixel gives NaN.  keep may be NULL.
+ * ws: gdn_masked_spatial_mean_ws_bytes(rows, HW) bytes, 16-byte aligned (per-row partial sums of the row splits). */
+size_t gdn_masked_spatial_mean_ws_bytes(long long rows, long long HW);
+int gdn_masked_spatial_mean(const float* x, const unsigned char* keep, long long rows, long long HW, float scale, float shift, float* out, void* ws,
+                            size_t ws_bytes, gdn_stream_t s);
 /* np.nanmean / np.nanstd (ddof 0) over M members (deep_ensemble.ipynb:463-464), member m at preds + m*member_stride, n
  * elements each, values de-standardised by scale/shift first.  stdev may be NULL. */
 int gdn_ensemble_stats(const float* preds, long long member_stride, int M, long long n, float scale, float shift, float* mean, float* stdev, gdn_stream_t s);

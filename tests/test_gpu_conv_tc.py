@@ -123,3 +123,55 @@ def test_perceptual_bf16_feature_storage():
     (l0, g0), (l1, g1) = res
     assert abs(l1 - l0) <= 1e-5 * abs(l0), (l0, l1)
     assert rel(g1, g0) < 1e-5, rel(g1, g0)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("train", [True, False])
+def test_bn_relu_fused_into_operand_packing(precision, train):
+    """DenseBlock (generator.py:29-54) and TransitionLayer (:57-67) with BatchNorm + ReLU applied while the convolution's bf16
+    operand is packed (engine.op_bn_act_conv: the normalised activation never exists in fp32) against the unfused launches
+    (BN + ReLU kernel, then packing): the same fused multiply-add and the same rounding, so outputs, input gradient, every
+    parameter gradient and the running statistics must agree to float32 round-off."""
+    from gan_danet_b200 import engine as E
+    from gan_danet_b200.models import generator as PG
+    import gan_danet_b200 as P
+    dev = "cuda:0"
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 64, 16, 24, generator=gen)
+    r1 = torch.randn(2, 160, 16, 24, generator=gen)
+
+    def run(fuse):
+        torch.manual_seed(5)
+        blk, tr = PG.DenseBlock(4, 64, 24), PG.TransitionLayer(160, 80)
+        for m in (blk, tr):
+            m.apply(P.weights_init_normal)
+        seq = torch.nn.Sequential(blk, tr).to(dev)
+        seq.train(train)
+        old, oldf = E.conv_precision, E.fuse_bn_into_pack
+        E.set_conv_precision(precision)
+        E.fuse_bn_into_pack = fuse
+        try:
+            xg = x.to(dev).requires_grad_(train)
+            if train:
+                y = seq(xg)
+                y.backward(torch.ones_like(y) * 0.5 + y.detach() * 0.1)
+            else:
+                with torch.no_grad():
+                    y = seq(xg)
+            torch.cuda.synchronize()
+        finally:
+            E.set_conv_precision(old)
+            E.fuse_bn_into_pack = oldf
+        grads = {k: p.grad.detach() for k, p in seq.named_parameters()} if train else {}
+        bufs = {k: v.detach().clone() for k, v in seq.state_dict().items() if "running" in k}
+        return y.detach(), (xg.grad.detach() if train else None), grads, bufs
+
+    yf, dxf, gf, bf = run(True)
+    yu, dxu, gu, bu = run(False)
+    assert rel(yf, yu) < 1e-6, rel(yf, yu)
+    for k in bu:
+        assert rel(bf[k], bu[k]) < 1e-6, k
+    if train:
+        assert rel(dxf, dxu) < 1e-5, rel(dxf, dxu)
+        for k in gu:
+            assert rel(gf[k], gu[k]) < 1e-5 or float(gu[k].abs().max()) < 1e-6, (k, rel(gf[k], gu[k]))
