@@ -60,3 +60,27 @@ def test_no_cpu_fallback():
     G = g.FlexibleUpsamplingModule(4, growth_rate=4, num_blocks=1, num_layers_per_block=1)
     with pytest.raises(g._lib.GdnError if hasattr(g, "_lib") else Exception):
         G(torch.zeros(1, 4, 4, 4))
+
+
+def test_custom_op_layer_registered():
+    """torch.ops.gandanet.* exist, infer shapes on meta tensors (register_fake) and have NO CPU kernel."""
+    import pytest
+    import torch
+    import gan_danet_b200.ops as O
+    for name in O.OPS:
+        assert hasattr(torch.ops.gandanet, name), name
+    x = torch.empty(2, 8, 16, 160, device="meta")
+    q = torch.empty(2, 8, 16, 20, device="meta")
+    g = torch.empty(1, device="meta")
+    y, o, lse = torch.ops.gandanet.pam_fwd(x, q, q, x, g, "fp16")
+    assert y.shape == x.shape and o.shape == (2, 128, 160) and lse.shape == (2, 128)
+    y, attn = torch.ops.gandanet.cam_fwd(x, g, True)
+    assert attn.shape == (2, 160, 160)
+    w = torch.empty(24, 160, 3, 3, device="meta")
+    assert torch.ops.gandanet.conv2d(x, w, None, 1, 1, 1, 0.0).shape == (2, 8, 16, 24)
+    assert torch.ops.gandanet.conv2d(x, w, None, 2, 1, 0, 0.0).shape == (2, 4, 8, 24)
+    assert torch.ops.gandanet.upsample_bicubic2x(x).shape == (2, 16, 32, 160)
+    with pytest.raises(NotImplementedError):
+        torch.ops.gandanet.upsample_bicubic2x(torch.zeros(1, 2, 2, 4))
+    with pytest.raises(NotImplementedError):
+        torch.ops.gandanet.pam_fwd(torch.zeros(1, 8, 16, 8), torch.zeros(1, 8, 16, 1), torch.zeros(1, 8, 16, 1), torch.zeros(1, 8, 16, 8), torch.zeros(1), "fp32")

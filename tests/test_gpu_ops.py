@@ -1,0 +1,118 @@
+"""torch.ops.gandanet.* (gan_danet_b200/ops.py, SURVEY 8b custom-op layer): the ops with their registered autograd formulas against
+the float64 CPU oracle / ATen, through the C ABI.  Tolerances: fp32 engine 1e-5 / 1e-3 (north_star), fused tcgen05 PAM 2e-3 / 1e-2."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _require_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from gan_danet_b200 import _lib
+    _lib.lib_for_device(0)
+    import gan_danet_b200.ops  # noqa: F401  (registers the ops)
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("precision,tol_y,tol_g", [("fp32", 1e-5, 1e-3), ("fp16", 2e-3, 2e-2)])
+def test_pam_op(golden, oracle, precision, tol_y, tol_g):
+    """pam_fwd + its autograd (pam_bwd) on the q/k/v projections of the golden PAM module (generator.py:104-122)."""
+    g = golden("pam_c160_8x16")
+    sd = {k: v.double() for k, v in g["sd"].items()}
+    x = g["x"].double()
+    leaves = [oracle.conv2d(x, sd[f"{n}.weight"], sd[f"{n}.bias"]).detach().requires_grad_(True) for n in ("query", "key", "value")]
+    xq = x.clone().requires_grad_(True)
+    gam = sd["gamma"].clone().requires_grad_(True)
+    b, c, h, w = x.shape
+    qm, km, vm = (t.reshape(b, -1, h * w) for t in leaves)
+    attn = oracle.softmax_lastdim(torch.einsum("bdi,bdj->bij", qm, km))
+    ref = gam * torch.einsum("bcj,bij->bci", vm, attn).reshape(b, c, h, w) + xq
+    want = torch.autograd.grad((ref * g["r"].double()).sum(), [xq] + leaves + [gam])
+    dev_in = [_nhwc(t.detach().float()).to(DEV).requires_grad_(True) for t in [xq] + leaves]
+    gd = gam.detach().float().to(DEV).requires_grad_(True)
+    y, o, lse = torch.ops.gandanet.pam_fwd(*dev_in, gd, precision)
+    y.backward(_nhwc(g["r"]).to(DEV))
+    torch.cuda.synchronize()
+    assert rel_err(_nchw(y), ref) < tol_y, rel_err(_nchw(y), ref)
+    assert o.shape == (b, h * w, c) and lse.shape == (b, h * w)
+    for got, w_ in zip([t.grad for t in dev_in], want[:4]):
+        assert rel_err(_nchw(got), w_) < tol_g, rel_err(_nchw(got), w_)
+    assert rel_err(gd.grad, want[4]) < tol_g
+
+
+@pytest.mark.parametrize("tc,tol_y,tol_g", [(False, 1e-5, 1e-3), (True, 1e-4, 5e-3)])
+def test_cam_op(golden, tc, tol_y, tol_g):
+    g = golden("cam_c160_8x16")
+    x = _nhwc(g["x"]).to(DEV).requires_grad_(True)
+    gam = g["sd"]["gamma"].to(DEV).requires_grad_(True)
+    y, attn = torch.ops.gandanet.cam_fwd(x, gam, tc)
+    y.backward(_nhwc(g["r"]).to(DEV))
+    assert rel_err(_nchw(y), g["y"]) < tol_y
+    assert rel_err(_nchw(x.grad), g["dx"]) < tol_g
+    assert rel_err(gam.grad, g["grads"]["gamma"]) < tol_g
+    assert attn.shape == (x.shape[0], 160, 160) and float((attn.sum(-1) - 1).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("bf16x3", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("cin,cout,k,stride,pad,act", [(46, 64, 3, 1, 1, 1), (160, 80, 1, 1, 0, 0), (64, 128, 3, 2, 1, 2)])
+def test_conv2d_op(prec, tol, cin, cout, k, stride, pad, act):
+    """conv2d + fused activation + autograd (conv2d_bwd) against ATen in float64 on every engine."""
+    from gan_danet_b200 import engine as E
+    gen = torch.Generator().manual_seed(cin)
+    x = torch.randn(2, cin, 16, 24, generator=gen)
+    w = torch.randn(cout, cin, k, k, generator=gen) * (cin * k * k) ** -0.5
+    bias = torch.randn(cout, generator=gen) * 0.1
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, bias))
+    z = F.conv2d(xd, wd, bd, stride=stride, padding=pad)
+    ref = z if act == 0 else (F.relu(z) if act == 1 else F.leaky_relu(z, 0.2))
+    r = torch.randn(ref.shape, generator=gen)
+    want = torch.autograd.grad((ref * r.double()).sum(), [xd, wd, bd])
+    old = E.conv_precision
+    E.set_conv_precision(prec)
+    try:
+        xg = _nhwc(x).to(DEV).requires_grad_(True)
+        wg, bg = w.to(DEV).requires_grad_(True), bias.to(DEV).requires_grad_(True)
+        y = torch.ops.gandanet.conv2d(xg, wg, bg, stride, pad, act, 0.2)
+        y.backward(_nhwc(r).to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        E.set_conv_precision(old)
+    assert rel_err(_nchw(y), ref) < tol, rel_err(_nchw(y), ref)
+    assert rel_err(_nchw(xg.grad), want[0]) < 3 * tol and rel_err(wg.grad, want[1]) < 3 * tol and rel_err(bg.grad, want[2]) < 3 * tol
+
+
+def test_bicubic_and_adamw_ops():
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 8, 9, 13, generator=gen)
+    xd = x.double().requires_grad_(True)
+    ref = F.interpolate(xd, scale_factor=2, mode="bicubic", align_corners=False)
+    r = torch.randn(ref.shape, generator=gen)
+    (want,) = torch.autograd.grad((ref * r.double()).sum(), [xd])
+    xg = _nhwc(x).to(DEV).requires_grad_(True)
+    y = torch.ops.gandanet.upsample_bicubic2x(xg)
+    y.backward(_nhwc(r).to(DEV))
+    assert rel_err(_nchw(y), ref) < 1e-6 and rel_err(_nchw(xg.grad), want) < 1e-6
+    # fused_adamw_ against torch.optim.AdamW (GAN_DANet_train.ipynb:182-183 hyper-parameters), three steps
+    p0 = torch.randn(1000, generator=gen)
+    grads = [torch.randn(1000, generator=gen) for _ in range(3)]
+    pr = torch.nn.Parameter(p0.clone().double())
+    opt = torch.optim.AdamW([pr], lr=2e-4, betas=(0.5, 0.999), weight_decay=1e-4)
+    p, m, v = p0.clone().to(DEV), torch.zeros(1000, device=DEV), torch.zeros(1000, device=DEV)
+    for step, gr in enumerate(grads, 1):
+        pr.grad = gr.double()
+        opt.step()
+        torch.ops.gandanet.fused_adamw_(p, gr.to(DEV), m, v, 2e-4, 0.5, 0.999, 1e-8, 1e-4, step, 1.0)
+    assert rel_err(p, pr) < 1e-6
