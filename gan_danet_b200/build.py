@@ -58,7 +58,22 @@ def build_library(verbose: bool = False, force: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    build_harness()
     return LIB_PATH
+
+
+def build_harness() -> str:
+    """tools/cabi_bench.cpp: the Python-free harness over the C ABI (plain g++, links the library, rpath = its own directory)."""
+    src = os.path.join(HERE, "..", "tools", "cabi_bench.cpp")
+    exe = os.path.join(HERE, "cabi_bench")
+    if os.path.exists(src) and _stale(exe, [src, LIB_PATH, os.path.join(HERE, "..", "include", "gandanet.h")]):
+        cuda = os.path.dirname(os.path.dirname(os.path.realpath(_nvcc()))) if os.path.isabs(_nvcc()) else "/usr/local/cuda"
+        cmd = ["g++", "-O2", "-std=c++17", src, "-I" + os.path.join(HERE, "..", "include"), "-I" + os.path.join(cuda, "include"), "-L" + HERE, "-lgandanet_sm100",
+               "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath,$ORIGIN", "-o", exe]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"cabi_bench build failed:\n{r.stdout}\n{r.stderr}")
+    return exe
 
 
 if __name__ == "__main__":

@@ -116,3 +116,19 @@ def test_bicubic_and_adamw_ops():
         opt.step()
         torch.ops.gandanet.fused_adamw_(p, gr.to(DEV), m, v, 2e-4, 0.5, 0.999, 1e-8, 1e-4, step, 1.0)
     assert rel_err(p, pr) < 1e-6
+
+
+def test_python_free_cabi_harness():
+    """tools/cabi_bench.cpp (built by gan_danet_b200/build.py): plain C++ over the C ABI, no torch -- runs the fused PAM forward and
+    backward and checks sampled rows against its own float64 host evaluation of generator.py:115-122 (exit code 0 = within 2e-3 / 6e-3)."""
+    import json
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gan_danet_b200", "cabi_bench")
+    if not os.path.exists(exe):
+        from gan_danet_b200.build import build_harness
+        build_harness()
+    r = subprocess.run([exe, "2", "2048", "184", "23"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["rel_err_y"] < 2e-3 and out["pam_fwd_tflops"] > 0
