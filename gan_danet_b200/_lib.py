@@ -63,7 +63,7 @@ class PamFwdArgs(C.Structure):
                 ("x", _vp), ("x_pitch", _i), ("gamma", _vp),
                 ("o", _vp), ("y", _vp), ("y_pitch", _i), ("lse", _vp),
                 ("B", _i), ("N", _i), ("C", _i), ("precision", _i), ("chunk", _i),
-                ("ws", _vp), ("ws_bytes", _sz)]
+                ("ws", _vp), ("ws_bytes", _sz), ("v16", _vp)]
 
 
 class PamBwdArgs(C.Structure):

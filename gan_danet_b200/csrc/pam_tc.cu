@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256) pack_qkv_kernel(const float* __restrict__
 #pragma unroll
       for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(c0 + e < d ? __ldg(src + (size_t)r * qk_pitch + c0 + e) : 0.f);
       *reinterpret_cast<uint4*>(dst + (size_t)r * DPAD + c0) = *reinterpret_cast<const uint4*>(h);
-    } else {
+    } else if (v != nullptr) {        // v == nullptr: the caller supplies the packed V operand (gdn_pam_fwd_args.v16)
       const int c0 = (lane - 8) * 8;
       __align__(16) __nv_bfloat16 h[8];
       if (vec4) {     // C % 4 == 0, 16-byte aligned rows: a group of four channels is entirely inside or entirely outside the C valid ones
@@ -394,10 +394,12 @@ extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
   char* w = reinterpret_cast<char*>(a->ws);
   __half* Qh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
   __half* Kh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
-  __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(w);
+  const __nv_bfloat16* Vb = a->v16 ? reinterpret_cast<const __nv_bfloat16*>(a->v16) : reinterpret_cast<__nv_bfloat16*>(w);
+  GDN_CHECK_ARG(((uintptr_t)Vb & 15) == 0);
   cudaStream_t st = as_stream(s);
   const long long pb = cdiv((long long)rows, 8);
-  pack_qkv_kernel<<<(unsigned)(pb < 16 * kNumSMs ? pb : 16 * kNumSMs), 256, 0, st>>>(a->q, a->k, a->qk_pitch, a->d, a->v, a->v_pitch, a->C, Qh, Kh, Vb, (long long)rows,
+  pack_qkv_kernel<<<(unsigned)(pb < 16 * kNumSMs ? pb : 16 * kNumSMs), 256, 0, st>>>(a->q, a->k, a->qk_pitch, a->d, a->v16 ? nullptr : a->v, a->v_pitch, a->C, Qh, Kh,
+                                                                                     a->v16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(w), (long long)rows,
                                                                                      a->C % 4 == 0 && a->v_pitch % 4 == 0 && ((uintptr_t)a->v & 15) == 0);
   GDN_CHECK_LAUNCH();
   CUtensorMap mq, mk, mv;

@@ -594,7 +594,7 @@ class Tape:
 
 
 def op_conv(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, stride: int = 1, pad: int = 0, act: int = ACT_NONE, slope: float = 0.0,
-            out: Optional[Var] = None) -> Var:
+            out: Optional[Var] = None, y16: Optional[Tensor] = None) -> Var:
     """nn.Conv2d (+ fused bias and activation).  ``w`` holds the OIHW parameter."""
     O, I, kh, kw = w.t.shape
     B, Hi, Wi, Cin = x.t.shape
@@ -604,7 +604,7 @@ def op_conv(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, stride: int = 1,
     if out is None:
         out = Var(new_nhwc(B, Ho, Wo, O, x.t))
     cctx = conv_forward(x.t, w.t.detach(), out.t, stride=stride, pad=pad, bias=None if bias is None else bias.t.detach(), act=act, slope=slope,
-                        keep=tape.record and w.needs_grad, x_packed=x.packed)
+                        keep=tape.record and w.needs_grad, x_packed=x.packed, y16=y16)
     y = out
 
     def bwd():
@@ -786,8 +786,32 @@ def op_bn_act(tape: Tape, x: Var, bn: BNState, *, training: bool, act: int = ACT
     return y
 
 
-def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, precision: int = PREC_FP32, out: Optional[Var] = None) -> Var:
-    """Position-attention core: y = gamma * softmax(q k^T) v + x  (generator.py:115-122)."""
+_pam_v16: Dict[Tuple[int, int, int], Tensor] = {}
+pam_v16_from_conv: bool = os.environ.get("GDN_PAM_V16", "1") != "0"
+
+
+def pam_v16_buffer(x: Tensor) -> Optional[Tensor]:
+    """bf16 [B*N, 192] operand buffer for the fused PAM forward, or None when the value projection cannot emit it.  The value
+    projection's tensor-core epilogue writes columns [0, C) (conv y16 output, pitch 192); column C = 1 (the softmax denominator comes
+    out of the P.V product) and the zero tail are written ONCE here -- one persistent buffer per (device, rows, C), so the packing pass
+    of gdn_pam_fwd only touches q and k (V is 80 % of its bytes)."""
+    B, H, W, Cc = x.shape
+    N = H * W
+    if not (pam_v16_from_conv and conv_precision == "bf16" and N % 128 == 0 and Cc < 192 and Cc % 4 == 0 and tc_eligible(Cc, Cc, 1, 1, 1, H, W)):
+        return None
+    key = (x.device.index or 0, B * N, Cc)
+    buf = _pam_v16.get(key)
+    if buf is None:
+        buf = torch.zeros((B * N, 192), dtype=torch.bfloat16, device=x.device)
+        buf[:, Cc] = 1.0
+        _pam_v16[key] = buf
+    return buf
+
+
+def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, precision: int = PREC_FP32, out: Optional[Var] = None,
+                v16: Optional[Tensor] = None) -> Var:
+    """Position-attention core: y = gamma * softmax(q k^T) v + x  (generator.py:115-122).  ``v16``: the value operand already packed
+    by the value projection's epilogue (pam_v16_buffer)."""
     lib = _lib(x.t)
     B, H, W, Cc = x.t.shape
     N, d = H * W, q.t.shape[-1]
@@ -810,6 +834,9 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
     need = lib.gdn_pam_fwd_ws_bytes(C.byref(a))
     buf = workspace("pam", need, dev)
     a.ws, a.ws_bytes = buf.data_ptr(), buf.numel()
+    if v16 is not None and precision == PREC_FP16:
+        assert v16.shape == (B * N, 192) and v16.dtype == torch.bfloat16
+        a.v16 = v16.data_ptr()
     fam = "pam_flash_fwd_kernel" if precision == PREC_FP16 else "pam_fwd_fp32"
     _timed(fam, 2.0 * B * N * N * (d + Cc), lambda: L.check(lib.gdn_pam_fwd(C.byref(a), _stream()), "gdn_pam_fwd"))
     y = out

@@ -210,11 +210,13 @@ class PAMModule(TapeModule):
         self.precision: Optional[str] = None
 
     def _build(self, ctx: BuildCtx, x: E.Var, out: Optional[E.Var] = None) -> E.Var:
+        prec = (self.precision or default_pam_precision())
         q = _conv(ctx, x, self.query)
         k = _conv(ctx, x, self.key)
-        v = _conv(ctx, x, self.value)
-        prec = (self.precision or default_pam_precision())
-        return E.op_pam_core(ctx.tape, x, q, k, v, ctx.v(self.gamma), precision=PREC_FP16 if prec == "fp16" else PREC_FP32, out=out)
+        # the value projection's epilogue also emits the bf16 operand of the fused kernel (no separate packing pass over V)
+        v16 = E.pam_v16_buffer(x.t) if prec == "fp16" else None
+        v = E.op_conv(ctx.tape, x, ctx.v(self.value.weight), ctx.v(self.value.bias), y16=v16)
+        return E.op_pam_core(ctx.tape, x, q, k, v, ctx.v(self.gamma), precision=PREC_FP16 if prec == "fp16" else PREC_FP32, out=out, v16=v16)
 
 
 class CAMModule(TapeModule):

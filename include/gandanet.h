@@ -279,6 +279,9 @@ typedef struct {
   float* o; float* y; int y_pitch; float* lse;
   int B, N, C; int precision; int chunk;
   void* ws; size_t ws_bytes;
+  const uint16_t* v16;  /* optional (GDN_PREC_FP16 only, may be NULL): v already packed as the kernel's bf16 operand [B*N][192] -- columns [0,C) = v,
+                           column C = 1, the rest 0 -- e.g. written by the value projection's epilogue (gdn_conv_tc_args.y16, pitch 192) into a
+                           buffer whose tail columns were initialised once; the packing pass then touches q and k only */
 } gdn_pam_fwd_args;
 size_t gdn_pam_fwd_ws_bytes(const gdn_pam_fwd_args* a);
 int gdn_pam_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s);

@@ -278,6 +278,47 @@ def test_pam_padded_grid_vs_oracle(oracle, B, C, hw):
     assert float((yc - (xx + 0.5 * 0.75)).abs().max()) < 2e-3
 
 
+def test_pam_value_operand_from_conv_epilogue():
+    """PAMModule in the product mode (bf16 tensor-core convs + fused fp16/bf16 PAM): the value projection's epilogue emits the bf16 V
+    operand of the fused kernel (engine.pam_v16_buffer, gdn_pam_fwd_args.v16) instead of a packing pass over V -- the same
+    round-to-nearest of the same fp32 values, so forward and every gradient are bitwise those of the packing path."""
+    from gan_danet_b200 import engine as E
+    from gan_danet_b200.models.generator import PAMModule
+    import gan_danet_b200 as P
+    gen = torch.Generator().manual_seed(9)
+    x = 0.5 * torch.randn(2, 184, 16, 32, generator=gen)
+    r = torch.randn(2, 184, 16, 32, generator=gen)
+
+    def run(flag):
+        torch.manual_seed(4)
+        m = PAMModule(184)
+        m.apply(P.weights_init_normal)
+        with torch.no_grad():
+            m.gamma.fill_(0.5)
+        m.precision = "fp16"
+        old, oldf = E.conv_precision, E.pam_v16_from_conv
+        E.set_conv_precision("bf16")
+        E.pam_v16_from_conv = flag
+        try:
+            assert (E.pam_v16_buffer(torch.empty(2, 16, 32, 184, device=DEV)) is not None) == flag
+            return _fwd_bwd(m, x, r)
+        finally:
+            E.set_conv_precision(old)
+            E.pam_v16_from_conv = oldf
+
+    y1, dx1, g1 = run(True)
+    y0, dx0, g0 = run(False)
+    assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
+    assert all(torch.equal(g1[k], g0[k]) for k in g0)
+    buf = E.pam_v16_buffer(torch.empty(2, 16, 32, 184, device=DEV)) if E.conv_precision == "bf16" else None
+    E.set_conv_precision("bf16")
+    try:
+        buf = E.pam_v16_buffer(torch.empty(2, 16, 32, 184, device=DEV))
+        assert float(buf[:, 184].float().min()) == 1.0 and float(buf[:, 185:].float().abs().max()) == 0.0      # the tail survived the epilogue writes
+    finally:
+        E.set_conv_precision("fp32")
+
+
 def test_pam_padding_is_exact():
     """The same aligned problem (N = 256) through the kernels directly and through the padded path forced to 512 rows: the
     padded keys get softmax weight 0 (2^-125 on the polynomial lanes) and the padded queries a zero cotangent, so forward and
