@@ -524,7 +524,8 @@ class Var:
 
     def __init__(self, t: Tensor, needs_grad: bool = True, parent: Optional["Var"] = None, c0: int = 0, c1: int = 0):
         self.t, self._g, self.needs_grad, self.parent, self.c0, self.c1 = t, None, needs_grad, parent, c0, c1
-        self.packed: Optional["Packed"] = None      # set by op_bn_act(packed_only=True): the value exists ONLY as a bf16 tensor-core operand (t is a shape carrier)
+        self.packed: Optional["Packed"] = None      # bf16 tensor-core operand of this value, consumed by op_conv instead of packing t again; after
+        # op_bn_act(packed_only=True) it is the ONLY form in which the value exists (t is then a shape carrier)
 
     @property
     def g(self) -> Optional[Tensor]:

@@ -211,6 +211,9 @@ class PAMModule(TapeModule):
 
     def _build(self, ctx: BuildCtx, x: E.Var, out: Optional[E.Var] = None) -> E.Var:
         prec = (self.precision or default_pam_precision())
+        B, H, W, Cc = x.t.shape
+        if x.packed is None and E.tc_eligible(Cc, self.query.out_channels, 1, 1, 1, H, W):
+            x.packed = E.pack_act(x.t)          # one bf16 operand of x for the three projections (and their three weight gradients)
         q = _conv(ctx, x, self.query)
         k = _conv(ctx, x, self.key)
         # the value projection's epilogue also emits the bf16 operand of the fused kernel (no separate packing pass over V)
