@@ -58,7 +58,10 @@ def build_library(verbose: bool = False, force: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    build_harness()
+    try:
+        build_harness()
+    except Exception as e:      # the harness is a convenience binary: the library (the product) is already built
+        print(f"[build] cabi_bench not built: {e}", file=sys.stderr)
     return LIB_PATH
 
 

@@ -809,6 +809,14 @@ def pam_v16_buffer(x: Tensor) -> Optional[Tensor]:
     return buf
 
 
+def release_buffers() -> None:
+    """Drops the engine's persistent device buffers (workspaces, packed frozen weights, PAM value-operand buffers); they are
+    re-created on demand.  Do not call while a captured CUDA graph that baked their addresses is still in use."""
+    _workspaces.clear()
+    _pam_v16.clear()
+    _frozen_weights.clear()
+
+
 def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, precision: int = PREC_FP32, out: Optional[Var] = None,
                 v16: Optional[Tensor] = None) -> Var:
     """Position-attention core: y = gamma * softmax(q k^T) v + x  (generator.py:115-122).  ``v16``: the value operand already packed
@@ -1078,6 +1086,28 @@ def op_maxpool2_bf16(tape: Tape, x: Var, x16: Tensor) -> Tuple[Var, Tensor]:
 
     tape.push(bwd)
     return y, y16
+
+
+def op_cat_rows(tape: Tape, parts: List[Var]) -> Var:
+    """Concatenation of parameter tensors along dim 0 (tiny: the weights / biases of projections that run as ONE convolution);
+    the backward hands every part its rows of the gradient."""
+    y = Var(torch.cat([p.t.detach() for p in parts], dim=0), any(p.needs_grad for p in parts))
+
+    def bwd():
+        if y.g is None:
+            return
+        r = 0
+        for p in parts:
+            n = p.t.shape[0]
+            if p.needs_grad:
+                p.add_grad(y.g[r:r + n].contiguous())
+            r += n
+
+    tape.push(bwd)
+    return y
+
+
+pam_merge_qk: bool = os.environ.get("GDN_PAM_MERGE_QK", "1") != "0"
 
 
 def op_copy(tape: Tape, x: Var, out: Var) -> Var:

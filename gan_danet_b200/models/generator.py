@@ -214,8 +214,16 @@ class PAMModule(TapeModule):
         B, H, W, Cc = x.t.shape
         if x.packed is None and E.tc_eligible(Cc, self.query.out_channels, 1, 1, 1, H, W):
             x.packed = E.pack_act(x.t)          # one bf16 operand of x for the three projections (and their three weight gradients)
-        q = _conv(ctx, x, self.query)
-        k = _conv(ctx, x, self.key)
+        if E.pam_merge_qk and x.packed is not None:
+            # query and key projections as ONE tensor-core convolution C -> 2d (concatenated weights): one forward, one weight gradient and
+            # one data gradient (one read-modify-write pass over dL/dx instead of two); q and k are channel slices of its output
+            d = self.query.out_channels
+            qk = E.op_conv(ctx.tape, x, E.op_cat_rows(ctx.tape, [ctx.v(self.query.weight), ctx.v(self.key.weight)]),
+                           E.op_cat_rows(ctx.tape, [ctx.v(self.query.bias), ctx.v(self.key.bias)]))
+            q, k = qk.slice(0, d), qk.slice(d, 2 * d)
+        else:
+            q = _conv(ctx, x, self.query)
+            k = _conv(ctx, x, self.key)
         # the value projection's epilogue also emits the bf16 operand of the fused kernel (no separate packing pass over V)
         v16 = E.pam_v16_buffer(x.t) if prec == "fp16" else None
         v = E.op_conv(ctx.tape, x, ctx.v(self.value.weight), ctx.v(self.value.bias), y16=v16)

@@ -319,6 +319,48 @@ def test_pam_value_operand_from_conv_epilogue():
         E.set_conv_precision("fp32")
 
 
+@pytest.mark.parametrize("conv", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("C,hw", [(184, (16, 32)), (160, (8, 16))])
+def test_pam_merged_query_key_projection(conv, C, hw):
+    """Query and key projections (generator.py:108-109) as one C -> 2d tensor-core convolution with concatenated weights against the two
+    separate convolutions: per output channel the same dot products, so y is bitwise equal; gradients differ only in float32 summation order
+    (the q and k contributions to dL/dx are added inside one GEMM instead of two accumulation passes)."""
+    from gan_danet_b200 import engine as E
+    from gan_danet_b200.models.generator import PAMModule
+    import gan_danet_b200 as P
+    gen = torch.Generator().manual_seed(C)
+    x = 0.5 * torch.randn(2, C, *hw, generator=gen)
+    r = torch.randn(2, C, *hw, generator=gen)
+
+    def run(flag):
+        torch.manual_seed(4)
+        m = PAMModule(C)
+        m.apply(P.weights_init_normal)
+        with torch.no_grad():
+            m.gamma.fill_(0.5)
+            m.query.weight.mul_(4.0)
+            m.key.weight.mul_(4.0)
+        m.precision = "fp16"
+        old, oldf = E.conv_precision, E.pam_merge_qk
+        E.set_conv_precision(conv)
+        E.pam_merge_qk = flag
+        try:
+            return _fwd_bwd(m, x, r)
+        finally:
+            E.set_conv_precision(old)
+            E.pam_merge_qk = oldf
+
+    y1, dx1, g1 = run(True)
+    y0, dx0, g0 = run(False)
+    assert torch.equal(y1, y0)
+    assert rel_err(dx1, dx0) < 1e-5, rel_err(dx1, dx0)
+    for k in g0:
+        if k == "key.bias":
+            assert float((g1[k] - g0[k]).abs().max()) < 1e-4 * float(g0["key.weight"].abs().max()) + 1e-7
+        else:
+            assert rel_err(g1[k], g0[k]) < 1e-4, (k, rel_err(g1[k], g0[k]))
+
+
 def test_pam_padding_is_exact():
     """The same aligned problem (N = 256) through the kernels directly and through the padded path forced to 512 rows: the
     padded keys get softmax weight 0 (2^-125 on the polynomial lanes) and the padded queries a zero cotangent, so forward and
