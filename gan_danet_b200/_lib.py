@@ -117,6 +117,7 @@ SIGNATURES = {
     "gdn_affine_act": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _vp, _i, _f, _vp]),
     "gdn_bn_bwd_reduce": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp]),
     "gdn_bn_bwd_apply": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
+    "gdn_bn_bwd_apply16": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
     "gdn_act_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _ll, _i, _i, _f, _vp]),
     "gdn_axpy": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _f, _i, _vp]),
     "gdn_scale_dev": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),

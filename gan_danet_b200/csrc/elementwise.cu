@@ -2,6 +2,7 @@
 // Reference call sites: nn.BatchNorm2d + nn.ReLU at /root/reference/models/generator.py:32-33,61-62,149-150,
 // 189-190,219-220,223-224; nn.LeakyReLU(0.2) at models/discriminator.py:68; nn.ReLU of VGG19 (models/losses.py:58).
 // All reductions are deterministic two-stage sums accumulated in double.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace gdn {
@@ -200,6 +201,7 @@ struct EwP {
   long long M; int C;
   const float* mean; const float* invstd; const float* weight; const float* scale; const float* shift;
   const double* sums; float alpha; int act; float slope;
+  __nv_bfloat16* o16; int o16_pitch;      // EW_BN_BWD, 128-bit path: the result as the bf16 tensor-core operand of the preceding convolution's gradient GEMMs (o may be NULL)
 };
 
 template <int OP>
@@ -261,9 +263,15 @@ __global__ void __launch_bounds__(256) ew_kernel(const EwP p) {
         r.x = ew_apply<OP>(p, a.x, b.x, c, invM); r.y = ew_apply<OP>(p, a.y, b.y, c + 1, invM);
         r.z = ew_apply<OP>(p, a.z, b.z, c + 2, invM); r.w = ew_apply<OP>(p, a.w, b.w, c + 3, invM);
       }
-      float4* op = reinterpret_cast<float4*>(p.o + (size_t)m * p.o_pitch + c);
-      if (p.accumulate) { float4 o = *op; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
-      *op = r;
+      if (OP == EW_BN_BWD && p.o16) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(r.x, r.y), h1 = __floats2bfloat162_rn(r.z, r.w);
+        *reinterpret_cast<uint2*>(p.o16 + (size_t)m * p.o16_pitch + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
+      if (OP != EW_BN_BWD || p.o) {
+        float4* op = reinterpret_cast<float4*>(p.o + (size_t)m * p.o_pitch + c);
+        if (p.accumulate) { float4 o = *op; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+        *op = r;
+      }
     } else {
       float a = p.a[(size_t)m * p.a_pitch + c];
       float b = (OP == EW_BN_BWD || OP == EW_ACT_BWD) ? p.b[(size_t)m * p.b_pitch + c] : 0.f;
@@ -389,6 +397,22 @@ extern "C" int gdn_bn_bwd_apply(const float* dy, int dy_pitch, int dy_c0, const 
     GDN_CHECK_LAUNCH();
   }
   return GDN_OK;
+}
+// The same stage 2 with the result written ONLY as bf16 [M][dx16_pitch] (round to nearest): dx of a BatchNorm that follows a bias-free
+// tensor-core convolution is consumed by that convolution's gradient GEMMs alone, whose operand it is -- the fp32 tensor (4 B written by
+// this kernel + 4 B read by the packing pass per element) never exists.
+extern "C" int gdn_bn_bwd_apply16(const float* dy, int dy_pitch, int dy_c0, const float* x, int x_pitch, int x_c0, uint16_t* dx16, int dx16_pitch,
+                                  long long M, int C, const float* mean, const float* invstd, const float* weight, const float* scale, const float* shift,
+                                  int act, float slope, const double* sums, gdn_stream_t s) {
+  GDN_CHECK_ARG(dy && x && dx16 && mean && invstd && scale && shift && sums && M > 0 && C > 0 && C % 8 == 0);
+  GDN_CHECK_ARG(dy_pitch >= dy_c0 + C && x_pitch >= x_c0 + C && dx16_pitch >= C && dx16_pitch % 4 == 0 && ((uintptr_t)dx16 & 7) == 0);
+  EwP p = {};
+  p.a = dy + dy_c0; p.a_pitch = dy_pitch; p.b = x + x_c0; p.b_pitch = x_pitch; p.o = nullptr; p.o_pitch = 4;
+  p.o16 = reinterpret_cast<__nv_bfloat16*>(dx16); p.o16_pitch = dx16_pitch;
+  p.M = M; p.C = C; p.mean = mean; p.invstd = invstd; p.weight = weight; p.scale = scale; p.shift = shift;
+  p.sums = sums; p.act = act; p.slope = slope;
+  if (!vec4_ok(p)) { set_error("gdn_bn_bwd_apply16: dy / x need 16-byte aligned rows (pitches and channel offsets multiples of 4)"); return GDN_EINVAL; }
+  return ew_launch<EW_BN_BWD>(p, as_stream(s));
 }
 extern "C" int gdn_act_bwd(const float* dy, int dy_pitch, int dy_c0, const float* y, int y_pitch, int y_c0,
                            float* dz, int dz_pitch, int dz_c0, long long M, int C, int act, float slope, gdn_stream_t s) {

@@ -520,10 +520,12 @@ def dot_ws(device) -> Tensor:
 
 class Var:
     """A tensor on the tape plus its (lazily created) gradient.  ``parent`` marks a channel slice of a wider buffer."""
-    __slots__ = ("t", "_g", "needs_grad", "parent", "c0", "c1", "packed")
+    __slots__ = ("t", "_g", "needs_grad", "parent", "c0", "c1", "packed", "g16", "grad16_only")
 
     def __init__(self, t: Tensor, needs_grad: bool = True, parent: Optional["Var"] = None, c0: int = 0, c1: int = 0):
         self.t, self._g, self.needs_grad, self.parent, self.c0, self.c1 = t, None, needs_grad, parent, c0, c1
+        self.g16: Optional["Packed"] = None         # the gradient as a bf16 tensor-core operand only (op_conv_bn_act): no fp32 gradient tensor exists
+        self.grad16_only = False                    # set on a convolution output whose single consumer (BatchNorm) may hand back g16 instead of g
         self.packed: Optional["Packed"] = None      # bf16 tensor-core operand of this value, consumed by op_conv instead of packing t again; after
         # op_bn_act(packed_only=True) it is the ONLY form in which the value exists (t is then a shape carrier)
 
@@ -609,6 +611,14 @@ def op_conv(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, stride: int = 1,
     y = out
 
     def bwd():
+        if y.g16 is not None:          # BatchNorm backward produced dz directly as the gradient GEMMs' bf16 operand (op_conv_bn_act)
+            assert y.g is None and act == ACT_NONE and bias is None
+            gw16 = torch.empty_like(w.t) if w.needs_grad else None
+            tgt16, acc16 = x.grad_target() if x.needs_grad else (None, False)
+            conv_backward(cctx, None, x.t, w.t.detach(), stride=stride, pad=pad, gw=gw16, gx=tgt16, gx_accumulate=acc16, dz_packed=y.g16, out_hw=(Ho, Wo))
+            if gw16 is not None:
+                w.add_grad(gw16)
+            return
         if y.g is None:
             return
         dy = y.g
@@ -713,6 +723,24 @@ class BNState:
         self.num_batches_tracked, self.eps, self.momentum = num_batches_tracked, eps, momentum
 
 
+conv_bn_packed_grad: bool = os.environ.get("GDN_CONV_BN_GRAD16", "1") != "0"
+
+
+def op_conv_bn_act(tape: Tape, x: Var, w: Var, bn: BNState, *, training: bool, act: int = ACT_RELU, slope: float = 0.0, stride: int = 1, pad: int = 0,
+                   out: Optional[Var] = None) -> Var:
+    """act(BN(conv(x))) with a bias-free convolution (generator.py:187-190 initial, :147-150 fuse, :218-224 upsample).  In the bf16 product
+    mode the gradient between BatchNorm and the convolution is never stored in fp32: BatchNorm's backward writes it as the bf16 operand of
+    the convolution's weight- and data-gradient GEMMs (gdn_bn_bwd_apply16), which is the only form in which it is read."""
+    z = op_conv(tape, x, w, None, stride=stride, pad=pad)
+    O, Cin, kh, kw = w.t.shape
+    _, Hi, Wi, _ = x.t.shape
+    _, Ho, Wo, _ = z.t.shape
+    z.grad16_only = bool(conv_bn_packed_grad and training and tape.record and conv_precision == "bf16" and O % 8 == 0 and pitch_of(z.t) % 4 == 0
+                         and z.t.data_ptr() % 16 == 0
+                         and conv_backward_tc_only(O, Cin, kh, kw, stride, Ho, Wo, Hi, Wi, w.needs_grad, x.needs_grad))
+    return op_bn_act(tape, z, bn, training=training, act=act, slope=slope, out=out)
+
+
 fuse_bn_into_pack: bool = os.environ.get("GDN_FUSE_BN_PACK", "1") != "0"
 
 
@@ -771,7 +799,13 @@ def op_bn_act(tape: Tape, x: Var, bn: BNState, *, training: bool, act: int = ACT
         buf = workspace("stat", lib.gdn_colstats_ws_bytes(M, Cc), dev)
         L.check(lib.gdn_bn_bwd_reduce(dy.data_ptr(), pitch_of(dy), 0, x.t.data_ptr(), pitch_of(x.t), 0, M, Cc, mean.data_ptr(), invstd.data_ptr(),
                                       scale.data_ptr(), shift.data_ptr(), act, slope, sums.data_ptr(), buf.data_ptr(), _stream()), "gdn_bn_bwd_reduce")
-        if x.needs_grad:
+        if x.needs_grad and x.grad16_only and x.g is None and x.parent is None and pitch_of(dy) % 4 == 0 and dy.data_ptr() % 16 == 0:
+            g16 = torch.empty((M, Cc), dtype=torch.bfloat16, device=dev)
+            L.check(lib.gdn_bn_bwd_apply16(dy.data_ptr(), pitch_of(dy), 0, x.t.data_ptr(), pitch_of(x.t), 0, g16.data_ptr(), Cc, M, Cc, mean.data_ptr(),
+                                           invstd.data_ptr(), bn.weight.t.data_ptr(), scale.data_ptr(), shift.data_ptr(), act, slope, sums.data_ptr(),
+                                           _stream()), "gdn_bn_bwd_apply16")
+            x.g16 = Packed(g16, None, Cc)
+        elif x.needs_grad:
             tgt, acc = x.grad_target()
             L.check(lib.gdn_bn_bwd_apply(dy.data_ptr(), pitch_of(dy), 0, x.t.data_ptr(), pitch_of(x.t), 0, tgt.data_ptr(), pitch_of(tgt), 0, int(acc),
                                          M, Cc, mean.data_ptr(), invstd.data_ptr(), bn.weight.t.data_ptr(), scale.data_ptr(), shift.data_ptr(),

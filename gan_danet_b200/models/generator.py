@@ -259,8 +259,10 @@ class DANetAttention(TapeModule):
         cat = E.Var(E.new_nhwc(B, H, W, 2 * Cc, x.t))
         self.position_attention._build(ctx, x, out=cat.slice(0, Cc))
         self.channel_attention._build(ctx, x, out=cat.slice(Cc, 2 * Cc))
-        f = _conv(ctx, cat, self.fuse[0])
-        return E.op_bn_act(ctx.tape, f, ctx.bn(self.fuse[1]), training=self.fuse[1].training, act=ACT_RELU)
+        conv = self.fuse[0]
+        assert conv.bias is None
+        return E.op_conv_bn_act(ctx.tape, cat, ctx.v(conv.weight), ctx.bn(self.fuse[1]), training=self.fuse[1].training, act=ACT_RELU,
+                                stride=conv.stride[0], pad=conv.padding[0])
 
 
 def _build_attention(attention_type: Optional[str], channels: int) -> Optional[nn.Module]:
@@ -333,8 +335,11 @@ class FlexibleUpsamplingModule(TapeModule):
         B, H, W, _ = xin.t.shape
         nblocks = len(self.dense_blocks)
         buf = self.dense_blocks[0].alloc(B, H, W, xin.t)
-        t = _conv(ctx, xin, self.initial[0])
-        E.op_bn_act(tape, t, ctx.bn(self.initial[1]), training=self.initial[1].training, act=ACT_RELU, out=buf.slice(0, self.dense_blocks[0].in_channels))
+        conv0, bn0, dst = self.initial[0], self.initial[1], buf.slice(0, self.dense_blocks[0].in_channels)
+        if conv0.bias is None:
+            E.op_conv_bn_act(tape, xin, ctx.v(conv0.weight), ctx.bn(bn0), training=bn0.training, act=ACT_RELU, stride=conv0.stride[0], pad=conv0.padding[0], out=dst)
+        else:
+            E.op_bn_act(tape, _conv(ctx, xin, conv0), ctx.bn(bn0), training=bn0.training, act=ACT_RELU, out=dst)
         skips: List[E.Var] = []
         x = buf
         for i in range(nblocks):
@@ -349,12 +354,12 @@ class FlexibleUpsamplingModule(TapeModule):
                 self.transition_layers[i]._build(ctx, x, out=buf.slice(0, nxt.in_channels))
                 x = buf
         up = self.upsample
-        x = _conv(ctx, x, up[0])
-        x = E.op_bn_act(tape, x, ctx.bn(up[1]), training=up[1].training, act=ACT_RELU)
-        x = E.op_bicubic_up2(tape, x)
-        x = _conv(ctx, x, up[4])
-        x = E.op_bn_act(tape, x, ctx.bn(up[5]), training=up[5].training, act=ACT_RELU)
-        x = E.op_bicubic_up2(tape, x)
+        for conv, bn in ((up[0], up[1]), (up[4], up[5])):
+            if conv.bias is None:
+                x = E.op_conv_bn_act(tape, x, ctx.v(conv.weight), ctx.bn(bn), training=bn.training, act=ACT_RELU, stride=conv.stride[0], pad=conv.padding[0])
+            else:
+                x = E.op_bn_act(tape, _conv(ctx, x, conv), ctx.bn(bn), training=bn.training, act=ACT_RELU)
+            x = E.op_bicubic_up2(tape, x)
         s: Optional[E.Var] = None
         for adjust, feat in zip(self.channel_adjust, reversed(skips)):
             s = E.op_conv_accumulate(tape, feat, ctx.v(adjust.weight), s)

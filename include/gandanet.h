@@ -235,6 +235,11 @@ int gdn_bn_bwd_apply(const float* dy, int dy_pitch, int dy_c0, const float* x, i
                      float* dx, int dx_pitch, int dx_c0, int accumulate, long long M, int C,
                      const float* mean, const float* invstd, const float* weight, const float* scale, const float* shift,
                      int act, float slope, const double* sums, float* dweight, float* dbias, gdn_stream_t s);
+/* stage 2 with dx written only as the bf16 operand [M][dx16_pitch] of the preceding bias-free tensor-core convolution's gradient GEMMs
+ * (conv -> BN -> ReLU chains: generator.py:187-190,147-150,218-224): no fp32 dx.  C % 8 == 0, 16-byte aligned rows. */
+int gdn_bn_bwd_apply16(const float* dy, int dy_pitch, int dy_c0, const float* x, int x_pitch, int x_c0, uint16_t* dx16, int dx16_pitch,
+                       long long M, int C, const float* mean, const float* invstd, const float* weight, const float* scale, const float* shift,
+                       int act, float slope, const double* sums, gdn_stream_t s);
 /* dz = dy * act'(y) given the activation OUTPUT y (ReLU / LeakyReLU) */
 int gdn_act_bwd(const float* dy, int dy_pitch, int dy_c0, const float* y, int y_pitch, int y_c0,
                 float* dz, int dz_pitch, int dz_c0, long long M, int C, int act, float slope, gdn_stream_t s);

@@ -175,3 +175,46 @@ def test_bn_relu_fused_into_operand_packing(precision, train):
         assert rel(dxf, dxu) < 1e-5, rel(dxf, dxu)
         for k in gu:
             assert rel(gf[k], gu[k]) < 1e-5 or float(gu[k].abs().max()) < 1e-6, (k, rel(gf[k], gu[k]))
+
+
+def test_conv_bn_relu_packed_gradient():
+    """conv -> BN -> ReLU chains of the generator (initial, DANet fuse, upsample: generator.py:147-150,187-190,218-224) in the bf16 product mode:
+    BatchNorm's backward hands the convolution its dz as a bf16 operand only (gdn_bn_bwd_apply16) instead of an fp32 tensor that is packed
+    afterwards -- the same round-to-nearest of the same fp32 values, so every gradient is bitwise that of the unfused path."""
+    from gan_danet_b200 import engine as E
+    import gan_danet_b200 as P
+    dev = "cuda:0"
+    from gan_danet_b200.synthetic import fast_batch
+    lr05, _, aux = fast_batch(3, 2, 16, 32)
+
+    def run(flag):
+        torch.manual_seed(0)
+        G = P.FlexibleUpsamplingModule(46)
+        G.apply(P.weights_init_normal)
+        with torch.no_grad():
+            for n, p in G.named_parameters():
+                if n.endswith("gamma"):
+                    p.fill_(0.05)
+        G = G.to(dev).train()
+        G.set_pam_precision("fp16")
+        old, oldf = E.conv_precision, E.conv_bn_packed_grad
+        E.set_conv_precision("bf16")
+        E.conv_bn_packed_grad = flag
+        try:
+            import sys, os
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+            import gan_danet_oracle as oracle
+            x = oracle.prepare_input(lr05, aux).to(dev).requires_grad_(True)
+            y = G(x)
+            y.backward(torch.ones_like(y) * 0.25 + 0.1 * y.detach())
+            torch.cuda.synchronize()
+        finally:
+            E.set_conv_precision(old)
+            E.conv_bn_packed_grad = oldf
+        return y.detach(), x.grad.detach(), {k: p.grad.detach() for k, p in G.named_parameters()}
+
+    y1, dx1, g1 = run(True)
+    y0, dx0, g0 = run(False)
+    assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
+    bad = [k for k in g0 if not torch.equal(g1[k], g0[k])]
+    assert not bad, bad[:5]
