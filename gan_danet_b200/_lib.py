@@ -63,7 +63,7 @@ class PamFwdArgs(C.Structure):
                 ("x", _vp), ("x_pitch", _i), ("gamma", _vp),
                 ("o", _vp), ("y", _vp), ("y_pitch", _i), ("lse", _vp),
                 ("B", _i), ("N", _i), ("C", _i), ("precision", _i), ("chunk", _i),
-                ("ws", _vp), ("ws_bytes", _sz), ("v16", _vp)]
+                ("ws", _vp), ("ws_bytes", _sz), ("v16", _vp), ("y16", _vp), ("y16_pitch", _i)]
 
 
 class PamBwdArgs(C.Structure):
@@ -140,6 +140,7 @@ SIGNATURES = {
     "gdn_cam_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "gdn_cam_tc_ws_bytes": (_sz, [_i, _i, _i]),
     "gdn_cam_fwd_tc": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "gdn_cam_fwd_tc16": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "gdn_cam_bwd_tc": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "gdn_row_softmax": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
     "gdn_cam_softmax": (_i, [_vp, _vp, _i, _i, _vp]),

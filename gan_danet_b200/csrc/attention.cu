@@ -160,8 +160,9 @@ extern "C" size_t gdn_pam_bwd_ws_bytes(const gdn_pam_bwd_args* a) {
 }
 
 extern "C" int gdn_pam_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
-  GDN_CHECK_ARG(a && a->q && a->k && a->v && a->x && a->gamma && a->o && a->y && a->lse);
-  GDN_CHECK_ARG(a->B > 0 && a->N > 0 && a->C > 0 && a->d > 0 && a->qk_pitch >= a->d && a->v_pitch >= a->C && a->x_pitch >= a->C && a->y_pitch >= a->C);
+  GDN_CHECK_ARG(a && a->q && a->k && a->v && a->x && a->gamma && a->o && a->lse);
+  GDN_CHECK_ARG(a->y || (a->y16 && a->precision != GDN_PREC_FP32));          // y may be omitted only when the tensor-core kernel writes the bf16 block
+  GDN_CHECK_ARG(a->B > 0 && a->N > 0 && a->C > 0 && a->d > 0 && a->qk_pitch >= a->d && a->v_pitch >= a->C && a->x_pitch >= a->C && (!a->y || a->y_pitch >= a->C));
   if (a->precision != GDN_PREC_FP32) return gdn_pam_tc_fwd(a, s);
   const int B = a->B, N = a->N, C = a->C, d = a->d;
   const int g = pam_chunk(B, N, a->chunk);
@@ -365,27 +366,32 @@ int cam_gram(const CamWs& w, const uint16_t* ah, const uint16_t* al, const uint1
 }
 // y[b][n][:] = alpha * W_b x[b][n][:] + res   with W_b = w[b] ([C][C] row-major fp32, packed here)
 int cam_project(const uint16_t* xh, const uint16_t* xl, const float* w, uint16_t* wh, uint16_t* wl, float* y, int y_pitch, const float* alpha_ptr,
-                const float* res, int res_pitch, int B, int N, int C, gdn_stream_t s) {
+                const float* res, int res_pitch, int B, int N, int C, gdn_stream_t s, uint16_t* y16 = nullptr, int y16_pitch = 0) {
   int rc = gdn_pack_weight_bf16(w, B * C, C, 0, C, 1, 1, 0, wh, wl, s);
   if (rc != GDN_OK) return rc;
   gdn_conv_tc_args c = {};
   c.x_hi = xh; c.x_lo = xl; c.w_hi = wh; c.w_lo = wl; c.y = y; c.y_pitch = y_pitch; c.res = res; c.res_pitch = res_pitch;
   c.B = B; c.Hi = 1; c.Wi = N; c.Cin = C; c.Ho = 1; c.Wo = N; c.Cout = C; c.kh = c.kw = 1; c.stride = 1; c.pad = 0;
   c.precision = GDN_PREC_BF16X3; c.alpha_ptr = alpha_ptr; c.groups = B;
+  c.y16 = y16; c.y16_pitch = y16_pitch;
   return gdn_conv2d_tc(&c, s);
 }
 }  // namespace
 
 extern "C" int gdn_cam_fwd_tc(const float* x, int x_pitch, const float* gamma, float* attn, float* y, int y_pitch, int B, int N, int C,
                               void* ws, size_t ws_bytes, gdn_stream_t s) {
-  GDN_CHECK_ARG(x && gamma && attn && y && ws && B > 0 && N > 0 && C > 0 && C % 4 == 0 && x_pitch >= C && y_pitch >= C);
+  return gdn_cam_fwd_tc16(x, x_pitch, gamma, attn, y, y_pitch, nullptr, 0, B, N, C, ws, ws_bytes, s);
+}
+extern "C" int gdn_cam_fwd_tc16(const float* x, int x_pitch, const float* gamma, float* attn, float* y, int y_pitch, uint16_t* y16, int y16_pitch, int B, int N, int C,
+                                void* ws, size_t ws_bytes, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && gamma && attn && (y || y16) && ws && B > 0 && N > 0 && C > 0 && C % 4 == 0 && x_pitch >= C && (!y || y_pitch >= C));
   if (ws_bytes < gdn_cam_tc_ws_bytes(B, N, C)) { set_error("gdn_cam_fwd_tc: workspace too small"); return GDN_EWORKSPACE; }
   CamWs w = cam_carve(ws, B, N, C);
   int rc;
   if ((rc = gdn_pack_act_bf16(x, x_pitch, 0, (long long)B * N, C, w.xh, w.xl, nullptr, nullptr, GDN_ACT_NONE, 0.f, s)) != GDN_OK) return rc;
   if ((rc = cam_gram(w, w.xh, w.xl, w.xh, w.xl, attn, nullptr, B, N, C, s)) != GDN_OK) return rc;              // energy = bmm(x, x^T)   (generator.py:131-132)
   if ((rc = gdn_row_softmax(attn, attn, (long long)B * C, C, 1, nullptr, s)) != GDN_OK) return rc;           // softmax(rowmax - E)     (:135-136)
-  return cam_project(w.xh, w.xl, attn, w.w1h, w.w1l, y, y_pitch, gamma, x, x_pitch, B, N, C, s);             // gamma*bmm(attn, x) + x  (:138-139)
+  return cam_project(w.xh, w.xl, attn, w.w1h, w.w1l, y, y_pitch, gamma, x, x_pitch, B, N, C, s, y16, y16_pitch);   // gamma*bmm(attn, x) + x  (:138-139)
 }
 
 extern "C" int gdn_cam_bwd_tc(const float* x, int x_pitch, const float* gamma, const float* attn, const float* dy, int dy_pitch,

@@ -73,6 +73,7 @@ struct FwdParams {
   const float* x; int x_pitch; const float* gamma;
   float* o; float* y; int y_pitch; float* lse;
   int B, N, C, tiles_per_sample;
+  __nv_bfloat16* y16; int y16_pitch;   // optional: y also (or, with y == NULL, only) as bf16 into a wider packed operand buffer (the DANet fuse convolution's input)
   int n_pv;      // MMA N of the P.V product: round_up(C + 1, 16) <= CPAD (C valid channels + the channel of ones); columns beyond it are never accumulated
 };
 
@@ -287,7 +288,12 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       const size_t grow = row0 + r;
       const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + grow * p.x_pitch + ch));
       *reinterpret_cast<float4*>(p.o + grow * p.C + ch) = on;
-      *reinterpret_cast<float4*>(p.y + grow * p.y_pitch + ch) = make_float4(fmaf(gm, on.x, xv.x), fmaf(gm, on.y, xv.y), fmaf(gm, on.z, xv.z), fmaf(gm, on.w, xv.w));
+      const float4 yv = make_float4(fmaf(gm, on.x, xv.x), fmaf(gm, on.y, xv.y), fmaf(gm, on.z, xv.z), fmaf(gm, on.w, xv.w));
+      if (p.y) *reinterpret_cast<float4*>(p.y + grow * p.y_pitch + ch) = yv;
+      if (p.y16) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(yv.x, yv.y), h1 = __floats2bfloat162_rn(yv.z, yv.w);
+        *reinterpret_cast<uint2*>(p.y16 + grow * p.y16_pitch + ch) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
     }
   }
   __syncthreads();
@@ -411,6 +417,9 @@ extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
   p.x = a->x; p.x_pitch = a->x_pitch; p.gamma = a->gamma; p.o = a->o; p.y = a->y; p.y_pitch = a->y_pitch; p.lse = a->lse;
   p.B = a->B; p.N = a->N; p.C = a->C; p.tiles_per_sample = a->N / TQ;
   p.n_pv = (a->C + 1 + 15) & ~15;
+  p.y16 = reinterpret_cast<__nv_bfloat16*>(a->y16); p.y16_pitch = a->y16_pitch;
+  GDN_CHECK_ARG(a->y || a->y16);
+  if (a->y16) GDN_CHECK_ARG(a->y16_pitch >= a->C && a->y16_pitch % 4 == 0 && ((uintptr_t)a->y16 & 7) == 0);
   pam_flash_fwd_kernel<<<a->B * p.tiles_per_sample, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
   GDN_CHECK_LAUNCH();
   return GDN_OK;

@@ -851,8 +851,19 @@ def release_buffers() -> None:
     _frozen_weights.clear()
 
 
+danet_cat16: bool = os.environ.get("GDN_DANET_CAT16", "1") != "0"
+
+
+def danet_cat16_ok(x: Tensor, pam_fp16: bool, fuse_cout: int) -> bool:
+    """True when PAM and CAM can write their outputs ONLY as bf16 column blocks of the fuse convolution's packed operand (generator.py:156-157
+    cat -> conv): product mode, fused tensor-core PAM on an aligned grid, tensor-core CAM, tensor-core fuse convolution."""
+    B, H, W, Cc = x.shape
+    return bool(danet_cat16 and pam_fp16 and conv_precision == "bf16" and (H * W) % 128 == 0 and Cc < 192 and Cc % 4 == 0 and _cam_tc(Cc)
+                and tc_eligible(2 * Cc, fuse_cout, 3, 3, 1, H, W))
+
+
 def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, precision: int = PREC_FP32, out: Optional[Var] = None,
-                v16: Optional[Tensor] = None) -> Var:
+                v16: Optional[Tensor] = None, y16: Optional[Tensor] = None) -> Var:
     """Position-attention core: y = gamma * softmax(q k^T) v + x  (generator.py:115-122).  ``v16``: the value operand already packed
     by the value projection's epilogue (pam_v16_buffer)."""
     lib = _lib(x.t)
@@ -860,6 +871,7 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
     N, d = H * W, q.t.shape[-1]
     dev = x.t.device
     if precision == PREC_FP16 and N % 128 != 0 and pam_pad_to_tiles and d < 32 and Cc < 192 and Cc % 4 == 0:
+        assert y16 is None
         return _op_pam_core_padded(tape, x, q, k, v, gamma, out)
     if precision == PREC_FP16 and (N % 128 != 0 or d > 32 or Cc >= 192 or Cc % 4 != 0):
         precision = PREC_FP32      # shape outside the tensor-core kernel's tiling: fp32 CUDA-core engine
@@ -880,6 +892,9 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
     if v16 is not None and precision == PREC_FP16:
         assert v16.shape == (B * N, 192) and v16.dtype == torch.bfloat16
         a.v16 = v16.data_ptr()
+    if y16 is not None:     # y only as a bf16 column block (a strided [B*N, C] view) of the consumer's packed operand: out.t is never written
+        assert precision == PREC_FP16 and y16.dtype == torch.bfloat16 and y16.shape == (B * N, Cc) and y16.stride(1) == 1
+        a.y, a.y16, a.y16_pitch = None, y16.data_ptr(), y16.stride(0)
     fam = "pam_flash_fwd_kernel" if precision == PREC_FP16 else "pam_fwd_fp32"
     _timed(fam, 2.0 * B * N * N * (d + Cc), lambda: L.check(lib.gdn_pam_fwd(C.byref(a), _stream()), "gdn_pam_fwd"))
     y = out
@@ -980,7 +995,7 @@ def _cam_tc(Cc: int) -> bool:
     return bool(use) and Cc % 4 == 0
 
 
-def op_cam(tape: Tape, x: Var, gamma: Var, *, out: Optional[Var] = None) -> Var:
+def op_cam(tape: Tape, x: Var, gamma: Var, *, out: Optional[Var] = None, y16: Optional[Tensor] = None) -> Var:
     """Channel attention: y = gamma * softmax(rowmax(E)-E) X + x with E = X X^T  (generator.py:128-139)."""
     lib = _lib(x.t)
     B, H, W, Cc = x.t.shape
@@ -990,7 +1005,12 @@ def op_cam(tape: Tape, x: Var, gamma: Var, *, out: Optional[Var] = None) -> Var:
         out = Var(torch.empty(x.t.shape, dtype=torch.float32, device=dev))
     attn = torch.empty((B, Cc, Cc), dtype=torch.float32, device=dev)
     tc = _cam_tc(Cc)
-    if tc:
+    if y16 is not None:     # output only as a bf16 column block of the consumer's packed operand (see op_pam_core)
+        assert tc and y16.dtype == torch.bfloat16 and y16.shape == (B * N, Cc) and y16.stride(1) == 1
+        buf = workspace("cam_tc", lib.gdn_cam_tc_ws_bytes(B, N, Cc), dev)
+        L.check(lib.gdn_cam_fwd_tc16(x.t.data_ptr(), pitch_of(x.t), gamma.t.data_ptr(), attn.data_ptr(), None, 0, y16.data_ptr(), y16.stride(0), B, N, Cc,
+                                     buf.data_ptr(), buf.numel(), _stream()), "gdn_cam_fwd_tc16")
+    elif tc:
         buf = workspace("cam_tc", lib.gdn_cam_tc_ws_bytes(B, N, Cc), dev)
         L.check(lib.gdn_cam_fwd_tc(x.t.data_ptr(), pitch_of(x.t), gamma.t.data_ptr(), attn.data_ptr(), out.t.data_ptr(), pitch_of(out.t), B, N, Cc,
                                    buf.data_ptr(), buf.numel(), _stream()), "gdn_cam_fwd_tc")

@@ -209,7 +209,7 @@ class PAMModule(TapeModule):
         self.gamma = nn.Parameter(torch.zeros(1))
         self.precision: Optional[str] = None
 
-    def _build(self, ctx: BuildCtx, x: E.Var, out: Optional[E.Var] = None) -> E.Var:
+    def _build(self, ctx: BuildCtx, x: E.Var, out: Optional[E.Var] = None, y16: Optional[torch.Tensor] = None) -> E.Var:
         prec = (self.precision or default_pam_precision())
         B, H, W, Cc = x.t.shape
         if x.packed is None and E.tc_eligible(Cc, self.query.out_channels, 1, 1, 1, H, W):
@@ -227,7 +227,7 @@ class PAMModule(TapeModule):
         # the value projection's epilogue also emits the bf16 operand of the fused kernel (no separate packing pass over V)
         v16 = E.pam_v16_buffer(x.t) if prec == "fp16" else None
         v = E.op_conv(ctx.tape, x, ctx.v(self.value.weight), ctx.v(self.value.bias), y16=v16)
-        return E.op_pam_core(ctx.tape, x, q, k, v, ctx.v(self.gamma), precision=PREC_FP16 if prec == "fp16" else PREC_FP32, out=out, v16=v16)
+        return E.op_pam_core(ctx.tape, x, q, k, v, ctx.v(self.gamma), precision=PREC_FP16 if prec == "fp16" else PREC_FP32, out=out, v16=v16, y16=y16)
 
 
 class CAMModule(TapeModule):
@@ -237,8 +237,8 @@ class CAMModule(TapeModule):
         super().__init__()
         self.gamma = nn.Parameter(torch.zeros(1))
 
-    def _build(self, ctx: BuildCtx, x: E.Var, out: Optional[E.Var] = None) -> E.Var:
-        return E.op_cam(ctx.tape, x, ctx.v(self.gamma), out=out)
+    def _build(self, ctx: BuildCtx, x: E.Var, out: Optional[E.Var] = None, y16: Optional[torch.Tensor] = None) -> E.Var:
+        return E.op_cam(ctx.tape, x, ctx.v(self.gamma), out=out, y16=y16)
 
 
 class DANetAttention(TapeModule):
@@ -257,9 +257,18 @@ class DANetAttention(TapeModule):
     def _build(self, ctx: BuildCtx, x: E.Var) -> E.Var:
         B, H, W, Cc = x.t.shape
         cat = E.Var(E.new_nhwc(B, H, W, 2 * Cc, x.t))
-        self.position_attention._build(ctx, x, out=cat.slice(0, Cc))
-        self.channel_attention._build(ctx, x, out=cat.slice(Cc, 2 * Cc))
         conv = self.fuse[0]
+        pam_prec = self.position_attention.precision or default_pam_precision()
+        if E.danet_cat16_ok(x.t, pam_prec == "fp16", conv.out_channels):
+            # cat[PAM, CAM] is read by the fuse convolution alone: both attention kernels write their result straight into its bf16 operand
+            # (column blocks [0, C) and [C, 2C)); the fp32 cat tensor is never written (it only carries the shape and, in backward, the gradient)
+            cat16 = torch.empty((B * H * W, 2 * Cc), dtype=torch.bfloat16, device=x.t.device)
+            cat.packed = E.Packed(cat16, None, 2 * Cc)
+            self.position_attention._build(ctx, x, out=cat.slice(0, Cc), y16=cat16[:, :Cc])
+            self.channel_attention._build(ctx, x, out=cat.slice(Cc, 2 * Cc), y16=cat16[:, Cc:])
+        else:
+            self.position_attention._build(ctx, x, out=cat.slice(0, Cc))
+            self.channel_attention._build(ctx, x, out=cat.slice(Cc, 2 * Cc))
         assert conv.bias is None
         return E.op_conv_bn_act(ctx.tape, cat, ctx.v(conv.weight), ctx.bn(self.fuse[1]), training=self.fuse[1].training, act=ACT_RELU,
                                 stride=conv.stride[0], pad=conv.padding[0])

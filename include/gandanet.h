@@ -287,6 +287,8 @@ typedef struct {
   const uint16_t* v16;  /* optional (GDN_PREC_FP16 only, may be NULL): v already packed as the kernel's bf16 operand [B*N][192] -- columns [0,C) = v,
                            column C = 1, the rest 0 -- e.g. written by the value projection's epilogue (gdn_conv_tc_args.y16, pitch 192) into a
                            buffer whose tail columns were initialised once; the packing pass then touches q and k only */
+  uint16_t* y16; int y16_pitch; /* optional (GDN_PREC_FP16 only): y also written as bf16 rows of pitch y16_pitch -- a column block of the packed
+                                   operand of the convolution that consumes cat[PAM, CAM] (generator.py:156-157); y may then be NULL */
 } gdn_pam_fwd_args;
 size_t gdn_pam_fwd_ws_bytes(const gdn_pam_fwd_args* a);
 int gdn_pam_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s);
@@ -320,6 +322,9 @@ int gdn_cam_bwd(const float* x, int x_pitch, const float* gamma, const float* at
 size_t gdn_cam_tc_ws_bytes(int B, int N, int C);
 int gdn_cam_fwd_tc(const float* x, int x_pitch, const float* gamma, float* attn, float* y, int y_pitch, int B, int N, int C,
                    void* ws, size_t ws_bytes, gdn_stream_t s);
+/* the same with y also (or, with y == NULL, only) written as bf16 rows of pitch y16_pitch (see gdn_pam_fwd_args.y16) */
+int gdn_cam_fwd_tc16(const float* x, int x_pitch, const float* gamma, float* attn, float* y, int y_pitch, uint16_t* y16, int y16_pitch, int B, int N, int C,
+                     void* ws, size_t ws_bytes, gdn_stream_t s);
 int gdn_cam_bwd_tc(const float* x, int x_pitch, const float* gamma, const float* attn, const float* dy, int dy_pitch,
                    float* dx, int dx_pitch, int accumulate, float* dgamma, int B, int N, int C, void* ws, size_t ws_bytes, void* dot_ws, gdn_stream_t s);
 /* in-place-capable row softmax of [rows][n] (negate: softmax(-x)); lse optional.  torch.softmax at generator.py:118,136 */

@@ -361,6 +361,42 @@ def test_pam_merged_query_key_projection(conv, C, hw):
             assert rel_err(g1[k], g0[k]) < 1e-4, (k, rel_err(g1[k], g0[k]))
 
 
+def test_danet_outputs_written_as_fuse_operand():
+    """DANetAttention (generator.py:142-157) in the product mode: PAM and CAM write their results only as bf16 column blocks of the fuse
+    convolution's packed operand (gdn_pam_fwd_args.y16, gdn_cam_fwd_tc16) instead of an fp32 cat tensor that is packed afterwards -- the same
+    rounding of the same values: output, input gradient and all parameter gradients bitwise equal to the unfused launches."""
+    from gan_danet_b200 import engine as E
+    from gan_danet_b200.models.generator import DANetAttention
+    import gan_danet_b200 as P
+    gen = torch.Generator().manual_seed(13)
+    x = 0.5 * torch.randn(2, 160, 16, 32, generator=gen)
+    r = torch.randn(2, 160, 16, 32, generator=gen)
+
+    def run(flag):
+        torch.manual_seed(6)
+        m = DANetAttention(160)
+        m.apply(P.weights_init_normal)
+        with torch.no_grad():
+            m.position_attention.gamma.fill_(0.5)
+            m.channel_attention.gamma.fill_(0.05)
+        m.position_attention.precision = "fp16"
+        old, oldf = E.conv_precision, E.danet_cat16
+        E.set_conv_precision("bf16")
+        E.danet_cat16 = flag
+        try:
+            assert E.danet_cat16_ok(torch.empty(2, 16, 32, 160, device=DEV), True, 160) == flag
+            return _fwd_bwd(m, x, r)
+        finally:
+            E.set_conv_precision(old)
+            E.danet_cat16 = oldf
+
+    y1, dx1, g1 = run(True)
+    y0, dx0, g0 = run(False)
+    assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
+    bad = [k for k in g0 if not torch.equal(g1[k], g0[k])]
+    assert not bad, bad
+
+
 def test_pam_padding_is_exact():
     """The same aligned problem (N = 256) through the kernels directly and through the padded path forced to 512 rows: the
     padded keys get softmax weight 0 (2^-125 on the polynomial lanes) and the padded queries a zero cotangent, so forward and
