@@ -851,6 +851,8 @@ def release_buffers() -> None:
     _frozen_weights.clear()
 
 
+# Measured on B200 (same box, back to back): 58.4 -> 57.5 ms/step, fused PAM forward 833 -> 854 TFLOP/s inside the step.  The bf16 store is its own
+# instantiation of the PAM kernel: as a run-time branch of the one kernel it cost the fp32-store launches 4 %.
 danet_cat16: bool = os.environ.get("GDN_DANET_CAT16", "1") != "0"
 
 

@@ -287,8 +287,8 @@ typedef struct {
   const uint16_t* v16;  /* optional (GDN_PREC_FP16 only, may be NULL): v already packed as the kernel's bf16 operand [B*N][192] -- columns [0,C) = v,
                            column C = 1, the rest 0 -- e.g. written by the value projection's epilogue (gdn_conv_tc_args.y16, pitch 192) into a
                            buffer whose tail columns were initialised once; the packing pass then touches q and k only */
-  uint16_t* y16; int y16_pitch; /* optional (GDN_PREC_FP16 only): y also written as bf16 rows of pitch y16_pitch -- a column block of the packed
-                                   operand of the convolution that consumes cat[PAM, CAM] (generator.py:156-157); y may then be NULL */
+  uint16_t* y16; int y16_pitch; /* optional (GDN_PREC_FP16 only): y written as bf16 rows of pitch y16_pitch -- a column block of the packed
+                                   operand of the convolution that consumes cat[PAM, CAM] (generator.py:156-157) INSTEAD of the fp32 y, which must then be NULL */
 } gdn_pam_fwd_args;
 size_t gdn_pam_fwd_ws_bytes(const gdn_pam_fwd_args* a);
 int gdn_pam_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s);
