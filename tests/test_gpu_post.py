@@ -201,3 +201,23 @@ def test_graphed_generator_matches_eager(hw, conv):
             GraphedGenerator(G, a[0], a[2])
     finally:
         E.set_conv_precision(old)
+
+
+def test_train_ensemble_small(tmp_path):
+    """EnsembleTrainer.train_ensemble (deep_ensemble.ipynb:322-340) in small: two members (seeds 42, 43) trained for two epochs of two batches
+    on this rank, checkpoints written under the notebook's file names, members differ, and they load back through load_ensemble_models."""
+    import gan_danet_b200 as P
+    from gan_danet_b200.ensemble import EnsembleTrainer
+    from gan_danet_b200.synthetic import make_batch
+    ens = EnsembleTrainer(2, dict(input_channels=46, attention_type="danet", epochs=2, perceptual=False, sample_hw=(32, 64)), ensemble_dir=str(tmp_path))
+
+    def batches(epoch):
+        return [tuple(t.to(DEV) for t in make_batch(4 * epoch + 2 * i, 2, 8, 16)) for i in range(2)]
+
+    curves = ens.train_ensemble(batches, epochs=2)
+    assert set(curves) == {0, 1} and all(len(c) == 4 and all(np.isfinite(c)) for c in curves.values())
+    assert curves[0] != curves[1]                                   # different seeds, same data split
+    assert os.path.basename(ens.member_path(0)) == "best_model_member_1.pth" and os.path.exists(ens.member_path(1))
+    models = ens.load_ensemble_models(P.FlexibleUpsamplingModule, torch.device(DEV), 46, "danet")
+    assert len(models) == 2 and not models[0].training
+    assert not torch.equal(models[0].state_dict()["final.weight"], models[1].state_dict()["final.weight"])
