@@ -13,5 +13,6 @@ from .models import (  # noqa: F401
     weights_init_normal,
 )
 from .models.losses import BCEWithLogitsLoss, L1Loss, MSELoss  # noqa: F401
+from . import ops  # noqa: F401,E402  registers torch.ops.gandanet.* (CUDA dispatch key only; no GPU needed to register)
 
 __version__ = "0.1.0"

@@ -1,3 +1,5 @@
+"""Pinned host -> device copy bandwidth and pin_memory cost of one step's inputs (776 MB): explains box-to-box differences of bench.py's `e2e`
+(55 GB/s on a healthy box; the first batch's copy is exposed, the following ones overlap the previous step)."""
 import torch, time
 x = torch.empty(194_000_000, dtype=torch.float32).pin_memory()
 d = torch.empty_like(x, device="cuda")
