@@ -84,3 +84,16 @@ def test_custom_op_layer_registered():
         torch.ops.gandanet.upsample_bicubic2x(torch.zeros(1, 2, 2, 4))
     with pytest.raises(NotImplementedError):
         torch.ops.gandanet.pam_fwd(torch.zeros(1, 8, 16, 8), torch.zeros(1, 8, 16, 1), torch.zeros(1, 8, 16, 1), torch.zeros(1, 8, 16, 8), torch.zeros(1), "fp32")
+
+
+def test_python_free_harness_builds():
+    """tools/cabi_bench.cpp (plain C++ over include/gandanet.h, no torch) compiles and links against the library: the header is usable from
+    C++ as it stands and the harness stays in step with the argument structs."""
+    import os
+    import subprocess
+    from gan_danet_b200.build import HERE, build_harness, build_library
+    build_library()
+    exe = build_harness()
+    assert os.path.exists(exe)
+    out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libgandanet_sm100.so" in out and os.path.join(HERE, "libgandanet_sm100.so") in out      # resolved through the $ORIGIN rpath
