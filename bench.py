@@ -10,12 +10,14 @@ batch with gradient all-reduce (weak scaling).  Rank 0 prints ONE JSON line.
   value     : samples/s with the batch resident in HBM (CUDA events, barrier + synchronize on both sides, max over ranks)
   e2e       : same metric through the public trainer API with the step's inputs copied from pinned host memory and the
               two scalar losses read back inside the timed region
-  roofline  : the fused tcgen05 PAM forward kernel -- algorithmic FLOPs 2*B*N^2*(d+C) per launch / mean launch time
-              (CUDA events on the launching stream inside the timed steps) against MEASURED_PEAKS.json bf16 (sustained)
-  cpu_baseline : the CPU oracle port of the reference step (oracle/gan_danet_oracle.py, fp32, all host threads) on a
-              bounded sample (batch 1 of the same grid), rank 0 at N = 1 only
---impl reference times that same CPU port as the reference arm (the reference is pure PyTorch, /root/reference does not
-exist on the GPU box).
+  roofline  : the north-star kernel pair, the fused tcgen05 PAM forward + backward (pam_flash_fwd_kernel, pam_flash_bwd_kernel<0|1>):
+              algorithmic FLOPs 6*B*N^2*(d+C) per module (2 forward + 4 backward, un-padded d and C, recompute excluded: SURVEY 8d) / the
+              CUDA-event time of those launches inside the timed steps, against MEASURED_PEAKS.json bf16_tflops_sustained (a kernel timed
+              inside a long step); `frac_of_burst_peak` is the same against bf16_tflops.  roofline_conv = the convolution family.
+  cpu_baseline : the REFERENCE's own modules (oracle/_ref/models, placed there by oracle/build_ref.py) driven by the notebook's loop
+              (oracle/notebook_step.py), fp32, all host threads, on BASELINE.json configs[0] (batch 4, same grid): 1 warm-up + median of 3
+              steps, rank 0 at N = 1 only; kind "port" (oracle/gan_danet_oracle.py) only when oracle/_ref is absent
+--impl reference times the same thing as the reference arm.
 """
 from __future__ import annotations
 
@@ -42,12 +44,13 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--grid", default="64x128", help="generator-input / PAM grid h x w")
-    ap.add_argument("--pam-precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--pam-precision", default="fp16x3", choices=["fp16x3", "fp16", "fp32"],
+                    help="fp16x3 = fused tcgen05 PAM with fp16 hi+lo split logit operands (the parity-grade default), fp16 = single fp16 logit operands, fp32 = CUDA-core engine")
     ap.add_argument("--conv-precision", default="bf16", choices=["fp32", "bf16", "bf16x3"],
                     help="convolutions: bf16 = tcgen05 tensor cores (BASELINE config dtype), bf16x3 = hi+lo split on tensor cores, fp32 = CUDA-core parity engine")
     ap.add_argument("--no-perceptual", action="store_true")
-    ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-other-mode", action="store_true", help="do not also time the other fused-PAM logit mode (extra key other_pam_mode)")
     ap.add_argument("--kernel-detail", action="store_true", help="print a per-shape table of the tensor-core launches to stderr")
     return ap.parse_args()
 
@@ -100,33 +103,61 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_step_rate(h, w, batch, steps, warmup, perceptual=True):
-    """The reference's algorithm on the host cores: oracle port of the G+D step, fp32, all torch threads."""
+CPU_TIMED_STEPS, CPU_WARMUP, CPU_BATCH = 3, 1, 4        # configs[0] = batch 4, 1 warm-up + median of 3 timed steps
+
+
+def cpu_reference_step_rate(h, w, batch=CPU_BATCH, steps=CPU_TIMED_STEPS, warmup=CPU_WARMUP):
+    """The reference's G+D step on the host cores, fp32, all threads: (samples/s from the MEDIAN step, seconds per step, threads, kind, note)."""
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)           # torchrun exports OMP_NUM_THREADS=1: the arm must still use the whole host
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import gan_danet_oracle as oracle
-    import gan_danet_b200 as P
+    import notebook_step as NS
     from gan_danet_b200.synthetic import fast_batch
-    torch.manual_seed(0)
-    G = P.FlexibleUpsamplingModule(46)
-    D = P.Discriminator1()
     lr05, real, aux = fast_batch(123, batch, h, w)
-    G.apply(P.weights_init_normal)
-    for mod in (D.conv1, D.conv2, D.conv3, D.conv4, D.fc2):
-        mod.apply(P.weights_init_normal)
-    D._materialise_fc1(real)
-    torch.manual_seed(2)
-    vgg = P.PerceptualLoss(pretrained=False, device=torch.device("cpu")).vgg.state_dict() if perceptual else None
-    if vgg is None:
-        raise SystemExit("the CPU port always evaluates the perceptual term")
-    st = oracle.TrainState({k: v.clone() for k, v in G.state_dict().items()}, {k: v.clone() for k, v in D.state_dict().items()}, dict(vgg))
-    for _ in range(warmup):
-        oracle.train_step(st, lr05, real, aux, 3, 150)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        oracle.train_step(st, lr05, real, aux, 3, 150)
-    dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, torch.get_num_threads()
+    ref_root = next((r for r in (os.path.join(ROOT, "oracle", "_ref"), "/root/reference") if os.path.isdir(os.path.join(r, "models"))), None)
+    times = []
+    if ref_root is not None:
+        M = NS.load_reference_models(ref_root)
+        torch.manual_seed(0)
+        G = M.FlexibleUpsamplingModule(input_channels=46, attention_type="danet")
+        D = M.Discriminator1()
+        NS.init_like_the_authors(M, G, D, real)
+        torch.manual_seed(2)
+        perc = M.PerceptualLoss(pretrained=False, device=torch.device("cpu"))     # no network: random-init VGG19, as on the GPU arm
+        tr = NS.NotebookTrainer(M, G.train(), D.train(), epochs=150, device="cpu", perceptual=perc)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            tr.step(lr05, real, aux, epoch=3)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind, note = "reference", f"the reference's own modules ({'oracle/_ref' if ref_root.endswith('_ref') else ref_root}/models) under the notebook's loop (oracle/notebook_step.py)"
+    else:
+        import gan_danet_oracle as oracle
+        import gan_danet_b200 as P
+        torch.manual_seed(0)
+        G = P.FlexibleUpsamplingModule(46)
+        D = P.Discriminator1()
+        G.apply(P.weights_init_normal)
+        for mod in (D.conv1, D.conv2, D.conv3, D.conv4, D.fc2):
+            mod.apply(P.weights_init_normal)
+        D._materialise_fc1(real)
+        torch.manual_seed(2)
+        vgg = P.PerceptualLoss(pretrained=False, device=torch.device("cpu")).vgg.state_dict()
+        st = oracle.TrainState({k: v.clone() for k, v in G.state_dict().items()}, {k: v.clone() for k, v in D.state_dict().items()}, dict(vgg))
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            oracle.train_step(st, lr05, real, aux, 3, 150)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind, note = "port", "CPU oracle port of the reference step (oracle/_ref absent)"
+    times.sort()
+    med = times[len(times) // 2]
+    return batch / med, med, torch.get_num_threads(), kind, note
+
+
+def cpu_sample_text(args, h, w, note):
+    return (f"BASELINE configs[0]: batch {CPU_BATCH}, C_in 46, grid {h}x{w}, full loss incl. perceptual, fp32; {CPU_WARMUP} warm-up + median of {CPU_TIMED_STEPS} "
+            f"timed steps (a bounded sample of the batch-{args.batch} workload, same grid); {note}")
 
 
 def run_reference(args):
@@ -134,13 +165,13 @@ def run_reference(args):
     if rank != 0:
         return
     h, w = (int(v) for v in args.grid.split("x"))
-    b = args.cpu_sample_batch
-    rate, spt, threads = cpu_reference_step_rate(h, w, b, args.steps, min(args.warmup, 1))
-    sample = f"{args.steps} steps of batch {b} (bounded sample of the batch-{args.batch} workload, same grid), fp32, CPU oracle port of the reference step"
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+    rate, spt, threads, kind, note = cpu_reference_step_rate(h, w)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": CPU_TIMED_STEPS, "warmup": CPU_WARMUP,
             "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": workload_name(args, h, w), "sample_batch": b},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": workload_name(args, h, w), "global_batch": world * args.batch, "parallelism": f"dp{world}", "sample_batch": CPU_BATCH,
+                       "requested_steps": args.steps, "note": "the CPU arm runs on rank 0's host only, whatever --gpus says"},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": cpu_sample_text(args, h, w, note)},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -300,32 +331,71 @@ def run_ours(args):
                 d[0] += 1; d[1] += e[0].elapsed_time(e[1]); d[2] += e[2]
         for (fam, name), (n, t, f) in sorted(det.items(), key=lambda kv: -kv[1][1]):
             print(f"[detail] {t / args.steps:8.3f} ms/step {n // args.steps:3d}x {f / (t * 1e-3) / 1e12:7.1f} TF/s  {fam} {name}", file=sys.stderr)
+    # ---- north-star roofline: fused PAM forward + backward together (BASELINE.json metric "PAM attention TFLOP/s vs peak")
+    def roof_pam():
+        f, b = fams.get("pam_flash_fwd_kernel"), fams.get("pam_flash_bwd_kernel")
+        if not f or not b:
+            return None
+        ms_tot = (f["ms_per_step"] + b["ms_per_step"]) * args.steps
+        fl_tot = sum(e[2] for fam in ("pam_flash_fwd_kernel", "pam_flash_bwd_kernel") for e in timing[fam])
+        ach = fl_tot / (ms_tot * 1e-3) / 1e12
+        burst = peaks.get("bf16_tflops") if peaks else None
+        tr_f, tr_b = traffic.get("pam_flash_fwd_kernel"), traffic.get("pam_flash_bwd_kernel")
+        return {"kernel": "pam_flash_fwd_kernel + pam_flash_bwd_kernel<0|1> (fused tcgen05/TMEM position attention, forward + backward of the three PAM modules, "
+                          "operand packing and rowdot passes inside the timed calls)",
+                "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": peak_src,
+                "frac_of_burst_peak": (ach / burst) if burst else None, "burst_peak": burst,
+                "forward_tflops": f["tflops"], "backward_tflops": b["tflops"], "forward_frac": f["tflops"] / peak_tf, "backward_frac": b["tflops"] / peak_tf,
+                "traffic": (tr_f + tr_b) if (tr_f and tr_b) else None, "traffic_unit": "bytes of DRAM traffic per forward + backward call (ncu, r01 pass)",
+                "algorithmic_flops_per_step": fl_tot / args.steps, "ms_per_step": ms_tot / args.steps, "share_of_step": ms_tot / ms,
+                "launches": f["launches"] + b["launches"]}
+
     tc_fams = [f for f in fams if f in notes]
-    dominant = max(tc_fams, key=lambda f: fams[f]["ms_per_step"]) if tc_fams else None
-    roofline = roof(dominant) if dominant else None
-    roofline_pam = roof("pam_flash_fwd_kernel")
+    roofline = roof_pam() if args.pam_precision != "fp32" else None
+    roofline_conv = roof("conv_tc_fwd_kernel")
+
+    # ---- the other fused-PAM logit mode as an extra key (same weights, same inputs, a few steps): fp16x3 is the parity-grade default,
+    # fp16 (single fp16 logit operands) the faster one
+    other = None
+    if args.pam_precision in ("fp16x3", "fp16") and world == 1 and not args.skip_other_mode:
+        alt = "fp16" if args.pam_precision == "fp16x3" else "fp16x3"
+        G.set_pam_precision(alt)
+        for _ in range(2):
+            tr.train_step(*resident)
+        sync_all()
+        n_alt = max(3, min(args.steps, 5))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n_alt):
+            tr.train_step(*resident)
+        a1.record()
+        sync_all()
+        ms_alt = a0.elapsed_time(a1) / n_alt
+        other = {"pam": alt, "value": B / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt, "steps": n_alt}
+        G.set_pam_precision(args.pam_precision)
 
     if rank == 0:
+        pam_txt = {"fp16x3": "; PAM core: fp16 hi+lo split logits, bf16 P/V forward, fp16 gradient operands", "fp16": "; PAM core: fp16 logits, bf16 P/V forward, fp16 gradient operands",
+                   "fp32": ""}[args.pam_precision]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (hi+lo split)", "fp32": "fp32"}[args.conv_precision] + " operands, fp32 accumulate; fp32 activation storage"
-                         + ("; PAM core fp16 logits, bf16 P/V" if args.pam_precision == "fp16" else ""),
+                "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (hi+lo split)", "fp32": "fp32"}[args.conv_precision] + " operands, fp32 accumulate; fp32 activation storage" + pam_txt,
                 "data": "synthetic (seeded smooth random fields, random-init weights, random-init VGG19)",
                 "config": {"workload": workload_name(args, h, w), "global_batch": world * B, "parallelism": f"dp{world}", "conv": args.conv_precision,
-                           "pam": "fused tcgen05 flash forward + backward" if args.pam_precision == "fp16" else "fp32 engine",
+                           "pam": f"fused tcgen05 flash forward + backward ({args.pam_precision})" if args.pam_precision != "fp32" else "fp32 engine",
                            "l2": "inputs larger than L2 (the aux stack alone is %.0f MB per step)" % (aux_h.numel() * 4 / 1e6)},
                 "clocks": clk, "gpu_launches": launches,
                 "e2e": {"value": value_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(last.numel() * 4),
                         "ms_per_step": ms_e2e / args.steps,
                         "readback": "loss_D, loss_G of every step copied D2H into pinned memory (non-blocking), awaited with a one-step lag"},
-                "roofline": roofline, "roofline_pam": roofline_pam,
+                "roofline": roofline if roofline is not None else roofline_conv, "roofline_conv": roofline_conv,
                 "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in fams.items()},
                 "losses": {k: float(out[k]) for k in ("loss_D", "loss_G")}}
+        if other is not None:
+            line["other_pam_mode"] = other
         if world == 1 and not args.skip_cpu_baseline:
-            b = args.cpu_sample_batch
-            rate, spt, threads = cpu_reference_step_rate(h, w, b, 1, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"1 warm-up + 1 timed step of batch {b} (bounded sample of the batch-{B} workload, same grid), fp32, CPU oracle port"}
+            rate, spt, threads, kind, note = cpu_reference_step_rate(h, w)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "s_per_step": spt, "sample": cpu_sample_text(args, h, w, note)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

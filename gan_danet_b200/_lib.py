@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgandanet_sm100.so")
 
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
-PREC_FP32, PREC_BF16, PREC_FP16, PREC_BF16X3 = 0, 1, 2, 3
+PREC_FP32, PREC_BF16, PREC_FP16, PREC_BF16X3, PREC_FP16X3 = 0, 1, 2, 3, 4
 
 _vp, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 

@@ -199,8 +199,8 @@ extern "C" int gdn_pam_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s) {
   GDN_CHECK_ARG(a->B > 0 && a->N > 0 && a->C > 0 && a->d > 0 && a->qk_pitch >= a->d && a->v_pitch >= a->C && a->dy_pitch >= a->C);
   const int B = a->B, N = a->N, C = a->C, d = a->d;
   int rc;
+  if (a->precision != GDN_PREC_FP32) return gdn_pam_tc_bwd(a, s);          // computes rowdot itself (fused with the max |dy| reduction of its operand scaling)
   if ((rc = gdn_rowdot(a->dy, a->dy_pitch, a->o, C, (long long)B * N, C, a->rowdot, s)) != GDN_OK) return rc;
-  if (a->precision != GDN_PREC_FP32) return gdn_pam_tc_bwd(a, s);
   const int g = pam_chunk(B, N, a->chunk);
   if (!a->ws || a->ws_bytes < gdn_pam_bwd_ws_bytes(a)) { set_error("gdn_pam_bwd: workspace too small"); return GDN_EWORKSPACE; }
   const size_t nn = align256((size_t)g * N * N * 4);

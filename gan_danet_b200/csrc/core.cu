@@ -79,18 +79,23 @@ extern "C" int gdn_pam_tc_init(void);   // pam_tc.cu: opts the tcgen05 kernels i
 extern "C" int gdn_conv_tc_init(void);  // conv_tc.cu
 extern "C" int gdn_linear_tc_init(void);  // linear_tc.cu
 
+// Per-device set-up (cudaFuncSetAttribute is per device).  The caller's current device is restored: initialising the library for cuda:1 must not
+// move the process (and with it torch.cuda.current_device()) to cuda:1.
 extern "C" int gdn_init(int device) {
-  GDN_CHECK_CUDA(cudaSetDevice(device));
+  int prev = -1;
+  GDN_CHECK_CUDA(cudaGetDevice(&prev));
   cudaDeviceProp prop;
   GDN_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {
     set_error("gdn_init: device %d is sm_%d%d, this library is sm_100a only", device, prop.major, prop.minor);
     return GDN_EARCH;
   }
+  GDN_CHECK_CUDA(cudaSetDevice(device));
   int rc = gdn_pam_tc_init();
-  if (rc != GDN_OK) return rc;
-  if ((rc = gdn_conv_tc_init()) != GDN_OK) return rc;
-  return gdn_linear_tc_init();
+  if (rc == GDN_OK) rc = gdn_conv_tc_init();
+  if (rc == GDN_OK) rc = gdn_linear_tc_init();
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  return rc;
 }
 
 extern "C" int gdn_nchw_to_nhwc(const float* src, float* dst, int dst_pitch, int dst_c0, int B, int C, int H, int W, gdn_stream_t s) {

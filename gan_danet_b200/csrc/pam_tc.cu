@@ -40,22 +40,31 @@ using namespace gdn::tc;
 
 constexpr int TQ = 128, TK = 64, DPAD = 32, CPAD = 192;
 constexpr int KS = 6, VS = 6;
-constexpr int Q_BYTES = TQ * DPAD * 2;          // 8 KB, 64-byte rows, SWIZZLE_64B
-constexpr int K_BYTES = TK * DPAD * 2;          // 4 KB
+constexpr int Q_CHUNK = TQ * DPAD * 2;          // 8 KB, 64-byte rows, SWIZZLE_64B
+constexpr int K_CHUNK = TK * DPAD * 2;          // 4 KB
 constexpr int V_CHUNK = TK * 128;               // 8 KB: [64 keys][64 channels] fp16, 128-byte rows, SWIZZLE_128B
 constexpr int V_BYTES = (CPAD / 64) * V_CHUNK;  // 24 KB per key tile
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + Q_BYTES;
-constexpr int OFF_V = OFF_K + KS * K_BYTES;     // 32768 (1024-aligned)
-constexpr int OFF_BAR = OFF_V + VS * V_BYTES;   // 180224
-constexpr int OFF_MREF = OFF_BAR + 512;         // float [128]: shared reference maximum per row (log2 units)
-constexpr int OFF_LS = OFF_MREF + 128 * 4;      // float [2][128]
-constexpr int OFF_TMEM = OFF_LS + 2 * 128 * 4;  // uint32 tmem base
-constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024; // + alignment slack
 constexpr int STG_STRIDE = CPAD + 4;            // floats per staged output row (conflict-free float4 column writes)
-static_assert(OFF_V % 1024 == 0, "swizzle atoms");
-static_assert(TQ * STG_STRIDE * 4 <= VS * V_BYTES, "epilogue staging fits in the V ring");
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+// Shared-memory plan.  SPLIT = 1 (precision GDN_PREC_FP16X3): the logit operands are fp16 hi + lo pairs (q = q_hi + q_lo exactly to 22 mantissa bits),
+// stored as two 32-column chunks per tile; S = q_hi k_hi^T + q_lo k_hi^T + q_hi k_lo^T accumulates in the same TMEM buffer (three pairs of K = 16
+// MMAs instead of one).  The reference has NO 1/sqrt(d) scale (generator.py:115-118): logits reach +-100, where a single fp16 product is off by
+// 0.05 -- a 5 % error of the softmax weight; the split brings the logit error to ~1e-5.
+template <int SPLIT>
+struct FwdSmem {
+  static constexpr int Q_BYTES = Q_CHUNK * (1 + SPLIT);
+  static constexpr int K_BYTES = K_CHUNK * (1 + SPLIT);
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KS * K_BYTES;     // 32768 / 65536 (1024-aligned)
+  static constexpr int OFF_BAR = OFF_V + VS * V_BYTES;
+  static constexpr int OFF_MREF = OFF_BAR + 512;         // float [128]: shared reference maximum per row (log2 units)
+  static constexpr int OFF_LS = OFF_MREF + 128 * 4;      // float [2][128]
+  static constexpr int OFF_TMEM = OFF_LS + 2 * 128 * 4;  // uint32 tmem base
+  static constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024; // + alignment slack
+  static_assert(OFF_V % 1024 == 0, "swizzle atoms");
+  static_assert(TQ * STG_STRIDE * 4 <= VS * V_BYTES, "epilogue staging fits in the V ring");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
 constexpr int NTHREADS = 384;
 constexpr uint32_t COL_O = 256;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -84,9 +93,12 @@ __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo_byt
 
 // Y16 = 1: y is written only as a bf16 column block (FwdParams::y16).  A separate instantiation: with the bf16 store as a run-time branch of the
 // one kernel, the fp32-store launches ran 4 % slower inside the training step (846 -> 813 TFLOP/s, measured three times each).
-template <int Y16>
+template <int Y16, int SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV, const FwdParams p) {
+  using SM = FwdSmem<SPLIT>;
+  constexpr int Q_BYTES = SM::Q_BYTES, K_BYTES = SM::K_BYTES, OFF_Q = SM::OFF_Q, OFF_K = SM::OFF_K, OFF_V = SM::OFF_V, OFF_BAR = SM::OFF_BAR,
+                OFF_MREF = SM::OFF_MREF, OFF_TMEM = SM::OFF_TMEM;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -117,11 +129,13 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     if (lane == 0) {   // ---- Q + K producer
       mbar_expect_tx(bar(BAR_Q), Q_BYTES);
       tma_load_2d(base + OFF_Q, &mapQ, bar(BAR_Q), 0, sample * p.N + qtile * TQ);
+      if (SPLIT) tma_load_2d(base + OFF_Q + Q_CHUNK, &mapQ, bar(BAR_Q), DPAD, sample * p.N + qtile * TQ);          // the lo halves: columns [32, 64)
       for (int t = 0; t < T; ++t) {
         const int st = t % KS;
         if (t >= KS) mbar_wait(bar(BAR_KEMPTY + st), ((t / KS) - 1) & 1);
         mbar_expect_tx(bar(BAR_KFULL + st), K_BYTES);
         tma_load_2d(base + OFF_K + st * K_BYTES, &mapK, bar(BAR_KFULL + st), 0, sample * p.N + t * TK);
+        if (SPLIT) tma_load_2d(base + OFF_K + st * K_BYTES + K_CHUNK, &mapK, bar(BAR_KFULL + st), DPAD, sample * p.N + t * TK);
       }
     }
   } else if (warp == 3) {
@@ -137,7 +151,8 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     }
   } else if (warp == 1) {
     // ---- P.V issuer: the whole warp runs the loop (uniform control flow and descriptors), one elected lane issues
-    // A = P and B = V are bf16; bit 16: B is MN-major.  N = n_pv: C = 160 needs 176 of the 192 padded channel columns (measured: no change, 806 TFLOP/s either way -- the tensor pipe is not this kernel's limiter)
+    // A = P and B = V are bf16 (P needs bf16's exponent range for the lazy reference; a bf16 x fp16 operand pair raises an illegal-instruction
+    // fault on sm_100a: kind::f16 wants ONE format for A and B -- tried in round 2); bit 16: B is MN-major.  N = n_pv: C = 160 needs 176 of the 192 padded channel columns (measured: no change, 806 TFLOP/s either way -- the tensor pipe is not this kernel's limiter)
     const uint32_t IDESC_PV = idesc_f16(TQ, p.n_pv) | (1u << 7) | (1u << 10) | (1u << 16);
     const uint64_t vd_base = smem_desc_mn(base + OFF_V, V_CHUNK, 1024, LAYOUT_SW128);     // 64-channel groups 8 KB apart, 8-key groups 1 KB apart
     const uint32_t tmem_o = tmem + COL_O;
@@ -177,7 +192,15 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       tc_fence_after();
       const uint32_t d = tmem + u * TK;
       if (elect_one()) {
-        umma_f16_i<0>(d, qd0, kd, IDESC_QK);
+        if (SPLIT) {      // the two small cross terms first, the leading term last
+          umma_f16_i<0>(d, qd0 + (Q_CHUNK >> 4), kd, IDESC_QK);                        // q_lo k_hi^T
+          umma_f16_i<1>(d, qd1 + (Q_CHUNK >> 4), kd + 2, IDESC_QK);
+          umma_f16_i<1>(d, qd0, kd + (K_CHUNK >> 4), IDESC_QK);                        // q_hi k_lo^T
+          umma_f16_i<1>(d, qd1, kd + (K_CHUNK >> 4) + 2, IDESC_QK);
+          umma_f16_i<1>(d, qd0, kd, IDESC_QK);                                         // q_hi k_hi^T
+        } else {
+          umma_f16_i<0>(d, qd0, kd, IDESC_QK);
+        }
         umma_f16_i<1>(d, qd1, kd + 2, IDESC_QK);
         tc_commit(bar(BAR_KEMPTY + st));
         tc_commit(bar(BAR_SFULL + u));
@@ -307,22 +330,34 @@ pam_flash_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   }
 }
 
+// fp32 -> fp16, round to nearest, saturating at the largest finite value (the network's q, k, v are O(10); an overflow must not become inf)
+__device__ __forceinline__ __half f2h_sat(float f) { return __float2half_rn(fminf(fmaxf(f, -65504.f), 65504.f)); }
+
 // ---- operand packing: fp32 NHWC slices -> tensor-core operands.  One warp per row: lanes 0-3 write the four 16-byte chunks of
 // Q[row][0..32) (fp16), lanes 4-7 those of K (fp16), lanes 8-31 the 24 chunks of V[row][0..192) (bf16; zero beyond C except the
 // channel of ones at column C, which makes the P.V product deliver the softmax denominator).
+// SPLIT: Q and K rows are 64 halves wide: [hi(32) | lo(32)] with hi = fp16(v), lo = fp16(v - hi).
+template <int SPLIT>
 __global__ void __launch_bounds__(256) pack_qkv_kernel(const float* __restrict__ q, const float* __restrict__ k, int qk_pitch, int d, const float* __restrict__ v, int v_pitch,
                                                        int C, __half* __restrict__ Qh, __half* __restrict__ Kh, __nv_bfloat16* __restrict__ Vb, long long rows, int vec4) {
   const int lane = threadIdx.x & 31;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  constexpr int QK_ROW = DPAD * (1 + SPLIT);
   for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
     if (lane < 8) {
       const float* src = lane < 4 ? q : k;
       __half* dst = lane < 4 ? Qh : Kh;
       const int c0 = (lane & 3) * 8;
       __align__(16) __half h[8];
+      __align__(16) __half l[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(c0 + e < d ? __ldg(src + (size_t)r * qk_pitch + c0 + e) : 0.f);
-      *reinterpret_cast<uint4*>(dst + (size_t)r * DPAD + c0) = *reinterpret_cast<const uint4*>(h);
+      for (int e = 0; e < 8; ++e) {
+        const float f = c0 + e < d ? __ldg(src + (size_t)r * qk_pitch + c0 + e) : 0.f;
+        h[e] = __float2half_rn(f);
+        if (SPLIT) l[e] = __float2half_rn(f - __half2float(h[e]));
+      }
+      *reinterpret_cast<uint4*>(dst + (size_t)r * QK_ROW + c0) = *reinterpret_cast<const uint4*>(h);
+      if (SPLIT) *reinterpret_cast<uint4*>(dst + (size_t)r * QK_ROW + DPAD + c0) = *reinterpret_cast<const uint4*>(l);
     } else if (v != nullptr) {        // v == nullptr: the caller supplies the packed V operand (gdn_pam_fwd_args.v16)
       const int c0 = (lane - 8) * 8;
       __align__(16) __nv_bfloat16 h[8];
@@ -344,9 +379,12 @@ __global__ void __launch_bounds__(256) pack_qkv_kernel(const float* __restrict__
 }
 // aug == nullptr: columns d, d+1 = 1 (the K side); else columns d, d+1 = -aug[row] split into fp16 hi + lo (the Q side: -lse), so that the
 // logit product of the backward kernels comes out of the tensor core as S - lse (exact to 2^-22 |lse|) and no thread ever loads lse.
+// split: rows are 64 halves wide, [hi(32) | lo(32)]; the lo chunk holds fp16(v - hi) in columns [0, d) and zeros elsewhere (the augmentation
+// columns live in the hi chunk only, so the two cross products add nothing to them).
 __global__ void __launch_bounds__(256) pack_qk_kernel(const float* __restrict__ src, int pitch, int d, __half* __restrict__ dst, long long rows,
-                                                      const float* __restrict__ aug, int augment) {
+                                                      const float* __restrict__ aug, int augment, int split) {
   const long long total = rows * DPAD;
+  const int row_w = split ? 2 * DPAD : DPAD;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long r = idx / DPAD; int c = (int)(idx % DPAD);
     float v = c < d ? src[(size_t)r * pitch + c] : 0.f;
@@ -358,7 +396,9 @@ __global__ void __launch_bounds__(256) pack_qk_kernel(const float* __restrict__ 
         v = c == d ? hi : a - hi;
       }
     }
-    dst[idx] = __float2half_rn(v);
+    const __half h = __float2half_rn(v);
+    dst[(size_t)r * row_w + c] = h;
+    if (split) dst[(size_t)r * row_w + DPAD + c] = c < d ? __float2half_rn(v - __half2float(h)) : __float2half_rn(0.f);
   }
 }
 
@@ -385,38 +425,47 @@ using namespace gdn::pamtc;
 
 extern "C" int gdn_pam_tc_bwd_init(void);
 extern "C" int gdn_pam_tc_init(void) {
-  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_fwd_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<0>::SMEM_BYTES));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<0>::SMEM_BYTES));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_fwd_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<1>::SMEM_BYTES));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<1>::SMEM_BYTES));
   return gdn_pam_tc_bwd_init();
 }
 
+static inline bool pam_tc_precision(int p) { return p == GDN_PREC_FP16 || p == GDN_PREC_FP16X3; }
+
 extern "C" size_t gdn_pam_tc_fwd_ws_bytes(const gdn_pam_fwd_args* a) {
   size_t rows = (size_t)a->B * a->N;
-  return 2 * align256(rows * DPAD * 2) + align256(rows * CPAD * 2);
+  const size_t qk_row = DPAD * 2 * (a->precision == GDN_PREC_FP16X3 ? 2 : 1);
+  return 2 * align256(rows * qk_row) + align256(rows * CPAD * 2);
 }
 
 extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
-  GDN_CHECK_ARG(a->precision == GDN_PREC_FP16);
+  GDN_CHECK_ARG(pam_tc_precision(a->precision));
+  const int split = a->precision == GDN_PREC_FP16X3;
   GDN_CHECK_ARG(a->N % TQ == 0 && a->d <= DPAD && a->C < CPAD && a->C % 4 == 0);      // C < CPAD: column C of V is the channel of ones
   GDN_CHECK_ARG(a->x_pitch % 4 == 0 && a->y_pitch % 4 == 0);
   GDN_CHECK_ARG(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->y & 15) == 0 && ((uintptr_t)a->o & 15) == 0);
   if (!a->ws || a->ws_bytes < gdn_pam_tc_fwd_ws_bytes(a)) { set_error("gdn_pam_fwd(fp16): workspace too small"); return GDN_EWORKSPACE; }
   const size_t rows = (size_t)a->B * a->N;
+  const size_t qk_cols = (size_t)DPAD * (split ? 2 : 1);
   char* w = reinterpret_cast<char*>(a->ws);
-  __half* Qh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
-  __half* Kh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
+  __half* Qh = reinterpret_cast<__half*>(w); w += align256(rows * qk_cols * 2);
+  __half* Kh = reinterpret_cast<__half*>(w); w += align256(rows * qk_cols * 2);
   const __nv_bfloat16* Vb = a->v16 ? reinterpret_cast<const __nv_bfloat16*>(a->v16) : reinterpret_cast<__nv_bfloat16*>(w);
   GDN_CHECK_ARG(((uintptr_t)Vb & 15) == 0);
   cudaStream_t st = as_stream(s);
   const long long pb = cdiv((long long)rows, 8);
-  pack_qkv_kernel<<<(unsigned)(pb < 16 * kNumSMs ? pb : 16 * kNumSMs), 256, 0, st>>>(a->q, a->k, a->qk_pitch, a->d, a->v16 ? nullptr : a->v, a->v_pitch, a->C, Qh, Kh,
-                                                                                     a->v16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(w), (long long)rows,
-                                                                                     a->C % 4 == 0 && a->v_pitch % 4 == 0 && ((uintptr_t)a->v & 15) == 0);
+  const unsigned pgrid = (unsigned)(pb < 16 * kNumSMs ? pb : 16 * kNumSMs);
+  const int vec4 = a->C % 4 == 0 && a->v_pitch % 4 == 0 && ((uintptr_t)a->v & 15) == 0;
+  __nv_bfloat16* vdst = a->v16 ? nullptr : reinterpret_cast<__nv_bfloat16*>(w);
+  if (split) pack_qkv_kernel<1><<<pgrid, 256, 0, st>>>(a->q, a->k, a->qk_pitch, a->d, a->v16 ? nullptr : a->v, a->v_pitch, a->C, Qh, Kh, vdst, (long long)rows, vec4);
+  else pack_qkv_kernel<0><<<pgrid, 256, 0, st>>>(a->q, a->k, a->qk_pitch, a->d, a->v16 ? nullptr : a->v, a->v_pitch, a->C, Qh, Kh, vdst, (long long)rows, vec4);
   GDN_CHECK_LAUNCH();
   CUtensorMap mq, mk, mv;
   int rc;
-  if ((rc = make_map(&mq, Qh, rows, DPAD, TQ, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
-  if ((rc = make_map(&mk, Kh, rows, DPAD, TK, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
+  if ((rc = make_map(&mq, Qh, rows, qk_cols, TQ, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
+  if ((rc = make_map(&mk, Kh, rows, qk_cols, TK, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
   if ((rc = make_map(&mv, Vb, rows, CPAD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) != GDN_OK) return rc;
   FwdParams p;
   p.x = a->x; p.x_pitch = a->x_pitch; p.gamma = a->gamma; p.o = a->o; p.y = a->y; p.y_pitch = a->y_pitch; p.lse = a->lse;
@@ -425,10 +474,14 @@ extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
   p.y16 = reinterpret_cast<__nv_bfloat16*>(a->y16); p.y16_pitch = a->y16_pitch;
   GDN_CHECK_ARG(a->y || a->y16);
   if (a->y16) GDN_CHECK_ARG(a->y16_pitch >= a->C && a->y16_pitch % 4 == 0 && ((uintptr_t)a->y16 & 7) == 0);
-  if (a->y16 && !a->y) pam_flash_fwd_kernel<1><<<a->B * p.tiles_per_sample, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
-  else {
+  const int grid = a->B * p.tiles_per_sample;
+  if (a->y16 && !a->y) {
+    if (split) pam_flash_fwd_kernel<1, 1><<<grid, NTHREADS, FwdSmem<1>::SMEM_BYTES, st>>>(mq, mk, mv, p);
+    else pam_flash_fwd_kernel<1, 0><<<grid, NTHREADS, FwdSmem<0>::SMEM_BYTES, st>>>(mq, mk, mv, p);
+  } else {
     GDN_CHECK_ARG(a->y && !a->y16);      // the bf16 block replaces the fp32 output (both at once is not a supported combination)
-    pam_flash_fwd_kernel<0><<<a->B * p.tiles_per_sample, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+    if (split) pam_flash_fwd_kernel<0, 1><<<grid, NTHREADS, FwdSmem<1>::SMEM_BYTES, st>>>(mq, mk, mv, p);
+    else pam_flash_fwd_kernel<0, 0><<<grid, NTHREADS, FwdSmem<0>::SMEM_BYTES, st>>>(mq, mk, mv, p);
   }
   GDN_CHECK_LAUNCH();
   return GDN_OK;
@@ -449,29 +502,40 @@ extern "C" int gdn_pam_tc_fwd(const gdn_pam_fwd_args* a, gdn_stream_t s) {
 // operands, the dy rows carry -rowdot (bf16 hi + lo) and the V rows 1 in two spare channel columns, so the tensor core delivers
 // X = S - lse and Y = dP - rowdot directly (ncu before: the per-column lse / rowdot broadcasts of the dK/dV launch were 39 % of the
 // shared-memory data pipe next to 57 % tensor-core operand reads).
-// Operand precision: logits fp16 x fp16 (identical to the forward kernel, so P matches the saved log-sum-exp);
-// everything that carries gradient magnitude (dy, dS, P for dV) is bf16 (fp32 exponent range: no underflow of small gradients).
+// Operand precision: every operand is fp16 (11-bit mantissa), fp32 accumulation.  Logits fp16 x fp16 (hi + lo split in GDN_PREC_FP16X3)
+// exactly as in the forward kernel, so P matches the saved log-sum-exp.  The gradient-carrying operands fit fp16's range through ONE
+// power-of-two scale per call: sc = 2^-ceil(log2 max|dy|) (device scalar, computed by the rowdot pass that reads dy anyway), dy*sc in
+// [-1, 1]; dS = P*(dP - rowdot)*sc is bounded by 2*C*max|v| and saturates instead of overflowing; P <= 1.  1/sc is folded into the
+// epilogue with gamma.  With bf16 gradient operands (round 1) the cancellation in dP - rowdot amplified the 2^-9 operand rounding to
+// 7e-3 on dq / dk at reference-scale logits (std 10); fp16: 1.4e-3 (tools/measure_pam_split.py, float64 emulation in DESIGN.md 4).
 //   warp 0: TMA producer   warp 1: tcgen05.mma issuer   warp 2: TMEM allocator   warps 4-11: softmax/dS (thread = TMEM lane = row)
 // TMEM: X0 X1 [0,128)  Y0 Y1 [128,256)  small accumulator (dQ | dK) [256,288)  dV [288,480)
 namespace gdn {
 namespace pamtc {
 namespace bwd {
 constexpr int TO = 128, TI = 64, NCH = CPAD / 64, ST = 4;
-constexpr int OQK_BYTES = TO * DPAD * 2;              // 8 KB  fp16 [128][32], SWIZZLE_64B
+constexpr int OQK_CHUNK = TO * DPAD * 2;              // 8 KB  fp16 [128][32], SWIZZLE_64B
 constexpr int OC_CHUNK = TO * 128;                    // 16 KB bf16 [128][64], SWIZZLE_128B
-constexpr int IQK_BYTES = TI * DPAD * 2;              // 4 KB
+constexpr int IQK_CHUNK = TI * DPAD * 2;              // 4 KB
 constexpr int IT_BYTES = DPAD * TI * 2;               // 4 KB  bf16 [32][64]
 constexpr int IC_CHUNK = TI * 128;                    // 8 KB  bf16 [64][64]
-constexpr int LR_BYTES = 2 * TI * 4;                  // lse | rowdot of the 64 inner rows (MODE 1)
-constexpr int OFF_OQK = 0;
-constexpr int OFF_OC = OFF_OQK + OQK_BYTES;           // 8192
-constexpr int OFF_IN = OFF_OC + NCH * OC_CHUNK;       // 57344
-constexpr int IN_IQK = 0, IN_IT = IQK_BYTES, IN_IC = IN_IT + IT_BYTES, IN_LR = IN_IC + NCH * IC_CHUNK;   // 0, 4096, 8192, 32768
-constexpr int IN_BYTES = 33 * 1024;                   // 33280 rounded up to a multiple of 1024
-constexpr int OFF_BARS = OFF_IN + ST * IN_BYTES;      // 192512 (P and dS never touch shared memory: they go back to TMEM over the consumed X / Y columns)
-constexpr int OFF_TSLOT = OFF_BARS + 256;
-constexpr int SMEM = OFF_TSLOT + 16 + 1024;
-static_assert(SMEM <= 227 * 1024, "shared memory budget");
+// SPLIT = 1 (GDN_PREC_FP16X3): the logit operands are fp16 hi + lo pairs, two 32-column chunks per tile, exactly as in the forward kernel
+// (X = o_lo i_hi^T + o_hi i_lo^T + o_hi i_hi^T; the -lse / 1 augmentation columns live in the hi chunks only).
+template <int SPLIT>
+struct BwdSmem {
+  static constexpr int OQK_BYTES = OQK_CHUNK * (1 + SPLIT);
+  static constexpr int IQK_BYTES = IQK_CHUNK * (1 + SPLIT);
+  static constexpr int OFF_OQK = 0;
+  static constexpr int OFF_OC = OFF_OQK + OQK_BYTES;           // 8192 / 16384
+  static constexpr int OFF_IN = OFF_OC + NCH * OC_CHUNK;       // 57344 / 65536
+  static constexpr int IN_IQK = 0, IN_IT = IQK_BYTES, IN_IC = IN_IT + IT_BYTES;   // IN_IC: 8192 / 12288
+  static constexpr int IN_BYTES = IN_IC + NCH * IC_CHUNK + 1024;           // 33 / 37 KB per stage
+  static constexpr int OFF_BARS = OFF_IN + ST * IN_BYTES;      // (P and dS never touch shared memory: they go back to TMEM over the consumed X / Y columns)
+  static constexpr int OFF_TSLOT = OFF_BARS + 256;
+  static constexpr int SMEM = OFF_TSLOT + 16 + 1024;
+  static_assert(OFF_OC % 1024 == 0 && OFF_IN % 1024 == 0 && IN_IC % 1024 == 0 && IN_BYTES % 1024 == 0, "swizzle atoms");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
 enum { B_OUT = 0, B_INFULL = 1, B_INEMPTY = B_INFULL + ST, B_XFULL = B_INEMPTY + ST, B_YFULL = B_XFULL + 2, B_DSFULL = B_YFULL + 2, B_ACC = B_DSFULL + 2,
        B_OCT = B_ACC + 1, B_COUNT = B_OCT + 1 };
 static_assert(B_COUNT * 8 <= 256, "barrier area");
@@ -489,16 +553,26 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// two fp32 -> packed fp16x2, round to nearest, saturating to +-65504 (an overflowing dS must not become inf: inf * 0 = NaN in the next MMA)
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 struct Params {
-  const float* lse; const float* rowdot; const float* gamma;
+  const float* lse; const float* rowdot; const float* gamma; const float* scale;   // scale[1] = sc (power of two applied to dy and rowdot), scale[2] = 1 / sc
   float* dq; float* dk; float* dv;
   int B, N, C, d;
 };
 
-template <int MODE>
+template <int MODE, int SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_constant__ CUtensorMap mapKh, const __grid_constant__ CUtensorMap mapV,
                      const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapQt, const __grid_constant__ CUtensorMap mapKt, const Params p) {
+  using SM = BwdSmem<SPLIT>;
+  constexpr int OQK_BYTES = SM::OQK_BYTES, IQK_BYTES = SM::IQK_BYTES, OFF_OQK = SM::OFF_OQK, OFF_OC = SM::OFF_OC, OFF_IN = SM::OFF_IN, IN_IQK = SM::IN_IQK,
+                IN_IT = SM::IN_IT, IN_IC = SM::IN_IC, IN_BYTES = SM::IN_BYTES, OFF_BARS = SM::OFF_BARS, OFF_TSLOT = SM::OFF_TSLOT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -539,7 +613,11 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     if (lane == 0) {   // ---- TMA producer
       mbar_expect_tx(bar(B_OUT), OQK_BYTES + NCH * OC_CHUNK);
       tma_load_2d(base + OFF_OQK, m_oqk, bar(B_OUT), 0, row0);
-      tma_load_2d(base + OFF_OQK + OQK_BYTES / 2, m_oqk, bar(B_OUT), 0, row0 + 64);
+      tma_load_2d(base + OFF_OQK + OQK_CHUNK / 2, m_oqk, bar(B_OUT), 0, row0 + 64);
+      if (SPLIT) {
+        tma_load_2d(base + OFF_OQK + OQK_CHUNK, m_oqk, bar(B_OUT), DPAD, row0);
+        tma_load_2d(base + OFF_OQK + OQK_CHUNK + OQK_CHUNK / 2, m_oqk, bar(B_OUT), DPAD, row0 + 64);
+      }
       for (int c = 0; c < NCH; ++c) {
         tma_load_2d(base + OFF_OC + c * OC_CHUNK, m_oc, bar(B_OUT), c * 64, row0);
         tma_load_2d(base + OFF_OC + c * OC_CHUNK + OC_CHUNK / 2, m_oc, bar(B_OUT), c * 64, row0 + 64);
@@ -551,13 +629,14 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
         const int irow = sample * p.N + t * TI;
         mbar_expect_tx(bar(B_INFULL + s), IQK_BYTES + IT_BYTES + NCH * IC_CHUNK);
         tma_load_2d(st + IN_IQK, m_iqk, bar(B_INFULL + s), 0, irow);
+        if (SPLIT) tma_load_2d(st + IN_IQK + IQK_CHUNK, m_iqk, bar(B_INFULL + s), DPAD, irow);
         tma_load_2d(st + IN_IT, m_it, bar(B_INFULL + s), t * TI, sample * DPAD);
         for (int c = 0; c < NCH; ++c) tma_load_2d(st + IN_IC + c * IC_CHUNK, m_ic, bar(B_INFULL + s), c * 64, irow);
       }
     }
   } else if (warp == 1) {
     // ---- MMA issuer: warp-uniform loop, one elected lane issues; descriptors are base descriptors plus 16-byte-unit offsets
-    constexpr uint32_t ID_X = idesc_f16(TO, TI), ID_Y = idesc_bf16(TO, TI, 0), ID_S = idesc_bf16(TO, DPAD, 0), ID_B = idesc_bf16(TO, CPAD, 1);
+    constexpr uint32_t ID_X = idesc_f16(TO, TI), ID_Y = idesc_f16(TO, TI), ID_S = idesc_f16(TO, DPAD), ID_B = idesc_f16(TO, CPAD) | (1u << 16);   // all fp16; ID_B: B MN-major
     const uint64_t d64 = smem_desc(base, 512, LAYOUT_SW64), d128 = smem_desc(base, 1024, LAYOUT_SW128);
     const uint64_t dmn = smem_desc_lbo(base, IC_CHUNK, 1024, LAYOUT_SW128);     // MN-major: 64-channel groups 8 KB apart, 8-row groups 1 KB apart
     const uint64_t oqk_d = d64 + (OFF_OQK >> 4), oc_d = d128 + (OFF_OC >> 4);
@@ -570,7 +649,15 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
       const uint32_t st_off = (uint32_t)(OFF_IN + s * IN_BYTES) >> 4;
       const uint64_t iqk_d = d64 + st_off + (IN_IQK >> 4), ic_d = d128 + st_off + (IN_IC >> 4);
       if (elect_one()) {
-        umma_f16_i<0>(tmem + COL_X + b * TI, oqk_d, iqk_d, ID_X);
+        if (SPLIT) {      // same order of terms as the forward kernel
+          umma_f16_i<0>(tmem + COL_X + b * TI, oqk_d + (OQK_CHUNK >> 4), iqk_d, ID_X);                 // o_lo i_hi^T
+          umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d + (OQK_CHUNK >> 4) + 2, iqk_d + 2, ID_X);
+          umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d, iqk_d + (IQK_CHUNK >> 4), ID_X);                 // o_hi i_lo^T
+          umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d + 2, iqk_d + (IQK_CHUNK >> 4) + 2, ID_X);
+          umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d, iqk_d, ID_X);                                    // o_hi i_hi^T (carries -lse)
+        } else {
+          umma_f16_i<0>(tmem + COL_X + b * TI, oqk_d, iqk_d, ID_X);
+        }
         umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d + 2, iqk_d + 2, ID_X);
         tc_commit(bar(B_XFULL + b));
 #pragma unroll
@@ -671,15 +758,11 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
         uint32_t ds_pk[16], p_pk[16];
         // Y already is dy V^T - rowdot (same trick: -rowdot and 1 in two spare channel columns): dS = P * Y
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          __nv_bfloat162 dsa = __floats2bfloat162_rn(x[i] * y[i], x[i + 1] * y[i + 1]);
-          __nv_bfloat162 dsb = __floats2bfloat162_rn(x[i + 2] * y[i + 2], x[i + 3] * y[i + 3]);
-          ds_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&dsa);
-          ds_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&dsb);
+        for (int i = 0; i < 32; i += 2) {
+          ds_pk[i >> 1] = pack_half2_sat(x[i] * y[i], x[i + 1] * y[i + 1]);
           if (MODE == 1) {
-            __nv_bfloat162 pa = __floats2bfloat162_rn(x[i], x[i + 1]), pb = __floats2bfloat162_rn(x[i + 2], x[i + 3]);
+            __half2 pa = __floats2half2_rn(x[i], x[i + 1]);          // P <= 1
             p_pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pa);
-            p_pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&pb);
           }
         }
         // dS (and P) go back to TMEM over already consumed Y (X) columns -- inner rows [32h, 32h+32) -> columns [16h, 16h+16) -- as the A
@@ -695,7 +778,7 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     // ---- epilogue
     mbar_wait(bar(B_ACC), 0);
     tc_fence_after();
-    const float g = __ldg(p.gamma);
+    const float g = __ldg(p.gamma) * __ldg(p.scale + 2);       // gamma / sc: an exact power-of-two rescale
     const size_t grow = (size_t)row0 + row;
     if (wg == 0) {
       float a[32];
@@ -727,33 +810,78 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
   }
 }
 
-// fp32 [rows][pitch] -> bf16 [rows][CPAD], zero padded
-// columns C, C+1: 1 (aug == nullptr, the V side) or -aug[row] split into bf16 hi + lo (the dy side: -rowdot), so that dy V^T comes out as Y - rowdot
-__global__ void __launch_bounds__(256) pack_rows_bf16_kernel(const float* __restrict__ src, int pitch, int C, long long rows, __nv_bfloat16* __restrict__ dst,
-                                                             const float* __restrict__ aug) {
+// rowdot[m] = sum_c dy[m][c] * o[m][c] (one warp per row) and, on the way, max |dy| over the whole tensor (atomicMax on the bit pattern of a
+// non-negative float; slot[0] must be zero before the launch)
+__global__ void __launch_bounds__(256) rowdot_amax_kernel(const float* __restrict__ dy, int dy_pitch, const float* __restrict__ o, int o_pitch, long long M, int C,
+                                                          float* __restrict__ out, unsigned* __restrict__ slot) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float amax = 0.f;
+  const bool v4 = (C % 4 == 0) && (dy_pitch % 4 == 0) && (o_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
+  for (long long m = warp; m < M; m += nwarps) {
+    float s = 0.f;
+    if (v4) {
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(dy + (size_t)m * dy_pitch + c)), b = __ldg(reinterpret_cast<const float4*>(o + (size_t)m * o_pitch + c));
+        s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        const float a = dy[(size_t)m * dy_pitch + c];
+        s = fmaf(a, o[(size_t)m * o_pitch + c], s);
+        amax = fmaxf(amax, fabsf(a));
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[m] = s;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+  if (lane == 0 && amax > 0.f && !(amax > 3.0e38f)) atomicMax(slot, __float_as_uint(amax));
+}
+// slot[0] = bits of max|dy|  ->  slot[1] = sc = 2^-(e+1) with max|dy| in [2^e, 2^(e+1)) (so |dy * sc| < 1), slot[2] = 1 / sc; both exact powers of two
+__global__ void pam_scale_kernel(float* slot) {
+  const unsigned bits = reinterpret_cast<unsigned*>(slot)[0];
+  int e = (int)(bits >> 23) - 127;                  // 0 (all-zero gradient) gives e = -127: clamp below
+  e = e < -100 ? -1 : (e > 100 ? 100 : e);
+  slot[1] = exp2f((float)(-(e + 1)));
+  slot[2] = exp2f((float)(e + 1));
+}
+// fp32 [rows][pitch] -> fp16 [rows][CPAD], zero padded, multiplied by the power-of-two scale *sc (sc == nullptr: 1).
+// via_bf16: the values are rounded to bf16 first (and are then exact in fp16): the V operand of the backward must be the SAME rounded V the
+// forward kernel multiplied P with, otherwise rowdot = sum dy*o (from the forward's o) and dP = dy V^T disagree by V's rounding and the
+// cancellation in dS = P*(dP - rowdot) amplifies it (float64 emulation: dq 2.2e-3 with the consistent V, 6.0e-3 with fp16-rounded V).
+// columns C, C+1: 1 (aug == nullptr, the V side) or -aug[row]*sc split into fp16 hi + lo (the dy side: -rowdot), so that dy V^T comes out as (dP - rowdot)*sc
+__global__ void __launch_bounds__(256) pack_rows_f16_kernel(const float* __restrict__ src, int pitch, int C, long long rows, __half* __restrict__ dst,
+                                                            const float* __restrict__ aug, const float* __restrict__ sc, int via_bf16) {
   const long long total = rows * (CPAD / 8);
+  const float scale = sc ? __ldg(sc) : 1.f;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long r = idx / (CPAD / 8); const int c0 = (int)(idx % (CPAD / 8)) * 8;
-    __align__(16) __nv_bfloat16 h[8];
+    __align__(16) __half h[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = c0 + e;
-      float v = c < C ? __ldg(src + (size_t)r * pitch + c) : 0.f;
+      float v = c < C ? __ldg(src + (size_t)r * pitch + c) * scale : 0.f;
+      if (via_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
       if (c == C || c == C + 1) {
         if (!aug) v = 1.f;
         else {
-          const float a = -__ldg(aug + r);
-          const float hi = __bfloat162float(__float2bfloat16_rn(a));
+          const float a = -__ldg(aug + r) * scale;
+          const float hi = __half2float(f2h_sat(a));
           v = c == C ? hi : a - hi;
         }
       }
-      h[e] = __float2bfloat16_rn(v);
+      h[e] = f2h_sat(v);
     }
     *reinterpret_cast<uint4*>(dst + (size_t)r * CPAD + c0) = *reinterpret_cast<const uint4*>(h);
   }
 }
-// fp32 [B][N][d] (pitch) -> bf16 [B][DPAD][N], zero rows for c >= d
-__global__ void __launch_bounds__(256) pack_t_bf16_kernel(const float* __restrict__ v, int pitch, int d, int N, __nv_bfloat16* __restrict__ vt) {
+// fp32 [B][N][d] (pitch) -> fp16 [B][DPAD][N], zero rows for c >= d
+__global__ void __launch_bounds__(256) pack_t_f16_kernel(const float* __restrict__ v, int pitch, int d, int N, __half* __restrict__ vt) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, n0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -764,7 +892,7 @@ __global__ void __launch_bounds__(256) pack_t_bf16_kernel(const float* __restric
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int n = n0 + tx;
-    if (n < N) vt[((size_t)b * DPAD + i) * N + n] = __float2bfloat16_rn(tile[tx][i]);
+    if (n < N) vt[((size_t)b * DPAD + i) * N + n] = f2h_sat(tile[tx][i]);
   }
 }
 static int make_map_t(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle sw) {
@@ -786,61 +914,82 @@ static int make_map_t(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, u
 using namespace gdn::pamtc::bwd;
 
 extern "C" int gdn_pam_tc_bwd_init(void) {
-  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM));
-  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_bwd_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<0>::SMEM));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_bwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<0>::SMEM));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_bwd_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<1>::SMEM));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(pam_flash_bwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<1>::SMEM));
   return GDN_OK;
 }
 
 extern "C" size_t gdn_pam_tc_bwd_ws_bytes(const gdn_pam_bwd_args* a) {
   const size_t rows = (size_t)a->B * a->N;
-  return 2 * align256(rows * DPAD * 2) + 2 * align256(rows * CPAD * 2) + 2 * align256((size_t)a->B * DPAD * a->N * 2);
+  const size_t qk_row = DPAD * 2 * (a->precision == GDN_PREC_FP16X3 ? 2 : 1);
+  return 256 + 2 * align256(rows * qk_row) + 2 * align256(rows * CPAD * 2) + 2 * align256((size_t)a->B * DPAD * a->N * 2);
 }
 
-// rowdot (= sum_c dy*o per row) has been computed by the caller (gdn_pam_bwd in attention.cu)
+// computes rowdot (= sum_c dy*o per row, an output: dgamma = sum rowdot) and the gradient scale itself
 extern "C" int gdn_pam_tc_bwd(const gdn_pam_bwd_args* a, gdn_stream_t s) {
-  GDN_CHECK_ARG(a->precision == GDN_PREC_FP16);
+  GDN_CHECK_ARG(a->precision == GDN_PREC_FP16 || a->precision == GDN_PREC_FP16X3);
+  const int split = a->precision == GDN_PREC_FP16X3;
   GDN_CHECK_ARG(a->N % TO == 0 && a->d + 2 <= DPAD && a->C + 2 <= CPAD && a->C % 4 == 0);    // two spare operand columns carry -lse / -rowdot
   GDN_CHECK_ARG(((uintptr_t)a->dv & 15) == 0 && ((uintptr_t)a->lse & 15) == 0 && ((uintptr_t)a->rowdot & 15) == 0);
   if (!a->ws || a->ws_bytes < gdn_pam_tc_bwd_ws_bytes(a)) { set_error("gdn_pam_bwd(fp16): workspace too small"); return GDN_EWORKSPACE; }
   const size_t rows = (size_t)a->B * a->N;
+  const size_t qk_cols = (size_t)DPAD * (split ? 2 : 1);
   char* w = reinterpret_cast<char*>(a->ws);
-  __half* Qh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
-  __half* Kh = reinterpret_cast<__half*>(w); w += align256(rows * DPAD * 2);
-  __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(w); w += align256(rows * CPAD * 2);
-  __nv_bfloat16* DYb = reinterpret_cast<__nv_bfloat16*>(w); w += align256(rows * CPAD * 2);
-  __nv_bfloat16* Qt = reinterpret_cast<__nv_bfloat16*>(w); w += align256((size_t)a->B * DPAD * a->N * 2);
-  __nv_bfloat16* Kt = reinterpret_cast<__nv_bfloat16*>(w);
+  float* slot = reinterpret_cast<float*>(w); w += 256;          // [0] bits of max|dy|, [1] sc, [2] 1/sc
+  __half* Qh = reinterpret_cast<__half*>(w); w += align256(rows * qk_cols * 2);
+  __half* Kh = reinterpret_cast<__half*>(w); w += align256(rows * qk_cols * 2);
+  __half* Vb = reinterpret_cast<__half*>(w); w += align256(rows * CPAD * 2);
+  __half* DYb = reinterpret_cast<__half*>(w); w += align256(rows * CPAD * 2);
+  __half* Qt = reinterpret_cast<__half*>(w); w += align256((size_t)a->B * DPAD * a->N * 2);
+  __half* Kt = reinterpret_cast<__half*>(w);
   cudaStream_t st = as_stream(s);
+  GDN_CHECK_CUDA(cudaMemsetAsync(slot, 0, 16, st));
+  {
+    const long long wb = cdiv((long long)rows, 8);
+    rowdot_amax_kernel<<<(unsigned)(wb < 16 * kNumSMs ? wb : 16 * kNumSMs), 256, 0, st>>>(a->dy, a->dy_pitch, a->o, a->C, (long long)rows, a->C, a->rowdot,
+                                                                                         reinterpret_cast<unsigned*>(slot));
+    GDN_CHECK_LAUNCH();
+    pam_scale_kernel<<<1, 1, 0, st>>>(slot);
+    GDN_CHECK_LAUNCH();
+  }
   const int pg = (int)(cdiv((long long)rows * DPAD, 256) < 16 * kNumSMs ? cdiv((long long)rows * DPAD, 256) : 16 * kNumSMs);
-  pack_qk_kernel<<<pg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, Qh, (long long)rows, a->lse, 1);       // columns d, d+1: -lse (hi, lo)
+  pack_qk_kernel<<<pg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, Qh, (long long)rows, a->lse, 1, split);       // columns d, d+1: -lse (hi, lo)
   GDN_CHECK_LAUNCH();
-  pack_qk_kernel<<<pg, 256, 0, st>>>(a->k, a->qk_pitch, a->d, Kh, (long long)rows, nullptr, 1);      // columns d, d+1: 1
+  pack_qk_kernel<<<pg, 256, 0, st>>>(a->k, a->qk_pitch, a->d, Kh, (long long)rows, nullptr, 1, split);      // columns d, d+1: 1
   GDN_CHECK_LAUNCH();
   const int rg = (int)(cdiv((long long)rows * (CPAD / 8), 256) < 16 * kNumSMs ? cdiv((long long)rows * (CPAD / 8), 256) : 16 * kNumSMs);
-  pack_rows_bf16_kernel<<<rg, 256, 0, st>>>(a->v, a->v_pitch, a->C, (long long)rows, Vb, nullptr);          // columns C, C+1: 1
+  pack_rows_f16_kernel<<<rg, 256, 0, st>>>(a->v, a->v_pitch, a->C, (long long)rows, Vb, nullptr, nullptr, 1);          // bf16-rounded v; columns C, C+1: 1
   GDN_CHECK_LAUNCH();
-  pack_rows_bf16_kernel<<<rg, 256, 0, st>>>(a->dy, a->dy_pitch, a->C, (long long)rows, DYb, a->rowdot);      // columns C, C+1: -rowdot (hi, lo)
+  pack_rows_f16_kernel<<<rg, 256, 0, st>>>(a->dy, a->dy_pitch, a->C, (long long)rows, DYb, a->rowdot, slot + 1, 0);    // dy*sc; columns C, C+1: -rowdot*sc (hi, lo)
   GDN_CHECK_LAUNCH();
   dim3 tg((unsigned)cdiv(a->N, 32), 1, (unsigned)a->B);
-  pack_t_bf16_kernel<<<tg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, a->N, Qt);
+  pack_t_f16_kernel<<<tg, 256, 0, st>>>(a->q, a->qk_pitch, a->d, a->N, Qt);
   GDN_CHECK_LAUNCH();
-  pack_t_bf16_kernel<<<tg, 256, 0, st>>>(a->k, a->qk_pitch, a->d, a->N, Kt);
+  pack_t_f16_kernel<<<tg, 256, 0, st>>>(a->k, a->qk_pitch, a->d, a->N, Kt);
   GDN_CHECK_LAUNCH();
   CUtensorMap mq, mk, mv, mdy, mqt, mkt;
   int rc;
-  if ((rc = make_map_t(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Qh, rows, DPAD, 64, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
-  if ((rc = make_map_t(&mk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Kh, rows, DPAD, 64, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
-  if ((rc = make_map_t(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, Vb, rows, CPAD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
-  if ((rc = make_map_t(&mdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, DYb, rows, CPAD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
-  if ((rc = make_map_t(&mqt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, Qt, (uint64_t)a->B * DPAD, (uint64_t)a->N, DPAD, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
-  if ((rc = make_map_t(&mkt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, Kt, (uint64_t)a->B * DPAD, (uint64_t)a->N, DPAD, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Qh, rows, qk_cols, 64, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Kh, rows, qk_cols, 64, DPAD, CU_TENSOR_MAP_SWIZZLE_64B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Vb, rows, CPAD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mdy, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, DYb, rows, CPAD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mqt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Qt, (uint64_t)a->B * DPAD, (uint64_t)a->N, DPAD, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
+  if ((rc = make_map_t(&mkt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Kt, (uint64_t)a->B * DPAD, (uint64_t)a->N, DPAD, 64, CU_TENSOR_MAP_SWIZZLE_128B)) != GDN_OK) return rc;
   bwd::Params p;
-  p.lse = a->lse; p.rowdot = a->rowdot; p.gamma = a->gamma; p.dq = a->dq; p.dk = a->dk; p.dv = a->dv;
+  p.lse = a->lse; p.rowdot = a->rowdot; p.gamma = a->gamma; p.scale = slot; p.dq = a->dq; p.dk = a->dk; p.dv = a->dv;
   p.B = a->B; p.N = a->N; p.C = a->C; p.d = a->d;
   const int grid = a->B * (a->N / TO);
-  pam_flash_bwd_kernel<0><<<grid, NTHREADS, bwd::SMEM, st>>>(mq, mk, mv, mdy, mqt, mkt, p);
-  GDN_CHECK_LAUNCH();
-  pam_flash_bwd_kernel<1><<<grid, NTHREADS, bwd::SMEM, st>>>(mq, mk, mv, mdy, mqt, mkt, p);
+  if (split) {
+    pam_flash_bwd_kernel<0, 1><<<grid, NTHREADS, BwdSmem<1>::SMEM, st>>>(mq, mk, mv, mdy, mqt, mkt, p);
+    GDN_CHECK_LAUNCH();
+    pam_flash_bwd_kernel<1, 1><<<grid, NTHREADS, BwdSmem<1>::SMEM, st>>>(mq, mk, mv, mdy, mqt, mkt, p);
+  } else {
+    pam_flash_bwd_kernel<0, 0><<<grid, NTHREADS, BwdSmem<0>::SMEM, st>>>(mq, mk, mv, mdy, mqt, mkt, p);
+    GDN_CHECK_LAUNCH();
+    pam_flash_bwd_kernel<1, 0><<<grid, NTHREADS, BwdSmem<0>::SMEM, st>>>(mq, mk, mv, mdy, mqt, mkt, p);
+  }
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

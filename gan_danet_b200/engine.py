@@ -13,12 +13,16 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import warnings
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib as L
-from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, PREC_BF16, PREC_BF16X3, PREC_FP16, PREC_FP32
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, PREC_BF16, PREC_BF16X3, PREC_FP16, PREC_FP16X3, PREC_FP32
+
+PAM_TC_PRECISIONS = (PREC_FP16, PREC_FP16X3)     # fused tcgen05 flash kernels: fp16 logit operands / fp16 hi+lo split logit operands
+PAM_PRECISION_NAMES = {"fp32": PREC_FP32, "fp16": PREC_FP16, "fp16x3": PREC_FP16X3}
 
 Tensor = torch.Tensor
 
@@ -40,22 +44,31 @@ def _stream() -> C.c_void_p:
 
 
 def _lib(t: Tensor):
+    """The library, initialised for the tensor's device.  Launches go to the CURRENT device's current stream (``_stream``), so a tensor that lives
+    on another device would be handed to the wrong GPU as a foreign pointer: refuse it here (the module entry points switch devices themselves)."""
     if not t.is_cuda:
         raise L.GdnError("gan_danet_b200 kernels need CUDA tensors on an sm_100 device (no CPU fallback)")
-    return L.lib_for_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    cur = _get_device() if _get_device is not None else torch.cuda.current_device()
+    if idx != cur:
+        raise L.GdnError(f"tensor on cuda:{idx} but the current device is cuda:{cur}: wrap the call in `with torch.cuda.device({idx}):` "
+                         "(TapeModule.forward and the trainers do)")
+    return L.lib_for_device(idx)
 
 
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-_workspaces: Dict[Tuple[int, str], Tensor] = {}
+_workspaces: Dict[Tuple[int, int, str], Tensor] = {}
 pam_bwd_tensor_core: bool = os.environ.get("GDN_PAM_BWD", "tc").lower() != "fp32"   # fused tcgen05 backward when the forward ran on tensor cores
 kernel_timing: Optional[dict] = None   # set to {} by bench.py: family -> [(start event, end event, algorithmic FLOPs)] on the launching stream
 
 
 def workspace(name: str, nbytes: int, device) -> Tensor:
-    key = (device.index if device.index is not None else 0, name)
+    """Scratch buffer per (device, stream, purpose): two streams of one device never share a workspace."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, _raw_stream(idx) if _raw_stream is not None else torch.cuda.current_stream(device).cuda_stream, name)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
@@ -218,6 +231,35 @@ def set_conv_precision(p: str) -> None:
     conv_precision = p
 
 
+class conv_precision_scope:
+    """``with conv_precision_scope('bf16x3'):`` -- the convolutions RECORDED inside run their forward in that precision (their backward closures
+    execute later, under whatever precision is current then).  Used for Discriminator1's forward in the product mode."""
+
+    def __init__(self, p: Optional[str]):
+        self.p = p
+
+    def __enter__(self):
+        global conv_precision
+        self.old = conv_precision
+        if self.p is not None:
+            set_conv_precision(self.p)
+
+    def __exit__(self, *exc):
+        global conv_precision
+        conv_precision = self.old
+        return False
+
+
+# Discriminator1 has no normalisation layer: the bf16 operand rounding of its three tensor-core convolutions reaches the logits directly, and
+# loss_D = BCE(logits) moved by up to 1.5e-2 against the reference in round 1 (200-step teacher-forced walk).  In the product mode its FORWARD
+# convolutions therefore use hi+lo split operands (3 MMA passes on 0.35 TF per step: +1 ms of 57); the backward stays bf16.
+discriminator_forward_x3: bool = os.environ.get("GDN_D_FORWARD_X3", "1") != "0"
+
+
+def discriminator_forward_precision() -> Optional[str]:
+    return "bf16x3" if (discriminator_forward_x3 and conv_precision == "bf16") else None
+
+
 def tc_eligible(cin: int, cout: int, kh: int, kw: int, stride: int, ho: int, wo: int) -> bool:
     """Shapes the tensor-core kernel takes; the rest (fully connected layers, 1- and 3-channel inputs) stay on the
     fp32 CUDA-core engine, which is HBM-bound there anyway."""
@@ -276,6 +318,12 @@ def bf16_storage_ok() -> bool:
 
 
 _frozen_weights: Dict[Tuple, Packed] = {}
+
+
+def drop_frozen_weights(uid: int) -> None:
+    """Evicts the packed weights of one PerceptualLoss instance (called by its weakref finalizer): keys start with (uid, ...)."""
+    for k in [k for k in _frozen_weights if isinstance(k[0], tuple) and k[0] and k[0][0] == uid]:
+        del _frozen_weights[k]
 
 
 def pack_weight(w: Tensor, transposed: bool, frozen_key: Optional[Tuple] = None) -> Packed:
@@ -580,15 +628,20 @@ class Tape:
     def __init__(self, record: bool = True):
         self.record = record
         self.ops: List[Callable[[], None]] = []
+        self.consumed = False
 
     def push(self, fn: Callable[[], None]) -> None:
         if self.record:
             self.ops.append(fn)
 
     def backward(self) -> None:
+        if self.consumed:
+            raise L.GdnError("this module's backward has already run: its saved buffers were released (call forward again; retain_graph / "
+                             "a second backward through the same output is not supported)")
         for fn in reversed(self.ops):
             fn()
         self.ops.clear()
+        self.consumed = True
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -872,11 +925,18 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
     B, H, W, Cc = x.t.shape
     N, d = H * W, q.t.shape[-1]
     dev = x.t.device
-    if precision == PREC_FP16 and N % 128 != 0 and pam_pad_to_tiles and d < 32 and Cc < 192 and Cc % 4 == 0:
+    tcp = precision in PAM_TC_PRECISIONS
+    if tcp and N % 128 != 0 and pam_pad_to_tiles and d < 32 and Cc < 192 and Cc % 4 == 0:
         assert y16 is None
-        return _op_pam_core_padded(tape, x, q, k, v, gamma, out)
-    if precision == PREC_FP16 and (N % 128 != 0 or d > 32 or Cc >= 192 or Cc % 4 != 0):
-        precision = PREC_FP32      # shape outside the tensor-core kernel's tiling: fp32 CUDA-core engine
+        return _op_pam_core_padded(tape, x, q, k, v, gamma, out, precision=precision)
+    if tcp and (N % 128 != 0 or d > 32 or Cc >= 192 or Cc % 4 != 0):
+        # shape outside the tensor-core kernels' tiling (the reference's channel counts 160/176/184 and d = 20..23 are inside): the fp32 CUDA-core
+        # engine materialises N x N chunks and is ~15x slower -- say so instead of silently falling off the cliff
+        if not pam_allow_fp32_fallback:
+            raise L.GdnError(f"op_pam_core: shape N={N} d={d} C={Cc} is outside the fused tensor-core kernel (needs d <= 32, C < 192, C % 4 == 0); "
+                             "pass precision 'fp32' explicitly or set engine.pam_allow_fp32_fallback = True")
+        warnings.warn(f"PAM shape N={N} d={d} C={Cc} runs on the fp32 CUDA-core engine (about 15x slower than the fused tcgen05 kernel)", RuntimeWarning, stacklevel=2)
+        precision, tcp = PREC_FP32, False
     if out is None:
         out = Var(torch.empty(x.t.shape, dtype=torch.float32, device=dev))
     o = torch.empty((B, N, Cc), dtype=torch.float32, device=dev)
@@ -891,13 +951,13 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
     need = lib.gdn_pam_fwd_ws_bytes(C.byref(a))
     buf = workspace("pam", need, dev)
     a.ws, a.ws_bytes = buf.data_ptr(), buf.numel()
-    if v16 is not None and precision == PREC_FP16:
+    if v16 is not None and tcp:
         assert v16.shape == (B * N, 192) and v16.dtype == torch.bfloat16
         a.v16 = v16.data_ptr()
     if y16 is not None:     # y only as a bf16 column block (a strided [B*N, C] view) of the consumer's packed operand: out.t is never written
-        assert precision == PREC_FP16 and y16.dtype == torch.bfloat16 and y16.shape == (B * N, Cc) and y16.stride(1) == 1
+        assert tcp and y16.dtype == torch.bfloat16 and y16.shape == (B * N, Cc) and y16.stride(1) == 1
         a.y, a.y16, a.y16_pitch = None, y16.data_ptr(), y16.stride(0)
-    fam = "pam_flash_fwd_kernel" if precision == PREC_FP16 else "pam_fwd_fp32"
+    fam = "pam_flash_fwd_kernel" if tcp else "pam_fwd_fp32"
     _timed(fam, 2.0 * B * N * N * (d + Cc), lambda: L.check(lib.gdn_pam_fwd(C.byref(a), _stream()), "gdn_pam_fwd"))
     y = out
 
@@ -919,7 +979,7 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
         need_b = lib.gdn_pam_bwd_ws_bytes(C.byref(b))
         wsb = workspace("pam", need_b, dev)
         b.ws, b.ws_bytes = wsb.data_ptr(), wsb.numel()
-        famb = "pam_flash_bwd_kernel" if b.precision == PREC_FP16 else "pam_bwd_fp32"
+        famb = "pam_flash_bwd_kernel" if b.precision in PAM_TC_PRECISIONS else "pam_bwd_fp32"
         _timed(famb, 4.0 * B * N * N * (d + Cc), lambda: L.check(lib.gdn_pam_bwd(C.byref(b), _stream()), "gdn_pam_bwd"))
         if gamma.needs_grad:
             gamma.add_grad(sums_to_float(colstats(rowdot), 1))
@@ -936,11 +996,13 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
     return y
 
 
+pam_allow_fp32_fallback: bool = os.environ.get("GDN_PAM_FP32_FALLBACK", "0") == "1"    # shapes outside the fused kernel: raise (default) or warn + fp32 engine
 pam_pad_to_tiles: bool = os.environ.get("GDN_PAM_PAD", "1") != "0"   # N % 128 != 0 (the authors' 45x22 grid, N = 990) on the tensor-core kernels
 PAM_KEY_MASK = -30000.0     # exactly representable in fp16; exp2((q.k + PAM_KEY_MASK) * log2e - m) underflows to 0 (2^-125 on the polynomial lanes)
 
 
-def _op_pam_core_padded(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, out: Optional[Var], pad_to: Optional[int] = None) -> Var:
+def _op_pam_core_padded(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, out: Optional[Var], pad_to: Optional[int] = None,
+                        precision: int = PREC_FP16X3) -> Var:
     """The fused tcgen05 kernels tile N in blocks of 128.  Other grids are padded to the next multiple per sample and the
     padded KEYS are masked through a spare column of the zero-padded logit operands (d < 32): q gets a column of ones, k a column
     that is 0 on real positions and PAM_KEY_MASK on padded ones, so every padded logit is S = -30000 and its softmax weight is 0.
@@ -961,7 +1023,7 @@ def _op_pam_core_padded(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, 
     kp[:, 0, N:, d] = PAM_KEY_MASK
     sub = Tape(record=tape.record)
     vars_p = [Var(padded(x.t, Cc), False), Var(qp, q.needs_grad), Var(kp, k.needs_grad), Var(padded(v.t, Cc), v.needs_grad)]
-    yp = op_pam_core(sub, *vars_p, gamma, precision=PREC_FP16)
+    yp = op_pam_core(sub, *vars_p, gamma, precision=precision)
     if out is None:
         out = Var(torch.empty(x.t.shape, dtype=torch.float32, device=dev))
     out.t.view(B, N, Cc).copy_(yp.t[:, 0, :N])          # view(): a channel slice of a concat buffer merges H and W without a copy
@@ -1228,32 +1290,44 @@ class TapeFunction(torch.autograd.Function):
         record = any(needs)
         tape = Tape(record)
         pvars = [Var(p.detach(), bool(needs[2 + i])) for i, p in enumerate(params)]
-        out, xin = build(tape, x.detach(), bool(needs[1]), pvars)
+        if not x.is_cuda:
+            raise L.GdnError("gan_danet_b200 modules need CUDA tensors on an sm_100 device (no CPU fallback)")
+        with torch.cuda.device(x.device):
+            out, xin = build(tape, x.detach(), bool(needs[1]), pvars)
         ctx.tape, ctx.pvars, ctx.xin, ctx.out = tape, pvars, xin, out
-        ctx.x_shape = x.shape
+        ctx.x_shape, ctx.dev = x.shape, x.device
+        ctx.params, ctx.versions = params, [p._version for p in params]      # an in-place update between forward and backward would be read by dgrad
         res = to_nchw(out.t) if out.t.dim() == 4 else out.t
         return res
 
     @staticmethod
     def backward(ctx, dout: Tensor):
+        if ctx.tape is None or ctx.tape.consumed:
+            raise L.GdnError("backward through a gan_danet_b200 module a second time: its saved buffers are released after the first backward "
+                             "(retain_graph=True / two separate backward passes through one forward are not supported -- sum the losses first)")
+        changed = [i for i, (p, v) in enumerate(zip(ctx.params, ctx.versions)) if p._version != v]
+        if changed:
+            raise L.GdnError(f"{len(changed)} parameter tensor(s) were modified in place between this module's forward and backward "
+                             "(e.g. optimizer.step() before .backward()): the data gradient would use the updated weights")
         out = ctx.out
-        dout = dout.contiguous()
-        out.g = grad_to_nhwc(dout) if out.t.dim() == 4 else dout
-        ctx.tape.backward()
-        gx = None
-        if ctx.needs_input_grad[1] and ctx.xin.g is not None:
-            gx = to_nchw(ctx.xin.g) if ctx.xin.g.dim() == 4 else ctx.xin.g
-        grads = []
-        for i, pv in enumerate(ctx.pvars):
-            if ctx.needs_input_grad[2 + i]:
-                g = pv.g
-                if g is None:
-                    g = torch.empty_like(pv.t)
-                    fill_(g.view(-1) if g.is_contiguous() else g, 0.0)
-                grads.append(g.view(pv.t.shape))
-            else:
-                grads.append(None)
-        ctx.tape = ctx.pvars = ctx.xin = ctx.out = None
+        with torch.cuda.device(ctx.dev):
+            dout = dout.contiguous()
+            out.g = grad_to_nhwc(dout) if out.t.dim() == 4 else dout
+            ctx.tape.backward()
+            gx = None
+            if ctx.needs_input_grad[1] and ctx.xin.g is not None:
+                gx = to_nchw(ctx.xin.g) if ctx.xin.g.dim() == 4 else ctx.xin.g
+            grads = []
+            for i, pv in enumerate(ctx.pvars):
+                if ctx.needs_input_grad[2 + i]:
+                    g = pv.g
+                    if g is None:
+                        g = torch.empty_like(pv.t)
+                        fill_(g.view(-1) if g.is_contiguous() else g, 0.0)
+                    grads.append(g.view(pv.t.shape))
+                else:
+                    grads.append(None)
+        ctx.pvars = ctx.xin = ctx.out = ctx.params = None       # ctx.tape stays (consumed) so that a second backward raises instead of returning zeros
         return (None, gx, *grads)
 
 

@@ -61,8 +61,9 @@ class Discriminator1(TapeModule):
 
     def _build(self, ctx: BuildCtx, x: E.Var) -> E.Var:
         slope = self.activation.negative_slope
-        for conv in (self.conv1, self.conv2, self.conv3, self.conv4):
-            x = _conv(ctx, x, conv, act=ACT_LRELU, slope=slope)
+        with E.conv_precision_scope(E.discriminator_forward_precision()):      # product mode: hi+lo split operands in the forward (no normalisation in D)
+            for conv in (self.conv1, self.conv2, self.conv3, self.conv4):
+                x = _conv(ctx, x, conv, act=ACT_LRELU, slope=slope)
         f = _flatten_nchw(ctx, x)
         h = E.op_linear(ctx.tape, f, ctx.v(self.fc1.weight), ctx.v(self.fc1.bias), act=ACT_LRELU, slope=slope)
         return E.op_linear(ctx.tape, h, ctx.v(self.fc2.weight), ctx.v(self.fc2.bias))

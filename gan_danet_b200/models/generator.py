@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from .. import engine as E
-from .._lib import ACT_NONE, ACT_RELU, PREC_FP16, PREC_FP32
+from .._lib import ACT_NONE, ACT_RELU, PREC_FP16, PREC_FP16X3, PREC_FP32
 
 # --- plain PyTorch modules the reference exports but never runs on the hot path --------------------
 
@@ -85,8 +85,13 @@ class CBAMBlock(nn.Module):
 
 
 def default_pam_precision() -> str:
-    """'fp16' = fused tcgen05 flash kernel (default), 'fp32' = CUDA-core parity engine.  Env: GDN_PAM_PRECISION."""
-    return os.environ.get("GDN_PAM_PRECISION", "fp16").lower()
+    """'fp16x3' = fused tcgen05 flash kernels with fp16 hi+lo split logit operands (default: the mode that meets the 1e-3 parity bar at the
+    reference's unscaled logits), 'fp16' = the same kernels with single fp16 logit operands (about 5 % faster, softmax weights off by up to 5 % at
+    |logit| ~ 100), 'fp32' = CUDA-core parity engine.  Env: GDN_PAM_PRECISION."""
+    p = os.environ.get("GDN_PAM_PRECISION", "fp16x3").lower()
+    if p not in E.PAM_PRECISION_NAMES:
+        raise ValueError(f"GDN_PAM_PRECISION={p!r}: expected one of {sorted(E.PAM_PRECISION_NAMES)}")
+    return p
 
 
 class BuildCtx:
@@ -197,8 +202,8 @@ class TransitionLayer(TapeModule):
 
 
 class PAMModule(TapeModule):
-    """Position attention, reference generator.py:104-122.  ``precision``: 'fp16' runs the fused tcgen05/TMEM flash
-    kernel (fp16 operands, fp32 accumulate), 'fp32' the CUDA-core parity engine."""
+    """Position attention, reference generator.py:104-122.  ``precision``: 'fp16x3' / 'fp16' run the fused tcgen05/TMEM flash
+    kernels (fp16 hi+lo split / single fp16 logit operands, fp32 accumulate), 'fp32' the CUDA-core parity engine."""
 
     def __init__(self, channels: int) -> None:
         super().__init__()
@@ -225,9 +230,11 @@ class PAMModule(TapeModule):
             q = _conv(ctx, x, self.query)
             k = _conv(ctx, x, self.key)
         # the value projection's epilogue also emits the bf16 operand of the fused kernel (no separate packing pass over V)
-        v16 = E.pam_v16_buffer(x.t) if prec == "fp16" else None
+        if prec not in E.PAM_PRECISION_NAMES:
+            raise ValueError(f"PAM precision {prec!r}: expected one of {sorted(E.PAM_PRECISION_NAMES)}")
+        v16 = E.pam_v16_buffer(x.t) if prec != "fp32" else None
         v = E.op_conv(ctx.tape, x, ctx.v(self.value.weight), ctx.v(self.value.bias), y16=v16)
-        return E.op_pam_core(ctx.tape, x, q, k, v, ctx.v(self.gamma), precision=PREC_FP16 if prec == "fp16" else PREC_FP32, out=out, v16=v16, y16=y16)
+        return E.op_pam_core(ctx.tape, x, q, k, v, ctx.v(self.gamma), precision=E.PAM_PRECISION_NAMES[prec], out=out, v16=v16, y16=y16)
 
 
 class CAMModule(TapeModule):
@@ -259,7 +266,7 @@ class DANetAttention(TapeModule):
         cat = E.Var(E.new_nhwc(B, H, W, 2 * Cc, x.t))
         conv = self.fuse[0]
         pam_prec = self.position_attention.precision or default_pam_precision()
-        if E.danet_cat16_ok(x.t, pam_prec == "fp16", conv.out_channels):
+        if E.danet_cat16_ok(x.t, pam_prec != "fp32", conv.out_channels):
             # cat[PAM, CAM] is read by the fuse convolution alone: both attention kernels write their result straight into its bf16 operand
             # (column blocks [0, C) and [C, 2C)); the fp32 cat tensor is never written (it only carries the shape and, in backward, the gradient)
             cat16 = torch.empty((B * H * W, 2 * Cc), dtype=torch.bfloat16, device=x.t.device)

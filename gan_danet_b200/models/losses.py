@@ -10,6 +10,9 @@ from __future__ import annotations
 import warnings
 from typing import Dict, List, Optional, Sequence, Set, Tuple
 
+import itertools
+import weakref
+
 import torch
 from torch import nn
 
@@ -177,6 +180,9 @@ def _make_vgg19_features() -> nn.Sequential:
     return nn.Sequential(*layers)
 
 
+_UIDS = itertools.count(1)
+
+
 class PerceptualLoss(nn.Module):
     """VGG-based perceptual loss with optional offline weights (reference losses.py:13-73).
 
@@ -186,6 +192,10 @@ class PerceptualLoss(nn.Module):
     def __init__(self, feature_layers: Sequence[int] = (1, 6, 11, 20), weights_path: Optional[str] = None, pretrained: bool = True,
                  device: Optional[torch.device] = None, use_gpu: Optional[bool] = None) -> None:
         super().__init__()
+        # identity of this instance in the engine's packed-weight cache: a process-wide counter, never id() (CPython reuses addresses of freed
+        # objects, and the caching allocator reuses data_ptr()s -- a later member's random VGG could hit a dead member's packed weights)
+        self._uid = next(_UIDS)
+        weakref.finalize(self, E.drop_frozen_weights, self._uid)
         self.feature_layers: Set[int] = set(feature_layers)
         if not self.feature_layers:
             raise ValueError("feature_layers must contain at least one index")
@@ -227,7 +237,7 @@ class PerceptualLoss(nn.Module):
         """(OIHW weight, cache key) of a frozen conv; a 1-channel input into conv1_1 uses the channel-summed weight
         (x.repeat(1,3,1,1) == 1-channel conv with sum_c W[:, c], SURVEY appendix A identity 5).  The engine caches the
         kernel operands (permuted fp32 or packed bf16) under the key."""
-        key = (id(self), idx, cin, conv.weight._version)
+        key = (self._uid, idx, cin, conv.weight._version)
         hit = self._wcache.get(key)
         if hit is None:
             w = conv.weight.detach()
@@ -396,6 +406,9 @@ def _relu(tape: E.Tape, x: E.Var) -> E.Var:
 class _PerceptualFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod: PerceptualLoss, x: torch.Tensor, y: torch.Tensor):
+        if ctx.needs_input_grad[2]:
+            raise L.GdnError("PerceptualLoss: the target `y` requires grad; only the first argument is differentiated here (the training loop "
+                             "passes the real field as `y`, GAN_DANet_train.ipynb:265).  Detach `y`, or swap the arguments.")
         need = ctx.needs_input_grad[1]
         dev = x.device
         lib = E._lib(x.detach())

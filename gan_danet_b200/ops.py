@@ -28,7 +28,7 @@ from torch import Tensor
 from . import _lib as L
 from . import engine as E
 
-_PRECISIONS = {"fp32": L.PREC_FP32, "fp16": L.PREC_FP16}
+_PRECISIONS = {"fp32": L.PREC_FP32, "fp16": L.PREC_FP16, "fp16x3": L.PREC_FP16X3}
 
 
 def _nhwc(t: Tensor, what: str) -> Tensor:
@@ -39,10 +39,13 @@ def _nhwc(t: Tensor, what: str) -> Tensor:
 
 def _pam_precision(precision: str, N: int, d: int, Cc: int) -> int:
     if precision not in _PRECISIONS:
-        raise L.GdnError(f"pam precision {precision!r}: expected 'fp16' (fused tcgen05 kernels) or 'fp32' (parity engine)")
+        raise L.GdnError(f"pam precision {precision!r}: expected 'fp16x3' / 'fp16' (fused tcgen05 kernels, split / single fp16 logit operands) or 'fp32' (parity engine)")
     p = _PRECISIONS[precision]
-    if p == L.PREC_FP16 and (N % 128 != 0 or d > 32 or Cc >= 192 or Cc % 4 != 0):
-        p = L.PREC_FP32          # outside the tensor-core tiling (the module path pads such grids: engine._op_pam_core_padded)
+    if p != L.PREC_FP32 and (N % 128 != 0 or d > 30 or Cc >= 191 or Cc % 4 != 0):
+        # No silent fall-back: the fp32 CUDA-core engine is ~15x slower, a cliff the caller must choose.  (The module path pads grids with
+        # N % 128 != 0 per sample and masks the padded keys: engine._op_pam_core_padded.)
+        raise L.GdnError(f"gandanet::pam_fwd/pam_bwd precision {precision!r}: shape N={N} d={d} C={Cc} is outside the fused tensor-core kernels "
+                         "(N % 128 == 0, d <= 30, C <= 188, C % 4 == 0); pad the grid to a multiple of 128 positions (PAMModule does) or pass precision='fp32'")
     return p
 
 

@@ -38,7 +38,7 @@ typedef enum {
 } gdn_status;
 
 enum { GDN_ACT_NONE = 0, GDN_ACT_RELU = 1, GDN_ACT_LRELU = 2 };
-enum { GDN_PREC_FP32 = 0, GDN_PREC_BF16 = 1, GDN_PREC_FP16 = 2, GDN_PREC_BF16X3 = 3 };
+enum { GDN_PREC_FP32 = 0, GDN_PREC_BF16 = 1, GDN_PREC_FP16 = 2, GDN_PREC_BF16X3 = 3, GDN_PREC_FP16X3 = 4 };
 
 int gdn_version(void);
 const char* gdn_last_error(void);
@@ -274,7 +274,11 @@ int gdn_maxpool2_bwd_bf16(const uint16_t* x, const float* dy, float* dx, int B, 
  * precision: GDN_PREC_FP32 = fp32 CUDA-core parity engine (reference formulation, `chunk` samples of NxN scratch at a
  *            time in `ws`; chunk 0 = auto);
  *            GDN_PREC_FP16 = fused flash-style tcgen05/TMEM kernel fed by TMA (fp16 operands, fp32 accumulate,
- *            online softmax); N must be a multiple of 128, d <= 32, C <= 192.
+ *            online softmax); N must be a multiple of 128, d <= 32, C <= 192;
+ *            GDN_PREC_FP16X3 = the same kernels with the logit operands split into fp16 hi + lo pairs
+ *            (S = q_hi k_hi^T + q_lo k_hi^T + q_hi k_lo^T, ~22 mantissa bits): the reference has no 1/sqrt(d) scale
+ *            (generator.py:115-118), its logits reach +-100 where one fp16 product is off by 0.05.  This is the mode
+ *            that meets the 1e-3 parity bar; same shape limits.
  * ws: gdn_pam_fwd_ws_bytes(a) bytes (operand packing for the tensor-core path, NxN scratch for the parity path).
  */
 typedef struct {
@@ -284,7 +288,7 @@ typedef struct {
   float* o; float* y; int y_pitch; float* lse;
   int B, N, C; int precision; int chunk;
   void* ws; size_t ws_bytes;
-  const uint16_t* v16;  /* optional (GDN_PREC_FP16 only, may be NULL): v already packed as the kernel's bf16 operand [B*N][192] -- columns [0,C) = v,
+  const uint16_t* v16;  /* optional (tensor-core precisions only, may be NULL): v already packed as the kernel's bf16 operand [B*N][192] -- columns [0,C) = v,
                            column C = 1, the rest 0 -- e.g. written by the value projection's epilogue (gdn_conv_tc_args.y16, pitch 192) into a
                            buffer whose tail columns were initialised once; the packing pass then touches q and k only */
   uint16_t* y16; int y16_pitch; /* optional (GDN_PREC_FP16 only): y written as bf16 rows of pitch y16_pitch -- a column block of the packed

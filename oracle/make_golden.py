@@ -59,7 +59,28 @@ def module_case(mod, x, r):
             "grads": {k: f32(p.grad) for k, p in mod.named_parameters() if p.grad is not None}}
 
 
+def srgand_case(M):
+    """J: SRGAND (models/discriminator.py:8-54; exported, never instantiated by the notebooks): dim 8, input [2,1,128,128] -> 2x2 before the pool."""
+    torch.manual_seed(5)
+    D = M.SRGAND(dim=8, in_channels=1)
+    D.apply(M.weights_init_normal)
+    D = D.double().train()
+    x = randn((2, 1, 128, 128), 60)
+    xg = x.double().requires_grad_(True)
+    z = D(xg)
+    (z * torch.tensor([[1.0], [-0.5]], dtype=torch.float64)).sum().backward()
+    save("srgand_dim8_128x128", {"seed": 5, "dim": 8, "x": x, "logits": f32(z), "dx": f32(xg.grad),
+                                 "grads_small": {k: f32(p.grad) for k, p in D.named_parameters() if p.numel() <= 30000},
+                                 "grad_norms": {k: float(p.grad.norm()) for k, p in D.named_parameters()},
+                                 "buffers_after": {k: f32(v) for k, v in D.state_dict().items() if "running" in k},
+                                 "keys": list(D.state_dict().keys())})
+
+
 def main():
+    if "--only-srgand" in sys.argv:
+        M, _ = ref_models()
+        srgand_case(M)
+        return
     M, gen = ref_models()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
 
@@ -211,6 +232,7 @@ def main():
         opt_G.step()
         hist.append({"loss_D": float(loss_D), "loss_G": float(loss_G), "adv": float(adv), "pixel": float(pix), "ssim": float(ss),
                      "tv": float(tv_), "perceptual": float(pe)})
+    srgand_case(M)
     save("train_2steps_8x16", {"seed": 0, "vgg_seed": 2, "epoch": epoch, "epochs": epochs, "history": hist,
                                "final_w": f32(G.final.weight), "d_fc2_w": f32(D.fc2.weight), "initial_bn_rm": f32(G.initial[1].running_mean)})
 

@@ -185,10 +185,11 @@ def _check_grads(grads, gold, tol, skip=()):
 
 
 @pytest.mark.parametrize("name,precision,tol_y,tol_g", [("pam_c160_8x16", "fp32", 1e-5, 1e-4), ("pam_c184_4x8", "fp32", 1e-5, 1e-4),
-                                                       ("pam_c160_8x16", "fp16", 2e-3, 1e-2)])
+                                                       ("pam_c160_8x16", "fp16", 2e-3, 1e-2), ("pam_c160_8x16", "fp16x3", 1e-3, 5e-3),
+                                                       ("pam_c184_4x8", "fp16x3", 1e-3, 5e-3)])
 def test_pam_module(golden, name, precision, tol_y, tol_g):
-    """PAMModule (generator.py:104-122), gamma = 0.5.  fp16 = tcgen05 flash forward (backward: fp32 engine on the saved
-    fp16-forward statistics); tolerance per SURVEY appendix C (fp16 operands: y 8.9e-4, gradients ~3e-3)."""
+    """PAMModule (generator.py:104-122), gamma = 0.5, against the reference's float64 run.  fp16 / fp16x3 = fused tcgen05 flash forward and
+    backward with single / hi+lo split fp16 logit operands (the 4x8 grid, N = 32, goes through the padded path)."""
     from gan_danet_b200.models.generator import PAMModule
     g = golden(name)
     C = g["x"].shape[1]
@@ -201,7 +202,8 @@ def test_pam_module(golden, name, precision, tol_y, tol_g):
     _check_grads(grads, g["grads"], tol_g, skip=("key.bias",))
     # d/d(key.bias) is analytically zero: compare against the weight-gradient scale (the tensor-core backward rounds dS to
     # bf16, so its column sums cancel to 2^-9 of the terms instead of fp32 epsilon)
-    assert grads["key.bias"].abs().max() < (1e-3 if precision == "fp32" else 1e-2) * grads["key.weight"].abs().max() + 1e-6
+    assert grads["key.bias"].abs().max() < (1e-3 if precision == "fp32" else 1e-2) * grads["key.weight"].abs().max() + 1e-6, \
+        (float(grads["key.bias"].abs().max()), float(grads["key.weight"].abs().max()))
 
 
 @pytest.mark.parametrize("B,C,hw", [(2, 184, (32, 32)), (1, 160, (64, 128))])
@@ -222,6 +224,8 @@ def test_pam_flash_kernel_vs_oracle(oracle, B, C, hw):
     m = m.to(DEV)
     with torch.no_grad():
         y16 = m(x.to(DEV))
+        m.precision = "fp16x3"
+        y16x3 = m(x.to(DEV))
         m.precision = "fp32"
         y32 = m(x.to(DEV))
     torch.cuda.synchronize()
@@ -230,6 +234,9 @@ def test_pam_flash_kernel_vs_oracle(oracle, B, C, hw):
     e16 = rel_err((y16.cpu().double() - x.double()) / 0.5, out_ref)
     assert e16 < 4e-3, e16                        # attention term itself (1.0-1.2e-3 at N = 8192 for fp16 operands)
     assert rel_err(y16, ref) < 2e-3
+    e16x3 = rel_err((y16x3.cpu().double() - x.double()) / 0.5, out_ref)
+    assert e16x3 < 3e-3 and e16x3 <= e16 * 1.05, (e16x3, e16)      # bf16 P and V remain (1.8e-3 at reference-scale logits)
+    assert rel_err(y16x3, ref) < 1e-3, rel_err(y16x3, ref)
 
 
 @pytest.mark.parametrize("B,C,hw", [(2, 184, (45, 22)), (1, 160, (9, 13)), (2, 176, (4, 8))])
@@ -257,16 +264,16 @@ def test_pam_padded_grid_vs_oracle(oracle, B, C, hw):
     ref = oracle.pam(xd, sd["query.weight"], sd["query.bias"], sd["key.weight"], sd["key.bias"], sd["value.weight"], sd["value.bias"], sd["gamma"])
     names = ["query.weight", "query.bias", "key.weight", "value.weight", "value.bias", "gamma"]
     want = torch.autograd.grad((ref * r.double()).sum(), [xd] + [sd[n] for n in names])
-    m.precision = "fp16"
+    m.precision = "fp16x3"
     assert E.pam_pad_to_tiles
     y, dx, grads = _fwd_bwd(m, x, r)
-    assert rel_err(y, ref) < 2e-3, rel_err(y, ref)
-    assert rel_err((y.cpu().double() - x.double()), (ref.detach() - x.double())) < 6e-3
-    # gradients: the 4x query/key weights make the attention path (bf16 P and dS operands) the dominant part of dx; measured 1.2e-2 at
-    # N = 990 and 3.0e-2 at N = 32 (few keys: no averaging).  That this is operand rounding and not the padding is shown bit-tight below.
-    assert rel_err(dx, want[0]) < 5e-2, rel_err(dx, want[0])
-    for n, w in zip(names, want[1:]):
-        assert rel_err(grads[n], w) < 5e-2, (n, rel_err(grads[n], w))
+    assert rel_err(y, ref) < 1e-3, rel_err(y, ref)
+    assert rel_err((y.cpu().double() - x.double()), (ref.detach() - x.double())) < 4e-3
+    # gradients with 4x query/key weights (logits far beyond the reference's +-100): round 1 (single fp16 logits, bf16 gradient operands) measured
+    # 1.2e-2 at N = 990 and 3.0e-2 at N = 32 and asserted 5e-2; split logits + fp16 gradient operands: asserted 5e-3 / 1e-2 (N = 32: no averaging over keys)
+    tol = 5e-3 if hw[0] * hw[1] >= 128 else 1e-2
+    errs = {"dx": rel_err(dx, want[0]), **{n: rel_err(grads[n], w) for n, w in zip(names, want[1:])}}
+    assert max(errs.values()) < tol, errs
     H, W = hw
     d = C // 8
     xx = torch.randn(B, H, W, C, generator=gen).to(DEV)
@@ -274,7 +281,7 @@ def test_pam_padded_grid_vs_oracle(oracle, B, C, hw):
     k = (2.0 * torch.randn(B, H, W, d, generator=gen)).to(DEV)
     gamma = torch.full((1,), 0.5, device=DEV)
     t = E.Tape(record=False)
-    yc = E.op_pam_core(t, E.Var(xx), E.Var(q), E.Var(k), E.Var(torch.full((B, H, W, C), 0.75, device=DEV)), E.Var(gamma), precision=PREC_FP16).t
+    yc = E.op_pam_core(t, E.Var(xx), E.Var(q), E.Var(k), E.Var(torch.full((B, H, W, C), 0.75, device=DEV)), E.Var(gamma), precision=E.PREC_FP16X3).t
     assert float((yc - (xx + 0.5 * 0.75)).abs().max()) < 2e-3
 
 
@@ -397,12 +404,13 @@ def test_danet_outputs_written_as_fuse_operand():
     assert not bad, bad
 
 
-def test_pam_padding_is_exact():
+@pytest.mark.parametrize("prec_name", ["fp16x3", "fp16"])
+def test_pam_padding_is_exact(prec_name):
     """The same aligned problem (N = 256) through the kernels directly and through the padded path forced to 512 rows: the
     padded keys get softmax weight 0 (2^-125 on the polynomial lanes) and the padded queries a zero cotangent, so forward and
     all gradients agree to float32 summation-order level -- far below the fp16/bf16 operand rounding."""
     from gan_danet_b200 import engine as E
-    from gan_danet_b200._lib import PREC_FP16
+    prec = E.PAM_PRECISION_NAMES[prec_name]
     B, H, W, C, d = 2, 16, 16, 184, 23
     gen = torch.Generator().manual_seed(11)
     x, v, dy = (torch.randn(B, H, W, C, generator=gen).to(DEV) for _ in range(3))
@@ -413,7 +421,7 @@ def test_pam_padding_is_exact():
         tape = E.Tape()
         vs = [E.Var(t) for t in (x, q, k, v)]
         gv = E.Var(gamma)
-        y = E._op_pam_core_padded(tape, *vs, gv, None, pad_to=512) if padded else E.op_pam_core(tape, *vs, gv, precision=PREC_FP16)
+        y = E._op_pam_core_padded(tape, *vs, gv, None, pad_to=512, precision=prec) if padded else E.op_pam_core(tape, *vs, gv, precision=prec)
         y.g = dy.clone()
         tape.backward()
         torch.cuda.synchronize()
@@ -489,13 +497,15 @@ def _make_generator(seed, gamma, precision):
     return G.train()
 
 
-@pytest.mark.parametrize("conv,precision,tol_y,tol_g", [("fp32", "fp32", 1e-4, 2e-3), ("bf16x3", "fp32", 1e-3, 1e-2), ("fp32", "fp16", 1e-3, 5e-2)])
+@pytest.mark.parametrize("conv,precision,tol_y,tol_g", [("fp32", "fp32", 1e-4, 2e-3), ("bf16x3", "fp32", 1e-3, 1e-2), ("fp32", "fp16", 1e-3, 5e-2),
+                                                        ("fp32", "fp16x3", 1e-3, 4e-2), ("bf16x3", "fp16x3", 1e-3, 4e-2)])
 def test_generator(golden, conv, precision, tol_y, tol_g):
     """FlexibleUpsamplingModule (generator.py:175-247) at C_in 46, grid 8x16, gamma 0.05: output, input gradient,
     per-tensor gradient norms, small gradient tensors and BN running statistics against the reference's float64 run.
     Measured (tools/measure_precision.py, B200): fp32 engine y 8e-7 / dx 4e-6; bf16x3 tensor-core convs y 1.9e-5 / dx 3.9e-3;
-    fp16-operand PAM y 8.5e-5 / dx 3.7e-2 (logits reach +-100 at the reference init: fp16 logits perturb the near-one-hot
-    softmax rows; the hi/lo-split QK^T mode is the planned fix)."""
+    fp16-operand PAM (round 1: single fp16 logits, bf16 gradient operands) y 8.5e-5 / dx 3.7e-2; 'fp16x3' (hi+lo split logits, fp16 gradient
+    operands): see profiles/r02_precision_modes.json.  Why a 1e-4 output difference is a 1e-2 gradient difference in this network (ReLU sign
+    flips: gradient error ~ sqrt(output error)) is measured on the CPU by tools/precision_bisect.py and asserted in tests/test_gpu_quantised.py."""
     from gan_danet_b200 import engine as E
     g = golden("generator_cin46_8x16")
     G = _make_generator(g["seed"], g["gamma"], precision)
@@ -565,7 +575,7 @@ def test_discriminator(golden):
         assert rel_err(dict(D.named_parameters())[k].grad, v) < 2e-3, k
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("fp16", 1e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("fp16", 1e-2), ("fp16x3", 1e-2)])
 def test_train_two_steps(golden, precision, tol):
     """Two full G+D steps (GAN_DANet_train.ipynb:225-269) against the reference modules + torch.optim.AdamW in float64.
     north_star bar: losses within 1 %."""
@@ -708,3 +718,35 @@ def test_resample_vector_paths(B, H, W, C):
     ref.backward(r2.double().permute(0, 3, 1, 2))
     assert torch.equal(mp.t.permute(0, 3, 1, 2).double(), ref.detach())
     assert rel_err(xv.g.permute(0, 3, 1, 2), xd.grad) < 1e-7
+
+
+def test_srgand(golden):
+    """SRGAND (models/discriminator.py:8-54): 4x4 stride-2 convolutions, BatchNorm + LeakyReLU(0.2), residual add, global average pool, Linear --
+    forward logits, input gradient, parameter gradients and BN running statistics against the reference's float64 run (fp32 engine: the 4x4
+    kernels are outside the tensor-core tiling).  This is the discriminator with the BatchNorm + LeakyReLU epilogue the north star names."""
+    import gan_danet_b200 as P
+    g = golden("srgand_dim8_128x128")
+    torch.manual_seed(g["seed"])
+    D = P.SRGAND(dim=g["dim"], in_channels=1)
+    D.apply(P.weights_init_normal)
+    assert list(D.state_dict().keys()) == g["keys"]
+    D = D.to(DEV).train()
+    x = g["x"].to(DEV).requires_grad_(True)
+    z = D(x)
+    z.backward(torch.tensor([[1.0], [-0.5]], device=DEV))
+    torch.cuda.synchronize()
+    assert rel_err(z, g["logits"]) < 1e-4, rel_err(z, g["logits"])
+    assert rel_err(x.grad, g["dx"]) < 2e-3, rel_err(x.grad, g["dx"])
+    params = dict(D.named_parameters())
+    bad = [(k, float(params[k].grad.double().norm()), n) for k, n in g["grad_norms"].items()
+           if abs(float(params[k].grad.double().norm()) - n) > 5e-3 * max(n, 1e-7) and not k.endswith(".bias")]
+    assert not bad, bad[:5]
+    # conv biases in front of a train-mode BatchNorm have an analytically zero gradient (the batch mean removes them): noise in the reference too
+    for k, v in g["grads_small"].items():
+        if k.startswith("conv") and k.endswith(".bias") and k not in ("conv1.bias",):
+            assert float(params[k].grad.abs().max()) < 1e-3 * max(float(params[k.replace(".bias", ".weight")].grad.abs().max()), 1e-12), k
+        else:
+            assert rel_err(params[k].grad, v) < 5e-3, (k, rel_err(params[k].grad, v))
+    sd = D.state_dict()
+    for k, v in g["buffers_after"].items():
+        assert rel_err(sd[k], v) < 1e-4, (k, rel_err(sd[k], v))

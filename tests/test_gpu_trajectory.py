@@ -78,7 +78,7 @@ def test_teacher_forced_trajectory_200_steps(oracle):
     vgg_sd = {k: v.clone() for k, v in P.PerceptualLoss(pretrained=False, device=torch.device("cpu")).vgg.state_dict().items()}
     st = oracle.TrainState({k: v.clone() for k, v in G0.state_dict().items()}, {k: v.clone() for k, v in D0.state_dict().items()}, vgg_sd)
 
-    modes = {"fp32": ("fp32", "fp32", 1e-2, 2e-3), "bf16": ("bf16", "fp16", 1e-2, 5e-3)}     # conv precision, PAM precision, loss tol, parameter tol
+    modes = {"fp32": ("fp32", "fp32", 1e-2, 2e-3), "bf16": ("bf16", "fp16x3", 1e-2, 5e-3)}     # conv precision, PAM precision, loss tol, parameter tol
     trainers = {}
     for name, (conv, pam, _, _) in modes.items():
         import copy

@@ -324,3 +324,52 @@ def test_post_resize(golden, oracle):
         ho, wo = case["out"].shape[-2:]
         got = oracle.resample2d(x, (ho, wo), "bicubic", scale=float(case["scale"]))
         assert rel_err(got, case["out"]) < 1e-12, case["scale"]
+
+
+def test_quantised_oracle_reduces_to_the_reference(golden):
+    """oracle/quantised_oracle.py with every rounding point switched off IS the reference generator (float64 golden, 1e-7); with the product
+    mode's rounding points on, its distance to the reference is the cost of bf16 operands (~1e-2 on the output), and the gradient
+    error follows the sqrt law of a ReLU network (dx ~ sqrt(y error))."""
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import quantised_oracle as Q
+    import precision_bisect as PB
+    g = golden("generator_cin46_8x16")
+    exact = PB.summarise(g, *PB.run(g, Q.Formats.exact()))
+    assert max(exact.values()) < 1e-7, exact
+    prod = PB.summarise(g, *PB.run(g, Q.Formats()))
+    assert 2e-3 < prod["y"] < 2e-2, prod
+    assert prod["dx"] < 6.0 * prod["y"] ** 0.5, prod
+    gonly = PB.summarise(g, *PB.run(g, Q.Formats(None, None, "bf16", None, None, None, None)))
+    assert gonly["y"] < 1e-7 and gonly["dx"] < 1e-2, gonly          # rounding only the gradient operands never touches the forward
+
+
+def test_notebook_loop_restatement_reproduces_the_golden_trajectory(golden):
+    """oracle/notebook_step.py (the notebook's loop GAN_DANet_train.ipynb:182-194,225-269 over a module namespace) driven with the reference's own
+    modules in float64 must reproduce the two-step golden trajectory that oracle/make_golden.py recorded from its own inline copy of the loop."""
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import notebook_step as NS
+    ref_root = next((r for r in (os.path.join(ROOT, "oracle", "_ref"), "/root/reference") if os.path.isdir(os.path.join(r, "models"))), None)
+    if ref_root is None:
+        pytest.skip("the reference's modules are neither under oracle/_ref nor /root/reference")
+    from gan_danet_b200.synthetic import make_batch
+    g = golden("train_2steps_8x16")
+    M = NS.load_reference_models(ref_root)
+    lr05, real, aux = make_batch(0, 2, 8, 16)
+    torch.manual_seed(g["seed"])
+    G = M.FlexibleUpsamplingModule(46)
+    D = M.Discriminator1()
+    NS.init_like_the_authors(M, G, D, real)
+    torch.manual_seed(g["vgg_seed"])
+    perc = M.PerceptualLoss(pretrained=False, device=torch.device("cpu"))
+    G, D = G.double().train(), D.double().train()
+    perc.vgg.double()
+    tr = NS.NotebookTrainer(M, G, D, epochs=g["epochs"], device="cpu", perceptual=perc)
+    tr.ssim_loss = tr.ssim_loss.double()
+    for step in range(2):
+        out = tr.step(lr05.double(), real.double(), aux.double(), epoch=g["epoch"])
+        for k, v in g["history"][step].items():
+            assert abs(out[k] - v) <= 1e-9 * max(abs(v), 1e-3), (step, k, out[k], v)
+    assert rel_err(G.final.weight, g["final_w"]) < 1e-6

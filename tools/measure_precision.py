@@ -9,7 +9,7 @@ from gan_danet_b200.models.generator import CAMModule, PAMModule
 
 g = torch.load(os.path.join(ROOT, "tests", "golden", "generator_cin46_8x16.pt"), weights_only=False)
 for conv in ("fp32", "bf16x3", "bf16"):
-    for pam in ("fp32", "fp16"):
+    for pam in ("fp32", "fp16", "fp16x3"):
         E.set_conv_precision(conv)
         torch.manual_seed(g["seed"])
         G = P.FlexibleUpsamplingModule(46); G.apply(P.weights_init_normal)
