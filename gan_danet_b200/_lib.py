@@ -127,6 +127,7 @@ SIGNATURES = {
     "gdn_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_bilinear_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_bicubic_down_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "gdn_bicubic_down_nchw_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_maxpool2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_maxpool2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_maxpool2_fwd_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -156,6 +157,8 @@ SIGNATURES = {
     "gdn_ssim": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "gdn_adamw": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "gdn_adamw_multi": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "gdn_adamw_dyn": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, _f, _vp]),
+    "gdn_adamw_multi_dyn": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _vp]),
     "gdn_fill": (_i, [_vp, _ll, _f, _vp]),
     "gdn_destandardise": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _f, _f, _vp]),
     "gdn_masked_spatial_mean_ws_bytes": (_sz, [_ll, _ll]),

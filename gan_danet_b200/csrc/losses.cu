@@ -171,9 +171,15 @@ __global__ void __launch_bounds__(ST_W* ST_H) ssim_kernel(const float* __restric
 }
 
 // ---- AdamW (decoupled weight decay), torch.optim.AdamW single-tensor formula
-struct AdamP { float lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, grad_scale; };
+// dyn != nullptr: lr, step_size (= lr / (1 - beta1^step)) and bc2_sqrt (= sqrt(1 - beta2^step)) are read from that device array instead of the
+// by-value fields -- the step-dependent scalars of a CUDA-graph-captured optimiser step (the graph bakes kernel arguments, not device memory)
+struct AdamP { float lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, grad_scale; const float* dyn; };
+__device__ __forceinline__ void adam_dyn(AdamP& a) {
+  if (a.dyn) { a.lr = __ldg(a.dyn); a.step_size = __ldg(a.dyn + 1); a.bc2_sqrt = __ldg(a.dyn + 2); }
+}
 template <int VEC>
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, AdamP a) {
+  adam_dyn(a);
   const long long nv = n / VEC;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
     float pv[VEC], gv[VEC], mv[VEC], vv[VEC];
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 constexpr int kAdamMulti = 64;
 struct AdamMultiP { float* p[kAdamMulti]; const float* g[kAdamMulti]; float* m[kAdamMulti]; float* v[kAdamMulti]; int n[kAdamMulti]; };
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const __grid_constant__ AdamMultiP t, AdamP a) {
+  adam_dyn(a);
   const int k = blockIdx.y;
   float* __restrict__ p = t.p[k]; const float* __restrict__ g = t.g[k]; float* __restrict__ m = t.m[k]; float* __restrict__ v = t.v[k];
   const int n = t.n[k];
@@ -322,11 +329,12 @@ extern "C" int gdn_ssim(const float* a, const float* b, int B, int H, int W, flo
   return GDN_OK;
 }
 
-extern "C" int gdn_adamw_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, float lr, float beta1,
-                               float beta2, float eps, float wd, int step, float grad_scale, gdn_stream_t s) {
-  GDN_CHECK_ARG(count > 0 && p && g && m && v && n && step >= 1);
+static int adamw_multi_impl(int count, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, float lr, float beta1,
+                            float beta2, float eps, float wd, int step, float grad_scale, const float* dyn, gdn_stream_t s) {
+  GDN_CHECK_ARG(count > 0 && p && g && m && v && n && (step >= 1 || dyn));
   AdamP a;
-  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = wd; a.grad_scale = grad_scale;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = wd; a.grad_scale = grad_scale; a.dyn = dyn;
+  if (step < 1) step = 1;
   double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   a.step_size = (float)((double)lr / bc1);
   a.bc2_sqrt = (float)sqrt(bc2);
@@ -349,11 +357,22 @@ extern "C" int gdn_adamw_multi(int count, float* const* p, const float* const* g
   return GDN_OK;
 }
 
-extern "C" int gdn_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd,
-                         int step, float grad_scale, gdn_stream_t s) {
-  GDN_CHECK_ARG(p && g && m && v && n > 0 && step >= 1);
+extern "C" int gdn_adamw_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, float lr, float beta1,
+                               float beta2, float eps, float wd, int step, float grad_scale, gdn_stream_t s) {
+  return adamw_multi_impl(count, p, g, m, v, n, lr, beta1, beta2, eps, wd, step, grad_scale, nullptr, s);
+}
+extern "C" int gdn_adamw_multi_dyn(int count, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, const float* dyn,
+                                   float beta1, float beta2, float eps, float wd, float grad_scale, gdn_stream_t s) {
+  GDN_CHECK_ARG(dyn != nullptr);
+  return adamw_multi_impl(count, p, g, m, v, n, 0.f, beta1, beta2, eps, wd, 0, grad_scale, dyn, s);
+}
+
+static int adamw_impl(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd,
+                      int step, float grad_scale, const float* dyn, gdn_stream_t s) {
+  GDN_CHECK_ARG(p && g && m && v && n > 0 && (step >= 1 || dyn));
   AdamP a;
-  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = wd; a.grad_scale = grad_scale;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = wd; a.grad_scale = grad_scale; a.dyn = dyn;
+  if (step < 1) step = 1;
   double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   a.step_size = (float)((double)lr / bc1);
   a.bc2_sqrt = (float)sqrt(bc2);
@@ -369,4 +388,14 @@ extern "C" int gdn_adamw(float* p, const float* g, float* m, float* v, long long
   }
   GDN_CHECK_LAUNCH();
   return GDN_OK;
+}
+
+extern "C" int gdn_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, float wd,
+                         int step, float grad_scale, gdn_stream_t s) {
+  return adamw_impl(p, g, m, v, n, lr, beta1, beta2, eps, wd, step, grad_scale, nullptr, s);
+}
+extern "C" int gdn_adamw_dyn(float* p, const float* g, float* m, float* v, long long n, const float* dyn, float beta1, float beta2, float eps, float wd,
+                             float grad_scale, gdn_stream_t s) {
+  GDN_CHECK_ARG(dyn != nullptr);
+  return adamw_impl(p, g, m, v, n, 0.f, beta1, beta2, eps, wd, 0, grad_scale, dyn, s);
 }

@@ -322,7 +322,10 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------ bicubic 1/f down-sampling, NCHW -> NHWC slice
-__global__ void __launch_bounds__(256) bicubic_down_kernel(const float* __restrict__ x, float* __restrict__ y, int y_pitch, int B, int C, int Hi, int Wi,
+__device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__global__ void __launch_bounds__(256) bicubic_down_kernel(const T* __restrict__ x, float* __restrict__ y, int y_pitch, int B, int C, int Hi, int Wi,
                                                             int Ho, int Wo, float ratio) {
   const long long total = (long long)B * C * Ho * Wo;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -331,14 +334,14 @@ __global__ void __launch_bounds__(256) bicubic_down_kernel(const float* __restri
     int y0, x0; float ty, tx, wy[4], wx[4];
     cubic_src(oy, ratio, y0, ty); cubic_src(ox, ratio, x0, tx);
     cubic_coeffs(ty, wy); cubic_coeffs(tx, wx);
-    const float* plane = x + ((size_t)b * C + c) * Hi * Wi;
+    const T* plane = x + ((size_t)b * C + c) * Hi * Wi;
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int iy = clampi(y0 - 1 + i, 0, Hi - 1);
       float rowacc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) rowacc = fmaf(wx[j], __ldg(plane + (size_t)iy * Wi + clampi(x0 - 1 + j, 0, Wi - 1)), rowacc);
+      for (int j = 0; j < 4; ++j) rowacc = fmaf(wx[j], ld_as_float(plane + (size_t)iy * Wi + clampi(x0 - 1 + j, 0, Wi - 1)), rowacc);
       acc = fmaf(wy[i], rowacc, acc);
     }
     y[(((size_t)b * Ho + oy) * Wo + ox) * y_pitch + c] = acc;
@@ -568,7 +571,16 @@ extern "C" int gdn_bicubic_down_nchw_to_nhwc(const float* x, float* y, int y_pit
   GDN_CHECK_ARG(x && y && B > 0 && C > 0 && Hi > 0 && Wi > 0 && (f == 2 || f == 4) && y_pitch >= y_c0 + C);
   int Ho = Hi / f, Wo = Wi / f;   // floor(in * 1/f)
   GDN_CHECK_ARG(Ho > 0 && Wo > 0);
-  bicubic_down_kernel<<<grid_for((long long)B * C * Ho * Wo), 256, 0, as_stream(s)>>>(x, y + y_c0, y_pitch, B, C, Hi, Wi, Ho, Wo, (float)f);
+  bicubic_down_kernel<float><<<grid_for((long long)B * C * Ho * Wo), 256, 0, as_stream(s)>>>(x, y + y_c0, y_pitch, B, C, Hi, Wi, Ho, Wo, (float)f);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_bicubic_down_nchw_to_nhwc_bf16(const uint16_t* x, float* y, int y_pitch, int y_c0, int B, int C, int Hi, int Wi, int f, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && y && B > 0 && C > 0 && Hi > 0 && Wi > 0 && (f == 2 || f == 4) && y_pitch >= y_c0 + C);
+  int Ho = Hi / f, Wo = Wi / f;
+  GDN_CHECK_ARG(Ho > 0 && Wo > 0);
+  bicubic_down_kernel<__nv_bfloat16><<<grid_for((long long)B * C * Ho * Wo), 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), y + y_c0, y_pitch, B, C, Hi, Wi,
+                                                                                                    Ho, Wo, (float)f);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

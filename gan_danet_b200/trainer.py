@@ -31,19 +31,65 @@ from .models.losses import BCEWithLogitsLoss, MSELoss
 
 class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW semantics (decoupled weight decay, bias correction, eps outside the sqrt) with one fused
-    sm_100a kernel per parameter tensor (``gdn_adamw``).  ``grad_scale`` folds the 1/world of data parallelism."""
+    sm_100a kernel per parameter tensor (``gdn_adamw``).  ``grad_scale`` folds the 1/world of data parallelism.
+
+    ``capturable = True`` (set by ``GraphedTrainStep``): ``step()`` neither counts steps nor passes step-dependent scalars by value -- the
+    kernels read lr, lr / (1 - beta1^t) and sqrt(1 - beta2^t) from a 3-float device array per parameter group, which ``advance()`` refreshes
+    (one tiny host -> device copy on the current stream) before every replay of the captured step.  The arithmetic is bit-identical to the eager
+    path: the three scalars are computed in double precision and rounded to float32 in both."""
 
     def __init__(self, params, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = 1.0
+        self.capturable = False
+        self._t = 0                     # steps taken (capturable mode: one common counter, as every parameter steps every iteration)
+        self._dyn: List[torch.Tensor] = []
+        self._dyn_host: List[torch.Tensor] = []
 
     SMALL = 1 << 20
+
+    def _ensure_state(self) -> None:
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+
+    def make_capturable(self) -> None:
+        """Switch to device-resident step scalars (call after at least one eager step, before the capture)."""
+        self._ensure_state()
+        steps = {int(self.state[p]["step"]) for g in self.param_groups for p in g["params"]}
+        assert len(steps) == 1, "capturable FusedAdamW needs all parameters at the same step"
+        self._t = steps.pop()
+        dev = self.param_groups[0]["params"][0].device
+        self._dyn = [torch.zeros(4, dtype=torch.float32, device=dev) for _ in self.param_groups]
+        self._dyn_host = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in self.param_groups]
+        self.capturable = True
+
+    def advance(self) -> None:
+        """Capturable mode: count one step and upload its scalars (outside the graph, on the current stream, before the replay)."""
+        assert self.capturable
+        self._t += 1
+        for group, dyn, host in zip(self.param_groups, self._dyn, self._dyn_host):
+            # gdn_adamw receives lr and the betas as C floats and widens them to double for the bias corrections: mirror that exactly
+            # (float32-rounded inputs, double arithmetic, float32-rounded results) so that the captured step is bit-identical to the eager one
+            f32 = lambda v: float(torch.tensor(float(v), dtype=torch.float32))   # noqa: E731
+            b1, b2 = (f32(b) for b in group["betas"])
+            lr = f32(group["lr"])
+            host[0] = lr
+            host[1] = lr / (1.0 - math.pow(b1, float(self._t)))
+            host[2] = math.sqrt(1.0 - math.pow(b2, float(self._t)))
+            dyn.copy_(host, non_blocking=True)
+            for p in group["params"]:
+                self.state[p]["step"] = self._t
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         import ctypes as C
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
             small = {}          # step -> list of (p, g, m, v, n): tensors below SMALL share one launch per 64 (gdn_adamw_multi)
             for p in group["params"]:
@@ -51,24 +97,37 @@ class FusedAdamW(torch.optim.Optimizer):
                     continue
                 st = self.state[p]
                 if not st:
+                    assert not self.capturable
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["step"] += 1
+                if not self.capturable:
+                    st["step"] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 assert p.is_contiguous()
                 if p.numel() < self.SMALL:
-                    small.setdefault(int(st["step"]), []).append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), p, g))
+                    small.setdefault(0 if self.capturable else int(st["step"]), []).append(
+                        (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), p, g))
                     continue
-                L.check(E._lib(p).gdn_adamw(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
-                                            float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                                            int(st["step"]), float(self.grad_scale), E._stream()), "gdn_adamw")
+                if self.capturable:
+                    L.check(E._lib(p).gdn_adamw_dyn(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), self._dyn[gi].data_ptr(),
+                                                    float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), float(self.grad_scale), E._stream()),
+                            "gdn_adamw_dyn")
+                else:
+                    L.check(E._lib(p).gdn_adamw(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                                                float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                                                int(st["step"]), float(self.grad_scale), E._stream()), "gdn_adamw")
             for step_no, items in small.items():
                 k = len(items)
                 arr = lambda j: (C.c_void_p * k)(*[it[j] for it in items])  # noqa: E731
                 ns = (C.c_longlong * k)(*[it[4] for it in items])
-                L.check(E._lib(items[0][5]).gdn_adamw_multi(k, arr(0), arr(1), arr(2), arr(3), ns, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                                                            float(group["weight_decay"]), step_no, float(self.grad_scale), E._stream()), "gdn_adamw_multi")
+                if self.capturable:
+                    L.check(E._lib(items[0][5]).gdn_adamw_multi_dyn(k, arr(0), arr(1), arr(2), arr(3), ns, self._dyn[gi].data_ptr(), float(b1), float(b2),
+                                                                    float(group["eps"]), float(group["weight_decay"]), float(self.grad_scale), E._stream()),
+                            "gdn_adamw_multi_dyn")
+                else:
+                    L.check(E._lib(items[0][5]).gdn_adamw_multi(k, arr(0), arr(1), arr(2), arr(3), ns, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                                                float(group["weight_decay"]), step_no, float(self.grad_scale), E._stream()), "gdn_adamw_multi")
         return loss
 
 
@@ -152,7 +211,10 @@ def prepare_input_nhwc(lr_grace_05: torch.Tensor, hr_aux: torch.Tensor) -> torch
     x = torch.empty((B, h, w, 1 + Ca), dtype=torch.float32, device=hr_aux.device)
     a, g = hr_aux.contiguous(), lr_grace_05.contiguous()
     L.check(lib.gdn_bicubic_down_nchw_to_nhwc(g.data_ptr(), x.data_ptr(), 1 + Ca, 0, B, 1, H2, W2, 2, E._stream()), "bicubic_down(grace)")
-    L.check(lib.gdn_bicubic_down_nchw_to_nhwc(a.data_ptr(), x.data_ptr(), 1 + Ca, 1, B, Ca, H4, W4, 4, E._stream()), "bicubic_down(aux)")
+    if a.dtype == torch.bfloat16:       # the aux stack transported as bf16 (half the host -> device bytes); taps widened to fp32 on the device
+        L.check(lib.gdn_bicubic_down_nchw_to_nhwc_bf16(a.data_ptr(), x.data_ptr(), 1 + Ca, 1, B, Ca, H4, W4, 4, E._stream()), "bicubic_down(aux, bf16)")
+    else:
+        L.check(lib.gdn_bicubic_down_nchw_to_nhwc(a.data_ptr(), x.data_ptr(), 1 + Ca, 1, B, Ca, H4, W4, 4, E._stream()), "bicubic_down(aux)")
     return x
 
 
@@ -194,6 +256,7 @@ class GANTrainer:
         self.allreduce = allreduce
         if allreduce is not None and fused_adamw:
             self.opt_G.grad_scale = 1.0 / allreduce.world
+        self._w_dev: Optional[torch.Tensor] = None       # [w, 1 - w] on the device: set by GraphedTrainStep (the captured step must not bake epoch / epochs)
 
     def _make_opt(self, params, lr):
         cls = FusedAdamW if self.fused_adamw else torch.optim.AdamW
@@ -270,8 +333,11 @@ class GANTrainer:
             for p in d_params:
                 p.requires_grad_(True)
         loss_adv = self.bce(fake_out, torch.ones_like(fake_out))
-        w = self.epoch / self.epochs
-        loss_G = (1 - w) * loss_pix + w * loss_adv + loss_tv
+        if self._w_dev is not None:
+            loss_G = self._w_dev[1] * loss_pix + self._w_dev[0] * loss_adv + loss_tv
+        else:
+            w = self.epoch / self.epochs
+            loss_G = (1 - w) * loss_pix + w * loss_adv + loss_tv
         if loss_perc is not None:
             loss_G = loss_G + loss_perc
         loss_G.backward()
@@ -284,6 +350,65 @@ class GANTrainer:
             out["perceptual"] = loss_perc.detach()
         out["hr"] = hr.detach()
         return out
+
+
+class GraphedTrainStep:
+    """``GANTrainer.train_step`` captured in ONE CUDA graph (input preparation, G forward, D step, G step with all loss terms, both backward passes,
+    both AdamW updates, BatchNorm running statistics): ~800 kernel launches replayed by a single ``cudaGraphLaunch`` instead of ~48 ms of host-side
+    enqueue per step.  What changes between iterations lives in device memory, not in kernel arguments:
+
+    * the batch: three static input buffers (``__call__`` copies the caller's device tensors into them);
+    * AdamW's step-dependent scalars and the learning rate: ``FusedAdamW.advance()`` (3 floats per parameter group);
+    * the adversarial weight ``w = epoch / epochs`` (GAN_DANet_train.ipynb:266): a 2-float device tensor refreshed when the epoch changes.
+
+    Losses are bit-identical to the eager step (same kernels, same order, same scalars: tests/test_gpu_graph.py).  Data parallel: the NCCL
+    all-reduces are captured with the step.  Everything the captured step allocates lives in the graph's private memory pool."""
+
+    def __init__(self, trainer: "GANTrainer", lr_grace_05: torch.Tensor, lr_grace_025: torch.Tensor, hr_aux: torch.Tensor, warmup: int = 2):
+        if not trainer.fused_adamw:
+            raise L.GdnError("GraphedTrainStep needs the fused AdamW (torch.optim.AdamW's step counter is not capturable here)")
+        self.tr = trainer
+        dev = lr_grace_025.device
+        self.static_in = [torch.empty_like(t) for t in (lr_grace_05, lr_grace_025, hr_aux)]
+        for dst, src in zip(self.static_in, (lr_grace_05, lr_grace_025, hr_aux)):
+            dst.copy_(src)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):            # real training steps: optimizer state, lazy fc1, persistent operand buffers now exist
+                trainer.train_step(*self.static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        trainer.opt_G.make_capturable()
+        trainer.opt_D.make_capturable()
+        self._w_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        trainer._w_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._epoch = None
+        self._refresh_scalars()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count
+        with torch.cuda.graph(self.graph):
+            self.static_out = trainer.train_step(*self.static_in)
+        self.launches_per_step = L.launch_count - n0       # C-ABI calls recorded into the graph (each one or more kernels)
+
+    def _refresh_scalars(self) -> None:
+        tr = self.tr
+        if self._epoch != tr.epoch:
+            w = tr.epoch / tr.epochs
+            self._w_host[0], self._w_host[1] = w, 1 - w        # float32(1 - w) computed in double, as the eager expression (1 - w) * loss does
+            tr._w_dev.copy_(self._w_host, non_blocking=True)
+            self._epoch = tr.epoch
+
+    def __call__(self, lr_grace_05: torch.Tensor, lr_grace_025: torch.Tensor, hr_aux: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """One training iteration.  Returns the step's losses / generated field as STATIC device tensors (overwritten by the next call)."""
+        for dst, src in zip(self.static_in, (lr_grace_05, lr_grace_025, hr_aux)):
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._refresh_scalars()
+        self.tr.opt_D.advance()
+        self.tr.opt_G.advance()
+        self.graph.replay()
+        return self.static_out
 
 
 def init_like_reference(G: FlexibleUpsamplingModule, D: Discriminator1, sample_real: torch.Tensor, seed: Optional[int] = None) -> None:

@@ -259,6 +259,9 @@ int gdn_bilinear_fwd(const float* x, float* y, int B, int Hi, int Wi, int Ho, in
 int gdn_bilinear_bwd(const float* dy, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s);
 /* F.interpolate(scale_factor=1/f, mode='bicubic') for f = 2 or 4 (GAN_DANet_train.ipynb:226,231): NCHW in -> NHWC slice out */
 int gdn_bicubic_down_nchw_to_nhwc(const float* x, float* y, int y_pitch, int y_c0, int B, int C, int Hi, int Wi, int f, gdn_stream_t s);
+/* the same with the input field held as bf16 (the aux stack of GAN_DANet_train.ipynb:227 transported host -> device at 2 bytes per value: 24 -> 12 MB per
+ * sample); taps are widened to fp32, the interpolation accumulates in fp32 */
+int gdn_bicubic_down_nchw_to_nhwc_bf16(const uint16_t* x, float* y, int y_pitch, int y_c0, int B, int C, int Hi, int Wi, int f, gdn_stream_t s);
 /* 2x2/2 max pool (VGG19 features idx 4,9,18; losses.py:58) */
 int gdn_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, gdn_stream_t s);
 int gdn_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s);
@@ -366,6 +369,13 @@ int gdn_adamw(float* p, const float* g, float* m, float* v, long long n, float l
  * step: one launch per 64 tensors instead of one per tensor (the generator's ~100 small parameter tensors) */
 int gdn_adamw_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, float lr, float beta1,
                     float beta2, float eps, float wd, int step, float grad_scale, gdn_stream_t s);
+/* The same two updates with the STEP-DEPENDENT scalars read from device memory: dyn[0] = lr, dyn[1] = lr / (1 - beta1^step), dyn[2] = sqrt(1 - beta2^step)
+ * (computed by the caller in double precision, exactly as gdn_adamw does from `step`).  A CUDA graph that captured the optimiser step bakes kernel
+ * arguments but not device memory: the caller refreshes the three floats before each replay (GAN_DANet_train.ipynb:256,269 once per iteration). */
+int gdn_adamw_dyn(float* p, const float* g, float* m, float* v, long long n, const float* dyn, float beta1, float beta2, float eps, float wd,
+                  float grad_scale, gdn_stream_t s);
+int gdn_adamw_multi_dyn(int count, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, const float* dyn,
+                        float beta1, float beta2, float eps, float wd, float grad_scale, gdn_stream_t s);
 int gdn_fill(float* p, long long n, float value, gdn_stream_t s);
 
 /* ------------------------------------------- deep-ensemble statistics and inference post-processing (f1, f3) */

@@ -54,7 +54,7 @@ def _oracle_run(qoracle, G, x, r, fmt, dtype=torch.float64):
     pnames = [k for k, _ in G.named_parameters()]
     sd = {k: (v.detach().to(dtype).cpu() if v.is_floating_point() else v.detach().cpu()) for k, v in G.state_dict().items()}
     sdp = {k: (v.clone().requires_grad_(True) if k in pnames else v) for k, v in sd.items()}
-    xd = x.to(dtype).requires_grad_(True)
+    xd = x.detach().clone().to(dtype).requires_grad_(True)        # clone: .to() of a tensor already in `dtype` would alias the golden fixture
     bufs = {}
     y = qoracle.generator_forward(sdp, xd, fmt, training=True, buffers_out=bufs)
     grads = torch.autograd.grad((y * r.to(dtype)).sum(), [xd] + [sdp[k] for k in pnames], allow_unused=True)
