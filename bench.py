@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--conv-precision", default="bf16", choices=["fp32", "bf16", "bf16x3"],
                     help="convolutions: bf16 = tcgen05 tensor cores (BASELINE config dtype), bf16x3 = hi+lo split on tensor cores, fp32 = CUDA-core parity engine")
     ap.add_argument("--no-perceptual", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="time the eager step instead of the CUDA-graph replay of it")
+    ap.add_argument("--aux-dtype", default="auto", choices=["auto", "bf16", "fp32"], help="host/transport format of the aux stack (auto: bf16 with bf16 convolutions)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-other-mode", action="store_true", help="do not also time the other fused-PAM logit mode (extra key other_pam_mode)")
     ap.add_argument("--kernel-detail", action="store_true", help="print a per-shape table of the tensor-core launches to stderr")
@@ -217,8 +219,13 @@ def run_ours(args):
     if world > 1:
         for p in list(G.parameters()) + list(D.parameters()):
             dist.broadcast(p.data, 0)
-    tr = GANTrainer(G, D, perc, epochs=150, allreduce=GradientAllReduce() if world > 1 else None)
+    tr = GANTrainer(G, D, perc, epochs=150, allreduce=GradientAllReduce(own_group=args.graph) if world > 1 else None)
     tr.epoch = 3
+    # The aux stack (45 x 4h x 4w per sample, 97 % of a batch's bytes) is held and transported as bf16 when the convolutions round their operands
+    # to bf16 anyway; the device-side bicubic down-sampling widens the taps to fp32 (trainer.prepare_input_nhwc).  --aux-dtype fp32 sends float32.
+    aux_dtype = {"auto": "bf16" if args.conv_precision == "bf16" else "fp32"}.get(args.aux_dtype, args.aux_dtype)
+    if aux_dtype == "bf16":
+        aux_h = aux_h.to(torch.bfloat16)
     pinned = [t.pin_memory() for t in (lr05_h, real_h, aux_h)]
     resident = [t.to(dev) for t in pinned]
 
@@ -232,19 +239,42 @@ def run_ours(args):
         tr.train_step(*resident)
     sync_all()
 
-    # ---- timed: inputs resident in HBM
+    # ---- eager pass with a CUDA-event bracket around every tensor-core C-ABI call: the per-kernel-family numbers (roofline, kernels)
+    n_prof = max(3, min(args.steps, 5)) if args.graph else args.steps
     clocks = ClockSampler(local)
     E.kernel_timing = {}
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(n_prof):
         out = tr.train_step(*resident)
     e1.record()
     sync_all()
-    launches = _lib.launch_count - launches0
-    ms = e0.elapsed_time(e1)
+    launches_eager = (_lib.launch_count - launches0) / n_prof
+    ms_eager = e0.elapsed_time(e1) / n_prof
     timing, E.kernel_timing = E.kernel_timing, None
+    prof_steps = n_prof
+
+    # ---- the step as ONE CUDA graph (trainer.GraphedTrainStep): the timed region replays it
+    step_fn, graph_info = tr.train_step, None
+    if args.graph:
+        from gan_danet_b200.trainer import GraphedTrainStep
+        gstep = GraphedTrainStep(tr, *resident, warmup=1)
+        step_fn = gstep
+        graph_info = {"captured": True, "c_abi_calls_per_step": gstep.launches_per_step}
+        for _ in range(2):
+            step_fn(*resident)
+        sync_all()
+
+    # ---- timed: inputs resident in HBM
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step_fn(*resident)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = int(round((graph_info["c_abi_calls_per_step"] if graph_info else launches_eager) * args.steps))
     clk = clocks.stop()
 
     # ---- timed: end to end through the trainer API with host buffers
@@ -254,8 +284,7 @@ def run_ours(args):
     pipe = HostBatchPipeline(dev)
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # The two losses of EVERY step are read back device -> host inside the timed region: a non-blocking copy into pinned memory, consumed with
-    # a one-step lag (step i-1's values are awaited after step i has been enqueued), as a training loop that logs its losses does.  A blocking
-    # read per step would drain the launch queue at every step boundary and starve the GPU during the launch-dense generator forward.
+    # a one-step lag (step i-1's values are awaited after step i has been enqueued), as a training loop that logs its losses does.
     host_losses = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
     read_done = [torch.cuda.Event() for _ in range(2)]
     history = []
@@ -265,7 +294,7 @@ def run_ours(args):
         dev_in = pipe.next()
         if i + 1 < args.steps:
             pipe.submit(pinned)                                      # step i+1's inputs travel while step i computes
-        out = tr.train_step(*dev_in)
+        out = step_fn(*dev_in)                                       # graph mode: + one device-to-device copy into the static input buffers
         host_losses[i % 2].copy_(torch.stack([out["loss_D"], out["loss_G"]]), non_blocking=True)    # device -> host read of the step's result
         read_done[i % 2].record()
         if i > 0:
@@ -297,8 +326,8 @@ def run_ours(args):
     for fam, evs in timing.items():
         tot_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
         fl = sum(e[2] for e in evs)
-        fams[fam] = {"launches": len(evs), "ms_per_step": tot_ms / args.steps, "tflops": fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else None,
-                     "share_of_step": tot_ms / ms}
+        fams[fam] = {"launches": len(evs), "ms_per_step": tot_ms / prof_steps, "tflops": fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else None,
+                     "share_of_step": tot_ms / (ms_eager * prof_steps)}
     notes = {"conv_tc_fwd_kernel": "tcgen05 implicit-GEMM convolution, forward + data gradient (all layers of G, D, VGG19)",
              "conv_tc_wgrad_kernel": "tcgen05 weight gradient (MN-major operands) incl. its split-K reduction",
              "pam_flash_fwd_kernel": "fused tcgen05 PAM forward incl. operand packing (Q, K fp16; P, V bf16)",
@@ -320,7 +349,7 @@ def run_ours(args):
         return {"kernel": fam + " (" + notes.get(fam, "") + ")", "bound": "tensor", "achieved": f["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": f["tflops"] / peak_tf, "traffic": traffic.get(fam), "traffic_unit": "bytes of DRAM traffic per launch (ncu, family mean)",
                 "peak_source": peak_src, "launches": f["launches"],
-                "mean_launch_ms": f["ms_per_step"] * args.steps / f["launches"], "share_of_step": f["share_of_step"]}
+                "mean_launch_ms": f["ms_per_step"] * prof_steps / f["launches"], "share_of_step": f["share_of_step"]}
 
     if args.kernel_detail and rank == 0:
         import collections
@@ -330,13 +359,13 @@ def run_ours(args):
                 d = det[(fam, e[3])]
                 d[0] += 1; d[1] += e[0].elapsed_time(e[1]); d[2] += e[2]
         for (fam, name), (n, t, f) in sorted(det.items(), key=lambda kv: -kv[1][1]):
-            print(f"[detail] {t / args.steps:8.3f} ms/step {n // args.steps:3d}x {f / (t * 1e-3) / 1e12:7.1f} TF/s  {fam} {name}", file=sys.stderr)
+            print(f"[detail] {t / prof_steps:8.3f} ms/step {n // prof_steps:3d}x {f / (t * 1e-3) / 1e12:7.1f} TF/s  {fam} {name}", file=sys.stderr)
     # ---- north-star roofline: fused PAM forward + backward together (BASELINE.json metric "PAM attention TFLOP/s vs peak")
     def roof_pam():
         f, b = fams.get("pam_flash_fwd_kernel"), fams.get("pam_flash_bwd_kernel")
         if not f or not b:
             return None
-        ms_tot = (f["ms_per_step"] + b["ms_per_step"]) * args.steps
+        ms_tot = (f["ms_per_step"] + b["ms_per_step"]) * prof_steps
         fl_tot = sum(e[2] for fam in ("pam_flash_fwd_kernel", "pam_flash_bwd_kernel") for e in timing[fam])
         ach = fl_tot / (ms_tot * 1e-3) / 1e12
         burst = peaks.get("bf16_tflops") if peaks else None
@@ -347,7 +376,8 @@ def run_ours(args):
                 "frac_of_burst_peak": (ach / burst) if burst else None, "burst_peak": burst,
                 "forward_tflops": f["tflops"], "backward_tflops": b["tflops"], "forward_frac": f["tflops"] / peak_tf, "backward_frac": b["tflops"] / peak_tf,
                 "traffic": (tr_f + tr_b) if (tr_f and tr_b) else None, "traffic_unit": "bytes of DRAM traffic per forward + backward call (ncu, r01 pass)",
-                "algorithmic_flops_per_step": fl_tot / args.steps, "ms_per_step": ms_tot / args.steps, "share_of_step": ms_tot / ms,
+                "algorithmic_flops_per_step": fl_tot / prof_steps, "ms_per_step": ms_tot / prof_steps, "share_of_step": ms_tot / (ms_eager * prof_steps),
+                "timed_in": f"{prof_steps} eager steps of the same trainer (CUDA events around each C-ABI call; the graph replay cannot be bracketed per kernel)",
                 "launches": f["launches"] + b["launches"]}
 
     tc_fams = [f for f in fams if f in notes]
@@ -357,7 +387,7 @@ def run_ours(args):
     # ---- the other fused-PAM logit mode as an extra key (same weights, same inputs, a few steps): fp16x3 is the parity-grade default,
     # fp16 (single fp16 logit operands) the faster one
     other = None
-    if args.pam_precision in ("fp16x3", "fp16") and world == 1 and not args.skip_other_mode:
+    if args.pam_precision in ("fp16x3", "fp16") and world == 1 and not args.skip_other_mode and not args.graph:
         alt = "fp16" if args.pam_precision == "fp16x3" else "fp16x3"
         G.set_pam_precision(alt)
         for _ in range(2):
@@ -383,7 +413,8 @@ def run_ours(args):
                 "data": "synthetic (seeded smooth random fields, random-init weights, random-init VGG19)",
                 "config": {"workload": workload_name(args, h, w), "global_batch": world * B, "parallelism": f"dp{world}", "conv": args.conv_precision,
                            "pam": f"fused tcgen05 flash forward + backward ({args.pam_precision})" if args.pam_precision != "fp32" else "fp32 engine",
-                           "l2": "inputs larger than L2 (the aux stack alone is %.0f MB per step)" % (aux_h.numel() * 4 / 1e6)},
+                           "cuda_graph": graph_info, "eager_ms_per_step": ms_eager, "aux_transport": aux_dtype,
+                           "l2": "inputs larger than L2 (the aux stack alone is %.0f MB per step)" % (aux_h.numel() * aux_h.element_size() / 1e6)},
                 "clocks": clk, "gpu_launches": launches,
                 "e2e": {"value": value_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(last.numel() * 4),
                         "ms_per_step": ms_e2e / args.steps,
@@ -399,6 +430,12 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if args.graph:
+            # the communicator whose collectives live in the captured graph is not torn down collectively (an eager operation on it after the
+            # capture does not complete on this stack: tools/probe_nccl_graph.py); every rank has printed / reduced what it had to
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

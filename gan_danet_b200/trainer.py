@@ -137,8 +137,14 @@ class GradientAllReduce:
     Tensors above ``big`` elements are reduced in place one by one (D's fc1 gradient is ~1 GB and is its own bucket);
     the rest are packed into one flat bucket per call.  The 1/world factor is applied by the optimizer (``grad_scale``)."""
 
-    def __init__(self, group=None, big: int = 1 << 20):
+    def __init__(self, group=None, big: int = 1 << 20, own_group: bool = False):
+        """``own_group``: create a process group (a communicator of its own) for the gradient reductions.  Needed when the step is captured in a CUDA
+        graph: on this stack an EAGER collective issued on a communicator after collectives of that communicator were captured never completes
+        (tools/probe_nccl_graph.py), so the captured reductions get a communicator nobody else uses -- barriers, broadcasts and the bench's timing
+        reductions stay on the default group.  Collective call: every rank must construct the object."""
         import torch.distributed as dist
+        if own_group and group is None and dist.is_initialized() and dist.get_world_size() > 1:
+            group = dist.new_group()
         self.dist, self.group, self.big = dist, group, big
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
@@ -387,7 +393,8 @@ class GraphedTrainStep:
         self._refresh_scalars()
         self.graph = torch.cuda.CUDAGraph()
         n0 = L.launch_count
-        with torch.cuda.graph(self.graph):
+        # thread_local: ProcessGroupNCCL's watchdog thread may query events while this thread captures (data parallel)
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if trainer.allreduce is not None else "global"):
             self.static_out = trainer.train_step(*self.static_in)
         self.launches_per_step = L.launch_count - n0       # C-ABI calls recorded into the graph (each one or more kernels)
 
