@@ -165,6 +165,8 @@ SIGNATURES = {
     "gdn_masked_spatial_mean": (_i, [_vp, _vp, _ll, _ll, _f, _f, _vp, _vp, _sz, _vp]),
     "gdn_ensemble_stats": (_i, [_vp, _ll, _i, _ll, _f, _f, _vp, _vp, _vp]),
     "gdn_hist_match": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "gdn_sort_rows_ws_bytes": (_sz, [_i, _i]),
+    "gdn_sort_rows": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp]),
     "gdn_bicubic_resize": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _f, _f, _vp]),
     "gdn_blend_region": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
 }

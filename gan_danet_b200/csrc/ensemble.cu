@@ -162,6 +162,67 @@ __global__ void __launch_bounds__(256) ensemble_stats_kernel(const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------ row-wise sort (np.sort / np.unique of test.ipynb:117-121)
+// Ascending sort of every row of [rows][n] (NaNs last, like np.sort), one CTA per row: bitonic network on order-preserving 32-bit keys.  Stages whose
+// compare distance fits a shared-memory chunk (8192 keys) run in shared memory, the log2(np / 8192) largest distances of each merge run on the row's
+// L2-resident key buffer in `ws`.  Fixed network => bitwise reproducible; replaces the two library sorts that were 4.4 of the 6 ms of histogram matching.
+constexpr int SORT_CH = 8192;
+__device__ __forceinline__ unsigned sort_key(float f) {
+  if (f != f) return 0xFFFFFFFEu;                                   // every NaN after every number (padding is 0xFFFFFFFF)
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float sort_unkey(unsigned k) {
+  if (k >= 0xFFFFFFFEu) return __int_as_float(0x7fc00000);
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+__device__ __forceinline__ void cmp_swap(unsigned& a, unsigned& b, bool ascending) {
+  if ((a > b) == ascending) { const unsigned t = a; a = b; b = t; }
+}
+__global__ void __launch_bounds__(1024, 2) sort_rows_kernel(const float* __restrict__ x, float* __restrict__ out, unsigned* __restrict__ ws, int n, int np) {
+  __shared__ unsigned sk[SORT_CH];
+  const int tid = threadIdx.x;
+  unsigned* g = ws + (size_t)blockIdx.x * np;
+  const float* xr = x + (size_t)blockIdx.x * n;
+  for (int i = tid; i < np; i += 1024) g[i] = i < n ? sort_key(xr[i]) : 0xFFFFFFFFu;
+  __syncthreads();
+  const int ch = np < SORT_CH ? np : SORT_CH;
+  // all merge sizes k <= ch, chunk by chunk in shared memory; then for every larger k: the distances >= ch in global memory, the rest per chunk
+  for (int k0 = 2; k0 <= np; k0 = (k0 < ch ? ch : k0) << 1) {
+    const int kfirst = k0 <= ch ? 2 : k0, klast = k0 <= ch ? ch : k0;      // first round: k = 2 .. ch inside the chunks
+    if (k0 > ch) {
+      for (int j = k0 >> 1; j >= ch; j >>= 1) {
+        for (int t = tid; t < (np >> 1); t += 1024) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          unsigned a = g[i], b = g[i | j];
+          cmp_swap(a, b, (i & k0) == 0);
+          g[i] = a; g[i | j] = b;
+        }
+        __syncthreads();
+      }
+    }
+    for (int c0 = 0; c0 < np; c0 += ch) {
+      for (int i = tid; i < ch; i += 1024) sk[i] = g[c0 + i];
+      __syncthreads();
+      for (int k = kfirst; k <= klast; k <<= 1) {
+        for (int j = (k > ch ? ch : k) >> 1; j >= 1; j >>= 1) {
+          for (int t = tid; t < (ch >> 1); t += 1024) {
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            unsigned a = sk[i], b = sk[i | j];
+            cmp_swap(a, b, ((c0 + i) & k) == 0);
+            sk[i] = a; sk[i | j] = b;
+          }
+          __syncthreads();
+        }
+      }
+      for (int i = tid; i < ch; i += 1024) g[c0 + i] = sk[i];
+      __syncthreads();
+    }
+  }
+  float* o = out + (size_t)blockIdx.x * n;
+  for (int i = tid; i < n; i += 1024) o[i] = sort_unkey(g[i]);
+}
+
 // ------------------------------------------------------------------------------------------------ histogram matching
 // number of elements <= v / < v in an ascending array
 __device__ __forceinline__ int upper_bound(const float* __restrict__ a, int n, float v) {
@@ -327,6 +388,16 @@ extern "C" int gdn_ensemble_stats(const float* preds, long long member_stride, i
     else if (M <= 16) ensemble_stats_kernel<16, 1><<<grid, 256, 0, st>>>(preds, member_stride, M, n, scale, shift, mean, stdev);
     else ensemble_stats_kernel<0, 1><<<grid, 256, 0, st>>>(preds, member_stride, M, n, scale, shift, mean, stdev);
   }
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+extern "C" size_t gdn_sort_rows_ws_bytes(int rows, int n) { return (size_t)rows * (size_t)next_pow2(n > 1 ? n : 2) * sizeof(unsigned); }
+extern "C" int gdn_sort_rows(const float* x, float* out, int rows, int n, void* ws, size_t ws_bytes, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && out && rows > 0 && n > 0 && n <= (1 << 26));
+  if (!ws || ws_bytes < gdn_sort_rows_ws_bytes(rows, n)) { set_error("gdn_sort_rows: workspace too small"); return GDN_EWORKSPACE; }
+  sort_rows_kernel<<<rows, 1024, 0, as_stream(s)>>>(x, out, reinterpret_cast<unsigned*>(ws), n, next_pow2(n > 1 ? n : 2));
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

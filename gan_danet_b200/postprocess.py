@@ -72,6 +72,17 @@ def ensemble_stats(preds: torch.Tensor, scale: float = 1.0, shift: float = 0.0, 
     return mean, std
 
 
+def sort_rows(x: torch.Tensor) -> torch.Tensor:
+    """Ascending sort of every row of a [rows, n] float32 tensor (NaNs last, as np.sort): ``gdn_sort_rows``, one CTA per row."""
+    x = _f32(x, "sort_rows")
+    rows, n = x.shape
+    lib = E._lib(x)
+    out = torch.empty_like(x)
+    ws = E.workspace("sort", lib.gdn_sort_rows_ws_bytes(rows, n), x.device)
+    L.check(lib.gdn_sort_rows(x.data_ptr(), out.data_ptr(), rows, n, ws.data_ptr(), ws.numel(), E._stream()), "gdn_sort_rows")
+    return out
+
+
 def hist_match(source: torch.Tensor, reference: torch.Tensor, weight: float = 0.2) -> torch.Tensor:
     """``apply_mild_histogram_matching`` (test.ipynb:115-131): per sample (leading axis) the source values are moved a
     fraction ``weight`` of the way to the reference distribution; ``weight = 1`` is ``simple_histogram_matching``."""
@@ -81,8 +92,7 @@ def hist_match(source: torch.Tensor, reference: torch.Tensor, weight: float = 0.
     if ref.shape[0] != B:
         raise L.GdnError("hist_match: source and reference need the same number of samples")
     s2, r2 = src.reshape(B, -1), ref.reshape(B, -1)
-    s_sorted = torch.sort(s2, dim=1).values.contiguous()
-    r_sorted = torch.sort(r2, dim=1).values.contiguous()
+    s_sorted, r_sorted = sort_rows(s2), sort_rows(r2)
     out = torch.empty_like(s2)
     L.check(E._lib(src).gdn_hist_match(s2.data_ptr(), s_sorted.data_ptr(), r_sorted.data_ptr(), out.data_ptr(), B, s2.shape[1], r2.shape[1], float(weight),
                                        E._stream()), "gdn_hist_match")

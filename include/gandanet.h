@@ -396,6 +396,10 @@ int gdn_ensemble_stats(const float* preds, long long member_stride, int M, long 
 /* mild_histogram_matching (test.ipynb:115-125; weight 1 = simple_histogram_matching :104-113) per sample: src [B][ns],
  * src_sorted / ref_sorted = ascending copies of the sample's source and reference values ([B][ns], [B][nt]),
  * out = (1-weight)*src + weight*np.interp(cdf_src(src), cdf_ref, ref_values), CDF arithmetic in float64 as numpy's. */
+/* ascending sort of every row of [rows][n] (NaNs last): the np.sort / np.unique step of simple_histogram_matching (test.ipynb:117-121).
+ * ws: gdn_sort_rows_ws_bytes(rows, n) bytes.  out may not alias x. */
+size_t gdn_sort_rows_ws_bytes(int rows, int n);
+int gdn_sort_rows(const float* x, float* out, int rows, int n, void* ws, size_t ws_bytes, gdn_stream_t s);
 int gdn_hist_match(const float* src, const float* src_sorted, const float* ref_sorted, float* out, int B, int ns, int nt, float weight, gdn_stream_t s);
 /* F.interpolate(scale_factor=(scale_h, scale_w), mode='bicubic', align_corners=False) on [rows][Hi][Wi] planes
  * (test.ipynb:553 x1.25, :559 x4); Ho = floor(Hi*scale_h), Wo = floor(Wi*scale_w) are passed by the caller. */

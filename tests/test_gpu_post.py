@@ -221,3 +221,21 @@ def test_train_ensemble_small(tmp_path):
     models = ens.load_ensemble_models(P.FlexibleUpsamplingModule, torch.device(DEV), 46, "danet")
     assert len(models) == 2 and not models[0].training
     assert not torch.equal(models[0].state_dict()["final.weight"], models[1].state_dict()["final.weight"])
+
+
+@pytest.mark.parametrize("rows,n", [(3, 1), (2, 5), (4, 1000), (5, 8192), (3, 15840), (2, 131072), (181, 20000)])
+def test_sort_rows(rows, n):
+    """gdn_sort_rows (the np.sort / np.unique step of test.ipynb:117-121, own bitonic kernel) against torch.sort: bitwise equal values, NaNs last."""
+    from gan_danet_b200 import postprocess as PP
+    g = torch.Generator().manual_seed(rows * 7 + n)
+    x = torch.randn(rows, n, generator=g)
+    x[0, 0] = float("nan")
+    if n > 4:
+        x[-1, 1] = float("nan"); x[0, 2] = -0.0; x[0, 3] = 0.0; x[-1, 4] = float("inf"); x[0, n // 2] = -float("inf")
+        x[-1, : n // 3] = x[-1, n // 3]          # a long run of equal values
+    x = x.to(DEV)
+    got = PP.sort_rows(x)
+    want = torch.sort(x, dim=1).values
+    torch.cuda.synchronize()
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.equal(torch.nan_to_num(got, nan=0.0), torch.nan_to_num(want, nan=0.0))      # -0.0 == 0.0 compare equal, as in np.sort's output order

@@ -78,7 +78,10 @@ def test_teacher_forced_trajectory_200_steps(oracle):
     vgg_sd = {k: v.clone() for k, v in P.PerceptualLoss(pretrained=False, device=torch.device("cpu")).vgg.state_dict().items()}
     st = oracle.TrainState({k: v.clone() for k, v in G0.state_dict().items()}, {k: v.clone() for k, v in D0.state_dict().items()}, vgg_sd)
 
-    modes = {"fp32": ("fp32", "fp32", 1e-2, 2e-3), "bf16": ("bf16", "fp16x3", 1e-2, 5e-3)}     # conv precision, PAM precision, loss tol, parameter tol
+    # conv precision, PAM precision, loss tol, parameter tol.  'bf16x3' = the tensor-core PARITY mode (hi+lo split conv operands + fused PAM with split
+    # logits): 1 % at EVERY step, like the fp32 engine.  'bf16' = the benchmarked mode: its generated field is 1e-2 away from the reference's
+    # (bf16 operands), which reaches D's logits -- 1 % on >= 95 % of the steps, 2 % everywhere (measured: 3 of 400 loss values above 1 %, worst 1.2 %)
+    modes = {"fp32": ("fp32", "fp32", 1e-2, 2e-3), "bf16x3": ("bf16x3", "fp16x3", 1e-2, 2e-3), "bf16": ("bf16", "fp16x3", 1e-2, 5e-3)}
     trainers = {}
     for name, (conv, pam, _, _) in modes.items():
         import copy
@@ -118,7 +121,7 @@ def test_teacher_forced_trajectory_200_steps(oracle):
                     dev = abs(float(out[k]) - ref[k]) / max(abs(ref[k]), 1e-3)
                     rec[k] = dev
                     worst[name][k] = max(worst[name][k], dev)
-                    if dev > (tol_l if name == "fp32" else 2 * tol_l):
+                    if dev > (2 * tol_l if name == "bf16" else tol_l):
                         failures.append((name, i, k, float(out[k]), ref[k]))
                 pe, ue = 0.0, 0.0
                 for mod, ref_sd, b4, names in ((tr.G, st.g, before["g"], WATCH_G), (tr.D, st.d, before["d"], WATCH_D)):
@@ -136,7 +139,7 @@ def test_teacher_forced_trajectory_200_steps(oracle):
         E.set_conv_precision(old)
         out_dir = os.path.join(ROOT, "gpurun_out")
         if os.path.isdir(out_dir):
-            with open(os.path.join(out_dir, "r01_trajectory_teacher_forced.json"), "w") as f:
+            with open(os.path.join(out_dir, "r02_trajectory_teacher_forced.json"), "w") as f:
                 json.dump({"steps": len(log["fp32"]), "worst": worst, "final_ref": ref if STEPS else None, "log": log}, f)
     print("teacher-forced worst deviations:", json.dumps(worst))
     assert not failures, failures[:8]

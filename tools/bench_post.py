@@ -48,7 +48,7 @@ cases = {
     "masked_spatial_mean": (lambda: PP.masked_spatial_mean(x, keep), 4 * n),
     "ensemble_stats(M=8, mean+std)": (lambda: PP.ensemble_stats(members), (4 * M + 8) * n),
     "hist_match kernel (sorted copies given)": (lambda: L.check(lib.gdn_hist_match(x.data_ptr(), s_sorted.data_ptr(), r_sorted.data_ptr(), out.data_ptr(), T, H * W, H * W, 0.2, E._stream())), 8 * n),
-    "hist_match incl. both torch.sort": (lambda: PP.hist_match(x, ref, 0.2), 8 * n),
+    "hist_match incl. both row sorts (gdn_sort_rows)": (lambda: PP.hist_match(x, ref, 0.2), 8 * n),
     "bicubic_resize x4 (64x128 -> 256x512)": (lambda: PP.bicubic_resize(small, 4), 4 * n + 4 * n // 16),
     "blend_region (in place)": (lambda: PP.smooth_blend(xb, ref, (8, H - 8, 8, W - 8)), 12 * n),
 }
