@@ -539,7 +539,15 @@ struct BwdSmem {
 enum { B_OUT = 0, B_INFULL = 1, B_INEMPTY = B_INFULL + ST, B_XFULL = B_INEMPTY + ST, B_YFULL = B_XFULL + 2, B_DSFULL = B_YFULL + 2, B_ACC = B_DSFULL + 2,
        B_OCT = B_ACC + 1, B_COUNT = B_OCT + 1 };
 static_assert(B_COUNT * 8 <= 256, "barrier area");
+// TMEM columns.  MODE 0 (dQ):    X0 X1 [0,128)  Y0 Y1 [128,256)  dQ [256,288)  dy_i (A operand of Y, loop invariant) [288,384)  Q_i hi|lo [384,416)
+//               MODE 1 (dK,dV): X0 X1 [0,128)  Y0 Y1 [128,256)  dK [256,288)  dV [288,480)                                     K_j hi|lo [480,512)
+// The loop-invariant outer operands live in TMEM (copied once per CTA by the softmax warps): an A operand in shared memory is re-read by every
+// MMA of every inner block (4 KB per K = 16 step), and the dK/dV launch is bound by the shared-memory pipe (ncu round 1: 57 % tensor-core operand
+// reads + 39 % LSU).  MODE 1 has no room for V_j (96 columns) next to two Y buffers: tried with ONE Y buffer in round 2 -- correct, but the
+// serialisation Y_{t+1} after dS_t cost more (2.76 -> 3.44 ms per backward) than the operand reads it saved.
 constexpr uint32_t COL_X = 0, COL_Y = 128, COL_SMALL = 256, COL_BIG = 288;
+template <int MODE> struct BwdCols { static constexpr uint32_t QK = MODE == 0 ? 384 : 480; };
+
 
 // kind::f16 instruction descriptor for bf16 operands (see conv_tc.cu): b_mn = 1 makes B MN-major
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn) {
@@ -566,11 +574,13 @@ struct Params {
   int B, N, C, d;
 };
 
+
 template <int MODE, int SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_constant__ CUtensorMap mapKh, const __grid_constant__ CUtensorMap mapV,
                      const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapQt, const __grid_constant__ CUtensorMap mapKt, const Params p) {
   using SM = BwdSmem<SPLIT>;
+  constexpr uint32_t COL_QK = BwdCols<MODE>::QK;          // outer logit operand (hi | lo chunks, 16 columns each)
   constexpr int OQK_BYTES = SM::OQK_BYTES, IQK_BYTES = SM::IQK_BYTES, OFF_OQK = SM::OFF_OQK, OFF_OC = SM::OFF_OC, OFF_IN = SM::OFF_IN, IN_IQK = SM::IN_IQK,
                 IN_IT = SM::IN_IT, IN_IC = SM::IN_IC, IN_BYTES = SM::IN_BYTES, OFF_BARS = SM::OFF_BARS, OFF_TSLOT = SM::OFF_TSLOT;
   extern __shared__ uint8_t smem_raw[];
@@ -640,26 +650,36 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     const uint64_t d64 = smem_desc(base, 512, LAYOUT_SW64), d128 = smem_desc(base, 1024, LAYOUT_SW128);
     const uint64_t dmn = smem_desc_lbo(base, IC_CHUNK, 1024, LAYOUT_SW128);     // MN-major: 64-channel groups 8 KB apart, 8-row groups 1 KB apart
     const uint64_t oqk_d = d64 + (OFF_OQK >> 4), oc_d = d128 + (OFF_OC >> 4);
-    auto issue_xy = [&](int t, int s, uint32_t ph) {
-      const int b = t & 1;
-      mbar_wait_spin(bar(B_INFULL + s), ph);
+    auto issue_x = [&](int t) {
+      const int b = t & 1, s = t % ST;
+      mbar_wait_spin(bar(B_INFULL + s), (uint32_t)(t / ST) & 1u);
       // X[b] / Y[b] hold P_{t-2} / dS_{t-2} until the accumulating products of block t-2 have read them; those were issued before
       // this call (same thread, same pipe: issue order), after the softmax group's DSFULL hand-over -- no separate "free" barriers
       tc_fence_after();
       const uint32_t st_off = (uint32_t)(OFF_IN + s * IN_BYTES) >> 4;
-      const uint64_t iqk_d = d64 + st_off + (IN_IQK >> 4), ic_d = d128 + st_off + (IN_IC >> 4);
+      const uint64_t iqk_d = d64 + st_off + (IN_IQK >> 4);
+      const uint32_t xd = tmem + COL_X + b * TI, ahi = tmem + COL_QK, alo = tmem + COL_QK + 16;     // A = outer logit operand from TMEM: K = 16 per 8 columns
       if (elect_one()) {
         if (SPLIT) {      // same order of terms as the forward kernel
-          umma_f16_i<0>(tmem + COL_X + b * TI, oqk_d + (OQK_CHUNK >> 4), iqk_d, ID_X);                 // o_lo i_hi^T
-          umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d + (OQK_CHUNK >> 4) + 2, iqk_d + 2, ID_X);
-          umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d, iqk_d + (IQK_CHUNK >> 4), ID_X);                 // o_hi i_lo^T
-          umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d + 2, iqk_d + (IQK_CHUNK >> 4) + 2, ID_X);
-          umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d, iqk_d, ID_X);                                    // o_hi i_hi^T (carries -lse)
+          umma_f16_ts_i<0>(xd, alo, iqk_d, ID_X);                                    // o_lo i_hi^T
+          umma_f16_ts_i<1>(xd, alo + 8, iqk_d + 2, ID_X);
+          umma_f16_ts_i<1>(xd, ahi, iqk_d + (IQK_CHUNK >> 4), ID_X);                 // o_hi i_lo^T
+          umma_f16_ts_i<1>(xd, ahi + 8, iqk_d + (IQK_CHUNK >> 4) + 2, ID_X);
+          umma_f16_ts_i<1>(xd, ahi, iqk_d, ID_X);                                    // o_hi i_hi^T (carries -lse)
         } else {
-          umma_f16_i<0>(tmem + COL_X + b * TI, oqk_d, iqk_d, ID_X);
+          umma_f16_ts_i<0>(xd, ahi, iqk_d, ID_X);
         }
-        umma_f16_i<1>(tmem + COL_X + b * TI, oqk_d + 2, iqk_d + 2, ID_X);
+        umma_f16_ts_i<1>(xd, ahi + 8, iqk_d + 2, ID_X);
         tc_commit(bar(B_XFULL + b));
+      }
+      __syncwarp();
+    };
+    auto issue_y = [&](int t) {
+      const int b = t & 1, s = t % ST;
+      const uint32_t ycol = tmem + COL_Y + b * TI;
+      const uint32_t st_off = (uint32_t)(OFF_IN + s * IN_BYTES) >> 4;          // (INFULL of this block has been awaited by issue_x)
+      const uint64_t ic_d = d128 + st_off + (IN_IC >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
 #pragma unroll
@@ -667,23 +687,17 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
             const uint64_t ad = oc_d + (uint64_t)(c * (OC_CHUNK >> 4) + ks * 2), bd = ic_d + (uint64_t)(c * (IC_CHUNK >> 4) + ks * 2);
             if (MODE == 0) {      // A = dy_i from TMEM (copied there once per CTA): 16 channels = 8 columns per step
               const uint32_t at = tmem + COL_BIG + (c * 4 + ks) * 8;
-              if (c == 0 && ks == 0) umma_f16_ts_i<0>(tmem + COL_Y + b * TI, at, bd, ID_Y); else umma_f16_ts_i<1>(tmem + COL_Y + b * TI, at, bd, ID_Y);
+              if (c == 0 && ks == 0) umma_f16_ts_i<0>(ycol, at, bd, ID_Y); else umma_f16_ts_i<1>(ycol, at, bd, ID_Y);
             } else {
-              if (c == 0 && ks == 0) umma_f16_i<0>(tmem + COL_Y + b * TI, ad, bd, ID_Y); else umma_f16_i<1>(tmem + COL_Y + b * TI, ad, bd, ID_Y);
+              if (c == 0 && ks == 0) umma_f16_i<0>(ycol, ad, bd, ID_Y); else umma_f16_i<1>(ycol, ad, bd, ID_Y);
             }
           }
         tc_commit(bar(B_YFULL + b));
       }
       __syncwarp();
     };
-    mbar_wait_spin(bar(B_OUT), 0);
-    if (MODE == 0) mbar_wait_spin(bar(B_OCT), 0);           // dy_i has been copied into TMEM by the softmax warps
-    issue_xy(0, 0, 0);
-    int s = 0, s1 = 1 % ST; uint32_t ph1 = (1 / ST) & 1;       // (stage, phase) of block t and of block t+1
-    for (int t = 0; t < T; ++t) {
-      if (t + 1 < T) issue_xy(t + 1, s1, ph1);
-      if (++s1 == ST) { s1 = 0; ph1 ^= 1; }
-      const int b = t & 1;
+    auto issue_acc = [&](int t) {
+      const int b = t & 1, s = t % ST;
       mbar_wait_spin(bar(B_DSFULL + b), (t >> 1) & 1);
       tc_fence_after();
       const uint32_t st_off = (uint32_t)(OFF_IN + s * IN_BYTES) >> 4;
@@ -708,7 +722,14 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
         tc_commit(bar(B_INEMPTY + s));
       }
       __syncwarp();
-      if (++s == ST) s = 0;
+    };
+    mbar_wait_spin(bar(B_OUT), 0);
+    mbar_wait_spin(bar(B_OCT), 0);           // the loop-invariant outer operands have been copied into TMEM by the softmax warps
+    // two X and two Y buffers: block t+1's logits and dP are formed while the softmax groups work on block t
+    issue_x(0); issue_y(0);
+    for (int t = 0; t < T; ++t) {
+      if (t + 1 < T) { issue_x(t + 1); issue_y(t + 1); }
+      issue_acc(t);
     }
     if (elect_one()) tc_commit(bar(B_ACC));
     __syncwarp();
@@ -717,21 +738,47 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;                  // TMEM lane = outer row
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    if (MODE == 0) {
-      // dy_i (outer tile, loop invariant, A operand of Y = dy_i V_j^T) goes to TMEM once: with A in shared memory every one of the
-      // 12 MMAs of a block re-reads its 4 KB A slice (49 instead of 33 cycles each, and the shared-memory pipe is the kernel's bound).
-      // Thread = row; warp group w copies 16-byte pieces 4w..4w+3 of each 128-byte swizzled row chunk: 8 bf16 = 4 TMEM columns per piece.
+    {
       mbar_wait(bar(B_OUT), 0);
+      // The outer logit operand (Q_i in MODE 0, K_j in MODE 1; hi and lo chunks) goes to TMEM once: the A operand of every X MMA.  Thread = row; a
+      // 64-byte SWIZZLE_64B row holds four 16-byte pieces, piece p at physical position p ^ ((row >> 1) & 3); 8 halves = 4 TMEM columns per piece.
+      // SPLIT: warp group 0 copies the hi chunk (columns [0,16)), group 1 the lo chunk ([16,32)); else each group copies two pieces of the one chunk.
+      {
+        const uint8_t* src = sm + OFF_OQK + (SPLIT ? wg * OQK_CHUNK : 0) + (row >> 3) * 512 + (row & 7) * 64;
+        const int sw = (row >> 1) & 3;
+        if (SPLIT) {
+          uint32_t v[16];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const uint8_t* src = sm + OFF_OC + c * OC_CHUNK + (row >> 3) * 1024 + (row & 7) * 128;
-        uint32_t v[16];
+          for (int j = 0; j < 4; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(src + ((j ^ sw) << 4));
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+          }
+          tmem_st16_u(tmem + lane_addr + COL_QK + wg * 16, v);
+        } else {
+          uint32_t v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 q = *reinterpret_cast<const uint4*>(src + (((wg * 4 + j) ^ (row & 7)) << 4));
-          v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+          for (int j = 0; j < 2; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(src + (((wg * 2 + j) ^ sw) << 4));
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+          }
+          tmem_st8_u(tmem + lane_addr + COL_QK + wg * 8, v);
         }
-        tmem_st16_u(tmem + lane_addr + COL_BIG + c * 32 + wg * 16, v);
+      }
+      if (MODE == 0) {
+        // dy_i (outer tile, loop invariant, A operand of Y = dy_i V_j^T) goes to TMEM too: with A in shared memory every one of the
+        // 12 MMAs of a block re-reads its 4 KB A slice (49 instead of 33 cycles each, and the shared-memory pipe is the kernel's bound).
+        // Warp group w copies 16-byte pieces 4w..4w+3 of each 128-byte swizzled row chunk: 8 values = 4 TMEM columns per piece.
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const uint8_t* src = sm + OFF_OC + c * OC_CHUNK + (row >> 3) * 1024 + (row & 7) * 128;
+          uint32_t v[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(src + (((wg * 4 + j) ^ (row & 7)) << 4));
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+          }
+          tmem_st16_u(tmem + lane_addr + COL_BIG + c * 32 + wg * 16, v);
+        }
       }
       tmem_wait_st();
       tc_fence_before();

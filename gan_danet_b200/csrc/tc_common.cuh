@@ -128,6 +128,12 @@ __device__ __forceinline__ void tmem_st16_u(uint32_t taddr, const uint32_t* r) {
                  "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
                : "memory");
 }
+// 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8_u(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 // one fp32 column: thread t of the warp gets TMEM lane (lane_base + t)
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
   uint32_t r;

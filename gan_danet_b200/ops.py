@@ -301,4 +301,101 @@ def fused_adamw_(p: Tensor, g: Tensor, m: Tensor, v: Tensor, lr: float, beta1: f
                                 E._stream()), "gdn_adamw")
 
 
-OPS = ("pam_fwd", "pam_bwd", "cam_fwd", "cam_bwd", "conv2d", "conv2d_bwd", "upsample_bicubic2x", "upsample_bicubic2x_bwd", "fused_adamw_")
+# ------------------------------------------------------------------------------------------------ BatchNorm statistics
+@torch.library.custom_op("gandanet::bn_stats_finalize", mutates_args=("running_mean", "running_var"), device_types="cuda")
+def bn_stats_finalize(x: Tensor, weight: Tensor, bias: Tensor, running_mean: Tensor, running_var: Tensor, eps: float, momentum: float) -> Tensor:
+    """Train-mode ``nn.BatchNorm2d`` statistics of an NHWC tensor (generator.py:32,62,149,189,219,223): per-channel batch mean / biased variance
+    (fp64 accumulation), the momentum update of the running statistics with the UNBIASED variance (in place), and the folded coefficients.
+    Returns coef [4, C] = (mean, invstd, scale = weight*invstd, shift = bias - mean*scale): ``y = x*scale + shift``."""
+    x = _nhwc(x, "bn_stats_finalize(x)")
+    lib = E._lib(x)
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    coef = torch.empty((4, Cc), dtype=torch.float32, device=x.device)
+    sums = E.colstats(x)
+    L.check(lib.gdn_bn_finalize(sums.data_ptr(), M, Cc, weight.data_ptr(), bias.data_ptr(), float(eps), float(momentum), running_mean.data_ptr(), running_var.data_ptr(),
+                                coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(), coef[3].data_ptr(), E._stream()), "gdn_bn_finalize")
+    return coef
+
+
+@bn_stats_finalize.register_fake
+def _(x, weight, bias, running_mean, running_var, eps, momentum):
+    return x.new_empty((4, x.shape[-1]))
+
+
+# ------------------------------------------------------------------------------------------------ bilinear skip fusion
+@torch.library.custom_op("gandanet::bilinear_resize_add_fwd", mutates_args=(), device_types="cuda")
+def bilinear_resize_add_fwd(s: Tensor, x: Tensor) -> Tensor:
+    """``x + F.interpolate(s, size=x.shape[1:3], mode='bilinear', align_corners=False)`` on NHWC tensors: the skip fusion of generator.py:242-246."""
+    s, x = _nhwc(s, "bilinear_resize_add_fwd(s)"), _nhwc(x, "bilinear_resize_add_fwd(x)")
+    B, Hi, Wi, Cc = s.shape
+    _, Ho, Wo, _ = x.shape
+    y = x.clone()
+    L.check(E._lib(x).gdn_bilinear_fwd(s.data_ptr(), y.data_ptr(), B, Hi, Wi, Ho, Wo, Cc, 1, E._stream()), "gdn_bilinear_fwd")
+    return y
+
+
+@bilinear_resize_add_fwd.register_fake
+def _(s, x):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("gandanet::bilinear_resize_add_bwd", mutates_args=(), device_types="cuda")
+def bilinear_resize_add_bwd(dy: Tensor, hi: int, wi: int) -> Tensor:
+    """Gradient of the resized term with respect to ``s`` (the adjoint gather of the bilinear resize); the gradient with respect to ``x`` is dy."""
+    dy = _nhwc(dy, "bilinear_resize_add_bwd(dy)")
+    B, Ho, Wo, Cc = dy.shape
+    ds = torch.empty((B, hi, wi, Cc), dtype=torch.float32, device=dy.device)
+    L.check(E._lib(dy).gdn_bilinear_bwd(dy.data_ptr(), ds.data_ptr(), B, hi, wi, Ho, Wo, Cc, 0, E._stream()), "gdn_bilinear_bwd")
+    return ds
+
+
+@bilinear_resize_add_bwd.register_fake
+def _(dy, hi, wi):
+    return dy.new_empty((dy.shape[0], hi, wi, dy.shape[3]))
+
+
+def _bil_setup(ctx, inputs, output):
+    ctx.hw = (inputs[0].shape[1], inputs[0].shape[2])
+
+
+def _bil_backward(ctx, dy):
+    dy = dy.contiguous()
+    return torch.ops.gandanet.bilinear_resize_add_bwd(dy, ctx.hw[0], ctx.hw[1]), dy
+
+
+bilinear_resize_add_fwd.register_autograd(_bil_backward, setup_context=_bil_setup)
+
+
+# ------------------------------------------------------------------------------------------------ generator objective
+@torch.library.custom_op("gandanet::multi_loss_fwd_bwd", mutates_args=(), device_types="cuda")
+def multi_loss_fwd_bwd(hr: Tensor, real: Tensor, fake_logits: Tensor, w_adv: float, tv_weight: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """The D-dependent and pixel-space terms of the generator objective in one op (GAN_DANet_train.ipynb:261-267, without the perceptual term):
+    ``loss = (1 - w_adv) * MSE(hr, real) + w_adv * BCEWithLogits(fake_logits, 1) + TV(hr; tv_weight)`` (losses.py:76-87 for TV), together with
+    its gradients: returns (losses [4] = total, pixel, adv, tv; d loss / d hr [B,1,H,W]; d loss / d fake_logits).  Every term adds value and
+    gradient in a single pass over its operand (gdn_mse / gdn_tv accumulate into one gradient field)."""
+    if hr.dim() != 4 or hr.shape != real.shape or hr.dtype != torch.float32:
+        raise L.GdnError("multi_loss_fwd_bwd: hr and real must be float32 [B, C, H, W] tensors of one shape")
+    hr, real, z = hr.contiguous(), real.contiguous(), fake_logits.contiguous()
+    lib = E._lib(hr)
+    B, Cc, H, W = hr.shape
+    dev = hr.device
+    part = torch.zeros(3, dtype=torch.float32, device=dev)                     # pixel, adv, tv
+    dhr = torch.empty_like(hr)
+    dz = torch.empty_like(z)
+    ws = E.dot_ws(dev)
+    st = E._stream()
+    L.check(lib.gdn_mse(hr.data_ptr(), real.data_ptr(), hr.numel(), part[0:1].data_ptr(), dhr.data_ptr(), 1.0 - w_adv, 0, ws.data_ptr(), st), "gdn_mse")
+    L.check(lib.gdn_tv(hr.data_ptr(), B * Cc, H, W, float(tv_weight) * Cc, part[2:3].data_ptr(), dhr.data_ptr(), 1.0, 1, ws.data_ptr(), st), "gdn_tv")
+    L.check(lib.gdn_bce_logits(z.data_ptr(), z.numel(), None, 1.0, part[1:2].data_ptr(), dz.data_ptr(), float(w_adv), st), "gdn_bce_logits")
+    total = ((1.0 - w_adv) * part[0] + w_adv * part[1] + part[2]).reshape(1)
+    return torch.cat([total, part]), dhr, dz
+
+
+@multi_loss_fwd_bwd.register_fake
+def _(hr, real, fake_logits, w_adv, tv_weight):
+    return hr.new_empty((4,)), torch.empty_like(hr), torch.empty_like(fake_logits)
+
+
+OPS = ("pam_fwd", "pam_bwd", "cam_fwd", "cam_bwd", "conv2d", "conv2d_bwd", "upsample_bicubic2x", "upsample_bicubic2x_bwd", "fused_adamw_",
+       "bn_stats_finalize", "bilinear_resize_add_fwd", "bilinear_resize_add_bwd", "multi_loss_fwd_bwd")

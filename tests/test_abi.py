@@ -80,6 +80,12 @@ def test_custom_op_layer_registered():
     assert torch.ops.gandanet.conv2d(x, w, None, 1, 1, 1, 0.0).shape == (2, 8, 16, 24)
     assert torch.ops.gandanet.conv2d(x, w, None, 2, 1, 0, 0.0).shape == (2, 4, 8, 24)
     assert torch.ops.gandanet.upsample_bicubic2x(x).shape == (2, 16, 32, 160)
+    c = torch.empty(160, device="meta")
+    assert torch.ops.gandanet.bn_stats_finalize(x, c, c, c, c, 1e-5, 0.1).shape == (4, 160)
+    assert torch.ops.gandanet.bilinear_resize_add_fwd(x, torch.empty(2, 32, 64, 160, device="meta")).shape == (2, 32, 64, 160)
+    hr = torch.empty(2, 1, 32, 64, device="meta")
+    lo, dhr, dz = torch.ops.gandanet.multi_loss_fwd_bwd(hr, hr, torch.empty(2, 1, device="meta"), 0.02, 1e-5)
+    assert lo.shape == (4,) and dhr.shape == hr.shape and dz.shape == (2, 1)
     with pytest.raises(NotImplementedError):
         torch.ops.gandanet.upsample_bicubic2x(torch.zeros(1, 2, 2, 4))
     with pytest.raises(NotImplementedError):

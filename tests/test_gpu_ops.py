@@ -6,6 +6,8 @@ import torch.nn.functional as F
 
 from conftest import rel_err
 
+rel = rel_err
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
@@ -132,3 +134,57 @@ def test_python_free_cabi_harness():
     assert r.returncode == 0, (r.stdout, r.stderr)
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["rel_err_y"] < 2e-3 and out["pam_fwd_tflops"] > 0
+
+
+def test_bn_stats_finalize_op():
+    """torch.ops.gandanet.bn_stats_finalize against nn.BatchNorm2d in train mode: normalisation coefficients and the in-place running statistics."""
+    import gan_danet_b200.ops  # noqa: F401
+    g = torch.Generator().manual_seed(3)
+    x = (2.0 * torch.randn(3, 5, 7, 24, generator=g) + 0.7).to(DEV)                  # NHWC
+    bn = torch.nn.BatchNorm2d(24).double()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(24, generator=g) + 0.5); bn.bias.copy_(torch.randn(24, generator=g))
+    w, b = bn.weight.detach().float().to(DEV), bn.bias.detach().float().to(DEV)
+    rm, rv = torch.zeros(24, device=DEV), torch.ones(24, device=DEV)
+    coef = torch.ops.gandanet.bn_stats_finalize(x, w, b, rm, rv, 1e-5, 0.1)
+    y = x * coef[2] + coef[3]
+    ref = bn.train()(x.cpu().double().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    assert rel(y, ref) < 1e-5
+    assert rel(rm, bn.running_mean) < 1e-5 and rel(rv, bn.running_var) < 1e-5
+
+
+def test_bilinear_resize_add_op():
+    import torch.nn.functional as F
+    import gan_danet_b200.ops  # noqa: F401
+    g = torch.Generator().manual_seed(4)
+    s = torch.randn(2, 6, 9, 8, generator=g).to(DEV).requires_grad_(True)
+    x = torch.randn(2, 24, 36, 8, generator=g).to(DEV).requires_grad_(True)
+    r = torch.randn(2, 24, 36, 8, generator=g).to(DEV)
+    y = torch.ops.gandanet.bilinear_resize_add_fwd(s, x)
+    (y * r).sum().backward()
+    sd, xd = s.detach().cpu().double().requires_grad_(True), x.detach().cpu().double().requires_grad_(True)
+    ref = xd + F.interpolate(sd.permute(0, 3, 1, 2), size=(24, 36), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    (ref * r.cpu().double()).sum().backward()
+    assert rel(y, ref) < 1e-6 and rel(s.grad, sd.grad) < 1e-5 and rel(x.grad, xd.grad) < 1e-6
+
+
+def test_multi_loss_op():
+    """torch.ops.gandanet.multi_loss_fwd_bwd against nn.MSELoss / nn.BCEWithLogitsLoss / the reference's TVLoss formula (losses.py:81-87) and autograd."""
+    import gan_danet_b200.ops  # noqa: F401
+    g = torch.Generator().manual_seed(5)
+    hr = torch.randn(3, 1, 16, 24, generator=g).to(DEV)
+    real = torch.randn(3, 1, 16, 24, generator=g).to(DEV)
+    z = torch.randn(3, 1, generator=g).to(DEV)
+    w, tvw = 0.02, 1e-5
+    losses, dhr, dz = torch.ops.gandanet.multi_loss_fwd_bwd(hr, real, z, w, tvw)
+    h, zz = hr.cpu().double().requires_grad_(True), z.cpu().double().requires_grad_(True)
+    pix = torch.nn.functional.mse_loss(h, real.cpu().double())
+    adv = torch.nn.functional.binary_cross_entropy_with_logits(zz, torch.ones_like(zz))
+    B, Cc, H, W = h.shape
+    tv = tvw * 2 * (((h[:, :, 1:] - h[:, :, :-1]) ** 2).sum() / (B * Cc * (H - 1) * W) + ((h[:, :, :, 1:] - h[:, :, :, :-1]) ** 2).sum() / (B * Cc * H * (W - 1))) / B
+    total = (1 - w) * pix + w * adv + tv
+    total.backward()
+    got = losses.cpu().double()
+    for a, b in zip(got, (total, pix, adv, tv)):
+        assert abs(float(a) - float(b)) < 1e-5 * abs(float(b)) + 1e-12, (float(a), float(b))
+    assert rel(dhr, h.grad) < 1e-5 and rel(dz, zz.grad) < 1e-5
