@@ -96,6 +96,7 @@ SIGNATURES = {
     "gdn_pack_weight_bf16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "gdn_conv2d_tc": (_i, [C.POINTER(ConvTcArgs), _vp]),
     "gdn_conv_tc_set_halo": (_i, [_i]),
+    "gdn_conv_tc_set_wgrad_swap": (_i, [_i]),
     "gdn_conv2d_wgrad_tc_ws_bytes": (_sz, [C.POINTER(WgradTcArgs)]),
     "gdn_conv2d_wgrad_tc": (_i, [C.POINTER(WgradTcArgs), _vp]),
     "gdn_linear_tc_supported": (_i, [_i, _i, _i]),
@@ -108,6 +109,7 @@ SIGNATURES = {
     "gdn_thin_conv_expand": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "gdn_thin_conv_expand_p": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "gdn_thin_conv_reduce": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "gdn_thin_conv_reduce_gated": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_thin_conv_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "gdn_thin_conv_wgrad": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "gdn_colstats_ws_bytes": (_sz, [_ll, _i]),

@@ -546,16 +546,17 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDYhi, const __grid_c
 }
 
 // out[co][out_c0+ci][tap] (OIHW) (+)= scale * sum_s ws[s][co][tap][ci]   -- fixed summation order => deterministic
+// swapped: the partial sums come from the role-swapped launch (gdn_conv2d_wgrad_tc: narrow Cout), ws[s][ci][taps-1-tap][co] with row width cin_w
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ ws, int splits, int Cout, int Cin, int taps, int cin_w,
                                        float* __restrict__ out, int out_cin_total, int out_c0, int accumulate, float scale,
-                                       const float* __restrict__ scale_ptr) {
+                                       const float* __restrict__ scale_ptr, int swapped) {
   if (scale_ptr) scale *= __ldg(scale_ptr);
   const long long total = (long long)Cout * taps * Cin;
-  const size_t split_stride = (size_t)Cout * taps * cin_w;
+  const size_t split_stride = (size_t)(swapped ? Cin : Cout) * taps * cin_w;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(idx % Cin); long long r = idx / Cin;
     const int tap = (int)(r % taps); const int co = (int)(r / taps);
-    const float* src = ws + ((size_t)co * taps + tap) * cin_w + ci;
+    const float* src = swapped ? ws + ((size_t)ci * taps + (taps - 1 - tap)) * cin_w + co : ws + ((size_t)co * taps + tap) * cin_w + ci;
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
     float* o = out + ((size_t)co * out_cin_total + out_c0 + ci) * taps + tap;
@@ -878,23 +879,48 @@ static void wgrad_plan(const gdn_wgrad_tc_args* a, WgParams* p) {
 }
 static int wgrad_splits(const WgParams* p) { return (int)cdiv(p->tiles_total, p->tiles_per_split); }
 
+// Narrow outputs (the DenseNet growth convolutions, generator.py:34: Cout = 24): with the output channels as the UMMA M dimension 24 of 128 accumulator
+// lanes do work.  dW[co][tap][ci] = sum_q dy[q][co] x[q + tap][ci] = sum_p x[p][ci] dy[p - tap][co] is the SAME kernel with the operands' roles swapped
+// (x as the "gradient" operand: M = input channels, dy as the shifted operand: N = 64 >= Cout) and the filter taps mirrored, for stride-1 "same"
+// convolutions (equal grids: the zero padding of one operand's shift is the other's).  The reduction pass transposes the partial sums back.
+static int g_wgrad_swap = 1;
+extern "C" int gdn_conv_tc_set_wgrad_swap(int enabled) { const int old = g_wgrad_swap; g_wgrad_swap = enabled ? 1 : 0; return old; }
+static bool wgrad_swap_ok(const gdn_wgrad_tc_args* a) {
+  return g_wgrad_swap && a->groups <= 1 && a->stride == 1 && a->Cout <= 32 && a->Cin >= 64 && a->Ho == a->Hi && a->Wo == a->Wi && a->kh == a->kw &&
+         2 * a->pad == a->kh - 1 && (a->kh & 1);
+}
+static gdn_wgrad_tc_args wgrad_swapped(const gdn_wgrad_tc_args* a) {
+  gdn_wgrad_tc_args b = *a;
+  b.dy_hi = a->x_hi; b.dy_lo = a->x_lo; b.x_hi = a->dy_hi; b.x_lo = a->dy_lo;
+  b.Cout = a->Cin; b.Cin = a->Cout;
+  return b;
+}
+
 extern "C" size_t gdn_conv2d_wgrad_tc_ws_bytes(const gdn_wgrad_tc_args* a) {
   if (a->groups > 1) return 0;
   WgParams p;
+  if (wgrad_swap_ok(a)) {
+    const gdn_wgrad_tc_args b = wgrad_swapped(a);
+    wgrad_plan(&b, &p);
+    return (size_t)wgrad_splits(&p) * b.Cout * p.taps_total * p.cin_w * sizeof(float);
+  }
   wgrad_plan(a, &p);
   return (size_t)wgrad_splits(&p) * a->Cout * p.taps_total * p.cin_w * sizeof(float);
 }
 
-extern "C" int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s) {
-  GDN_CHECK_ARG(a && a->dy_hi && a->x_hi && a->out && (a->ws || a->groups > 1));
+extern "C" int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* orig, gdn_stream_t s) {
+  GDN_CHECK_ARG(orig && orig->dy_hi && orig->x_hi && orig->out && (orig->ws || orig->groups > 1));
+  GDN_CHECK_ARG(orig->out_cin_total >= orig->out_c0 + orig->Cin);
+  const bool swapped = wgrad_swap_ok(orig);
+  const gdn_wgrad_tc_args sw = swapped ? wgrad_swapped(orig) : *orig;
+  const gdn_wgrad_tc_args* a = &sw;
   GDN_CHECK_ARG(a->groups <= 1 || (a->groups == a->B && a->kh == 1 && a->kw == 1 && a->Cin % 4 == 0 && !a->accumulate && ((uintptr_t)a->out & 15) == 0));
   GDN_CHECK_ARG(a->B > 0 && a->Cin > 0 && a->Cout > 0 && a->kh > 0 && a->kw > 0 && a->kw <= 3 && a->kh <= 3 && (a->stride == 1 || a->stride == 2));
-  GDN_CHECK_ARG(a->out_cin_total >= a->out_c0 + a->Cin);
   GDN_CHECK_ARG(a->precision == GDN_PREC_BF16 || (a->precision == GDN_PREC_BF16X3 && a->dy_lo && a->x_lo));
   WgParams p;
   wgrad_plan(a, &p);
   const int splits = wgrad_splits(&p);
-  if (a->ws_bytes < gdn_conv2d_wgrad_tc_ws_bytes(a)) { set_error("gdn_conv2d_wgrad_tc: workspace too small"); return GDN_EWORKSPACE; }
+  if (a->ws_bytes < gdn_conv2d_wgrad_tc_ws_bytes(orig)) { set_error("gdn_conv2d_wgrad_tc: workspace too small"); return GDN_EWORKSPACE; }
   GDN_CHECK_ARG(((uintptr_t)a->ws & 15) == 0);
   p.ws = a->ws;
   if (a->groups > 1) { p.direct = a->out; p.direct_pitch = a->Cin; p.scale_ptr = a->scale_ptr; }
@@ -916,8 +942,8 @@ extern "C" int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* a, gdn_stream_t s) {
   if (a->groups > 1) return GDN_OK;
   const long long total = (long long)a->Cout * p.taps_total * a->Cin;
   const int blocks = (int)(cdiv(total, 256) < 4 * kNumSMs ? cdiv(total, 256) : 4 * kNumSMs);
-  wgrad_tc_reduce_kernel<<<blocks, 256, 0, st>>>(a->ws, splits, a->Cout, a->Cin, p.taps_total, p.cin_w, a->out, a->out_cin_total, a->out_c0, a->accumulate, a->scale,
-                                                 a->scale_ptr);
+  wgrad_tc_reduce_kernel<<<blocks, 256, 0, st>>>(a->ws, splits, orig->Cout, orig->Cin, p.taps_total, p.cin_w, a->out, a->out_cin_total, a->out_c0, a->accumulate, a->scale,
+                                                 a->scale_ptr, swapped ? 1 : 0);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

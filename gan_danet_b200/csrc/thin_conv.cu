@@ -105,7 +105,8 @@ constexpr int RT_H = 16, RT_W = 32, R_MAXPIX = (RT_H + 2) * (RT_W + 2);
 
 template <int CPL>   // channels per lane: C = 8 * CPL
 __global__ void __launch_bounds__(256, CPL <= 8 ? 2 : 1) reduce_kernel(const float* __restrict__ V, int v_pitch, const float* __restrict__ w, const float* __restrict__ bias,
-                                                                       float* S, const float* res /* may alias S */, Geo g, int transposed, int tiles_x, int tiles_y) {
+                                                                       float* S, const float* res /* may alias S */, Geo g, int transposed, int tiles_x, int tiles_y,
+                                                                       const float* __restrict__ gate, int gate_pitch, float gate_slope) {
   __shared__ float Ts[9][R_MAXPIX + 4];
   constexpr int NJ = CPL / 4;
   const int lane8 = threadIdx.x & 7, slot = threadIdx.x >> 3;   // 32 pixel slots per pass
@@ -130,13 +131,24 @@ __global__ void __launch_bounds__(256, CPL <= 8 ? 2 : 1) reduce_kernel(const flo
   const int n = vy_n * vx_n;
   const int passes = (n + 31) >> 5;
   const float* vb = V + (size_t)b * g.Hv * g.Wv * v_pitch + lane8 * 4;
+  const float* gb = gate ? gate + (size_t)b * g.Hv * g.Wv * gate_pitch + lane8 * 4 : nullptr;
+  // gate: V is the gradient of an activation's OUTPUT and gate that output (ReLU / LeakyReLU): the wide tensor is multiplied by act'(gate) while it is
+  // loaded, so that the activation backward is not a pass of its own (1 GB read + 1 GB written per 64-channel 256x512 batch of 32)
   auto load = [&](int i, float4* dst) {
     const int ry = i / vx_n, rx = i - ry * vx_n;
     const int vy = vy_lo + ry, vx = vx_lo + rx;
     const bool ok = i < n && vy >= 0 && vy < g.Hv && vx >= 0 && vx < g.Wv;
-    const float* src = vb + (size_t)(ok ? vy * g.Wv + vx : 0) * v_pitch;
+    const size_t pix = (size_t)(ok ? vy * g.Wv + vx : 0);
+    const float* src = vb + pix * v_pitch;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) dst[j] = ok ? __ldg(reinterpret_cast<const float4*>(src + j * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NJ; ++j) {
+      dst[j] = ok ? __ldg(reinterpret_cast<const float4*>(src + j * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gb && ok) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(gb + pix * gate_pitch + j * 32));
+        dst[j].x = q.x > 0.f ? dst[j].x : gate_slope * dst[j].x; dst[j].y = q.y > 0.f ? dst[j].y : gate_slope * dst[j].y;
+        dst[j].z = q.z > 0.f ? dst[j].z : gate_slope * dst[j].z; dst[j].w = q.w > 0.f ? dst[j].w : gate_slope * dst[j].w;
+      }
+    }
   };
   const bool b2 = lane8 & 4, b1 = lane8 & 2, b0 = lane8 & 1;
   float4 cur[NJ], nxt[NJ];
@@ -323,8 +335,15 @@ extern "C" int gdn_thin_conv_expand_p(const float* s_in, const float* w, const f
   return GDN_OK;
 }
 
+extern "C" int gdn_thin_conv_reduce_gated(const float* v_in, int v_pitch, const float* gate, int gate_pitch, float gate_slope, const float* w, const float* bias, float* s_out,
+                                          const float* res, int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int transposed, gdn_stream_t st);
 extern "C" int gdn_thin_conv_reduce(const float* v_in, int v_pitch, const float* w, const float* bias, float* s_out, const float* res,
                                     int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int transposed, gdn_stream_t st) {
+  return gdn_thin_conv_reduce_gated(v_in, v_pitch, nullptr, 0, 0.f, w, bias, s_out, res, B, Hv, Wv, C, Hs, Ws, stride, pad, transposed, st);
+}
+extern "C" int gdn_thin_conv_reduce_gated(const float* v_in, int v_pitch, const float* gate, int gate_pitch, float gate_slope, const float* w, const float* bias, float* s_out,
+                                          const float* res, int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int transposed, gdn_stream_t st) {
+  GDN_CHECK_ARG(!gate || (gate_pitch >= C && gate_pitch % 4 == 0 && ((uintptr_t)gate & 15) == 0));
   GDN_CHECK_ARG(v_in && w && s_out && thin_ok(C) && v_pitch >= C && v_pitch % 4 == 0 && ((uintptr_t)v_in & 15) == 0 && (transposed || stride == 1) && stride >= 1);
   GDN_CHECK_ARG((long long)B * Hv * Wv < (1ll << 31) && pad >= 0 && pad <= 2);
   Geo g = {B, Hv, Wv, C, Hs, Ws, stride, pad};
@@ -332,9 +351,9 @@ extern "C" int gdn_thin_conv_reduce(const float* v_in, int v_pitch, const float*
   const long long blocks = (long long)B * tiles_x * tiles_y;
   GDN_CHECK_ARG(blocks < (1ll << 31));
   cudaStream_t s = as_stream(st);
-  if (C == 32) reduce_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y);
-  else if (C == 64) reduce_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y);
-  else reduce_kernel<16><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y);
+  if (C == 32) reduce_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y, gate, gate_pitch, gate_slope);
+  else if (C == 64) reduce_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y, gate, gate_pitch, gate_slope);
+  else reduce_kernel<16><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y, gate, gate_pitch, gate_slope);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

@@ -464,6 +464,23 @@ def conv_backward_tc_only(O: int, Cin: int, kh: int, kw: int, stride: int, Ho: i
     return ok_w and ok_x
 
 
+def thin_gated_dgrad_ok(x: Tensor, w: Tensor, dy: Tensor, y: Tensor, stride: int, gx: Optional[Tensor], need_gw: bool, need_bias: bool) -> bool:
+    """True when the data gradient of a 1 -> C convolution + activation can take act'(y) while loading dy (gdn_thin_conv_reduce_gated): nothing else
+    needs the activation's input gradient (no weight / bias gradient requested: frozen VGG19 conv1_1, Discriminator1.conv1 in the generator step)."""
+    O, I, kh, kw = w.shape
+    return bool(not need_gw and not need_bias and gx is not None and gx.is_contiguous() and _thin_kind(I, O, kh, kw, stride, x, dy) == "expand"
+                and pitch_of(y) % 4 == 0 and y.data_ptr() % 16 == 0)
+
+
+def thin_gated_dgrad(dy: Tensor, y: Tensor, x: Tensor, w: Tensor, gx: Tensor, *, stride: int, pad: int, accumulate: bool, slope: float) -> None:
+    """gx (+)= conv_transpose(dy * act'(y), w) for a 1 -> C convolution: the activation backward is fused into the gradient kernel's loads."""
+    O = w.shape[0]
+    B, Hi, Wi, _ = x.shape
+    _, Ho, Wo, _ = dy.shape
+    L.check(_lib(x).gdn_thin_conv_reduce_gated(dy.data_ptr(), pitch_of(dy), y.data_ptr(), pitch_of(y), float(slope), w.contiguous().data_ptr(), None, gx.data_ptr(),
+                                               gx.data_ptr() if accumulate else None, B, Ho, Wo, O, Hi, Wi, stride, pad, 1, _stream()), "gdn_thin_conv_reduce_gated")
+
+
 def conv_backward(ctx: ConvCtx, dz: Optional[Tensor], x: Tensor, w: Tensor, *, stride: int = 1, pad: int = 0, gw: Optional[Tensor] = None,
                   gx: Optional[Tensor] = None, gx_accumulate: bool = False, frozen_key: Optional[Tuple] = None, dz_packed: Optional[Packed] = None,
                   out_hw: Optional[Tuple[int, int]] = None) -> None:
@@ -684,6 +701,9 @@ def op_conv(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, stride: int = 1,
                           dz_packed=pack_actgrad(dy, y.t, act, slope), out_hw=(Ho, Wo))
             if gw is not None:
                 w.add_grad(gw)
+            return
+        if act in (ACT_RELU, ACT_LRELU) and thin_gated_dgrad_ok(x.t, w.t, dy, y.t, stride, tgt, gw is not None, need_bias):
+            thin_gated_dgrad(dy, y.t, x.t, w.t.detach(), tgt, stride=stride, pad=pad, accumulate=acc, slope=slope if act == ACT_LRELU else 0.0)
             return
         if act != ACT_NONE:
             dz = torch.empty(y.t.shape, dtype=torch.float32, device=dy.device)

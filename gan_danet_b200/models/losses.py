@@ -370,6 +370,9 @@ def _frozen_conv16(tape: E.Tape, x: E.Var, x16, wk: Tuple[torch.Tensor, Tuple], 
         if y.g is None or not x.needs_grad:
             return
         tgt, acc = x.grad_target()
+        if thin and E.thin_gated_dgrad_ok(x.t, w, y.g, y.t, 1, tgt, False, False):
+            E.thin_gated_dgrad(y.g, y.t, x.t, w, tgt, stride=1, pad=1, accumulate=acc, slope=0.0)      # ReLU backward inside the gradient kernel's loads
+            return
         if thin or not E.conv_backward_tc_only(O, Cin, 3, 3, 1, H, W, H, W, False, True):
             dz = torch.empty_like(y.g)
             E.act_bwd(y.g, y.t, dz, ACT_RELU, 0.0)
@@ -430,9 +433,15 @@ class _PerceptualFn(torch.autograd.Function):
             g = torch.empty_like(f.t) if need else None
             L.check(lib.gdn_l1(f.t.data_ptr(), t.data_ptr(), f.t.numel(), loss.data_ptr(), 1, E._ptr(g), 1.0, 0, ws.data_ptr(), E._stream()), "gdn_l1")
             if need:
-                def bwd():
-                    f.add_grad(g)
-                tape.push(bwd)
+                if f.g is None and f.parent is None:
+                    # the L1 term's gradient IS the feature's gradient buffer from here on: the data gradient of the next convolution accumulates
+                    # into it in its epilogue (res = gx) instead of a separate read-modify-write pass over the tapped map (1 GB at relu1_1).
+                    # Same two summands, same single fp32 addition => bit-identical to adding g afterwards.
+                    f.g = g
+                else:
+                    def bwd():
+                        f.add_grad(g)
+                    tape.push(bwd)
 
         mod._features(tape, xin, on_feature)
         ctx.tape, ctx.xin = tape, xin

@@ -152,6 +152,8 @@ typedef struct {
 int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s);
 /* test hook: enable/disable the halo-reuse variant of the forward kernel (stride-1 3x3, narrow output tiles); returns the old setting */
 int gdn_conv_tc_set_halo(int enabled);
+/* test hook: enable/disable the role-swapped weight gradient for narrow outputs (Cout <= 32, the DenseNet growth convolutions of generator.py:34) */
+int gdn_conv_tc_set_wgrad_swap(int enabled);
 /*
  * Weight gradient: out[co][out_c0+ci][kh][kw] (OIHW, out_cin_total input channels) (+)= scale * sum_pixels dy * x.
  * dy: packed [B,Ho,Wo,Cout_p8]; x: packed [B,Hi,Wi,Cin_p8].  Deterministic (split-K through ws, fixed-order reduction).
@@ -206,6 +208,11 @@ int gdn_thin_conv_expand_p(const float* s_in, const float* w, const float* bias,
 /* S = sum_k sum_c V w[c][k] + bias[0] + res   (transposed == 0: C->1 forward, v = s + k - pad; 1: data gradient of the 1->C conv) */
 int gdn_thin_conv_reduce(const float* v_in, int v_pitch, const float* w, const float* bias, float* s_out, const float* res,
                          int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int transposed, gdn_stream_t st);
+/* the same with the wide tensor multiplied by act'(gate) while it is loaded (gate = the activation's output: ReLU for gate_slope 0, LeakyReLU otherwise):
+ * the data gradient of a 1 -> C convolution followed by an activation (VGG19 conv1_1 + ReLU, losses.py:58; Discriminator1.conv1 + LeakyReLU,
+ * discriminator.py:71) without a separate activation-backward pass */
+int gdn_thin_conv_reduce_gated(const float* v_in, int v_pitch, const float* gate, int gate_pitch, float gate_slope, const float* w, const float* bias, float* s_out,
+                               const float* res, int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int transposed, gdn_stream_t s);
 /* dw[c][k] (+)= sum_v V[v][c] S[v*stride + k - pad]   (flip: S at v + pad - k).  Deterministic two-stage reduction. */
 size_t gdn_thin_conv_wgrad_ws_bytes(int B, int Hv, int Wv, int C);
 int gdn_thin_conv_wgrad(const float* v, int v_pitch, const float* s_in, float* dw, int accumulate, int B, int Hv, int Wv, int C, int Hs, int Ws,

@@ -218,3 +218,36 @@ def test_conv_bn_relu_packed_gradient():
     assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
     bad = [k for k in g0 if not torch.equal(g1[k], g0[k])]
     assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k", [(2, 136, 24, 64, 128, 3), (1, 64, 24, 45, 22, 3), (2, 160, 24, 16, 32, 3), (1, 88, 16, 9, 13, 1), (1, 152, 32, 8, 200, 3)])
+def test_wgrad_role_swap(B, Cin, Cout, H, W, k, precision):
+    """Weight gradient of the narrow (growth) convolutions of the dense blocks (generator.py:34): the role-swapped launch (input channels as the
+    UMMA M dimension, taps mirrored) against the direct one on the same bf16 operands -- the same products, another accumulation order."""
+    from gan_danet_b200 import _lib, engine as E
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(B * 100 + Cin)
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev)
+    dy = torch.randn(B, H, W, Cout, generator=g).to(dev)
+    lib = _lib.lib_for_device(0)
+    old = E.conv_precision
+    E.set_conv_precision(precision)
+    try:
+        out = []
+        for swap in (1, 0):
+            prev = lib.gdn_conv_tc_set_wgrad_swap(swap)
+            try:
+                gw = torch.empty(Cout, Cin, k, k, device=dev)
+                E.wgrad_tc_raw(E.pack_act(dy), E.pack_act(x), gw, B=B, in_hw=(H, W), out_hw=(H, W), cin=Cin, cout=Cout, kh=k, kw=k, stride=1, pad=k // 2)
+                torch.cuda.synchronize()
+                out.append(gw)
+            finally:
+                lib.gdn_conv_tc_set_wgrad_swap(prev)
+        err = float((out[0].double() - out[1].double()).norm() / out[1].double().norm())
+        assert err < 1e-5, err
+        xr, dyr = (bf16_round(t) if precision == "bf16" else t for t in (x, dy))
+        ref = torch.nn.grad.conv2d_weight(xr.double().permute(0, 3, 1, 2), (Cout, Cin, k, k), dyr.double().permute(0, 3, 1, 2), padding=k // 2)
+        assert float((out[0].double() - ref).norm() / ref.norm()) < (1e-5 if precision == "bf16" else 1e-4)
+    finally:
+        E.set_conv_precision(old)
