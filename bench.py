@@ -295,6 +295,7 @@ def run_ours(args):
         if i + 1 < args.steps:
             pipe.submit(pinned)                                      # step i+1's inputs travel while step i computes
         out = step_fn(*dev_in)                                       # graph mode: + one device-to-device copy into the static input buffers
+        pipe.release()
         host_losses[i % 2].copy_(torch.stack([out["loss_D"], out["loss_G"]]), non_blocking=True)    # device -> host read of the step's result
         read_done[i % 2].record()
         if i > 0:

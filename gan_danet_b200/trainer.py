@@ -179,31 +179,53 @@ class GradientAllReduce:
 class HostBatchPipeline:
     """Double-buffered host -> device input pipeline (the DataLoader -> ``.to(device)`` hand-off of
     GAN_DANet_train.ipynb:225-228): the pinned host batch of step i+1 is copied on a side stream while step i computes, so
-    the 24 MB/sample aux stack never stalls the kernels.  ``next()`` returns device tensors that are safe to use on the
-    current stream."""
+    the 12-24 MB/sample aux stack never stalls the kernels.  The device side is two PREALLOCATED staging sets (no per-step allocation, no
+    allocator bookkeeping across streams): ``next()`` returns the staged tensors of the batch submitted last, safe to use on the current
+    stream; ``release()`` -- called once the consumer's reads are enqueued -- lets the copy after next overwrite that set."""
 
-    def __init__(self, device: torch.device):
+    def __init__(self, device: torch.device, depth: int = 2):
         self.device = device
         self.copy_stream = torch.cuda.Stream(device=device)
-        self._pending = None
+        self.depth = depth
+        self.slots: List[Optional[List[torch.Tensor]]] = [None] * depth
+        self.free_ev: List[Optional[torch.cuda.Event]] = [None] * depth
+        self._n = 0
+        self._pending: Optional[Tuple[int, torch.cuda.Event]] = None
+        self._held: Optional[int] = None
 
     def submit(self, host_tensors) -> None:
         """Start the asynchronous copy of one (pinned) host batch."""
+        k = self._n % self.depth
+        self._n += 1
+        if self.slots[k] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(self.slots[k], host_tensors)):
+            self.slots[k] = [torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_tensors]
+            self.free_ev[k] = None
         with torch.cuda.stream(self.copy_stream):
-            dev = [t.to(self.device, non_blocking=True) for t in host_tensors]
+            if self.free_ev[k] is not None:
+                self.copy_stream.wait_event(self.free_ev[k])          # the consumer of this set's previous batch has finished reading it
+            else:
+                self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            for d, h in zip(self.slots[k], host_tensors):
+                d.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        self._pending = (dev, ev)
+        self._pending = (k, ev)
 
     def next(self):
         """Device tensors of the batch submitted last (waits for its copy on the current stream, not on the host)."""
-        dev, ev = self._pending
+        k, ev = self._pending
         self._pending = None
-        cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(ev)
-        for t in dev:
-            t.record_stream(cur)
-        return dev
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        self._held = k
+        return self.slots[k]
+
+    def release(self) -> None:
+        """The reads of the batch handed out by the last ``next()`` are enqueued on the current stream: its staging set may be refilled after them."""
+        if self._held is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self.free_ev[self._held] = ev
+            self._held = None
 
 
 def prepare_input_nhwc(lr_grace_05: torch.Tensor, hr_aux: torch.Tensor) -> torch.Tensor:
