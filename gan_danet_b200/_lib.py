@@ -126,12 +126,14 @@ SIGNATURES = {
     "gdn_sums_to_float": (_i, [_vp, _vp, _i, _f, _vp]),
     "gdn_bicubic_up2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_bicubic_up2_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "gdn_bicubic_up2_bilinear_add_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_bilinear_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_bicubic_down_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_bicubic_down_nchw_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_maxpool2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_maxpool2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "gdn_maxpool2_bwd_relu_pack16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_maxpool2_fwd_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_maxpool2_bwd_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_pam_fwd_ws_bytes": (_sz, [C.POINTER(PamFwdArgs)]),

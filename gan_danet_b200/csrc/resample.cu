@@ -116,7 +116,11 @@ __global__ void __launch_bounds__(256) bicubic_up2_bwd_kernel(const float* __res
 // ---- 128-bit fast paths ------------------------------------------------------------------------------------------------
 // x2 bicubic: output rows 2i / 2i+1 read input rows i-2..i+1 (t = 0.75) / i-1..i+2 (t = 0.25); one thread produces the 2x2
 // output block of input pixel (i, j) from the 5x5 clamped neighbourhood, separably (25 loads for 4 outputs instead of 64).
-__global__ void __launch_bounds__(256) bicubic_up2_fwd_v4_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+// ADD: y = up2(x) + bilinear_resize(s -> 2H x 2W) in the same pass (the skip fusion of generator.py:242-246 lands on the last up-sampling's output:
+// one write of the 64-channel full-resolution tensor instead of write + read-modify-write).
+template <int ADD>
+__global__ void __launch_bounds__(256) bicubic_up2_fwd_v4_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C,
+                                                                  const float* __restrict__ s, int Hs, int Ws) {
   const int Cv = C >> 2, Wo = 2 * W;
   const long long total = (long long)B * H * W * Cv;
   float w75[4], w25[4];
@@ -150,6 +154,27 @@ __global__ void __launch_bounds__(256) bicubic_up2_fwd_v4_kernel(const float* __
         const float wv = w25[k - 1];
         o[1][0].x = fmaf(wv, h0.x, o[1][0].x); o[1][0].y = fmaf(wv, h0.y, o[1][0].y); o[1][0].z = fmaf(wv, h0.z, o[1][0].z); o[1][0].w = fmaf(wv, h0.w, o[1][0].w);
         o[1][1].x = fmaf(wv, h1.x, o[1][1].x); o[1][1].y = fmaf(wv, h1.y, o[1][1].y); o[1][1].z = fmaf(wv, h1.z, o[1][1].z); o[1][1].w = fmaf(wv, h1.w, o[1][1].w);
+      }
+    }
+    if (ADD) {
+      const float ry = (float)Hs / (float)(2 * H), rx = (float)Ws / (float)Wo;
+      const float* sb = s + (size_t)b * Hs * Ws * C + c;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        int y0, y1; float ty;
+        linear_src(2 * i + a, ry, Hs, y0, y1, ty);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int x0, x1; float tx;
+          linear_src(2 * j + e, rx, Ws, x0, x1, tx);
+          const float w00 = (1.f - ty) * (1.f - tx), w01 = (1.f - ty) * tx, w10 = ty * (1.f - tx), w11 = ty * tx;
+          const float4 q00 = __ldg(reinterpret_cast<const float4*>(sb + ((size_t)y0 * Ws + x0) * C)), q01 = __ldg(reinterpret_cast<const float4*>(sb + ((size_t)y0 * Ws + x1) * C));
+          const float4 q10 = __ldg(reinterpret_cast<const float4*>(sb + ((size_t)y1 * Ws + x0) * C)), q11 = __ldg(reinterpret_cast<const float4*>(sb + ((size_t)y1 * Ws + x1) * C));
+          float4 rr;
+          rr.x = w00 * q00.x + w01 * q01.x + w10 * q10.x + w11 * q11.x; rr.y = w00 * q00.y + w01 * q01.y + w10 * q10.y + w11 * q11.y;
+          rr.z = w00 * q00.z + w01 * q01.z + w10 * q10.z + w11 * q11.z; rr.w = w00 * q00.w + w01 * q01.w + w10 * q10.w + w11 * q11.w;
+          o[a][e].x += rr.x; o[a][e].y += rr.y; o[a][e].z += rr.z; o[a][e].w += rr.w;
+        }
       }
     }
 #pragma unroll
@@ -231,6 +256,46 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_v4_kernel(const float* __res
       if (has_y1) *reinterpret_cast<float4*>(dx + p00 + (size_t)W * C) = z;
       if (has_x1 && has_y1) *reinterpret_cast<float4*>(dx + p00 + (size_t)W * C + C) = z;
     }
+  }
+}
+
+// The same routing fused with the ReLU backward of the pooled map and the operand packing of the preceding convolution's data-gradient GEMM: x is the
+// OUTPUT of conv + ReLU (VGG19 conv1_2 / conv2_2 / conv3_4, losses.py:58) and feeds only this pool, so dz = route(dy) * (x > 0) is needed only as a bf16
+// [pixel][C] operand.  Replaces maxpool2_bwd (x read, fp32 dx written) + pack_actgrad (dx and x read again): 12 -> 6.5 bytes per element of x.
+// One thread per pooling window and 8 channels; H, W even, C % 8 == 0.  Bit-identical to the two-pass path (same routing, same gate, same rounding).
+__global__ void __launch_bounds__(256) maxpool2_bwd_relu_pack16_kernel(const float* __restrict__ x, const float* __restrict__ dy, __nv_bfloat16* __restrict__ dz,
+                                                                       int B, int H, int W, int C) {
+  const int Cv = C >> 3, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cv) << 3; long long r = idx / Cv;
+    const int ox = (int)(r % Wo); r /= Wo; const int oy = (int)(r % Ho); const int b = (int)(r / Ho);
+    const size_t p00 = (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + c;
+    const size_t off[4] = {p00, p00 + C, p00 + (size_t)W * C, p00 + (size_t)W * C + C};
+    float v[4][8], g[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x + off[k])), bq = __ldg(reinterpret_cast<const float4*>(x + off[k] + 4));
+      v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w; v[k][4] = bq.x; v[k][5] = bq.y; v[k][6] = bq.z; v[k][7] = bq.w;
+    }
+    {
+      const float* gp = dy + (((size_t)b * Ho + oy) * Wo + ox) * C + c;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(gp)), bq = __ldg(reinterpret_cast<const float4*>(gp + 4));
+      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = bq.x; g[5] = bq.y; g[6] = bq.z; g[7] = bq.w;
+    }
+    __align__(16) __nv_bfloat16 o[4][8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float m = v[0][e]; int a = 0;
+      if (v[1][e] > m) { m = v[1][e]; a = 1; }
+      if (v[2][e] > m) { m = v[2][e]; a = 2; }
+      if (v[3][e] > m) { m = v[3][e]; a = 3; }
+      const float ge = m > 0.f ? g[e] : 0.f;                 // ReLU backward on the routed element (x is a ReLU output: x > 0 <=> pre-activation > 0)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k][e] = __float2bfloat16_rn(a == k ? ge : 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dz + off[k]) = *reinterpret_cast<const uint4*>(o[k]);
   }
 }
 
@@ -537,8 +602,14 @@ using namespace gdn;
 
 extern "C" int gdn_bicubic_up2_fwd(const float* x, float* y, int B, int H, int W, int C, gdn_stream_t s) {
   GDN_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0);
-  if (C % 4 == 0 && al16(x) && al16(y)) bicubic_up2_fwd_v4_kernel<<<grid_for((long long)B * H * W * (C / 4)), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
+  if (C % 4 == 0 && al16(x) && al16(y)) bicubic_up2_fwd_v4_kernel<0><<<grid_for((long long)B * H * W * (C / 4)), 256, 0, as_stream(s)>>>(x, y, B, H, W, C, nullptr, 0, 0);
   else bicubic_up2_fwd_kernel<1><<<grid_for((long long)B * 4 * H * W * C), 256, 0, as_stream(s)>>>(x, y, B, H, W, C);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_bicubic_up2_bilinear_add_fwd(const float* x, const float* skip, float* y, int B, int H, int W, int Hs, int Ws, int C, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && skip && y && B > 0 && H > 0 && W > 0 && Hs > 0 && Ws > 0 && C > 0 && C % 4 == 0 && al16(x) && al16(y) && al16(skip));
+  bicubic_up2_fwd_v4_kernel<1><<<grid_for((long long)B * H * W * (C / 4)), 256, 0, as_stream(s)>>>(x, y, B, H, W, C, skip, Hs, Ws);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
@@ -601,6 +672,12 @@ extern "C" int gdn_maxpool2_fwd_bf16(const uint16_t* x, uint16_t* y, int B, int 
 extern "C" int gdn_maxpool2_bwd_bf16(const uint16_t* x, const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s) {
   GDN_CHECK_ARG(x && dy && dx && B > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0 && al16(x) && al16(dy) && al16(dx));
   maxpool2_bwd_bf16_kernel<<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 4)), 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), dy, dx, B, H, W, C);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_maxpool2_bwd_relu_pack16(const float* x, const float* dy, uint16_t* dz16, int B, int H, int W, int C, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && dy && dz16 && B > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0 && al16(x) && al16(dy) && al16(dz16));
+  maxpool2_bwd_relu_pack16_kernel<<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8)), 256, 0, as_stream(s)>>>(x, dy, reinterpret_cast<__nv_bfloat16*>(dz16), B, H, W, C);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

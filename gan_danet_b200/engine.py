@@ -1124,17 +1124,33 @@ def op_cam(tape: Tape, x: Var, gamma: Var, *, out: Optional[Var] = None, y16: Op
     return y
 
 
-def op_bicubic_up2(tape: Tape, x: Var) -> Var:
+upsample_skip_fusion: bool = os.environ.get("GDN_UP2_SKIP_FUSION", "1") != "0"
+
+
+def op_bicubic_up2(tape: Tape, x: Var, skip: Optional[Var] = None) -> Var:
+    """nn.Upsample(scale_factor=2, mode='bicubic') (generator.py:221,225).  ``skip``: y = up2(x) + bilinear_resize(skip -> y's grid) in the same pass
+    (the skip fusion of generator.py:242-246 on the last up-sampling: the full-resolution tensor is written once)."""
     lib = _lib(x.t)
     B, H, W, Cc = x.t.shape
     assert x.t.is_contiguous()
     y = Var(new_nhwc(B, 2 * H, 2 * W, Cc, x.t))
-    L.check(lib.gdn_bicubic_up2_fwd(x.t.data_ptr(), y.t.data_ptr(), B, H, W, Cc, _stream()), "gdn_bicubic_up2_fwd")
+    if skip is not None:
+        _, Hs, Ws, Cs = skip.t.shape
+        assert Cs == Cc and skip.t.is_contiguous() and Cc % 4 == 0
+        L.check(lib.gdn_bicubic_up2_bilinear_add_fwd(x.t.data_ptr(), skip.t.data_ptr(), y.t.data_ptr(), B, H, W, Hs, Ws, Cc, _stream()), "gdn_bicubic_up2_bilinear_add_fwd")
+    else:
+        L.check(lib.gdn_bicubic_up2_fwd(x.t.data_ptr(), y.t.data_ptr(), B, H, W, Cc, _stream()), "gdn_bicubic_up2_fwd")
 
     def bwd():
-        if y.g is None or not x.needs_grad:
+        if y.g is None:
             return
         assert y.g.is_contiguous()
+        if skip is not None and skip.needs_grad:
+            tgt, acc = skip.grad_target()
+            assert tgt.is_contiguous()
+            L.check(lib.gdn_bilinear_bwd(y.g.data_ptr(), tgt.data_ptr(), B, Hs, Ws, 2 * H, 2 * W, Cc, int(acc), _stream()), "gdn_bilinear_bwd")
+        if not x.needs_grad:
+            return
         gx = new_nhwc(B, H, W, Cc, x.t)
         L.check(lib.gdn_bicubic_up2_bwd(y.g.data_ptr(), gx.data_ptr(), B, H, W, Cc, _stream()), "gdn_bicubic_up2_bwd")
         x.add_grad(gx)
@@ -1202,6 +1218,35 @@ def op_maxpool2(tape: Tape, x: Var) -> Var:
         gx = new_nhwc(B, H, W, Cc, x.t)
         L.check(lib.gdn_maxpool2_bwd(x.t.data_ptr(), y.g.data_ptr(), gx.data_ptr(), B, H, W, Cc, _stream()), "gdn_maxpool2_bwd")
         x.add_grad(gx)
+
+    tape.push(bwd)
+    return y
+
+
+pool_relu_pack_fusion: bool = os.environ.get("GDN_POOL_RELU_PACK", "1") != "0"
+
+
+def op_maxpool2_relu_packed(tape: Tape, x: Var) -> Var:
+    """MaxPool2d(2, 2) of a conv + ReLU output that feeds ONLY this pool and whose convolution takes its data gradient as a packed bf16 operand: the
+    backward writes x.g16 = bf16(route(dy) * (x > 0)) in one pass (gdn_maxpool2_bwd_relu_pack16) instead of an fp32 dx followed by pack_actgrad."""
+    lib = _lib(x.t)
+    B, H, W, Cc = x.t.shape
+    if not (pool_relu_pack_fusion and conv_precision == "bf16" and H % 2 == 0 and W % 2 == 0 and Cc % 8 == 0 and x.t.is_contiguous()):
+        return op_maxpool2(tape, x)
+    y = Var(new_nhwc(B, H // 2, W // 2, Cc, x.t))
+    L.check(lib.gdn_maxpool2_fwd(x.t.data_ptr(), y.t.data_ptr(), B, H, W, Cc, _stream()), "gdn_maxpool2_fwd")
+
+    def bwd():
+        if y.g is None or not x.needs_grad:
+            return
+        if x.g is not None or x.parent is not None or x.g16 is not None:      # another consumer already produced a gradient: the generic route
+            gx = new_nhwc(B, H, W, Cc, x.t)
+            L.check(lib.gdn_maxpool2_bwd(x.t.data_ptr(), y.g.data_ptr(), gx.data_ptr(), B, H, W, Cc, _stream()), "gdn_maxpool2_bwd")
+            x.add_grad(gx)
+            return
+        dz16 = torch.empty((B * H * W, Cc), dtype=torch.bfloat16, device=x.t.device)
+        L.check(lib.gdn_maxpool2_bwd_relu_pack16(x.t.data_ptr(), y.g.data_ptr(), dz16.data_ptr(), B, H, W, Cc, _stream()), "gdn_maxpool2_bwd_relu_pack16")
+        x.g16 = Packed(dz16, None, Cc)
 
     tape.push(bwd)
     return y

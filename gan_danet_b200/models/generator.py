@@ -369,17 +369,26 @@ class FlexibleUpsamplingModule(TapeModule):
                 buf = nxt.alloc(B, H, W, xin.t)
                 self.transition_layers[i]._build(ctx, x, out=buf.slice(0, nxt.in_channels))
                 x = buf
+        # skip projections (generator.py:242-246) at the low resolution: the 1x1 convolutions commute with the (linear) bilinear resize
+        s: Optional[E.Var] = None
+        for adjust, feat in zip(self.channel_adjust, reversed(skips)):
+            s = E.op_conv_accumulate(tape, feat, ctx.v(adjust.weight), s)
         up = self.upsample
-        for conv, bn in ((up[0], up[1]), (up[4], up[5])):
+        stages = ((up[0], up[1]), (up[4], up[5]))
+        fused_skip = False
+        for k, (conv, bn) in enumerate(stages):
             if conv.bias is None:
                 x = E.op_conv_bn_act(tape, x, ctx.v(conv.weight), ctx.bn(bn), training=bn.training, act=ACT_RELU, stride=conv.stride[0], pad=conv.padding[0])
             else:
                 x = E.op_bn_act(tape, _conv(ctx, x, conv), ctx.bn(bn), training=bn.training, act=ACT_RELU)
-            x = E.op_bicubic_up2(tape, x)
-        s: Optional[E.Var] = None
-        for adjust, feat in zip(self.channel_adjust, reversed(skips)):
-            s = E.op_conv_accumulate(tape, feat, ctx.v(adjust.weight), s)
-        if s is not None:
+            # the last up-sampling adds the resized skip sum while it writes its output (one pass over the 64-channel full-resolution tensor)
+            last = k == len(stages) - 1
+            if last and s is not None and E.upsample_skip_fusion and x.t.shape[-1] == s.t.shape[-1] and x.t.shape[-1] % 4 == 0:
+                x = E.op_bicubic_up2(tape, x, skip=s)
+                fused_skip = True
+            else:
+                x = E.op_bicubic_up2(tape, x)
+        if s is not None and not fused_skip:
             x = E.op_bilinear_add_(tape, s, x)
         return _conv(ctx, x, self.final)
 

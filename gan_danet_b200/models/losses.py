@@ -278,6 +278,8 @@ class PerceptualLoss(nn.Module):
             elif isinstance(layer, nn.MaxPool2d):
                 if cur16 is not None:
                     cur, cur16 = E.op_maxpool2_bf16(tape, cur, cur16)
+                elif tape.record and idx >= 2 and isinstance(layers[idx - 1], nn.ReLU) and isinstance(layers[idx - 2], nn.Conv2d) and (idx - 1) not in self.feature_layers:
+                    cur = E.op_maxpool2_relu_packed(tape, cur)      # untapped conv + ReLU output feeding only this pool: fused gradient route
                 else:
                     cur = E.op_maxpool2(tape, cur)
             if idx in self.feature_layers:
@@ -367,9 +369,13 @@ def _frozen_conv16(tape: E.Tape, x: E.Var, x16, wk: Tuple[torch.Tensor, Tuple], 
                               x_packed=E.Packed(x16, None, Cin) if x16 is not None else None, y16=y16)
 
     def bwd():
-        if y.g is None or not x.needs_grad:
+        if (y.g is None and y.g16 is None) or not x.needs_grad:
             return
         tgt, acc = x.grad_target()
+        if y.g16 is not None:          # the pool's backward already produced dz = route(dy) * relu'(y) as the packed operand (op_maxpool2_relu_packed)
+            assert y.g is None and not thin
+            E.conv_backward(cctx, None, x.t, w, pad=1, gx=tgt, gx_accumulate=acc, frozen_key=key, dz_packed=y.g16, out_hw=(H, W))
+            return
         if thin and E.thin_gated_dgrad_ok(x.t, w, y.g, y.t, 1, tgt, False, False):
             E.thin_gated_dgrad(y.g, y.t, x.t, w, tgt, stride=1, pad=1, accumulate=acc, slope=0.0)      # ReLU backward inside the gradient kernel's loads
             return

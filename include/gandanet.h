@@ -261,6 +261,9 @@ int gdn_sums_to_float(const double* sums, float* out, int n, float scale, gdn_st
 /* nn.Upsample(scale_factor=2, mode='bicubic', align_corners=False), generator.py:221,225 (A=-0.75, clamped taps) */
 int gdn_bicubic_up2_fwd(const float* x, float* y, int B, int H, int W, int C, gdn_stream_t s);
 int gdn_bicubic_up2_bwd(const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s);
+/* y = up2(x) + F.interpolate(skip, size=(2H, 2W), mode='bilinear', align_corners=False): the last up-sampling of generator.py:225 and the skip fusion of
+ * :242-246 in one pass over the full-resolution tensor (x [B,H,W,C], skip [B,Hs,Ws,C], y [B,2H,2W,C]; C % 4 == 0).  Backward: gdn_bicubic_up2_bwd and gdn_bilinear_bwd of dy */
+int gdn_bicubic_up2_bilinear_add_fwd(const float* x, const float* skip, float* y, int B, int H, int W, int Hs, int Ws, int C, gdn_stream_t s);
 /* F.interpolate(size=(Ho,Wo), mode='bilinear', align_corners=False), generator.py:244: y (+)= resize(x) */
 int gdn_bilinear_fwd(const float* x, float* y, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s);
 int gdn_bilinear_bwd(const float* dy, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s);
@@ -272,6 +275,9 @@ int gdn_bicubic_down_nchw_to_nhwc_bf16(const uint16_t* x, float* y, int y_pitch,
 /* 2x2/2 max pool (VGG19 features idx 4,9,18; losses.py:58) */
 int gdn_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, gdn_stream_t s);
 int gdn_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s);
+/* pooling backward fused with the ReLU backward of the pooled map x (a conv + ReLU output that feeds only this pool: VGG19 conv1_2 / conv2_2 / conv3_4) and
+ * with the operand packing of that convolution's data-gradient GEMM: dz16 [B*H*W][C] bf16 = route(dy) * (x > 0).  Even H, W; C % 8 == 0 */
+int gdn_maxpool2_bwd_relu_pack16(const float* x, const float* dy, uint16_t* dz16, int B, int H, int W, int C, gdn_stream_t s);
 /* the same pooling (VGG19 of losses.py:58) on bf16 feature maps [B,H,W,C], C % 8 == 0; the gradient stays fp32 (even H, W) */
 int gdn_maxpool2_fwd_bf16(const uint16_t* x, uint16_t* y, int B, int H, int W, int C, gdn_stream_t s);
 int gdn_maxpool2_bwd_bf16(const uint16_t* x, const float* dy, float* dx, int B, int H, int W, int C, gdn_stream_t s);
