@@ -388,7 +388,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
-constexpr int WG_DY_SLOTS = 2, WG_X_SLOTS = 4;
+constexpr int WG_DY_SLOTS = 2, WG_X_SLOTS = 8;     // WG_X_SLOTS: the most x slots a launch may use (barrier layout); WgParams::x_slots are in use
 constexpr int WG_DY_BYTES = 2 * A_BYTES;    // [128 px][64 co] x 2 channel boxes (UMMA M = 128 output channels)
 
 struct WgParams {
@@ -398,6 +398,7 @@ struct WgParams {
   int tiles_w, tiles_h, tiles_total, tiles_per_split;
   int Wt, Ht, cs, pad, kw;
   int ci_tile, ci_tiles, co_tiles, tap_groups, taps_per_cta, nsplit, tmem_cols;
+  int x_slots;                 // depth of the shifted-operand ring: the kernel is bound by bytes in flight per SM (TMA latency x ring depth), ncu round 2
 };
 
 __global__ void __launch_bounds__(NTHREADS)
@@ -409,7 +410,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDYhi, const __grid_c
   const int nbox = p.ci_tile / 64;
   const int x_bytes = nbox * A_BYTES;
   const uint32_t dy_base = base, x_base = base + WG_DY_SLOTS * WG_DY_BYTES;
-  const uint32_t bar_base = x_base + WG_X_SLOTS * x_bytes;
+  const int XS = p.x_slots;
+  const uint32_t bar_base = x_base + XS * x_bytes;
   auto dyfull = [&](int s) { return bar_base + 8 * s; };
   auto dyempty = [&](int s) { return bar_base + 8 * (WG_DY_SLOTS + s); };
   auto xfull = [&](int s) { return bar_base + 8 * (2 * WG_DY_SLOTS + s); };
@@ -430,7 +432,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDYhi, const __grid_c
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_DY_SLOTS; ++s) { mbar_init(dyfull(s), 1); mbar_init(dyempty(s), 1); }
-    for (int s = 0; s < WG_X_SLOTS; ++s) { mbar_init(xfull(s), 1); mbar_init(xempty(s), 1); }
+    for (int s = 0; s < XS; ++s) { mbar_init(xfull(s), 1); mbar_init(xempty(s), 1); }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -472,8 +474,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDYhi, const __grid_c
           for (int tl = 0; tl < p.taps_per_cta; ++tl, ++n) {
             const int tap = tap0 + tl;
             const int dh = tap / p.kw - p.pad, dw = tap % p.kw - p.pad;
-            const int s = n % WG_X_SLOTS;
-            if (n >= WG_X_SLOTS) mbar_wait(xempty(s), ((n / WG_X_SLOTS) - 1) & 1);
+            const int s = n % XS;
+            if (n >= XS) mbar_wait(xempty(s), ((n / XS) - 1) & 1);
             mbar_expect_tx(xfull(s), x_bytes);
             for (int bx = 0; bx < nbox; ++bx)
               tma_load_4d(x_base + s * x_bytes + bx * A_BYTES, m, xfull(s), cit * p.ci_tile + bx * 64, tw * p.Wt * p.cs + dw, th * p.Ht * p.cs + dh, t);
@@ -505,7 +507,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDYhi, const __grid_c
             tc_commit(xempty(sx));
           }
           __syncwarp();
-          if (++sx == WG_X_SLOTS) { sx = 0; phx ^= 1; }
+          if (++sx == XS) { sx = 0; phx ^= 1; }
         }
         if (elect_one()) tc_commit(dyempty(sd));
         __syncwarp();
@@ -870,7 +872,11 @@ static void wgrad_plan(const gdn_wgrad_tc_args* a, WgParams* p) {
   p->tiles_w = (int)cdiv(a->Wo, p->Wt); p->tiles_h = (int)cdiv(a->Ho, p->Ht);
   p->tiles_total = a->B * p->tiles_h * p->tiles_w;
   const int units = p->co_tiles * p->ci_tiles * p->tap_groups;
-  int splits = (int)cdiv(2 * kNumSMs, units);
+  // one CTA per SM (128-198 KB of shared memory): the grid is a whole number of waves -- 2 * 148 / units rounded DOWN (rounded up, 300 CTAs on 148 SMs
+  // ran as three waves: ncu round 2, the dense-block growth convolutions)
+  int splits = (2 * kNumSMs) / units;
+  if (splits < 1) splits = 1;
+  p->x_slots = p->ci_tile == 64 ? 8 : 4;         // 64-channel tiles: 16 KB slots, eight of them (the 128-channel tile's four 32 KB slots fill the budget)
   const int max_splits = p->tiles_total / 8 > 0 ? p->tiles_total / 8 : 1;
   if (splits > max_splits) splits = max_splits;
   p->tiles_per_split = (int)cdiv(p->tiles_total, splits);
@@ -883,7 +889,8 @@ static int wgrad_splits(const WgParams* p) { return (int)cdiv(p->tiles_total, p-
 // lanes do work.  dW[co][tap][ci] = sum_q dy[q][co] x[q + tap][ci] = sum_p x[p][ci] dy[p - tap][co] is the SAME kernel with the operands' roles swapped
 // (x as the "gradient" operand: M = input channels, dy as the shifted operand: N = 64 >= Cout) and the filter taps mirrored, for stride-1 "same"
 // convolutions (equal grids: the zero padding of one operand's shift is the other's).  The reduction pass transposes the partial sums back.
-static int g_wgrad_swap = 1;
+static int g_wgrad_swap = 0;      // measured (tools/profile_wgrad.py): no faster than the direct launch (0.187 vs 0.189 ms at C_in 136, slower at C_in 64) --
+                                  // these weight gradients are bound by the operand ring's latency, not by the MMA; kept behind the hook, tested
 extern "C" int gdn_conv_tc_set_wgrad_swap(int enabled) { const int old = g_wgrad_swap; g_wgrad_swap = enabled ? 1 : 0; return old; }
 static bool wgrad_swap_ok(const gdn_wgrad_tc_args* a) {
   return g_wgrad_swap && a->groups <= 1 && a->stride == 1 && a->Cout <= 32 && a->Cin >= 64 && a->Ho == a->Hi && a->Wo == a->Wi && a->kh == a->kw &&
@@ -933,7 +940,7 @@ extern "C" int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* orig, gdn_stream_t s
   if ((rc = make_act_map(&mxh, a->x_hi, Cip, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
   mxl = mxh;
   if (p.nsplit == 3 && (rc = make_act_map(&mxl, a->x_lo, Cip, a->Wi, a->Hi, a->B, p.Wt, p.Ht, p.cs)) != GDN_OK) return rc;
-  const size_t smem = (size_t)WG_DY_SLOTS * WG_DY_BYTES + (size_t)WG_X_SLOTS * (p.ci_tile / 64) * A_BYTES + 8 * (2 * WG_DY_SLOTS + 2 * WG_X_SLOTS + 2) + 1024;
+  const size_t smem = (size_t)WG_DY_SLOTS * WG_DY_BYTES + (size_t)p.x_slots * (p.ci_tile / 64) * A_BYTES + 8 * (2 * WG_DY_SLOTS + 2 * WG_X_SLOTS + 2) + 1024;
   dim3 grid((unsigned)(p.co_tiles * p.ci_tiles * p.tap_groups), (unsigned)splits);
   GDN_CHECK_ARG(grid.y <= 65535);
   cudaStream_t st = as_stream(s);
