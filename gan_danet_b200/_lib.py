@@ -127,6 +127,8 @@ SIGNATURES = {
     "gdn_bicubic_up2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_bicubic_up2_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_bicubic_up2_bilinear_add_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "gdn_tap_shift_sum": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "gdn_tap_shift_expand": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_bilinear_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_bicubic_down_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -299,6 +299,52 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_relu_pack16_kernel(const flo
   }
 }
 
+// ------------------------------------------------------------------ tap planes of a C -> 1 3x3 convolution (generator.py:228 after :225,:242-246)
+// final(up2(u) + resize(s)) is linear and the resamplers act per channel, so the channel reduction of the 3x3 convolution can run BEFORE the
+// resampling: z_t = sum_c w[c][t] u_c (a 1x1 convolution to 9 "tap planes" at low resolution), Z = up2(z) + resize(zs), and
+//   y[p] = bias + sum_t Z_t[p + t]   (zero outside the grid: the convolution's zero padding)
+// -- the 64-channel full-resolution tensor never exists (9 planes instead: 7x less traffic).  T = planes per pixel (9 used, padded to 12).
+__global__ void __launch_bounds__(256) tap_shift_sum_kernel(const float* __restrict__ Z, int T, const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W) {
+  const long long total = (long long)B * H * W;
+  const float b0 = bias ? __ldg(bias) : 0.f;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % W); long long r = idx / W;
+    const int i = (int)(r % H); const int b = (int)(r / H);
+    float acc = b0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int ii = i + a - 1;
+      if (ii < 0 || ii >= H) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int jj = j + c - 1;
+        if (jj < 0 || jj >= W) continue;
+        acc += __ldg(Z + (((size_t)b * H + ii) * W + jj) * T + a * 3 + c);
+      }
+    }
+    y[idx] = acc;
+  }
+}
+// adjoint: dZ[b][i][j][a*3+c] = dy[b][i-a+1][j-c+1] (0 outside), planes 9..T-1 = 0
+__global__ void __launch_bounds__(256) tap_shift_expand_kernel(const float* __restrict__ dy, float* __restrict__ dZ, int T, int B, int H, int W) {
+  const long long total = (long long)B * H * W;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % W); long long r = idx / W;
+    const int i = (int)(r % H); const int b = (int)(r / H);
+    float* o = dZ + (size_t)idx * T;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int ii = i - a + 1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int jj = j - c + 1;
+        o[a * 3 + c] = (ii >= 0 && ii < H && jj >= 0 && jj < W) ? __ldg(dy + ((size_t)b * H + ii) * W + jj) : 0.f;
+      }
+    }
+    for (int t = 9; t < T; ++t) o[t] = 0.f;
+  }
+}
+
 // ------------------------------------------------------------------ bilinear resize to (Ho, Wo)
 template <int VEC>
 __global__ void __launch_bounds__(256) bilinear_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C,
@@ -610,6 +656,18 @@ extern "C" int gdn_bicubic_up2_fwd(const float* x, float* y, int B, int H, int W
 extern "C" int gdn_bicubic_up2_bilinear_add_fwd(const float* x, const float* skip, float* y, int B, int H, int W, int Hs, int Ws, int C, gdn_stream_t s) {
   GDN_CHECK_ARG(x && skip && y && B > 0 && H > 0 && W > 0 && Hs > 0 && Ws > 0 && C > 0 && C % 4 == 0 && al16(x) && al16(y) && al16(skip));
   bicubic_up2_fwd_v4_kernel<1><<<grid_for((long long)B * H * W * (C / 4)), 256, 0, as_stream(s)>>>(x, y, B, H, W, C, skip, Hs, Ws);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_tap_shift_sum(const float* Z, int T, const float* bias, float* y, int B, int H, int W, gdn_stream_t s) {
+  GDN_CHECK_ARG(Z && y && T >= 9 && B > 0 && H > 0 && W > 0);
+  tap_shift_sum_kernel<<<grid_for((long long)B * H * W), 256, 0, as_stream(s)>>>(Z, T, bias, y, B, H, W);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_tap_shift_expand(const float* dy, float* dZ, int T, int B, int H, int W, gdn_stream_t s) {
+  GDN_CHECK_ARG(dy && dZ && T >= 9 && B > 0 && H > 0 && W > 0);
+  tap_shift_expand_kernel<<<grid_for((long long)B * H * W), 256, 0, as_stream(s)>>>(dy, dZ, T, B, H, W);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

@@ -381,8 +381,11 @@ class FlexibleUpsamplingModule(TapeModule):
                 x = E.op_conv_bn_act(tape, x, ctx.v(conv.weight), ctx.bn(bn), training=bn.training, act=ACT_RELU, stride=conv.stride[0], pad=conv.padding[0])
             else:
                 x = E.op_bn_act(tape, _conv(ctx, x, conv), ctx.bn(bn), training=bn.training, act=ACT_RELU)
-            # the last up-sampling adds the resized skip sum while it writes its output (one pass over the 64-channel full-resolution tensor)
             last = k == len(stages) - 1
+            if last and self.final.stride[0] == 1 and self.final.padding[0] == 1 and E.head_tap_planes_ok(x, s, ctx.v(self.final.weight)):
+                # up2 -> (+ skips) -> final 3x3 conv (64 -> 1) with the channel reduction hoisted in front of the resampling: no 64-channel tensor at 4h x 4w
+                return E.op_upsample_skip_final(tape, x, s, ctx.v(self.final.weight), ctx.v(self.final.bias))
+            # otherwise the last up-sampling adds the resized skip sum while it writes its output (one pass over the full-resolution tensor)
             if last and s is not None and E.upsample_skip_fusion and x.t.shape[-1] == s.t.shape[-1] and x.t.shape[-1] % 4 == 0:
                 x = E.op_bicubic_up2(tape, x, skip=s)
                 fused_skip = True

@@ -264,6 +264,12 @@ int gdn_bicubic_up2_bwd(const float* dy, float* dx, int B, int H, int W, int C, 
 /* y = up2(x) + F.interpolate(skip, size=(2H, 2W), mode='bilinear', align_corners=False): the last up-sampling of generator.py:225 and the skip fusion of
  * :242-246 in one pass over the full-resolution tensor (x [B,H,W,C], skip [B,Hs,Ws,C], y [B,2H,2W,C]; C % 4 == 0).  Backward: gdn_bicubic_up2_bwd and gdn_bilinear_bwd of dy */
 int gdn_bicubic_up2_bilinear_add_fwd(const float* x, const float* skip, float* y, int B, int H, int W, int Hs, int Ws, int C, gdn_stream_t s);
+/* The generator's head (generator.py:225,228,242-246) without its 64-channel full-resolution tensor: final(up2(u) + resize(s)) is linear and the resamplers
+ * act per channel, so the 3x3 convolution's channel reduction runs first at low resolution (a 1x1 convolution to T >= 9 "tap planes", plane t = kh*3 + kw),
+ * the planes are resampled, and y[b][i][j] = bias[0] + sum_{kh,kw} Z[b][i+kh-1][j+kw-1][kh*3+kw] (zero outside the grid).  Z: [B,H,W,T]; y, dy: [B,H,W]. */
+int gdn_tap_shift_sum(const float* Z, int T, const float* bias, float* y, int B, int H, int W, gdn_stream_t s);
+/* adjoint: dZ[b][i][j][kh*3+kw] = dy[b][i-kh+1][j-kw+1] (0 outside the grid), planes 9..T-1 = 0 */
+int gdn_tap_shift_expand(const float* dy, float* dZ, int T, int B, int H, int W, gdn_stream_t s);
 /* F.interpolate(size=(Ho,Wo), mode='bilinear', align_corners=False), generator.py:244: y (+)= resize(x) */
 int gdn_bilinear_fwd(const float* x, float* y, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s);
 int gdn_bilinear_bwd(const float* dy, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s);
