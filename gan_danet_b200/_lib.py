@@ -129,6 +129,10 @@ SIGNATURES = {
     "gdn_bicubic_up2_bilinear_add_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_tap_shift_sum": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     "gdn_tap_shift_expand": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "gdn_narrow_conv1x1_fwd": (_i, [_vp, _i, _vp, _i, _vp, _ll, _vp]),
+    "gdn_narrow_conv1x1_dgrad": (_i, [_vp, _i, _vp, _i, _vp, _ll, _i, _vp]),
+    "gdn_narrow_conv1x1_wgrad_ws_bytes": (_sz, [_ll, _i, _i]),
+    "gdn_narrow_conv1x1_wgrad": (_i, [_vp, _i, _vp, _i, _ll, _vp, _i, _vp, _sz, _vp]),
     "gdn_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_bilinear_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_bicubic_down_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -300,6 +300,104 @@ __global__ void __launch_bounds__(128) wgrad_final_kernel(const float* __restric
 }  // namespace thin
 }  // namespace gdn
 
+
+// ------------------------------------------------------------------------------------------------ narrow 1x1 convolutions (C <-> T <= 16 channels)
+// The generator head's tap planes (engine.op_upsample_skip_final): z[px][t] = sum_c u[px][c] wp[t][c] and its two gradients.  HBM-bound single passes over
+// the C-channel tensor (the fp32 implicit-GEMM engine ran these at 0.8 TB/s: N = 12 is far below its tile).  T <= 16, C % 4 == 0, C <= 256.
+namespace gdn {
+namespace narrow {
+constexpr int NT = 16;
+// thread = pixel; weights [T][C] in shared memory (broadcast reads)
+__global__ void __launch_bounds__(256) fwd_kernel(const float* __restrict__ u, int C, const float* __restrict__ wp, int T, float* __restrict__ z, long long M) {
+  extern __shared__ float ws[];
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) ws[i] = wp[i];
+  __syncthreads();
+  for (long long px = blockIdx.x * (long long)blockDim.x + threadIdx.x; px < M; px += (long long)gridDim.x * blockDim.x) {
+    float acc[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+    const float4* row = reinterpret_cast<const float4*>(u + (size_t)px * C);
+    for (int q = 0; q < (C >> 2); ++q) {
+      const float4 v = __ldg(row + q);
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        if (t < T) {
+          const float4 w4 = *reinterpret_cast<const float4*>(ws + t * C + 4 * q);
+          acc[t] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, acc[t]))));
+        }
+    }
+    float* o = z + (size_t)px * T;
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+      if (t < T) o[t] = acc[t];
+  }
+}
+// du[px][c] (+)= sum_t dz[px][t] wp[t][c]; thread = (pixel, 4-channel chunk): the C/4 threads of a pixel write one contiguous row
+__global__ void __launch_bounds__(256) dgrad_kernel(const float* __restrict__ dz, int T, const float* __restrict__ wp, int C, float* __restrict__ du, long long M, int accumulate) {
+  extern __shared__ float ws[];
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) ws[i] = wp[i];
+  __syncthreads();
+  const int Cv = C >> 2;
+  const long long total = M * Cv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long px = idx / Cv; const int q = (int)(idx - px * Cv);
+    float4 acc = accumulate ? *reinterpret_cast<const float4*>(du + (size_t)px * C + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* g = dz + (size_t)px * T;
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+      if (t < T) {
+        const float gv = __ldg(g + t);
+        const float4 w4 = *reinterpret_cast<const float4*>(ws + t * C + 4 * q);
+        acc.x = fmaf(gv, w4.x, acc.x); acc.y = fmaf(gv, w4.y, acc.y); acc.z = fmaf(gv, w4.z, acc.z); acc.w = fmaf(gv, w4.w, acc.w);
+      }
+    *reinterpret_cast<float4*>(du + (size_t)px * C + 4 * q) = acc;
+  }
+}
+// partial[block][t][c] = sum over the block's pixels of dz[px][t] u[px][c]; thread = (4-channel chunk, pixel slot); fixed order => deterministic
+__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dz, int T, const float* __restrict__ u, int C, long long M, long long px_per_block,
+                                                    float* __restrict__ partial) {
+  extern __shared__ float red[];                 // [slots][T][C]
+  const int Cv = C >> 2, slots = blockDim.x / Cv;
+  const int q = threadIdx.x % Cv, slot = threadIdx.x / Cv;
+  float acc[NT][4];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  const long long p0 = blockIdx.x * px_per_block, p1 = p0 + px_per_block < M ? p0 + px_per_block : M;
+  if (slot < slots)
+    for (long long px = p0 + slot; px < p1; px += slots) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(u + (size_t)px * C) + q);
+      const float* g = dz + (size_t)px * T;
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        if (t < T) {
+          const float gv = __ldg(g + t);
+          acc[t][0] = fmaf(gv, v.x, acc[t][0]); acc[t][1] = fmaf(gv, v.y, acc[t][1]); acc[t][2] = fmaf(gv, v.z, acc[t][2]); acc[t][3] = fmaf(gv, v.w, acc[t][3]);
+        }
+    }
+  if (slot < slots) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+      if (t < T) *reinterpret_cast<float4*>(red + ((size_t)slot * T + t) * C + 4 * q) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    float sum = 0.f;
+    for (int sl = 0; sl < slots; ++sl) sum += red[(size_t)sl * T * C + i];
+    partial[(size_t)blockIdx.x * T * C + i] = sum;
+  }
+}
+__global__ void wgrad_final_kernel(const float* __restrict__ partial, int nblocks, int n, float* __restrict__ out, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s0 = 0.f, s1 = 0.f;
+  int b = 0;
+  for (; b + 1 < nblocks; b += 2) { s0 += partial[(size_t)b * n + i]; s1 += partial[(size_t)(b + 1) * n + i]; }
+  if (b < nblocks) s0 += partial[(size_t)b * n + i];
+  out[i] = accumulate ? out[i] + (s0 + s1) : s0 + s1;
+}
+}  // namespace narrow
+}  // namespace gdn
+
 using namespace gdn;
 using namespace gdn::thin;
 
@@ -384,6 +482,41 @@ extern "C" int gdn_thin_conv_wgrad(const float* v, int v_pitch, const float* s_i
   else wgrad_kernel<0, 1><<<blocks, 256, smem, s>>>(v, v_pitch, s_in, ws, g, gpb, flip);
   GDN_CHECK_LAUNCH();
   wgrad_final_kernel<<<C * 9, 128, 0, s>>>(ws, blocks, C * 9, dw, accumulate);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+// ---- narrow 1x1 convolutions
+static inline bool narrow_ok(int C, int T) { return C > 0 && C % 4 == 0 && C <= 256 && T > 0 && T <= gdn::narrow::NT; }
+static inline int narrow_wgrad_blocks(long long M) { long long b = cdiv(M, 512); return (int)(b < 4 * kNumSMs ? (b > 0 ? b : 1) : 4 * kNumSMs); }
+extern "C" int gdn_narrow_conv1x1_fwd(const float* u, int C, const float* wp, int T, float* z, long long M, gdn_stream_t st) {
+  GDN_CHECK_ARG(u && wp && z && M > 0 && narrow_ok(C, T) && ((uintptr_t)u & 15) == 0);
+  const long long blocks = cdiv(M, 256);
+  gdn::narrow::fwd_kernel<<<(unsigned)(blocks < 16 * kNumSMs ? blocks : 16 * kNumSMs), 256, (size_t)T * C * sizeof(float), as_stream(st)>>>(u, C, wp, T, z, M);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_narrow_conv1x1_dgrad(const float* dz, int T, const float* wp, int C, float* du, long long M, int accumulate, gdn_stream_t st) {
+  GDN_CHECK_ARG(dz && wp && du && M > 0 && narrow_ok(C, T) && ((uintptr_t)du & 15) == 0);
+  const long long blocks = cdiv(M * (C / 4), 256);
+  gdn::narrow::dgrad_kernel<<<(unsigned)(blocks < 16 * kNumSMs ? blocks : 16 * kNumSMs), 256, (size_t)T * C * sizeof(float), as_stream(st)>>>(dz, T, wp, C, du, M, accumulate);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" size_t gdn_narrow_conv1x1_wgrad_ws_bytes(long long M, int C, int T) { return (size_t)narrow_wgrad_blocks(M) * T * C * sizeof(float); }
+extern "C" int gdn_narrow_conv1x1_wgrad(const float* dz, int T, const float* u, int C, long long M, float* gwp, int accumulate, void* ws, size_t ws_bytes, gdn_stream_t st) {
+  GDN_CHECK_ARG(dz && u && gwp && ws && M > 0 && narrow_ok(C, T) && ((uintptr_t)u & 15) == 0 && 256 % (C / 4) == 0);
+  if (ws_bytes < gdn_narrow_conv1x1_wgrad_ws_bytes(M, C, T)) { set_error("gdn_narrow_conv1x1_wgrad: workspace too small"); return GDN_EWORKSPACE; }
+  const int blocks = narrow_wgrad_blocks(M);
+  const long long ppb = cdiv(M, blocks);
+  const int slots = 256 / (C / 4);
+  const size_t smem = (size_t)slots * T * C * sizeof(float);
+  GDN_CHECK_ARG(smem <= 200 * 1024);
+  if (smem > 48 * 1024) GDN_CHECK_CUDA(cudaFuncSetAttribute(gdn::narrow::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device, cheap
+  cudaStream_t s = as_stream(st);
+  gdn::narrow::wgrad_kernel<<<blocks, 256, smem, s>>>(dz, T, u, C, M, ppb, reinterpret_cast<float*>(ws));
+  GDN_CHECK_LAUNCH();
+  gdn::narrow::wgrad_final_kernel<<<(unsigned)cdiv(T * C, 128), 128, 0, s>>>(reinterpret_cast<const float*>(ws), blocks, T * C, gwp, accumulate);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

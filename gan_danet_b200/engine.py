@@ -1182,13 +1182,36 @@ def op_upsample_skip_final(tape: Tape, u: Var, s: Optional[Var], w: Var, bias: O
     wp = torch.zeros((T, Cc), dtype=torch.float32, device=dev)
     wp[:9].copy_(w.t.detach().reshape(Cc, 9).t())                      # wp[kh*3+kw][c] = w[0][c][kh][kw]
     wpt = wp.t().contiguous()                                           # [C, T]: the adjoint 1x1 convolution's weight
+    narrow = Cc % 4 == 0 and Cc <= 256 and 256 % (Cc // 4) == 0        # HBM-bound narrow 1x1 kernels (thin_conv.cu); else the fp32 implicit-GEMM engine
+
+    def c1x1(x_t: Tensor, out: Tensor) -> None:
+        if narrow:
+            L.check(lib.gdn_narrow_conv1x1_fwd(x_t.data_ptr(), Cc, wp.data_ptr(), T, out.data_ptr(), rows_of(x_t), _stream()), "gdn_narrow_conv1x1_fwd")
+        else:
+            conv_raw(x_t, wp.view(T, 1, 1, Cc), out, kh=1, kw=1)
+
+    def c1x1_dgrad(dz_t: Tensor, tgt: Tensor, acc: bool) -> None:
+        if narrow and tgt.is_contiguous():
+            L.check(lib.gdn_narrow_conv1x1_dgrad(dz_t.data_ptr(), T, wp.data_ptr(), Cc, tgt.data_ptr(), rows_of(dz_t), int(acc), _stream()), "gdn_narrow_conv1x1_dgrad")
+        else:
+            conv_raw(dz_t, wpt.view(Cc, 1, 1, T), tgt, kh=1, kw=1, res=tgt if acc else None)
+
+    def c1x1_wgrad(dz_t: Tensor, x_t: Tensor, out: Tensor, acc: bool) -> None:
+        if narrow:
+            M = rows_of(x_t)
+            buf = workspace("narrow_wgrad", lib.gdn_narrow_conv1x1_wgrad_ws_bytes(M, Cc, T), dev)
+            L.check(lib.gdn_narrow_conv1x1_wgrad(dz_t.data_ptr(), T, x_t.data_ptr(), Cc, M, out.data_ptr(), int(acc), buf.data_ptr(), buf.numel(), _stream()),
+                    "gdn_narrow_conv1x1_wgrad")
+        else:
+            wgrad_raw(dz_t, x_t, out, kh=1, kw=1, accumulate=acc)
+
     z = new_nhwc(B, H, W, T, u.t)
-    conv_raw(u.t, wp.view(T, 1, 1, Cc), z, kh=1, kw=1)
+    c1x1(u.t, z)
     Z = new_nhwc(B, 2 * H, 2 * W, T, u.t)
     if s is not None:
         _, Hs, Ws, _ = s.t.shape
         zs = new_nhwc(B, Hs, Ws, T, u.t)
-        conv_raw(s.t, wp.view(T, 1, 1, Cc), zs, kh=1, kw=1)
+        c1x1(s.t, zs)
         L.check(lib.gdn_bicubic_up2_bilinear_add_fwd(z.data_ptr(), zs.data_ptr(), Z.data_ptr(), B, H, W, Hs, Ws, T, _stream()), "gdn_bicubic_up2_bilinear_add_fwd")
     else:
         L.check(lib.gdn_bicubic_up2_fwd(z.data_ptr(), Z.data_ptr(), B, H, W, T, _stream()), "gdn_bicubic_up2_fwd")
@@ -1208,18 +1231,18 @@ def op_upsample_skip_final(tape: Tape, u: Var, s: Optional[Var], w: Var, bias: O
         gwp = None
         if w.needs_grad:
             gwp = torch.empty((T, Cc, 1, 1), dtype=torch.float32, device=dev)
-            wgrad_raw(dz, u.t, gwp, kh=1, kw=1)
+            c1x1_wgrad(dz, u.t, gwp, False)
         if u.needs_grad:
             tgt, acc = u.grad_target()
-            conv_raw(dz, wpt.view(Cc, 1, 1, T), tgt, kh=1, kw=1, res=tgt if acc else None)
+            c1x1_dgrad(dz, tgt, acc)
         if s is not None and (s.needs_grad or w.needs_grad):
             dzs = new_nhwc(B, Hs, Ws, T, u.t)
             L.check(lib.gdn_bilinear_bwd(dZ.data_ptr(), dzs.data_ptr(), B, Hs, Ws, 2 * H, 2 * W, T, 0, _stream()), "gdn_bilinear_bwd")
             if w.needs_grad:
-                wgrad_raw(dzs, s.t, gwp, kh=1, kw=1, accumulate=True)
+                c1x1_wgrad(dzs, s.t, gwp, True)
             if s.needs_grad:
                 tgt, acc = s.grad_target()
-                conv_raw(dzs, wpt.view(Cc, 1, 1, T), tgt, kh=1, kw=1, res=tgt if acc else None)
+                c1x1_dgrad(dzs, tgt, acc)
         if gwp is not None:
             w.add_grad(gwp.view(T, Cc)[:9].t().reshape(1, Cc, 3, 3).contiguous())
         if bias is not None and bias.needs_grad:

@@ -270,6 +270,12 @@ int gdn_bicubic_up2_bilinear_add_fwd(const float* x, const float* skip, float* y
 int gdn_tap_shift_sum(const float* Z, int T, const float* bias, float* y, int B, int H, int W, gdn_stream_t s);
 /* adjoint: dZ[b][i][j][kh*3+kw] = dy[b][i-kh+1][j-kw+1] (0 outside the grid), planes 9..T-1 = 0 */
 int gdn_tap_shift_expand(const float* dy, float* dZ, int T, int B, int H, int W, gdn_stream_t s);
+/* the 1x1 convolution C -> T <= 16 tap planes of that head and its gradients, HBM-bound single passes (C % 4 == 0, C <= 256; wp: [T][C] row-major):
+ * z[px][t] = sum_c u[px][c] wp[t][c];  du[px][c] (+)= sum_t dz[px][t] wp[t][c];  gwp[t][c] (+)= sum_px dz[px][t] u[px][c] (deterministic two-stage) */
+int gdn_narrow_conv1x1_fwd(const float* u, int C, const float* wp, int T, float* z, long long M, gdn_stream_t s);
+int gdn_narrow_conv1x1_dgrad(const float* dz, int T, const float* wp, int C, float* du, long long M, int accumulate, gdn_stream_t s);
+size_t gdn_narrow_conv1x1_wgrad_ws_bytes(long long M, int C, int T);
+int gdn_narrow_conv1x1_wgrad(const float* dz, int T, const float* u, int C, long long M, float* gwp, int accumulate, void* ws, size_t ws_bytes, gdn_stream_t s);
 /* F.interpolate(size=(Ho,Wo), mode='bilinear', align_corners=False), generator.py:244: y (+)= resize(x) */
 int gdn_bilinear_fwd(const float* x, float* y, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s);
 int gdn_bilinear_bwd(const float* dy, float* dx, int B, int Hi, int Wi, int Ho, int Wo, int C, int accumulate, gdn_stream_t s);

@@ -750,3 +750,38 @@ def test_srgand(golden):
     sd = D.state_dict()
     for k, v in g["buffers_after"].items():
         assert rel_err(sd[k], v) < 1e-4, (k, rel_err(sd[k], v))
+
+
+@pytest.mark.parametrize("with_skip", [True, False])
+def test_generator_head_tap_planes(with_skip):
+    """engine.op_upsample_skip_final (final 3x3 conv's channel reduction hoisted in front of the bicubic x2 / bilinear skip resize: no 64-channel
+    full-resolution tensor) against the unfused chain up2 -> (+ resize(s)) -> conv3x3 on the same kernels, and against ATen in float64: output and
+    all gradients.  Exact in real arithmetic; asserted at 2e-5 (another fp32 summation order)."""
+    import torch.nn.functional as F
+    from gan_danet_b200 import engine as E
+    g = torch.Generator().manual_seed(31)
+    B, H, W, C = 2, 12, 20, 64
+    u = torch.randn(B, H, W, C, generator=g).to(DEV)
+    s = torch.randn(B, H // 2, W // 2, C, generator=g).to(DEV) if with_skip else None
+    w = (0.1 * torch.randn(1, C, 3, 3, generator=g)).to(DEV)
+    b = torch.randn(1, generator=g).to(DEV)
+    r = torch.randn(B, 2 * H, 2 * W, 1, generator=g).to(DEV)
+    tape = E.Tape()
+    uv, sv, wv, bv = E.Var(u), (E.Var(s) if with_skip else None), E.Var(w), E.Var(b)
+    assert E.head_tap_planes_ok(uv, sv, wv)
+    y = E.op_upsample_skip_final(tape, uv, sv, wv, bv)
+    y.g = r.clone()
+    tape.backward()
+    torch.cuda.synchronize()
+    ud, wd, bd = (t.detach().cpu().double().requires_grad_(True) for t in (u, w, b))
+    x2 = F.interpolate(ud.permute(0, 3, 1, 2), scale_factor=2, mode="bicubic", align_corners=False)
+    sd = None
+    if with_skip:
+        sd = s.detach().cpu().double().requires_grad_(True)
+        x2 = x2 + F.interpolate(sd.permute(0, 3, 1, 2), size=(2 * H, 2 * W), mode="bilinear", align_corners=False)
+    ref = F.conv2d(x2, wd, bd, padding=1).permute(0, 2, 3, 1)
+    (ref * r.cpu().double()).sum().backward()
+    assert rel_err(y.t, ref) < 2e-5, rel_err(y.t, ref)
+    assert rel_err(uv.g, ud.grad) < 2e-5 and rel_err(wv.g, wd.grad) < 2e-5 and rel_err(bv.g, bd.grad) < 2e-5
+    if with_skip:
+        assert rel_err(sv.g, sd.grad) < 2e-5
