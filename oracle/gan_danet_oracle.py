@@ -29,8 +29,8 @@ states the algorithm rather than delegating it.  Convolutions use
 Pinning: the reference holds no tests or golden vectors for this path (SURVEY
 §4, §8c).  The oracle is pinned against outputs of the *reference itself*
 imported in the build container (``oracle/make_golden.py`` -> fixtures under
-``tests/golden/``; ``tests/test_oracle_vs_reference.py`` re-checks live when
-``/root/reference`` is present).
+``tests/golden/``; ``tests/test_oracle_golden.py`` checks the oracle against them and
+re-checks live against the reference when ``/root/reference`` is present).
 
 Everything works in float32 or float64 (pass double tensors).
 """
