@@ -148,44 +148,50 @@ def qpam(x: Tensor, sd: Dict[str, Tensor], prefix: str, f: Formats) -> Tensor:
 
 
 def generator_forward(sd: Dict[str, Tensor], x: Tensor, f: Formats, training: bool = True, buffers_out: Optional[Dict[str, Tensor]] = None,
-                      taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
-    """``gan_danet_oracle.generator_forward`` with the product mode's rounding points (see the module docstring)."""
+                      taps: Optional[Dict[str, Tensor]] = None, fmt_for=None) -> Tensor:
+    """``gan_danet_oracle.generator_forward`` with the product mode's rounding points (see the module docstring).
+    ``fmt_for(name) -> Formats`` overrides the formats per convolution (names: initial, dense{b}.{l}, pam{b}, fuse{b}, trans{b}, up0, up1, adjust{i}):
+    which layers' operand rounding costs what (tools/precision_bisect.py --layers)."""
     blocks, layers, has_attn = O.generator_structure(sd)
+    f0 = f
+
+    def fm(name):
+        return f0 if fmt_for is None else fmt_for(name)
 
     def tap(name, t):
         if taps is not None:
             taps[name] = t
         return t
 
-    x = qconv(x, sd["initial.0.weight"], None, f, padding=1)
+    x = qconv(x, sd["initial.0.weight"], None, fm("initial"), padding=1)
     x = tap("initial", O.relu(O._bn(sd, "initial.1.", x, training, buffers_out)))
     skips: List[Tensor] = []
     for bi in range(blocks):
         for li in range(layers):
             p = f"dense_blocks.{bi}.layers.{li}."
             y = O.relu(O._bn(sd, p + "bn.", x, training, buffers_out))
-            y = qconv(y, sd[p + "conv.weight"], sd[p + "conv.bias"], f, padding=1)
+            y = qconv(y, sd[p + "conv.weight"], sd[p + "conv.bias"], fm(f"dense{bi}.{li}"), padding=1)
             x = torch.cat([x, y], dim=1)
         tap(f"dense{bi}", x)
         if has_attn:
             a = f"attention_modules.{bi}."
-            pos = tap(f"pam{bi}", qpam(x, sd, a + "position_attention.", f))
+            pos = tap(f"pam{bi}", qpam(x, sd, a + "position_attention.", fm(f"pam{bi}")))
             ch = tap(f"cam{bi}", O.cam(x, sd[a + "channel_attention.gamma"]))
-            fz = qconv(torch.cat([pos, ch], dim=1), sd[a + "fuse.0.weight"], None, f, padding=1)
+            fz = qconv(torch.cat([pos, ch], dim=1), sd[a + "fuse.0.weight"], None, fm(f"fuse{bi}"), padding=1)
             x = O.relu(O._bn(sd, a + "fuse.1.", fz, training, buffers_out))
         skips.append(tap(f"skip{bi}", x))
         if bi != blocks - 1:
             t = f"transition_layers.{bi}.layer."
             y = O.relu(O._bn(sd, t + "0.", x, training, buffers_out))
-            x = tap(f"trans{bi}", qconv(y, sd[t + "2.weight"], sd[t + "2.bias"], f))
-    x = qconv(x, sd["upsample.0.weight"], None, f, padding=1)
+            x = tap(f"trans{bi}", qconv(y, sd[t + "2.weight"], sd[t + "2.bias"], fm(f"trans{bi}")))
+    x = qconv(x, sd["upsample.0.weight"], None, fm("up0"), padding=1)
     x = O.bicubic_up2(O.relu(O._bn(sd, "upsample.1.", x, training, buffers_out)))
-    x = qconv(x, sd["upsample.4.weight"], None, f, padding=1)
+    x = qconv(x, sd["upsample.4.weight"], None, fm("up1"), padding=1)
     x = O.bicubic_up2(O.relu(O._bn(sd, "upsample.5.", x, training, buffers_out)))
     tap("up2", x)
     s = None
     for i, feat in enumerate(reversed(skips)):          # projections hoisted in front of the (linear) resize, as on the device
-        pz = qconv(feat, sd[f"channel_adjust.{i}.weight"], None, f)
+        pz = qconv(feat, sd[f"channel_adjust.{i}.weight"], None, fm(f"adjust{i}"))
         s = pz if s is None else s + pz
     if s is not None:
         x = x + O.bilinear_to(s, (x.shape[2], x.shape[3]))

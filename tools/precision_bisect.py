@@ -2,7 +2,7 @@
 (tests/golden/generator_cin46_8x16.pt), one rounding point at a time.  It answers which operand format costs what in the tensor-core
 product mode without a GPU.  Test infrastructure (imports oracle/).
 
-    python tools/precision_bisect.py [--json out.json]
+    python tools/precision_bisect.py [--layers] [--json out.json]
 """
 import json
 import os
@@ -34,11 +34,11 @@ def seeded_state(seed, gamma):
     return {k: v.double() for k, v in G.state_dict().items()}, [k for k, _ in G.named_parameters()]
 
 
-def run(g, f):
+def run(g, f, fmt_for=None):
     sd, pnames = seeded_state(g["seed"], g["gamma"])
     sdp = {k: (v.clone().requires_grad_(True) if k in pnames else v) for k, v in sd.items()}
     x = g["x"].double().requires_grad_(True)
-    y = Q.generator_forward(sdp, x, f)
+    y = Q.generator_forward(sdp, x, f, fmt_for=fmt_for)
     grads = torch.autograd.grad((y * g["r"].double()).sum(), [x] + [sdp[k] for k in pnames], allow_unused=True)
     gd = {k: (t if t is not None else torch.zeros_like(sdp[k])) for k, t in zip(pnames, grads[1:])}
     return y.detach(), grads[0], gd
@@ -69,5 +69,15 @@ if __name__ == "__main__":
         res = summarise(g, *run(g, f))
         out[name] = res
         print(f"{name:70s} y {res['y']:.2e}  dx {res['dx']:.2e}  grads {res['grads_whole_vector']:.2e}", flush=True)
+    if "--layers" in sys.argv:
+        # which layer group's bf16 operand rounding costs what: the product mode's formats on ONE group of convolutions, exact elsewhere
+        groups = {"initial conv": lambda n: n == "initial", "dense-layer convs": lambda n: n.startswith("dense"), "PAM (projections + core)": lambda n: n.startswith("pam"),
+                  "fuse convs": lambda n: n.startswith("fuse"), "transition convs": lambda n: n.startswith("trans"), "upsample conv 0": lambda n: n == "up0",
+                  "upsample conv 1": lambda n: n == "up1", "skip projections": lambda n: n.startswith("adjust")}
+        ex, pr = Q.Formats.exact(), Q.Formats()
+        for name, pred in groups.items():
+            res = summarise(g, *run(g, pr, fmt_for=lambda n, pred=pred: pr if pred(n) else ex))
+            out["only " + name] = res
+            print(f"{'only ' + name:70s} y {res['y']:.2e}  dx {res['dx']:.2e}  grads {res['grads_whole_vector']:.2e}", flush=True)
     if "--json" in sys.argv:
         json.dump(out, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
