@@ -547,6 +547,11 @@ static_assert(B_COUNT * 8 <= 256, "barrier area");
 // serialisation Y_{t+1} after dS_t cost more (2.76 -> 3.44 ms per backward) than the operand reads it saved.
 constexpr uint32_t COL_X = 0, COL_Y = 128, COL_SMALL = 256, COL_BIG = 288;
 template <int MODE> struct BwdCols { static constexpr uint32_t QK = MODE == 0 ? 384 : 480; };
+#ifndef GDN_PAM_BWD_POLY
+#define GDN_PAM_BWD_POLY 0
+#endif
+constexpr bool BWD_POLY = GDN_PAM_BWD_POLY != 0;      // one exponential in four on the FMA pipe as in the forward kernel: measured SLOWER here in both rounds
+                                                       // (round 2, TMEM-resident operands: 2.99 -> 3.04 ms per backward) -- the exp units are not this kernel's limiter
 
 
 // kind::f16 instruction descriptor for bf16 operands (see conv_tc.cu): b_mn = 1 makes B MN-major
@@ -798,7 +803,7 @@ pam_flash_bwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_con
         tmem_ld32(tmem + lane_addr + COL_X + b * TI + col0, x);
         // X already is S - lse (the operands carry -lse and 1 in two spare columns of the logit product): P = exp(X) <= 1
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = ex2(x[i] * LOG2E);       // (the forward's one-in-four polynomial exp2 measured 2 % slower here)
+        for (int i = 0; i < 32; ++i) x[i] = (BWD_POLY && (i & 3) == 3) ? ex2_poly(x[i] * LOG2E) : ex2(x[i] * LOG2E);
         if (h == 0) { mbar_wait(bar(B_YFULL + b), (t >> 1) & 1); tc_fence_after(); }
         float y[32];
         tmem_ld32(tmem + lane_addr + COL_Y + b * TI + col0, y);
