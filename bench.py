@@ -288,6 +288,8 @@ def run_ours(args):
     step_fn, graph_info = tr.train_step, None
     if args.graph:
         from gan_danet_b200.trainer import GraphedTrainStep
+        E.release_buffers()                  # eager-pass workspaces / operand buffers are re-created inside the graph's pool
+        torch.cuda.empty_cache()             # hand the eager passes' cached blocks back before the graph takes its private pool (~60 GB of 180)
         gstep = GraphedTrainStep(tr, *resident, warmup=1)
         step_fn = gstep
         graph_info = {"captured": True, "c_abi_calls_per_step": gstep.launches_per_step}
@@ -429,6 +431,7 @@ def run_ours(args):
                 "config": {"workload": workload_name(args, h, w), "global_batch": world * B, "parallelism": f"dp{world}", "conv": args.conv_precision,
                            "pam": f"fused tcgen05 flash forward + backward ({args.pam_precision})" if args.pam_precision != "fp32" else "fp32 engine",
                            "cuda_graph": graph_info, "eager_ms_per_step": ms_eager, "aux_transport": aux_dtype,
+                           "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
                            "l2": "inputs larger than L2 (the aux stack alone is %.0f MB per step)" % (aux_h.numel() * aux_h.element_size() / 1e6)},
                 "clocks": clk, "gpu_launches": launches,
                 "e2e": {"value": value_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(last.numel() * 4),
