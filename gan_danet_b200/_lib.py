@@ -110,6 +110,9 @@ SIGNATURES = {
     "gdn_thin_conv_expand_p": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "gdn_thin_conv_reduce": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_thin_conv_reduce_gated": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "gdn_thin_conv_tap_l1_supported": (_i, [_i, _i, _i]),
+    "gdn_thin_conv_tap_l1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _f, _vp, _sz, _vp]),
+    "gdn_thin_conv_tap_dgrad": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_thin_conv_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "gdn_thin_conv_wgrad": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "gdn_colstats_ws_bytes": (_sz, [_ll, _i]),
@@ -117,6 +120,11 @@ SIGNATURES = {
     "gdn_bn_finalize": (_i, [_vp, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gdn_bn_eval_coeffs": (_i, [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     "gdn_affine_act": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _vp, _i, _f, _vp]),
+    "gdn_stat_fused_ws_bytes": (_sz, [_ll, _i]),
+    "gdn_stat_fused_counters": (_i, []),
+    "gdn_bn_stats": (_i, [_vp, _i, _i, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gdn_colsums_f": (_i, [_vp, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gdn_bn_bwd_reduce_f": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "gdn_bn_bwd_reduce": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp]),
     "gdn_bn_bwd_apply": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
     "gdn_bn_bwd_apply16": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),

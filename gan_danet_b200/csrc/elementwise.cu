@@ -19,13 +19,83 @@ static StatPlan stat_plan(long long M) {
   return p;
 }
 
+
+// ---- single-launch statistics (round 2): the blocks of a colreduce launch finish the reduction themselves instead of handing their partial
+// rows to colreduce_final_kernel + bn_finalize_kernel (+ sums_to_float_kernel): 70 BatchNorm passes per step were three to four launches each,
+// the follow-ups latency-bound (14 + 6 + 4 us).  Two-level "last block done" scheme, fixed membership and fixed summation order at both levels
+// => still bitwise deterministic: blocks are grouped by kStatGroup; the last block of a group to arrive (ticket counter) adds the group's
+// partial rows in block order into a group row; the last group to finish adds the group rows in group order and finalises.  The counters
+// are zero on entry and restored to zero by the finishing block (safe under CUDA-graph replay).
+constexpr int kStatGroup = 16;
+struct StatTail {
+  unsigned* counters;        // [1 + groups], zero on entry; nullptr: no tail (two-launch path)
+  double* group_partial;     // [groups][2C]
+  double* out;               // [2C] final sums (may be nullptr)
+  float* fout;               // [2C] the same as float (BatchNorm backward: dbias | dweight), may be nullptr
+  int bn;                    // != 0: BatchNorm2d train-mode finalize
+  long long M;
+  const float* weight; const float* bias; float eps, momentum;
+  float* running_mean; float* running_var; long long* num_batches_tracked;
+  float* mean; float* invstd; float* scale; float* shift;
+};
+
+__device__ __forceinline__ void bn_finalize_channel(const StatTail& t, int c, double s0, double s1) {
+  const double m = s0 / (double)t.M;
+  double var = s1 / (double)t.M - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)t.eps));
+  const float w = t.weight ? t.weight[c] : 1.f, b = t.bias ? t.bias[c] : 0.f;
+  const float sc = w * is;
+  t.mean[c] = (float)m; t.invstd[c] = is; t.scale[c] = sc; t.shift[c] = b - (float)m * sc;
+  if (t.running_mean) t.running_mean[c] = (1.f - t.momentum) * t.running_mean[c] + t.momentum * (float)m;
+  if (t.running_var) {
+    const double unbiased = t.M > 1 ? var * ((double)t.M / (double)(t.M - 1)) : var;
+    t.running_var[c] = (1.f - t.momentum) * t.running_var[c] + t.momentum * (float)unbiased;
+  }
+}
+
+// Called by every thread of every block after the block's partial row has been written.
+__device__ void stat_tail(const StatTail& t, const double* partial, int C) {
+  if (t.counters == nullptr) return;
+  __shared__ unsigned s_last;
+  const int n2 = 2 * C, nblocks = gridDim.x;
+  const int groups = (nblocks + kStatGroup - 1) / kStatGroup, g = blockIdx.x / kStatGroup;
+  const int b0 = g * kStatGroup, b1 = (b0 + kStatGroup < nblocks) ? b0 + kStatGroup : nblocks;
+  __threadfence();                       // this thread's partial sums are visible device-wide before the ticket is taken
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&t.counters[1 + g], 1u) == (unsigned)(b1 - b0 - 1)) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int j = threadIdx.x; j < n2; j += blockDim.x) {
+    double a = 0.0;
+    for (int b = b0; b < b1; ++b) a += __ldcg(partial + (size_t)b * n2 + j);
+    t.group_partial[(size_t)g * n2 + j] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&t.counters[0], 1u) == (unsigned)(groups - 1)) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int q = 0; q < groups; ++q) { s0 += __ldcg(t.group_partial + (size_t)q * n2 + c); s1 += __ldcg(t.group_partial + (size_t)q * n2 + C + c); }
+    if (t.out) { t.out[c] = s0; t.out[C + c] = s1; }
+    if (t.fout) { t.fout[c] = (float)s0; t.fout[C + c] = (float)s1; }
+    if (t.bn) bn_finalize_channel(t, c, s0, s1);
+  }
+  if (threadIdx.x == 0 && t.bn && t.num_batches_tracked) *t.num_batches_tracked += 1;
+  for (int i = threadIdx.x; i <= groups; i += blockDim.x) t.counters[i] = 0u;
+}
+
 // MODE 0: (sum x, sum x^2).  MODE 1: g = dy*act'(x*scale+shift): (sum g, sum g*xhat).
 template <int MODE>
 __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ dy, int dy_pitch,
                                                         long long M, int C, long long rows_per_block,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
-                                                        int act, float slope, double* __restrict__ partial) {
+                                                        int act, float slope, double* __restrict__ partial, const StatTail tail) {
   __shared__ double sh[2][8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long r0 = blockIdx.x * rows_per_block;
@@ -63,6 +133,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict_
     }
     __syncthreads();
   }
+  stat_tail(tail, partial, C);
 }
 
 
@@ -74,7 +145,7 @@ __global__ void __launch_bounds__(256) colreduce_v4_kernel(const float* __restri
                                                            long long M, int C, long long rows_per_block,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ scale, const float* __restrict__ shift,
-                                                           int act, float slope, double* __restrict__ partial) {
+                                                           int act, float slope, double* __restrict__ partial, const StatTail tail) {
   __shared__ double sh[256][9];
   const int Cv = C >> 2;
   const long long r0 = blockIdx.x * rows_per_block;
@@ -144,6 +215,7 @@ __global__ void __launch_bounds__(256) colreduce_v4_kernel(const float* __restri
     }
     __syncthreads();
   }
+  stat_tail(tail, partial, C);
 }
 
 // out[j] = sum_b partial[b][j], j < n2.  One warp per column group of 8: lanes = 32 interleaved slices of the block dimension, four
@@ -327,14 +399,19 @@ __global__ void __launch_bounds__(256) scale_dev_kernel(const float* __restrict_
 
 template <int MODE>
 static int colreduce(const float* x, int x_pitch, const float* dy, int dy_pitch, long long M, int C, const float* mean, const float* invstd,
-                     const float* scale, const float* shift, int act, float slope, double* out, void* ws, cudaStream_t st) {
+                     const float* scale, const float* shift, int act, float slope, double* out, void* ws, cudaStream_t st, StatTail tail = StatTail{}) {
   StatPlan pl = stat_plan(M);
   double* partial = reinterpret_cast<double*>(ws);
+  if (tail.counters) {            // single launch: group rows and ticket counters follow the partial rows in the workspace
+    tail.group_partial = partial + (size_t)pl.blocks * 2 * C;
+    tail.out = out;
+  }
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool v4 = C % 4 == 0 && x_pitch % 4 == 0 && al(x) && (MODE == 0 || (dy_pitch % 4 == 0 && al(dy) && al(mean) && al(invstd) && al(scale) && al(shift)));
-  if (v4) colreduce_v4_kernel<MODE><<<pl.blocks, 256, 0, st>>>(x, x_pitch, dy, dy_pitch, M, C, pl.rows_per_block, mean, invstd, scale, shift, act, slope, partial);
-  else colreduce_kernel<MODE><<<pl.blocks, 256, 0, st>>>(x, x_pitch, dy, dy_pitch, M, C, pl.rows_per_block, mean, invstd, scale, shift, act, slope, partial);
+  if (v4) colreduce_v4_kernel<MODE><<<pl.blocks, 256, 0, st>>>(x, x_pitch, dy, dy_pitch, M, C, pl.rows_per_block, mean, invstd, scale, shift, act, slope, partial, tail);
+  else colreduce_kernel<MODE><<<pl.blocks, 256, 0, st>>>(x, x_pitch, dy, dy_pitch, M, C, pl.rows_per_block, mean, invstd, scale, shift, act, slope, partial, tail);
   GDN_CHECK_LAUNCH();
+  if (tail.counters) return GDN_OK;
   colreduce_final_kernel<<<(unsigned)cdiv(2 * C, 8), 256, 0, st>>>(partial, pl.blocks, 2 * C, out);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
@@ -357,6 +434,36 @@ extern "C" int gdn_bn_finalize(const double* sums, long long M, int C, const flo
   bn_finalize_kernel<<<(unsigned)cdiv(C, 128), 128, 0, as_stream(s)>>>(sums, M, C, weight, bias, eps, momentum, running_mean, running_var, mean, invstd, scale, shift);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
+}
+extern "C" size_t gdn_stat_fused_ws_bytes(long long M, int C) {
+  StatPlan pl = stat_plan(M > 0 ? M : 1);
+  return ((size_t)pl.blocks + (size_t)cdiv(pl.blocks, kStatGroup)) * 2 * (size_t)C * sizeof(double);
+}
+extern "C" int gdn_stat_fused_counters(void) { return 1 + (int)cdiv(kMaxStatBlocks, kStatGroup); }
+extern "C" int gdn_bn_stats(const float* x, int pitch, int c0, long long M, int C, const float* weight, const float* bias, float eps, float momentum,
+                            float* running_mean, float* running_var, long long* num_batches_tracked, float* mean, float* invstd, float* scale,
+                            float* shift, void* ws, unsigned* counters, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && ws && counters && M > 0 && C > 0 && pitch >= c0 + C && mean && invstd && scale && shift);
+  StatTail t = {};
+  t.counters = counters; t.bn = 1; t.M = M; t.weight = weight; t.bias = bias; t.eps = eps; t.momentum = momentum;
+  t.running_mean = running_mean; t.running_var = running_var; t.num_batches_tracked = num_batches_tracked;
+  t.mean = mean; t.invstd = invstd; t.scale = scale; t.shift = shift;
+  return colreduce<0>(x + c0, pitch, nullptr, 0, M, C, nullptr, nullptr, nullptr, nullptr, 0, 0.f, nullptr, ws, as_stream(s), t);
+}
+extern "C" int gdn_colsums_f(const float* x, int pitch, int c0, long long M, int C, double* sums, float* fsums, void* ws, unsigned* counters, gdn_stream_t s) {
+  GDN_CHECK_ARG(x && ws && counters && M > 0 && C > 0 && pitch >= c0 + C && (sums || fsums));
+  StatTail t = {};
+  t.counters = counters; t.fout = fsums;
+  return colreduce<0>(x + c0, pitch, nullptr, 0, M, C, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, ws, as_stream(s), t);
+}
+extern "C" int gdn_bn_bwd_reduce_f(const float* dy, int dy_pitch, int dy_c0, const float* x, int x_pitch, int x_c0, long long M, int C,
+                                   const float* mean, const float* invstd, const float* scale, const float* shift, int act, float slope,
+                                   double* sums, float* fsums, void* ws, unsigned* counters, gdn_stream_t s) {
+  GDN_CHECK_ARG(dy && x && mean && invstd && scale && shift && sums && ws && counters && M > 0 && C > 0);
+  GDN_CHECK_ARG(dy_pitch >= dy_c0 + C && x_pitch >= x_c0 + C);
+  StatTail t = {};
+  t.counters = counters; t.fout = fsums;
+  return colreduce<1>(x + x_c0, x_pitch, dy + dy_c0, dy_pitch, M, C, mean, invstd, scale, shift, act, slope, sums, ws, as_stream(s), t);
 }
 extern "C" int gdn_bn_eval_coeffs(const float* weight, const float* bias, const float* running_mean, const float* running_var, float eps,
                                   int C, float* scale, float* shift, gdn_stream_t s) {

@@ -86,13 +86,93 @@ __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ S
       if (act == GDN_ACT_RELU) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
       else if (act == GDN_ACT_LRELU) { acc.x = fmaxf(acc.x, acc.x * slope); acc.y = fmaxf(acc.y, acc.y * slope); acc.z = fmaxf(acc.z, acc.z * slope); acc.w = fmaxf(acc.w, acc.w * slope); }
       if (res) { const float4 rr = *reinterpret_cast<const float4*>(res + (p + i) * res_pitch + c); acc.x += rr.x; acc.y += rr.y; acc.z += rr.z; acc.w += rr.w; }
-      *reinterpret_cast<float4*>(V + (p + i) * v_pitch + c) = acc;
+      if (V) *reinterpret_cast<float4*>(V + (p + i) * v_pitch + c) = acc;
       if (V16) {
         const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
         *reinterpret_cast<uint2*>(V16 + (p + i) * g.C + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
       }
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------- L1 term of a tapped 1 -> C conv + ReLU
+// partial[block] = sum over pixels and channels of | relu(conv(Sa))[p][c] - relu(conv(Sb))[p][c] |   (3x3, stride 1, pad 1)
+// The perceptual loss taps relu1_1 (losses.py:60-72 with feature_layers containing 1): conv1_1 has ONE input channel here (the channel-summed
+// weight), so both 64-channel maps are 9 FMAs per element away from the two single-channel images.  Recomputing them costs less than
+// reading them: the fp32 maps (2 x 1.07 GB at 256x512, batch 32) are never written, and the L1 pass (2.1 GB read, 1 GB gradient written)
+// does not exist.  Same FMA order as expand_kernel => the recomputed features are bitwise the ones expand_kernel would have stored.
+template <int PX>
+__global__ void __launch_bounds__(256, 2) l1_fields_kernel(const float* __restrict__ Sa, const float* __restrict__ Sb, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, Geo g, double* __restrict__ partial) {
+  constexpr int NC = PX + 2;
+  const int lanes = g.C >> 2;
+  const int c = (threadIdx.x % lanes) << 2;
+  float2 w01[9], w23[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    w01[k] = make_float2(__ldg(w + (c + 0) * 9 + k), __ldg(w + (c + 1) * 9 + k));
+    w23[k] = make_float2(__ldg(w + (c + 2) * 9 + k), __ldg(w + (c + 3) * 9 + k));
+  }
+  const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int gx = g.Wv / PX;
+  const int total = g.B * g.Hv * gx;
+  const int gpp = 256 / lanes;
+  float acc = 0.f; double dacc = 0.0; int cnt = 0;
+  for (int gi = blockIdx.x * gpp + threadIdx.x / lanes; gi < total; gi += gridDim.x * gpp) {
+    const int xg = gi % gx, r = gi / gx, y = r % g.Hv, b = r / g.Hv;
+    const int x0 = xg * PX;
+    const size_t fo = (size_t)b * g.Hs * g.Ws;
+    const int sx0 = x0 - 1, sy0 = y - 1;
+    float sa[3][NC], sb[3][NC];
+    if (sy0 >= 0 && sy0 + 2 < g.Hs && sx0 >= 0 && sx0 + NC <= g.Ws) {
+      const size_t o0 = fo + (size_t)sy0 * g.Ws + sx0;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) { sa[kh][j] = __ldg(Sa + o0 + kh * g.Ws + j); sb[kh][j] = __ldg(Sb + o0 + kh * g.Ws + j); }
+    } else {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int sy = sy0 + kh;
+        const bool rowok = sy >= 0 && sy < g.Hs;
+        const size_t ro = fo + (size_t)(rowok ? sy : 0) * g.Ws;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const int sx = sx0 + j;
+          const bool ok = rowok && sx >= 0 && sx < g.Ws;
+          sa[kh][j] = ok ? __ldg(Sa + ro + sx) : 0.f; sb[kh][j] = ok ? __ldg(Sb + ro + sx) : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+      float2 a01 = make_float2(bv.x, bv.y), a23 = make_float2(bv.z, bv.w), b01 = a01, b23 = a23;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float2 s2 = make_float2(sa[kh][i + kw], sa[kh][i + kw]), t2 = make_float2(sb[kh][i + kw], sb[kh][i + kw]);
+          a01 = __ffma2_rn(s2, w01[kh * 3 + kw], a01); a23 = __ffma2_rn(s2, w23[kh * 3 + kw], a23);
+          b01 = __ffma2_rn(t2, w01[kh * 3 + kw], b01); b23 = __ffma2_rn(t2, w23[kh * 3 + kw], b23);
+        }
+      acc += fabsf(fmaxf(a01.x, 0.f) - fmaxf(b01.x, 0.f)) + fabsf(fmaxf(a01.y, 0.f) - fmaxf(b01.y, 0.f));
+      acc += fabsf(fmaxf(a23.x, 0.f) - fmaxf(b23.x, 0.f)) + fabsf(fmaxf(a23.y, 0.f) - fmaxf(b23.y, 0.f));
+    }
+    if (++cnt == 4) { dacc += (double)acc; acc = 0.f; cnt = 0; }
+  }
+  dacc += (double)acc;
+  __shared__ double sh[32];
+  const double tot = block_sum<double>(dacc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+// loss[0] (+)= coef * sum_b partial[b]   (one block, fixed order: deterministic)
+__global__ void __launch_bounds__(256) l1_fields_finish_kernel(const double* __restrict__ partial, int nblocks, double coef, float* loss, int accumulate) {
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) a += partial[b];
+  a = block_sum<double>(a, sh);
+  if (threadIdx.x == 0) { const float v = (float)(coef * a); loss[0] = accumulate ? loss[0] + v : v; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------- reduce
@@ -103,11 +183,19 @@ __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ S
 // gradient of the 1 -> C conv: v = (q + pad - k) / stride when divisible.  Fixed summation order: deterministic.
 constexpr int RT_H = 16, RT_W = 32, R_MAXPIX = (RT_H + 2) * (RT_W + 2);
 
-template <int CPL>   // channels per lane: C = 8 * CPL
+// RECOMP (data gradient of a tapped 1 -> C conv + ReLU, stride 1, pad 1: VGG19 conv1_1 with the L1 term at relu1_1): neither the activation output
+// (the gate) nor the L1 term's gradient exists in memory; both are recomputed from the two single-channel fields Fa (generated) and Fb (target):
+//   f = relu(conv(F) + cbias),  dz[p][c] = (V[p][c] + gcoef * sign(fa - fb)) * [fa > 0]
+// in expand_kernel's FMA order, so gate and seed are bitwise what the stored maps would have given.
+constexpr int RF_H = RT_H + 4, RF_W = RT_W + 4;
+template <int CPL, bool RECOMP = false>   // channels per lane: C = 8 * CPL
 __global__ void __launch_bounds__(256, CPL <= 8 ? 2 : 1) reduce_kernel(const float* __restrict__ V, int v_pitch, const float* __restrict__ w, const float* __restrict__ bias,
                                                                        float* S, const float* res /* may alias S */, Geo g, int transposed, int tiles_x, int tiles_y,
-                                                                       const float* __restrict__ gate, int gate_pitch, float gate_slope) {
+                                                                       const float* __restrict__ gate, int gate_pitch, float gate_slope,
+                                                                       const float* __restrict__ Fa = nullptr, const float* __restrict__ Fb = nullptr,
+                                                                       const float* __restrict__ cbias = nullptr, float gcoef = 0.f) {
   __shared__ float Ts[9][R_MAXPIX + 4];
+  __shared__ float Fs[RECOMP ? 2 : 1][RECOMP ? RF_H * RF_W : 1];
   constexpr int NJ = CPL / 4;
   const int lane8 = threadIdx.x & 7, slot = threadIdx.x >> 3;   // 32 pixel slots per pass
   float wr[NJ][4][9];
@@ -153,9 +241,51 @@ __global__ void __launch_bounds__(256, CPL <= 8 ? 2 : 1) reduce_kernel(const flo
   const bool b2 = lane8 & 4, b1 = lane8 & 2, b0 = lane8 & 1;
   float4 cur[NJ], nxt[NJ];
   load(slot, cur);
+  const int fw = vx_n + 2;
+  float cb[NJ][4];
+  if (RECOMP) {
+    // the two fields' tile: rows vy_lo - 1 .. vy_lo + vy_n, columns vx_lo - 1 .. vx_lo + vx_n, zero outside the image (the convolution's padding)
+    const size_t fo = (size_t)b * g.Hs * g.Ws;
+    for (int idx = threadIdx.x; idx < (vy_n + 2) * fw; idx += 256) {
+      const int fy = vy_lo - 1 + idx / fw, fx = vx_lo - 1 + idx % fw;
+      const bool ok = fy >= 0 && fy < g.Hs && fx >= 0 && fx < g.Ws;
+      Fs[0][idx] = ok ? __ldg(Fa + fo + (size_t)fy * g.Ws + fx) : 0.f;
+      Fs[RECOMP ? 1 : 0][idx] = ok ? __ldg(Fb + fo + (size_t)fy * g.Ws + fx) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cb[j][e] = cbias ? __ldg(cbias + j * 32 + lane8 * 4 + e) : 0.f;
+    __syncthreads();
+  }
   for (int ps = 0; ps < passes; ++ps) {
     const int i = ps * 32 + slot;
     load(i + 32, nxt);                      // next pass in flight while this one is reduced (i + 32 >= n loads nothing)
+    if (RECOMP) {
+      const int ry = i / vx_n, rx = i - ry * vx_n;
+      const int vy = vy_lo + ry, vx = vx_lo + rx;
+      if (i < n && vy >= 0 && vy < g.Hv && vx >= 0 && vx < g.Wv) {
+        float2 win[9];                      // (generated, target) field values under the nine taps of this pixel
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) win[kh * 3 + kw] = make_float2(Fs[0][(ry + kh) * fw + rx + kw], Fs[RECOMP ? 1 : 0][(ry + kh) * fw + rx + kw]);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          float cv[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f = make_float2(cb[j][e], cb[j][e]);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) f = __ffma2_rn(win[k], make_float2(wr[j][e][k], wr[j][e][k]), f);
+            const float d = fmaxf(f.x, 0.f) - fmaxf(f.y, 0.f);
+            const float seed = d > 0.f ? gcoef : (d < 0.f ? -gcoef : 0.f);
+            cv[e] = f.x > 0.f ? cv[e] + seed : 0.f;
+          }
+          cur[j] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        }
+      }
+    }
     // nine per-tap dot products over this lane's channels: taps in pairs on the packed fp32x2 FMA (5 instead of 9 instructions per channel)
     float2 t2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     float t8s = 0.f;
@@ -415,7 +545,7 @@ extern "C" int gdn_thin_conv_expand_p(const float* s_in, const float* w, const f
                                       int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int flip, int act, float slope, uint16_t* v16, gdn_stream_t st) {
   GDN_CHECK_ARG(((uintptr_t)v16 & 7) == 0);
   __nv_bfloat16* V16 = reinterpret_cast<__nv_bfloat16*>(v16);
-  GDN_CHECK_ARG(s_in && w && v_out && thin_ok(C) && v_pitch >= C && v_pitch % 4 == 0 && ((uintptr_t)v_out & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0));
+  GDN_CHECK_ARG(s_in && w && (v_out || (v16 && !res)) && thin_ok(C) && (!v_out || (v_pitch >= C && v_pitch % 4 == 0 && ((uintptr_t)v_out & 15) == 0)) && (!bias || ((uintptr_t)bias & 15) == 0));
   GDN_CHECK_ARG(!res || (res_pitch % 4 == 0 && ((uintptr_t)res & 15) == 0));
   GDN_CHECK_ARG((long long)B * Hv * Wv < (1ll << 31) && stride >= 1);
   Geo g = {B, Hv, Wv, C, Hs, Ws, stride, pad};
@@ -452,6 +582,38 @@ extern "C" int gdn_thin_conv_reduce_gated(const float* v_in, int v_pitch, const 
   if (C == 32) reduce_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y, gate, gate_pitch, gate_slope);
   else if (C == 64) reduce_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y, gate, gate_pitch, gate_slope);
   else reduce_kernel<16><<<(unsigned)blocks, 256, 0, s>>>(v_in, v_pitch, w, bias, s_out, res, g, transposed, tiles_x, tiles_y, gate, gate_pitch, gate_slope);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
+extern "C" int gdn_thin_conv_tap_l1_supported(int C, int H, int W) { return thin_ok(C) && C <= 64 && W % 4 == 0 && H > 0; }
+extern "C" int gdn_thin_conv_tap_l1(const float* fa, const float* fb, const float* w, const float* cbias, int B, int H, int W, int C, float* loss, int loss_accumulate,
+                                    float scale, void* ws, size_t ws_bytes, gdn_stream_t st) {
+  GDN_CHECK_ARG(fa && fb && w && loss && ws && gdn_thin_conv_tap_l1_supported(C, H, W) && (!cbias || ((uintptr_t)cbias & 15) == 0));
+  GDN_CHECK_ARG((long long)B * H * W < (1ll << 31));
+  Geo g = {B, H, W, C, H, W, 1, 1};
+  const int gpp = 256 / (C / 4);
+  long long blocks = cdiv((long long)B * H * (W / 4), gpp);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (ws_bytes < (size_t)blocks * sizeof(double)) { set_error("gdn_thin_conv_tap_l1: workspace too small"); return GDN_EWORKSPACE; }
+  cudaStream_t s = as_stream(st);
+  l1_fields_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(fa, fb, w, cbias, g, reinterpret_cast<double*>(ws));
+  GDN_CHECK_LAUNCH();
+  l1_fields_finish_kernel<<<1, 256, 0, s>>>(reinterpret_cast<const double*>(ws), (int)blocks, (double)scale / ((double)B * H * W * C), loss, loss_accumulate);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+extern "C" int gdn_thin_conv_tap_dgrad(const float* dy, int dy_pitch, const float* fa, const float* fb, const float* w, const float* cbias, float gcoef, float* s_out,
+                                       const float* res, int B, int H, int W, int C, gdn_stream_t st) {
+  GDN_CHECK_ARG(dy && fa && fb && w && s_out && gdn_thin_conv_tap_l1_supported(C, H, W) && dy_pitch >= C && dy_pitch % 4 == 0 && ((uintptr_t)dy & 15) == 0);
+  GDN_CHECK_ARG((long long)B * H * W < (1ll << 31));
+  Geo g = {B, H, W, C, H, W, 1, 1};
+  const int tiles_x = (int)cdiv(W, RT_W), tiles_y = (int)cdiv(H, RT_H);
+  const long long blocks = (long long)B * tiles_x * tiles_y;
+  GDN_CHECK_ARG(blocks < (1ll << 31));
+  cudaStream_t s = as_stream(st);
+  if (C == 32) reduce_kernel<4, true><<<(unsigned)blocks, 256, 0, s>>>(dy, dy_pitch, w, nullptr, s_out, res, g, 1, tiles_x, tiles_y, nullptr, 0, 0.f, fa, fb, cbias, gcoef);
+  else reduce_kernel<8, true><<<(unsigned)blocks, 256, 0, s>>>(dy, dy_pitch, w, nullptr, s_out, res, g, 1, tiles_x, tiles_y, nullptr, 0, 0.f, fa, fb, cbias, gcoef);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

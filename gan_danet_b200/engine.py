@@ -76,6 +76,20 @@ def workspace(name: str, nbytes: int, device) -> Tensor:
     return buf
 
 
+_stat_counters: Dict[Tuple[int, int], Tensor] = {}
+fused_stat_tail: bool = os.environ.get("GDN_FUSED_STATS", "1") != "0"   # single-launch BatchNorm statistics / backward reductions (gdn_bn_stats, gdn_bn_bwd_reduce_f)
+
+
+def stat_counters(device) -> Tensor:
+    """Ticket counters of the single-launch reductions: zero on entry, restored to zero by the kernel; one buffer per (device, stream)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, _raw_stream(idx) if _raw_stream is not None else torch.cuda.current_stream(device).cuda_stream)
+    buf = _stat_counters.get(key)
+    if buf is None:
+        buf = _stat_counters[key] = torch.zeros(L.load().gdn_stat_fused_counters(), dtype=torch.int32, device=device)
+    return buf
+
+
 def _timed(family: str, flops: float, fn: Callable[[], None], detail: str = "") -> None:
     """Runs ``fn`` (one C-ABI call); when bench.py collects timings, brackets it with CUDA events on the current stream."""
     if kernel_timing is None:
@@ -390,6 +404,8 @@ def wgrad_tc_raw(dyp: Packed, xp: Packed, out: Tensor, *, B: int, in_hw: Tuple[i
 
 
 thin_conv_enabled: bool = os.environ.get("GDN_THIN_CONV", "1") != "0"
+# relu1_1 of the perceptual loss recomputed from the single-channel images instead of stored (models/losses.py::_frozen_conv1_tap)
+vgg_tap1_recompute: bool = os.environ.get("GDN_VGG_TAP1_RECOMPUTE", "1") != "0"
 
 
 def _thin_kind(Cin: int, O: int, kh: int, kw: int, stride: int, x: Tensor, y: Tensor, act: int = ACT_NONE, bias=None, res=None) -> Optional[str]:
@@ -553,6 +569,18 @@ def colstats(x: Tensor) -> Tensor:
     return out
 
 
+def colsum_f32(x: Tensor) -> Tensor:
+    """float[C]: per-channel sum over all rows of an NHWC view (bias gradients, d gamma); double accumulation, ONE launch."""
+    if not fused_stat_tail:
+        return sums_to_float(colstats(x), x.shape[-1])
+    lib = _lib(x)
+    M, Cc = rows_of(x), x.shape[-1]
+    out = torch.empty(2 * Cc, dtype=torch.float32, device=x.device)
+    buf = workspace("stat", lib.gdn_stat_fused_ws_bytes(M, Cc), x.device)
+    L.check(lib.gdn_colsums_f(x.data_ptr(), pitch_of(x), 0, M, Cc, None, out.data_ptr(), buf.data_ptr(), stat_counters(x.device).data_ptr(), _stream()), "gdn_colsums_f")
+    return out[:Cc]
+
+
 def sums_to_float(sums: Tensor, n: int, scale: float = 1.0) -> Tensor:
     out = torch.empty(n, dtype=torch.float32, device=sums.device)
     L.check(_lib(out).gdn_sums_to_float(sums.data_ptr(), out.data_ptr(), n, float(scale), _stream()), "gdn_sums_to_float")
@@ -711,7 +739,7 @@ def op_conv(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, stride: int = 1,
         else:
             dz = dy
         if need_bias:
-            bias.add_grad(sums_to_float(colstats(dz), O))
+            bias.add_grad(colsum_f32(dz))
         conv_backward(cctx, dz, x.t, w.t.detach(), stride=stride, pad=pad, gw=gw, gx=tgt, gx_accumulate=acc)
         if gw is not None:
             w.add_grad(gw)
@@ -759,7 +787,7 @@ def op_linear(tape: Tape, x: Var, w: Var, bias: Optional[Var], *, act: int = ACT
         dz = dz.contiguous()
         dz4 = dz.view(Bn, 1, 1, Fout)
         if bias is not None and bias.needs_grad:
-            bias.add_grad(sums_to_float(colstats(dz), Fout))
+            bias.add_grad(colsum_f32(dz))
         if w.needs_grad:
             gw = torch.empty_like(w.t)
             if tc and Bn % 32 == 0 and Fout % 256 == 0:
@@ -842,13 +870,22 @@ def op_bn_act(tape: Tape, x: Var, bn: BNState, *, training: bool, act: int = ACT
     coef = torch.empty((4, Cc), dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
     mean, invstd, scale, shift = coef[0], coef[1], coef[2], coef[3]
     if training:
-        sums = colstats(x.t)
         upd = update_running and bn.running_mean is not None
-        L.check(lib.gdn_bn_finalize(sums.data_ptr(), M, Cc, bn.weight.t.data_ptr(), bn.bias.t.data_ptr(), bn.eps, bn.momentum,
-                                    bn.running_mean.data_ptr() if upd else None, bn.running_var.data_ptr() if upd else None,
-                                    mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), _stream()), "gdn_bn_finalize")
-        if upd and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        nbt = bn.num_batches_tracked if upd else None
+        if fused_stat_tail and (nbt is None or (nbt.dtype == torch.int64 and nbt.device == dev)):
+            # statistics, finalize and the num_batches_tracked increment in ONE launch (the reduction's last block finishes it)
+            buf = workspace("stat", lib.gdn_stat_fused_ws_bytes(M, Cc), dev)
+            L.check(lib.gdn_bn_stats(x.t.data_ptr(), pitch_of(x.t), 0, M, Cc, bn.weight.t.data_ptr(), bn.bias.t.data_ptr(), bn.eps, bn.momentum,
+                                     bn.running_mean.data_ptr() if upd else None, bn.running_var.data_ptr() if upd else None, _ptr(nbt),
+                                     mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), buf.data_ptr(), stat_counters(dev).data_ptr(),
+                                     _stream()), "gdn_bn_stats")
+        else:
+            sums = colstats(x.t)
+            L.check(lib.gdn_bn_finalize(sums.data_ptr(), M, Cc, bn.weight.t.data_ptr(), bn.bias.t.data_ptr(), bn.eps, bn.momentum,
+                                        bn.running_mean.data_ptr() if upd else None, bn.running_var.data_ptr() if upd else None,
+                                        mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), _stream()), "gdn_bn_finalize")
+            if nbt is not None:
+                nbt.add_(1)
     else:
         L.check(lib.gdn_bn_eval_coeffs(bn.weight.t.data_ptr(), bn.bias.t.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                        bn.eps, Cc, scale.data_ptr(), shift.data_ptr(), _stream()), "gdn_bn_eval_coeffs")
@@ -869,9 +906,17 @@ def op_bn_act(tape: Tape, x: Var, bn: BNState, *, training: bool, act: int = ACT
             raise L.GdnError("backward through eval-mode BatchNorm is not supported")
         dy = y.g
         sums = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
-        buf = workspace("stat", lib.gdn_colstats_ws_bytes(M, Cc), dev)
-        L.check(lib.gdn_bn_bwd_reduce(dy.data_ptr(), pitch_of(dy), 0, x.t.data_ptr(), pitch_of(x.t), 0, M, Cc, mean.data_ptr(), invstd.data_ptr(),
-                                      scale.data_ptr(), shift.data_ptr(), act, slope, sums.data_ptr(), buf.data_ptr(), _stream()), "gdn_bn_bwd_reduce")
+        gb = None
+        if fused_stat_tail:
+            gb = torch.empty(2 * Cc, dtype=torch.float32, device=dev)
+            buf = workspace("stat", lib.gdn_stat_fused_ws_bytes(M, Cc), dev)
+            L.check(lib.gdn_bn_bwd_reduce_f(dy.data_ptr(), pitch_of(dy), 0, x.t.data_ptr(), pitch_of(x.t), 0, M, Cc, mean.data_ptr(), invstd.data_ptr(),
+                                            scale.data_ptr(), shift.data_ptr(), act, slope, sums.data_ptr(), gb.data_ptr(), buf.data_ptr(),
+                                            stat_counters(dev).data_ptr(), _stream()), "gdn_bn_bwd_reduce_f")
+        else:
+            buf = workspace("stat", lib.gdn_colstats_ws_bytes(M, Cc), dev)
+            L.check(lib.gdn_bn_bwd_reduce(dy.data_ptr(), pitch_of(dy), 0, x.t.data_ptr(), pitch_of(x.t), 0, M, Cc, mean.data_ptr(), invstd.data_ptr(),
+                                          scale.data_ptr(), shift.data_ptr(), act, slope, sums.data_ptr(), buf.data_ptr(), _stream()), "gdn_bn_bwd_reduce")
         if x.needs_grad and x.grad16_only and x.g is None and x.parent is None and pitch_of(dy) % 4 == 0 and dy.data_ptr() % 16 == 0:
             g16 = torch.empty((M, Cc), dtype=torch.bfloat16, device=dev)
             L.check(lib.gdn_bn_bwd_apply16(dy.data_ptr(), pitch_of(dy), 0, x.t.data_ptr(), pitch_of(x.t), 0, g16.data_ptr(), Cc, M, Cc, mean.data_ptr(),
@@ -883,7 +928,8 @@ def op_bn_act(tape: Tape, x: Var, bn: BNState, *, training: bool, act: int = ACT
             L.check(lib.gdn_bn_bwd_apply(dy.data_ptr(), pitch_of(dy), 0, x.t.data_ptr(), pitch_of(x.t), 0, tgt.data_ptr(), pitch_of(tgt), 0, int(acc),
                                          M, Cc, mean.data_ptr(), invstd.data_ptr(), bn.weight.t.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                          act, slope, sums.data_ptr(), None, None, _stream()), "gdn_bn_bwd_apply")
-        gb = sums_to_float(sums, 2 * Cc)          # (sum g, sum g*xhat) = (dbias, dweight)
+        if gb is None:
+            gb = sums_to_float(sums, 2 * Cc)          # (sum g, sum g*xhat) = (dbias, dweight)
         gwb = (gb[Cc:], gb[:Cc])
         if bn.weight.needs_grad:
             bn.weight.add_grad(gwb[0])
@@ -920,6 +966,7 @@ def release_buffers() -> None:
     """Drops the engine's persistent device buffers (workspaces, packed frozen weights, PAM value-operand buffers); they are
     re-created on demand.  Do not call while a captured CUDA graph that baked their addresses is still in use."""
     _workspaces.clear()
+    _stat_counters.clear()
     _pam_v16.clear()
     _frozen_weights.clear()
 
@@ -1002,7 +1049,7 @@ def op_pam_core(tape: Tape, x: Var, q: Var, k: Var, v: Var, gamma: Var, *, preci
         famb = "pam_flash_bwd_kernel" if b.precision in PAM_TC_PRECISIONS else "pam_bwd_fp32"
         _timed(famb, 4.0 * B * N * N * (d + Cc), lambda: L.check(lib.gdn_pam_bwd(C.byref(b), _stream()), "gdn_pam_bwd"))
         if gamma.needs_grad:
-            gamma.add_grad(sums_to_float(colstats(rowdot), 1))
+            gamma.add_grad(colsum_f32(rowdot))
         if q.needs_grad:
             q.add_grad(dq)
         if k.needs_grad:
@@ -1246,7 +1293,7 @@ def op_upsample_skip_final(tape: Tape, u: Var, s: Optional[Var], w: Var, bias: O
         if gwp is not None:
             w.add_grad(gwp.view(T, Cc)[:9].t().reshape(1, Cc, 3, 3).contiguous())
         if bias is not None and bias.needs_grad:
-            bias.add_grad(sums_to_float(colstats(dy.view(-1, 1)), 1))
+            bias.add_grad(colsum_f32(dy.view(-1, 1)))
 
     tape.push(bwd)
     return y

@@ -260,13 +260,22 @@ class PerceptualLoss(nn.Module):
             return None
         return {t - 1 for t in self.feature_layers}, convs[-1]
 
-    def _features_bf16(self, tape: E.Tape, x: E.Var, on_feature, plan) -> None:
+    def _features_bf16(self, tape: E.Tape, x: E.Var, on_feature, plan, tap1: Optional[dict] = None) -> None:
         """Same features with bf16-only storage of the untapped maps (conv precision 'bf16': the next conv would round them to bf16
-        anyway): every conv epilogue writes the next conv's packed operand, max-pool runs on bf16, only tapped maps exist in fp32."""
+        anyway): every conv epilogue writes the next conv's packed operand, max-pool runs on bf16, only tapped maps exist in fp32.
+        ``tap1`` (see _tap1_recompute_ok): relu1_1 is tapped but never stored -- conv1_1 emits only conv1_2's bf16 operand, the L1 term
+        and its gradient are recomputed from the single-channel images (``tap1['target']``: the other branch's image, None on that branch)."""
         fp32_convs, last_conv = plan
         layers = list(self.vgg)
         cur, cur16 = x, None
         for idx, layer in enumerate(layers):
+            if idx == 0 and tap1 is not None:
+                w, key = self._weights(0, layer, 1)
+                cur, cur16 = _frozen_conv1_tap(tape, x, w, layer.bias.detach(), tap1.get("target"))
+                continue
+            if idx == 1 and tap1 is not None:
+                on_feature(1, cur, (x.t, self._weights(0, layers[0], 1)[0], layers[0].bias.detach()))
+                continue
             if isinstance(layer, nn.Conv2d):
                 # a recorded (gradient-carrying) max-pool routes the gradient to the arg-max of the fp32 map: bf16 rounding creates ties
                 # that "first maximum in scan order" would break differently (measured: 4 % change of dL/dx), so the maps feeding a
@@ -285,7 +294,19 @@ class PerceptualLoss(nn.Module):
             if idx in self.feature_layers:
                 on_feature(idx, cur)
 
-    def _features(self, tape: E.Tape, x: E.Var, on_feature) -> None:
+    def _tap1_recompute_ok(self, x: torch.Tensor) -> bool:
+        """relu1_1 tapped, single-channel input, bf16 feature-map path, a second conv behind conv1_1 (its data gradient is what the tap's
+        gradient is added to): the tapped map can be recomputed instead of stored (engine flag ``vgg_tap1_recompute``)."""
+        if not (E.vgg_tap1_recompute and E.bf16_storage_ok() and E.thin_conv_enabled and 1 in self.feature_layers and x.dim() == 4 and x.shape[1] == 1):
+            return False
+        plan = self._bf16_plan()
+        layers = list(self.vgg)
+        if plan is None or plan[1] == 0 or not isinstance(layers[0], nn.Conv2d) or layers[0].kernel_size != (3, 3) or layers[0].padding != (1, 1) \
+                or layers[0].stride != (1, 1) or layers[0].bias is None or not isinstance(layers[2], nn.Conv2d):
+            return False
+        return bool(L.load().gdn_thin_conv_tap_l1_supported(layers[0].out_channels, x.shape[2], x.shape[3]))
+
+    def _features(self, tape: E.Tape, x: E.Var, on_feature, tap1: Optional[dict] = None) -> None:
         plan = self._bf16_plan() if E.bf16_storage_ok() else None
         if plan is not None:
             # every conv after the first must take the tensor-core path at its resolution (bf16-only maps have no fp32 fallback)
@@ -301,7 +322,8 @@ class PerceptualLoss(nn.Module):
             if cin == x.t.shape[-1]:
                 plan = None
         if plan is not None:
-            return self._features_bf16(tape, x, on_feature, plan)
+            return self._features_bf16(tape, x, on_feature, plan, tap1)
+        assert tap1 is None, "relu1_1 recomputation needs the bf16 feature-map path"
         cur = x
         for idx, layer in enumerate(self.vgg):
             if isinstance(layer, nn.Conv2d):
@@ -391,6 +413,33 @@ def _frozen_conv16(tape: E.Tape, x: E.Var, x16, wk: Tuple[torch.Tensor, Tuple], 
     return y, y16
 
 
+def _frozen_conv1_tap(tape: E.Tape, x: E.Var, w: torch.Tensor, bias: torch.Tensor, target: Optional[torch.Tensor]):
+    """conv1_1 (1 -> C, channel-summed weight) + ReLU of a branch whose relu1_1 tap is recomputed: only the bf16 operand of conv1_2 is written.
+    Backward (generated branch): dL/dx = conv_T((dy + d L1 / d relu1_1) * relu'), gate and L1 gradient recomputed from x and ``target``."""
+    O = w.shape[0]
+    B, H, W, _ = x.t.shape
+    assert x.t.is_contiguous()
+    y = E.Var(E.new_nhwc(B, H, W, O, x.t))          # shape carrier (never written or read); its gradient is a real fp32 tensor
+    y16 = torch.empty((B * H * W, O), dtype=torch.bfloat16, device=x.t.device)
+    lib = E._lib(x.t)
+    wc = w.contiguous()
+    L.check(lib.gdn_thin_conv_expand_p(x.t.data_ptr(), wc.data_ptr(), bias.data_ptr(), None, 0, None, 0, B, H, W, O, H, W, 1, 1, 0, ACT_RELU, 0.0,
+                                       y16.data_ptr(), E._stream()), "gdn_thin_conv_expand_p")
+
+    def bwd():
+        if y.g is None or not x.needs_grad:
+            return
+        assert target is not None and y.g16 is None
+        tgt, acc = x.grad_target()
+        assert tgt.is_contiguous()
+        L.check(lib.gdn_thin_conv_tap_dgrad(y.g.data_ptr(), E.pitch_of(y.g), x.t.data_ptr(), target.data_ptr(), wc.data_ptr(), bias.data_ptr(),
+                                            1.0 / float(B * H * W * O), tgt.data_ptr(), tgt.data_ptr() if acc else None, B, H, W, O, E._stream()),
+                "gdn_thin_conv_tap_dgrad")
+
+    tape.push(bwd)
+    return y, y16
+
+
 def _relu(tape: E.Tape, x: E.Var) -> E.Var:
     """Stand-alone ReLU (only where a feature is tapped between a conv and its ReLU)."""
     Cc = x.t.shape[-1]
@@ -428,12 +477,20 @@ class _PerceptualFn(torch.autograd.Function):
         ytape = E.Tape(record=False)
         yfeat: Dict[int, torch.Tensor] = {}
         yin = E.op_from_nchw(ytape, y.detach(), False)
-        mod._features(ytape, yin, lambda i, f: yfeat.__setitem__(i, f.t))
+        rec = mod._tap1_recompute_ok(x) and x.shape == y.shape
+        mod._features(ytape, yin, lambda i, f, info=None: yfeat.__setitem__(i, f.t), tap1={"target": None} if rec else None)
         # generated branch: recorded; L1 terms add value and d/dfeature in one pass
         tape = E.Tape(record=need)
         xin = E.op_from_nchw(tape, x.detach(), need)
 
-        def on_feature(i: int, f: E.Var) -> None:
+        def on_feature(i: int, f: E.Var, info=None) -> None:
+            if info is not None:
+                # relu1_1 of both branches recomputed from the two images: value here, gradient inside conv1_1's data-gradient kernel
+                xf, w1, b1 = info
+                Bf, Hf, Wf, _ = xf.shape
+                L.check(lib.gdn_thin_conv_tap_l1(xf.data_ptr(), yin.t.data_ptr(), w1.data_ptr(), b1.data_ptr(), Bf, Hf, Wf, w1.shape[0], loss.data_ptr(), 1, 1.0,
+                                                 ws.data_ptr(), ws.numel(), E._stream()), "gdn_thin_conv_tap_l1")
+                return
             t = yfeat[i]
             assert f.t.is_contiguous() and t.is_contiguous()
             g = torch.empty_like(f.t) if need else None
@@ -449,7 +506,7 @@ class _PerceptualFn(torch.autograd.Function):
                         f.add_grad(g)
                     tape.push(bwd)
 
-        mod._features(tape, xin, on_feature)
+        mod._features(tape, xin, on_feature, tap1={"target": yin.t} if rec else None)
         ctx.tape, ctx.xin = tape, xin
         return loss.reshape(())
 

@@ -213,6 +213,17 @@ int gdn_thin_conv_reduce(const float* v_in, int v_pitch, const float* w, const f
  * discriminator.py:71) without a separate activation-backward pass */
 int gdn_thin_conv_reduce_gated(const float* v_in, int v_pitch, const float* gate, int gate_pitch, float gate_slope, const float* w, const float* bias, float* s_out,
                                const float* res, int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int transposed, gdn_stream_t s);
+/* A TAPPED 1 -> C conv + ReLU (3x3, stride 1, pad 1) without its fp32 output: the perceptual loss's relu1_1 term (losses.py:60-72 with conv1_1 on the
+ * channel-summed weight, losses.py:64-65) recomputed from the two single-channel images instead of stored (2 x 1.07 GB written, 2.1 GB read, 1 GB of L1
+ * gradient written and re-read per step at 256x512, batch 32).  gdn_thin_conv_expand_p with v_out == NULL writes only the bf16 operand of conv1_2.
+ *   tap_l1   : loss[0] (+)= scale * mean | relu(conv(fa) + cbias) - relu(conv(fb) + cbias) |      (ws: >= 8 * 148 doubles)
+ *   tap_dgrad: s_out = conv_transpose((dy + gcoef * sign(relu(conv fa) - relu(conv fb))) * [conv fa + cbias > 0], w) (+ res)
+ * dy [B,H,W,C] = the gradient arriving from conv1_2; fa generated / fb target field [B,H,W]; C = 32 or 64, W % 4 == 0. */
+int gdn_thin_conv_tap_l1_supported(int C, int H, int W);
+int gdn_thin_conv_tap_l1(const float* fa, const float* fb, const float* w, const float* cbias, int B, int H, int W, int C, float* loss, int loss_accumulate,
+                         float scale, void* ws, size_t ws_bytes, gdn_stream_t st);
+int gdn_thin_conv_tap_dgrad(const float* dy, int dy_pitch, const float* fa, const float* fb, const float* w, const float* cbias, float gcoef, float* s_out,
+                            const float* res, int B, int H, int W, int C, gdn_stream_t st);
 /* dw[c][k] (+)= sum_v V[v][c] S[v*stride + k - pad]   (flip: S at v + pad - k).  Deterministic two-stage reduction. */
 size_t gdn_thin_conv_wgrad_ws_bytes(int B, int Hv, int Wv, int C);
 int gdn_thin_conv_wgrad(const float* v, int v_pitch, const float* s_in, float* dw, int accumulate, int B, int Hv, int Wv, int C, int Hs, int Ws,
@@ -227,6 +238,23 @@ int gdn_colstats(const float* x, int pitch, int c0, long long M, int C, double* 
  * saves mean and invstd; updates running stats (momentum, unbiased var). */
 int gdn_bn_finalize(const double* sums, long long M, int C, const float* weight, const float* bias, float eps, float momentum,
                     float* running_mean, float* running_var, float* mean, float* invstd, float* scale, float* shift, gdn_stream_t s);
+/* Single-launch forms (round 2).  The blocks of the reduction finish it themselves (two-level last-block-done scheme with a fixed summation
+ * order: bitwise deterministic), so train-mode BatchNorm statistics (generator.py:32,61,149,189,219,223) are ONE launch instead of
+ * gdn_colstats (2 launches) + gdn_bn_finalize + the num_batches_tracked increment, and the BatchNorm backward reduction is one launch instead of
+ * gdn_bn_bwd_reduce (2) + gdn_sums_to_float.  ws: gdn_stat_fused_ws_bytes(M, C) bytes; counters: gdn_stat_fused_counters() 32-bit words that are
+ * ZERO on entry (the finishing block restores them to zero; one buffer per stream). */
+size_t gdn_stat_fused_ws_bytes(long long M, int C);
+int gdn_stat_fused_counters(void);
+/* statistics + gdn_bn_finalize (+ *num_batches_tracked += 1 when given) */
+int gdn_bn_stats(const float* x, int pitch, int c0, long long M, int C, const float* weight, const float* bias, float eps, float momentum,
+                 float* running_mean, float* running_var, long long* num_batches_tracked, float* mean, float* invstd, float* scale,
+                 float* shift, void* ws, unsigned* counters, gdn_stream_t s);
+/* gdn_colstats with the sums also (or only) as float: sums / fsums [2C], either may be NULL */
+int gdn_colsums_f(const float* x, int pitch, int c0, long long M, int C, double* sums, float* fsums, void* ws, unsigned* counters, gdn_stream_t s);
+/* gdn_bn_bwd_reduce with the sums also as float (fsums[0..C) = dbias, fsums[C..2C) = dweight; may be NULL) */
+int gdn_bn_bwd_reduce_f(const float* dy, int dy_pitch, int dy_c0, const float* x, int x_pitch, int x_c0, long long M, int C,
+                        const float* mean, const float* invstd, const float* scale, const float* shift, int act, float slope,
+                        double* sums, float* fsums, void* ws, unsigned* counters, gdn_stream_t s);
 /* eval-mode: scale/shift from running statistics */
 int gdn_bn_eval_coeffs(const float* weight, const float* bias, const float* running_mean, const float* running_var, float eps,
                        int C, float* scale, float* shift, gdn_stream_t s);
