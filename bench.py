@@ -242,6 +242,10 @@ def run_ours(args):
     # ---- eager pass with a CUDA-event bracket around every tensor-core C-ABI call: the per-kernel-family numbers (roofline, kernels)
     n_prof = max(3, min(args.steps, 5)) if args.graph else args.steps
     clocks = ClockSampler(local)
+    # (one stream: the side-stream overlaps of the trainer -- D's AdamW and the perceptual target branch beside tensor-bound work -- would let a
+    # bracketed kernel share the SMs with another branch and inflate its time; the per-family numbers are serial-execution numbers)
+    overlap_flags = (tr.overlap_opt_D, tr.overlap_target)
+    tr.overlap_opt_D = tr.overlap_target = False
     E.kernel_timing = {}
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -254,6 +258,7 @@ def run_ours(args):
     ms_eager = e0.elapsed_time(e1) / n_prof
     timing, E.kernel_timing = E.kernel_timing, None
     prof_steps = n_prof
+    tr.overlap_opt_D, tr.overlap_target = overlap_flags
 
     # ---- the other modes as extra keys (eager, a few steps, same trainer): the faster single-fp16-logit PAM, and the tensor-core PARITY mode
     # (hi+lo split convolutions + split-logit PAM: 1e-3 on the generator output, losses within 1 % at every step -- DESIGN.md 4)
@@ -431,6 +436,7 @@ def run_ours(args):
                 "config": {"workload": workload_name(args, h, w), "global_batch": world * B, "parallelism": f"dp{world}", "conv": args.conv_precision,
                            "pam": f"fused tcgen05 flash forward + backward ({args.pam_precision})" if args.pam_precision != "fp32" else "fp32 engine",
                            "cuda_graph": graph_info, "eager_ms_per_step": ms_eager, "aux_transport": aux_dtype,
+                           "side_stream_overlap": {"opt_D": bool(overlap_flags[0]), "perceptual_target": bool(overlap_flags[1])},
                            "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
                            "l2": "inputs larger than L2 (the aux stack alone is %.0f MB per step)" % (aux_h.numel() * aux_h.element_size() / 1e6)},
                 "clocks": clk, "gpu_launches": launches,

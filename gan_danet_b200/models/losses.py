@@ -299,28 +299,32 @@ class PerceptualLoss(nn.Module):
         gradient is added to): the tapped map can be recomputed instead of stored (engine flag ``vgg_tap1_recompute``)."""
         if not (E.vgg_tap1_recompute and E.bf16_storage_ok() and E.thin_conv_enabled and 1 in self.feature_layers and x.dim() == 4 and x.shape[1] == 1):
             return False
-        plan = self._bf16_plan()
+        plan = self._bf16_plan_for(x.shape[2], x.shape[3], 1)
         layers = list(self.vgg)
         if plan is None or plan[1] == 0 or not isinstance(layers[0], nn.Conv2d) or layers[0].kernel_size != (3, 3) or layers[0].padding != (1, 1) \
                 or layers[0].stride != (1, 1) or layers[0].bias is None or not isinstance(layers[2], nn.Conv2d):
             return False
         return bool(L.load().gdn_thin_conv_tap_l1_supported(layers[0].out_channels, x.shape[2], x.shape[3]))
 
-    def _features(self, tape: E.Tape, x: E.Var, on_feature, tap1: Optional[dict] = None) -> None:
+    def _bf16_plan_for(self, H: int, W: int, cin0: int):
+        """_bf16_plan() if the bf16 feature-map path applies to an input of this grid and channel count, else None."""
         plan = self._bf16_plan() if E.bf16_storage_ok() else None
         if plan is not None:
             # every conv after the first must take the tensor-core path at its resolution (bf16-only maps have no fp32 fallback)
-            _, H, W, cin = x.t.shape
+            cin = cin0
             for layer in self.vgg:
                 if isinstance(layer, nn.MaxPool2d):
                     H, W = H // 2, W // 2
                 elif isinstance(layer, nn.Conv2d):
                     if cin != 1 and not (E.tc_eligible(cin, layer.out_channels, 3, 3, 1, H, W) and layer.out_channels % 8 == 0 and H % 2 == 0 and W % 2 == 0):
-                        plan = None
-                        break
+                        return None
                     cin = layer.out_channels
-            if cin == x.t.shape[-1]:
-                plan = None
+            if cin == cin0:
+                return None
+        return plan
+
+    def _features(self, tape: E.Tape, x: E.Var, on_feature, tap1: Optional[dict] = None) -> None:
+        plan = self._bf16_plan_for(x.t.shape[1], x.t.shape[2], x.t.shape[3])
         if plan is not None:
             return self._features_bf16(tape, x, on_feature, plan, tap1)
         assert tap1 is None, "relu1_1 recomputation needs the bf16 feature-map path"
@@ -340,6 +344,36 @@ class PerceptualLoss(nn.Module):
                 raise NotImplementedError(type(layer))
             if idx in self.feature_layers:
                 on_feature(idx, cur)
+
+    def _target_features(self, y: torch.Tensor, rec: bool):
+        """Forward-only features of the target branch: (NHWC input Var, {tap index: tensor})."""
+        ytape = E.Tape(record=False)
+        yfeat: Dict[int, torch.Tensor] = {}
+        yin = E.op_from_nchw(ytape, y.detach(), False)
+        self._features(ytape, yin, lambda i, f, info=None: yfeat.__setitem__(i, f.t), tap1={"target": None} if rec else None)
+        return yin, yfeat
+
+    def prefetch_target(self, y: torch.Tensor, stream: "torch.cuda.Stream") -> None:
+        """Evaluates the target branch (it depends on ``y`` alone: the real field of GAN_DANet_train.ipynb:265) on ``stream``, forked from the
+        current stream, so that it runs beside whatever is enqueued next (the trainer: the generator's forward pass).  The next ``forward(x, y)``
+        with this ``y`` joins the stream and uses the result.  The cached tensors live in ``stream``'s allocator pool: they are released before
+        the next prefetch forks from the consumer stream again, so a recycled block is never written while the consumer still reads it."""
+        cur = torch.cuda.current_stream(y.device)
+        stream.wait_stream(cur)
+        rec = self._tap1_recompute_ok(y)
+        self._prefetched = None
+        with torch.cuda.stream(stream):
+            out = self._target_features(y, rec)
+            done = torch.cuda.Event()
+            done.record(stream)       # the consumer waits for THIS point only, not for what the caller enqueues on ``stream`` afterwards
+        self._prefetched = (y.data_ptr(), y._version, tuple(y.shape), rec, out, done)
+
+    def _take_target(self, y: torch.Tensor, rec: bool):
+        pre, self._prefetched = getattr(self, "_prefetched", None), None
+        if pre is not None and pre[:4] == (y.data_ptr(), y._version, tuple(y.shape), rec):
+            torch.cuda.current_stream(y.device).wait_event(pre[5])
+            return pre[4]
+        return self._target_features(y, rec)
 
     def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         return _PerceptualFn.apply(self, x, y)
@@ -474,11 +508,8 @@ class _PerceptualFn(torch.autograd.Function):
         E.fill_(loss, 0.0)
         ws = E.dot_ws(dev)
         # target branch: forward only
-        ytape = E.Tape(record=False)
-        yfeat: Dict[int, torch.Tensor] = {}
-        yin = E.op_from_nchw(ytape, y.detach(), False)
         rec = mod._tap1_recompute_ok(x) and x.shape == y.shape
-        mod._features(ytape, yin, lambda i, f, info=None: yfeat.__setitem__(i, f.t), tap1={"target": None} if rec else None)
+        yin, yfeat = mod._take_target(y, rec)
         # generated branch: recorded; L1 terms add value and d/dfeature in one pass
         tape = E.Tape(record=need)
         xin = E.op_from_nchw(tape, x.detach(), need)

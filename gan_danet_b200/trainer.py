@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, Iterable, List, Optional, Tuple
 
 import torch
@@ -285,6 +286,12 @@ class GANTrainer:
         if allreduce is not None and fused_adamw:
             self.opt_G.grad_scale = 1.0 / allreduce.world
         self._w_dev: Optional[torch.Tensor] = None       # [w, 1 - w] on the device: set by GraphedTrainStep (the captured step must not bake epoch / epochs)
+        # Optional side-stream overlaps (off by default: measured on B200, graph replay, batch 32: D's AdamW -- a 7.5 GB HBM-bound pass -- beside the
+        # tensor-bound VGG19 forward passes: 52.66 -> 52.51 ms; additionally the perceptual target branch beside G's forward: 53.06 ms, i.e. SLOWER --
+        # the step's kernels already fill the SMs, concurrency only adds L2 / scheduling contention)
+        self.overlap_opt_D = os.environ.get("GDN_OVERLAP_OPT_D", "0") == "1"
+        self.overlap_target = os.environ.get("GDN_OVERLAP_TARGET", "0") == "1"
+        self._side: Optional[torch.cuda.Stream] = None
 
     def _make_opt(self, params, lr):
         cls = FusedAdamW if self.fused_adamw else torch.optim.AdamW
@@ -313,6 +320,16 @@ class GANTrainer:
                     if p.grad is not None:
                         p.grad.mul_(1.0 / self.allreduce.world)
 
+    def _step_D(self, d_params, finish_reduce) -> None:
+        """optimizer_D.step() (GAN_DANet_train.ipynb:256) on the current stream, after the gradient reduction (data parallel)."""
+        if finish_reduce is not None:
+            finish_reduce()
+            if not self.fused_adamw and self.allreduce.world > 1:
+                for p in d_params:
+                    if p.grad is not None:
+                        p.grad.mul_(1.0 / self.allreduce.world)
+        self.opt_D.step()
+
     def train_step(self, lr_grace_05: torch.Tensor, lr_grace_025: torch.Tensor, hr_aux: torch.Tensor) -> Dict[str, torch.Tensor]:
         """One iteration of the hot loop.  Inputs are device tensors (NCHW, as ``CustomDataset`` yields them).
         Returns the scalar losses as 0-dim device tensors (no host sync)."""
@@ -320,6 +337,10 @@ class GANTrainer:
         real = lr_grace_025
         B = real.shape[0]
         self._ensure_opt_D(real)
+        if real.is_cuda and (self.overlap_opt_D or self.overlap_target) and (self._side is None or self._side.device != real.device):
+            self._side = torch.cuda.Stream(device=real.device)
+        if self.overlap_target and real.is_cuda and self.perceptual is not None:
+            self.perceptual.prefetch_target(real, self._side)
         x = prepare_input_nhwc(lr_grace_05, hr_aux)                       # :226-232
         hr = generator_forward_nhwc(G, x)                                 # :243
 
@@ -333,7 +354,15 @@ class GANTrainer:
         d_params = list(D.parameters())
         # data parallel: D's gradient all-reduce (~1 GB: fc1) is launched here and awaited only before D's optimiser step; the terms of the
         # generator objective that do not involve D (pixel, TV, perceptual: two VGG19 forward passes) are evaluated while it is in flight
-        finish_reduce = self.allreduce.start(d_params) if self.allreduce is not None else None
+        side = None
+        if self.overlap_opt_D and real.is_cuda:
+            side = self._side
+            side.wait_stream(torch.cuda.current_stream(real.device))
+            with torch.cuda.stream(side):
+                self._step_D(d_params, self.allreduce.start(d_params) if self.allreduce is not None else None)
+            finish_reduce = None
+        else:
+            finish_reduce = self.allreduce.start(d_params) if self.allreduce is not None else None
 
         # ---- generator step (:259-269), D-independent terms
         self.opt_G.zero_grad(set_to_none=True)
@@ -344,13 +373,10 @@ class GANTrainer:
         loss_tv = self.tv(hr)
         loss_perc = self.perceptual(hr, real) if self.perceptual is not None else None
 
-        if finish_reduce is not None:
-            finish_reduce()
-            if not self.fused_adamw and self.allreduce.world > 1:
-                for p in d_params:
-                    if p.grad is not None:
-                        p.grad.mul_(1.0 / self.allreduce.world)
-        self.opt_D.step()
+        if side is not None:
+            torch.cuda.current_stream(real.device).wait_stream(side)      # D's updated parameters are read from here on
+        else:
+            self._step_D(d_params, finish_reduce)
 
         # ---- adversarial term: D already updated, its parameter gradients are not needed here
         for p in d_params:

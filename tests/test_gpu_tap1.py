@@ -54,7 +54,7 @@ def test_tap_kernels_vs_float64(shape):
     assert rel(gx, ad.grad[:, 0]) < 2e-4
 
 
-@pytest.mark.parametrize("shape", [(2, 32, 64), (1, 48, 40)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("shape", [(2, 32, 64), (1, 48, 64)], ids=lambda s: "x".join(map(str, s)))
 def test_perceptual_recompute_matches_stored(shape):
     """PerceptualLoss in the bf16 product mode with and without the recomputation: same loss (summation order only), same input gradient."""
     import gan_danet_b200 as P
@@ -83,3 +83,21 @@ def test_perceptual_recompute_matches_stored(shape):
     finally:
         E.set_conv_precision(old_prec)
         E.vgg_tap1_recompute = old_flag
+
+
+def test_perceptual_recompute_falls_back_on_ineligible_grid():
+    """A grid whose deeper VGG levels leave the bf16 feature-map path (odd width after three poolings) keeps the stored relu1_1 map."""
+    import gan_danet_b200 as P
+    from gan_danet_b200 import engine as E
+    dev = torch.device("cuda", 0)
+    old_prec = E.conv_precision
+    E.set_conv_precision("bf16")
+    try:
+        torch.manual_seed(5)
+        crit = P.PerceptualLoss(feature_layers=(1, 6, 11, 20), pretrained=False, device=dev)
+        x = torch.randn(1, 1, 48, 40, device=dev, requires_grad=True)
+        assert not crit._tap1_recompute_ok(x)
+        crit(x, torch.randn(1, 1, 48, 40, device=dev)).backward()
+        assert torch.isfinite(x.grad).all()
+    finally:
+        E.set_conv_precision(old_prec)
