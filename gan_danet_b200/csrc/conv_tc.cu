@@ -614,6 +614,174 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapDYhi, const __grid_c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ narrow-output weight gradient (round 2)
+// The DenseNet growth convolutions (generator.py:34: C_i -> 24, 3x3, twelve per step) ran their weight gradient at 66-125 TFLOP/s on the kernel
+// above: nine shifted x tiles (16-32 KB each) per pixel tile feed nine tiny MMAs, 1400 cycles per tap against ~200 of tensor work, 9x the
+// x traffic.  Here the NARROW operand is shifted instead: per 128-pixel tile q the shared-memory tile
+//     dycol[q][(tap, co)] = dy[q - (tap - pad)][co]          (216 columns for Cout = 24, zero outside the image)
+// is assembled by 27 small TMA boxes ([128 px][8 ch], 16-byte rows, no swizzle -- exactly the canonical MN-major "interleave" layout of
+// tcgen05: 8 channels contiguous, pixel rows 16 B apart, 8-pixel groups 128 B apart, channel groups 2 KB apart), x is loaded ONCE, and
+//     D[(tap, co)][ci] += dycol^T x                          (M = 256 = two UMMA halves, N = round_up(Cin, 16), K = 128 pixels)
+// is one chain of 16 MMAs per tile into TMEM-resident accumulators that live for the CTA's whole lifetime (persistent CTAs, one partial sum
+// per CTA, fixed-order reduction => deterministic).  Operand traffic per tile: 54 KB + x instead of 9 x (x + dy).
+constexpr int WC_GROUP_BYTES = BM * 16;                       // [128 px][8 ch] bf16
+constexpr int WC_GROUPS = 32;                                 // 256 accumulator rows; groups >= 9 * G stay zero
+constexpr int WC_COL_BYTES = WC_GROUPS * WC_GROUP_BYTES;      // 64 KB
+// ROW variant (tiles of one image row, Wt = 128): the three kw-shifts of a (kh, channel group) are ONE box of 130 pixels read at start addresses
+// +0 / +16 / +32 bytes (no swizzle: any 16-byte aligned start is legal), so 3 * G boxes per tile instead of 9 * G (TMA moves these boxes as 16-byte
+// rows: the row count, not the byte count, is what they cost).  Accumulator rows are then ordered (kw, kh, co): three M = 128 products per K step.
+constexpr int WR_BOX_BYTES = (BM + 2) * 16;                   // 2080 bytes per box ...
+constexpr int WR_SLOT_BYTES = 17 * 128;                       // ... in slots of 2176: TMA wants 128-byte aligned shared-memory destinations
+constexpr int WR_COL_BYTES = 16 * WR_SLOT_BYTES;              // 34 KB: 16 slots = the 128 accumulator rows of one product (slots >= 3 * G stay zero)
+constexpr int WC_STAGES = 2;
+struct WcParams {
+  float* ws;                   // [ctas][taps * Cout][N] fp32 partial sums
+  int Cout, G, ngroups, nbox, N, tmem_cols;
+  int tiles_w, tiles_h, tiles_total, Wt, Ht;
+  int lbo, sbo;                // A descriptor strides (bytes): 8-pixel groups / 8-channel groups
+};
+
+template <bool ROW>
+__global__ void __launch_bounds__(NTHREADS)
+conv_tc_wgrad_col_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX, const WcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int COL_BYTES = ROW ? WR_COL_BYTES : WC_COL_BYTES;
+  const int stage_bytes = COL_BYTES + p.nbox * A_BYTES;
+  const uint32_t bar_base = base + WC_STAGES * stage_bytes;
+  auto full = [&](int s) { return bar_base + 8 * s; };
+  auto empty = [&](int s) { return bar_base + 8 * (WC_STAGES + s); };
+  const uint32_t acc_bar = bar_base + 8 * (2 * WC_STAGES);
+  const uint32_t tmem_slot_addr = acc_bar + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot_addr - base));
+  const int ntiles = (p.tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles blockIdx.x, + gridDim.x, ...
+  const int col_tx = ROW ? 3 * p.G * WR_BOX_BYTES : p.ngroups * WC_GROUP_BYTES;                    // bytes TMA writes per stage
+
+  for (int s = 0; s < WC_STAGES; ++s) {      // the groups TMA never writes (and the slot padding) must read as zero
+    uint4* z = reinterpret_cast<uint4*>(sm + s * stage_bytes);
+    for (int i = threadIdx.x; i < COL_BYTES / 16; i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_async_smem();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WC_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- TMA producer: the shifted dy boxes + the x tile per pixel tile
+      for (int n = 0; n < ntiles; ++n) {
+        int t = blockIdx.x + n * gridDim.x;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int s = n % WC_STAGES;
+        if (n >= WC_STAGES) mbar_wait(empty(s), ((n / WC_STAGES) - 1) & 1);
+        const uint32_t st = base + s * stage_bytes;
+        mbar_expect_tx(full(s), col_tx + p.nbox * A_BYTES);
+        for (int bx = 0; bx < p.nbox; ++bx) tma_load_4d(st + COL_BYTES + bx * A_BYTES, &mapX, full(s), bx * 64, tw * p.Wt, th * p.Ht, t);
+        if (ROW) {
+          for (int kh = 0; kh < 3; ++kh)
+            for (int g = 0; g < p.G; ++g)      // pixels tw*128 - 1 .. tw*128 + 128 of image row th - (kh - 1)
+              tma_load_4d(st + (kh * p.G + g) * WR_SLOT_BYTES, &mapDY, full(s), g * 8, tw * BM - 1, th - (kh - 1), t);
+        } else {
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+            for (int g = 0; g < p.G; ++g)
+              tma_load_4d(st + (tap * p.G + g) * WC_GROUP_BYTES, &mapDY, full(s), g * 8, tw * p.Wt - dw, th * p.Ht - dh, t);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: A = dycol (MN-major, no swizzle), B = x (MN-major, SWIZZLE_128B, 64-channel boxes LBO = 16 KB apart)
+    const uint32_t idesc = idesc_bf16(128, p.N, 1, 1);
+    const uint64_t a0 = smem_desc_lbo(base, (uint32_t)p.lbo, (uint32_t)p.sbo, 0);
+    const uint64_t b0 = smem_desc_lbo(base, A_BYTES, 1024, LAYOUT_SW128);
+    for (int n = 0; n < ntiles; ++n) {
+      const int s = n % WC_STAGES;
+      mbar_wait_spin(full(s), (uint32_t)(n / WC_STAGES) & 1u);
+      tc_fence_after();
+      const uint64_t ad = a0 + (uint64_t)((s * stage_bytes) >> 4), bd = b0 + (uint64_t)((s * stage_bytes + COL_BYTES) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < BM / 16; ++ks) {       // 16 pixels: 256 B of every dy group, 2 KB of every x box
+          const uint32_t acc = (n > 0 || ks > 0) ? 1u : 0u;
+          if (ROW) {
+            // window kw starts 2 - kw pixels into the 130-pixel box: dycol[q][kw] = dy[q - (kw - 1)] = box pixel (q + 1) - (kw - 1)
+            umma_f16(tmem, ad + ks * 16 + 2, bd + ks * 128, idesc, acc);
+            umma_f16(tmem + p.N, ad + ks * 16 + 1, bd + ks * 128, idesc, acc);
+            umma_f16(tmem + 2 * p.N, ad + ks * 16, bd + ks * 128, idesc, acc);
+          } else {
+            umma_f16(tmem, ad + ks * 16, bd + ks * 128, idesc, acc);
+            umma_f16(tmem + p.N, ad + ((16 * WC_GROUP_BYTES) >> 4) + ks * 16, bd + ks * 128, idesc, acc);
+          }
+        }
+        tc_commit(empty(s));
+      }
+      __syncwarp();
+    }
+    if (elect_one()) tc_commit(acc_bar);
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---- epilogue: thread = accumulator row; this CTA's partial sums to the workspace
+    const int q = warp & 3;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    for (int h = 0; h < (ROW ? 3 : 2); ++h) {
+      const int r = q * 32 + lane;
+      int tap, co; bool ok;
+      if (ROW) { const int i = r >> 3; tap = (i / p.G) * 3 + h; co = (i % p.G) * 8 + (r & 7); ok = i < 3 * p.G && co < p.Cout; }     // accumulator h = kw, row = (kh, co)
+      else { const int g = (h * 128 + r) >> 3; tap = g / p.G; co = (g % p.G) * 8 + (r & 7); ok = g < p.ngroups && co < p.Cout; }
+      float* dst = p.ws + (((size_t)blockIdx.x * 9 + tap) * p.Cout + co) * p.N;
+      for (int c = 0; c < p.N; c += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * p.N + c, v);
+        if (ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            if (c + e < p.N) *reinterpret_cast<float4*>(dst + c + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+// out[co][out_c0+ci][tap] (OIHW) (+)= scale * sum_cta ws[cta][tap][co][ci]   -- fixed summation order => deterministic
+__global__ void wgrad_col_reduce_kernel(const float* __restrict__ ws, int ctas, int Cout, int Cin, int N, float* __restrict__ out, int out_cin_total, int out_c0,
+                                        int accumulate, float scale, const float* __restrict__ scale_ptr) {
+  if (scale_ptr) scale *= __ldg(scale_ptr);
+  const long long total = (long long)Cout * 9 * Cin;
+  const size_t cta_stride = (size_t)9 * Cout * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % Cin); long long r = idx / Cin;
+    const int co = (int)(r % Cout); const int tap = (int)(r / Cout);
+    const float* src = ws + ((size_t)tap * Cout + co) * N + ci;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = 0;
+    for (; c + 3 < ctas; c += 4) { a0 += src[c * cta_stride]; a1 += src[(c + 1) * cta_stride]; a2 += src[(c + 2) * cta_stride]; a3 += src[(c + 3) * cta_stride]; }
+    for (; c < ctas; ++c) a0 += src[c * cta_stride];
+    const float acc = (a0 + a1) + (a2 + a3);
+    float* o = out + ((size_t)co * out_cin_total + out_c0 + ci) * 9 + tap;
+    *o = accumulate ? *o + acc * scale : acc * scale;
+  }
+}
+
 // out[co][out_c0+ci][tap] (OIHW) (+)= scale * sum_s ws[s][co][tap][ci]   -- fixed summation order => deterministic
 // swapped: the partial sums come from the role-swapped launch (gdn_conv2d_wgrad_tc: narrow Cout), ws[s][ci][taps-1-tap][co] with row width cin_w
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ ws, int splits, int Cout, int Cin, int taps, int cin_w,
@@ -716,6 +884,19 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int Cp, int W, int H, i
   if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(activation Cp=%d W=%d H=%d B=%d box %dx%d cs=%d) failed (%d)", Cp, W, H, B, Wt, Ht, cs, (int)r); return GDN_ECUDA; }
   return GDN_OK;
 }
+// the same tensor as [128 px][8 ch] boxes without swizzle (conv_tc_wgrad_col_kernel's shifted dy groups)
+static int make_act_map8(CUtensorMap* m, const void* ptr, int Cp, int W, int H, int B, int Wt, int Ht) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return GDN_ECUDA; }
+  cuuint64_t gdim[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstride[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
+  cuuint32_t box[4] = {8, (cuuint32_t)Wt, (cuuint32_t)Ht, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(8-channel groups Cp=%d W=%d H=%d B=%d box %dx%d) failed (%d)", Cp, W, H, B, Wt, Ht, (int)r); return GDN_ECUDA; }
+  return GDN_OK;
+}
 // 3-D packed weight map: dims (Kp, R, taps), box (64, n_tile, 1)
 static int make_weight_map(CUtensorMap* m, const void* ptr, int Kp, int R, int taps, int n_tile) {
   EncodeTiledFn enc = get_encode();
@@ -751,6 +932,8 @@ extern "C" int gdn_conv_tc_init(void) {
   GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   return GDN_OK;
 }
 
@@ -970,8 +1153,51 @@ static gdn_wgrad_tc_args wgrad_swapped(const gdn_wgrad_tc_args* a) {
   return b;
 }
 
+// conv_tc_wgrad_col_kernel applies to 3x3 stride-1 "same" convolutions with at most 24 output channels (9 taps x 3 groups of 8 = 216 <= 256 accumulator rows)
+static int g_wgrad_col = 1;
+extern "C" int gdn_conv_tc_set_wgrad_col(int enabled) { const int old = g_wgrad_col; g_wgrad_col = enabled ? 1 : 0; return old; }
+static bool wgrad_col_ok(const gdn_wgrad_tc_args* a) {
+  return g_wgrad_col && a->groups <= 1 && a->precision == GDN_PREC_BF16 && a->kh == 3 && a->kw == 3 && a->stride == 1 && a->pad == 1 && a->Ho == a->Hi && a->Wo == a->Wi &&
+         a->Cout <= 24 && a->Cin >= 16 && a->Cin <= 192;
+}
+static int g_wgrad_col_row = 1;    // test hook: the one-image-row variant (3 * G boxes of 130 pixels) where the tile is a 128-pixel row
+extern "C" int gdn_conv_tc_set_wgrad_col_row(int enabled) { const int old = g_wgrad_col_row; g_wgrad_col_row = enabled ? 1 : 0; return old; }
+static void wgrad_col_plan(const gdn_wgrad_tc_args* a, WcParams* p, int* ctas, bool* row) {
+  p->Cout = a->Cout; p->G = (a->Cout + 7) / 8; p->ngroups = 9 * p->G;
+  p->nbox = (int)cdiv(a->Cin, 64); p->N = (int)cdiv(a->Cin, 16) * 16;
+  tile_shape(a->Wo, &p->Wt, &p->Ht);
+  *row = g_wgrad_col_row && p->Wt == BM && p->Ht == 1 && 3 * p->N + 32 <= 512;
+  p->tmem_cols = pow2_cols((*row ? 3 : 2) * p->N + 32);
+  p->tiles_w = (int)cdiv(a->Wo, p->Wt); p->tiles_h = (int)cdiv(a->Ho, p->Ht);
+  p->tiles_total = a->B * p->tiles_h * p->tiles_w;
+  *ctas = p->tiles_total < kNumSMs ? p->tiles_total : kNumSMs;
+  p->lbo = 128; p->sbo = *row ? WR_SLOT_BYTES : WC_GROUP_BYTES;
+}
+static int wgrad_col_launch(const gdn_wgrad_tc_args* a, cudaStream_t st) {
+  WcParams p; int ctas; bool row;
+  wgrad_col_plan(a, &p, &ctas, &row);
+  GDN_CHECK_ARG(((uintptr_t)a->ws & 15) == 0 && p.tmem_cols <= 512);
+  p.ws = a->ws;
+  const int Cop = (a->Cout + 7) & ~7, Cip = (a->Cin + 7) & ~7;
+  CUtensorMap mdy, mx;
+  int rc;
+  if ((rc = make_act_map8(&mdy, a->dy_hi, Cop, a->Wo, a->Ho, a->B, row ? BM + 2 : p.Wt, p.Ht)) != GDN_OK) return rc;
+  if ((rc = make_act_map(&mx, a->x_hi, Cip, a->Wi, a->Hi, a->B, p.Wt, p.Ht, 1)) != GDN_OK) return rc;
+  const size_t smem = (size_t)WC_STAGES * ((row ? WR_COL_BYTES : WC_COL_BYTES) + p.nbox * A_BYTES) + 8 * (2 * WC_STAGES + 2) + 16 + 1024;
+  GDN_CHECK_ARG(smem <= (size_t)SMEM_LIMIT);
+  if (row) conv_tc_wgrad_col_kernel<true><<<ctas, NTHREADS, smem, st>>>(mdy, mx, p);
+  else conv_tc_wgrad_col_kernel<false><<<ctas, NTHREADS, smem, st>>>(mdy, mx, p);
+  GDN_CHECK_LAUNCH();
+  const long long total = (long long)a->Cout * 9 * a->Cin;
+  const int blocks = (int)(cdiv(total, 256) < 4 * kNumSMs ? cdiv(total, 256) : 4 * kNumSMs);
+  wgrad_col_reduce_kernel<<<blocks, 256, 0, st>>>(a->ws, ctas, a->Cout, a->Cin, p.N, a->out, a->out_cin_total, a->out_c0, a->accumulate, a->scale, a->scale_ptr);
+  GDN_CHECK_LAUNCH();
+  return GDN_OK;
+}
+
 extern "C" size_t gdn_conv2d_wgrad_tc_ws_bytes(const gdn_wgrad_tc_args* a) {
   if (a->groups > 1) return 0;
+  if (wgrad_col_ok(a)) { WcParams pc; int ctas; bool row; wgrad_col_plan(a, &pc, &ctas, &row); return (size_t)ctas * 9 * a->Cout * pc.N * sizeof(float); }
   WgParams p;
   if (wgrad_swap_ok(a)) {
     const gdn_wgrad_tc_args b = wgrad_swapped(a);
@@ -985,6 +1211,10 @@ extern "C" size_t gdn_conv2d_wgrad_tc_ws_bytes(const gdn_wgrad_tc_args* a) {
 extern "C" int gdn_conv2d_wgrad_tc(const gdn_wgrad_tc_args* orig, gdn_stream_t s) {
   GDN_CHECK_ARG(orig && orig->dy_hi && orig->x_hi && orig->out && (orig->ws || orig->groups > 1));
   GDN_CHECK_ARG(orig->out_cin_total >= orig->out_c0 + orig->Cin);
+  if (wgrad_col_ok(orig)) {
+    if (orig->ws_bytes < gdn_conv2d_wgrad_tc_ws_bytes(orig)) { set_error("gdn_conv2d_wgrad_tc: workspace too small"); return GDN_EWORKSPACE; }
+    return wgrad_col_launch(orig, as_stream(s));
+  }
   const bool swapped = wgrad_swap_ok(orig);
   const gdn_wgrad_tc_args sw = swapped ? wgrad_swapped(orig) : *orig;
   const gdn_wgrad_tc_args* a = &sw;

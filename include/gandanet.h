@@ -154,6 +154,11 @@ int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s);
 int gdn_conv_tc_set_halo(int enabled);
 /* test hook: enable/disable the role-swapped weight gradient for narrow outputs (Cout <= 32, the DenseNet growth convolutions of generator.py:34) */
 int gdn_conv_tc_set_wgrad_swap(int enabled);
+/* test hook: enable/disable the narrow-output weight-gradient kernel (3x3 stride-1 "same" convolutions with Cout <= 24 and Cin <= 192 in the bf16 precision --
+ * the twelve DenseNet growth convolutions of generator.py:34: the 24-channel dy is the shifted operand, x is read once per pixel tile); returns the old setting */
+int gdn_conv_tc_set_wgrad_col(int enabled);
+/* test hook: within that kernel, the one-image-row variant (tiles of 128 consecutive pixels: 3 boxes of 130 pixels replace the 9 shifted boxes) */
+int gdn_conv_tc_set_wgrad_col_row(int enabled);
 /*
  * Weight gradient: out[co][out_c0+ci][kh][kw] (OIHW, out_cin_total input channels) (+)= scale * sum_pixels dy * x.
  * dy: packed [B,Ho,Wo,Cout_p8]; x: packed [B,Hi,Wi,Cin_p8].  Deterministic (split-K through ws, fixed-order reduction).

@@ -251,3 +251,46 @@ def test_wgrad_role_swap(B, Cin, Cout, H, W, k, precision):
         assert float((out[0].double() - ref).norm() / ref.norm()) < (1e-5 if precision == "bf16" else 1e-4)
     finally:
         E.set_conv_precision(old)
+
+
+WGCOL_CASES = [(1, 8, 16, 64, 24), (2, 16, 128, 136, 24), (1, 45, 22, 88, 24), (1, 5, 200, 88, 24), (1, 32, 64, 80, 20), (1, 16, 128, 112, 8), (3, 64, 128, 160, 24), (1, 9, 13, 16, 3)]
+
+
+@pytest.mark.parametrize("case", WGCOL_CASES, ids=[f"b{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}" for c in WGCOL_CASES])
+def test_wgrad_narrow_output_kernel(case):
+    """conv_tc_wgrad_col_kernel (weight gradient of the DenseNet growth convolutions, generator.py:34: the shifted operand is dy, one MMA chain per pixel
+    tile) against float64 on the same bf16-rounded operands (fp32-accumulation accuracy) and against the general weight-gradient kernel; bitwise
+    repeatable; the accumulate flag adds."""
+    from gan_danet_b200 import _lib, engine as E
+    B, H, W, Cin, Cout = case
+    dev = torch.device("cuda", 0)
+    lib = _lib.lib_for_device(0)
+    g = torch.Generator().manual_seed(Cin * 7 + H)
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev)
+    dy = torch.randn(B, H, W, Cout, generator=g).to(dev)
+    old = E.conv_precision
+    E.set_conv_precision("bf16")
+    try:
+        xp, dyp = E.pack_act(x), E.pack_act(dy)
+        res = {}
+        for col, row in ((0, 1), (1, 1), (1, 1), (2, 0)):       # general kernel; narrow kernel (twice: determinism, accumulate); narrow kernel without the row variant
+            prev, prev_row = lib.gdn_conv_tc_set_wgrad_col(1 if col else 0), lib.gdn_conv_tc_set_wgrad_col_row(row)
+            try:
+                gw = torch.zeros(Cout, Cin, 3, 3, device=dev)
+                E.wgrad_tc_raw(dyp, xp, gw, B=B, in_hw=(H, W), out_hw=(H, W), cin=Cin, cout=Cout, kh=3, kw=3, pad=1)
+                if col and col in res:
+                    assert torch.equal(gw, res[col])        # deterministic
+                    E.wgrad_tc_raw(dyp, xp, gw, B=B, in_hw=(H, W), out_hw=(H, W), cin=Cin, cout=Cout, kh=3, kw=3, pad=1, accumulate=True)
+                    torch.testing.assert_close(gw, 2 * res[col], rtol=1e-6, atol=1e-6)
+                else:
+                    res[col] = gw.clone()
+            finally:
+                lib.gdn_conv_tc_set_wgrad_col(prev)
+                lib.gdn_conv_tc_set_wgrad_col_row(prev_row)
+        xr, dr = bf16_round(x).double().permute(0, 3, 1, 2), bf16_round(dy).double().permute(0, 3, 1, 2)
+        w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, device=dev, requires_grad=True)
+        (F.conv2d(xr, w, padding=1) * dr).sum().backward()
+        assert rel(res[1], w.grad) < 1e-5 and rel(res[2], w.grad) < 1e-5
+        assert rel(res[1], res[0]) < 2e-5
+    finally:
+        E.set_conv_precision(old)
