@@ -98,6 +98,7 @@ SIGNATURES = {
     "gdn_conv_tc_set_halo": (_i, [_i]),
     "gdn_conv_tc_set_wgrad_swap": (_i, [_i]),
     "gdn_conv_tc_set_wgrad_col": (_i, [_i]),
+    "gdn_conv_tc_set_col": (_i, [_i]),
     "gdn_conv_tc_set_wgrad_col_row": (_i, [_i]),
     "gdn_conv2d_wgrad_tc_ws_bytes": (_sz, [C.POINTER(WgradTcArgs)]),
     "gdn_conv2d_wgrad_tc": (_i, [C.POINTER(WgradTcArgs), _vp]),

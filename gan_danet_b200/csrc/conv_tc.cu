@@ -65,6 +65,7 @@ struct FwdParams {
   int kchunks, n_tile, n_tiles, total_tiles, nsplit, stages, tmem_cols, wt_shift;
   int act; float slope; int vec4; int halo_bo, kgroup;
   int w_resident;             // HALO: all weight tiles of the layer stay in shared memory for the CTA's lifetime (loaded once)
+  int col_k;                  // COL mode: channels of the narrow operand (<= 24)
   TapList taps;
 };
 
@@ -89,20 +90,35 @@ __device__ __forceinline__ uint64_t smem_desc_bo(uint32_t addr, uint32_t sbo_byt
          ((uint64_t)(use_bo ? ((addr >> 7) & 7) : 0) << 49) | ((uint64_t)layout_type << 61);
 }
 
-template <bool HALO>
+// [128 px + 2][8 ch] boxes of a narrow (<= 24 channel) operand, no swizzle: tcgen05's canonical "interleave" layout (8 channels contiguous, pixel rows 16 B
+// apart).  Used as the MN-major A operand of conv_tc_wgrad_col_kernel and as the K-major A operand of the COL mode below.
+constexpr int WR_BOX_BYTES = (BM + 2) * 16;                   // 2080 bytes per box ...
+constexpr int WR_SLOT_BYTES = 17 * 128;                       // ... in slots of 2176: TMA wants 128-byte aligned shared-memory destinations
+constexpr int WR_COL_BYTES = 16 * WR_SLOT_BYTES;              // 34 KB: 16 slots = the 128 accumulator rows of one product (slots >= 3 * G stay zero)
+
+// COL mode (MODE 2, round 2): data gradient of a 3x3 stride-1 "same" convolution whose OUTPUT side is narrow (the DenseNet growth convolutions,
+// generator.py:34: dz has 24 channels).  With one K-iteration per (tap, 64-channel chunk) 24 of 64 K columns did work and nine 18 KB weight tiles were
+// streamed per pixel tile (0.11-0.14 ms per layer, neither MMA- nor HBM-bound).  Here the reduction runs over (kw, kh, co) = 3 x 80 columns as ONE
+// chain of 15 K steps: A = the im2col'd dz tile (3 * G boxes of 130 pixels, the kw shift is the start address; K-major "interleave" layout),
+// B = the packed weights [tap][ci][co], resident in shared memory for the CTA's lifetime as 8-column groups ([n_tile rows][16 B], K-major interleave).
+constexpr int COL_KGROUPS = 10;                               // K groups (of 8) per kw: 3 * G <= 9 real + zero padding to a whole number of K = 16 steps
+template <int MODE>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_constant__ CUtensorMap mapXlo,
                    const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  constexpr bool HALO = MODE == 1, COL = MODE == 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b_bytes = p.n_tile * 128;
   // !HALO: ring of (A tile | W tile) stages.  HALO: ring of HALO_SLOTS halo boxes, then a ring of p.stages W tiles (full/empty barriers).
+  // COL: two im2col'd operand tiles, then the resident weight groups.
   const int sub_bytes = A_BYTES + b_bytes;
   const int stage_bytes = p.kgroup * (HALO ? b_bytes : sub_bytes);
-  const uint32_t ring_off = HALO ? HALO_SLOTS * HALO_SLOT : 0;
-  const uint32_t epi_off = ring_off + p.stages * stage_bytes;
+  const uint32_t ring_off = HALO ? HALO_SLOTS * HALO_SLOT : (COL ? 2 * WR_COL_BYTES : 0);
+  const int col_wstride = p.n_tile * 16;                   // COL: bytes per weight K group ([n_tile rows][8 columns])
+  const uint32_t epi_off = ring_off + (COL ? 3 * COL_KGROUPS * col_wstride : p.stages * stage_bytes);
   const uint32_t bar_base = base + epi_off + EPI_WARPS * EPI_STAGE_BYTES;
   auto full = [&](int s) { return bar_base + 8 * s; };
   auto empty = [&](int s) { return bar_base + 8 * (MAX_STAGES + s); };
@@ -115,6 +131,11 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
   const int KI = p.taps.n * p.nsplit * p.kchunks;          // K-iterations per tile
   const int acc_stride = p.tmem_cols >> 1;                 // column distance of the two accumulator buffers
 
+  if (COL) {      // zero padding groups of both operands (never written by TMA)
+    uint4* z = reinterpret_cast<uint4*>(sm);
+    for (int i = threadIdx.x; i < (int)(epi_off >> 4); i += FWD_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_WARPS); mbar_init(afull(b), 1); mbar_init(aempty(b), 1); }
@@ -132,6 +153,25 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {   // ---- TMA producer
       int it = 0, na = 0;
+      if (COL) {
+        const int G = (p.col_k + 7) >> 3;
+        mbar_expect_tx(full(0), 9 * G * col_wstride);
+        for (int kw = 0; kw < 3; ++kw)
+          for (int kh = 0; kh < 3; ++kh)
+            for (int g = 0; g < G; ++g)
+              tma_load_3d(base + ring_off + (kw * COL_KGROUPS + kh * G + g) * col_wstride, &mapWhi, full(0), g * 8, 0, kh * 3 + kw);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++na) {
+          int t = tile;
+          const int tw = t % p.tiles_w; t /= p.tiles_w;
+          const int th = t % p.tiles_h; t /= p.tiles_h;
+          const int sa = na & 1;
+          if (na >= 2) mbar_wait(aempty(sa), ((na >> 1) - 1) & 1);
+          mbar_expect_tx(afull(sa), 3 * G * WR_BOX_BYTES);
+          for (int kh = 0; kh < 3; ++kh)
+            for (int g = 0; g < G; ++g)      // pixels tw*128 - 1 .. tw*128 + 128 of image row th - (kh - 1): the kw shift is the window's start address
+              tma_load_4d(base + sa * WR_COL_BYTES + (kh * G + g) * WR_SLOT_BYTES, &mapXhi, afull(sa), g * 8, tw * BM - 1, th - (kh - 1), t);
+        }
+      } else {
       if (HALO && p.w_resident) {
         // small layers (e.g. 64 -> 64: 9 x 8 KB): the weights are the same for every tile of this persistent CTA -- load them once instead
         // of once per tile (ncu on the 64 -> 64 layer at 256x512: L2 -> SM traffic 122 KB per tile, 72 KB of it weights; tensor pipe 28 %)
@@ -206,6 +246,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
           }
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ---- MMA issuer.  The whole warp runs the (uniform) loops and waits; one elected lane issues the tcgen05 instructions, whose
@@ -221,7 +262,26 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapXhi, const __grid_cons
       if (lt >= 2) mbar_wait_spin(acc_empty(ab), ((lt >> 1) - 1) & 1);     // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t d_tmem = tmem + ab * acc_stride;
-      if (HALO && p.w_resident) {
+      if (COL) {
+        if (lt == 0) mbar_wait_spin(full(0), 0);
+        mbar_wait_spin(afull(sa), pha);
+        tc_fence_after();
+        const uint32_t idc = idesc_bf16(BM, p.n_tile, 0, 0);
+        // K-major interleave descriptors: LBO = distance of consecutive K groups of 8, SBO = distance of consecutive 8-row groups (128 B)
+        const uint64_t a0 = smem_desc_lbo(base + sa * WR_COL_BYTES, WR_SLOT_BYTES, 128, 0);
+        const uint64_t b0 = smem_desc_lbo(base + ring_off, (uint32_t)col_wstride, 128, 0);
+        if (elect_one()) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int j = 0; j < COL_KGROUPS / 2; ++j)
+              umma_f16(d_tmem, a0 + (uint64_t)(2 - kw) + (uint64_t)((2 * j * WR_SLOT_BYTES) >> 4), b0 + (uint64_t)(((kw * COL_KGROUPS + 2 * j) * col_wstride) >> 4), idc,
+                       (kw > 0 || j > 0) ? 1u : 0u);
+          tc_commit(aempty(sa));
+        }
+        __syncwarp();
+        if (++sa == 2) { sa = 0; pha ^= 1; }
+      } else if (HALO && p.w_resident) {
         for (int kk = 0; kk < p.kchunks * p.nsplit; ++kk) {
           mbar_wait_spin(afull(sa), pha);
           tc_fence_after();
@@ -631,9 +691,6 @@ constexpr int WC_COL_BYTES = WC_GROUPS * WC_GROUP_BYTES;      // 64 KB
 // ROW variant (tiles of one image row, Wt = 128): the three kw-shifts of a (kh, channel group) are ONE box of 130 pixels read at start addresses
 // +0 / +16 / +32 bytes (no swizzle: any 16-byte aligned start is legal), so 3 * G boxes per tile instead of 9 * G (TMA moves these boxes as 16-byte
 // rows: the row count, not the byte count, is what they cost).  Accumulator rows are then ordered (kw, kh, co): three M = 128 products per K step.
-constexpr int WR_BOX_BYTES = (BM + 2) * 16;                   // 2080 bytes per box ...
-constexpr int WR_SLOT_BYTES = 17 * 128;                       // ... in slots of 2176: TMA wants 128-byte aligned shared-memory destinations
-constexpr int WR_COL_BYTES = 16 * WR_SLOT_BYTES;              // 34 KB: 16 slots = the 128 accumulator rows of one product (slots >= 3 * G stay zero)
 constexpr int WC_STAGES = 2;
 struct WcParams {
   float* ws;                   // [ctas][taps * Cout][N] fp32 partial sums
@@ -911,6 +968,20 @@ static int make_weight_map(CUtensorMap* m, const void* ptr, int Kp, int R, int t
   return GDN_OK;
 }
 
+// the packed weights as [n_tile rows][8 columns] boxes without swizzle (COL mode: K groups of the resident weight operand)
+static int make_weight_map8(CUtensorMap* m, const void* ptr, int Kp, int R, int taps, int n_tile) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return GDN_ECUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)R, (cuuint64_t)taps};
+  cuuint64_t gstride[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)R * Kp * 2};
+  cuuint32_t box[3] = {8, (cuuint32_t)n_tile, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(weight groups Kp=%d R=%d taps=%d n_tile=%d) failed (%d)", Kp, R, taps, n_tile, (int)r); return GDN_ECUDA; }
+  return GDN_OK;
+}
+
 // pixel tile shape: Wt = smallest power of two >= min(W, 128) (>= 8), Ht = 128 / Wt
 static void tile_shape(int W, int* Wt, int* Ht) {
   int wt = 8;
@@ -925,12 +996,16 @@ using namespace gdn;
 using namespace gdn::convtc;
 
 static bool g_halo_enabled = true;
+static bool g_col_enabled = true;
+/* test hook: the COL mode of the forward kernel (data gradient with a narrow gradient operand: DenseNet growth convolutions); returns the previous setting */
+extern "C" int gdn_conv_tc_set_col(int enabled) { const int old = g_col_enabled; g_col_enabled = enabled != 0; return old; }
 /* test hook: switch the halo-reuse variant of the forward kernel off (returns the previous setting) */
 extern "C" int gdn_conv_tc_set_halo(int enabled) { const int old = g_halo_enabled; g_halo_enabled = enabled != 0; return old; }
 
 extern "C" int gdn_conv_tc_init(void) {
-  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   GDN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1078,6 +1153,20 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
     bool halo = g_halo_enabled && p.cs == 1 && p.os == 1 && p.Wt == BM && p.Ht == 1 && p.taps.n == 9 && halo_shape;
     for (int tp = 0; tp < p.taps.n && halo; ++tp) halo = p.taps.dh[tp] >= -1 && p.taps.dh[tp] <= 1 && p.taps.dw[tp] >= -1 && p.taps.dw[tp] <= 1;
     CUtensorMap mxh, mxl, mwh, mwl;
+    // COL mode: narrow-operand data gradient (see the kernel): one-row tiles of 128 pixels, one output-channel tile, bf16
+    const size_t smem_col = (size_t)2 * WR_COL_BYTES + (size_t)3 * COL_KGROUPS * p.n_tile * 16 + EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * MAX_STAGES + 10) + 1024;
+    const bool col = g_col_enabled && a->transposed && a->stride == 1 && a->kh == 3 && a->kw == 3 && a->pad == 1 && nsplit == 1 && groups == 1 && a->Cin <= 24 &&
+                     p.Wt == BM && p.Ht == 1 && n_tiles == 1 && smem_col <= (size_t)SMEM_LIMIT;
+    if (col) {
+      FwdParams pc = p;
+      pc.col_k = a->Cin; pc.stages = 1;
+      if ((rc = make_act_map8(&mxh, a->x_hi, Cp, a->Wi, a->Hi, a->B, BM + 2, 1)) != GDN_OK) return rc;
+      if ((rc = make_weight_map8(&mwh, a->w_hi, Cp, a->Cout, taps * groups, p.n_tile)) != GDN_OK) return rc;
+      const int gridc = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+      conv_tc_fwd_kernel<2><<<gridc, FWD_THREADS, smem_col, st>>>(mxh, mxh, mwh, mwh, pc);
+      GDN_CHECK_LAUNCH();
+      continue;
+    }
     const int bw = halo ? HALO_W : p.Wt, bh = halo ? HALO_ROWS : p.Ht;
     if ((rc = make_act_map(&mxh, a->x_hi, Cp, a->Wi, a->Hi, a->B, bw, bh, p.cs)) != GDN_OK) return rc;
     mxl = mxh;
@@ -1098,9 +1187,9 @@ extern "C" int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s) {
       if (ph.w_resident) { ph.kgroup = 9; ph.stages = p.kchunks * nsplit; if (ph.stages > MAX_STAGES) ph.stages = MAX_STAGES; }   // ring area = the resident weight block
       const size_t smem_h = (size_t)HALO_SLOTS * HALO_SLOT + (ph.w_resident ? (size_t)w_all : (size_t)ph.stages * ph.kgroup * b_bytes) + EPI_WARPS * EPI_STAGE_BYTES +
                             8 * (2 * MAX_STAGES + 10) + 1024;
-      conv_tc_fwd_kernel<true><<<grid, FWD_THREADS, smem_h, st>>>(mxh, mxl, mwh, mwl, ph);
+      conv_tc_fwd_kernel<1><<<grid, FWD_THREADS, smem_h, st>>>(mxh, mxl, mwh, mwl, ph);
     } else {
-      conv_tc_fwd_kernel<false><<<grid, FWD_THREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);
+      conv_tc_fwd_kernel<0><<<grid, FWD_THREADS, smem, st>>>(mxh, mxl, mwh, mwl, p);
     }
     GDN_CHECK_LAUNCH();
   }

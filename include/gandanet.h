@@ -152,6 +152,9 @@ typedef struct {
 int gdn_conv2d_tc(const gdn_conv_tc_args* a, gdn_stream_t s);
 /* test hook: enable/disable the halo-reuse variant of the forward kernel (stride-1 3x3, narrow output tiles); returns the old setting */
 int gdn_conv_tc_set_halo(int enabled);
+/* test hook: enable/disable the COL mode of the forward kernel (data gradient of 3x3 stride-1 "same" convolutions with at most 24 output channels --
+ * the DenseNet growth convolutions of generator.py:34 -- as one K = 3 x 80 product over the im2col'd gradient tile with resident weights) */
+int gdn_conv_tc_set_col(int enabled);
 /* test hook: enable/disable the role-swapped weight gradient for narrow outputs (Cout <= 32, the DenseNet growth convolutions of generator.py:34) */
 int gdn_conv_tc_set_wgrad_swap(int enabled);
 /* test hook: enable/disable the narrow-output weight-gradient kernel (3x3 stride-1 "same" convolutions with Cout <= 24 and Cin <= 192 in the bf16 precision --

@@ -294,3 +294,39 @@ def test_wgrad_narrow_output_kernel(case):
         assert rel(res[1], res[0]) < 2e-5
     finally:
         E.set_conv_precision(old)
+
+
+COL_CASES = [(1, 16, 128, 136, 24), (2, 3, 256, 112, 24), (1, 8, 128, 64, 20), (1, 5, 128, 160, 8), (1, 7, 128, 248, 24), (3, 64, 128, 88, 24)]
+
+
+@pytest.mark.parametrize("case", COL_CASES, ids=[f"b{c[0]}_{c[1]}x{c[2]}_{c[4]}to{c[3]}" for c in COL_CASES])
+def test_dgrad_narrow_gradient_col_mode(case):
+    """COL mode of the forward kernel (data gradient of the DenseNet growth convolutions, generator.py:34: one K = 3 x 80 product over the im2col'd
+    24-channel gradient tile, weights resident) against float64 on the same bf16-rounded operands and against the per-tap kernel, with the
+    accumulating epilogue (res = the gradient buffer itself) the dense block uses."""
+    from gan_danet_b200 import _lib, engine as E
+    B, H, W, Cin, Cout = case
+    dev = torch.device("cuda", 0)
+    lib = _lib.lib_for_device(0)
+    g = torch.Generator().manual_seed(Cin * 3 + W)
+    dy = torch.randn(B, H, W, Cout, generator=g).to(dev)
+    w = (0.1 * torch.randn(Cout, Cin, 3, 3, generator=g)).to(dev)
+    res0 = torch.randn(B, H, W, Cin, generator=g).to(dev)
+    old = E.conv_precision
+    E.set_conv_precision("bf16")
+    try:
+        dyp, wt = E.pack_act(dy), E.pack_weight(w, True)
+        outs = []
+        for col in (0, 1, 1):
+            prev = lib.gdn_conv_tc_set_col(col)
+            try:
+                gx = res0.clone()
+                E.conv_tc_raw(dyp, wt, gx, (H, W), cin=Cout, kh=3, kw=3, pad=1, transposed=True, res=gx)
+                outs.append(gx)
+            finally:
+                lib.gdn_conv_tc_set_col(prev)
+        ref = F.conv_transpose2d(bf16_round(dy).double().permute(0, 3, 1, 2), bf16_round(w).double(), padding=1).permute(0, 2, 3, 1) + res0.double()
+        assert rel(outs[1], ref) < 1e-5 and rel(outs[0], ref) < 1e-5
+        assert torch.equal(outs[1], outs[2])
+    finally:
+        E.set_conv_precision(old)

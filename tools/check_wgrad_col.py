@@ -38,3 +38,32 @@ for case in ((1, 8, 16, 64, 24), (2, 16, 128, 136, 24), (1, 45, 22, 88, 24), (1,
     run(*case)
 for Cin in (64, 88, 136, 160):
     run(32, 64, 128, Cin, 24, timing=True)
+
+
+def run_dgrad(B, H, W, Cin, Cout, timing=False):
+    """data gradient of the Cin -> Cout convolution (Cout narrow): COL mode against the per-tap kernel and float64"""
+    g = torch.Generator().manual_seed(Cin * 3 + W)
+    dy = torch.randn(B, H, W, Cout, generator=g).to(dev)
+    w = (0.1 * torch.randn(Cout, Cin, 3, 3, generator=g)).to(dev)
+    res0 = torch.randn(B, H, W, Cin, generator=g).to(dev)
+    dyp, wt = E.pack_act(dy), E.pack_weight(w, True)
+    outs = {}
+    for name, col in (("per-tap", 0), ("col", 1)):
+        lib.gdn_conv_tc_set_col(col)
+        gx = res0.clone()
+        fn = lambda: E.conv_tc_raw(dyp, wt, gx, (H, W), cin=Cout, kh=3, kw=3, pad=1, transposed=True, res=gx)
+        fn(); torch.cuda.synchronize()
+        out = gx.clone(); t = None
+        if timing:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10): fn()
+            e1.record(); torch.cuda.synchronize(); t = e0.elapsed_time(e1) / 10
+        outs[name] = (out, t)
+    lib.gdn_conv_tc_set_col(1)
+    ref = F.conv_transpose2d(dy.to(torch.bfloat16).double().permute(0, 3, 1, 2), w.to(torch.bfloat16).double(), padding=1).permute(0, 2, 3, 1) + res0.double()
+    print(f"dgrad B{B} {H}x{W} C{Cout}->{Cin}: " + "  ".join(f"{k}: vs f64 {rel(v[0], ref):.2e}" + (f" {v[1]*1e3:.0f} us" if v[1] else "") for k, v in outs.items()), flush=True)
+for case in ((1, 16, 128, 136, 24), (2, 3, 256, 112, 24), (1, 8, 128, 64, 20), (1, 5, 128, 160, 8), (1, 7, 128, 248, 24)):
+    run_dgrad(*case)
+for Cin in (64, 88, 136, 160):
+    run_dgrad(32, 64, 128, Cin, 24, timing=True)
