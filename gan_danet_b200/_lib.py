@@ -113,9 +113,10 @@ SIGNATURES = {
     "gdn_thin_conv_expand_p": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "gdn_thin_conv_reduce": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "gdn_thin_conv_reduce_gated": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "gdn_thin_conv_tap_l1_supported": (_i, [_i, _i, _i]),
-    "gdn_thin_conv_tap_l1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _f, _vp, _sz, _vp]),
-    "gdn_thin_conv_tap_dgrad": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "gdn_thin_conv_tap_supported": (_i, [_i, _i, _i]),
+    "gdn_thin_conv_tap_mask_bytes": (_sz, [_i, _i, _i, _i]),
+    "gdn_thin_conv_tap_pair": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gdn_thin_conv_tap_dgrad": (_i, [_vp, _i, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gdn_thin_conv_wgrad_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "gdn_thin_conv_wgrad": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "gdn_colstats_ws_bytes": (_sz, [_ll, _i]),

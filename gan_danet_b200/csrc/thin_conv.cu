@@ -96,18 +96,23 @@ __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ S
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------- L1 term of a tapped 1 -> C conv + ReLU
-// partial[block] = sum over pixels and channels of | relu(conv(Sa))[p][c] - relu(conv(Sb))[p][c] |   (3x3, stride 1, pad 1)
-// The perceptual loss taps relu1_1 (losses.py:60-72 with feature_layers containing 1): conv1_1 has ONE input channel here (the channel-summed
-// weight), so both 64-channel maps are 9 FMAs per element away from the two single-channel images.  Recomputing them costs less than
-// reading them: the fp32 maps (2 x 1.07 GB at 256x512, batch 32) are never written, and the L1 pass (2.1 GB read, 1 GB gradient written)
-// does not exist.  Same FMA order as expand_kernel => the recomputed features are bitwise the ones expand_kernel would have stored.
+// ---------------------------------------------------------------------------------------------------------------- tapped 1 -> C conv + ReLU of an image PAIR
+// The perceptual loss taps relu1_1 (losses.py:60-72 with feature_layers containing 1) and conv1_1 has ONE input channel here (the channel-summed
+// weight, losses.py:64-65): both 64-channel maps are 9 FMAs per element away from the two single-channel images.  One pass over the two images
+//   * writes both maps ONLY as the bf16 operands of conv1_2 (V16a generated, V16b target),
+//   * accumulates the L1 term  sum | relu(conv Sa) - relu(conv Sb) |,
+//   * and keeps what the backward pass needs of the two fp32 maps -- 2 bits per element: 0 = ReLU closed (fa <= 0), else 2 + sign(fa' - fb') --
+//     as one byte per (pixel, 4 channels): 67 MB instead of 2 x 1.07 GB at 256x512, batch 32.
+// The fp32 maps (2 x 1.07 GB written), the L1 pass over them (2.1 GB read, 1 GB of gradient written and re-read) never exist.  Same FMA order as
+// expand_kernel => gate, sign and bf16 operands are bitwise those of the stored-map path.
 template <int PX>
-__global__ void __launch_bounds__(256, 2) l1_fields_kernel(const float* __restrict__ Sa, const float* __restrict__ Sb, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, Geo g, double* __restrict__ partial) {
+__global__ void __launch_bounds__(256, 2) tap_pair_kernel(const float* __restrict__ Sa, const float* __restrict__ Sb, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, Geo g, double* __restrict__ partial,
+                                                          __nv_bfloat16* __restrict__ V16a, __nv_bfloat16* __restrict__ V16b, uint8_t* __restrict__ mask) {
   constexpr int NC = PX + 2;
   const int lanes = g.C >> 2;
-  const int c = (threadIdx.x % lanes) << 2;
+  const int lc = threadIdx.x % lanes;
+  const int c = lc << 2;
   float2 w01[9], w23[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(256, 2) l1_fields_kernel(const float* __restri
         }
       }
     }
+    const size_t p = ((size_t)b * g.Hv + y) * g.Wv + x0;
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
       float2 a01 = make_float2(bv.x, bv.y), a23 = make_float2(bv.z, bv.w), b01 = a01, b23 = a23;
@@ -156,8 +162,25 @@ __global__ void __launch_bounds__(256, 2) l1_fields_kernel(const float* __restri
           a01 = __ffma2_rn(s2, w01[kh * 3 + kw], a01); a23 = __ffma2_rn(s2, w23[kh * 3 + kw], a23);
           b01 = __ffma2_rn(t2, w01[kh * 3 + kw], b01); b23 = __ffma2_rn(t2, w23[kh * 3 + kw], b23);
         }
-      acc += fabsf(fmaxf(a01.x, 0.f) - fmaxf(b01.x, 0.f)) + fabsf(fmaxf(a01.y, 0.f) - fmaxf(b01.y, 0.f));
-      acc += fabsf(fmaxf(a23.x, 0.f) - fmaxf(b23.x, 0.f)) + fabsf(fmaxf(a23.y, 0.f) - fmaxf(b23.y, 0.f));
+      const float fa[4] = {a01.x, a01.y, a23.x, a23.y};
+      const float ra[4] = {fmaxf(a01.x, 0.f), fmaxf(a01.y, 0.f), fmaxf(a23.x, 0.f), fmaxf(a23.y, 0.f)};
+      const float rb[4] = {fmaxf(b01.x, 0.f), fmaxf(b01.y, 0.f), fmaxf(b23.x, 0.f), fmaxf(b23.y, 0.f)};
+      unsigned code = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = ra[e] - rb[e];
+        acc += fabsf(d);
+        code |= (fa[e] > 0.f ? (d > 0.f ? 3u : (d < 0.f ? 1u : 2u)) : 0u) << (2 * e);
+      }
+      if (V16a) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(ra[0], ra[1]), h1 = __floats2bfloat162_rn(ra[2], ra[3]);
+        *reinterpret_cast<uint2*>(V16a + (p + i) * g.C + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
+      if (V16b) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(rb[0], rb[1]), h1 = __floats2bfloat162_rn(rb[2], rb[3]);
+        *reinterpret_cast<uint2*>(V16b + (p + i) * g.C + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
+      if (mask) mask[(p + i) * lanes + lc] = (uint8_t)code;
     }
     if (++cnt == 4) { dacc += (double)acc; acc = 0.f; cnt = 0; }
   }
@@ -183,19 +206,15 @@ __global__ void __launch_bounds__(256) l1_fields_finish_kernel(const double* __r
 // gradient of the 1 -> C conv: v = (q + pad - k) / stride when divisible.  Fixed summation order: deterministic.
 constexpr int RT_H = 16, RT_W = 32, R_MAXPIX = (RT_H + 2) * (RT_W + 2);
 
-// RECOMP (data gradient of a tapped 1 -> C conv + ReLU, stride 1, pad 1: VGG19 conv1_1 with the L1 term at relu1_1): neither the activation output
-// (the gate) nor the L1 term's gradient exists in memory; both are recomputed from the two single-channel fields Fa (generated) and Fb (target):
-//   f = relu(conv(F) + cbias),  dz[p][c] = (V[p][c] + gcoef * sign(fa - fb)) * [fa > 0]
-// in expand_kernel's FMA order, so gate and seed are bitwise what the stored maps would have given.
-constexpr int RF_H = RT_H + 4, RF_W = RT_W + 4;
-template <int CPL, bool RECOMP = false>   // channels per lane: C = 8 * CPL
+// MASKED (data gradient of a tapped 1 -> C conv + ReLU, stride 1, pad 1: VGG19 conv1_1 with the L1 term at relu1_1): neither the activation output
+// (the gate) nor the L1 term's gradient exists as a tensor; tap_pair_kernel left 2 bits per element (one byte per pixel and 4 channels):
+//   code 0: ReLU closed, dz = 0;   else dz[p][c] = V[p][c] + (code - 2) * gcoef      (code - 2 = sign(fa' - fb'))
+template <int CPL, bool MASKED = false>   // channels per lane: C = 8 * CPL
 __global__ void __launch_bounds__(256, CPL <= 8 ? 2 : 1) reduce_kernel(const float* __restrict__ V, int v_pitch, const float* __restrict__ w, const float* __restrict__ bias,
                                                                        float* S, const float* res /* may alias S */, Geo g, int transposed, int tiles_x, int tiles_y,
                                                                        const float* __restrict__ gate, int gate_pitch, float gate_slope,
-                                                                       const float* __restrict__ Fa = nullptr, const float* __restrict__ Fb = nullptr,
-                                                                       const float* __restrict__ cbias = nullptr, float gcoef = 0.f) {
+                                                                       const uint8_t* __restrict__ mask = nullptr, float gcoef = 0.f) {
   __shared__ float Ts[9][R_MAXPIX + 4];
-  __shared__ float Fs[RECOMP ? 2 : 1][RECOMP ? RF_H * RF_W : 1];
   constexpr int NJ = CPL / 4;
   const int lane8 = threadIdx.x & 7, slot = threadIdx.x >> 3;   // 32 pixel slots per pass
   float wr[NJ][4][9];
@@ -222,12 +241,20 @@ __global__ void __launch_bounds__(256, CPL <= 8 ? 2 : 1) reduce_kernel(const flo
   const float* gb = gate ? gate + (size_t)b * g.Hv * g.Wv * gate_pitch + lane8 * 4 : nullptr;
   // gate: V is the gradient of an activation's OUTPUT and gate that output (ReLU / LeakyReLU): the wide tensor is multiplied by act'(gate) while it is
   // loaded, so that the activation backward is not a pass of its own (1 GB read + 1 GB written per 64-channel 256x512 batch of 32)
-  auto load = [&](int i, float4* dst) {
+  const uint8_t* mb = MASKED ? mask + (size_t)b * g.Hv * g.Wv * (g.C >> 2) + lane8 : nullptr;
+  auto load = [&](int i, float4* dst, unsigned& mk) {
     const int ry = i / vx_n, rx = i - ry * vx_n;
     const int vy = vy_lo + ry, vx = vx_lo + rx;
     const bool ok = i < n && vy >= 0 && vy < g.Hv && vx >= 0 && vx < g.Wv;
     const size_t pix = (size_t)(ok ? vy * g.Wv + vx : 0);
     const float* src = vb + pix * v_pitch;
+    if (MASKED) {
+      mk = 0u;
+      if (ok) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) mk |= (unsigned)__ldg(mb + pix * (g.C >> 2) + j * 8) << (8 * j);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       dst[j] = ok ? __ldg(reinterpret_cast<const float4*>(src + j * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -240,50 +267,21 @@ __global__ void __launch_bounds__(256, CPL <= 8 ? 2 : 1) reduce_kernel(const flo
   };
   const bool b2 = lane8 & 4, b1 = lane8 & 2, b0 = lane8 & 1;
   float4 cur[NJ], nxt[NJ];
-  load(slot, cur);
-  const int fw = vx_n + 2;
-  float cb[NJ][4];
-  if (RECOMP) {
-    // the two fields' tile: rows vy_lo - 1 .. vy_lo + vy_n, columns vx_lo - 1 .. vx_lo + vx_n, zero outside the image (the convolution's padding)
-    const size_t fo = (size_t)b * g.Hs * g.Ws;
-    for (int idx = threadIdx.x; idx < (vy_n + 2) * fw; idx += 256) {
-      const int fy = vy_lo - 1 + idx / fw, fx = vx_lo - 1 + idx % fw;
-      const bool ok = fy >= 0 && fy < g.Hs && fx >= 0 && fx < g.Ws;
-      Fs[0][idx] = ok ? __ldg(Fa + fo + (size_t)fy * g.Ws + fx) : 0.f;
-      Fs[RECOMP ? 1 : 0][idx] = ok ? __ldg(Fb + fo + (size_t)fy * g.Ws + fx) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < NJ; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) cb[j][e] = cbias ? __ldg(cbias + j * 32 + lane8 * 4 + e) : 0.f;
-    __syncthreads();
-  }
+  unsigned mcur = 0u, mnxt = 0u;
+  load(slot, cur, mcur);
   for (int ps = 0; ps < passes; ++ps) {
     const int i = ps * 32 + slot;
-    load(i + 32, nxt);                      // next pass in flight while this one is reduced (i + 32 >= n loads nothing)
-    if (RECOMP) {
-      const int ry = i / vx_n, rx = i - ry * vx_n;
-      const int vy = vy_lo + ry, vx = vx_lo + rx;
-      if (i < n && vy >= 0 && vy < g.Hv && vx >= 0 && vx < g.Wv) {
-        float2 win[9];                      // (generated, target) field values under the nine taps of this pixel
+    load(i + 32, nxt, mnxt);                // next pass in flight while this one is reduced (i + 32 >= n loads nothing)
+    if (MASKED) {
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+      for (int j = 0; j < NJ; ++j) {
+        float cv[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) win[kh * 3 + kw] = make_float2(Fs[0][(ry + kh) * fw + rx + kw], Fs[RECOMP ? 1 : 0][(ry + kh) * fw + rx + kw]);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          float cv[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float2 f = make_float2(cb[j][e], cb[j][e]);
-#pragma unroll
-            for (int k = 0; k < 9; ++k) f = __ffma2_rn(win[k], make_float2(wr[j][e][k], wr[j][e][k]), f);
-            const float d = fmaxf(f.x, 0.f) - fmaxf(f.y, 0.f);
-            const float seed = d > 0.f ? gcoef : (d < 0.f ? -gcoef : 0.f);
-            cv[e] = f.x > 0.f ? cv[e] + seed : 0.f;
-          }
-          cur[j] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        for (int e = 0; e < 4; ++e) {
+          const unsigned code = (mcur >> (8 * j + 2 * e)) & 3u;
+          cv[e] = code ? fmaf((float)((int)code - 2), gcoef, cv[e]) : 0.f;
         }
+        cur[j] = make_float4(cv[0], cv[1], cv[2], cv[3]);
       }
     }
     // nine per-tap dot products over this lane's channels: taps in pairs on the packed fp32x2 FMA (5 instead of 9 instructions per channel)
@@ -324,6 +322,7 @@ __global__ void __launch_bounds__(256, CPL <= 8 ? 2 : 1) reduce_kernel(const flo
     }
 #pragma unroll
     for (int j = 0; j < NJ; ++j) cur[j] = nxt[j];
+    mcur = mnxt;
   }
   __syncthreads();
   const float bs = bias ? __ldg(bias) : 0.f;
@@ -586,34 +585,36 @@ extern "C" int gdn_thin_conv_reduce_gated(const float* v_in, int v_pitch, const 
   return GDN_OK;
 }
 
-extern "C" int gdn_thin_conv_tap_l1_supported(int C, int H, int W) { return thin_ok(C) && C <= 64 && W % 4 == 0 && H > 0; }
-extern "C" int gdn_thin_conv_tap_l1(const float* fa, const float* fb, const float* w, const float* cbias, int B, int H, int W, int C, float* loss, int loss_accumulate,
-                                    float scale, void* ws, size_t ws_bytes, gdn_stream_t st) {
-  GDN_CHECK_ARG(fa && fb && w && loss && ws && gdn_thin_conv_tap_l1_supported(C, H, W) && (!cbias || ((uintptr_t)cbias & 15) == 0));
-  GDN_CHECK_ARG((long long)B * H * W < (1ll << 31));
+extern "C" int gdn_thin_conv_tap_supported(int C, int H, int W) { return thin_ok(C) && C <= 64 && W % 4 == 0 && H > 0; }
+extern "C" size_t gdn_thin_conv_tap_mask_bytes(int B, int H, int W, int C) { return (size_t)B * H * W * (C / 4); }
+extern "C" int gdn_thin_conv_tap_pair(const float* fa, const float* fb, const float* w, const float* cbias, int B, int H, int W, int C, float* loss, int loss_accumulate,
+                                      float scale, uint16_t* v16a, uint16_t* v16b, uint8_t* mask, void* ws, size_t ws_bytes, gdn_stream_t st) {
+  GDN_CHECK_ARG(fa && fb && w && loss && ws && gdn_thin_conv_tap_supported(C, H, W) && (!cbias || ((uintptr_t)cbias & 15) == 0));
+  GDN_CHECK_ARG((long long)B * H * W < (1ll << 31) && ((uintptr_t)v16a & 7) == 0 && ((uintptr_t)v16b & 7) == 0);
   Geo g = {B, H, W, C, H, W, 1, 1};
   const int gpp = 256 / (C / 4);
   long long blocks = cdiv((long long)B * H * (W / 4), gpp);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-  if (ws_bytes < (size_t)blocks * sizeof(double)) { set_error("gdn_thin_conv_tap_l1: workspace too small"); return GDN_EWORKSPACE; }
+  if (ws_bytes < (size_t)blocks * sizeof(double)) { set_error("gdn_thin_conv_tap_pair: workspace too small"); return GDN_EWORKSPACE; }
   cudaStream_t s = as_stream(st);
-  l1_fields_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(fa, fb, w, cbias, g, reinterpret_cast<double*>(ws));
+  tap_pair_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(fa, fb, w, cbias, g, reinterpret_cast<double*>(ws), reinterpret_cast<__nv_bfloat16*>(v16a),
+                                                       reinterpret_cast<__nv_bfloat16*>(v16b), mask);
   GDN_CHECK_LAUNCH();
   l1_fields_finish_kernel<<<1, 256, 0, s>>>(reinterpret_cast<const double*>(ws), (int)blocks, (double)scale / ((double)B * H * W * C), loss, loss_accumulate);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }
-extern "C" int gdn_thin_conv_tap_dgrad(const float* dy, int dy_pitch, const float* fa, const float* fb, const float* w, const float* cbias, float gcoef, float* s_out,
-                                       const float* res, int B, int H, int W, int C, gdn_stream_t st) {
-  GDN_CHECK_ARG(dy && fa && fb && w && s_out && gdn_thin_conv_tap_l1_supported(C, H, W) && dy_pitch >= C && dy_pitch % 4 == 0 && ((uintptr_t)dy & 15) == 0);
+extern "C" int gdn_thin_conv_tap_dgrad(const float* dy, int dy_pitch, const uint8_t* mask, const float* w, float gcoef, float* s_out, const float* res,
+                                       int B, int H, int W, int C, gdn_stream_t st) {
+  GDN_CHECK_ARG(dy && mask && w && s_out && gdn_thin_conv_tap_supported(C, H, W) && dy_pitch >= C && dy_pitch % 4 == 0 && ((uintptr_t)dy & 15) == 0);
   GDN_CHECK_ARG((long long)B * H * W < (1ll << 31));
   Geo g = {B, H, W, C, H, W, 1, 1};
   const int tiles_x = (int)cdiv(W, RT_W), tiles_y = (int)cdiv(H, RT_H);
   const long long blocks = (long long)B * tiles_x * tiles_y;
   GDN_CHECK_ARG(blocks < (1ll << 31));
   cudaStream_t s = as_stream(st);
-  if (C == 32) reduce_kernel<4, true><<<(unsigned)blocks, 256, 0, s>>>(dy, dy_pitch, w, nullptr, s_out, res, g, 1, tiles_x, tiles_y, nullptr, 0, 0.f, fa, fb, cbias, gcoef);
-  else reduce_kernel<8, true><<<(unsigned)blocks, 256, 0, s>>>(dy, dy_pitch, w, nullptr, s_out, res, g, 1, tiles_x, tiles_y, nullptr, 0, 0.f, fa, fb, cbias, gcoef);
+  if (C == 32) reduce_kernel<4, true><<<(unsigned)blocks, 256, 0, s>>>(dy, dy_pitch, w, nullptr, s_out, res, g, 1, tiles_x, tiles_y, nullptr, 0, 0.f, mask, gcoef);
+  else reduce_kernel<8, true><<<(unsigned)blocks, 256, 0, s>>>(dy, dy_pitch, w, nullptr, s_out, res, g, 1, tiles_x, tiles_y, nullptr, 0, 0.f, mask, gcoef);
   GDN_CHECK_LAUNCH();
   return GDN_OK;
 }

@@ -263,19 +263,17 @@ class PerceptualLoss(nn.Module):
     def _features_bf16(self, tape: E.Tape, x: E.Var, on_feature, plan, tap1: Optional[dict] = None) -> None:
         """Same features with bf16-only storage of the untapped maps (conv precision 'bf16': the next conv would round them to bf16
         anyway): every conv epilogue writes the next conv's packed operand, max-pool runs on bf16, only tapped maps exist in fp32.
-        ``tap1`` (see _tap1_recompute_ok): relu1_1 is tapped but never stored -- conv1_1 emits only conv1_2's bf16 operand, the L1 term
-        and its gradient are recomputed from the single-channel images (``tap1['target']``: the other branch's image, None on that branch)."""
+        ``tap1`` (see _tap1_recompute_ok / _tap1_pair): relu1_1 is tapped but never stored -- ``tap1['y16']`` is this branch's conv1_1 + ReLU output as
+        the bf16 operand of conv1_2, ``tap1['mask']`` (generated branch) the 2-bit gate / L1-sign codes its backward pass needs."""
         fp32_convs, last_conv = plan
         layers = list(self.vgg)
         cur, cur16 = x, None
         for idx, layer in enumerate(layers):
             if idx == 0 and tap1 is not None:
-                w, key = self._weights(0, layer, 1)
-                cur, cur16 = _frozen_conv1_tap(tape, x, w, layer.bias.detach(), tap1.get("target"))
+                cur, cur16 = _frozen_conv1_tap(tape, x, self._weights(0, layer, 1)[0], tap1["y16"], tap1.get("mask"))
                 continue
             if idx == 1 and tap1 is not None:
-                on_feature(1, cur, (x.t, self._weights(0, layers[0], 1)[0], layers[0].bias.detach()))
-                continue
+                continue            # the tap's L1 term was accumulated by the pair kernel (PerceptualLoss._tap1_pair)
             if isinstance(layer, nn.Conv2d):
                 # a recorded (gradient-carrying) max-pool routes the gradient to the arg-max of the fp32 map: bf16 rounding creates ties
                 # that "first maximum in scan order" would break differently (measured: 4 % change of dL/dx), so the maps feeding a
@@ -304,7 +302,7 @@ class PerceptualLoss(nn.Module):
         if plan is None or plan[1] == 0 or not isinstance(layers[0], nn.Conv2d) or layers[0].kernel_size != (3, 3) or layers[0].padding != (1, 1) \
                 or layers[0].stride != (1, 1) or layers[0].bias is None or not isinstance(layers[2], nn.Conv2d):
             return False
-        return bool(L.load().gdn_thin_conv_tap_l1_supported(layers[0].out_channels, x.shape[2], x.shape[3]))
+        return bool(L.load().gdn_thin_conv_tap_supported(layers[0].out_channels, x.shape[2], x.shape[3]))
 
     def _bf16_plan_for(self, H: int, W: int, cin0: int):
         """_bf16_plan() if the bf16 feature-map path applies to an input of this grid and channel count, else None."""
@@ -345,35 +343,55 @@ class PerceptualLoss(nn.Module):
             if idx in self.feature_layers:
                 on_feature(idx, cur)
 
-    def _target_features(self, y: torch.Tensor, rec: bool):
+    def _tap1_pair(self, xin: torch.Tensor, yin: torch.Tensor, loss: torch.Tensor, need_mask: bool):
+        """conv1_1 + ReLU of both branches in ONE pass over the two single-channel images (gdn_thin_conv_tap_pair): the bf16 operands of conv1_2
+        (generated, target), the relu1_1 L1 term added to ``loss``, and the 2-bit gate / sign codes for the backward pass."""
+        conv = self.vgg[0]
+        w = self._weights(0, conv, 1)[0]
+        B, H, W, _ = xin.shape
+        O = w.shape[0]
+        dev = xin.device
+        lib = E._lib(xin)
+        y16a = torch.empty((B * H * W, O), dtype=torch.bfloat16, device=dev)
+        y16b = torch.empty((B * H * W, O), dtype=torch.bfloat16, device=dev)
+        mask = torch.empty(lib.gdn_thin_conv_tap_mask_bytes(B, H, W, O), dtype=torch.uint8, device=dev) if need_mask else None
+        ws = E.dot_ws(dev)
+        L.check(lib.gdn_thin_conv_tap_pair(xin.data_ptr(), yin.data_ptr(), w.contiguous().data_ptr(), conv.bias.detach().data_ptr(), B, H, W, O, loss.data_ptr(), 1, 1.0,
+                                           y16a.data_ptr(), y16b.data_ptr(), E._ptr(mask), ws.data_ptr(), ws.numel(), E._stream()), "gdn_thin_conv_tap_pair")
+        return y16a, y16b, mask
+
+    def _target_features(self, y: torch.Tensor, tap1: Optional[dict] = None, yin: Optional[E.Var] = None):
         """Forward-only features of the target branch: (NHWC input Var, {tap index: tensor})."""
         ytape = E.Tape(record=False)
         yfeat: Dict[int, torch.Tensor] = {}
-        yin = E.op_from_nchw(ytape, y.detach(), False)
-        self._features(ytape, yin, lambda i, f, info=None: yfeat.__setitem__(i, f.t), tap1={"target": None} if rec else None)
+        if yin is None:
+            yin = E.op_from_nchw(ytape, y.detach(), False)
+        self._features(ytape, yin, lambda i, f: yfeat.__setitem__(i, f.t), tap1=tap1)
         return yin, yfeat
 
     def prefetch_target(self, y: torch.Tensor, stream: "torch.cuda.Stream") -> None:
         """Evaluates the target branch (it depends on ``y`` alone: the real field of GAN_DANet_train.ipynb:265) on ``stream``, forked from the
         current stream, so that it runs beside whatever is enqueued next (the trainer: the generator's forward pass).  The next ``forward(x, y)``
-        with this ``y`` joins the stream and uses the result.  The cached tensors live in ``stream``'s allocator pool: they are released before
-        the next prefetch forks from the consumer stream again, so a recycled block is never written while the consumer still reads it."""
+        with this ``y`` joins the stream and uses the result.  Not used when relu1_1 is evaluated by the pair kernel (which needs both images).
+        The cached tensors live in ``stream``'s allocator pool: they are released before the next prefetch forks from the consumer stream again,
+        so a recycled block is never written while the consumer still reads it."""
+        self._prefetched = None
+        if self._tap1_recompute_ok(y):
+            return
         cur = torch.cuda.current_stream(y.device)
         stream.wait_stream(cur)
-        rec = self._tap1_recompute_ok(y)
-        self._prefetched = None
         with torch.cuda.stream(stream):
-            out = self._target_features(y, rec)
+            out = self._target_features(y)
             done = torch.cuda.Event()
             done.record(stream)       # the consumer waits for THIS point only, not for what the caller enqueues on ``stream`` afterwards
-        self._prefetched = (y.data_ptr(), y._version, tuple(y.shape), rec, out, done)
+        self._prefetched = (y.data_ptr(), y._version, tuple(y.shape), out, done)
 
-    def _take_target(self, y: torch.Tensor, rec: bool):
+    def _take_target(self, y: torch.Tensor):
         pre, self._prefetched = getattr(self, "_prefetched", None), None
-        if pre is not None and pre[:4] == (y.data_ptr(), y._version, tuple(y.shape), rec):
-            torch.cuda.current_stream(y.device).wait_event(pre[5])
-            return pre[4]
-        return self._target_features(y, rec)
+        if pre is not None and pre[:3] == (y.data_ptr(), y._version, tuple(y.shape)):
+            torch.cuda.current_stream(y.device).wait_event(pre[4])
+            return pre[3]
+        return self._target_features(y)
 
     def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         return _PerceptualFn.apply(self, x, y)
@@ -447,28 +465,22 @@ def _frozen_conv16(tape: E.Tape, x: E.Var, x16, wk: Tuple[torch.Tensor, Tuple], 
     return y, y16
 
 
-def _frozen_conv1_tap(tape: E.Tape, x: E.Var, w: torch.Tensor, bias: torch.Tensor, target: Optional[torch.Tensor]):
-    """conv1_1 (1 -> C, channel-summed weight) + ReLU of a branch whose relu1_1 tap is recomputed: only the bf16 operand of conv1_2 is written.
-    Backward (generated branch): dL/dx = conv_T((dy + d L1 / d relu1_1) * relu'), gate and L1 gradient recomputed from x and ``target``."""
+def _frozen_conv1_tap(tape: E.Tape, x: E.Var, w: torch.Tensor, y16: torch.Tensor, mask: Optional[torch.Tensor]):
+    """conv1_1 (1 -> C, channel-summed weight) + ReLU of a branch whose relu1_1 tap is not stored: ``y16`` (written by the pair kernel) is the bf16
+    operand of conv1_2.  Backward (generated branch): dL/dx = conv_T((dy + d L1 / d relu1_1) * relu'), gate and L1 sign from ``mask``."""
     O = w.shape[0]
     B, H, W, _ = x.t.shape
-    assert x.t.is_contiguous()
     y = E.Var(E.new_nhwc(B, H, W, O, x.t))          # shape carrier (never written or read); its gradient is a real fp32 tensor
-    y16 = torch.empty((B * H * W, O), dtype=torch.bfloat16, device=x.t.device)
-    lib = E._lib(x.t)
     wc = w.contiguous()
-    L.check(lib.gdn_thin_conv_expand_p(x.t.data_ptr(), wc.data_ptr(), bias.data_ptr(), None, 0, None, 0, B, H, W, O, H, W, 1, 1, 0, ACT_RELU, 0.0,
-                                       y16.data_ptr(), E._stream()), "gdn_thin_conv_expand_p")
 
     def bwd():
         if y.g is None or not x.needs_grad:
             return
-        assert target is not None and y.g16 is None
+        assert mask is not None and y.g16 is None
         tgt, acc = x.grad_target()
         assert tgt.is_contiguous()
-        L.check(lib.gdn_thin_conv_tap_dgrad(y.g.data_ptr(), E.pitch_of(y.g), x.t.data_ptr(), target.data_ptr(), wc.data_ptr(), bias.data_ptr(),
-                                            1.0 / float(B * H * W * O), tgt.data_ptr(), tgt.data_ptr() if acc else None, B, H, W, O, E._stream()),
-                "gdn_thin_conv_tap_dgrad")
+        L.check(E._lib(x.t).gdn_thin_conv_tap_dgrad(y.g.data_ptr(), E.pitch_of(y.g), mask.data_ptr(), wc.data_ptr(), 1.0 / float(B * H * W * O), tgt.data_ptr(),
+                                                    tgt.data_ptr() if acc else None, B, H, W, O, E._stream()), "gdn_thin_conv_tap_dgrad")
 
     tape.push(bwd)
     return y, y16
@@ -509,19 +521,20 @@ class _PerceptualFn(torch.autograd.Function):
         ws = E.dot_ws(dev)
         # target branch: forward only
         rec = mod._tap1_recompute_ok(x) and x.shape == y.shape
-        yin, yfeat = mod._take_target(y, rec)
-        # generated branch: recorded; L1 terms add value and d/dfeature in one pass
         tape = E.Tape(record=need)
         xin = E.op_from_nchw(tape, x.detach(), need)
+        tap_g = None
+        if rec:
+            # relu1_1 of both branches from ONE pass over the two images: conv1_2's operands, the tap's L1 term, and the backward pass's 2-bit codes
+            yin = E.op_from_nchw(E.Tape(record=False), y.detach(), False)
+            y16a, y16b, mask = mod._tap1_pair(xin.t, yin.t, loss, need)
+            yin, yfeat = mod._target_features(y, tap1={"y16": y16b}, yin=yin)
+            tap_g = {"y16": y16a, "mask": mask}
+        else:
+            yin, yfeat = mod._take_target(y)       # target branch: forward only (possibly prefetched on a side stream)
 
-        def on_feature(i: int, f: E.Var, info=None) -> None:
-            if info is not None:
-                # relu1_1 of both branches recomputed from the two images: value here, gradient inside conv1_1's data-gradient kernel
-                xf, w1, b1 = info
-                Bf, Hf, Wf, _ = xf.shape
-                L.check(lib.gdn_thin_conv_tap_l1(xf.data_ptr(), yin.t.data_ptr(), w1.data_ptr(), b1.data_ptr(), Bf, Hf, Wf, w1.shape[0], loss.data_ptr(), 1, 1.0,
-                                                 ws.data_ptr(), ws.numel(), E._stream()), "gdn_thin_conv_tap_l1")
-                return
+        # generated branch: recorded; L1 terms add value and d/dfeature in one pass
+        def on_feature(i: int, f: E.Var) -> None:
             t = yfeat[i]
             assert f.t.is_contiguous() and t.is_contiguous()
             g = torch.empty_like(f.t) if need else None
@@ -537,7 +550,7 @@ class _PerceptualFn(torch.autograd.Function):
                         f.add_grad(g)
                     tape.push(bwd)
 
-        mod._features(tape, xin, on_feature, tap1={"target": yin.t} if rec else None)
+        mod._features(tape, xin, on_feature, tap1=tap_g)
         ctx.tape, ctx.xin = tape, xin
         return loss.reshape(())
 

@@ -221,17 +221,20 @@ int gdn_thin_conv_reduce(const float* v_in, int v_pitch, const float* w, const f
  * discriminator.py:71) without a separate activation-backward pass */
 int gdn_thin_conv_reduce_gated(const float* v_in, int v_pitch, const float* gate, int gate_pitch, float gate_slope, const float* w, const float* bias, float* s_out,
                                const float* res, int B, int Hv, int Wv, int C, int Hs, int Ws, int stride, int pad, int transposed, gdn_stream_t s);
-/* A TAPPED 1 -> C conv + ReLU (3x3, stride 1, pad 1) without its fp32 output: the perceptual loss's relu1_1 term (losses.py:60-72 with conv1_1 on the
- * channel-summed weight, losses.py:64-65) recomputed from the two single-channel images instead of stored (2 x 1.07 GB written, 2.1 GB read, 1 GB of L1
- * gradient written and re-read per step at 256x512, batch 32).  gdn_thin_conv_expand_p with v_out == NULL writes only the bf16 operand of conv1_2.
- *   tap_l1   : loss[0] (+)= scale * mean | relu(conv(fa) + cbias) - relu(conv(fb) + cbias) |      (ws: >= 8 * 148 doubles)
- *   tap_dgrad: s_out = conv_transpose((dy + gcoef * sign(relu(conv fa) - relu(conv fb))) * [conv fa + cbias > 0], w) (+ res)
- * dy [B,H,W,C] = the gradient arriving from conv1_2; fa generated / fb target field [B,H,W]; C = 32 or 64, W % 4 == 0. */
-int gdn_thin_conv_tap_l1_supported(int C, int H, int W);
-int gdn_thin_conv_tap_l1(const float* fa, const float* fb, const float* w, const float* cbias, int B, int H, int W, int C, float* loss, int loss_accumulate,
-                         float scale, void* ws, size_t ws_bytes, gdn_stream_t st);
-int gdn_thin_conv_tap_dgrad(const float* dy, int dy_pitch, const float* fa, const float* fb, const float* w, const float* cbias, float gcoef, float* s_out,
-                            const float* res, int B, int H, int W, int C, gdn_stream_t st);
+/* A TAPPED 1 -> C conv + ReLU (3x3, stride 1, pad 1) of an image PAIR without its fp32 outputs: the perceptual loss's relu1_1 term (losses.py:60-72 with
+ * conv1_1 on the channel-summed weight, losses.py:64-65).  One pass over the two single-channel images writes both maps only as the bf16 operands of
+ * conv1_2, accumulates the L1 term and keeps 2 bits per element for the backward pass (ReLU gate and sign of the L1 gradient: one byte per pixel and
+ * 4 channels) -- instead of 2 x 1.07 GB of fp32 maps written, 2.1 GB read by the L1 pass and 1 GB of L1 gradient written and re-read (256x512, batch 32).
+ *   tap_pair : loss[0] (+)= scale * mean | relu(conv(fa) + cbias) - relu(conv(fb) + cbias) |; v16a / v16b [B*H*W][C] bf16 (either may be NULL);
+ *              mask [B*H*W][C/4] bytes (may be NULL); ws: >= 8 * 148 doubles
+ *   tap_dgrad: s_out = conv_transpose((dy + gcoef * sign) * gate, w) (+ res) with gate / sign from the mask; dy [B,H,W,C] = the gradient arriving from conv1_2
+ * fa generated / fb target field [B,H,W]; C = 32 or 64, W % 4 == 0. */
+int gdn_thin_conv_tap_supported(int C, int H, int W);
+size_t gdn_thin_conv_tap_mask_bytes(int B, int H, int W, int C);
+int gdn_thin_conv_tap_pair(const float* fa, const float* fb, const float* w, const float* cbias, int B, int H, int W, int C, float* loss, int loss_accumulate,
+                           float scale, uint16_t* v16a, uint16_t* v16b, uint8_t* mask, void* ws, size_t ws_bytes, gdn_stream_t st);
+int gdn_thin_conv_tap_dgrad(const float* dy, int dy_pitch, const uint8_t* mask, const float* w, float gcoef, float* s_out, const float* res,
+                            int B, int H, int W, int C, gdn_stream_t st);
 /* dw[c][k] (+)= sum_v V[v][c] S[v*stride + k - pad]   (flip: S at v + pad - k).  Deterministic two-stage reduction. */
 size_t gdn_thin_conv_wgrad_ws_bytes(int B, int Hv, int Wv, int C);
 int gdn_thin_conv_wgrad(const float* v, int v_pitch, const float* s_in, float* dw, int accumulate, int B, int Hv, int Wv, int C, int Hs, int Ws,
