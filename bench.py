@@ -50,6 +50,8 @@ def parse():
                     help="convolutions: bf16 = tcgen05 tensor cores (BASELINE config dtype), bf16x3 = hi+lo split on tensor cores, fp32 = CUDA-core parity engine")
     ap.add_argument("--no-perceptual", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="time the eager step instead of the CUDA-graph replay of it")
+    ap.add_argument("--shard-big", action="store_true", help="N > 1: reduce-scatter Discriminator1.fc1's gradient, update 1/N of it per rank, all-gather the weight "
+                    "(GradientAllReduce(shard_big=True)) instead of all-reducing the 1 GB gradient and running the 7.5 GB AdamW pass on every rank")
     ap.add_argument("--aux-dtype", default="auto", choices=["auto", "bf16", "fp32"], help="host/transport format of the aux stack (auto: bf16 with bf16 convolutions)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-other-mode", action="store_true", help="do not also time the single-fp16-logit PAM and the bf16x3 parity mode (extra key other_modes)")
@@ -219,7 +221,7 @@ def run_ours(args):
     if world > 1:
         for p in list(G.parameters()) + list(D.parameters()):
             dist.broadcast(p.data, 0)
-    tr = GANTrainer(G, D, perc, epochs=150, allreduce=GradientAllReduce(own_group=args.graph) if world > 1 else None)
+    tr = GANTrainer(G, D, perc, epochs=150, allreduce=GradientAllReduce(own_group=args.graph, shard_big=args.shard_big) if world > 1 else None)
     tr.epoch = 3
     # The aux stack (45 x 4h x 4w per sample, 97 % of a batch's bytes) is held and transported as bf16 when the convolutions round their operands
     # to bf16 anyway; the device-side bicubic down-sampling widens the taps to fp32 (trainer.prepare_input_nhwc).  --aux-dtype fp32 sends float32.
@@ -436,6 +438,7 @@ def run_ours(args):
                 "config": {"workload": workload_name(args, h, w), "global_batch": world * B, "parallelism": f"dp{world}", "conv": args.conv_precision,
                            "pam": f"fused tcgen05 flash forward + backward ({args.pam_precision})" if args.pam_precision != "fp32" else "fp32 engine",
                            "cuda_graph": graph_info, "eager_ms_per_step": ms_eager, "aux_transport": aux_dtype,
+                           "fc1_sharded": bool(args.shard_big and world > 1),
                            "side_stream_overlap": {"opt_D": bool(overlap_flags[0]), "perceptual_target": bool(overlap_flags[1])},
                            "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
                            "l2": "inputs larger than L2 (the aux stack alone is %.0f MB per step)" % (aux_h.numel() * aux_h.element_size() / 1e6)},

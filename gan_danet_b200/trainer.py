@@ -43,20 +43,35 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = 1.0
         self.capturable = False
+        # data parallel, sharded big tensors (GradientAllReduce(shard_big=True)): parameter -> (lo, hi) element range this rank updates; its
+        # exp_avg / exp_avg_sq exist for that range only (ZeRO-1 for Discriminator1.fc1: 1/world of the 7.5 GB AdamW pass and of its 2 GB state)
+        self.shard_of = None
         self._t = 0                     # steps taken (capturable mode: one common counter, as every parameter steps every iteration)
         self._dyn: List[torch.Tensor] = []
         self._dyn_host: List[torch.Tensor] = []
 
     SMALL = 1 << 20
 
+    def _range(self, p) -> Optional[Tuple[int, int]]:
+        return self.shard_of(p) if self.shard_of is not None else None
+
+    def _init_state(self, p) -> None:
+        st = self.state[p]
+        st["step"] = 0
+        r = self._range(p)
+        if r is None:
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        else:
+            st["exp_avg"] = torch.zeros(r[1] - r[0], dtype=p.dtype, device=p.device)
+            st["exp_avg_sq"] = torch.zeros(r[1] - r[0], dtype=p.dtype, device=p.device)
+            st["shard"] = r
+
     def _ensure_state(self) -> None:
         for group in self.param_groups:
             for p in group["params"]:
-                st = self.state[p]
-                if not st:
-                    st["step"] = 0
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                if not self.state[p]:
+                    self._init_state(p)
 
     def make_capturable(self) -> None:
         """Switch to device-resident step scalars (call after at least one eager step, before the capture)."""
@@ -99,13 +114,24 @@ class FusedAdamW(torch.optim.Optimizer):
                 st = self.state[p]
                 if not st:
                     assert not self.capturable
-                    st["step"] = 0
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    self._init_state(p)
                 if not self.capturable:
                     st["step"] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 assert p.is_contiguous()
+                r = self._range(p)
+                if r is not None:          # this rank's slice of a sharded tensor (the gradient slice holds the reduce-scattered sum)
+                    assert st.get("shard") == r, "the shard of a parameter changed after its optimizer state was created"
+                    pw, gw, n = p.data.view(-1)[r[0]:r[1]], g.view(-1)[r[0]:r[1]], r[1] - r[0]
+                    if self.capturable:
+                        L.check(E._lib(p).gdn_adamw_dyn(pw.data_ptr(), gw.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), n, self._dyn[gi].data_ptr(),
+                                                        float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), float(self.grad_scale), E._stream()),
+                                "gdn_adamw_dyn")
+                    else:
+                        L.check(E._lib(p).gdn_adamw(pw.data_ptr(), gw.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), n,
+                                                    float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                                                    int(st["step"]), float(self.grad_scale), E._stream()), "gdn_adamw")
+                    continue
                 if p.numel() < self.SMALL:
                     small.setdefault(0 if self.capturable else int(st["step"]), []).append(
                         (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), p, g))
@@ -138,7 +164,7 @@ class GradientAllReduce:
     Tensors above ``big`` elements are reduced in place one by one (D's fc1 gradient is ~1 GB and is its own bucket);
     the rest are packed into one flat bucket per call.  The 1/world factor is applied by the optimizer (``grad_scale``)."""
 
-    def __init__(self, group=None, big: int = 1 << 20, own_group: bool = False):
+    def __init__(self, group=None, big: int = 1 << 20, own_group: bool = False, shard_big: bool = False):
         """``own_group``: create a process group (a communicator of its own) for the gradient reductions.  Needed when the step is captured in a CUDA
         graph: on this stack an EAGER collective issued on a communicator after collectives of that communicator were captured never completes
         (tools/probe_nccl_graph.py), so the captured reductions get a communicator nobody else uses -- barriers, broadcasts and the bench's timing
@@ -148,15 +174,52 @@ class GradientAllReduce:
             group = dist.new_group()
         self.dist, self.group, self.big = dist, group, big
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # ``shard_big`` (ZeRO-1 for the big tensors): a tensor above ``big`` elements is REDUCE-SCATTERED in place -- rank r ends up with
+        # the summed gradient of elements [r n / W, (r + 1) n / W) only -- the optimizer updates that slice (``shard_of``, FusedAdamW.shard_of) and
+        # ``gather_params`` all-gathers the updated slices in place.  Same bytes on the wire as the all-reduce it replaces (a ring all-reduce IS a
+        # reduce-scatter followed by an all-gather), but AdamW touches 1 / W of Discriminator1.fc1 (7.5 GB per step) and its state shrinks W-fold.
+        self.shard_big = bool(shard_big) and self.world > 1
+        self._shards: Dict[int, Tuple[int, int]] = {}
+
+    def shard_of(self, p) -> Optional[Tuple[int, int]]:
+        """(lo, hi) element range of ``p`` this rank owns, or None when ``p`` is replicated."""
+        if not self.shard_big or p.numel() <= self.big or p.numel() % self.world != 0:
+            return None
+        n = p.numel() // self.world
+        return (self.rank * n, (self.rank + 1) * n)
+
+    def gather_params(self, params: Iterable[torch.nn.Parameter]) -> None:
+        """All-gathers (in place) the parameter slices the ranks have just updated; call after the optimizer step."""
+        if not self.shard_big:
+            return
+        handles = []
+        for p in params:
+            r = self.shard_of(p)
+            if r is not None:
+                flat = p.data.view(-1)
+                handles.append(self.dist.all_gather_into_tensor(flat, flat[r[0]:r[1]], group=self.group, async_op=True))
+        for h in handles:
+            h.wait()
 
     def start(self, params: Iterable[torch.nn.Parameter]):
         """Launches the reductions (ordered after the work already queued on the current stream) and returns a ``finish`` callable.
         Kernels enqueued between ``start`` and ``finish`` overlap the collective (NCCL runs on its own stream)."""
         if self.world == 1:
             return lambda: None
-        grads = [p.grad for p in params if p.grad is not None]
+        params = [p for p in params if p.grad is not None]
+        grads = [p.grad for p in params]
         small = [g for g in grads if g.numel() <= self.big]
-        handles = [self.dist.all_reduce(g, group=self.group, async_op=True) for g in grads if g.numel() > self.big]
+        handles = []
+        for p, g in zip(params, grads):
+            if g.numel() <= self.big:
+                continue
+            r = self.shard_of(p)
+            if r is not None and g.is_contiguous():
+                flat = g.view(-1)
+                handles.append(self.dist.reduce_scatter_tensor(flat[r[0]:r[1]], flat, group=self.group, async_op=True))
+            else:
+                handles.append(self.dist.all_reduce(g, group=self.group, async_op=True))
         flat = None
         if small:
             flat = torch.cat([g.reshape(-1) for g in small])
@@ -283,8 +346,12 @@ class GANTrainer:
         self.bce, self.mse, self.tv, self.ssim = BCEWithLogitsLoss(), MSELoss(), TVLoss(tv_weight), SSIM()
         self.eval_ssim = eval_ssim
         self.allreduce = allreduce
+        if allreduce is not None and allreduce.shard_big and not fused_adamw:
+            raise L.GdnError("GradientAllReduce(shard_big=True) needs the fused AdamW (torch.optim.AdamW keeps full-size state)")
         if allreduce is not None and fused_adamw:
             self.opt_G.grad_scale = 1.0 / allreduce.world
+            if allreduce.shard_big:
+                self.opt_G.shard_of = allreduce.shard_of
         self._w_dev: Optional[torch.Tensor] = None       # [w, 1 - w] on the device: set by GraphedTrainStep (the captured step must not bake epoch / epochs)
         # Optional side-stream overlaps (off by default: measured on B200, graph replay, batch 32: D's AdamW -- a 7.5 GB HBM-bound pass -- beside the
         # tensor-bound VGG19 forward passes: 52.66 -> 52.51 ms; additionally the perceptual target branch beside G's forward: 53.06 ms, i.e. SLOWER --
@@ -303,6 +370,8 @@ class GANTrainer:
             self.opt_D = self._make_opt(self.D.parameters(), self.lr_d)
             if self.allreduce is not None and self.fused_adamw:
                 self.opt_D.grad_scale = 1.0 / self.allreduce.world
+                if self.allreduce.shard_big:
+                    self.opt_D.shard_of = self.allreduce.shard_of
 
     def end_epoch(self) -> None:
         """scheduler_D.step(); scheduler_U.step() (GAN_DANet_train.ipynb:294-295)."""
@@ -329,6 +398,8 @@ class GANTrainer:
                     if p.grad is not None:
                         p.grad.mul_(1.0 / self.allreduce.world)
         self.opt_D.step()
+        if self.allreduce is not None:
+            self.allreduce.gather_params(d_params)
 
     def train_step(self, lr_grace_05: torch.Tensor, lr_grace_025: torch.Tensor, hr_aux: torch.Tensor) -> Dict[str, torch.Tensor]:
         """One iteration of the hot loop.  Inputs are device tensors (NCHW, as ``CustomDataset`` yields them).
@@ -398,6 +469,8 @@ class GANTrainer:
         g_params = list(G.parameters())
         self._reduce(g_params)
         self.opt_G.step()
+        if self.allreduce is not None:
+            self.allreduce.gather_params(g_params)
         out.update({"loss_D": loss_D.detach(), "loss_G": loss_G.detach(), "adv": loss_adv.detach(), "pixel": loss_pix.detach(),
                     "tv": loss_tv.detach()})
         if loss_perc is not None:

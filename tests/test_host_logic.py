@@ -80,6 +80,58 @@ def _dp_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _shard_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gan_danet_b200.trainer import GradientAllReduce
+    g = torch.Generator().manual_seed(5)
+    p0 = [torch.randn(n, generator=g) for n in (7, 2_000_000, 33, 1_500_001)]        # a shardable big tensor, small ones, a big one NOT divisible by the world size
+    gr = [[torch.randn(p.shape, generator=g) for p in p0] for _ in range(world)]     # every rank knows every rank's gradient (for the expected value)
+    lr = 0.1
+
+    def run(shard):
+        params = [torch.nn.Parameter(p.clone()) for p in p0]
+        for p, gg in zip(params, gr[rank]):
+            p.grad = gg.clone()
+        ar = GradientAllReduce(shard_big=shard)
+        ar.start(params)()
+        with torch.no_grad():
+            for p in params:          # a plain SGD step on whatever slice this rank owns (the optimizer-side contract of shard_of)
+                r = ar.shard_of(p)
+                if r is None:
+                    p -= lr * p.grad
+                else:
+                    p.view(-1)[r[0]:r[1]] -= lr * p.grad.view(-1)[r[0]:r[1]]
+        ar.gather_params(params)
+        return ar, params
+
+    ar_s, sharded = run(True)
+    _, plain = run(False)
+    want = [p - lr * sum(gr[r][i] for r in range(world)) for i, p in enumerate(p0)]
+    ok = ar_s.shard_of(sharded[1]) == (rank * 1_000_000, (rank + 1) * 1_000_000) and ar_s.shard_of(sharded[0]) is None and ar_s.shard_of(sharded[3]) is None
+    for a, b, w in zip(sharded, plain, want):
+        ok = ok and torch.allclose(a, w, rtol=1e-6, atol=1e-6) and torch.allclose(b, w, rtol=1e-6, atol=1e-6)
+    # the updated parameters are identical on every rank
+    chk = torch.stack([a.detach().double().sum() for a in sharded])
+    all_chk = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(all_chk, chk)
+    ok = ok and all(torch.equal(c, all_chk[0]) for c in all_chk)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_big_tensor_gloo_world2():
+    """GradientAllReduce(shard_big=True): reduce-scatter of the big gradient, slice-wise update, all-gather of the parameter == all-reduce + full update
+    (Discriminator1.fc1 under data parallelism); tensors that do not divide by the world size keep the all-reduce."""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_shard_worker, args=(world, port, out), nprocs=world, join=True)
+        assert out[0] and out[1]
+
+
 def test_gradient_allreduce_gloo_world2():
     """The N > 1 path: gradients are summed over ranks (bucketed small tensors + in-place large ones)."""
     import torch.multiprocessing as mp
