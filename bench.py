@@ -50,8 +50,9 @@ def parse():
                     help="convolutions: bf16 = tcgen05 tensor cores (BASELINE config dtype), bf16x3 = hi+lo split on tensor cores, fp32 = CUDA-core parity engine")
     ap.add_argument("--no-perceptual", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="time the eager step instead of the CUDA-graph replay of it")
-    ap.add_argument("--shard-big", action="store_true", help="N > 1: reduce-scatter Discriminator1.fc1's gradient, update 1/N of it per rank, all-gather the weight "
-                    "(GradientAllReduce(shard_big=True)) instead of all-reducing the 1 GB gradient and running the 7.5 GB AdamW pass on every rank")
+    ap.add_argument("--no-shard-big", dest="shard_big", action="store_false", help="N > 1: all-reduce Discriminator1.fc1's 1 GB gradient and run the 7.5 GB AdamW pass on every "
+                    "rank, instead of the default: reduce-scatter the gradient, update 1/N of the tensor per rank, all-gather the weight (GradientAllReduce(shard_big=True); "
+                    "measured 51.5 vs 52.1 ms/step at N = 8, 51.4 vs 51.6 at N = 2)")
     ap.add_argument("--aux-dtype", default="auto", choices=["auto", "bf16", "fp32"], help="host/transport format of the aux stack (auto: bf16 with bf16 convolutions)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-other-mode", action="store_true", help="do not also time the single-fp16-logit PAM and the bf16x3 parity mode (extra key other_modes)")
