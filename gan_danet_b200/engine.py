@@ -274,6 +274,20 @@ def discriminator_forward_precision() -> Optional[str]:
     return "bf16x3" if (discriminator_forward_x3 and conv_precision == "bf16") else None
 
 
+# The generator's FORWARD convolutions on hi+lo split operands inside the product mode (off by default; bench.py and GANTrainer callers switch it on).
+# bf16 operand rounding of the forward puts the generated field 9e-3 from the reference's (float64 run of generator.py:230-247), which is what moves
+# loss_D / loss_G by more than 1 % on a few of 200 teacher-forced steps (tools/trajectory_quantised_cpu.py shows the same with the reference's own
+# modules and bf16 operands: the format, not the kernels).  With split forward operands the field is 1.5e-4 away (the parity mode's forward) while
+# every gradient GEMM still reads single bf16 operands (the hi parts): 3x the MMA work on the 2.4 ms of generator forward convolutions only.
+# Quantised-oracle prediction (oracle/quantised_oracle.py Formats.forward_x3): y 1.5e-4, dx 4.1e-2, parameter gradients 3.8e-2 (bf16 forward: 9.0e-3 /
+# 1.9e-1 / 1.8e-1 -- the sqrt law of DESIGN.md 4: no flipped ReLU masks, no wrong gradients).
+generator_forward_x3: bool = os.environ.get("GDN_G_FORWARD_X3", "0") == "1"
+
+
+def generator_forward_precision() -> Optional[str]:
+    return "bf16x3" if (generator_forward_x3 and conv_precision == "bf16") else None
+
+
 def tc_eligible(cin: int, cout: int, kh: int, kw: int, stride: int, ho: int, wo: int) -> bool:
     """Shapes the tensor-core kernel takes; the rest (fully connected layers, 1- and 3-channel inputs) stay on the
     fp32 CUDA-core engine, which is HBM-bound there anyway."""

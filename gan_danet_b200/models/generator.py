@@ -346,7 +346,12 @@ class FlexibleUpsamplingModule(TapeModule):
                 m.precision = precision
 
     def _build_nhwc(self, ctx: BuildCtx, xin: E.Var) -> E.Var:
-        """Forward on an NHWC input Var (the fused input-prep path feeds this directly)."""
+        """Forward on an NHWC input Var (the fused input-prep path feeds this directly).  With engine.generator_forward_x3 the product mode records
+        the forward convolutions with hi+lo split operands (their backward closures run later, on the hi parts, like Discriminator1's)."""
+        with E.conv_precision_scope(E.generator_forward_precision()):
+            return self._build_nhwc_scoped(ctx, xin)
+
+    def _build_nhwc_scoped(self, ctx: BuildCtx, xin: E.Var) -> E.Var:
         tape = ctx.tape
         B, H, W, _ = xin.t.shape
         nblocks = len(self.dense_blocks)

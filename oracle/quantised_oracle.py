@@ -51,6 +51,10 @@ def rnd(t: Tensor, fmt: Optional[str]) -> Tensor:
         return t.float().clamp(-65504.0, 65504.0).half().to(t.dtype)
     if fmt == "fp32":
         return t.float().to(t.dtype)
+    if fmt == "bf16x3":     # hi + lo split operand (conv precision 'bf16x3'): hi = bf16(v), lo = bf16(v - hi); the lo*lo product is dropped on the device (~2^-17 relative)
+        v = t.float()
+        hi = v.bfloat16().float()
+        return (hi + (v - hi).bfloat16().float()).to(t.dtype)
     raise ValueError(fmt)
 
 
@@ -64,10 +68,19 @@ class Formats:
     pam_v: Optional[str] = "bf16"        # value operand (forward, and dP = dy V^T in the backward)
     pam_g: Optional[str] = "fp16"        # backward: scaled dy, dS, q, k, P
     pam_logits: Optional[str] = None     # 'fp16' emulates the single-fp16 logit operands of PAM mode 'fp16'; None = split (exact)
+    # formats of the SAVED input / weight operands that the two gradient GEMMs read; "same" = the forward's.  The mixed mode (forward with hi+lo split
+    # operands, backward on the hi parts alone: engine.generator_forward_x3, Discriminator1's forward) is conv_x = conv_w = 'bf16x3', *_bwd = 'bf16'
+    conv_x_bwd: Optional[str] = "same"
+    conv_w_bwd: Optional[str] = "same"
 
     @staticmethod
     def exact() -> "Formats":
         return Formats(None, None, None, None, None, None, None)
+
+    @staticmethod
+    def forward_x3() -> "Formats":
+        """Product mode with the generator's forward convolutions on hi+lo split operands (their gradient GEMMs read the hi parts: bf16)."""
+        return Formats(conv_x="bf16x3", conv_w="bf16x3", conv_x_bwd="bf16", conv_w_bwd="bf16")
 
 
 class QConv(torch.autograd.Function):
@@ -76,7 +89,7 @@ class QConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, stride, padding, f: Formats):
         xq, wq = rnd(x, f.conv_x), rnd(w, f.conv_w)
-        ctx.save_for_backward(xq, wq)
+        ctx.save_for_backward(xq if f.conv_x_bwd == "same" else rnd(x, f.conv_x_bwd), wq if f.conv_w_bwd == "same" else rnd(w, f.conv_w_bwd))
         ctx.cfg = (stride, padding, f, b is not None)
         return F.conv2d(xq, wq, b, stride=stride, padding=padding)
 

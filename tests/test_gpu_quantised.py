@@ -134,3 +134,54 @@ def test_generator_parity_mode_with_fused_pam(golden):
     print(f"\n[precision] bf16x3 convs + PAM fp16x3 vs fp64 reference: y {ey:.2e} dx {edx:.2e} grads {eg:.2e}")
     assert ey < 1e-3, ey
     assert edx < 4e-2 and eg < 4e-2, (edx, eg)
+
+
+def test_generator_benchmarked_mode_forward_x3(golden, qoracle):
+    """The mode bench.py runs: conv precision 'bf16' with engine.generator_forward_x3 -- the generator's FORWARD convolutions on hi+lo split operands
+    (recorded under conv_precision_scope('bf16x3'), like Discriminator1's), every gradient GEMM on single bf16 operands (the hi parts) -- fused PAM
+    'fp16x3'.
+    * the forward is the parity mode's: bitwise the output of conv precision 'bf16x3' (same kernels, same operands) and <= 1e-3 from the reference's
+      float64 run (north_star's bar on the generator output);
+    * the gradients are those of a network whose forward is exact to 1.5e-4 and whose backward operands are bf16: the quantisation-aware oracle with
+      Formats.forward_x3() predicts dx 4.1e-2 / parameter gradients 3.8e-2 against the float64 reference (bf16 forward: 1.9e-1 / 1.8e-1 -- flipped ReLU
+      masks); asserted <= 1e-1 against the reference and against the oracle."""
+    from gan_danet_b200 import engine as E
+    g = golden("generator_cin46_8x16")
+
+    def run(conv, gx3):
+        G = _seeded_generator(g["seed"], g["gamma"])
+        G.set_pam_precision("fp16x3")
+        old, old_gx3 = E.conv_precision, E.generator_forward_x3
+        E.set_conv_precision(conv)
+        E.generator_forward_x3 = gx3
+        try:
+            assert E.generator_forward_precision() == ("bf16x3" if gx3 else None)
+            Gd = G.to(DEV)
+            x = g["x"].to(DEV).requires_grad_(True)
+            y = Gd(x)
+            assert E.conv_precision == conv                       # the scope restored the mode
+            y.backward(g["r"].to(DEV))
+            torch.cuda.synchronize()
+        finally:
+            E.set_conv_precision(old)
+            E.generator_forward_x3 = old_gx3
+        return G, y.detach(), x.grad, {k: p.grad for k, p in Gd.named_parameters()}, Gd.state_dict()
+
+    _, y_par, _, _, _ = run("bf16x3", False)
+    G, y, dx, grads, sd = run("bf16", True)
+    assert torch.equal(y, y_par), rel_err(y, y_par)
+    yq, dxq, gq, bufq = _oracle_run(qoracle, G, g["x"], g["r"], qoracle.Formats.forward_x3())
+    rep = {"cuda_vs_fp64_reference": {"y": rel_err(y, g["y"]), "dx": rel_err(dx, g["dx"]), "grads_whole_vector": _whole_vector(grads, g["grads_small"])},
+           "cuda_vs_quantised_oracle": {"y": rel_err(y, yq), "dx": rel_err(dx, dxq), "grads_whole_vector": _whole_vector(grads, gq)},
+           "quantised_oracle_vs_fp64_reference": {"y": rel_err(yq, g["y"]), "dx": rel_err(dxq, g["dx"]),
+                                                  "grads_whole_vector": _whole_vector(gq, {k: v for k, v in g["grads_small"].items()})}}
+    print("\n[precision] bf16 convs, generator forward x3 + PAM fp16x3: %s" % json.dumps(rep))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "precision_benchmarked_mode_gx3.json"), "w"), indent=1)
+    c = rep["cuda_vs_fp64_reference"]
+    assert c["y"] < 1e-3, rep
+    assert c["dx"] < 1e-1 and c["grads_whole_vector"] < 1e-1, rep
+    q = rep["cuda_vs_quantised_oracle"]
+    assert q["y"] < 1e-3 and q["dx"] < 1e-1 and q["grads_whole_vector"] < 1e-1, rep
+    for k, v in g["buffers_after"].items():
+        assert rel_err(sd[k], v) < 1e-4, (k, rel_err(sd[k], v))

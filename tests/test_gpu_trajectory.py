@@ -82,7 +82,11 @@ def test_teacher_forced_trajectory_200_steps(oracle):
     # conv precision, PAM precision, loss tol, parameter tol.  'bf16x3' = the tensor-core PARITY mode (hi+lo split conv operands + fused PAM with split
     # logits): 1 % at EVERY step, like the fp32 engine.  'bf16' = the benchmarked mode: its generated field is 1e-2 away from the reference's
     # (bf16 operands), which reaches D's logits -- 1 % on >= 95 % of the steps, 2 % everywhere (measured: 3 of 400 loss values above 1 %, worst 1.2 %)
-    modes = {"fp32": ("fp32", "fp32", 1e-2, 2e-3), "bf16x3": ("bf16x3", "fp16x3", 1e-2, 2e-3), "bf16": ("bf16", "fp16x3", 1e-2, 5e-3)}
+    # 'bf16+gx3' = the BENCHMARKED mode (bench.py): bf16 operands everywhere except the forward convolutions of G (engine.generator_forward_x3) and of D,
+    # which run on hi+lo split operands -- the generated field is then the parity mode's (1.5e-4 from the reference) and the losses must be within 1 % at
+    # EVERY step, like the fp32 engine; every gradient GEMM still reads single bf16 operands (parameter tolerance of the bf16 mode)
+    modes = {"fp32": ("fp32", "fp32", 1e-2, 2e-3), "bf16x3": ("bf16x3", "fp16x3", 1e-2, 2e-3), "bf16": ("bf16", "fp16x3", 1e-2, 5e-3),
+             "bf16+gx3": ("bf16", "fp16x3", 1e-2, 5e-3)}
     trainers = {}
     for name, (conv, pam, _, _) in modes.items():
         import copy
@@ -100,7 +104,7 @@ def test_teacher_forced_trajectory_200_steps(oracle):
     log = {name: [] for name in modes}
     worst = {name: {"loss_D": 0.0, "loss_G": 0.0, "param": 0.0, "update": 0.0} for name in modes}
     failures = []
-    old = E.conv_precision
+    old, old_gx3 = E.conv_precision, E.generator_forward_x3
     try:
         for i in range(STEPS):
             epoch = i // per_epoch
@@ -112,6 +116,7 @@ def test_teacher_forced_trajectory_200_steps(oracle):
             for name, tr in trainers.items():
                 conv, _, tol_l, tol_p = modes[name]
                 E.set_conv_precision(conv)
+                E.generator_forward_x3 = name == "bf16+gx3"
                 tr.epoch = epoch
                 for opt, lr in ((tr.opt_D, lr_d), (tr.opt_G, lr_g)):
                     for grp in opt.param_groups:
@@ -138,6 +143,7 @@ def test_teacher_forced_trajectory_200_steps(oracle):
         torch.cuda.synchronize()
     finally:
         E.set_conv_precision(old)
+        E.generator_forward_x3 = old_gx3
         out_dir = os.path.join(ROOT, "gpurun_out")
         if os.path.isdir(out_dir):
             with open(os.path.join(out_dir, "r02_trajectory_teacher_forced.json"), "w") as f:
@@ -173,7 +179,7 @@ def test_teacher_forced_steps_at_the_north_star_grid(oracle):
     torch.manual_seed(22)
     vgg_sd = {k: v.clone() for k, v in P.PerceptualLoss(pretrained=False, device=torch.device("cpu")).vgg.state_dict().items()}
     st = oracle.TrainState({k: v.clone() for k, v in G0.state_dict().items()}, {k: v.clone() for k, v in D0.state_dict().items()}, vgg_sd)
-    modes = {"fp32": ("fp32", "fp32", 1e-2), "bf16x3": ("bf16x3", "fp16x3", 1e-2), "bf16": ("bf16", "fp16x3", 2e-2)}
+    modes = {"fp32": ("fp32", "fp32", 1e-2), "bf16x3": ("bf16x3", "fp16x3", 1e-2), "bf16": ("bf16", "fp16x3", 2e-2), "bf16+gx3": ("bf16", "fp16x3", 1e-2)}
     trainers = {}
     for name, (conv, pam, _) in modes.items():
         G, D = copy.deepcopy(G0).to(DEV), copy.deepcopy(D0).to(DEV)
@@ -186,7 +192,7 @@ def test_teacher_forced_steps_at_the_north_star_grid(oracle):
         tr.epoch = 3
         tr._ensure_opt_D(batches[0][1].to(DEV))
         trainers[name] = tr
-    old = E.conv_precision
+    old, old_gx3 = E.conv_precision, E.generator_forward_x3
     report = {}
     try:
         for i, b in enumerate(batches):
@@ -196,6 +202,7 @@ def test_teacher_forced_steps_at_the_north_star_grid(oracle):
             for name, tr in trainers.items():
                 conv, _, tol = modes[name]
                 E.set_conv_precision(conv)
+                E.generator_forward_x3 = name == "bf16+gx3"
                 out = tr.train_step(*(t.to(DEV) for t in b))
                 for k in ("loss_D", "loss_G", "pixel", "perceptual"):
                     dev = abs(float(out[k]) - ref[k]) / max(abs(ref[k]), 1e-3)
@@ -203,5 +210,6 @@ def test_teacher_forced_steps_at_the_north_star_grid(oracle):
                     assert dev <= tol, (name, i, k, float(out[k]), ref[k])
     finally:
         E.set_conv_precision(old)
+        E.generator_forward_x3 = old_gx3
         E.release_buffers()
     print("north-star-grid teacher-forced deviations:", {f"{k[0]}/{k[1]}/{k[2]}": round(v, 6) for k, v in report.items()})

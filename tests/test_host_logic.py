@@ -181,3 +181,31 @@ def test_ensemble_gather_gloo_world2():
         out = mgr.dict()
         mp.spawn(_ens_worker, args=(2, port, out), nprocs=2, join=True)
         assert out[0] and out[1]
+
+
+def test_generator_forward_precision_scope():
+    """engine.generator_forward_x3: inside the product mode ('bf16') the generator records its forward under conv_precision_scope('bf16x3'); in every
+    other mode the flag does nothing, and the scope restores the outer mode (also when the body raises)."""
+    from gan_danet_b200 import engine as E
+    old, old_flag = E.conv_precision, E.generator_forward_x3
+    try:
+        E.generator_forward_x3 = True
+        for mode, want in (("bf16", "bf16x3"), ("bf16x3", None), ("fp32", None)):
+            E.set_conv_precision(mode)
+            assert E.generator_forward_precision() == want
+            with E.conv_precision_scope(E.generator_forward_precision()):
+                assert E.conv_precision == (want or mode)
+                assert not (want and E.bf16_storage_ok())          # the bf16-only operand shortcuts are off while the forward is recorded with split operands
+            assert E.conv_precision == mode
+        E.set_conv_precision("bf16")
+        try:
+            with E.conv_precision_scope(E.generator_forward_precision()):
+                raise RuntimeError("body failed")
+        except RuntimeError:
+            pass
+        assert E.conv_precision == "bf16"
+        E.generator_forward_x3 = False
+        assert E.generator_forward_precision() is None
+    finally:
+        E.set_conv_precision(old)
+        E.generator_forward_x3 = old_flag

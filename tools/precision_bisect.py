@@ -57,6 +57,7 @@ if __name__ == "__main__":
         "exact (must reproduce the golden)": Q.Formats.exact(),
         "product mode: bf16 convs + fp16x3 PAM": Q.Formats(),
         "product mode with single-fp16 logits (PAM 'fp16')": Q.Formats(pam_logits="fp16"),
+        "what-if, not implemented: fp16 forward operands (conv x / w, PAM P / V), bf16 conv gradient operand": Q.Formats("fp16", "fp16", "bf16", "fp16", "fp16", "fp16", None),
         "conv operands only (x, w bf16; gradient operand exact)": Q.Formats("bf16", "bf16", None, None, None, None, None),
         "conv gradient operand only": Q.Formats(None, None, "bf16", None, None, None, None),
         "conv x only": Q.Formats("bf16", None, None, None, None, None, None),

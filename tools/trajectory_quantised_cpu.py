@@ -52,7 +52,10 @@ st = O.TrainState({k: v.clone() for k, v in G0.state_dict().items()}, {k: v.clon
 vgg64 = {k: v.double() for k, v in vgg_sd.items()}
 d64 = lambda sd: {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}  # noqa: E731
 
-fmts = {"bf16 operands (product mode)": Q.Formats(), "exact (float64 re-evaluation: the float32 oracle's own noise)": Q.Formats.exact()}
+fmts = {"bf16 operands (product mode)": Q.Formats(),
+        # what-if (not implemented on the device): tcgen05 kind::f16 takes fp16 operands at the bf16 rate; activations and weights of this network fit fp16's range
+        "fp16 forward operands (what-if: conv x / w and PAM P / V in fp16, gradient operands unchanged)": Q.Formats("fp16", "fp16", "bf16", "fp16", "fp16", "fp16", None),
+        "exact (float64 re-evaluation: the float32 oracle's own noise)": Q.Formats.exact()}
 log = {k: [] for k in fmts}
 t0 = time.time()
 with torch.no_grad():
