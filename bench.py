@@ -384,10 +384,11 @@ def run_ours(args):
              "pam_flash_bwd_kernel": "fused tcgen05 PAM backward (dQ launch + dK/dV launch) incl. rowdot and operand packing"}
 
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, family mean) from the committed ncu pass of the same step
-    # (profiles/r02_dram_traffic.json, written by tools/aggregate_traffic.py); null when the file or the family is missing
+    # (profiles/r02c_dram_traffic.json for the default --g-forward x3, r02_dram_traffic.json for --g-forward bf16; written by tools/aggregate_traffic.py);
+    # null when the file or the family is missing
     traffic = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02c_dram_traffic.json" if gx3 else "r02_dram_traffic.json")))
         traffic = {k: v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"] for k, v in tj["families"].items()}
     except Exception:
         pass
@@ -427,7 +428,7 @@ def run_ours(args):
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": peak_src,
                 "frac_of_burst_peak": (ach / burst) if burst else None, "burst_peak": burst,
                 "forward_tflops": f["tflops"], "backward_tflops": b["tflops"], "forward_frac": f["tflops"] / peak_tf, "backward_frac": b["tflops"] / peak_tf,
-                "traffic": (tr_f + tr_b) if (tr_f and tr_b) else None, "traffic_unit": "bytes of DRAM traffic per module call = forward launch + the two backward launches (ncu pass of the same step, profiles/r02_dram_traffic.json)",
+                "traffic": (tr_f + tr_b) if (tr_f and tr_b) else None, "traffic_unit": "bytes of DRAM traffic per module call = forward launch + the two backward launches (ncu pass of the same step, profiles/r02c_dram_traffic.json)",
                 "algorithmic_flops_per_step": fl_tot / prof_steps, "ms_per_step": ms_tot / prof_steps, "share_of_step": ms_tot / (ms_eager * prof_steps),
                 "timed_in": f"{prof_steps} eager steps of the same trainer (CUDA events around each C-ABI call; the graph replay cannot be bracketed per kernel)",
                 "launches": f["launches"] + b["launches"]}

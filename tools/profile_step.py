@@ -18,12 +18,14 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--grid", default="64x128")
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--conv-precision", default="bf16")
+ap.add_argument("--g-forward", default="x3", choices=["x3", "bf16"], help="as bench.py: the generator's forward convolutions on hi+lo split operands (default) or single bf16")
 ap.add_argument("--pam-only", action="store_true", help="profile only a PAM forward (C=184) instead of the whole step")
 args = ap.parse_args()
 h, w = (int(v) for v in args.grid.split("x"))
 dev = torch.device("cuda:0")
 from gan_danet_b200 import engine as E  # noqa: E402
 E.set_conv_precision(args.conv_precision)
+E.generator_forward_x3 = args.g_forward == "x3" and args.conv_precision == "bf16"
 torch.manual_seed(0)
 if args.pam_only:
     from gan_danet_b200.models.generator import PAMModule
