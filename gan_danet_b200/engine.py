@@ -256,12 +256,31 @@ class conv_precision_scope:
         global conv_precision
         self.old = conv_precision
         if self.p is not None:
+            _outer_precision.append(conv_precision)
             set_conv_precision(self.p)
 
     def __exit__(self, *exc):
         global conv_precision
+        if self.p is not None:
+            _outer_precision.pop()
         conv_precision = self.old
         return False
+
+
+_outer_precision: List[str] = []      # precision outside each active conv_precision_scope (innermost last)
+
+
+def backward_conv_precision() -> str:
+    """The precision the backward closures of what is being recorded will run under: the mode outside the outermost active conv_precision_scope."""
+    return _outer_precision[0] if _outer_precision else conv_precision
+
+
+def split_forward_in_product_mode() -> bool:
+    """True while a forward is recorded with hi+lo split operands inside the product mode (generator_forward_x3, Discriminator1's forward).  Two
+    operand shortcuts of the bf16 mode stay valid there because they do not touch what the split forward computes: the value projection's epilogue may
+    still emit the fused PAM's bf16 V operand (the kernel rounds V to bf16 itself: the same round-to-nearest of the same fp32 value), and BatchNorm's
+    backward may still hand the convolution its dz as a bf16 operand only (the gradient GEMMs run under 'bf16' and would round it anyway)."""
+    return conv_precision == "bf16x3" and backward_conv_precision() == "bf16"
 
 
 # Discriminator1 has no normalisation layer: the bf16 operand rounding of its three tensor-core convolutions reaches the logits directly, and
@@ -454,7 +473,8 @@ def conv_forward(x: Tensor, w: Tensor, y: Optional[Tensor], *, stride: int = 1, 
     B, Hi, Wi, Cin = x.shape
     Ho, Wo = (Hi + 2 * pad - kh) // stride + 1, (Wi + 2 * pad - kw) // stride + 1
     if y is None or x_packed is not None:
-        assert tc_eligible(Cin, O, kh, kw, stride, Ho, Wo) and (conv_precision == "bf16" or (y is not None and y16 is None)) and (y16 is not None or y is not None)
+        assert tc_eligible(Cin, O, kh, kw, stride, Ho, Wo) and (y16 is not None or y is not None)
+        assert conv_precision == "bf16" or (y is not None and (y16 is None or split_forward_in_product_mode()))
         xp = x_packed if x_packed is not None else pack_act(x)
         conv_tc_raw(xp, pack_weight(w, False, frozen_key), y, (Hi, Wi), cin=Cin, kh=kh, kw=kw, stride=stride, pad=pad, bias=bias, act=act, slope=slope, res=res,
                     y16=y16, out_shape=(B, Ho, Wo, O))
@@ -850,7 +870,7 @@ def op_conv_bn_act(tape: Tape, x: Var, w: Var, bn: BNState, *, training: bool, a
     O, Cin, kh, kw = w.t.shape
     _, Hi, Wi, _ = x.t.shape
     _, Ho, Wo, _ = z.t.shape
-    z.grad16_only = bool(conv_bn_packed_grad and training and tape.record and conv_precision == "bf16" and O % 8 == 0 and pitch_of(z.t) % 4 == 0
+    z.grad16_only = bool(conv_bn_packed_grad and training and tape.record and (conv_precision == "bf16" or split_forward_in_product_mode()) and O % 8 == 0 and pitch_of(z.t) % 4 == 0
                          and z.t.data_ptr() % 16 == 0
                          and conv_backward_tc_only(O, Cin, kh, kw, stride, Ho, Wo, Hi, Wi, w.needs_grad, x.needs_grad))
     return op_bn_act(tape, z, bn, training=training, act=act, slope=slope, out=out)
@@ -965,7 +985,7 @@ def pam_v16_buffer(x: Tensor) -> Optional[Tensor]:
     of gdn_pam_fwd only touches q and k (V is 80 % of its bytes)."""
     B, H, W, Cc = x.shape
     N = H * W
-    if not (pam_v16_from_conv and conv_precision == "bf16" and N % 128 == 0 and Cc < 192 and Cc % 4 == 0 and tc_eligible(Cc, Cc, 1, 1, 1, H, W)):
+    if not (pam_v16_from_conv and (conv_precision == "bf16" or split_forward_in_product_mode()) and N % 128 == 0 and Cc < 192 and Cc % 4 == 0 and tc_eligible(Cc, Cc, 1, 1, 1, H, W)):
         return None
     key = (x.device.index or 0, B * N, Cc)
     buf = _pam_v16.get(key)

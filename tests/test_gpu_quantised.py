@@ -148,12 +148,13 @@ def test_generator_benchmarked_mode_forward_x3(golden, qoracle):
     from gan_danet_b200 import engine as E
     g = golden("generator_cin46_8x16")
 
-    def run(conv, gx3):
+    def run(conv, gx3, shortcuts=True):
         G = _seeded_generator(g["seed"], g["gamma"])
         G.set_pam_precision("fp16x3")
-        old, old_gx3 = E.conv_precision, E.generator_forward_x3
+        old, old_gx3, old_sc = E.conv_precision, E.generator_forward_x3, (E.pam_v16_from_conv, E.conv_bn_packed_grad)
         E.set_conv_precision(conv)
         E.generator_forward_x3 = gx3
+        E.pam_v16_from_conv = E.conv_bn_packed_grad = shortcuts
         try:
             assert E.generator_forward_precision() == ("bf16x3" if gx3 else None)
             Gd = G.to(DEV)
@@ -165,11 +166,17 @@ def test_generator_benchmarked_mode_forward_x3(golden, qoracle):
         finally:
             E.set_conv_precision(old)
             E.generator_forward_x3 = old_gx3
+            E.pam_v16_from_conv, E.conv_bn_packed_grad = old_sc
         return G, y.detach(), x.grad, {k: p.grad for k, p in Gd.named_parameters()}, Gd.state_dict()
 
     _, y_par, _, _, _ = run("bf16x3", False)
     G, y, dx, grads, sd = run("bf16", True)
     assert torch.equal(y, y_par), rel_err(y, y_par)
+    # the two operand shortcuts that stay on inside the split forward (engine.split_forward_in_product_mode: the value projection's epilogue emits the
+    # fused PAM's bf16 V operand; BatchNorm's backward hands the convolution its dz as a bf16 operand only) change no bit of the output or of any gradient
+    _, y_ns, dx_ns, grads_ns, _ = run("bf16", True, shortcuts=False)
+    assert torch.equal(y, y_ns) and torch.equal(dx, dx_ns)
+    assert not [k for k in grads if not torch.equal(grads[k], grads_ns[k])]
     yq, dxq, gq, bufq = _oracle_run(qoracle, G, g["x"], g["r"], qoracle.Formats.forward_x3())
     rep = {"cuda_vs_fp64_reference": {"y": rel_err(y, g["y"]), "dx": rel_err(dx, g["dx"]), "grads_whole_vector": _whole_vector(grads, g["grads_small"])},
            "cuda_vs_quantised_oracle": {"y": rel_err(y, yq), "dx": rel_err(dx, dxq), "grads_whole_vector": _whole_vector(grads, gq)},

@@ -6,15 +6,19 @@ profiles/r01_trajectory_envelope.txt measures the same growth here), so the 200 
 (float32 -- the reference's own CPU arithmetic) with the faithful schedule (w = epoch/epochs, CosineAnnealingWarmRestarts per
 epoch, four batches per epoch, GAN_DANet_train.ipynb:186-187,225-295), and AT EVERY STEP the CUDA trainer starts from the
 oracle's full state (G and D parameters, BatchNorm buffers, AdamW moments and step count), runs the same step and must give
-loss_D and loss_G within 1 % and post-step parameters within 2e-3.  Both the fp32 parity engine and the product mode
-(bf16 tcgen05 convolutions, fused fp16/bf16 PAM kernels) are driven from the same oracle walk.
+loss_D and loss_G within 1 % and post-step parameters within 2e-3.  Four modes are driven from the same oracle walk: the fp32 parity engine, the
+tensor-core parity mode, the BENCHMARKED mode (bench.py) and the all-bf16 mode it replaced.
 
-Measured on a B200 (profiles/r02_trajectory_teacher_forced.json): fp32 engine -- worst loss deviation over the 200 steps 5.5e-6,
-parameters 2.6e-5; tensor-core parity mode (bf16x3 convolutions + fused PAM with split logits) -- worst 2.5e-4 (loss_D) / 6.7e-4 (loss_G),
-parameters 1.1e-3; benchmarked mode (bf16 convolutions) -- median 1.2e-3 / 1.6e-3, worst 1.2e-2 / 1.1e-2 (3 of 400 values above 1 %: the
-generator's own 1e-2 bf16 error on the field D looks at; D's forward convolutions already use hi+lo split operands), parameters 3.5e-3.
-Asserted: fp32 engine and parity mode 1 % at EVERY step (north_star's bar); benchmarked mode 1 % on at least 95 % of the steps and 2 % at
-every step, parameters 5e-3.  The per-step deviations are written to gpurun_out/r02_trajectory_teacher_forced.json when that directory exists.
+Measured on a B200 (profiles/r02_trajectory_teacher_forced.json), worst deviation over the 200 steps (loss_D / loss_G / parameters):
+  fp32      fp32 engine                                                            3.1e-6 / 3.1e-4 (one step; median 3.6e-7) / 2.6e-5
+  bf16x3    hi+lo split convolutions + fused PAM with split logits (parity mode)    2.4e-4 / 6.7e-4 / 1.1e-3
+  bf16+gx3  BENCHMARKED: bf16 operands, the FORWARD convolutions of G (engine.generator_forward_x3) and of D on hi+lo split operands, every
+            gradient GEMM and VGG19 on single bf16 operands                         2.4e-4 / 6.8e-4 / 1.1e-3
+  bf16      bf16 operands in G's forward too (bench.py --g-forward bf16)            1.2e-2 / 1.1e-2 (median 1.2e-3 / 1.6e-3; 3 of 400 values above 1 %) / 3.5e-3
+Asserted: fp32 engine, parity mode AND the benchmarked mode 1 % at EVERY step (north_star's bar); the all-bf16 mode 1 % on at least 95 % of the steps
+and 2 % at every step, parameters 5e-3 (its generated field is 9e-3 from the reference's -- the cost of bf16 forward operands for ANY implementation:
+tools/trajectory_quantised_cpu.py walks the same steps on the CPU with the reference algorithm and bf16 operands and finds loss_D above 1 % on 7 steps).
+The per-step deviations are written to gpurun_out/r02_trajectory_teacher_forced.json when that directory exists.
 A second test walks two teacher-forced steps at the NORTH-STAR grid (64x128: PAM over N = 8192 positions, 64 key tiles per query tile).
 """
 import json
@@ -84,9 +88,9 @@ def test_teacher_forced_trajectory_200_steps(oracle):
     # (bf16 operands), which reaches D's logits -- 1 % on >= 95 % of the steps, 2 % everywhere (measured: 3 of 400 loss values above 1 %, worst 1.2 %)
     # 'bf16+gx3' = the BENCHMARKED mode (bench.py): bf16 operands everywhere except the forward convolutions of G (engine.generator_forward_x3) and of D,
     # which run on hi+lo split operands -- the generated field is then the parity mode's (1.5e-4 from the reference) and the losses must be within 1 % at
-    # EVERY step, like the fp32 engine; every gradient GEMM still reads single bf16 operands (parameter tolerance of the bf16 mode)
+    # EVERY step and the post-step parameters within 2e-3, like the fp32 engine and the parity mode; every gradient GEMM still reads single bf16 operands
     modes = {"fp32": ("fp32", "fp32", 1e-2, 2e-3), "bf16x3": ("bf16x3", "fp16x3", 1e-2, 2e-3), "bf16": ("bf16", "fp16x3", 1e-2, 5e-3),
-             "bf16+gx3": ("bf16", "fp16x3", 1e-2, 5e-3)}
+             "bf16+gx3": ("bf16", "fp16x3", 1e-2, 2e-3)}
     trainers = {}
     for name, (conv, pam, _, _) in modes.items():
         import copy

@@ -195,8 +195,10 @@ def test_generator_forward_precision_scope():
             assert E.generator_forward_precision() == want
             with E.conv_precision_scope(E.generator_forward_precision()):
                 assert E.conv_precision == (want or mode)
-                assert not (want and E.bf16_storage_ok())          # the bf16-only operand shortcuts are off while the forward is recorded with split operands
-            assert E.conv_precision == mode
+                assert not (want and E.bf16_storage_ok())          # the bf16-only feature storage is off while the forward is recorded with split operands
+                assert E.backward_conv_precision() == mode          # ... and the backward closures will run under the outer mode
+                assert E.split_forward_in_product_mode() == (want is not None)
+            assert E.conv_precision == mode and E.backward_conv_precision() == mode and not E.split_forward_in_product_mode()
         E.set_conv_precision("bf16")
         try:
             with E.conv_precision_scope(E.generator_forward_precision()):
