@@ -297,7 +297,8 @@ def discriminator_forward_precision() -> Optional[str]:
 # bf16 operand rounding of the forward puts the generated field 9e-3 from the reference's (float64 run of generator.py:230-247), which is what moves
 # loss_D / loss_G by more than 1 % on a few of 200 teacher-forced steps (tools/trajectory_quantised_cpu.py shows the same with the reference's own
 # modules and bf16 operands: the format, not the kernels).  With split forward operands the field is 1.5e-4 away (the parity mode's forward) while
-# every gradient GEMM still reads single bf16 operands (the hi parts): 3x the MMA work on the 2.4 ms of generator forward convolutions only.
+# every gradient GEMM still reads single bf16 operands (the hi parts): 3x the MMA work on the 2.4 ms of generator forward convolutions only
+# (measured on B200, same box, graph replay: 54.98 vs 50.46 ms per step; the all-split parity mode: 91.6 ms).
 # Quantised-oracle prediction (oracle/quantised_oracle.py Formats.forward_x3): y 1.5e-4, dx 4.1e-2, parameter gradients 3.8e-2 (bf16 forward: 9.0e-3 /
 # 1.9e-1 / 1.8e-1 -- the sqrt law of DESIGN.md 4: no flipped ReLU masks, no wrong gradients).
 generator_forward_x3: bool = os.environ.get("GDN_G_FORWARD_X3", "0") == "1"
