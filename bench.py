@@ -7,6 +7,11 @@ AdamW updates) over one synthetic batch.  N = 1 runs BASELINE.json configs[1] (p
 => PAM over 8192 positions, output 256x512); N > 1 (torchrun, one rank per GPU, NCCL) is configs[2]: the same per-GPU
 batch with gradient all-reduce (weak scaling).  Rank 0 prints ONE JSON line.
 
+Precision of the timed step: bf16 tensor-core operands with fp32 accumulation; the FORWARD convolutions of the generator and of the
+discriminator on hi+lo split bf16 operands (--g-forward x3, the default: generator output 1.5e-4 from the reference's float64 run, losses within 1 %
+of the reference at every one of 200 teacher-forced steps -- tests/test_gpu_trajectory.py); fused PAM with fp16 hi+lo split logits.  --g-forward bf16
+is the all-bf16 step (8 % faster, misses the 1 % bar on ~1 % of the steps); every line carries it as other_modes.g_forward_bf16.
+
   value     : samples/s with the batch resident in HBM (CUDA events, barrier + synchronize on both sides, max over ranks)
   e2e       : same metric through the public trainer API with the step's inputs copied from pinned host memory and the
               two scalar losses read back inside the timed region

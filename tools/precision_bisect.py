@@ -55,7 +55,8 @@ if __name__ == "__main__":
     g = torch.load(os.path.join(ROOT, "tests", "golden", "generator_cin46_8x16.pt"), weights_only=False)
     cases = {
         "exact (must reproduce the golden)": Q.Formats.exact(),
-        "product mode: bf16 convs + fp16x3 PAM": Q.Formats(),
+        "all-bf16 product mode: bf16 convs + fp16x3 PAM": Q.Formats(),
+        "BENCHMARKED mode: forward convolutions on hi+lo split operands, gradient GEMMs on bf16 (engine.generator_forward_x3)": Q.Formats.forward_x3(),
         "product mode with single-fp16 logits (PAM 'fp16')": Q.Formats(pam_logits="fp16"),
         "what-if, not implemented: fp16 forward operands (conv x / w, PAM P / V), bf16 conv gradient operand": Q.Formats("fp16", "fp16", "bf16", "fp16", "fp16", "fp16", None),
         "conv operands only (x, w bf16; gradient operand exact)": Q.Formats("bf16", "bf16", None, None, None, None, None),
@@ -69,7 +70,7 @@ if __name__ == "__main__":
     for name, f in cases.items():
         res = summarise(g, *run(g, f))
         out[name] = res
-        print(f"{name:70s} y {res['y']:.2e}  dx {res['dx']:.2e}  grads {res['grads_whole_vector']:.2e}", flush=True)
+        print(f"{name:118s} y {res['y']:.2e}  dx {res['dx']:.2e}  grads {res['grads_whole_vector']:.2e}", flush=True)
     if "--layers" in sys.argv:
         # which layer group's bf16 operand rounding costs what: the product mode's formats on ONE group of convolutions, exact elsewhere
         groups = {"initial conv": lambda n: n == "initial", "dense-layer convs": lambda n: n.startswith("dense"), "PAM (projections + core)": lambda n: n.startswith("pam"),
