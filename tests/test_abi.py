@@ -103,3 +103,45 @@ def test_python_free_harness_builds():
     assert os.path.exists(exe)
     out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
     assert "libgandanet_sm100.so" in out and os.path.join(HERE, "libgandanet_sm100.so") in out      # resolved through the $ORIGIN rpath
+
+
+def test_product_never_touches_the_oracle_and_fails_loudly_without_the_library(tmp_path):
+    """The oracle is test infrastructure: no module of the product package imports, names a path into, or executes anything under oracle/
+    (only tests/, __graft_entry__.smoke() and bench.py's CPU arm may), and a missing library is an error, not a fallback."""
+    import ast
+    import pytest
+    from gan_danet_b200 import _lib
+    pkg = os.path.dirname(os.path.abspath(_lib.__file__))
+    offenders = []
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(root, f)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                for n in names:
+                    if n.split(".")[0] in ("oracle", "gan_danet_oracle", "quantised_oracle", "notebook_step", "postprocess_oracle", "build_ref", "make_golden"):
+                        offenders.append((f, n))
+                if isinstance(node, ast.Constant) and isinstance(node.value, str) and "oracle" in node.value and ("/" in node.value or node.value == "oracle"):
+                    # string constants naming an oracle PATH (docstrings and comments-as-strings mention oracle files by name: removed below)
+                    offenders.append((f, node.value[:60]))
+    docstrings = set()
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                for node in ast.walk(ast.parse(open(os.path.join(root, f)).read())):
+                    if isinstance(node, ast.Expr) and isinstance(node.value, ast.Constant) and isinstance(node.value.value, str):
+                        docstrings.add(node.value.value[:60])
+    offenders = [o for o in offenders if o[1] not in docstrings]
+    assert not offenders, offenders
+    with pytest.raises(_lib.GdnError, match="no CPU fallback"):
+        saved, _lib._lib = _lib._lib, None
+        try:
+            _lib.load(str(tmp_path / "libgandanet_sm100.so"))
+        finally:
+            _lib._lib = saved
