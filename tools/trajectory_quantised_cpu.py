@@ -53,6 +53,8 @@ vgg64 = {k: v.double() for k, v in vgg_sd.items()}
 d64 = lambda sd: {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}  # noqa: E731
 
 fmts = {"bf16 operands (product mode)": Q.Formats(),
+        # the benchmarked mode (engine.generator_forward_x3): forward convolutions on hi+lo split operands; what remains is the fused PAM's bf16 P / V
+        "split forward operands (benchmarked mode: conv x / w hi+lo, PAM P / V bf16)": Q.Formats.forward_x3(),
         # what-if (not implemented on the device): tcgen05 kind::f16 takes fp16 operands at the bf16 rate; activations and weights of this network fit fp16's range
         "fp16 forward operands (what-if: conv x / w and PAM P / V in fp16, gradient operands unchanged)": Q.Formats("fp16", "fp16", "bf16", "fp16", "fp16", "fp16", None),
         "exact (float64 re-evaluation: the float32 oracle's own noise)": Q.Formats.exact()}
