@@ -1,5 +1,5 @@
-"""The BENCHMARKED mode (conv precision 'bf16' on tcgen05, fused PAM 'fp16x3', bf16-only operand shortcuts enabled: exactly what bench.py
-runs) asserted end to end against the quantisation-aware oracle (oracle/quantised_oracle.py: the reference algorithm, generator.py:230-247,
+"""The all-bf16 product mode (conv precision 'bf16' on tcgen05, fused PAM 'fp16x3', bf16-only operand shortcuts enabled: `bench.py --g-forward bf16`,
+the benchmarked mode until the last session of round 2) asserted end to end against the quantisation-aware oracle (oracle/quantised_oracle.py: the reference algorithm, generator.py:230-247,
 with rounding hooks exactly where these kernels round, accumulated in float64) -- SURVEY 7.4-1.
 
 What the numbers mean:
@@ -16,6 +16,9 @@ What the numbers mean:
 * quantisation-aware oracle vs the reference's float64 golden: the cost of the operand formats themselves; REPORTED (and bounded loosely), it is not
   an implementation property: y 9.0e-3, dx 1.9e-1 on this 8x16-grid / batch-2 fixture (BatchNorm over 256 values) for bf16 operands of ANY
   implementation, the reference's own modules included (SURVEY 7.4 measured 9.2e-3 / 1.8e-2..3.8e-2 on a 32x64 grid, batch 4).
+
+The mode bench.py runs NOW (forward convolutions on hi+lo split operands: engine.generator_forward_x3) is the last test of this file: its output
+is bitwise the parity mode's (1.5e-4 from the reference) and its gradients are within 2.7e-2 of the reference's float64 run.
 """
 import json
 import os
