@@ -1,12 +1,15 @@
-"""Quantisation-aware CPU oracle of the generator for the tensor-core PRODUCT mode (conv precision 'bf16', PAM 'fp16x3').
+"""Quantisation-aware CPU oracle of the generator for the tensor-core PRODUCT modes: conv precision 'bf16' with PAM 'fp16x3' (``Formats()``: single
+bf16 operands everywhere) and the benchmarked variant of it whose FORWARD convolutions run on hi+lo split operands (``Formats.forward_x3()``:
+engine.generator_forward_x3; the gradient GEMMs read the bf16 hi parts of the saved operands).
 
 THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE (same rules as gan_danet_oracle.py: only tests/, smoke() and bench.py's CPU
 legs may import it).
 
 It is the reference algorithm (``gan_danet_oracle.generator_forward``, i.e. /root/reference/models/generator.py:230-247) with
 rounding hooks at EXACTLY the points where the product-mode kernels round, everything else accumulated in float64
-(SURVEY 7.4-1).  The CUDA path is asserted against this oracle at 1e-3; the oracle's own distance to the plain float64 run of
-the reference is the *reported* cost of the operand formats (tests/test_gpu_quantised.py, profiles/r02_precision_modes.json).
+(SURVEY 7.4-1).  The CUDA path is asserted against this oracle (tests/test_gpu_quantised.py: as close to it as the oracle is to its own float32
+evaluation for the all-bf16 mode; 1e-3 on the output for the split forward); the oracle's own distance to the plain float64 run of the reference is
+the *reported* cost of the operand formats (profiles/r02_precision_product_mode_*.json, r02_precision_benchmarked_mode_gx3.json).
 
 Rounding points of the product mode (gan_danet_b200/engine.py, csrc/conv_tc.cu, csrc/pam_tc.cu):
 
